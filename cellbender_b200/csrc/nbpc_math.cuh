@@ -1,0 +1,191 @@
+// fp32 device math for the NB (+) Poisson moment-matched likelihood and its gradients.
+//
+// Replaces the op chain of NegativeBinomialPoissonConvApprox.log_prob
+// (reference: cellbender/remove_background/distributions/NegativeBinomialPoissonConvApprox.py:105-143,
+//  formula :63-70) with ONE evaluation per element, kept in registers.
+//
+// The reference formula  L = lgamma(v+a) - lgamma(v+1) - lgamma(a) + a(log a - log(a+m)) + v(log m - log(a+m)),
+// a = alpha_hat = (m/mu)^2 alpha, m = mu + lam, cancels catastrophically in fp32 when a is large
+// (a reaches 1e10..1e25 whenever mu << lam; SURVEY.md finding 2).  We evaluate the SAME function
+// in cancellation-free form so that the fp32 result tracks an fp64 evaluation of the reference:
+//   w = m/a = mu^2/(m alpha)
+//   L(v=0)  = -a log1p(w) = -m log1p(w)/w
+//   L(v>0)  = T + L(0) + [v log m - lgamma(v+1)],   T = sum_{i<v} log1p((i-m)/(a+m))
+//             (= lgamma(v+a) - lgamma(a) - v log(a+m) exactly, for integer v)
+//   large v: T via a Stirling difference and the Poisson part in deviance form
+//             v phi(m/v - 1) - 0.5 log(2 pi v) - S(v),  phi(u) = log1p(u) - u.
+// Gradients, with A1 = a dL/da kept finite:
+//   dL/dm = a (v-m) / (m (a+m)) = (v-m)/(m (1+w))
+//   A1    = sum_{i<v} (m-i)/((a+i)(1+w)) + m h(w),   h(w) = 1/(1+w) - log1p(w)/w
+//   dL/dmu = dL/dm - 2 A1 lam/(m mu);  dL/dlam = dL/dm + 2 A1/m;  dL/dalpha = A1/alpha
+// Poisson branch (mu < 1e-5 lam): L = v log lam - lam - lgamma(v+1), dL/dlam = v/lam - 1, no grad to mu, alpha.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace cb {
+
+constexpr int kSmallCount = 16;  // counts <= this use exact integer recurrences
+
+// The math below is __host__ __device__ so that tests/test_host_math.py can run the very same
+// fp32 code on the CPU (no GPU in the build container) against the fp64 golden vectors.
+#define CB_HD __host__ __device__ __forceinline__
+
+// lgamma(v+1) = log(v!) for v = 0..16 (exact to fp32)
+#define CB_LOGFACT_TABLE                                                                                   \
+  {0.0f, 0.0f, 0.69314718056f, 1.79175946923f, 3.17805383035f, 4.78749174278f, 6.57925121201f,             \
+   8.52516136107f, 10.6046029027f, 12.8018274801f, 15.1044125730f, 17.5023078459f, 19.9872144957f,         \
+   22.5521638531f, 25.1912211827f, 27.8992713838f, 30.6718601061f}
+__device__ __constant__ float kLogFactDev[kSmallCount + 1] = CB_LOGFACT_TABLE;
+static const float kLogFactHost[kSmallCount + 1] = CB_LOGFACT_TABLE;
+CB_HD float log_fact(int v) {
+#ifdef __CUDA_ARCH__
+  return kLogFactDev[v];
+#else
+  return kLogFactHost[v];
+#endif
+}
+
+// phi(u) = log1p(u) - u, cancellation-free for small |u|
+CB_HD float phi_f(float u) {
+  if (fabsf(u) < 0.25f) {
+    // u^2 * (-1/2 + u/3 - u^2/4 + ... - u^10/12)
+    float p = -1.0f / 12.0f;
+    p = fmaf(p, u, 1.0f / 11.0f);
+    p = fmaf(p, u, -1.0f / 10.0f);
+    p = fmaf(p, u, 1.0f / 9.0f);
+    p = fmaf(p, u, -1.0f / 8.0f);
+    p = fmaf(p, u, 1.0f / 7.0f);
+    p = fmaf(p, u, -1.0f / 6.0f);
+    p = fmaf(p, u, 1.0f / 5.0f);
+    p = fmaf(p, u, -1.0f / 4.0f);
+    p = fmaf(p, u, 1.0f / 3.0f);
+    p = fmaf(p, u, -1.0f / 2.0f);
+    return u * u * p;
+  }
+  return log1pf(u) - u;
+}
+
+// log(num/den) for num, den > 0; cancellation-free near 1 and safe when num << den
+// (num_minus_den is passed separately so that it is not lost to rounding when den is huge)
+CB_HD float log_ratio(float num, float den, float num_minus_den) {
+  const float d = num_minus_den / den;
+  return (fabsf(d) < 0.25f) ? log1pf(d) : logf(num / den);
+}
+// phi(t - 1) = log t - t + 1 for t > 0
+CB_HD float phi_ratio(float t) { return (fabsf(t - 1.0f) < 0.25f) ? phi_f(t - 1.0f) : logf(t) - (t - 1.0f); }
+
+// q(w) = log1p(w)/w  (-> 1 as w -> 0), w >= 0
+CB_HD float log1p_over_x(float w) { return (w > 0.0f) ? log1pf(w) / w : 1.0f; }
+
+// h(w) = 1/(1+w) - log1p(w)/w = sum_{k>=1} (-w)^k k/(k+1)
+CB_HD float h_f(float w, float inv1pw, float q) {
+  if (w < 0.25f) {
+    float p = 11.0f / 12.0f;  // k = 11
+    p = fmaf(p, -w, 10.0f / 11.0f);
+    p = fmaf(p, -w, 9.0f / 10.0f);
+    p = fmaf(p, -w, 8.0f / 9.0f);
+    p = fmaf(p, -w, 7.0f / 8.0f);
+    p = fmaf(p, -w, 6.0f / 7.0f);
+    p = fmaf(p, -w, 5.0f / 6.0f);
+    p = fmaf(p, -w, 4.0f / 5.0f);
+    p = fmaf(p, -w, 3.0f / 4.0f);
+    p = fmaf(p, -w, 2.0f / 3.0f);
+    p = fmaf(p, -w, 1.0f / 2.0f);
+    return -w * p;
+  }
+  return inv1pw - q;
+}
+
+// Stirling remainder S(z) = 1/(12 z) - 1/(360 z^3) + 1/(1260 z^5),  lgamma(z) = (z-.5) log z - z + .5 log(2 pi) + S(z)
+CB_HD float stirling_S(float z) {
+  const float r = 1.0f / z, r2 = r * r;
+  return r * (1.0f / 12.0f + r2 * (-1.0f / 360.0f + r2 * (1.0f / 1260.0f)));
+}
+// S(z + d) - S(z), leading term in difference form (no cancellation when d << z)
+CB_HD float stirling_S_diff(float z, float d) {
+  const float z2 = z + d, r1 = 1.0f / z, r2 = 1.0f / z2;
+  const float hi1 = r1 * r1 * r1 * (-1.0f / 360.0f + r1 * r1 * (1.0f / 1260.0f));
+  const float hi2 = r2 * r2 * r2 * (-1.0f / 360.0f + r2 * r2 * (1.0f / 1260.0f));
+  return -(1.0f / 12.0f) * d * r1 * r2 + (hi2 - hi1);
+}
+// psi(z) = log z + P(z),  P(z) = -1/(2z) - 1/(12 z^2) + 1/(120 z^4) - 1/(252 z^6);  returns P(z + d) - P(z)
+CB_HD float digamma_P_diff(float z, float d) {
+  const float z2 = z + d, r1 = 1.0f / z, r2 = 1.0f / z2;
+  const float q1 = r1 * r1, q2 = r2 * r2;
+  const float hi1 = q1 * q1 * (1.0f / 120.0f - q1 * (1.0f / 252.0f));
+  const float hi2 = q2 * q2 * (1.0f / 120.0f - q2 * (1.0f / 252.0f));
+  return 0.5f * d * r1 * r2 + (1.0f / 12.0f) * d * (z + z2) * q1 * q2 + (hi2 - hi1);
+}
+
+// log Poisson pmf  v log(rate) - rate - lgamma(v+1), v a non-negative integer-valued float
+CB_HD float poisson_logpmf(float v, float rate) {
+  if (v == 0.0f) return -rate;
+  if (v <= float(kSmallCount)) return v * logf(rate) - rate - log_fact(int(v));
+  // deviance form: v phi(rate/v - 1) - 0.5 log(2 pi v) - S(v)
+  return v * phi_ratio(rate / v) - 0.5f * logf(6.283185307179586f * v) - stirling_S(v);
+}
+
+struct NbpcOut {
+  float L, dmu, dlam, dalpha;
+};
+
+// One element of NBPCapprox.log_prob (+ gradients when GRAD).  mu, alpha, lam > 0; v >= 0 integer-valued.
+template <bool GRAD>
+CB_HD NbpcOut nbpc_eval(float v, float mu, float alpha, float lam) {
+  NbpcOut o;
+  o.dmu = 0.f, o.dlam = 0.f, o.dalpha = 0.f;
+  if (mu < 1e-5f * lam) {  // reference: empty_indices = mu < 1e-5 * lam  -> Poisson(lam)
+    o.L = poisson_logpmf(v, lam);
+    if (GRAD) o.dlam = v / lam - 1.0f;
+    return o;
+  }
+  const float m = mu + lam;
+  const float w = (mu / m) * (mu / alpha);  // = m / alpha_hat
+  const float inv1pw = 1.0f / (1.0f + w);
+  const float q = log1p_over_x(w);
+  const float L0 = -m * q;  // = -a log1p(m/a)
+  float T = 0.f, S1 = 0.f;  // S1 = sum (m-i)/((a+i)(1+w))
+  if (v > 0.0f) {
+    const float a = fminf(m / w, 1e30f);  // alpha_hat (huge when mu << lam; clamp keeps inf*0 out)
+    const float apm = a + m;
+    int k;
+    float vr = 0.f;  // counts handled by the Stirling remainder
+    if (v <= float(kSmallCount)) {
+      k = int(v);
+    } else {
+      k = (a < 8.0f) ? 8 : 0;
+      vr = v - float(k);
+    }
+    for (int i = 0; i < k; ++i) {
+      const float fi = float(i);
+      T += log_ratio(a + fi, apm, fi - m);
+      if (GRAD) S1 += (m - fi) / ((a + fi) * (1.0f + w));
+    }
+    if (vr > 0.0f) {
+      // remaining counts: shift (a, m) -> (a + k, m - k); a' + m' = a + m
+      const float a2 = a + float(k), m2 = m - float(k);
+      const float u = vr / a2;
+      T += a2 * phi_f(u) - 0.5f * log1pf(u) + vr * log_ratio(a2 + vr, apm, vr - m2) + stirling_S_diff(a2, vr);
+      if (GRAD) {
+        // a * [psi(a2+vr) - psi(a2) - vr/(a+m)] = a * [phi(u) + u m2/(a+m) + P(a2+vr) - P(a2)]
+        S1 += a * (phi_f(u) + u * m2 / apm + digamma_P_diff(a2, vr));
+      }
+      o.L = T - a * phi_f(w) + poisson_logpmf(v, m);  // L0 + m = -a phi(w)
+    } else {
+      o.L = T + L0 + (v * logf(m) - log_fact(int(v)));
+    }
+  } else {
+    o.L = L0;
+  }
+  if (GRAD) {
+    const float dLdm = (v - m) / m * inv1pw;
+    const float A1 = S1 + m * h_f(w, inv1pw, q);
+    o.dmu = dLdm - 2.0f * A1 * (lam / m) / mu;
+    o.dlam = dLdm + 2.0f * A1 / m;
+    o.dalpha = A1 / alpha;
+  }
+  return o;
+}
+
+}  // namespace cb

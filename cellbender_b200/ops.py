@@ -1,0 +1,275 @@
+"""Torch-facing wrappers of the C-ABI kernels.  torch is plumbing here (device memory, streams);
+all compute is in ``libcellbender_b200.so``.  Every function requires CUDA tensors and raises if the
+extension is missing -- there is no CPU path in the product."""
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import current_stream, ptr
+from .exceptions import NanException
+
+
+def round_up(n: int, k: int) -> int:
+    return (n + k - 1) // k * k
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cellbender_b200 ops require CUDA tensors (no CPU fallback)")
+
+
+def alloc_rows(n_rows: int, n_cols: int, device, zero: bool = True) -> torch.Tensor:
+    """Row-major [n_rows, ld] fp32 with ld % 4 == 0; use ``[:, :n_cols]`` for the logical matrix."""
+    ld = round_up(n_cols, 4)
+    f = torch.zeros if zero else torch.empty
+    return f((n_rows, ld), dtype=torch.float32, device=device)
+
+
+@dataclass
+class DeviceCSR:
+    """Count matrix resident in HBM: indptr int64[R+1], indices int32[nnz] (sorted per row), data fp32[nnz]."""
+
+    indptr: torch.Tensor
+    indices: torch.Tensor
+    data: torch.Tensor
+    shape: Tuple[int, int]
+
+    @staticmethod
+    def from_scipy(mat, device) -> "DeviceCSR":
+        import scipy.sparse as sp
+
+        mat = sp.csr_matrix(mat)
+        mat.sum_duplicates()
+        mat.sort_indices()
+        return DeviceCSR(
+            torch.as_tensor(mat.indptr.astype(np.int64), device=device),
+            torch.as_tensor(mat.indices.astype(np.int32), device=device),
+            torch.as_tensor(mat.data.astype(np.float32), device=device),
+            (int(mat.shape[0]), int(mat.shape[1])),
+        )
+
+    @property
+    def n_genes(self) -> int:
+        return self.shape[1]
+
+
+def gather_rows(csr: DeviceCSR, row_ids: torch.Tensor, amb_unit: Optional[torch.Tensor] = None,
+                want: Sequence[str] = ("raw", "norm", "lognorm"), out: Optional[Dict[str, torch.Tensor]] = None):
+    """cb_csr_gather_rows.  Returns dict with the requested dense [B, ld] matrices and 'feats' [B, 4]
+    (sum, nnz, dot(x, amb_unit), max)."""
+    _req_cuda(csr.indptr, row_ids)
+    B, G = int(row_ids.numel()), csr.n_genes
+    dev = row_ids.device
+    out = {} if out is None else out
+    for k in want:
+        if k not in out:
+            out[k] = alloc_rows(B, G, dev, zero=False)
+    if "feats" not in out:
+        out["feats"] = torch.empty((B, 4), dtype=torch.float32, device=dev)
+    ld = round_up(G, 4)
+    _cabi.lib().call(
+        "cb_csr_gather_rows", ptr(csr.indptr), ptr(csr.indices), ptr(csr.data), ptr(row_ids), B, G, ld, ptr(amb_unit),
+        ptr(out.get("raw") if "raw" in want else None), ptr(out.get("norm") if "norm" in want else None),
+        ptr(out.get("lognorm") if "lognorm" in want else None), ptr(out["feats"]), current_stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# NBPCapprox.log_prob as a differentiable op (drop-in for the reference distribution's log_prob)
+# ------------------------------------------------------------------------------------------------------
+def _strides3(t: torch.Tensor, shape3):
+    """view `t` broadcast to the 3-D logical shape; broadcast dims get element stride 0"""
+    t3 = t.reshape((1,) * (3 - t.dim()) + tuple(t.shape)).expand(shape3)
+    return t3, tuple(t3.stride())
+
+
+def _as3(*ts):
+    shape = torch.broadcast_shapes(*[t.shape for t in ts])
+    if len(shape) > 3:
+        lead = int(np.prod(shape[:-2]))
+        shape3 = (lead, shape[-2], shape[-1])
+        ts = [t.expand(shape).reshape(shape3) for t in ts]  # may copy for exotic broadcasts
+    else:
+        shape3 = (1,) * (3 - len(shape)) + tuple(shape)
+    return shape, shape3, ts
+
+
+class _NbpcApproxLogProb(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, value, mu, alpha, lam):
+        _req_cuda(value, mu, alpha, lam)
+        args = [t.float() for t in (value, mu, alpha, lam)]
+        shape, shape3, args = _as3(*args)
+        packed = [_strides3(t, shape3) for t in args]
+        import ctypes
+
+        sarr = [(ctypes.c_longlong * 3)(*s) for _, s in packed]
+        out = torch.empty(shape3, dtype=torch.float32, device=value.device)
+        flag = torch.zeros(1, dtype=torch.int32, device=value.device)
+        E, B, G = shape3
+        _cabi.lib().call(
+            "cb_nbpc_approx_log_prob_fwd", ptr(packed[0][0]), ctypes.addressof(sarr[0]), ptr(packed[1][0]),
+            ctypes.addressof(sarr[1]), ptr(packed[2][0]), ctypes.addressof(sarr[2]), ptr(packed[3][0]),
+            ctypes.addressof(sarr[3]), ptr(out), E, B, G, ptr(flag), current_stream())
+        ctx.save_for_backward(*[p[0] for p in packed])
+        ctx.strides = [p[1] for p in packed]
+        ctx.shape, ctx.shape3 = shape, shape3
+        ctx.in_shapes = [t.shape for t in (value, mu, alpha, lam)]
+        ctx.nan_flag = flag
+        return out.reshape(shape)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        import ctypes
+
+        v3, m3, a3, l3 = ctx.saved_tensors
+        sarr = [(ctypes.c_longlong * 3)(*s) for s in ctx.strides]
+        E, B, G = ctx.shape3
+        go = grad_out.reshape(ctx.shape3).contiguous().float()
+        dmu, dlam, dal = (torch.empty(ctx.shape3, dtype=torch.float32, device=go.device) for _ in range(3))
+        _cabi.lib().call(
+            "cb_nbpc_approx_log_prob_bwd", ptr(v3), ctypes.addressof(sarr[0]), ptr(m3), ctypes.addressof(sarr[1]),
+            ptr(a3), ctypes.addressof(sarr[2]), ptr(l3), ctypes.addressof(sarr[3]), ptr(go), ptr(dmu), ptr(dlam),
+            ptr(dal), E, B, G, current_stream())
+
+        def red(g, shp):
+            return g.reshape(ctx.shape).sum_to_size(shp) if tuple(shp) != tuple(ctx.shape) else g.reshape(ctx.shape)
+
+        return None, red(dmu, ctx.in_shapes[1]), red(dal, ctx.in_shapes[2]), red(dlam, ctx.in_shapes[3])
+
+
+def nbpc_approx_log_prob(value, mu, alpha, lam, check_nan: bool = True):
+    """log_prob of NegativeBinomialPoissonConvApprox(mu, alpha, lam) at `value`, broadcasting like the
+    reference (...ConvApprox.py:105-143).  Raises NanException like the reference when a NaN appears."""
+    alpha = torch.as_tensor(alpha, dtype=torch.float32, device=mu.device)
+    out = _NbpcApproxLogProb.apply(value, mu, alpha, lam)
+    if check_nan and bool(torch.isnan(out.sum())):
+        bad = [n for n, t in (("mu", mu), ("alpha", alpha), ("lam", lam)) if bool(torch.isnan(t.log().sum()))]
+        raise NanException(param=", ".join(bad))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused ELBO observation terms
+# ------------------------------------------------------------------------------------------------------
+SUM_NAMES = ("L1", "L0", "LE", "dL1_da_mu1", "dL1_dcA1", "dL1_dcB1", "dL1_dalpha", "dL0_dcA0", "dL0_dcB0",
+             "dL0_dalpha", "dLE_dcAE", "dLE_dcBE")
+
+
+def elbo_obs(csr: DeviceCSR, row_ids, logits, chi_ambient, chi_bar, coef, alpha, w, *, out=None):
+    """cb_elbo_obs_fwd_bwd + cb_colsum_rows.  logits: [B, ld] buffer (ld % 4 == 0) holding G valid columns.
+    chi_ambient / chi_bar: fp32 [>= G] 16-byte aligned.  Returns dict(sums [B,12], dlogits [B,ld], dchi_ambient [G],
+    lse [B], nan_flag)."""
+    _req_cuda(logits, chi_ambient, chi_bar, coef, alpha, w, row_ids)
+    B, G = int(row_ids.numel()), csr.n_genes
+    ld = logits.stride(0)
+    assert logits.shape[0] == B and ld % 4 == 0 and ld >= G and logits.stride(1) == 1
+    dev = logits.device
+    out = {} if out is None else out
+    if "sums" not in out:
+        out["sums"] = torch.empty((B, 12), dtype=torch.float32, device=dev)
+    if "dlogits" not in out:
+        out["dlogits"] = torch.zeros((B, ld), dtype=torch.float32, device=dev)
+    if "qamb" not in out:
+        out["qamb"] = torch.empty((B, ld), dtype=torch.float32, device=dev)
+    if "dchi_ambient" not in out:
+        out["dchi_ambient"] = torch.empty(G, dtype=torch.float32, device=dev)
+    if "lse" not in out:
+        out["lse"] = torch.empty(B, dtype=torch.float32, device=dev)
+    if "nan_flag" not in out:
+        out["nan_flag"] = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = current_stream()
+    L = _cabi.lib()
+    L.call("cb_elbo_obs_fwd_bwd", ptr(csr.indptr), ptr(csr.indices), ptr(csr.data), ptr(row_ids), B, G, ptr(logits), ld,
+           ptr(chi_ambient), ptr(chi_bar), ptr(coef), ptr(alpha), ptr(w), ptr(out["sums"]), ptr(out["dlogits"]),
+           ptr(out["qamb"]), ld, ptr(out["lse"]), ptr(out["nan_flag"]), st)
+    L.call("cb_colsum_rows", ptr(out["qamb"]), B, G, ld, ptr(out["dchi_ambient"]), st)
+    return out
+
+
+def colsum_rows(mat: torch.Tensor, n_cols: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req_cuda(mat)
+    out = torch.empty(n_cols, dtype=torch.float32, device=mat.device) if out is None else out
+    _cabi.lib().call("cb_colsum_rows", ptr(mat), mat.shape[0], n_cols, mat.stride(0), ptr(out), current_stream())
+    return out
+
+
+def row_logsumexp(mat: torch.Tensor, n_cols: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req_cuda(mat)
+    out = torch.empty(mat.shape[0], dtype=torch.float32, device=mat.device) if out is None else out
+    _cabi.lib().call("cb_row_logsumexp", ptr(mat), mat.shape[0], n_cols, mat.stride(0), ptr(out), current_stream())
+    return out
+
+
+def clipped_adam_step(p, g, m, v, lr_table, beta1_table, step, beta2=0.999, eps=1e-8, clip=10.0, grad_scale=1.0):
+    """cb_clipped_adam_step over flat fp32 buffers; `step` is a device int64[1] counter (incremented)."""
+    _req_cuda(p, g, m, v, lr_table, beta1_table, step)
+    _cabi.lib().call("cb_clipped_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), ptr(lr_table), ptr(beta1_table),
+                     lr_table.numel(), ptr(step), float(beta2), float(eps), float(clip), float(grad_scale),
+                     current_stream())
+
+
+def exclusive_scan_i32(x: torch.Tensor):
+    """Exclusive prefix sum int32 -> int64 positions; returns (positions, total as 0-dim device tensor)."""
+    _req_cuda(x)
+    n = x.numel()
+    L = _cabi.lib()
+    out = torch.empty(n, dtype=torch.int64, device=x.device)
+    scratch = torch.empty(int(L.raw("cb_scan_scratch_elems")(n)), dtype=torch.int64, device=x.device)
+    total = torch.zeros(1, dtype=torch.int64, device=x.device)
+    L.call("cb_exclusive_scan_i32", ptr(x), n, ptr(out), ptr(scratch), ptr(total), current_stream())
+    return out, total
+
+
+# ------------------------------------------------------------------------------------------------------
+# posterior noise-count COO
+# ------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def posterior_coo(csr: DeviceCSR, cell_rows, logits, lse, chi_ambient, chi_bar, a_mu, c_a, c_b, alpha, n_window,
+                  barcode_all, gene_all, total_n_genes: int, n_counts_max: int = 20, log_thresh: float = -10.0,
+                  lambda_multiplier: float = 1.0):
+    """Noise-count posterior of the stored counts of `cell_rows`, as sorted COO arrays on the device.
+
+    logits [S*Bc, ld] / lse [S*Bc] hold the decoder output of every latent sample (row = s*Bc + b);
+    a_mu, c_a, c_b [S*Bc], alpha [S] the per-sample rate coefficients; n_window [Bc] int32;
+    barcode_all [Bc] / gene_all [G] int64 map to indices of the full count matrix.
+    Returns (m int64, c int32, log_prob fp32, off_m int64, off_v int32)."""
+    _req_cuda(cell_rows, logits, lse, a_mu, c_a, c_b, alpha, n_window, barcode_all, gene_all)
+    L = _cabi.lib()
+    st = current_stream()
+    dev = logits.device
+    Bc, G = int(cell_rows.numel()), csr.n_genes
+    S = int(alpha.numel())
+    assert logits.shape[0] == S * Bc and logits.stride(1) == 1
+    nnz_per_cell = (csr.indptr[cell_rows + 1] - csr.indptr[cell_rows])
+    entry_start = torch.zeros(Bc + 1, dtype=torch.int64, device=dev)
+    entry_start[1:] = torch.cumsum(nnz_per_cell, 0)
+    n_entries = int(entry_start[-1].item())
+    stride = int(L.raw("cb_posterior_window_stride")(int(n_counts_max)))
+    logp = torch.empty((max(n_entries, 1), stride), dtype=torch.float32, device=dev)
+    low = torch.empty(max(n_entries, 1), dtype=torch.int32, device=dev)
+    keep = torch.empty(max(n_entries, 1), dtype=torch.int32, device=dev)
+    entry_m = torch.empty(max(n_entries, 1), dtype=torch.int64, device=dev)
+    L.call("cb_posterior_noise_window", ptr(csr.indptr), ptr(csr.indices), ptr(csr.data), ptr(cell_rows), Bc, G, S,
+           ptr(logits), logits.stride(0), ptr(lse), ptr(chi_ambient), ptr(chi_bar), ptr(a_mu), ptr(c_a), ptr(c_b),
+           ptr(alpha), ptr(n_window), ptr(entry_start), int(n_counts_max), float(log_thresh), float(lambda_multiplier),
+           ptr(logp), ptr(low), ptr(keep), st)
+    L.call("cb_posterior_entry_index", ptr(csr.indptr), ptr(csr.indices), ptr(cell_rows), Bc, ptr(barcode_all),
+           ptr(gene_all), int(total_n_genes), ptr(entry_start), ptr(entry_m), st)
+    keep = keep[:n_entries]
+    keep_pos, keep_total = exclusive_scan_i32(keep)
+    has_off = ((keep > 0) & (low[:n_entries] != 0)).to(torch.int32)
+    off_pos, off_total = exclusive_scan_i32(has_off)
+    n_keep, n_off = int(keep_total.item()), int(off_total.item())
+    coo_m = torch.empty(n_keep, dtype=torch.int64, device=dev)
+    coo_c = torch.empty(n_keep, dtype=torch.int32, device=dev)
+    coo_lp = torch.empty(n_keep, dtype=torch.float32, device=dev)
+    off_m = torch.empty(n_off, dtype=torch.int64, device=dev)
+    off_v = torch.empty(n_off, dtype=torch.int32, device=dev)
+    L.call("cb_posterior_compact", n_entries, int(n_counts_max), ptr(entry_m), ptr(logp), ptr(low), ptr(keep),
+           ptr(keep_pos), ptr(off_pos), float(log_thresh), ptr(coo_m), ptr(coo_c), ptr(coo_lp), ptr(off_m), ptr(off_v), st)
+    return coo_m, coo_c, coo_lp, off_m, off_v

@@ -1,0 +1,140 @@
+/* cellbender_b200 -- C ABI of the B200-native (sm_100a) hot path of CellBender `remove-background`.
+ *
+ * The reference (broadinstitute/CellBender, pure Python/PyTorch/Pyro) has no FFI: its boundary is a set of
+ * Python call sites.  Every entry point below names the reference call site it
+ * replaces (paths relative to /root/reference/cellbender/remove_background/).  INTEGRATION.md shows the
+ * ctypes stub a maintainer would add at each site.
+ *
+ * Conventions
+ *   - plain C: device pointers + sizes, no torch types.  Every pointer is a DEVICE pointer unless its
+ *     name ends in _h.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - all calls are asynchronous on `stream`; the caller owns every buffer (allocate through any allocator).
+ *   - return value: 0 = launched OK; non-zero = error, message in cb_last_error() (thread-local).
+ *   - dense matrices are row-major fp32 with a leading dimension `ld` that is a multiple of 4 (16-byte rows).
+ *   - CSR count matrices: indptr int64[R+1], indices int32[nnz] (sorted, unique per row), data fp32[nnz].
+ *   - "m" indices (flattened count-matrix index n * G_all + g) are int64 (posterior.py:1554-1575).
+ */
+#ifndef CELLBENDER_B200_H_
+#define CELLBENDER_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int cb_abi_version(void);
+const char* cb_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * A1/A2  minibatch loader.  Replaces DataLoader.__next__ + sparse_collate (data/dataprep.py:153-193,
+ * 275-292), transform_input (vae/encoder.py:343-381) and the count features of
+ * EncodeNonZLatents.forward (vae/encoder.py:250-272).
+ *   row_ids[n_rows]   rows of the device-resident CSR chosen by the host RNG (np.random order preserved)
+ *   amb_unit[G]       unit-L2-norm ambient profile (encoder.py:266-270), may be NULL
+ *   x_raw/x_norm/x_lognorm [n_rows, ld]   counts, x/(sum+1e-5), log1p(x/(sum+1e-5)); any may be NULL
+ *   row_feats[n_rows, 4]                  sum(x), #(x>0), dot(x, amb_unit), max(x); may be NULL          */
+int cb_csr_gather_rows(const long long* indptr, const int* indices, const float* data, const long long* row_ids,
+                       int n_rows, int n_genes, long long ld, const float* amb_unit, float* x_raw, float* x_norm,
+                       float* x_lognorm, float* row_feats, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * A7  NegativeBinomialPoissonConvApprox.log_prob(value)  (distributions/NegativeBinomialPoissonConvApprox.py:105-143)
+ * and its backward.  Logical shape [E, B, G]; s* are element strides {e, b, g} of each operand (0 = broadcast),
+ * i.e. value [B,G], mu/lam [2,B,G] and a scalar alpha as pyro's enumeration produces them (model.py:338-346).
+ * nan_flag: int32 on device, OR-ed with 1 if any output is NaN (the host raises NanException, ...Approx.py:129-141). */
+int cb_nbpc_approx_log_prob_fwd(const float* value, const long long* sv, const float* mu, const long long* sm,
+                                const float* alpha, const long long* sa, const float* lam, const long long* sl,
+                                float* out, int E, int B, int G, int* nan_flag, void* stream);
+int cb_nbpc_approx_log_prob_bwd(const float* value, const long long* sv, const float* mu, const long long* sm,
+                                const float* alpha, const long long* sa, const float* lam, const long long* sl,
+                                const float* grad_out, float* dmu, float* dlam, float* dalpha, int E, int B, int G,
+                                void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * A5(softmax)+A6+A7+K7  observation terms of the ELBO, forward and backward fused.  Replaces, per svi.step:
+ * Decoder softmax (vae/decoder.py:46-47), calculate_mu/calculate_lambda with y enumerated (model.py:25-85,308-320),
+ * NBPCapprox(...).to_event(1).log_prob(x) (model.py:338-346), the Poisson "obs_empty" site (model.py:374-398) and
+ * their autograd backward.
+ *   coef[n_rows, 7]   a_mu1, cA1, cB1, cA0, cB0, cAE, cBE:  mu_y1 = a_mu1*chi + 1e-10, mu_y0 = 1e-10,
+ *                     lam_* = cA* * chi_ambient + cB* * chi_bar + 1e-10
+ *   alpha[1]          1/phi + 1e-10 (model.py:334,341)
+ *   w[n_rows, 3]      d loss / d (L_y1, L_y0, L_E)
+ *   sums[n_rows, 12]  L_y1, L_y0, L_E, dL1/da_mu1, dL1/dcA1, dL1/dcB1, dL1/dalpha, dL0/dcA0, dL0/dcB0, dL0/dalpha,
+ *                     dLE/dcAE, dLE/dcBE
+ *   dlogits[n_rows, ldl]  d loss / d logits;   qamb[n_rows, ldq]  per-row d loss / d chi_ambient (sum rows with
+ *                     cb_colsum_rows);   lse_out[n_rows] row logsumexp of logits (may be NULL)                 */
+int cb_elbo_obs_fwd_bwd(const long long* indptr, const int* indices, const float* data, const long long* row_ids,
+                        int n_rows, int n_genes, const float* logits, long long ldl, const float* chi_ambient,
+                        const float* chi_bar, const float* coef, const float* alpha, const float* w, float* sums,
+                        float* dlogits, float* qamb, long long ldq, float* lse_out, int* nan_flag, void* stream);
+int cb_colsum_rows(const float* in, int n_rows, int n_cols, long long ld, float* out, void* stream);
+int cb_row_logsumexp(const float* in, int n_rows, int n_cols, long long ld, float* lse, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K8  fused ClippedAdam + OneCycleLR over one flat buffer.  Replaces get_optimizer (run.py:593-629) and the
+ * per-parameter optimizer/scheduler steps at train.py:56-60.  lr_table/beta1_table[table_len] hold torch
+ * OneCycleLR's per-step values; *step_ptr (device int64) counts completed steps and is incremented here.       */
+int cb_clipped_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
+                         const float* beta1_table, long long table_len, long long* step_ptr, float beta2, float eps,
+                         float clip, float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * A10-A12  posterior noise-count log-probability over the stored (non-zero) counts.  Replaces
+ * Posterior._log_prob_noise_count_tensor (posterior.py:784-859), the normalisation and running log-mean of
+ * noise_log_pdf (posterior.py:698-735) and the thresholding/sparsify/index translation of
+ * _get_cell_noise_count_posterior_coo (posterior.py:528-576), dense_to_sparse_op_torch (sparse_utils.py:10-33),
+ * IndexConverter.get_m_indices (posterior.py:1554-1575).
+ *   cell_rows[n_cells]     CSR rows of the cells (p > 0.5) of this chunk
+ *   logits[n_samples*n_cells, ldl], lse[n_samples*n_cells]   decoder output per latent sample (row = s*n_cells + b)
+ *   a_mu/c_a/c_b [n_samples*n_cells], alpha[n_samples]   mu = a_mu*chi, lam = c_a*chi_ambient + c_b*chi_bar
+ *   n_window[n_cells]      n = min(n_counts_max, max count of the cell's reference minibatch) (posterior.py:816)
+ *   entry_start[n_cells+1] exclusive prefix of the cells' stored-count numbers
+ *   logp_out[n_entries, stride], low_out[n_entries], keep_cnt[n_entries]; stride = cb_posterior_window_stride() */
+int cb_posterior_window_stride(int n_counts_max);
+int cb_posterior_noise_window(const long long* indptr, const int* indices, const float* data, const long long* cell_rows,
+                              int n_cells, int n_genes, int n_samples, const float* logits, long long ldl,
+                              const float* lse, const float* chi_ambient, const float* chi_bar, const float* a_mu,
+                              const float* c_a, const float* c_b, const float* alpha, const int* n_window,
+                              const long long* entry_start, int n_counts_max, float log_thresh, float lambda_multiplier,
+                              float* logp_out, int* low_out, int* keep_cnt, void* stream);
+int cb_posterior_entry_index(const long long* indptr, const int* indices, const long long* cell_rows, int n_cells,
+                             const long long* barcode_all, const long long* gene_all, long long total_n_genes,
+                             const long long* entry_start, long long* entry_m, void* stream);
+int cb_posterior_compact(long long n_entries, int n_counts_max, const long long* entry_m, const float* logp,
+                         const int* low, const int* keep_cnt, const long long* keep_pos, const long long* off_pos,
+                         float log_thresh, long long* coo_m, int* coo_c, float* coo_lp, long long* off_m, int* off_v,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * A13-A15  estimators over the (m, c)-sorted posterior COO.  Replace apply_function_dense_chunks
+ * (estimation.py:747-793), MAP/Mean/ThresholdCDF/SingleSample (estimation.py:89-204),
+ * _estimation_array_to_csr (estimation.py:207-235) and MultipleChoiceKnapsack._chunk_estimate_noise
+ * (estimation.py:552-702).  mode: 0 MAP, 1 Mean, 2 ThresholdCDF(q), 3 SingleSample(seed).
+ * off_m/off_v[n_off]: noise offsets sorted by m (the reference's Dict[int,int]).                              */
+long long cb_scan_scratch_elems(long long n);
+int cb_exclusive_scan_i32(const int* in, long long n, long long* out, long long* scratch, long long* total_out,
+                          void* stream);
+int cb_segment_heads(const long long* m, const int* c, long long n, int* head, int* unsorted_flag, void* stream);
+int cb_segment_starts(const int* head, const long long* pos, long long n, long long* seg_start, int* seg_of,
+                      void* stream);
+int cb_segment_estimate(int mode, const long long* m, const int* c, const float* lp, const long long* seg_start,
+                        long long n_seg, long long n_entries, const long long* off_m, const int* off_v, long long n_off,
+                        double q, int n_cols, unsigned long long seed, long long* seg_m, int* out_i, float* out_f,
+                        long long* map_pos, void* stream);
+int cb_csr_from_segments(const long long* seg_m, long long n_seg, long long n_rows, long long n_cols, long long* indptr,
+                         int* col, void* stream);
+int cb_mckp_gene_deficit(const long long* seg_m, const int* map_val, long long n_seg, const double* target,
+                         long long n_genes, long long* gene_sum, long long* deficit, void* stream);
+int cb_mckp_candidates(const long long* m, const int* c, const float* lp, const int* seg_of, const long long* map_pos,
+                       const long long* deficit, long long n_entries, long long n_genes, int* is_cand,
+                       unsigned long long* key, void* stream);
+int cb_mckp_compact(const int* is_cand, const long long* pos, const unsigned long long* key, long long n_entries,
+                    unsigned long long* cand_key, long long* cand_idx, void* stream);
+int cb_mckp_select(const unsigned long long* sorted_key, const long long* sorted_idx, long long n_cand,
+                   const long long* deficit, const int* seg_of, int* steps, void* stream);
+int cb_mckp_finalize(const long long* seg_m, const int* map_val, const int* steps, const long long* deficit,
+                     long long n_seg, long long n_genes, int* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CELLBENDER_B200_H_ */

@@ -108,3 +108,75 @@ def get_p_logit_prior(log_counts, log_cell_prior_counts, surely_empty_counts, na
     out = torch.where(log_counts <= thresh, ones * -100.0, out)
     out = torch.where(log_counts >= log_cell_prior_counts, ones * 10.0, out)
     return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# Multiprecision truth (small cases only).  The reference formula cancels catastrophically even in
+# float64 when alpha_hat = (m/mu)^2 alpha is large (errors up to 1e-3 absolute, gradients pure noise:
+# see tests/golden/nbpc.npz 'approx_f64' vs 'approx_mp'), so the CUDA kernels are judged against an
+# 60-digit evaluation of the SAME formula and of its analytic derivatives.
+# ----------------------------------------------------------------------------------------------------
+def nbpc_approx_mp(value, mu, alpha, lam, dps: int = 60):
+    """Elementwise (numpy arrays, broadcast beforehand) -> (L, dL/dmu, dL/dlam, dL/dalpha) as float64.
+    The Poisson-branch test ``mu < 1e-5 * lam`` is evaluated in float32, as the product evaluates it."""
+    import mpmath as mp
+    import numpy as np
+
+    value, mu, alpha, lam = np.broadcast_arrays(*(np.asarray(a, dtype=np.float64) for a in (value, mu, alpha, lam)))
+    shape = value.shape
+    value, mu, alpha, lam = (a.ravel() for a in (value, mu, alpha, lam))
+    L, dmu, dlam, dal = (np.zeros(value.size) for _ in range(4))
+    with mp.workdps(dps):
+        for i in range(value.size):
+            v, m_, a_, l_ = mp.mpf(value[i]), mp.mpf(mu[i]), mp.mpf(alpha[i]), mp.mpf(lam[i])
+            if np.float32(mu[i]) < np.float32(1e-5) * np.float32(lam[i]):
+                L[i] = float(v * mp.log(l_) - l_ - mp.loggamma(v + 1))
+                dlam[i] = float(v / l_ - 1)
+                continue
+            mh = m_ + l_
+            ah = mh ** 2 * a_ / m_ ** 2
+            L[i] = float(mp.loggamma(v + ah) - mp.loggamma(v + 1) - mp.loggamma(ah)
+                         + ah * (mp.log(ah) - mp.log(ah + mh)) + v * (mp.log(mh) - mp.log(ah + mh)))
+            dLda = mp.digamma(v + ah) - mp.digamma(ah) + mp.log(ah / (ah + mh)) + (mh - v) / (ah + mh)
+            dLdm = v / mh - (ah + v) / (ah + mh)
+            dmu[i] = float(dLdm + dLda * (-2 * ah * l_ / (mh * m_)))
+            dlam[i] = float(dLdm + dLda * (2 * ah / mh))
+            dal[i] = float(dLda * ah / a_)
+    return L.reshape(shape), dmu.reshape(shape), dlam.reshape(shape), dal.reshape(shape)
+
+
+def elbo_obs_oracle(x, logits, chi_ambient, chi_bar, coef, alpha, w):
+    """Truth for the fused observation-term kernel (cb_elbo_obs_fwd_bwd): numpy float64 + multiprecision
+    likelihood.  x [B,G] dense counts; coef [B,7] = a_mu1, cA1, cB1, cA0, cB0, cAE, cBE; w [B,3].
+    Rates as in model.py:49-54,78-80,338-346,385-397 written in factored form.  Returns a dict with the same
+    fields as the kernel: sums [B,12], dlogits [B,G], dchi_ambient [G], lse [B]."""
+    import numpy as np
+
+    x, logits, chi_ambient, chi_bar, coef, w = (np.asarray(a, dtype=np.float64) for a in
+                                                (x, logits, chi_ambient, chi_bar, coef, w))
+    alpha = float(alpha)
+    mx = logits.max(-1, keepdims=True)
+    lse = (mx + np.log(np.exp(logits - mx).sum(-1, keepdims=True)))
+    chi = np.exp(logits - lse)
+    a_mu1, cA1, cB1, cA0, cB0, cAE, cBE = (coef[:, i:i + 1] for i in range(7))
+    mu1 = a_mu1 * chi + 1e-10
+    lam1 = cA1 * chi_ambient + cB1 * chi_bar + 1e-10
+    lam0 = cA0 * chi_ambient + cB0 * chi_bar + 1e-10
+    lamE = cAE * chi_ambient + cBE * chi_bar + 1e-10
+    # the product computes rates in fp32: evaluate the truth at the fp32-rounded rates' float64 values? No --
+    # the truth uses exact float64 rates; rate rounding is part of the kernel's error budget.
+    L1, dmu1, dlam1, dal1 = nbpc_approx_mp(x, mu1, alpha, lam1)
+    L0, _, dlam0, dal0 = nbpc_approx_mp(x, np.full_like(mu1, 1e-10), alpha, lam0)
+    from scipy.special import gammaln
+
+    LE = x * np.log(lamE) - lamE - gammaln(x + 1)
+    dE = x / lamE - 1.0
+    sums = np.stack([
+        L1.sum(-1), L0.sum(-1), LE.sum(-1), (dmu1 * chi).sum(-1), (dlam1 * chi_ambient).sum(-1),
+        (dlam1 * chi_bar).sum(-1), dal1.sum(-1), (dlam0 * chi_ambient).sum(-1), (dlam0 * chi_bar).sum(-1),
+        dal0.sum(-1), (dE * chi_ambient).sum(-1), (dE * chi_bar).sum(-1)], axis=1)
+    w1, w0, wE = (w[:, i:i + 1] for i in range(3))
+    gchi = w1 * a_mu1 * dmu1
+    dlogits = chi * (gchi - (gchi * chi).sum(-1, keepdims=True))
+    dchi_amb = (w1 * cA1 * dlam1 + w0 * cA0 * dlam0 + wE * cAE * dE).sum(0)
+    return {"sums": sums, "dlogits": dlogits, "dchi_ambient": dchi_amb, "lse": lse[:, 0]}

@@ -1,0 +1,47 @@
+"""The C-ABI library loads and exports every symbol include/cellbender_b200.h declares (no compute calls)."""
+import os
+import subprocess
+
+import pytest
+
+from cellbender_b200 import _cabi, build
+
+
+@pytest.fixture(scope="module")
+def built():
+    build.build()
+    return _cabi.lib()
+
+
+def test_library_exports_every_declared_symbol(built):
+    protos = _cabi.parse_header()
+    assert len(protos) >= 24
+    out = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    missing = [n for n in protos if n not in exported]
+    assert not missing, f"declared in the header but not exported: {missing}"
+
+
+def test_abi_version_and_error_string(built):
+    assert built.raw("cb_abi_version")() == 1
+    assert isinstance(built.last_error(), str)
+
+
+def test_sass_is_sm100a():
+    out = subprocess.run(["cuobjdump", "-lelf", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_cabi.CabiError):
+        _cabi._Lib()
+
+
+def test_ops_refuse_cpu_tensors(built):
+    import torch
+
+    from cellbender_b200 import ops
+
+    with pytest.raises(RuntimeError):
+        ops.row_logsumexp(torch.zeros(2, 4), 4)

@@ -1,0 +1,75 @@
+"""Numerics of the kernels' fp32 device math, run on the CPU: the math headers are __host__ __device__, so the
+very same source is compiled for the host (tools/host_math_check.cu) and compared with the multiprecision /
+float64 truth.  This is how kernel numerics are iterated on in the GPU-less build container; the -m gpu tests
+repeat the comparison through the real kernels."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import posterior as opost
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def hostlib(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("hostmath") / "hostmath.so")
+    subprocess.run(["nvcc", "-O2", "-shared", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets", "-o", so,
+                    os.path.join(ROOT, "tools", "host_math_check.cu")], check=True)
+    return ctypes.CDLL(so)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_nbpc_fp32_math_vs_multiprecision(hostlib, golden_dir):
+    g = np.load(os.path.join(golden_dir, "nbpc.npz"))
+    v, mu, al, lam = (np.ascontiguousarray(g[k], dtype=np.float32) for k in ("value", "mu", "alpha", "lam"))
+    n = v.size
+    L, dmu, dlam, dal = (np.zeros(n, np.float32) for _ in range(4))
+    hostlib.host_nbpc_eval(n, _p(v), _p(mu), _p(al), _p(lam), _p(L), _p(dmu), _p(dlam), _p(dal))
+    ref = g["approx_mp"]
+    err = np.abs(L - ref) / np.maximum(np.abs(ref), 1.0)
+    small = v <= 64
+    # tolerance of north_star: 1e-5 relative (to max(|L|,1)); counts in the hundreds get 3e-5
+    assert err[small].max() < 1e-5, err[small].max()
+    assert err.max() < 3e-5, err.max()
+    # the reference's own fp32 evaluation is far worse on the same inputs (context for the tolerance)
+    ref32 = np.abs(g["approx_f32"] - ref) / np.maximum(np.abs(ref), 1.0)
+    assert np.nanmax(ref32) > 1e-2
+    for name, mine in (("dmu", dmu), ("dlam", dlam), ("dalpha", dal)):
+        r = g[f"approx_{name}_mp"]
+        e = np.abs(mine - r) / np.maximum(np.abs(r), 1e-3)
+        assert e.max() < 1e-3, (name, e.max())
+        assert np.mean(e > 1e-4) < 0.01, (name, np.mean(e > 1e-4))
+
+
+@pytest.mark.parametrize("tag", ["big", "small", "huge"])
+def test_noise_window_fp32_math_vs_float64(hostlib, golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "posterior_logprob.npz"))
+    data, mu, lam, alpha = (g[f"{tag}_{k}"] for k in ("data", "mu", "lam", "alpha"))
+    d32, m32, l32, a32 = (np.asarray(a, np.float32) for a in (data, mu + 1e-30, lam + 1e-30, alpha + 1e-30))
+    lp, low = opost.log_prob_noise_count_tensor(
+        torch.tensor(d32, dtype=torch.float64), torch.tensor(m32, dtype=torch.float64),
+        torch.tensor(l32, dtype=torch.float64), torch.tensor(float(a32), dtype=torch.float64), n_counts_max=20,
+        mimic_float_casts=False)
+    lpn = (lp - torch.logsumexp(lp, -1, keepdim=True)).numpy()
+    n = lp.shape[-1]
+    nz = np.nonzero(d32 > 0)
+    x, m_, l_ = (np.ascontiguousarray(a[nz]) for a in (d32, m32, l32))
+    a_ = np.full(x.size, a32, np.float32)
+    prob = np.zeros((x.size, 32), np.float32)
+    lo = np.zeros(x.size, np.int32)
+    hostlib.host_noise_window_pmf(x.size, _p(x), _p(m_), _p(l_), _p(a_), n, _p(prob), _p(lo))
+    np.testing.assert_array_equal(lo, low.numpy()[nz].astype(np.int32))
+    ref = lpn[nz]
+    with np.errstate(divide="ignore"):
+        mine = np.log(prob[:, :n])
+    keep = ref >= -10.0  # the posterior keeps log prob >= -10 (posterior.py:426,533)
+    err = np.abs(mine - ref)[keep] / np.maximum(np.abs(ref[keep]), 1.0)
+    assert err.max() < 1e-5, err.max()

@@ -54,7 +54,10 @@ def golden_nbpc():
     value = torch.poisson((mu + lam).clamp(max=500.0), generator=g)
     value[torch.rand(n, generator=g) < 0.5] = 0.0
     value[-8:] = torch.tensor([1, 2, 3, 50, 100, 200, 400, 600], dtype=torch.float64)
+    # inputs are made exactly fp32-representable so fp32 / fp64 / multiprecision all see the same numbers
+    mu, lam, alpha, value = (t.float().double() for t in (mu, lam, alpha, value))
     out = {}
+    out.update(_nbpc_multiprecision(mu.numpy(), alpha.numpy(), lam.numpy(), value.numpy()))
     for name, dt in (("f64", torch.float64), ("f32", torch.float32)):
         m_, a_, l_, v_ = (t.to(dt).clone() for t in (mu, alpha, lam, value))
         m_.requires_grad_(True), a_.requires_grad_(True), l_.requires_grad_(True)
@@ -71,6 +74,15 @@ def golden_nbpc():
     out["exact_f64"] = lpx.numpy()
     np.savez_compressed(os.path.join(OUT, "nbpc.npz"), mu=mu.numpy(), alpha=alpha.numpy(), lam=lam.numpy(),
                         value=value.numpy(), **out)
+
+
+def _nbpc_multiprecision(mu, alpha, lam, value):
+    """Multiprecision (mpmath) evaluation of the reference formula ...ConvApprox.py:63-70,117-127 and of its
+    analytic derivatives; see oracle/nbpc.py:nbpc_approx_mp."""
+    from oracle.nbpc import nbpc_approx_mp
+
+    L, dmu, dlam, dal = nbpc_approx_mp(value, mu, alpha, lam, dps=80)
+    return {"approx_mp": L, "approx_dmu_mp": dmu, "approx_dlam_mp": dlam, "approx_dalpha_mp": dal}
 
 
 def golden_rates():
