@@ -1,0 +1,372 @@
+"""The remove-background model: the same object the reference builds (class name, constructor signature,
+attributes: reference cellbender/remove_background/model.py:88-230), with the pyro ``model``/``guide`` pair
+replaced by an explicit, pyro-free ELBO program whose heavy terms run in the B200 kernels.
+
+Why pyro-free: pyro-ppl is not part of this image (SURVEY.md finding 1) and its per-step Python (two traces,
+enumeration, ~40 optimizer objects) is itself slower than the whole B200 step.  The ELBO computed here is the
+one ``TraceEnum_ELBO(max_plate_nesting=1)`` computes for ``model``/``guide`` with ``y`` enumerated in the guide
+(restated from model.py:232-574); because no reference test pins an ELBO value and pyro
+is absent, PARITY OF THE ELBO IS UNPINNED against pyro itself -- it is pinned against the oracle restatement
+(oracle/elbo.py), term by term.
+
+Parameter handling mirrors pyro's param store: every ``pyro.param`` site is an UNCONSTRAINED nn.Parameter plus a
+``torch.distributions.transform_to(constraint)`` (exp / sigmoid-interval / stick-breaking), which is what pyro
+optimises (model.py:245-249, 468-513).
+"""
+import math
+from typing import Any, Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.distributions import Beta, Gamma, LogNormal, Normal, constraints, transform_to
+
+from . import consts, ops
+from .exceptions import NanException
+from .vae import CompositeEncoder, EncoderInputs
+
+
+def calculate_lambda(model_type: str, epsilon, chi_ambient, d_empty, y=None, d_cell=None, rho=None, chi_bar=None):
+    """Noise rate (reference model.py:25-58); dense form kept for callers outside the fused kernel."""
+    if model_type in ("simple", "ambient"):
+        return epsilon.unsqueeze(-1) * d_empty.unsqueeze(-1) * chi_ambient
+    if model_type == "swapping":
+        return (rho.unsqueeze(-1) * chi_bar * epsilon.unsqueeze(-1)
+                * (y.unsqueeze(-1) * d_cell.unsqueeze(-1) + d_empty.unsqueeze(-1)))
+    if model_type == "full":
+        return epsilon.unsqueeze(-1) * (
+            (1.0 - rho.unsqueeze(-1)) * chi_ambient * d_empty.unsqueeze(-1)
+            + rho.unsqueeze(-1) * chi_bar * (y.unsqueeze(-1) * d_cell.unsqueeze(-1) + d_empty.unsqueeze(-1)))
+    raise NotImplementedError(f"model_type was set to {model_type}, which is not implemented.")
+
+
+def calculate_mu(model_type: str, epsilon, d_cell, chi, y=None, rho=None):
+    """Mean expression (reference model.py:61-85)."""
+    if model_type == "simple":
+        return epsilon.unsqueeze(-1) * d_cell.unsqueeze(-1) * chi
+    if model_type == "ambient":
+        return y.unsqueeze(-1) * epsilon.unsqueeze(-1) * d_cell.unsqueeze(-1) * chi
+    if model_type in ("swapping", "full"):
+        return (1.0 - rho.unsqueeze(-1)) * y.unsqueeze(-1) * epsilon.unsqueeze(-1) * d_cell.unsqueeze(-1) * chi
+    raise NotImplementedError(f"model_type was set to {model_type}, which is not implemented.")
+
+
+def rate_coefficients(model_type: str, epsilon, d_cell, d_empty, rho):
+    """calculate_mu / calculate_lambda in the factored form the fused kernel consumes:
+       mu_y1 = a_mu1 * chi;  lam_y = cAy * chi_ambient + cBy * chi_bar;  lam_E likewise (epsilon = 1, y = 0,
+       rho and d_cell detached: model.py:378-393).  Returns [B, 7] = a_mu1, cA1, cB1, cA0, cB0, cAE, cBE."""
+    zero = torch.zeros_like(epsilon)
+    if model_type == "full":
+        r = rho
+        rd = rho.detach()
+        cols = ((1 - r) * epsilon * d_cell, epsilon * (1 - r) * d_empty, epsilon * r * (d_cell + d_empty),
+                epsilon * (1 - r) * d_empty, epsilon * r * d_empty, (1 - rd) * d_empty, rd * d_empty)
+    elif model_type == "swapping":
+        r = rho
+        rd = rho.detach()
+        cols = ((1 - r) * epsilon * d_cell, zero, epsilon * r * (d_cell + d_empty), zero, epsilon * r * d_empty, zero,
+                rd * d_empty)
+    elif model_type == "ambient":
+        cols = (epsilon * d_cell, epsilon * d_empty, zero, epsilon * d_empty, zero, d_empty, zero)
+    else:
+        raise NotImplementedError(f"model_type '{model_type}' has no empty-droplet mixture; use 'ambient', 'swapping' or 'full'")
+    return torch.stack(cols, dim=1)
+
+
+def get_p_logit_prior(log_counts, log_cell_prior_counts, surely_empty_counts, naive_p_logit_prior):
+    """Per-droplet logit cell-probability prior (reference model.py:577-592)."""
+    ones = torch.ones_like(log_counts)
+    p = ones * naive_p_logit_prior
+    thresh = (torch.as_tensor(surely_empty_counts, dtype=log_counts.dtype, device=log_counts.device).log()
+              + log_cell_prior_counts) / 2
+    p = torch.where(log_counts <= thresh, ones * -100.0, p)
+    p = torch.where(log_counts >= log_cell_prior_counts, ones * consts.REG_LOGIT_MEAN, p)
+    return p
+
+
+class ParamStore(nn.Module):
+    """pyro's param store for this model: unconstrained nn.Parameters + constraint transforms."""
+
+    def __init__(self):
+        super().__init__()
+        self.unconstrained = nn.ParameterDict()
+        self._constraints: Dict[str, Any] = {}
+
+    def setup(self, name: str, init: torch.Tensor, constraint=constraints.real):
+        with torch.no_grad():
+            u = transform_to(constraint).inv(init.detach().clone().float())
+        self.unconstrained[name] = nn.Parameter(u.contiguous())
+        self._constraints[name] = constraint
+
+    def keys(self):
+        return self.unconstrained.keys()
+
+    def __contains__(self, name):
+        return name in self.unconstrained
+
+    def get(self, name: str) -> torch.Tensor:
+        return transform_to(self._constraints[name])(self.unconstrained[name])
+
+    def __getitem__(self, name):
+        return self.get(name)
+
+
+def _masked_lower_median(values: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """values[mask].median() (torch.median = lower median) without a host sync: sort with +inf padding and
+    gather element (k-1)//2.  Returns 1.0 when the mask is empty (the reference would raise there)."""
+    k = mask.sum()
+    srt, _ = torch.sort(torch.where(mask, values, torch.full_like(values, float("inf"))))
+    idx = torch.clamp((k - 1) // 2, min=0)
+    med = srt.gather(0, idx.reshape(1)).squeeze(0)
+    return torch.where(k > 0, med, torch.ones_like(med))
+
+
+class _ObsTerm(torch.autograd.Function):
+    """sum_b sum_k w[b,k] * L[b,k] with L = (L_y1, L_y0, L_E) of the fused observation kernel.  All gradients
+    are produced by the same launch that produces the value, so backward only hands them out (upstream
+    gradient must be the scalar 1 that ``loss.backward()`` supplies; it is applied to the small tensors)."""
+
+    @staticmethod
+    def forward(ctx, h_dec, w_out, b_out, chi_ambient, coef, alpha, w, model):
+        csr, row_ids, bufs = model._obs_ctx
+        G = csr.n_genes
+        B = h_dec.shape[0]
+        logits = bufs["logits"][:B]
+        torch.addmm(b_out, h_dec, w_out.t(), out=logits[:, :G])  # decoder output layer (library GEMM for now)
+        chi_a = bufs["chi_a"]
+        chi_a[:G].copy_(chi_ambient)
+        oo = bufs["obs_out"]
+        out = ops.elbo_obs(csr, row_ids, logits, chi_a, bufs["chi_b"], coef.contiguous(), alpha.reshape(1).contiguous(),
+                           w.contiguous(), out={"sums": oo["sums"][:B], "dlogits": oo["dlogits"][:B], "qamb": oo["qamb"][:B],
+                                                "dchi_ambient": oo["dchi_ambient"], "lse": oo["lse"], "nan_flag": oo["nan_flag"]})
+        sums = out["sums"]
+        L = sums[:, :3]
+        ctx.save_for_backward(h_dec, w_out, sums, w, out["dlogits"], out["dchi_ambient"])
+        ctx.G = G
+        ctx.mark_non_differentiable(L)
+        return (w * L).sum(), L
+
+    @staticmethod
+    def backward(ctx, g, _gL):
+        h_dec, w_out, sums, w, dlogits, dchi_amb = ctx.saved_tensors
+        G = ctx.G
+        dl = dlogits[:, :G]
+        d_h = (dl @ w_out) * g
+        d_w = dl.t() @ h_dec  # [G, H]
+        d_b = ops.colsum_rows(dlogits, G)
+        w1, w0, wE = w[:, 0], w[:, 1], w[:, 2]
+        d_coef = torch.stack((w1 * sums[:, 3], w1 * sums[:, 4], w1 * sums[:, 5], w0 * sums[:, 7], w0 * sums[:, 8],
+                              wE * sums[:, 10], wE * sums[:, 11]), dim=1) * g
+        d_alpha = ((w1 * sums[:, 6] + w0 * sums[:, 9]).sum() * g).reshape(())
+        return d_h, d_w, d_b, dchi_amb * g, d_coef, d_alpha, None, None
+
+
+class RemoveBackgroundPyroModel(nn.Module):
+    """Model + variational guide (reference model.py:88-230 for the constructor; :232-574 for the terms)."""
+
+    def __init__(self, model_type: str, encoder: CompositeEncoder, decoder: nn.Module,
+                 dataset_obj_priors: Dict[str, Any], n_analyzed_genes: int, n_droplets: int,
+                 analyzed_gene_names: np.ndarray, empty_UMI_threshold: int, log_counts_crossover: float,
+                 use_cuda: bool = True, phi_loc_prior: float = consts.PHI_LOC_PRIOR,
+                 phi_scale_prior: float = consts.PHI_SCALE_PRIOR, rho_alpha_prior: float = consts.RHO_ALPHA_PRIOR,
+                 rho_beta_prior: float = consts.RHO_BETA_PRIOR, epsilon_prior: float = consts.EPSILON_PRIOR,
+                 use_exact_log_prob: bool = False, device: Optional[str] = None):
+        super().__init__()
+        if not use_cuda:
+            raise RuntimeError("cellbender_b200 runs on CUDA only (no CPU fallback); pass use_cuda=True")
+        if model_type == "simple":
+            raise NotImplementedError("the B200 hot path covers model types with empty droplets "
+                                      "('ambient', 'swapping', 'full'); 'simple' has no enumerated y")
+        if use_exact_log_prob:
+            raise NotImplementedError("USE_EXACT_LOG_PROB is False in the reference (consts.py:68); "
+                                      "only the default approximate likelihood is on the hot path")
+        self.model_type = model_type
+        self.include_empties = True
+        self.include_rho = model_type in ("full", "swapping")
+        self.n_genes = n_analyzed_genes
+        self.n_droplets = n_droplets
+        self.analyzed_gene_names = analyzed_gene_names
+        self.z_dim = int(decoder.input_dim)
+        self.encoder = encoder
+        self.encoder_modules = nn.ModuleDict({k: v for k, v in encoder.items()})  # registers the encoder parameters
+        self.decoder = decoder
+        self.use_exact_log_prob = use_exact_log_prob
+        self.loss: Dict[str, Dict[str, list]] = {"train": {"epoch": [], "elbo": []}, "test": {"epoch": [], "elbo": []},
+                                                 "learning_rate": {"epoch": [], "value": []}}
+        self.log_counts_crossover = log_counts_crossover
+        self.counts_crossover = float(np.exp(log_counts_crossover))
+        self.device = device or "cuda"
+        self.use_cuda = True
+        dev = self.device
+
+        p = dataset_obj_priors
+        assert p["d_std"] > 0, f"Issue with prior: d_std is {p['d_std']}, but should be > 0."
+        assert p["cell_counts"] > 0, f"Issue with prior: cell_counts is {p['cell_counts']}, but should be > 0."
+        assert p["empty_counts"] > 0, f"Issue with prior: empty_counts should be > 0, but is {p['empty_counts']}"
+        chi_amb0 = torch.as_tensor(p["chi_ambient"]).float()
+        chi_bar0 = torch.as_tensor(p["chi_bar"]).float()
+        assert np.isclose(float(chi_amb0.sum()), 1.0, atol=1e-5), "Issue with prior: chi_ambient should sum to 1"
+        assert np.isclose(float(chi_bar0.sum()), 1.0, atol=1e-5), "Issue with prior: chi_bar should sum to 1"
+
+        def scalar(v):
+            return torch.tensor(float(v), dtype=torch.float32, device=dev)
+
+        self.d_cell_loc_prior = scalar(np.log1p(p["cell_counts"]))
+        self.d_cell_scale_prior = scalar(p["d_std"])
+        self.z_loc_prior = torch.zeros(self.z_dim, device=dev)
+        self.z_scale_prior = torch.ones(self.z_dim, device=dev)
+        self.epsilon_prior = scalar(epsilon_prior)
+        self.phi_loc_prior = scalar(phi_loc_prior)
+        self.phi_scale_prior = scalar(phi_scale_prior)
+        self.phi_conc_prior = scalar(phi_loc_prior ** 2 / phi_scale_prior ** 2)
+        self.phi_rate_prior = scalar(phi_loc_prior / phi_scale_prior ** 2)
+        self.d_empty_loc_prior = scalar(np.log1p(p["empty_counts"], dtype=np.float32).item())
+        self.d_empty_scale_prior = scalar(p["d_empty_std"])
+        self.p_logit_prior = scalar(p["cell_logit"])
+        self.chi_ambient_init = chi_amb0.to(dev)
+        self.avg_gene_expression = chi_bar0.to(dev)
+        self.empty_UMI_threshold = scalar(empty_UMI_threshold)
+        self.rho_alpha_prior = scalar(rho_alpha_prior)
+        self.rho_beta_prior = scalar(rho_beta_prior)
+
+        # pyro.param sites (model.py:245-249, 468-513)
+        ps = ParamStore()
+        ps.setup("chi_ambient", self.chi_ambient_init, constraints.simplex)
+        ps.setup("d_cell_scale", torch.tensor([consts.D_CELL_SCALE_INIT]), constraints.positive)
+        ps.setup("d_empty_loc", self.d_empty_loc_prior, constraints.positive)
+        ps.setup("d_empty_scale", self.d_empty_scale_prior, constraints.positive)
+        if self.include_rho:
+            interval = constraints.interval(consts.RHO_PARAM_MIN, consts.RHO_PARAM_MAX)
+            ps.setup("rho_alpha", self.rho_alpha_prior, interval)
+            ps.setup("rho_beta", self.rho_beta_prior, interval)
+        ps.setup("phi_loc", self.phi_loc_prior, constraints.positive)
+        ps.setup("phi_scale", self.phi_scale_prior, constraints.positive)
+        self.param_store = ps
+        self.to(dev)
+        if "other" in encoder:
+            encoder["other"].d_empty_loc_fn = lambda: self.param_store["d_empty_loc"]
+        self._obs_ctx = None
+        self._bufs: Dict[int, dict] = {}
+        self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    # ---- pyro.param(...) compatibility -----------------------------------------------------------------
+    def param(self, name: str) -> torch.Tensor:
+        return self.param_store[name]
+
+    # ---- buffers reused across steps (fixed addresses: CUDA-graph friendly) -----------------------------
+    def _work_buffers(self, B: int) -> dict:
+        key = 0
+        if key not in self._bufs or self._bufs[key]["cap"] < B:
+            G, dev = self.n_genes, self.device
+            cap = max(B, 8)
+            ld = ops.round_up(G, 4)
+            chi_b = torch.zeros(ld, device=dev)
+            chi_b[:G] = self.avg_gene_expression
+            self._bufs[key] = {
+                "cap": cap, "logits": torch.zeros((cap, ld), device=dev), "chi_a": torch.zeros(ld, device=dev),
+                "chi_b": chi_b,
+                "obs_out": {"sums": torch.empty((cap, 12), device=dev), "dlogits": torch.zeros((cap, ld), device=dev),
+                            "qamb": torch.empty((cap, ld), device=dev), "dchi_ambient": torch.empty(G, device=dev),
+                            "lse": torch.empty(cap, device=dev), "nan_flag": self.nan_flag}}
+        return self._bufs[key]
+
+    # ---- the ELBO --------------------------------------------------------------------------------------
+    def draw_guide_samples(self, inp: EncoderInputs, enc: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """rsample every continuous guide site, in the guide's order (model.py:506-567)."""
+        ps = self.param_store
+        B = inp.feats.shape[0]
+        phi_loc, phi_scale = ps["phi_loc"], ps["phi_scale"]
+        s = {"phi": Gamma(phi_loc.pow(2) / phi_scale.pow(2), phi_loc / phi_scale.pow(2)).rsample()}
+        if self.include_rho:
+            s["rho"] = Beta(ps["rho_alpha"], ps["rho_beta"]).expand([B]).rsample()
+        s["d_empty"] = LogNormal(ps["d_empty_loc"], ps["d_empty_scale"]).expand([B]).rsample()
+        s["p_logit_reg"] = Normal(enc["p_y"], consts.P_LOGIT_SCALE).rsample()
+        s["z"] = Normal(enc["z"]["loc"], enc["z"]["scale"]).rsample()
+        prob = enc["p_y"].sigmoid().detach()
+        s["d_cell"] = LogNormal(prob * enc["d_loc"] + (1 - prob) * self.d_cell_loc_prior, ps["d_cell_scale"]).rsample()
+        s["epsilon"] = Gamma((prob * enc["epsilon"] + (1 - prob)) * self.epsilon_prior, self.epsilon_prior).rsample()
+        return s
+
+    def elbo_terms(self, csr: ops.DeviceCSR, row_ids: torch.Tensor, inp: EncoderInputs,
+                   samples: Optional[Dict[str, torch.Tensor]] = None, row_keep_scale: Optional[torch.Tensor] = None,
+                   sampler=None) -> Dict[str, torch.Tensor]:
+        """All terms of the ELBO for one minibatch.  Returns a dict of scalar tensors whose
+        sum is the ELBO, plus 'loss' = -ELBO.  ``samples``/``sampler`` let tests inject fixed noise."""
+        ps = self.param_store
+        B = inp.feats.shape[0]
+        chi_ambient = ps["chi_ambient"]
+        enc = self.encoder(x=inp, chi_ambient=chi_ambient.detach(), cell_prior_log=self.d_cell_loc_prior,
+                           row_keep_scale=row_keep_scale)
+        if samples is None:
+            samples = (sampler or self.draw_guide_samples)(inp, enc)
+        phi, d_empty, v, z, d_cell, epsilon = (samples[k] for k in ("phi", "d_empty", "p_logit_reg", "z", "d_cell", "epsilon"))
+        rho = samples["rho"] if self.include_rho else torch.zeros_like(d_cell)
+        p_y = enc["p_y"]
+        log_q1, log_q0 = F.logsigmoid(p_y), F.logsigmoid(-p_y)
+        q1, q0 = log_q1.exp(), log_q0.exp()
+        prob = p_y.sigmoid().detach()
+        counts = inp.counts
+        t: Dict[str, torch.Tensor] = {}
+
+        # global phi
+        phi_loc, phi_scale = ps["phi_loc"], ps["phi_scale"]
+        t["phi"] = (Gamma(self.phi_conc_prior, self.phi_rate_prior).log_prob(phi)
+                    - Gamma(phi_loc.pow(2) / phi_scale.pow(2), phi_loc / phi_scale.pow(2)).log_prob(phi))
+        # z: model side unmasked, guide side masked by y (model.py:262-264, 553-555)
+        t["z"] = (Normal(self.z_loc_prior, self.z_scale_prior).log_prob(z).sum(-1).sum()
+                  - (q1 * Normal(enc["z"]["loc"], enc["z"]["scale"]).log_prob(z).sum(-1)).sum())
+        d_cell_loc_gated = prob * enc["d_loc"] + (1 - prob) * self.d_cell_loc_prior
+        t["d_cell"] = (LogNormal(self.d_cell_loc_prior, self.d_cell_scale_prior).log_prob(d_cell)
+                       - LogNormal(d_cell_loc_gated, ps["d_cell_scale"]).log_prob(d_cell)).sum()
+        if self.include_rho:
+            t["rho"] = (Beta(self.rho_alpha_prior, self.rho_beta_prior).log_prob(rho)
+                        - Beta(ps["rho_alpha"], ps["rho_beta"]).log_prob(rho)).sum()
+        eps_gated = prob * enc["epsilon"] + (1 - prob)
+        t["epsilon"] = (Gamma(self.epsilon_prior, self.epsilon_prior).log_prob(epsilon)
+                        - Gamma(eps_gated * self.epsilon_prior, self.epsilon_prior).log_prob(epsilon)).sum()
+        t["d_empty"] = (LogNormal(self.d_empty_loc_prior, self.d_empty_scale_prior).log_prob(d_empty)
+                        - LogNormal(ps["d_empty_loc"], ps["d_empty_scale"]).log_prob(d_empty)).sum()
+        # y: enumerated in the guide (model.py:295-301, 547)
+        plp = get_p_logit_prior(counts.log(), self.d_cell_loc_prior, self.empty_UMI_threshold, self.p_logit_prior)
+        t["y"] = (q1 * (F.logsigmoid(plp) - log_q1) + q0 * (F.logsigmoid(-plp) - log_q0)).sum()
+        t["p_logit_reg"] = (Normal(self.p_logit_prior, consts.P_LOGIT_SCALE).log_prob(v)
+                            - Normal(p_y, consts.P_LOGIT_SCALE).log_prob(v)).sum()
+
+        # observation terms: decoder output layer + fused likelihood kernel
+        alpha = phi.reciprocal() + consts.NBPC_ALPHA_EPS_SAFEGAURD
+        coef = rate_coefficients(self.model_type, epsilon, d_cell, d_empty, rho)
+        w = -torch.stack((q1, q0, consts.REG_SCALE_AMBIENT_EXPRESSION * q0), dim=1)  # d(-ELBO)/dL
+        h_dec = self.decoder.hidden(z)
+        lin = self.decoder.out_linear
+        self._obs_ctx = (csr, row_ids, self._work_buffers(B))
+        neg_obs, L = _ObsTerm.apply(h_dec, lin.weight, lin.bias, chi_ambient, coef, alpha, w.detach(), self)
+        dice = (w * L).sum()  # carries d/d p_y through the enumeration weights; value cancels below
+        t["obs"] = -(neg_obs + dice - dice.detach())
+        self._last_L = L
+
+        # soft semi-supervision of p_y (no gradient: p_passback is detached; model.py:400-427)
+        p_det = p_y.detach()
+        empty_m = counts < self.counts_crossover
+        cell_m = counts >= self.counts_crossover
+        t["obs_probably_empty_y"] = consts.REG_SCALE_SOFT_SUPERVISION * torch.where(
+            empty_m, Normal(-consts.REG_LOGIT_MEAN, consts.REG_LOGIT_SOFT_SCALE).log_prob(p_det), torch.zeros_like(p_det)).sum()
+        t["obs_probably_cell_y"] = consts.REG_SCALE_SOFT_SUPERVISION * torch.where(
+            cell_m, Normal(consts.REG_LOGIT_MEAN, consts.REG_LOGIT_SOFT_SCALE).log_prob(p_det), torch.zeros_like(p_det)).sum()
+        # epsilon medians (model.py:429-443)
+        surely_cell = counts >= self.d_cell_loc_prior.exp()
+        one = torch.ones((), device=counts.device)
+        med_cell = _masked_lower_median(epsilon, cell_m)
+        t["epsilon_mean"] = torch.where(surely_cell.sum() >= 2, Normal(med_cell, 0.01).log_prob(one), torch.zeros_like(one))
+        t["epsilon_empty_mean"] = Normal(_masked_lower_median(epsilon, empty_m), 0.01).log_prob(one)
+
+        elbo = sum(t.values())
+        t["loss"] = -elbo
+        t["_enc"] = enc  # for callers that need p_y etc.
+        return t
+
+    def check_nan(self):
+        """Raise NanException like the reference's log_prob does (...ConvApprox.py:129-141); one host sync."""
+        if int(self.nan_flag.item()) != 0:
+            self.nan_flag.zero_()
+            raise NanException(param="mu, alpha, lam (fused likelihood kernel)")

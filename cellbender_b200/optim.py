@@ -1,0 +1,121 @@
+"""Optimizer: pyro's ClippedAdam driven by torch's OneCycleLR (reference run.py:593-629), fused over one flat
+parameter buffer (csrc/adam.cu).
+
+Reference semantics kept: one optimizer step per minibatch followed by one scheduler step (train.py:56-60);
+``OneCycleLR(max_lr = 10 lr, total_steps = n_batches * epochs)`` with torch's defaults (pct_start 0.3, cosine
+annealing, div_factor 25, final_div_factor 1e4, cycle_momentum: beta1 0.95 -> 0.85 -> 0.95); elementwise gradient
+clamp at +-10 (pyro ClippedAdam ``clip_norm``), beta2 0.999, eps 1e-8, no weight decay, lrd 1; stepping beyond
+``total_steps`` raises like torch's scheduler does (pinned by the reference's tests/test_train.py:87-108).
+``constant_learning_rate=True`` gives plain ClippedAdam at ``lr`` with beta1 0.9 (run.py:621-627).
+"""
+from typing import Iterable, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def one_cycle_tables(learning_rate: float, total_steps: int):
+    """Per-step (lr, beta1) of torch.optim.lr_scheduler.OneCycleLR wrapped around an Adam-family optimizer."""
+    dummy = torch.optim.Adam([torch.zeros(1, requires_grad=True)], lr=learning_rate, betas=(0.9, 0.999))
+    sched = torch.optim.lr_scheduler.OneCycleLR(dummy, max_lr=learning_rate * 10, total_steps=total_steps)
+    lrs, b1s = [], []
+    for k in range(total_steps):
+        lrs.append(dummy.param_groups[0]["lr"])
+        b1s.append(dummy.param_groups[0]["betas"][0])
+        dummy.step()
+        if k < total_steps - 1:
+            sched.step()
+    return lrs, b1s
+
+
+class FlatClippedAdam:
+    """All trainable tensors re-homed into ONE contiguous fp32 buffer (the nn.Parameters become views, names and
+    shapes unchanged), with flat gradient / first-moment / second-moment buffers beside it."""
+
+    def __init__(self, params: Iterable[nn.Parameter], learning_rate: float, total_steps: Optional[int],
+                 constant_learning_rate: bool = False, clip_norm: float = 10.0, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.params: List[nn.Parameter] = [p for p in params if p.requires_grad]
+        assert self.params, "no parameters to optimise"
+        dev = self.params[0].device
+        self.device = dev
+        sizes = [p.numel() for p in self.params]
+        # each tensor starts on a 16-byte boundary so the big weight matrices stay vector/TMA friendly
+        self.offsets, off = [], 0
+        for n in sizes:
+            self.offsets.append(off)
+            off += (n + 3) // 4 * 4
+        self.n = off
+        self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad_views = []
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                view = self.flat_p[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                self.grad_views.append(self.flat_g[o:o + p.numel()].view(p.shape))
+        self.learning_rate = learning_rate
+        self.total_steps = total_steps
+        self.constant_learning_rate = constant_learning_rate or total_steps is None
+        if self.constant_learning_rate:
+            lrs, b1s = [learning_rate], [betas[0]]
+        else:
+            lrs, b1s = one_cycle_tables(learning_rate, total_steps)
+        self._lrs = lrs
+        self.lr_table = torch.tensor(lrs, dtype=torch.float32, device=dev)
+        self.beta1_table = torch.tensor(b1s, dtype=torch.float32, device=dev)
+        self.beta2, self.eps, self.clip = betas[1], eps, clip_norm
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)  # optimizer steps taken (device side)
+        self.host_steps = 0
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    def collect_grads(self):
+        """Gather the autograd-produced gradients into the flat buffer (missing gradient = 0)."""
+        src, dst = [], []
+        for p, gv in zip(self.params, self.grad_views):
+            if p.grad is None:
+                gv.zero_()
+            elif p.grad.data_ptr() != gv.data_ptr():
+                src.append(p.grad)
+                dst.append(gv)
+        if src:
+            torch._foreach_copy_(dst, src)
+
+    def step(self, grad_scale: float = 1.0):
+        """One ClippedAdam step over the flat buffers + one scheduler step."""
+        if not self.constant_learning_rate and self.host_steps >= self.total_steps:
+            raise ValueError(f"Tried to step {self.host_steps + 1} times. The specified number of total steps is "
+                             f"{self.total_steps}")
+        ops.clipped_adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_table, self.beta1_table,
+                              self.step_count, beta2=self.beta2, eps=self.eps, clip=self.clip, grad_scale=grad_scale)
+        self.host_steps += 1
+
+    def get_last_lr(self) -> List[float]:
+        """LR that the NEXT optimizer step will use (what OneCycleLR.get_last_lr() reports after its step)."""
+        if self.constant_learning_rate:
+            return [self.learning_rate]
+        return [self._lrs[min(self.host_steps, len(self._lrs) - 1)]]
+
+    def state_dict(self):
+        return {"flat_m": self.flat_m, "flat_v": self.flat_v, "step": self.step_count, "host_steps": self.host_steps,
+                "total_steps": self.total_steps, "learning_rate": self.learning_rate}
+
+    def load_state_dict(self, sd):
+        self.flat_m.copy_(sd["flat_m"])
+        self.flat_v.copy_(sd["flat_v"])
+        self.step_count.copy_(sd["step"])
+        self.host_steps = int(sd["host_steps"])
+
+
+def get_optimizer(model, n_batches: int, batch_size: int, epochs: int, learning_rate: float,
+                  constant_learning_rate: bool, total_epochs_for_testing_only: Optional[int] = None) -> FlatClippedAdam:
+    """Reference run.py:593-629 (same arguments, plus the model whose parameters are optimised)."""
+    total_steps = n_batches * (total_epochs_for_testing_only if total_epochs_for_testing_only is not None else epochs)
+    return FlatClippedAdam(model.parameters(), learning_rate, total_steps, constant_learning_rate=constant_learning_rate)

@@ -1,0 +1,100 @@
+"""Construction of the inference objects exactly as the reference's run_inference does it (reference
+cellbender/remove_background/run.py:632-856): seeds, EncodeZ / EncodeNonZLatents / Decoder hyper-parameters,
+batch size rule, train/test split, optimizer.  The CLI, file I/O, report and checkpoint tarball around it are out of
+scope -- a caller that has a prepared dataset object gets the same model trained the same way.
+"""
+import argparse
+import logging
+import random
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import consts
+from .dataprep import DataLoader, prep_sparse_data_for_training
+from .model import RemoveBackgroundPyroModel
+from .optim import FlatClippedAdam, get_optimizer
+from .train import SVI, run_training
+from .vae import CompositeEncoder, Decoder, EncodeNonZLatents, EncodeZ
+
+logger = logging.getLogger("cellbender")
+
+
+def default_args(**overrides) -> argparse.Namespace:
+    """The reference's argparse defaults on the hot path (argparser.py:119-182, 234-243, 295-304, 335-344)."""
+    d = dict(model="full", epochs=150, z_dim=64, z_hidden_dims=[512], learning_rate=1e-4, training_fraction=0.9,
+             fraction_empties=0.2, constant_learning_rate=False, epoch_elbo_fail_fraction=None,
+             final_elbo_fail_fraction=None, posterior_batch_size=consts.PROB_POSTERIOR_BATCH_SIZE, fpr=[0.01],
+             estimator="mckp", use_cuda=True, debug=False, checkpoint_min=7.0)
+    d.update(overrides)
+    return argparse.Namespace(**d)
+
+
+def set_rng_seed(seed: int):
+    """pyro.set_rng_seed (run.py:664-666): python, numpy and torch (all devices)."""
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+def build_model(dataset_obj, args, device: Optional[str] = None) -> RemoveBackgroundPyroModel:
+    """run.py:695-743."""
+    n_genes = int(dataset_obj.analyzed_gene_inds.size)
+    encoder_z = EncodeZ(input_dim=n_genes, hidden_dims=args.z_hidden_dims, output_dim=args.z_dim, use_batch_norm=False,
+                        use_layer_norm=False, input_transform="normalize")
+    encoder_other = EncodeNonZLatents(
+        n_genes=n_genes, z_dim=args.z_dim, log_count_crossover=dataset_obj.priors["log_counts_crossover"],
+        prior_log_cell_counts=np.log1p(dataset_obj.priors["cell_counts"]),
+        empty_log_count_threshold=np.log1p(dataset_obj.empty_UMI_threshold),
+        prior_logit_cell_prob=dataset_obj.priors["cell_logit"], input_transform="log_normalize")
+    encoder = CompositeEncoder({"z": encoder_z, "other": encoder_other})
+    decoder = Decoder(input_dim=args.z_dim, hidden_dims=args.z_hidden_dims[::-1], use_batch_norm=True,
+                      use_layer_norm=False, output_dim=n_genes)
+    gene_names = np.array([f"g{n:05d}" for n in dataset_obj.analyzed_gene_inds])
+    return RemoveBackgroundPyroModel(
+        model_type=args.model, encoder=encoder, decoder=decoder, dataset_obj_priors=dataset_obj.priors,
+        n_analyzed_genes=n_genes, n_droplets=int(dataset_obj.analyzed_barcode_inds.size),
+        analyzed_gene_names=gene_names, empty_UMI_threshold=dataset_obj.empty_UMI_threshold,
+        log_counts_crossover=dataset_obj.priors["log_counts_crossover"], use_cuda=True, device=device)
+
+
+def setup_inference(dataset_obj, args, device: Optional[str] = None, total_epochs_for_testing_only: Optional[int] = None,
+                    rank: int = 0, world_size: int = 1):
+    """Everything run_inference builds before training starts (run.py:658-786).  With world_size > 1 every rank
+    builds the identical model (same seed) and takes a disjoint shard of the training droplets (see dp.py)."""
+    set_rng_seed(consts.RANDOM_SEED)
+    count_matrix = dataset_obj.get_count_matrix()
+    model = build_model(dataset_obj, args, device=device)
+    frac = args.training_fraction
+    batch_size = int(min(consts.MAX_BATCH_SIZE, frac * dataset_obj.analyzed_barcode_inds.size / 2))
+    empties = dataset_obj.get_count_matrix_empties()
+    if world_size > 1:
+        from .dp import shard_rows
+
+        count_matrix = count_matrix[shard_rows(count_matrix.shape[0], rank, world_size)]
+        np.random.seed(consts.RANDOM_SEED + 7919 * rank)  # per-rank loader stream (empties choice, shuffles)
+    train_loader, test_loader = prep_sparse_data_for_training(
+        dataset=count_matrix, empty_drop_dataset=empties, batch_size=batch_size, training_fraction=frac,
+        fraction_empties=args.fraction_empties, shuffle=True, device=device)
+    scheduler = get_optimizer(model, n_batches=len(train_loader), batch_size=train_loader.batch_size, epochs=args.epochs,
+                              learning_rate=args.learning_rate, constant_learning_rate=args.constant_learning_rate,
+                              total_epochs_for_testing_only=total_epochs_for_testing_only)
+    svi = SVI(model, scheduler)
+    return model, scheduler, svi, train_loader, test_loader
+
+
+def run_inference(dataset_obj, args, device: Optional[str] = None, total_epochs_for_testing_only: Optional[int] = None
+                  ) -> Tuple[RemoveBackgroundPyroModel, FlatClippedAdam, DataLoader, DataLoader]:
+    """Full inference procedure (run.py:632-856 without checkpoint tarballs and the ELBO-retry re-entry)."""
+    model, scheduler, svi, train_loader, test_loader = setup_inference(
+        dataset_obj, args, device=device, total_epochs_for_testing_only=total_epochs_for_testing_only)
+    if args.epochs > 0:
+        logger.info("Running inference...")
+        run_training(model=model, svi=svi, train_loader=train_loader, test_loader=test_loader, epochs=args.epochs,
+                     test_freq=5, epoch_elbo_fail_fraction=args.epoch_elbo_fail_fraction,
+                     final_elbo_fail_fraction=args.final_elbo_fail_fraction, learning_rate=args.learning_rate)
+        logger.info("Inference procedure complete.")
+    return model, scheduler, train_loader, test_loader

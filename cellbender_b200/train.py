@@ -1,0 +1,169 @@
+"""Training loop with the reference's structure and criteria (reference cellbender/remove_background/train.py:
+train_epoch :34-72, evaluate_epoch :75-104, run_training :108-300), driving the B200 step.
+
+``SVI`` here is the pyro-free stand-in for ``pyro.infer.SVI(model.model, model.guide, scheduler,
+TraceEnum_ELBO)`` (run.py:783-786): ``step(batch)`` = loss + backward + optimizer step, ``evaluate_loss(batch)``
+= loss only.  Losses stay on the device; they are summed there and read once per epoch (the reference syncs every
+step through ``loss.item()``).
+"""
+import logging
+import sys
+import time
+from datetime import datetime
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .dataprep import DataLoader, MiniBatch
+from .exceptions import ElboException, NanException
+from .model import RemoveBackgroundPyroModel
+from .optim import FlatClippedAdam
+
+logger = logging.getLogger("cellbender")
+
+
+class SVI:
+    def __init__(self, model: RemoveBackgroundPyroModel, optim: FlatClippedAdam):
+        self.model = model
+        self.optim = optim
+        self._amb_unit = None
+
+    def _ambient_unit_vector(self) -> torch.Tensor:
+        """x_ambient / ||x_ambient||_2 of EncodeNonZLatents.forward (vae/encoder.py:266-270); the d_empty factor
+        cancels in the normalisation."""
+        chi = self.model.param_store["chi_ambient"].detach()
+        return (chi / torch.linalg.vector_norm(chi)).contiguous()
+
+    def loss_terms(self, batch: MiniBatch):
+        inp = batch.encoder_inputs(self._ambient_unit_vector())
+        return self.model.elbo_terms(batch.loader.csr, batch.row_ids, inp)
+
+    def step(self, batch: MiniBatch) -> torch.Tensor:
+        """One training step; returns the loss (-ELBO, summed over the minibatch) as a 0-dim device tensor."""
+        self.optim.zero_grad()
+        terms = self.loss_terms(batch)
+        loss = terms["loss"]
+        loss.backward()
+        self.optim.collect_grads()
+        self.optim.step()
+        return loss.detach()
+
+    @torch.no_grad()
+    def evaluate_loss(self, batch: MiniBatch) -> torch.Tensor:
+        return self.loss_terms(batch)["loss"].detach()
+
+
+def is_scheduler(optim) -> bool:
+    return isinstance(optim, FlatClippedAdam) and not optim.constant_learning_rate
+
+
+def train_epoch(svi: SVI, train_loader: DataLoader) -> float:
+    """-ELBO per droplet over one pass of the training loader (train.py:34-72)."""
+    epoch_loss = torch.zeros((), device=svi.model.device)
+    normalizer_train = 0.0
+    for x_cell_batch in train_loader:
+        epoch_loss += svi.step(x_cell_batch)  # optimizer step + scheduler step are fused (train.py:56-60)
+        normalizer_train += x_cell_batch.size(0)
+    svi.model.check_nan()
+    return float(epoch_loss.item()) / normalizer_train
+
+
+def evaluate_epoch(svi: SVI, test_loader: DataLoader) -> float:
+    """Test-set loss (train.py:75-104)."""
+    test_loss = torch.zeros((), device=svi.model.device)
+    normalizer_test = 0.0
+    for x_cell_batch in test_loader:
+        test_loss += svi.evaluate_loss(x_cell_batch)
+        normalizer_test += x_cell_batch.size(0)
+    return float(test_loss.item()) / normalizer_test if normalizer_test > 0 else np.nan
+
+
+def run_training(model: RemoveBackgroundPyroModel, svi: SVI, train_loader: DataLoader, test_loader: Optional[DataLoader],
+                 epochs: int, test_freq: int = 10, final_elbo_fail_fraction: Optional[float] = None,
+                 epoch_elbo_fail_fraction: Optional[float] = None, learning_rate: Optional[float] = None,
+                 checkpoint_fn=None, checkpoint_freq: int = 10, debug: bool = False) -> Tuple[List[float], List[float]]:
+    """Full course of training with periodic test-set evaluation and the reference's ELBO failure criteria
+    (train.py:108-300).  ``checkpoint_fn(epoch)`` is called where the reference saves a checkpoint."""
+    train_elbo: List[float] = []
+    epoch_checkpoint_freq = 1000
+    try:
+        start_epoch = 1 if len(model.loss["train"]["epoch"]) == 0 else model.loss["train"]["epoch"][-1] + 1
+        for epoch in range(start_epoch, epochs + 1):
+            if epoch == start_epoch + 1:
+                t = time.time()
+            model.train()
+            total_epoch_loss_train = train_epoch(svi, train_loader)
+            train_elbo.append(-total_epoch_loss_train)
+            last_learning_rate = svi.optim.get_last_lr()[0] if is_scheduler(svi.optim) else learning_rate
+            model.loss["train"]["epoch"].append(epoch)
+            model.loss["train"]["elbo"].append(-total_epoch_loss_train)
+            model.loss["learning_rate"]["epoch"].append(epoch)
+            model.loss["learning_rate"]["value"].append(last_learning_rate)
+            if epoch == start_epoch + 1:
+                time_per_epoch = time.time() - t
+                logger.info("[epoch %03d]  average training loss: %.4f  (%.1f seconds per epoch)"
+                            % (epoch, total_epoch_loss_train, time_per_epoch))
+                epoch_checkpoint_freq = int(np.ceil(60 * checkpoint_freq / max(time_per_epoch, 1e-9)))
+            else:
+                logger.info("[epoch %03d]  average training loss: %.4f" % (epoch, total_epoch_loss_train))
+
+            if (test_loader is not None) and (len(test_loader) > 0) and epoch % test_freq == 0:
+                model.eval()
+                total_epoch_loss_test = evaluate_epoch(svi, test_loader)
+                model.loss["test"]["epoch"].append(epoch)
+                model.loss["test"]["elbo"].append(-total_epoch_loss_test)
+                logger.info("[epoch %03d] average test loss: %.4f" % (epoch, total_epoch_loss_test))
+                if (epoch_elbo_fail_fraction is not None) and (len(model.loss["test"]["elbo"]) > 2):
+                    current_diff = max(0.0, model.loss["test"]["elbo"][-2] - model.loss["test"]["elbo"][-1])
+                    overall_diff = np.abs(model.loss["test"]["elbo"][-2] - model.loss["test"]["elbo"][0])
+                    fractional_spike = current_diff / overall_diff
+                    if fractional_spike > epoch_elbo_fail_fraction:
+                        raise ElboException(
+                            f"Training failed because test loss moved {current_diff:.2f} in the wrong direction, and "
+                            f"that is {fractional_spike:.2f} of the total test ELBO change, > specified "
+                            f"epoch_elbo_fail_fraction {epoch_elbo_fail_fraction:.2f}")
+
+            if checkpoint_fn is not None and (((checkpoint_freq > 0) and (epoch % epoch_checkpoint_freq == 0))
+                                              or (epoch == epochs)):
+                checkpoint_fn(epoch)
+
+        if final_elbo_fail_fraction is not None and len(model.loss["test"]["elbo"]) > 0:
+            best_test_elbo = max(model.loss["test"]["elbo"])
+            if model.loss["test"]["elbo"][-1] < best_test_elbo:
+                final_best_diff = best_test_elbo - model.loss["test"]["elbo"][-1]
+                initial_best_diff = best_test_elbo - model.loss["test"]["elbo"][0]
+                if initial_best_diff == 0:
+                    raise ElboException(
+                        f"Training failed because there was no improvement from the initial test loss "
+                        f"{model.loss['test']['elbo'][0]:.2f}. Final test loss was {model.loss['test']['elbo'][-1]}")
+                elif (final_best_diff / initial_best_diff) > final_elbo_fail_fraction:
+                    raise ElboException(
+                        f"Training failed because final test loss {model.loss['test']['elbo'][-1]:.2f} is not "
+                        f"sufficiently close to best test loss {best_test_elbo:.2f}, compared to the initial test loss "
+                        f"{model.loss['test']['elbo'][0]:.2f}. Fractional difference is "
+                        f"{final_best_diff / initial_best_diff:.2f}, which is > specified final_elbo_fail_fraction "
+                        f"{final_elbo_fail_fraction:.2f}")
+
+    except KeyboardInterrupt:
+        logger.info("Inference procedure stopped by keyboard interrupt... will save a checkpoint.")
+        if checkpoint_fn is not None:
+            checkpoint_fn(-1)
+    except ElboException as e:
+        logger.info(e.message)
+        raise e
+    except NanException as nan:
+        print(nan.message)
+        logger.info(f"Inference procedure terminated early due to a NaN value in: {nan.param}\n\n"
+                    f"The suggested fix is to reduce the learning rate by a factor of two.\n\n")
+        sys.exit(1)
+
+    logger.info(datetime.now().strftime("%Y-%m-%d %H:%M:%S"))
+    if (final_elbo_fail_fraction is not None) and (len(model.loss["test"]["elbo"]) > 1):
+        best_test_elbo = max(model.loss["test"]["elbo"])
+        if -model.loss["test"]["elbo"][-1] >= -best_test_elbo * (1 + final_elbo_fail_fraction):
+            raise ElboException(
+                f"Training failed because final test loss ({-model.loss['test']['elbo'][-1]:.4f}) exceeds best test "
+                f"loss ({-best_test_elbo:.4f}) by >= {100 * final_elbo_fail_fraction:.1f}%")
+    torch.cuda.empty_cache()
+    return train_elbo, model.loss["test"]["elbo"]

@@ -1,0 +1,301 @@
+"""Encoder / decoder networks with the reference's module interface (same class names, constructor
+arguments, attribute paths and state_dict keys -- they are part of the checkpoint layout, SURVEY.md
+Appendix B), computing through the B200 kernels.
+
+Reference: cellbender/remove_background/vae/{base,encoder,decoder}.py.
+
+What runs where
+  * the three G -> 512 input layers and the 512 -> G output layer (the only large contractions) go through
+    ``gemm.linear_big`` (hand-written tcgen05 GEMM when enabled, see csrc/gemm_tf32.cu);
+  * the dense minibatch never exists as raw counts: the loader hands over ``EncoderInputs`` produced by the
+    gather kernel (x/(sum+eps), log1p of it, per-droplet features);
+  * the decoder stops at the logits: softmax is fused into the likelihood kernel (``Decoder.forward`` still
+    returns chi for callers that want it).
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import consts
+from .gemm import linear_big
+
+
+@dataclass
+class EncoderInputs:
+    """Output of the gather kernel for one minibatch (cb_csr_gather_rows)."""
+
+    x_norm: torch.Tensor  # [B, ld]  x / (sum + 1e-5)            (EncodeZ input, transform 'normalize')
+    x_lognorm: torch.Tensor  # [B, ld]  log1p(x / (sum + 1e-5))  (EncodeNonZLatents input, 'log_normalize')
+    feats: torch.Tensor  # [B, 4]   sum, nnz, dot(x, ambient unit vector), max
+    n_genes: int
+
+    @property
+    def counts(self) -> torch.Tensor:
+        return self.feats[:, 0]
+
+
+class FullyConnectedLayer(nn.Module):
+    """Linear (+ BatchNorm1d(momentum=0.01, eps=0.001)) (+ activation), reference vae/base.py:31-82."""
+
+    def __init__(self, input_dim: int, output_dim: int, activation=nn.ReLU, use_batch_norm: bool = False,
+                 use_layer_norm: bool = False, dropout_rate: Optional[float] = None):
+        super().__init__()
+        self.input_dim, self.output_dim = input_dim, output_dim
+        modules: List[nn.Module] = []
+        if dropout_rate is not None:
+            modules.append(nn.Dropout(p=dropout_rate))
+        modules.append(nn.Linear(in_features=input_dim, out_features=output_dim))
+        if use_batch_norm:
+            modules.append(nn.BatchNorm1d(num_features=output_dim, momentum=0.01, eps=0.001))
+        if use_layer_norm:
+            modules.append(nn.LayerNorm(normalized_shape=output_dim, elementwise_affine=False))
+        if activation is not None:
+            modules.append(activation() if isinstance(activation, type) else activation)
+        self.layer = nn.Sequential(*modules)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.layer(x)
+
+
+class FullyConnectedNetwork(nn.Module):
+    """Stack of FullyConnectedLayer, reference vae/base.py:85-148."""
+
+    def __init__(self, input_dim: int, hidden_dims: List[int], output_dim: int, hidden_activation=nn.ReLU(),
+                 output_activation=None, use_batch_norm: bool = False, use_layer_norm: bool = False,
+                 norm_output: bool = False, dropout_rate: Optional[float] = None, dropout_input: bool = False):
+        super().__init__()
+        if use_layer_norm and use_batch_norm:
+            raise UserWarning("You are trying to use both batch norm and layer norm. That's probably too much norm.")
+        dims = list(zip([input_dim] + hidden_dims, hidden_dims + [output_dim]))
+        n_layers = 1 + len(hidden_dims)
+        self.network = nn.Sequential(*[
+            FullyConnectedLayer(
+                input_dim=i, output_dim=j,
+                activation=hidden_activation if (layer < n_layers - 1) else output_activation,
+                use_batch_norm=use_batch_norm if ((layer < n_layers - 1) or norm_output) else False,
+                use_layer_norm=use_layer_norm if ((layer < n_layers - 1) or norm_output) else False,
+                dropout_rate=None if ((layer == 0) and not dropout_input) else dropout_rate)
+            for layer, (i, j) in enumerate(dims)])
+
+    def forward(self, x: torch.Tensor):
+        return self.network(x)
+
+
+def transform_input(x: torch.Tensor, transform: Optional[str], eps: float = 1e-5) -> torch.Tensor:
+    """Dense-tensor version of the reference's transform_input (vae/encoder.py:343-381)."""
+    if transform is None:
+        return x
+    if transform == "log":
+        return x.log1p()
+    if transform == "normalize":
+        return x / (x.sum(dim=-1, keepdim=True) + eps)
+    if transform == "normalize_log":
+        x = x.log1p()
+        return x / (x.sum(dim=-1, keepdim=True) + eps)
+    if transform == "log_normalize":
+        return (x / (x.sum(dim=-1, keepdim=True) + eps)).log1p()
+    raise NotImplementedError("Specified an input transform that is not supported.  Choose from 'log' or 'normalize'.")
+
+
+def _as_inputs(x, n_genes: int, chi_ambient=None, d_empty_loc=None) -> EncoderInputs:
+    """Accept either EncoderInputs (hot path) or a dense count tensor (reference call signature)."""
+    if isinstance(x, EncoderInputs):
+        return x
+    x = x.reshape(-1, n_genes).float()
+    xn = transform_input(x, "normalize")
+    if chi_ambient is not None and d_empty_loc is not None:
+        amb = d_empty_loc.exp().detach() * chi_ambient.detach()
+        dot = (x * (amb / torch.linalg.vector_norm(amb))).sum(-1)
+    else:
+        dot = torch.zeros(x.shape[0], device=x.device)
+    feats = torch.stack([x.sum(-1), (x > 0).sum(-1).float(), dot, x.max(-1).values], dim=1)
+    return EncoderInputs(xn, xn.log1p(), feats, n_genes)
+
+
+class EncodeZ(FullyConnectedNetwork):
+    """Gene expression -> latent z (loc, scale).  Reference vae/encoder.py:55-125."""
+
+    def __init__(self, input_dim: int, hidden_dims: List[int], output_dim: int, input_transform: Optional[str] = None,
+                 **kwargs):
+        assert len(hidden_dims) > 0, "EncodeZ needs to have at least one hidden layer"
+        super().__init__(input_dim=input_dim, hidden_dims=hidden_dims[:-1], output_dim=hidden_dims[-1],
+                         hidden_activation=nn.Softplus(), output_activation=nn.Softplus(), norm_output=True, **kwargs)
+        self.transform = input_transform
+        self.input_dim = input_dim
+        self.output_dim = output_dim
+        self.loc_out = nn.Linear(hidden_dims[-1], output_dim)
+        self.sig_out = nn.Linear(hidden_dims[-1], output_dim)
+
+    def forward(self, x, **kwargs) -> Dict[str, torch.Tensor]:
+        inp = _as_inputs(x, self.input_dim)
+        assert self.transform == "normalize", "the B200 path implements input_transform='normalize' (run.py:707)"
+        first = self.network[0].layer
+        lin = first[0]
+        h = linear_big(inp.x_norm, lin.weight, lin.bias, n_in=self.input_dim)
+        for mod in list(first)[1:]:
+            h = mod(h)
+        for layer in list(self.network)[1:]:
+            h = layer(h)
+        loc = self.loc_out(h)
+        scale = torch.exp(self.sig_out(h))
+        return {"loc": loc.squeeze(), "scale": scale.squeeze()}
+
+
+class EncodeNonZLatents(nn.Module):
+    """Gene expression -> (logit cell probability, cell size, epsilon).  Reference vae/encoder.py:132-340.
+    ``d_empty_loc_fn`` replaces the reference's ``pyro.param("d_empty_loc")`` lookups (encoder.py:262,268,330):
+    it is set by the model object to return the current parameter value."""
+
+    def __init__(self, n_genes: int, z_dim: int, log_count_crossover: float, prior_log_cell_counts: float,
+                 empty_log_count_threshold: float, prior_logit_cell_prob: float, input_transform: Optional[str] = None):
+        super().__init__()
+        self.n_genes = n_genes
+        self.z_dim = z_dim
+        self.transform = input_transform
+        self.output_dim = 1
+        self.INITIAL_WEIGHT_FOR_LOG_COUNTS = 1.0
+        self.P_OUTPUT_SCALE = 5.0
+        self.log_count_crossover = log_count_crossover
+        self.empty_log_count_threshold = empty_log_count_threshold
+        self.prior_log_cell_counts = prior_log_cell_counts
+        self.prior_logit_cell_prob = prior_logit_cell_prob
+        self.EPS_OUTPUT_SCALE = 0.2
+        self.EPS_OUTPUT_MEAN = 0.6931
+        additional_features_p = 4
+        self.layer1 = nn.Linear(additional_features_p + self.n_genes, 512)
+        self.batchnorm1 = nn.BatchNorm1d(num_features=512)
+        self.layer2 = nn.Linear(additional_features_p + 512, 512)
+        self.batchnorm2 = nn.BatchNorm1d(num_features=512)
+        self.layer3 = nn.Linear(additional_features_p + 512, 1)
+        additional_features_eps = 4
+        self.eps_network = nn.Sequential(
+            nn.Linear(additional_features_eps + self.n_genes, 512), nn.BatchNorm1d(num_features=512), nn.Softplus(),
+            nn.Linear(512, 512), nn.BatchNorm1d(num_features=512), nn.Softplus(), nn.Linear(512, 1))
+        self.softplus = nn.Softplus()
+        self.dropout50 = nn.Dropout1d(p=0.5)
+        self.offset: Optional[dict] = None
+        self.x_scaling = None
+        self.batchnorm0 = nn.BatchNorm1d(num_features=self.n_genes)
+        self.d_empty_loc_fn = None  # callable -> 0-dim tensor (set by RemoveBackgroundPyroModel)
+
+    def _d_empty_loc(self, device):
+        if self.d_empty_loc_fn is None:
+            raise RuntimeError("EncodeNonZLatents.d_empty_loc_fn is not set (the model object sets it)")
+        return self.d_empty_loc_fn().detach().to(device)
+
+    def forward(self, x, chi_ambient: Optional[torch.Tensor], z: torch.Tensor, row_keep_scale: Optional[torch.Tensor] = None,
+                **kwargs) -> Dict[str, torch.Tensor]:
+        assert self.transform == "log_normalize", "the B200 path implements input_transform='log_normalize' (run.py:717)"
+        G = self.n_genes
+        d_empty_loc = self._d_empty_loc(z.device) if chi_ambient is not None else None
+        inp = _as_inputs(x, G, chi_ambient, d_empty_loc)
+        counts = inp.feats[:, 0:1]
+        log_sum = counts.log1p()
+        log_nnz = inp.feats[:, 1:2].log1p()
+        if chi_ambient is not None:
+            overlap = -0.5 * (torch.clamp(log_sum - d_empty_loc, min=0.0) / 0.1).pow(2)
+            eps_overlap = inp.feats[:, 2:3]
+        else:
+            overlap = torch.zeros_like(counts)
+            eps_overlap = torch.zeros_like(counts)
+
+        # BatchNorm over genes + Dropout1d(0.5), which on a 2-D input drops whole droplet rows (torch 2.11).
+        xt = inp.x_lognorm[:, :G]
+        x_in = self.batchnorm0(xt)
+        if self.training:
+            if row_keep_scale is None:
+                row_keep_scale = torch.bernoulli(torch.full((xt.shape[0],), 0.5, device=xt.device)) * 2.0
+            x_in = x_in * row_keep_scale.unsqueeze(-1)
+        znorm = torch.linalg.vector_norm(z.detach().reshape(xt.shape[0], -1), ord=2, dim=-1, keepdim=True)
+        p_feat = torch.cat((log_sum, log_nnz, overlap, znorm), dim=-1)
+        e_feat = torch.cat((log_sum, log_nnz, eps_overlap, znorm), dim=-1)
+
+        def first_layer(lin: nn.Linear, feat):
+            # Linear(cat(feat, x_in)) split into the large gene block and the 4 feature columns
+            return linear_big(x_in, lin.weight, lin.bias, n_in=G, col_offset=4) + feat @ lin.weight[:, :4].t()
+
+        x_ = self.softplus(self.batchnorm1(first_layer(self.layer1, p_feat)))
+        x_ = self.softplus(self.batchnorm2(self.layer2(torch.cat((p_feat, x_), dim=-1))))
+        p_out = self.layer3(torch.cat((p_feat, x_), dim=-1)).squeeze(-1)
+
+        e = self.eps_network[0]
+        h = first_layer(e, e_feat)
+        for mod in list(self.eps_network)[1:]:
+            h = mod(h)
+        eps_out = h.squeeze(-1)
+
+        ls = log_sum.squeeze(-1)
+        if self.offset is None:
+            self.offset = dict()
+            cells = ls > self.log_count_crossover
+            assert cells.sum() > 4, "Fewer than 4 cells passed to encoder minibatch"
+            self.offset["logit_p"] = p_out.mean().item()
+            self.offset["epsilon"] = eps_out[cells].mean().item()
+
+        dlt = ls - self.log_count_crossover
+        p_y_logit = (p_out - self.offset["logit_p"]) + dlt.abs().pow(0.5) * torch.sign(dlt) * 10.0
+        beta = 50.0
+        alpha = (beta * (ls - self.prior_log_cell_counts)).sigmoid()
+        p_y_logit = (1.0 - alpha) * p_y_logit + alpha * consts.REG_LOGIT_MEAN
+        alpha_empty = (beta * (ls - self.empty_log_count_threshold)).sigmoid()
+        p_y_logit = alpha_empty * p_y_logit + (1.0 - alpha_empty) * (-1 * consts.REG_LOGIT_MEAN)
+
+        epsilon = 2.0 * (eps_out * self.EPS_OUTPUT_SCALE - 1.0986122886681098).sigmoid() + 0.5
+        d_empty = self._d_empty_loc(z.device).exp() if chi_ambient is not None else torch.zeros((), device=z.device)
+        d_loc = (self.softplus((self.softplus(counts.squeeze(-1) / (epsilon + 1e-2) - d_empty) + 1e-10).log()
+                               - self.log_count_crossover) + self.log_count_crossover)
+        return {"p_y": p_y_logit, "d_loc": d_loc, "epsilon": epsilon}
+
+
+class CompositeEncoder(dict):
+    """Several encoders run on the same input (reference vae/encoder.py:11-52)."""
+
+    def __init__(self, module_dict):
+        super().__init__(module_dict)
+        self.module_dict = module_dict
+
+    def __call__(self, **kwargs):
+        return self.forward(**kwargs)
+
+    def forward(self, **kwargs) -> Dict[str, torch.Tensor]:
+        out = dict()
+        out["z"] = self.module_dict["z"].forward(**kwargs)
+        for key, value in self.module_dict.items():
+            if key == "z":
+                continue
+            out[key] = value.forward(**kwargs, z=out["z"]["loc"].detach())
+            if key == "other":
+                for subkey, v in out[key].items():
+                    out[subkey] = v
+                del out[key]
+        return out
+
+
+class Decoder(FullyConnectedNetwork):
+    """Latent z -> fractional expression chi (softmax).  Reference vae/decoder.py:6-47."""
+
+    def __init__(self, input_dim: int, **kwargs):
+        super().__init__(input_dim=input_dim, **kwargs)
+        self.input_dim = input_dim
+        self.softmax = nn.Softmax(dim=-1)
+
+    def hidden(self, z: torch.Tensor) -> torch.Tensor:
+        """Everything before the final 512 -> G Linear."""
+        h = z
+        for layer in list(self.network)[:-1]:
+            h = layer(h)
+        return h
+
+    @property
+    def out_linear(self) -> nn.Linear:
+        return self.network[-1].layer[0]
+
+    def logits(self, z: torch.Tensor) -> torch.Tensor:
+        lin = self.out_linear
+        return linear_big(self.hidden(z), lin.weight, lin.bias, n_in=lin.in_features, wide_output=True)
+
+    def forward(self, z: torch.Tensor) -> torch.Tensor:
+        return self.softmax(self.logits(z))

@@ -1,0 +1,177 @@
+"""-m gpu parity of the whole per-minibatch ELBO (value of every term, gradient of every parameter) against the
+oracle restatement, with identical base noise on both sides; plus training-loop behaviour."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import elbo as oelbo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _small_dataset(seed=0, n_genes=96):
+    from cellbender_b200 import synth
+
+    sim = synth.simulate_dataset(n_genes=n_genes, cells_of_each_type=[25, 25], n_droplets=600, cell_mean_umi=2000.0,
+                                 empty_mean_umi=60.0, dirichlet_alpha=0.5, seed=seed, device="cpu", cell_chunk=64)
+    return synth.prepare_dataset(sim, expected_cells=50, total_droplets_included=150)
+
+
+def _setup(model_type="full", epochs=3):
+    from cellbender_b200 import run
+
+    ds = _small_dataset()
+    args = run.default_args(epochs=epochs, z_dim=8, z_hidden_dims=[32], model=model_type)
+    model, opt, svi, train_loader, test_loader = run.setup_inference(ds, args, device=DEV)
+    return ds, args, model, opt, svi, train_loader, test_loader
+
+
+def _oracle_inputs(model, offset):
+    params, buffers = {}, {}
+    for pre, mod in (("enc_z.", model.encoder["z"]), ("enc_o.", model.encoder["other"]), ("dec.", model.decoder)):
+        for k, v in mod.named_parameters():
+            params[pre + k] = v.detach().double().cpu().clone().requires_grad_(True)
+        for k, v in mod.named_buffers():
+            buffers[pre + k] = v.detach().double().cpu().clone()
+    for k, v in model.param_store.unconstrained.items():
+        params["ps." + k] = v.detach().double().cpu().clone().requires_grad_(True)
+    enc_o = model.encoder["other"]
+    cfg = dict(chi_bar=model.avg_gene_expression.double().cpu(), log_count_crossover=enc_o.log_count_crossover,
+               prior_log_cell_counts=float(enc_o.prior_log_cell_counts),
+               empty_log_count_threshold=float(enc_o.empty_log_count_threshold), offset=offset,
+               d_cell_loc_prior=float(model.d_cell_loc_prior), d_cell_scale_prior=float(model.d_cell_scale_prior),
+               epsilon_prior=float(model.epsilon_prior), phi_conc_prior=float(model.phi_conc_prior),
+               phi_rate_prior=float(model.phi_rate_prior), rho_alpha_prior=float(model.rho_alpha_prior),
+               rho_beta_prior=float(model.rho_beta_prior), d_empty_loc_prior=float(model.d_empty_loc_prior),
+               d_empty_scale_prior=float(model.d_empty_scale_prior), empty_UMI_threshold=float(model.empty_UMI_threshold),
+               p_logit_prior=float(model.p_logit_prior))
+    return params, buffers, cfg
+
+
+def _product_param_grads(model):
+    out = {}
+    for pre, mod in (("enc_z.", model.encoder["z"]), ("enc_o.", model.encoder["other"]), ("dec.", model.decoder)):
+        for k, v in mod.named_parameters():
+            out[pre + k] = None if v.grad is None else v.grad.detach().double().cpu()
+    for k, v in model.param_store.unconstrained.items():
+        out["ps." + k] = None if v.grad is None else v.grad.detach().double().cpu()
+    return out
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_elbo_terms_and_gradients_match_oracle(training):
+    ds, args, model, opt, svi, train_loader, _ = _setup()
+    batch = next(iter(train_loader))
+    model.train()
+    with torch.no_grad():
+        svi.loss_terms(batch)  # first forward fixes the encoder's offset heuristics (encoder.py:300-309)
+    offset = dict(model.encoder["other"].offset)
+    model.train(training)
+    B, Z = batch.size(0), model.z_dim
+    g = torch.Generator().manual_seed(5)
+    keep = (torch.bernoulli(torch.full((B,), 0.5), generator=g) * 2.0) if training else None
+
+    # concentrations at which gamma / beta base samples are drawn (needs the encoder's epsilon)
+    inp = batch.encoder_inputs(svi._ambient_unit_vector())
+    with torch.no_grad():
+        enc0 = model.encoder(x=inp, chi_ambient=model.param_store["chi_ambient"].detach(), cell_prior_log=model.d_cell_loc_prior,
+                             row_keep_scale=None if keep is None else keep.to(DEV))
+        prob0 = enc0["p_y"].sigmoid()
+        ps = model.param_store
+        conc = {"phi": (ps["phi_loc"] ** 2 / ps["phi_scale"] ** 2).cpu(),
+                "epsilon": ((prob0 * enc0["epsilon"] + 1 - prob0) * model.epsilon_prior).cpu(),
+                "rho_alpha": ps["rho_alpha"].cpu(), "rho_beta": ps["rho_beta"].cpu()}
+    noise = oelbo.draw_noise(B, Z, conc, generator=g)
+
+    def sampler(inp_, enc):
+        n = {k: v.to(DEV) for k, v in noise.items()}
+        ps_ = model.param_store
+        pl, psc = ps_["phi_loc"], ps_["phi_scale"]
+        prob = enc["p_y"].sigmoid().detach()
+        return {
+            "phi": oelbo.gamma_rsample(pl ** 2 / psc ** 2, pl / psc ** 2, n["phi"]),
+            "rho": oelbo.beta_rsample(ps_["rho_alpha"], ps_["rho_beta"], n["rho"]),
+            "d_empty": torch.exp(ps_["d_empty_loc"] + ps_["d_empty_scale"] * n["d_empty"]),
+            "p_logit_reg": enc["p_y"] + 2.0 * n["p_logit_reg"],
+            "z": enc["z"]["loc"] + enc["z"]["scale"] * n["z"],
+            "d_cell": torch.exp(prob * enc["d_loc"] + (1 - prob) * model.d_cell_loc_prior + ps_["d_cell_scale"] * n["d_cell"]),
+            "epsilon": oelbo.gamma_rsample((prob * enc["epsilon"] + 1 - prob) * model.epsilon_prior, model.epsilon_prior,
+                                           n["epsilon"]),
+        }
+
+    opt.zero_grad()
+    terms = model.elbo_terms(batch.loader.csr, batch.row_ids, inp, sampler=sampler,
+                             row_keep_scale=None if keep is None else keep.to(DEV))
+    terms["loss"].backward()
+    model.check_nan()
+    got = _product_param_grads(model)
+
+    params, buffers, cfg = _oracle_inputs(model, offset)
+    x = batch.dense().double().cpu()
+    ref = oelbo.elbo(x, params, buffers, cfg, {k: v.double() for k, v in noise.items()},
+                     None if keep is None else keep.double(), training=training, likelihood="mp")
+    ref["loss"].backward()
+
+    names = [k for k in ref if not k.startswith("_")]
+    for k in names:
+        a, b = float(terms[k].detach()), float(ref[k].detach())
+        # the small KL-type terms are sums of large cancelling fp32 pieces (e.g. 50 log 50 per droplet in
+        # Gamma.log_prob) evaluated with the very torch.distributions calls the reference makes, so their fp32
+        # rounding (~1e-3 absolute) is the reference's own; the observation term and the total get 1e-5 relative.
+        tol = 1e-5 * max(abs(b), 1.0) + (0.0 if k in ("obs", "loss") else 3e-3)
+        assert abs(a - b) <= tol, (k, a, b)
+    assert abs(float(terms["loss"].detach()) - float(ref["loss"].detach())) <= 1e-5 * abs(float(ref["loss"].detach()))
+    worst = {}
+    for k, p in params.items():
+        if p.grad is None:
+            assert got[k] is None or float(got[k].abs().max()) == 0.0, k
+            continue
+        assert got[k] is not None, f"product has no gradient for {k}"
+        scale = float(p.grad.abs().max())
+        err = float((got[k] - p.grad).abs().max())
+        worst[k] = err / max(scale, 1e-6)
+        assert err <= 2e-3 * scale + 2e-4, (k, err, scale)  # atol: biases feeding a BatchNorm have zero true gradient
+    assert len(worst) >= 30  # every encoder / decoder / param-store tensor was compared
+
+
+def test_training_reduces_loss_and_matches_oracle_optimizer_trajectory():
+    """A few epochs on the small dataset: loss goes down, LR follows OneCycle, parameters move, no NaN; the
+    extra-step behaviour of the scheduler is the reference's (tests/test_train.py:87-108)."""
+    from cellbender_b200 import train
+
+    ds, args, model, opt, svi, train_loader, test_loader = _setup(epochs=4)
+    n_batches = len(train_loader)
+    assert opt.total_steps == n_batches * 4
+    assert abs(opt.get_last_lr()[0] - args.learning_rate * 10 / 25) < 1e-12  # starts at max_lr / 25
+    p0 = opt.flat_p.clone()
+    elbo_train, elbo_test = train.run_training(model, svi, train_loader, test_loader, epochs=4, test_freq=2)
+    assert len(elbo_train) == 4 and len(elbo_test) == 2
+    assert all(np.isfinite(elbo_train)) and elbo_train[-1] > elbo_train[0]
+    assert float((opt.flat_p - p0).abs().max()) > 0
+    assert opt.host_steps == n_batches * 4 and int(opt.step_count.item()) == opt.host_steps
+    assert abs(max(opt._lrs) - args.learning_rate * 10) < 1e-9
+    with pytest.raises(ValueError):
+        svi.step(next(iter(train_loader)))  # one step beyond total_steps raises, like torch's OneCycleLR
+
+
+def test_loader_matches_reference_golden(golden_dir):
+    """Device loader vs the reference DataLoader's own output for the same numpy seed (tests/golden/dataloader.npz)."""
+    import os
+
+    import scipy.sparse as sp
+
+    from cellbender_b200.dataprep import DataLoader
+
+    g = np.load(os.path.join(golden_dir, "dataloader.npz"))
+    dataset, empties = sp.csr_matrix(g["dataset"]), sp.csr_matrix(g["empties"])
+    np.random.seed(1234)
+    loader = DataLoader(dataset, empties, batch_size=16, fraction_empties=0.2, shuffle=True, device=DEV)
+    assert len(loader) == int(g["n_batches"])
+    for epoch in (0, 1):
+        batches = [b.dense().cpu().numpy() for b in loader]
+        assert len(batches) == int(g["n_batches"])
+        for i, b in enumerate(batches):
+            np.testing.assert_array_equal(b, g[f"e{epoch}_b{i}"])
