@@ -21,6 +21,9 @@ _SCALARS = {
 }
 
 
+from ._cabi_counts import LAUNCHES as _LAUNCHES
+
+
 class CabiError(RuntimeError):
     pass
 
@@ -55,6 +58,7 @@ class _Lib:
                 "Build it with `python -m cellbender_b200.build` or `python -c 'import __graft_entry__ as g; g.build()'`."
             )
         self._dll = ctypes.CDLL(LIB_PATH)
+        self.launch_count = 0  # kernels launched through this library (bench.py reports it as gpu_launches)
         self.protos = parse_header()
         for name, (restype, argtypes) in self.protos.items():
             try:
@@ -69,6 +73,7 @@ class _Lib:
 
     def call(self, name: str, *args):
         """Call an int-status entry point; raise CabiError with the library's message on failure."""
+        self.launch_count += _LAUNCHES.get(name, 1)
         rc = getattr(self._dll, name)(*args)
         if rc != 0:
             raise CabiError(f"{name} failed (status {rc}): {self.last_error()}")

@@ -1,0 +1,92 @@
+"""Multi-GPU execution: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch) for the single exchange
+step of training; no collective on the posterior/estimation path until the final gather.  The reference is
+single-GPU only ("CellBender only makes use of 1 GPU", docs/source/troubleshooting/index.rst:399), so this is new
+surface; SURVEY.md section 8e states the semantics.
+
+Training (data parallel): every rank holds the full parameter set and the surely-empty droplets, and a disjoint
+shard of the analysed droplets (``shard_rows``).  Each step every rank runs its own 255-droplet minibatch; the ELBO is
+a plain SUM over droplets (train.py:56-63), so the exchange is ONE all-reduce(SUM) of the flat fp32 gradient buffer
+(69.4 M values at the PBMC8k shape), after which every rank applies the identical fused ClippedAdam update.
+Stated consequences: the global minibatch is 255 x world_size droplets; an epoch is n_batches(shard) steps, so
+OneCycleLR's total_steps shrinks by world_size; BatchNorm statistics, Dropout1d masks, epsilon medians and the
+reparameterisation noise are per-rank (different CUDA seeds per rank); the encoder's first-forward offset heuristic
+(encoder.py:300-309) is computed on rank 0 and broadcast.
+
+Posterior / estimation: ``shard_cells`` splits the p > 0.5 cell list into contiguous ranges; ranks compute their COO
+pieces independently (``Posterior.device_posterior(cell_subset=...)``) and ``gather_posterior`` concatenates them.
+MCKP needs all cells of a gene, so it runs on the gathered COO (one gene-keyed exchange = the gather itself).
+"""
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_rows(n_rows: int, rank: int, world_size: int) -> np.ndarray:
+    """Strided shard: droplets are sorted by UMI count, so striding keeps the cell / empty mix of every shard equal."""
+    return np.arange(rank, n_rows, world_size)
+
+
+def shard_cells(n_cells: int, rank: int, world_size: int) -> np.ndarray:
+    """Contiguous range of the cell list (keeps each rank's COO piece in (m, c) order)."""
+    bounds = np.linspace(0, n_cells, world_size + 1).astype(np.int64)
+    return np.arange(bounds[rank], bounds[rank + 1])
+
+
+def attach(svi, world_size: int):
+    """Make ``svi.step`` data-parallel: all-reduce(SUM) the flat gradient buffer between backward and the optimizer."""
+    if world_size <= 1:
+        return svi
+    opt = svi.optim
+    base_collect = opt.collect_grads
+    rank = dist.get_rank()
+    torch.manual_seed(1234 + 104729 * rank)
+    torch.cuda.manual_seed(1234 + 104729 * rank)
+
+    def collect_and_reduce():
+        base_collect()
+        dist.all_reduce(opt.flat_g, op=dist.ReduceOp.SUM)
+
+    opt.collect_grads = collect_and_reduce
+    svi.sync_offsets = lambda: broadcast_encoder_offsets(svi.model)
+    return svi
+
+
+def broadcast_encoder_offsets(model):
+    enc = model.encoder["other"]
+    vals = [0.0, 0.0] if enc.offset is None else [enc.offset["logit_p"], enc.offset["epsilon"]]
+    t = torch.tensor(vals, dtype=torch.float64, device=model.device)
+    dist.broadcast(t, src=0)
+    enc.offset = {"logit_p": float(t[0]), "epsilon": float(t[1])}
+
+
+def gather_posterior(piece, world_size: int):
+    """All-gather the ranks' DevicePosteriorCOO pieces (variable length) and concatenate in rank order."""
+    from .estimation import DevicePosteriorCOO
+
+    if world_size <= 1:
+        return piece
+    dev = piece.m.device
+    sizes = torch.tensor([piece.m.numel(), piece.off_m.numel()], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world_size)]
+    dist.all_gather(all_sizes, sizes)
+    n_max = int(max(s[0] for s in all_sizes))
+    o_max = int(max(s[1] for s in all_sizes))
+
+    def gather(t: torch.Tensor, n_pad: int, counts: List[int]):
+        buf = torch.zeros(n_pad, dtype=t.dtype, device=dev)
+        buf[: t.numel()] = t
+        outs = [torch.zeros_like(buf) for _ in range(world_size)]
+        dist.all_gather(outs, buf)
+        return torch.cat([o[:c] for o, c in zip(outs, counts)])
+
+    nc = [int(s[0]) for s in all_sizes]
+    oc = [int(s[1]) for s in all_sizes]
+    out = DevicePosteriorCOO(gather(piece.m, n_max, nc), gather(piece.c, n_max, nc), gather(piece.log_prob, n_max, nc),
+                             gather(piece.off_m, o_max, oc), gather(piece.off_v, o_max, oc), piece.n_cols)
+    out.ensure_sorted()
+    if out.off_m.numel() > 1:
+        o = torch.argsort(out.off_m)
+        out.off_m, out.off_v = out.off_m[o].contiguous(), out.off_v[o].contiguous()
+    return out

@@ -273,3 +273,8 @@ def posterior_coo(csr: DeviceCSR, cell_rows, logits, lse, chi_ambient, chi_bar, 
     L.call("cb_posterior_compact", n_entries, int(n_counts_max), ptr(entry_m), ptr(logp), ptr(low), ptr(keep),
            ptr(keep_pos), ptr(off_pos), float(log_thresh), ptr(coo_m), ptr(coo_c), ptr(coo_lp), ptr(off_m), ptr(off_v), st)
     return coo_m, coo_c, coo_lp, off_m, off_v
+
+
+def gather_feats(csr: DeviceCSR, row_ids: torch.Tensor, amb_unit: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-droplet features only ([B, 4]: sum, nnz, dot with amb_unit, max) -- no dense rows are written."""
+    return gather_rows(csr, row_ids, amb_unit, want=())["feats"]

@@ -1,0 +1,257 @@
+"""Posterior generation on the GPU behind the reference's ``Posterior`` interface (reference
+cellbender/remove_background/posterior.py:170-980): same constructor, same ``latents_map`` /
+``cell_noise_count_posterior_coo(**kwargs)`` / ``compute_denoised_counts(estimator_constructor, **kwargs)`` methods,
+same return types (scipy COO keyed by m = n * G_all + g plus the offsets dict).
+
+Differences in HOW:
+  * the encoder runs once per cell chunk, not once per latent sample (it is deterministic in eval mode);
+  * all S latent samples of a chunk go through ONE decoder GEMM ([S * cells, 512] x [512, G]);
+  * the noise-count log-probability is evaluated only at stored counts, with the sample average kept in registers
+    (csrc/posterior.cu), and the COO is emitted on the device already in the reference's (m, c) order;
+  * the estimators consume the device-resident COO directly (estimation.DevicePosteriorCOO).
+Monte-Carlo noise: torch's CUDA generator instead of pyro's trace order, so individual draws differ from a pyro run;
+the distribution they are drawn from is the guide's (model.py:506-567), and y is fixed to its MAP (y_map=True).
+"""
+import logging
+from typing import Dict, Optional
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+from torch.distributions import Beta, Gamma, LogNormal, Normal
+
+from . import consts, ops
+from .estimation import DevicePosteriorCOO, EstimationMethod, IndexConverter
+from .model import RemoveBackgroundPyroModel
+from .vae import EncoderInputs
+
+logger = logging.getLogger("cellbender")
+
+
+def csr_set_rows_to_zero(csr: sp.csr_matrix, row_inds) -> sp.csr_matrix:
+    """reference sparse_utils.py:58-73 (vectorised)."""
+    csr = csr.tocsr(copy=True)
+    row_inds = np.fromiter(row_inds, dtype=np.int64) if not isinstance(row_inds, np.ndarray) else row_inds
+    mask = np.zeros(csr.shape[0], dtype=bool)
+    mask[row_inds] = True
+    csr.data[np.repeat(mask, np.diff(csr.indptr))] = 0
+    csr.eliminate_zeros()
+    return csr
+
+
+class Posterior:
+    """Posterior on latent variables and denoised counts (reference posterior.py:170-237)."""
+
+    def __init__(self, dataset_obj, vi_model: Optional[RemoveBackgroundPyroModel], posterior_batch_size: int = 128,
+                 counts_dtype: np.dtype = np.dtype(np.uint32), float_threshold: Optional[float] = 0.5, debug: bool = False,
+                 cells_per_chunk: int = 512):
+        self.dataset_obj = dataset_obj
+        self.vi_model = vi_model
+        if vi_model is not None:
+            vi_model.eval()
+            vi_model.encoder["z"].eval()
+            vi_model.encoder["other"].eval()
+            vi_model.decoder.eval()
+        self.use_cuda = True
+        self.device = "cuda" if vi_model is None else vi_model.device
+        self.analyzed_gene_inds = None if dataset_obj is None else dataset_obj.analyzed_gene_inds
+        self.count_matrix_shape = None if dataset_obj is None else dataset_obj.matrix.shape
+        self.barcode_inds = None if self.count_matrix_shape is None else np.arange(0, self.count_matrix_shape[0])
+        self.dtype = counts_dtype
+        self.debug = debug
+        self.float_threshold = float_threshold
+        self.posterior_batch_size = posterior_batch_size
+        self.cells_per_chunk = cells_per_chunk
+        self._noise_count_posterior_coo: Optional[sp.coo_matrix] = None
+        self._noise_count_posterior_kwargs: Optional[dict] = None
+        self._noise_count_posterior_coo_offsets: Optional[Dict[int, int]] = None
+        self._noise_count_regularized_posterior_coo = None
+        self._noise_count_regularized_posterior_kwargs = None
+        self._device_posterior: Optional[DevicePosteriorCOO] = None
+        self._latents: Optional[Dict[str, np.ndarray]] = None
+        self._csr: Optional[ops.DeviceCSR] = None
+        if dataset_obj is not None:
+            self.index_converter = IndexConverter(total_n_cells=self.count_matrix_shape[0],
+                                                  total_n_genes=self.count_matrix_shape[1])
+
+    # ---- device-resident analysed count matrix -------------------------------------------------------------
+    def _device_csr(self) -> ops.DeviceCSR:
+        if self._csr is None:
+            self._csr = ops.DeviceCSR.from_scipy(self.dataset_obj.get_count_matrix(), self.device)
+        return self._csr
+
+    def _amb_unit(self) -> torch.Tensor:
+        chi = self.vi_model.param_store["chi_ambient"].detach()
+        return (chi / torch.linalg.vector_norm(chi)).contiguous()
+
+    def _encode(self, rows: torch.Tensor):
+        csr = self._device_csr()
+        out = ops.gather_rows(csr, rows, self._amb_unit(), want=("norm", "lognorm"))
+        inp = EncoderInputs(out["norm"], out["lognorm"], out["feats"], csr.n_genes)
+        m = self.vi_model
+        enc = m.encoder(x=inp, chi_ambient=m.param_store["chi_ambient"].detach(), cell_prior_log=m.d_cell_loc_prior)
+        return inp, enc
+
+    # ---- latents (posterior.py:861-917) ----------------------------------------------------------------------
+    @property
+    def latents_map(self) -> Dict[str, np.ndarray]:
+        if self._latents is None:
+            self._get_latents_map()
+        return self._latents
+
+    @torch.no_grad()
+    def _get_latents_map(self):
+        if self.vi_model is None:
+            self._latents = {"z": None, "d": None, "p": None, "phi_loc_scale": None, "epsilon": None}
+            return None
+        m = self.vi_model
+        n = self._device_csr().shape[0]
+        z = torch.empty((n, m.encoder["z"].output_dim), device=self.device)
+        d, p, eps = (torch.empty(n, device=self.device) for _ in range(3))
+        d_cell_scale = m.param_store["d_cell_scale"]
+        for start in range(0, n, 500):
+            rows = torch.arange(start, min(n, start + 500), device=self.device)
+            _, enc = self._encode(rows)
+            sl = slice(start, start + rows.numel())
+            z[sl] = enc["z"]["loc"].reshape(rows.numel(), -1)
+            d[sl] = LogNormal(loc=enc["d_loc"], scale=d_cell_scale).mean
+            p[sl] = enc["p_y"].sigmoid()
+            eps[sl] = Gamma(enc["epsilon"] * m.epsilon_prior, m.epsilon_prior).mean
+        self._latents = {"z": z.double().cpu().numpy(), "d": d.double().cpu().numpy(), "p": p.double().cpu().numpy(),
+                         "phi_loc_scale": [m.param_store["phi_loc"].item(), m.param_store["phi_scale"].item()],
+                         "epsilon": eps.double().cpu().numpy()}
+
+    # ---- noise-count posterior (posterior.py:388-594, 669-859) -----------------------------------------------
+    def cell_noise_count_posterior_coo(self, **kwargs) -> sp.coo_matrix:
+        if (self._noise_count_posterior_coo is None) or (kwargs != self._noise_count_posterior_kwargs):
+            self._get_cell_noise_count_posterior_coo(**kwargs)
+            self._noise_count_posterior_kwargs = kwargs
+        return self._noise_count_posterior_coo
+
+    @torch.no_grad()
+    def sample_rate_coefficients(self, enc: Dict[str, torch.Tensor], n_samples: int, y_map: bool = True):
+        """S latent draws from the guide for a chunk of B droplets (sample_mu_lambda_alpha, posterior.py:737-782,
+        with the model's returned quantities in factored form: mu = a_mu * chi(z), lam = c_a * chi_ambient + c_b *
+        chi_bar, alpha = 1 / phi).  NOTE the reference returns the lambda of the empty-droplet regulariser block
+        (epsilon = 1, y = 0; model.py:385-393,445), reproduced here."""
+        if not y_map:
+            raise NotImplementedError("only y_map=True (the value the reference's pipeline uses) is supported")
+        m, ps = self.vi_model, self.vi_model.param_store
+        B, S = enc["p_y"].shape[0], n_samples
+        phi_loc, phi_scale = ps["phi_loc"], ps["phi_scale"]
+        phi = Gamma(phi_loc.pow(2) / phi_scale.pow(2), phi_loc / phi_scale.pow(2)).sample((S,))
+        rho = Beta(ps["rho_alpha"], ps["rho_beta"]).sample((S, B)) if m.include_rho else torch.zeros((S, B), device=self.device)
+        d_empty = LogNormal(ps["d_empty_loc"], ps["d_empty_scale"]).sample((S, B))
+        z = Normal(enc["z"]["loc"].reshape(B, -1), enc["z"]["scale"].reshape(B, -1)).sample((S,))
+        prob = enc["p_y"].sigmoid()
+        d_cell = LogNormal(prob * enc["d_loc"] + (1 - prob) * m.d_cell_loc_prior, ps["d_cell_scale"]).sample((S,))
+        epsilon = Gamma((prob * enc["epsilon"] + (1 - prob)) * m.epsilon_prior, m.epsilon_prior).sample((S,))
+        y = (enc["p_y"] > 0).float().expand(S, B)
+        if m.model_type == "full":
+            a_mu, c_a, c_b = (1 - rho) * y * epsilon * d_cell, (1 - rho) * d_empty, rho * d_empty
+        elif m.model_type == "swapping":
+            a_mu, c_a, c_b = (1 - rho) * y * epsilon * d_cell, torch.zeros_like(rho), rho * d_empty
+        else:  # ambient
+            a_mu, c_a, c_b = y * epsilon * d_cell, d_empty, torch.zeros_like(d_empty)
+        return z, a_mu, c_a, c_b, phi.reciprocal()
+
+    @torch.no_grad()
+    def _get_cell_noise_count_posterior_coo(self, n_samples: int = 20, y_map: bool = True, n_counts_max: int = 20,
+                                            smallest_log_probability: float = -10.0) -> sp.coo_matrix:
+        dev_post = self.device_posterior(n_samples=n_samples, y_map=y_map, n_counts_max=n_counts_max,
+                                         smallest_log_probability=smallest_log_probability)
+        shape = [int(np.prod(self.count_matrix_shape, dtype=np.uint64)), n_counts_max]
+        self._noise_count_posterior_coo = dev_post.to_scipy(shape)
+        self._noise_count_posterior_coo_offsets = dev_post.offsets_dict()
+        return self._noise_count_posterior_coo
+
+    @torch.no_grad()
+    def device_posterior(self, n_samples: int = 20, y_map: bool = True, n_counts_max: int = 20,
+                         smallest_log_probability: float = -10.0, cell_subset: Optional[np.ndarray] = None,
+                         lambda_multiplier: float = 1.0) -> DevicePosteriorCOO:
+        """The posterior COO, computed and left on the device.  ``cell_subset`` (indices into the p > 0.5 cell list)
+        restricts the computation (used for barcode sharding across GPUs)."""
+        m = self.vi_model
+        csr = self._device_csr()
+        G = csr.n_genes
+        cell_logic = self.latents_map["p"] > consts.CELL_PROB_CUTOFF
+        if cell_logic.sum() == 0:
+            logger.error(f"ERROR: Found zero droplets with posterior cell probability > {consts.CELL_PROB_CUTOFF}.")
+            raise RuntimeError("Zero cells found!")
+        cell_rows_all = np.flatnonzero(cell_logic)  # rows of the analysed count matrix
+        # window size per cell: min(n_counts_max, max count inside the reference's minibatch of that cell)
+        feats = []
+        for start in range(0, cell_rows_all.size, 4096):
+            rows = torch.as_tensor(cell_rows_all[start:start + 4096], device=self.device)
+            feats.append(ops.gather_feats(csr, rows)[:, 3])
+        row_max = torch.cat(feats)
+        pb = self.posterior_batch_size
+        n_b = (cell_rows_all.size + pb - 1) // pb
+        padded = torch.zeros(n_b * pb, device=self.device)
+        padded[: row_max.numel()] = row_max
+        group_max = padded.view(n_b, pb).max(dim=1).values
+        # the reference drops a trailing minibatch of < 4 cells (dataprep.py:155-161)
+        n_eff = cell_rows_all.size if (cell_rows_all.size % pb == 0 or cell_rows_all.size % pb >= consts.SMALLEST_ALLOWED_BATCH) \
+            else cell_rows_all.size - cell_rows_all.size % pb
+        n_window_all = torch.clamp(group_max.repeat_interleave(pb)[: cell_rows_all.size], max=float(n_counts_max)).to(torch.int32)
+        sel = np.arange(n_eff) if cell_subset is None else np.asarray(cell_subset)[np.asarray(cell_subset) < n_eff]
+
+        barcode_all = torch.as_tensor(np.asarray(self.dataset_obj.analyzed_barcode_inds)[cell_rows_all].astype(np.int64),
+                                      device=self.device)
+        gene_all = torch.as_tensor(np.asarray(self.analyzed_gene_inds).astype(np.int64), device=self.device)
+        ld = ops.round_up(G, 4)
+        chi_a = torch.zeros(ld, device=self.device)
+        chi_b = torch.zeros(ld, device=self.device)
+        chi_a[:G] = m.param_store["chi_ambient"].detach()
+        chi_b[:G] = m.avg_gene_expression
+        lin = m.decoder.out_linear
+        pieces = []
+        S = n_samples
+        logits = None
+        for start in range(0, sel.size, self.cells_per_chunk):
+            idx = sel[start:start + self.cells_per_chunk]
+            rows = torch.as_tensor(cell_rows_all[idx], device=self.device)
+            Bc = rows.numel()
+            _, enc = self._encode(rows)
+            z, a_mu, c_a, c_b, alpha = self.sample_rate_coefficients(enc, S, y_map=y_map)
+            h = m.decoder.hidden(z.reshape(S * Bc, -1))
+            if logits is None or logits.shape[0] < S * Bc:
+                logits = torch.zeros((S * self.cells_per_chunk, ld), device=self.device)
+            lg = logits[: S * Bc]
+            torch.addmm(lin.bias, h, lin.weight.t(), out=lg[:, :G])  # ONE decoder GEMM for all samples of the chunk
+            lse = ops.row_logsumexp(lg, G)
+            idx_t = torch.as_tensor(idx, device=self.device)
+            pieces.append(ops.posterior_coo(
+                csr, rows, lg, lse, chi_a, chi_b, a_mu.reshape(-1).contiguous(), c_a.reshape(-1).contiguous(),
+                c_b.reshape(-1).contiguous(), alpha.contiguous(), n_window_all[idx_t].contiguous(),
+                barcode_all[idx_t].contiguous(), gene_all, int(self.count_matrix_shape[1]), n_counts_max=n_counts_max,
+                log_thresh=smallest_log_probability, lambda_multiplier=lambda_multiplier))
+        cat = lambda i, dt: torch.cat([p[i] for p in pieces]) if pieces else torch.zeros(0, dtype=dt, device=self.device)
+        post = DevicePosteriorCOO(cat(0, torch.int64), cat(1, torch.int32), cat(2, torch.float32), cat(3, torch.int64),
+                                  cat(4, torch.int32), n_cols=n_counts_max)
+        # barcode indices of the full matrix need not be increasing in cell-list order -> make (m, c) order global
+        post.ensure_sorted()
+        if post.off_m.numel() > 1:
+            o = torch.argsort(post.off_m)
+            post.off_m, post.off_v = post.off_m[o].contiguous(), post.off_v[o].contiguous()
+        if cell_subset is None:
+            self._device_posterior = post
+        return post
+
+    # ---- denoised counts (posterior.py:282-330) --------------------------------------------------------------
+    def compute_denoised_counts(self, estimator_constructor: "type[EstimationMethod]", **kwargs) -> sp.csc_matrix:
+        if self._noise_count_posterior_coo is None and self._device_posterior is None:
+            self.cell_noise_count_posterior_coo()
+        estimator = estimator_constructor(index_converter=self.index_converter)
+        if self._device_posterior is not None:
+            noise_csr = estimator.estimate_noise(noise_log_prob_coo=self._device_posterior, noise_offsets=None, **kwargs)
+        else:
+            noise_csr = estimator.estimate_noise(noise_log_prob_coo=self._noise_count_posterior_coo,
+                                                 noise_offsets=self._noise_count_posterior_coo_offsets, **kwargs)
+        count_matrix = self.dataset_obj.matrix
+        cell_inds = np.asarray(self.dataset_obj.analyzed_barcode_inds)[self.latents_map["p"] > consts.CELL_PROB_CUTOFF]
+        empty_logic = np.ones(count_matrix.shape[0], dtype=bool)
+        empty_logic[cell_inds] = False
+        cell_counts = csr_set_rows_to_zero(csr=count_matrix, row_inds=np.flatnonzero(empty_logic))
+        denoised_counts = cell_counts - noise_csr
+        return denoised_counts.tocsc()
