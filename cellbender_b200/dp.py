@@ -38,17 +38,10 @@ def attach(svi, world_size: int):
     """Make ``svi.step`` data-parallel: all-reduce(SUM) the flat gradient buffer between backward and the optimizer."""
     if world_size <= 1:
         return svi
-    opt = svi.optim
-    base_collect = opt.collect_grads
     rank = dist.get_rank()
     torch.manual_seed(1234 + 104729 * rank)
     torch.cuda.manual_seed(1234 + 104729 * rank)
-
-    def collect_and_reduce():
-        base_collect()
-        dist.all_reduce(opt.flat_g, op=dist.ReduceOp.SUM)
-
-    opt.collect_grads = collect_and_reduce
+    svi.after_backward = lambda opt: dist.all_reduce(opt.flat_g, op=dist.ReduceOp.SUM)
     svi.sync_offsets = lambda: broadcast_encoder_offsets(svi.model)
     return svi
 

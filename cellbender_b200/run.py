@@ -26,7 +26,8 @@ def default_args(**overrides) -> argparse.Namespace:
     d = dict(model="full", epochs=150, z_dim=64, z_hidden_dims=[512], learning_rate=1e-4, training_fraction=0.9,
              fraction_empties=0.2, constant_learning_rate=False, epoch_elbo_fail_fraction=None,
              final_elbo_fail_fraction=None, posterior_batch_size=consts.PROB_POSTERIOR_BATCH_SIZE, fpr=[0.01],
-             estimator="mckp", use_cuda=True, debug=False, checkpoint_min=7.0)
+             estimator="mckp", use_cuda=True, debug=False, checkpoint_min=7.0,
+             use_cuda_graph=True)
     d.update(overrides)
     return argparse.Namespace(**d)
 
@@ -65,6 +66,8 @@ def setup_inference(dataset_obj, args, device: Optional[str] = None, total_epoch
                     rank: int = 0, world_size: int = 1):
     """Everything run_inference builds before training starts (run.py:658-786).  With world_size > 1 every rank
     builds the identical model (same seed) and takes a disjoint shard of the training droplets (see dp.py)."""
+    # the reference switches distribution argument validation off (run.py:659-660); it costs a host sync per check
+    torch.distributions.Distribution.set_default_validate_args(False)
     set_rng_seed(consts.RANDOM_SEED)
     count_matrix = dataset_obj.get_count_matrix()
     model = build_model(dataset_obj, args, device=device)
@@ -82,7 +85,7 @@ def setup_inference(dataset_obj, args, device: Optional[str] = None, total_epoch
     scheduler = get_optimizer(model, n_batches=len(train_loader), batch_size=train_loader.batch_size, epochs=args.epochs,
                               learning_rate=args.learning_rate, constant_learning_rate=args.constant_learning_rate,
                               total_epochs_for_testing_only=total_epochs_for_testing_only)
-    svi = SVI(model, scheduler)
+    svi = SVI(model, scheduler, use_cuda_graph=getattr(args, "use_cuda_graph", True))
     return model, scheduler, svi, train_loader, test_loader
 
 

@@ -23,11 +23,34 @@ from .optim import FlatClippedAdam
 logger = logging.getLogger("cellbender")
 
 
+class _StaticBatch:
+    """Fixed-address stand-in for a MiniBatch (row ids live in a static device buffer) used under CUDA graphs."""
+
+    def __init__(self, loader: DataLoader, n: int, device):
+        self.loader = loader
+        self.n = n
+        self.row_ids = torch.zeros(n, dtype=torch.int64, device=device)
+
+    def size(self, dim: int = 0) -> int:
+        return (self.n, self.loader.csr.n_genes)[dim]
+
+    encoder_inputs = MiniBatch.encoder_inputs
+
+
 class SVI:
-    def __init__(self, model: RemoveBackgroundPyroModel, optim: FlatClippedAdam):
+    """``step`` / ``evaluate_loss`` of pyro's SVI for this model.  With ``use_cuda_graph`` the whole training step
+    (gather -> encoders -> sampling -> decoder -> fused likelihood fwd+bwd -> backward -> fused ClippedAdam) is
+    captured once per minibatch size and replayed: one graph launch instead of ~10^3 kernel launches per step."""
+
+    def __init__(self, model: RemoveBackgroundPyroModel, optim: FlatClippedAdam, use_cuda_graph: bool = False,
+                 graph_warmup: int = 3):
         self.model = model
         self.optim = optim
-        self._amb_unit = None
+        self.use_cuda_graph = use_cuda_graph
+        self.graph_warmup = graph_warmup
+        self._graphs = {}
+        self._eager_steps = 0
+        self.after_backward = None  # hook(optim): e.g. the data-parallel gradient all-reduce (dp.attach)
 
     def _ambient_unit_vector(self) -> torch.Tensor:
         """x_ambient / ||x_ambient||_2 of EncodeNonZLatents.forward (vae/encoder.py:266-270); the d_empty factor
@@ -35,19 +58,63 @@ class SVI:
         chi = self.model.param_store["chi_ambient"].detach()
         return (chi / torch.linalg.vector_norm(chi)).contiguous()
 
-    def loss_terms(self, batch: MiniBatch):
+    def loss_terms(self, batch):
         inp = batch.encoder_inputs(self._ambient_unit_vector())
         return self.model.elbo_terms(batch.loader.csr, batch.row_ids, inp)
 
-    def step(self, batch: MiniBatch) -> torch.Tensor:
-        """One training step; returns the loss (-ELBO, summed over the minibatch) as a 0-dim device tensor."""
+    def _step_eager(self, batch) -> torch.Tensor:
         self.optim.zero_grad()
         terms = self.loss_terms(batch)
         loss = terms["loss"]
         loss.backward()
         self.optim.collect_grads()
+        if self.after_backward is not None:
+            self.after_backward(self.optim)
         self.optim.step()
         return loss.detach()
+
+    def step(self, batch: MiniBatch) -> torch.Tensor:
+        """One training step; returns the loss (-ELBO, summed over the minibatch) as a 0-dim device tensor."""
+        if not self.use_cuda_graph or self.model.encoder["other"].offset is None or self._eager_steps < self.graph_warmup:
+            self._eager_steps += 1  # first steps run eagerly (sets the encoder offsets, warms allocator and cuBLAS)
+            return self._step_eager(batch)
+        key = (id(batch.loader), batch.n, self.model.training)
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = self._capture(batch)
+            self._graphs[key] = entry
+        static, graph, loss = entry
+        static.row_ids.copy_(batch.row_ids)
+        if not self.optim.constant_learning_rate and self.optim.host_steps >= self.optim.total_steps:
+            raise ValueError(f"Tried to step {self.optim.host_steps + 1} times. The specified number of total steps is "
+                             f"{self.optim.total_steps}")
+        graph.replay()
+        self.optim.host_steps += 1
+        return loss
+
+    def _capture(self, batch: MiniBatch):
+        static = _StaticBatch(batch.loader, batch.n, self.model.device)
+        static.row_ids.copy_(batch.row_ids)
+        # the captured step must not change training state twice: snapshot, run warm-up + capture, restore
+        snap_p, snap_m, snap_v = self.optim.flat_p.clone(), self.optim.flat_m.clone(), self.optim.flat_v.clone()
+        snap_step, host_steps = self.optim.step_count.clone(), self.optim.host_steps
+        bn_state = {k: v.clone() for k, v in self.model.state_dict().items() if "running_" in k or "num_batches" in k}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._step_eager(static)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self._step_eager(static)
+        with torch.no_grad():
+            self.optim.flat_p.copy_(snap_p), self.optim.flat_m.copy_(snap_m), self.optim.flat_v.copy_(snap_v)
+            self.optim.step_count.copy_(snap_step)
+            self.optim.host_steps = host_steps
+            sd = self.model.state_dict()
+            for k, v in bn_state.items():
+                sd[k].copy_(v)
+        return static, graph, loss
 
     @torch.no_grad()
     def evaluate_loss(self, batch: MiniBatch) -> torch.Tensor:
