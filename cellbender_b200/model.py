@@ -229,6 +229,10 @@ class RemoveBackgroundPyroModel(nn.Module):
         self.empty_UMI_threshold = scalar(empty_UMI_threshold)
         self.rho_alpha_prior = scalar(rho_alpha_prior)
         self.rho_beta_prior = scalar(rho_beta_prior)
+        # python-float distribution arguments would be host->device copies inside a captured CUDA graph
+        self._k = {"p_logit_scale": scalar(consts.P_LOGIT_SCALE), "reg_logit_mean": scalar(consts.REG_LOGIT_MEAN),
+                   "neg_reg_logit_mean": scalar(-consts.REG_LOGIT_MEAN), "reg_logit_soft_scale": scalar(consts.REG_LOGIT_SOFT_SCALE),
+                   "eps_median_scale": scalar(0.01), "one": scalar(1.0)}
 
         # pyro.param sites (model.py:245-249, 468-513)
         ps = ParamStore()
@@ -281,7 +285,7 @@ class RemoveBackgroundPyroModel(nn.Module):
         if self.include_rho:
             s["rho"] = Beta(ps["rho_alpha"], ps["rho_beta"]).expand([B]).rsample()
         s["d_empty"] = LogNormal(ps["d_empty_loc"], ps["d_empty_scale"]).expand([B]).rsample()
-        s["p_logit_reg"] = Normal(enc["p_y"], consts.P_LOGIT_SCALE).rsample()
+        s["p_logit_reg"] = Normal(enc["p_y"], self._k["p_logit_scale"]).rsample()
         s["z"] = Normal(enc["z"]["loc"], enc["z"]["scale"]).rsample()
         prob = enc["p_y"].sigmoid().detach()
         s["d_cell"] = LogNormal(prob * enc["d_loc"] + (1 - prob) * self.d_cell_loc_prior, ps["d_cell_scale"]).rsample()
@@ -330,8 +334,8 @@ class RemoveBackgroundPyroModel(nn.Module):
         # y: enumerated in the guide (model.py:295-301, 547)
         plp = get_p_logit_prior(counts.log(), self.d_cell_loc_prior, self.empty_UMI_threshold, self.p_logit_prior)
         t["y"] = (q1 * (F.logsigmoid(plp) - log_q1) + q0 * (F.logsigmoid(-plp) - log_q0)).sum()
-        t["p_logit_reg"] = (Normal(self.p_logit_prior, consts.P_LOGIT_SCALE).log_prob(v)
-                            - Normal(p_y, consts.P_LOGIT_SCALE).log_prob(v)).sum()
+        t["p_logit_reg"] = (Normal(self.p_logit_prior, self._k["p_logit_scale"]).log_prob(v)
+                            - Normal(p_y, self._k["p_logit_scale"]).log_prob(v)).sum()
 
         # observation terms: decoder output layer + fused likelihood kernel
         alpha = phi.reciprocal() + consts.NBPC_ALPHA_EPS_SAFEGAURD
@@ -350,15 +354,18 @@ class RemoveBackgroundPyroModel(nn.Module):
         empty_m = counts < self.counts_crossover
         cell_m = counts >= self.counts_crossover
         t["obs_probably_empty_y"] = consts.REG_SCALE_SOFT_SUPERVISION * torch.where(
-            empty_m, Normal(-consts.REG_LOGIT_MEAN, consts.REG_LOGIT_SOFT_SCALE).log_prob(p_det), torch.zeros_like(p_det)).sum()
+            empty_m, Normal(self._k["neg_reg_logit_mean"], self._k["reg_logit_soft_scale"]).log_prob(p_det),
+            torch.zeros_like(p_det)).sum()
         t["obs_probably_cell_y"] = consts.REG_SCALE_SOFT_SUPERVISION * torch.where(
-            cell_m, Normal(consts.REG_LOGIT_MEAN, consts.REG_LOGIT_SOFT_SCALE).log_prob(p_det), torch.zeros_like(p_det)).sum()
+            cell_m, Normal(self._k["reg_logit_mean"], self._k["reg_logit_soft_scale"]).log_prob(p_det),
+            torch.zeros_like(p_det)).sum()
         # epsilon medians (model.py:429-443)
         surely_cell = counts >= self.d_cell_loc_prior.exp()
-        one = torch.ones((), device=counts.device)
+        one = self._k["one"]
         med_cell = _masked_lower_median(epsilon, cell_m)
-        t["epsilon_mean"] = torch.where(surely_cell.sum() >= 2, Normal(med_cell, 0.01).log_prob(one), torch.zeros_like(one))
-        t["epsilon_empty_mean"] = Normal(_masked_lower_median(epsilon, empty_m), 0.01).log_prob(one)
+        t["epsilon_mean"] = torch.where(surely_cell.sum() >= 2, Normal(med_cell, self._k["eps_median_scale"]).log_prob(one),
+                                        torch.zeros_like(one))
+        t["epsilon_empty_mean"] = Normal(_masked_lower_median(epsilon, empty_m), self._k["eps_median_scale"]).log_prob(one)
 
         elbo = sum(t.values())
         t["loss"] = -elbo
