@@ -15,6 +15,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 import torch
 
+from . import _cabi
 from .dataprep import DataLoader, MiniBatch
 from .exceptions import ElboException, NanException
 from .model import RemoveBackgroundPyroModel
@@ -83,12 +84,13 @@ class SVI:
         if entry is None:
             entry = self._capture(batch)
             self._graphs[key] = entry
-        static, graph, loss = entry
+        static, graph, loss, n_launch = entry
         static.row_ids.copy_(batch.row_ids)
         if not self.optim.constant_learning_rate and self.optim.host_steps >= self.optim.total_steps:
             raise ValueError(f"Tried to step {self.optim.host_steps + 1} times. The specified number of total steps is "
                              f"{self.optim.total_steps}")
         graph.replay()
+        _cabi.lib().launch_count += n_launch  # kernels of ours inside the replayed graph
         self.optim.host_steps += 1
         return loss
 
@@ -105,8 +107,11 @@ class SVI:
             self._step_eager(static)
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
+        n0 = _cabi.lib().launch_count
         with torch.cuda.graph(graph):
             loss = self._step_eager(static)
+        n_launch = _cabi.lib().launch_count - n0
+        _cabi.lib().launch_count = n0  # capture records launches, it does not run them
         with torch.no_grad():
             self.optim.flat_p.copy_(snap_p), self.optim.flat_m.copy_(snap_m), self.optim.flat_v.copy_(snap_v)
             self.optim.step_count.copy_(snap_step)
@@ -114,7 +119,7 @@ class SVI:
             sd = self.model.state_dict()
             for k, v in bn_state.items():
                 sd[k].copy_(v)
-        return static, graph, loss
+        return static, graph, loss, n_launch
 
     @torch.no_grad()
     def evaluate_loss(self, batch: MiniBatch) -> torch.Tensor:
