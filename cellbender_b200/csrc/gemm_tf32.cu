@@ -1,0 +1,416 @@
+// K3/K4: the large contractions of the encoder / decoder MLPs on the 5th-generation tensor cores.
+//
+// Replaces the cuBLAS SGEMMs behind nn.Linear in EncodeZ / EncodeNonZLatents / Decoder (reference
+// vae/encoder.py:97-125, 211-228, 279-298; vae/decoder.py:41-47) and their autograd backward.
+//
+//   C[M, N] (=, +=)  A[M, K] * B[N, K]^T  (+ bias[N])        fp32 in, TF32 multiply, fp32 accumulate in TMEM
+//
+// Blackwell execution model (sm_100a): one warp issues TMA (cp.async.bulk.tensor) into a ring of
+// 128B-swizzled shared-memory stages, one elected thread issues tcgen05.mma.kind::tf32 with the accumulator in
+// TMEM (128 lanes x up to 512 columns), four warps drain TMEM with tcgen05.ld and write the result.
+// mbarriers hand stages back and forth; tcgen05.commit releases a stage when its MMAs have been consumed.
+//
+// Operand layouts.  Both operands may be "K-major" (stored [rows = M or N, cols = K], the nn.Linear forward
+// case) or "MN-major" (stored [rows = K, cols = M or N], which is what the weight-gradient products
+// dW = dY^T X and the input-gradient products dX = dY W see when nothing is transposed in memory).  The TMA
+// boxes are always 32 fp32 (128 B) wide in the contiguous dimension, so the two cases only differ in the
+// shared-memory descriptor (canonical UMMA layouts ((8,m),(T,2)):((8T,SBO),(1,T)) vs ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)))
+// and in the a_major / b_major bits of the instruction descriptor.  Out-of-bounds parts of a box (K tail, the
+// 255-row minibatch) are zero-filled by TMA, so no padding copies are needed.
+//
+// Skinny shapes (M = 255 with K = 33 538) are split along K across CTAs; partial tiles go to a workspace with
+// plain stores and a second kernel sums them in a fixed order (deterministic; no floating-point atomics).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace cb {
+
+constexpr int kGemmThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;  // 32 fp32 = 128 B = one swizzle row
+constexpr int kUmmaK = 8;    // tf32: 32 B per MMA along K
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once all previously issued tcgen05 ops of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 64-bit shared-memory matrix descriptor, SWIZZLE_128B (layout type 2), descriptor version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+
+struct GemmParams {
+  float* C;              // direct output (split_k == 1) [M, ldc]
+  float* workspace;      // partial tiles (split_k > 1)  [split_k][Mpad][Npad]
+  const float* bias;     // [N] or nullptr (direct path only; the reduce kernel adds it on the split path)
+  long long ldc;
+  int M, N, K;
+  int k_blocks_total;    // ceil(K / 32)
+  int k_blocks_per_split;
+  int split_k;
+  int accumulate;        // C += ... (direct path)
+  long long Mpad, Npad;
+};
+
+// MT = accumulators of 128 rows per CTA, BN = tile width; MT * BN <= 512 TMEM columns.
+template <int MT, int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
+  constexpr uint32_t kABytes = MT * kBlockM * kBlockK * 4;  // per stage
+  constexpr uint32_t kBBytes = BN * kBlockK * 4;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = (MT * BN <= 32) ? 32 : (MT * BN <= 64) ? 64 : (MT * BN <= 128) ? 128 : (MT * BN <= 256) ? 256 : 512;
+  static_assert(MT * BN <= 512, "accumulators exceed TMEM");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * (MT * kBlockM);
+  const int split = blockIdx.z;
+  const int kb_begin = split * p.k_blocks_per_split;
+  const int kb_end = min(p.k_blocks_total, kb_begin + p.k_blocks_per_split);
+  const int n_kb = max(kb_end - kb_begin, 0);
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      for (int i = 0; i < n_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = smem + s * kStageBytes;
+        uint8_t* b_dst = a_dst + kABytes;
+        mbar_expect_tx(&full_bar[s], kStageBytes);
+        const int k0 = (kb_begin + i) * kBlockK;
+        if (!A_MN) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) tma_load_2d(&tmap_a, &full_bar[s], a_dst + mt * 16384, k0, m0 + mt * kBlockM);
+        } else {
+#pragma unroll
+          for (int j = 0; j < MT * 4; ++j) tma_load_2d(&tmap_a, &full_bar[s], a_dst + j * 4096, m0 + j * 32, k0);
+        }
+        if (!B_MN) {
+#pragma unroll
+          for (int j = 0; j < BN / 128; ++j) tma_load_2d(&tmap_b, &full_bar[s], b_dst + j * 16384, k0, n0 + j * 128);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(&tmap_b, &full_bar[s], b_dst + j * 4096, n0 + j * 32, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      // instruction descriptor: D fp32, A/B tf32, majors, N >> 3, M >> 4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(A_MN) << 15) | (uint32_t(B_MN) << 16) |
+                             (uint32_t(BN >> 3) << 17) | (uint32_t(kBlockM >> 4) << 24);
+      for (int i = 0; i < n_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + s * kStageBytes);
+        const uint32_t b_base = a_base + kABytes;
+#pragma unroll
+        for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
+          const uint64_t bdesc = B_MN ? make_smem_desc(b_base + k4 * 1024, 4096, 1024) : make_smem_desc(b_base + k4 * 32, 16, 1024);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t adesc = A_MN ? make_smem_desc(a_base + mt * 16384 + k4 * 1024, 4096, 1024)
+                                        : make_smem_desc(a_base + mt * 16384 + k4 * 32, 16, 1024);
+            umma_tf32(tmem_base + mt * BN, adesc, bdesc, idesc, (i > 0 || k4 > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[s]);  // stage free once these MMAs have read it
+      }
+      umma_commit(&accum_bar);  // accumulator complete
+    }
+  } else {
+    // ======================= epilogue: TMEM -> registers -> global =======================
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const bool to_ws = p.split_k > 1;
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int row = m0 + mt * kBlockM + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        if (n_kb > 0) {
+          tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(mt * BN + c), v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        const int col = n0 + c;
+        if (to_ws) {
+          float* dst = p.workspace + ((long long)split * p.Mpad + row) * p.Npad + col;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else if (row < p.M && col < p.N) {
+          float* dst = p.C + (long long)row * p.ldc + col;
+          const int nv = min(32, p.N - col);
+          if (nv == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              if (p.bias != nullptr) {
+                const float4 b = *reinterpret_cast<const float4*>(p.bias + col + i);
+                o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
+              }
+              if (p.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(dst + i);
+                o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+              }
+              *reinterpret_cast<float4*>(dst + i) = o;
+            }
+          } else {
+            for (int i = 0; i < nv; ++i) {
+              float o = v[i];
+              if (p.bias != nullptr) o += p.bias[col + i];
+              if (p.accumulate) o += dst[i];
+              dst[i] = o;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// out[m, n] (=, +=) sum_s ws[s][m][n] + bias[n]   -- fixed summation order
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int split_k, long long Mpad, long long Npad,
+                                                            float* __restrict__ C, long long ldc, int M, int N,
+                                                            const float* __restrict__ bias, int accumulate) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)M * N;
+  if (idx >= total) return;
+  const int m = int(idx / N), n = int(idx % N);
+  float acc = 0.f;
+  for (int s = 0; s < split_k; ++s) acc += ws[((long long)s * Mpad + m) * Npad + n];
+  if (bias != nullptr) acc += bias[n];
+  float* dst = C + (long long)m * ldc + n;
+  *dst = accumulate ? (*dst + acc) : acc;
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] row-major with leading dimension ld; box = 32 cols x box_rows, 128B swizzle, zero OOB fill
+static int make_tmap(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+  auto enc = get_encode();
+  if (enc == nullptr) return 1;
+  cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t gstride[1] = {cuuint64_t(ld) * 4};
+  cuuint32_t box[2] = {32u, cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+template <int MT, int BN, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  constexpr int kStage = (MT * kBlockM + BN) * kBlockK * 4;
+  constexpr int STAGES = (kStage <= 48 * 1024) ? 4 : 3;
+  const int smem = STAGES * kStage + 1024;
+  auto kern = gemm_tf32_kernel<MT, BN, A_MN, B_MN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 3;
+    configured = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + MT * kBlockM - 1) / (MT * kBlockM), p.split_k);
+  kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, p);
+  return 0;
+}
+
+}  // namespace cb
+
+// workspace elements needed for a given problem (0 when split_k == 1)
+extern "C" long long cb_gemm_tf32_workspace_elems(int M, int N, int split_k) {
+  if (split_k <= 1) return 0;
+  const long long Mpad = (M + 255) / 256 * 256, Npad = (N + 255) / 256 * 256;
+  return (long long)split_k * Mpad * Npad;
+}
+
+// Suggested split along K so that about one CTA per SM streams the operands (skinny-M products).
+extern "C" int cb_gemm_tf32_suggest_split(int M, int N, int K) {
+  const int mt = (M > 128) ? 2 : 1;
+  const int bn = (N >= 256 && mt == 1) ? 256 : 128;
+  const long long tiles = (long long)((M + mt * 128 - 1) / (mt * 128)) * ((N + bn - 1) / bn);
+  const int kb = (K + 31) / 32;
+  if (tiles >= 148 || kb < 16) return 1;
+  long long s = 148 / tiles;
+  if (s > kb / 4) s = kb / 4;
+  return int(s < 1 ? 1 : s);
+}
+
+extern "C" int cb_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C,
+                            long long ldc, int M, int N, int K, const float* bias, int accumulate, int split_k,
+                            float* workspace, long long workspace_elems, void* stream) {
+  using namespace cb;
+  CB_REQUIRE(M > 0 && N > 0 && K > 0, "cb_gemm_tf32: bad shape M=%d N=%d K=%d", M, N, K);
+  CB_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0, "cb_gemm_tf32: lda=%lld / ldb=%lld must be multiples of 4 (TMA needs 16-byte rows)",
+             lda, ldb);
+  CB_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0, "cb_gemm_tf32: operands must be 16-byte aligned");
+  if (split_k < 1) split_k = 1;
+  const int kb_total = (K + kBlockK - 1) / kBlockK;
+  if (split_k > kb_total) split_k = kb_total;
+  GemmParams p;
+  p.C = C, p.workspace = workspace, p.bias = bias, p.ldc = ldc, p.M = M, p.N = N, p.K = K;
+  p.k_blocks_total = kb_total;
+  p.k_blocks_per_split = (kb_total + split_k - 1) / split_k;
+  split_k = (kb_total + p.k_blocks_per_split - 1) / p.k_blocks_per_split;  // every split owns >= 1 k-block
+  p.split_k = split_k;
+  p.accumulate = accumulate;
+  p.Mpad = (M + 255) / 256 * 256, p.Npad = (N + 255) / 256 * 256;
+  if (split_k > 1) {
+    CB_REQUIRE(workspace != nullptr && workspace_elems >= (long long)split_k * p.Mpad * p.Npad,
+               "cb_gemm_tf32: workspace too small (%lld < %lld)", workspace_elems, (long long)split_k * p.Mpad * p.Npad);
+    p.bias = nullptr;
+  }
+  CUtensorMap ta, tb;
+  // K-major operand: tensor [rows = M|N, cols = K], box 32 x 128 rows.  MN-major: tensor [rows = K, cols = M|N], box 32 x 32 rows.
+  int e = a_mn ? make_tmap(&ta, A, K, M, lda, 32) : make_tmap(&ta, A, M, K, lda, 128);
+  CB_REQUIRE(e == 0, "cb_gemm_tf32: cuTensorMapEncodeTiled failed for A (code %d)", e);
+  e = b_mn ? make_tmap(&tb, B, K, N, ldb, 32) : make_tmap(&tb, B, N, K, ldb, 128);
+  CB_REQUIRE(e == 0, "cb_gemm_tf32: cuTensorMapEncodeTiled failed for B (code %d)", e);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool two = M > 128;
+  // tile choice: MT = 2 accumulators when M > 128; BN = 256 only with a single accumulator
+  const bool wide = (!two) && N >= 256;
+  int rc = 0;
+#define CB_DISPATCH(MT, BN)                                                              \
+  do {                                                                                   \
+    if (!a_mn && !b_mn) rc = launch<MT, BN, false, false>(ta, tb, p, st);                 \
+    else if (!a_mn && b_mn) rc = launch<MT, BN, false, true>(ta, tb, p, st);              \
+    else if (a_mn && !b_mn) rc = launch<MT, BN, true, false>(ta, tb, p, st);              \
+    else rc = launch<MT, BN, true, true>(ta, tb, p, st);                                  \
+  } while (0)
+  if (two) CB_DISPATCH(2, 128);
+  else if (wide) CB_DISPATCH(1, 256);
+  else CB_DISPATCH(1, 128);
+#undef CB_DISPATCH
+  CB_REQUIRE(rc == 0, "cb_gemm_tf32: kernel configuration failed (code %d)", rc);
+  if (split_k > 1) {
+    const long long total = (long long)M * N;
+    splitk_reduce_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(workspace, split_k, p.Mpad, p.Npad, C, ldc, M, N, bias, accumulate);
+  }
+  return cb::check_launch("cb_gemm_tf32");
+}

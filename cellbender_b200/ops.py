@@ -278,3 +278,36 @@ def posterior_coo(csr: DeviceCSR, cell_rows, logits, lse, chi_ambient, chi_bar, 
 def gather_feats(csr: DeviceCSR, row_ids: torch.Tensor, amb_unit: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Per-droplet features only ([B, 4]: sum, nnz, dot with amb_unit, max) -- no dense rows are written."""
     return gather_rows(csr, row_ids, amb_unit, want=())["feats"]
+
+
+# ------------------------------------------------------------------------------------------------------
+# tcgen05 TF32 GEMM
+# ------------------------------------------------------------------------------------------------------
+_GEMM_WS = {}
+
+
+def gemm_tf32(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
+              out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, accumulate: bool = False,
+              split_k: Optional[int] = None) -> torch.Tensor:
+    """C[M,N] (=,+=) A[M,K] @ B[N,K]^T (+ bias) through cb_gemm_tf32.
+
+    a: stored [M, >=K] (a_mn=False) or [K, >=M] (a_mn=True), last dim contiguous, row stride % 4 == 0; same for b."""
+    _req_cuda(a, b)
+    L = _cabi.lib()
+    assert a.stride(-1) == 1 and b.stride(-1) == 1 and a.dtype == torch.float32 and b.dtype == torch.float32
+    dev = a.device
+    if out is None:
+        out = torch.empty((M, round_up(N, 4)), dtype=torch.float32, device=dev)[:, :N]
+    if split_k is None:
+        split_k = int(L.raw("cb_gemm_tf32_suggest_split")(M, N, K))
+    ws_elems = int(L.raw("cb_gemm_tf32_workspace_elems")(M, N, split_k))
+    ws = None
+    if ws_elems:
+        key = (dev, torch.cuda.current_stream().cuda_stream)
+        ws = _GEMM_WS.get(key)
+        if ws is None or ws.numel() < ws_elems:
+            ws = torch.empty(ws_elems, dtype=torch.float32, device=dev)
+            _GEMM_WS[key] = ws
+    L.call("cb_gemm_tf32", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out), out.stride(0), M, N, K,
+           ptr(bias), int(accumulate), split_k, ptr(ws), ws_elems, current_stream())
+    return out

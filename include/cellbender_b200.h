@@ -70,6 +70,21 @@ int cb_colsum_rows(const float* in, int n_rows, int n_cols, long long ld, float*
 int cb_row_logsumexp(const float* in, int n_rows, int n_cols, long long ld, float* lse, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * A3-A5  the large contractions of EncodeZ / EncodeNonZLatents / Decoder (vae/encoder.py:97-125, 211-228, 279-298;
+ * vae/decoder.py:41-47) and their backward, on tcgen05 tensor cores (TF32 multiply, fp32 accumulate in TMEM).
+ *   C[M, N] (=, +=) A[M, K] * B[N, K]^T (+ bias[N])
+ * a_mn / b_mn = 0: operand stored [M|N rows, K cols] (K-major, the nn.Linear forward case);
+ *             = 1: operand stored [K rows, M|N cols] (what dW = dY^T X and dX = dY W see, no transposes in memory).
+ * lda / ldb multiples of 4 and 16-byte aligned bases (TMA); out-of-range rows/cols are zero-filled.
+ * split_k > 1 streams K across CTAs (skinny M): partial tiles in `workspace`
+ * (cb_gemm_tf32_workspace_elems floats), summed in a fixed order.                                            */
+long long cb_gemm_tf32_workspace_elems(int M, int N, int split_k);
+int cb_gemm_tf32_suggest_split(int M, int N, int K);
+int cb_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C,
+                 long long ldc, int M, int N, int K, const float* bias, int accumulate, int split_k, float* workspace,
+                 long long workspace_elems, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * K8  fused ClippedAdam + OneCycleLR over one flat buffer.  Replaces get_optimizer (run.py:593-629) and the
  * per-parameter optimizer/scheduler steps at train.py:56-60.  lr_table/beta1_table[table_len] hold torch
  * OneCycleLR's per-step values; *step_ptr (device int64) counts completed steps and is incremented here.       */

@@ -1,0 +1,64 @@
+"""-m gpu: the hand-written tcgen05 TF32 GEMM against torch (float64) on every operand-major combination and on the
+shapes of the training step.  Tolerance: TF32 keeps 10 mantissa bits; the kernel is compared (a) strictly with a
+float64 product of the TF32-TRUNCATED operands (same rounding as the tensor core: 2e-5 of scale, i.e. only fp32
+accumulation order), (b) loosely with the exact product (2e-3 of scale)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _tf32_trunc(t):
+    return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def _check(M, N, K, a_mn, b_mn, split_k=None, bias=False, accumulate=False, seed=0):
+    from cellbender_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    ld = lambda n: ops.round_up(n, 4)
+    A = torch.randn((K, ld(M)) if a_mn else (M, ld(K)), device=DEV, generator=g)
+    B = torch.randn((K, ld(N)) if b_mn else (N, ld(K)), device=DEV, generator=g)
+    Al = (A[:, :M].t() if a_mn else A[:, :K])
+    Bl = (B[:, :N].t() if b_mn else B[:, :K])
+    bias_t = torch.randn(N, device=DEV, generator=g) if bias else None
+    out = torch.full((M, ld(N)), 7.0, device=DEV)
+    c0 = out[:, :N].clone()
+    ops.gemm_tf32(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, out=out[:, :N], bias=bias_t, accumulate=accumulate, split_k=split_k)
+    torch.cuda.synchronize()
+    extra = (bias_t.double() if bias else 0) + (c0.double() if accumulate else 0)
+    ref_trunc = _tf32_trunc(Al.contiguous()).double() @ _tf32_trunc(Bl.contiguous()).double().t() + extra
+    ref_exact = Al.double() @ Bl.double().t() + extra
+    got = out[:, :N].double()
+    scale = float(ref_exact.abs().max())
+    e_trunc = float((got - ref_trunc).abs().max()) / scale
+    e_exact = float((got - ref_exact).abs().max()) / scale
+    assert float(out[:, N:].sub(7.0).abs().max() if ld(N) > N else 0.0) == 0.0, "padding columns were written"
+    assert e_trunc < 2e-5, (M, N, K, a_mn, b_mn, split_k, e_trunc, e_exact)
+    assert e_exact < 2e-3, (M, N, K, a_mn, b_mn, split_k, e_trunc, e_exact)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 256, 64), (200, 130, 100), (255, 512, 1000), (300, 77, 333)])
+def test_gemm_all_majors_small(M, N, K, a_mn, b_mn):
+    _check(M, N, K, a_mn, b_mn, split_k=1)
+
+
+@pytest.mark.parametrize("split_k", [2, 7, None])
+def test_gemm_split_k_bias_accumulate(split_k):
+    _check(255, 512, 5000, False, False, split_k=split_k, bias=True)
+    _check(255, 512, 5000, False, True, split_k=split_k, bias=True, accumulate=True)
+    _check(255, 130, 999, False, False, split_k=1, bias=True, accumulate=True)
+
+
+def test_gemm_training_step_shapes():
+    """PBMC8k shapes: G = 33 538 (not a multiple of 4 -> padded leading dimension), B = 255, H = 512."""
+    G, Bn, H = 33538, 255, 512
+    _check(Bn, H, G, False, False, bias=True)         # encoder input layers: X[B,G] . W[H,G]^T   (split-K)
+    _check(Bn, G, H, False, False, split_k=1, bias=True)   # decoder output layer: h[B,H] . Wd[G,H]^T
+    _check(Bn, H, G, False, True)                     # dh = dlogits[B,G] . Wd[G,H]            (B MN-major, split-K)
+    _check(H, G, Bn, True, True, split_k=1)           # dW = dY^T[H,B] . X[B,G]                (both MN-major)
+    _check(G, H, Bn, True, True, split_k=1)           # dWd = dlogits^T[G,B] . h[B,H]
+    _check(Bn, G, H, False, True, split_k=1)          # dX = dY[B,H] . W[H,G]                  (B MN-major)
