@@ -14,7 +14,8 @@
 // case) or "MN-major" (stored [rows = K, cols = M or N], which is what the weight-gradient products
 // dW = dY^T X and the input-gradient products dX = dY W see when nothing is transposed in memory).  The TMA
 // boxes are always 32 fp32 (128 B) wide in the contiguous dimension, so the two cases only differ in the
-// shared-memory descriptor (canonical UMMA layouts ((8,m),(T,2)):((8T,SBO),(1,T)) vs ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)))
+// shared-memory descriptor (canonical UMMA layouts ((8,m),(T,2)):((8T,SBO),(1,T)) vs ((T,8,m),(4,k)):((1,T,LBO),(8T,SBO)) with the
+// 32-byte-atom 128B swizzle that tf32 MN-major operands require)
 // and in the a_major / b_major bits of the instruction descriptor.  Out-of-bounds parts of a box (K tail, the
 // 255-row minibatch) are zero-filled by TMA, so no padding copies are needed.
 //
@@ -105,14 +106,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// 64-bit shared-memory matrix descriptor, SWIZZLE_128B (layout type 2), descriptor version 1 (Blackwell)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// 64-bit shared-memory matrix descriptor, descriptor version 1 (Blackwell).
+// layout_type 2 = SWIZZLE_128B (K-major operands); 1 = SWIZZLE_128B_BASE32B, the only layout the tensor core
+// accepts for MN-major 32-bit (tf32) operands: 128 B rows, 32 B chunks XOR-ed with (row & 3), atoms of 4 K-rows.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
   d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= uint64_t(1) << 46;
-  d |= uint64_t(2) << 61;
+  d |= uint64_t(layout_type) << 61;
   return d;
 }
 
@@ -211,11 +214,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t b_base = a_base + kABytes;
 #pragma unroll
         for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
-          const uint64_t bdesc = B_MN ? make_smem_desc(b_base + k4 * 1024, 4096, 1024) : make_smem_desc(b_base + k4 * 32, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc(b_base + k4 * 1024, 4096, 512, 1) : make_smem_desc(b_base + k4 * 32, 16, 1024, 2);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
-            const uint64_t adesc = A_MN ? make_smem_desc(a_base + mt * 16384 + k4 * 1024, 4096, 1024)
-                                        : make_smem_desc(a_base + mt * 16384 + k4 * 32, 16, 1024);
+            const uint64_t adesc = A_MN ? make_smem_desc(a_base + mt * 16384 + k4 * 1024, 4096, 512, 1)
+                                        : make_smem_desc(a_base + mt * 16384 + k4 * 32, 16, 1024, 2);
             umma_tf32(tmem_base + mt * BN, adesc, bdesc, idesc, (i > 0 || k4 > 0) ? 1u : 0u);
           }
         }
@@ -311,7 +314,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 // 2-D fp32 tensor [rows, cols] row-major with leading dimension ld; box = 32 cols x box_rows, 128B swizzle, zero OOB fill
-static int make_tmap(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+static int make_tmap(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows,
+                     bool mn_major) {
   auto enc = get_encode();
   if (enc == nullptr) return 1;
   cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
@@ -319,7 +323,8 @@ static int make_tmap(CUtensorMap* map, const float* base, long long rows, long l
   cuuint32_t box[2] = {32u, cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 2;
 }
@@ -387,9 +392,9 @@ extern "C" int cb_gemm_tf32(const float* A, long long lda, int a_mn, const float
   }
   CUtensorMap ta, tb;
   // K-major operand: tensor [rows = M|N, cols = K], box 32 x 128 rows.  MN-major: tensor [rows = K, cols = M|N], box 32 x 32 rows.
-  int e = a_mn ? make_tmap(&ta, A, K, M, lda, 32) : make_tmap(&ta, A, M, K, lda, 128);
+  int e = a_mn ? make_tmap(&ta, A, K, M, lda, 32, true) : make_tmap(&ta, A, M, K, lda, 128, false);
   CB_REQUIRE(e == 0, "cb_gemm_tf32: cuTensorMapEncodeTiled failed for A (code %d)", e);
-  e = b_mn ? make_tmap(&tb, B, K, N, ldb, 32) : make_tmap(&tb, B, N, K, ldb, 128);
+  e = b_mn ? make_tmap(&tb, B, K, N, ldb, 32, true) : make_tmap(&tb, B, N, K, ldb, 128, false);
   CB_REQUIRE(e == 0, "cb_gemm_tf32: cuTensorMapEncodeTiled failed for B (code %d)", e);
   cudaStream_t st = (cudaStream_t)stream;
   const bool two = M > 128;
