@@ -1,18 +1,26 @@
-"""The four large contractions of a training step (three G -> 512 encoder input layers, one 512 -> G decoder
-output layer; reference vae/encoder.py:97-105,211,220 and vae/decoder.py:41-47).
+"""The large contractions of a training step (three G -> 512 encoder input layers, one 512 -> G decoder output
+layer; reference vae/encoder.py:97-105,211,220 and vae/decoder.py:41-47), their backward, and the gene-wise
+BatchNorm + row dropout in front of them (vae/encoder.py:239,279).
 
 ``BACKEND``:
-  'cublas'   torch.matmul (library GEMM; fp32 unless TF32 is allowed) -- the plumbing default while the
-             hand-written kernel is being brought up;
-  'tcgen05'  csrc/gemm_tf32.cu: TMA-fed tcgen05.mma kind::tf32 with TMEM accumulators (set by
-             ``cellbender_b200.gemm.set_backend('tcgen05')`` once its parity tests are green on the GPU).
+  'tcgen05'  csrc/gemm_tf32.cu -- hand-written TMA-fed tcgen05.mma kind::tf32 with TMEM accumulators (default on
+             the training / posterior path).  TF32 multiply (10-bit mantissa, truncation), fp32 accumulation.
+             Stated tolerance vs an fp32/fp64 product: 2e-3 of the output scale per element (tests/test_gemm_gpu.py);
+             on the ELBO: <= 2e-3 relative (tests/test_step_gpu.py::test_elbo_tf32_backend_tolerance).
+  'cublas'   torch.matmul in full fp32 (library SIMT SGEMM) -- the reference's arithmetic; used by the 1e-5 parity
+             tests and as the "library baseline" in profiles/.
+Weight gradients are written by the GEMM epilogue straight into the optimizer's flat gradient buffer (the
+nn.Parameter carries its gradient view as ``_cb_grad_view``), so no extra copy or accumulation pass exists.
 """
 from typing import Optional
 
 import torch
 import torch.nn.functional as F
 
-BACKEND = "cublas"
+from . import ops
+from ._cabi import current_stream, lib, ptr
+
+BACKEND = "tcgen05"
 
 
 def set_backend(name: str):
@@ -21,11 +29,135 @@ def set_backend(name: str):
     BACKEND = name
 
 
-def linear_big(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], n_in: int, col_offset: int = 0,
-               wide_output: bool = False) -> torch.Tensor:
-    """y = x[:, :n_in] @ weight[:, col_offset:col_offset + n_in].T + bias   (nn.Linear layout: weight [out, in]).
+def _grad_target(weight: torch.Tensor) -> torch.Tensor:
+    gv = getattr(weight, "_cb_grad_view", None)
+    if gv is None:
+        gv = torch.empty_like(weight)
+    return gv
 
-    x may carry padding columns beyond n_in (rows are 16-byte aligned buffers from the gather kernel)."""
-    xs = x[:, :n_in]
-    w = weight[:, col_offset:col_offset + n_in]
-    return F.linear(xs, w, bias)
+
+def _tma_ok(t: torch.Tensor) -> bool:
+    return (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0
+            and t.data_ptr() % 16 == 0)
+
+
+class _MultiLinearBig(torch.autograd.Function):
+    """Several nn.Linear layers that read the SAME wide input x (EncodeNonZLatents' layer1 and eps_network.0, or the
+    single EncodeZ input layer):
+         y_i = x[:, :n_in] @ W_i[:, off:off+n_in]^T + feat_i @ W_i[:, :off]^T + bias_i
+    One autograd node, so the input gradient dx = sum_i dy_i @ W_i is accumulated by the GEMM epilogue (no separate
+    add pass over [B, G]) and every dW_i lands directly in the optimizer's flat gradient buffer."""
+
+    @staticmethod
+    def forward(ctx, x, n_in: int, col_offset: int, *args):
+        feats, weights, biases = args[0::3], args[1::3], args[2::3]
+        B = x.shape[0]
+        ys = []
+        for feat, w, b in zip(feats, weights, biases):
+            y = ops.gemm_tf32(x, w[:, col_offset:col_offset + n_in], B, w.shape[0], n_in, bias=b)
+            if feat is not None:
+                y = torch.addmm(y, feat, w[:, :col_offset].t())
+            ys.append(y)
+        ctx.save_for_backward(x, *[t for t in feats if t is not None], *weights)
+        ctx.meta = (len(weights), n_in, col_offset, [f is not None for f in feats], [b is not None for b in biases])
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        n, n_in, off, has_feat, has_bias = ctx.meta
+        saved = list(ctx.saved_tensors)
+        x = saved.pop(0)
+        feats = [saved.pop(0) if h else None for h in has_feat]
+        weights = saved
+        B = x.shape[0]
+        need_dx = ctx.needs_input_grad[0]
+        dx = None
+        if need_dx:
+            dx = ops.alloc_rows(B, n_in, x.device, zero=False)[:, :n_in]
+        grads = []
+        first = True
+        for i in range(n):
+            dy = dys[i].contiguous()
+            w, feat = weights[i], feats[i]
+            H = w.shape[0]
+            dw = db = dfeat = None
+            if ctx.needs_input_grad[3 + 3 * i + 1]:
+                dw = _grad_target(w)
+                # dW[H, n_in] = dy^T[H, B] . x[B, n_in]: both operands stored with the reduction dim (B) as rows
+                ops.gemm_tf32(dy, x, H, n_in, B, a_mn=True, b_mn=True, out=dw[:, off:off + n_in], split_k=1)
+                if off:
+                    dw[:, :off] = dy.t() @ feat
+            if need_dx:
+                # dx[B, n_in] (+)= dy[B, H] . W[H, n_in]
+                ops.gemm_tf32(dy, w[:, off:off + n_in], B, n_in, H, b_mn=True, out=dx, accumulate=not first, split_k=1)
+                first = False
+            if has_bias[i] and ctx.needs_input_grad[3 + 3 * i + 2]:
+                db = dy.sum(0)
+            if feat is not None and ctx.needs_input_grad[3 + 3 * i]:
+                dfeat = dy @ w[:, :off]
+            grads += [dfeat, dw, db]
+        return (dx, None, None, *grads)
+
+
+def multi_linear_big(x: torch.Tensor, layers, n_in: int, col_offset: int = 0):
+    """``layers`` = [(nn.Linear, feat or None), ...] applied to the same wide input x; returns a tuple of outputs.
+    x may carry padding columns beyond n_in (16-byte-aligned rows from the gather / BN kernels)."""
+    ws = [lin.weight for lin, _ in layers]
+    use_tc = (BACKEND == "tcgen05" and _tma_ok(x) and all(_tma_ok(w) for w in ws)
+              and all((w.data_ptr() + 4 * col_offset) % 16 == 0 for w in ws))
+    if use_tc:
+        args = []
+        for lin, feat in layers:
+            args += [feat, lin.weight, lin.bias]
+        return _MultiLinearBig.apply(x, n_in, col_offset, *args)
+    outs = []
+    for lin, feat in layers:
+        y = F.linear(x[:, :n_in], lin.weight[:, col_offset:col_offset + n_in], lin.bias)
+        if feat is not None:
+            y = y + feat @ lin.weight[:, :col_offset].t()
+        outs.append(y)
+    return tuple(outs)
+
+
+def linear_big(x: torch.Tensor, lin: torch.nn.Linear, n_in: int, col_offset: int = 0, feat: Optional[torch.Tensor] = None):
+    return multi_linear_big(x, [(lin, feat)], n_in, col_offset)[0]
+
+
+class _BN0Dropout(torch.autograd.Function):
+    """dropout50(batchnorm0(x)) of EncodeNonZLatents (vae/encoder.py:239,279) through cb_bn0_forward / _backward."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, keep, training: bool, momentum: float, eps: float, n_genes: int):
+        B, G = x.shape[0], n_genes
+        y = ops.alloc_rows(B, G, x.device, zero=False)
+        mean = torch.empty(G, device=x.device)
+        rstd = torch.empty(G, device=x.device)
+        lib().call("cb_bn0_forward", ptr(x), x.stride(0), B, G, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+                   ptr(keep), int(training), float(momentum), float(eps), ptr(y), y.stride(0), ptr(mean), ptr(rstd),
+                   current_stream())
+        ctx.save_for_backward(x, keep if keep is not None else torch.empty(0, device=x.device), mean, rstd)
+        ctx.meta = (G, keep is not None)
+        return y[:, :G]
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, keep, mean, rstd = ctx.saved_tensors
+        G, has_keep = ctx.meta
+        if dy.stride(1) != 1:
+            dy = dy.contiguous()
+        dgamma = torch.empty(G, device=x.device)
+        dbeta = torch.empty(G, device=x.device)
+        lib().call("cb_bn0_backward", ptr(x), x.stride(0), ptr(dy), dy.stride(0), x.shape[0], G, ptr(keep) if has_keep else None,
+                   ptr(mean), ptr(rstd), ptr(dgamma), ptr(dbeta), current_stream())
+        return None, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def bn0_dropout(x: torch.Tensor, bn: torch.nn.BatchNorm1d, keep: Optional[torch.Tensor], training: bool, n_genes: int):
+    """dropout(bn(x[:, :n_genes])) as a [B, n_genes] view of a 16-byte-row buffer (GEMM/TMA friendly)."""
+    if x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1:
+        if training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        return _BN0Dropout.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, keep if training else None, training,
+                                 bn.momentum if bn.momentum is not None else 0.1, bn.eps, n_genes)
+    y = bn(x[:, :n_genes])
+    return y * keep.unsqueeze(-1) if (training and keep is not None) else y

@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.distributions import Beta, Gamma, LogNormal, Normal, constraints, transform_to
 
-from . import consts, ops
+from . import consts, gemm, ops
 from .exceptions import NanException
 from .vae import CompositeEncoder, EncoderInputs
 
@@ -133,7 +133,10 @@ class _ObsTerm(torch.autograd.Function):
         G = csr.n_genes
         B = h_dec.shape[0]
         logits = bufs["logits"][:B]
-        torch.addmm(b_out, h_dec, w_out.t(), out=logits[:, :G])  # decoder output layer (library GEMM for now)
+        if gemm.BACKEND == "tcgen05":
+            ops.gemm_tf32(h_dec.contiguous(), w_out, B, G, w_out.shape[1], out=logits[:, :G], bias=b_out, split_k=1)
+        else:
+            torch.addmm(b_out, h_dec, w_out.t(), out=logits[:, :G])  # library fp32 GEMM (parity-test back-end)
         chi_a = bufs["chi_a"]
         chi_a[:G].copy_(chi_ambient)
         oo = bufs["obs_out"]
@@ -152,8 +155,14 @@ class _ObsTerm(torch.autograd.Function):
         h_dec, w_out, sums, w, dlogits, dchi_amb = ctx.saved_tensors
         G = ctx.G
         dl = dlogits[:, :G]
-        d_h = (dl @ w_out) * g
-        d_w = dl.t() @ h_dec  # [G, H]
+        if gemm.BACKEND == "tcgen05":
+            B, H = h_dec.shape
+            d_h = ops.gemm_tf32(dlogits, w_out, B, H, G, b_mn=True) * g          # dlogits[B,G] . Wd[G,H], split-K
+            d_w = gemm._grad_target(w_out)
+            ops.gemm_tf32(dlogits, h_dec.contiguous(), G, H, B, a_mn=True, b_mn=True, out=d_w, split_k=1)  # dlogits^T . h
+        else:
+            d_h = (dl @ w_out) * g
+            d_w = dl.t() @ h_dec  # [G, H]
         d_b = ops.colsum_rows(dlogits, G)
         w1, w0, wE = w[:, 0], w[:, 1], w[:, 2]
         d_coef = torch.stack((w1 * sums[:, 3], w1 * sums[:, 4], w1 * sums[:, 5], w0 * sums[:, 7], w0 * sums[:, 8],

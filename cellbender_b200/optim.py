@@ -40,11 +40,18 @@ class FlatClippedAdam:
         assert self.params, "no parameters to optimise"
         dev = self.params[0].device
         self.device = dev
-        sizes = [p.numel() for p in self.params]
-        # each tensor starts on a 16-byte boundary so the big weight matrices stay vector/TMA friendly
-        self.offsets, off = [], 0
-        for n in sizes:
+        # each tensor starts on a 16-byte boundary; large 2-D weights additionally get a row stride that is a
+        # multiple of 4 floats (TMA needs 16-byte rows; G = 33 538 is not a multiple of 4) -- the nn.Parameter then is
+        # a strided view [rows, cols] of a [rows, ld] block, the padding columns stay zero forever.
+        def padded_ld(p):
+            return (p.shape[1] + 3) // 4 * 4 if (p.dim() == 2 and p.numel() >= (1 << 16)) else None
+
+        self.offsets, self.lds, off = [], [], 0
+        for p in self.params:
+            ld = padded_ld(p)
+            n = p.numel() if ld is None else p.shape[0] * ld
             self.offsets.append(off)
+            self.lds.append(ld)
             off += (n + 3) // 4 * 4
         self.n = off
         self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
@@ -53,11 +60,18 @@ class FlatClippedAdam:
         self.flat_v = torch.zeros(off, dtype=torch.float32, device=dev)
         self.grad_views = []
         with torch.no_grad():
-            for p, o in zip(self.params, self.offsets):
-                view = self.flat_p[o:o + p.numel()].view(p.shape)
+            for p, o, ld in zip(self.params, self.offsets, self.lds):
+                if ld is None:
+                    view = self.flat_p[o:o + p.numel()].view(p.shape)
+                    gview = self.flat_g[o:o + p.numel()].view(p.shape)
+                else:
+                    rows, cols = p.shape
+                    view = self.flat_p[o:o + rows * ld].view(rows, ld)[:, :cols]
+                    gview = self.flat_g[o:o + rows * ld].view(rows, ld)[:, :cols]
                 view.copy_(p.data)
                 p.data = view
-                self.grad_views.append(self.flat_g[o:o + p.numel()].view(p.shape))
+                p._cb_grad_view = gview  # GEMM epilogues write weight gradients here directly (gemm.py)
+                self.grad_views.append(gview)
         self.learning_rate = learning_rate
         self.total_steps = total_steps
         self.constant_learning_rate = constant_learning_rate or total_steps is None

@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import consts
-from .gemm import linear_big
+from .gemm import bn0_dropout, linear_big, multi_linear_big
 
 
 @dataclass
@@ -134,7 +134,7 @@ class EncodeZ(FullyConnectedNetwork):
         assert self.transform == "normalize", "the B200 path implements input_transform='normalize' (run.py:707)"
         first = self.network[0].layer
         lin = first[0]
-        h = linear_big(inp.x_norm, lin.weight, lin.bias, n_in=self.input_dim)
+        h = linear_big(inp.x_norm, lin, n_in=self.input_dim)
         for mod in list(first)[1:]:
             h = mod(h)
         for layer in list(self.network)[1:]:
@@ -202,27 +202,25 @@ class EncodeNonZLatents(nn.Module):
             overlap = torch.zeros_like(counts)
             eps_overlap = torch.zeros_like(counts)
 
-        # BatchNorm over genes + Dropout1d(0.5), which on a 2-D input drops whole droplet rows (torch 2.11).
-        xt = inp.x_lognorm[:, :G]
-        x_in = self.batchnorm0(xt)
-        if self.training:
-            if row_keep_scale is None:
-                row_keep_scale = torch.bernoulli(torch.full((xt.shape[0],), 0.5, device=xt.device)) * 2.0
-            x_in = x_in * row_keep_scale.unsqueeze(-1)
-        znorm = torch.linalg.vector_norm(z.detach().reshape(xt.shape[0], -1), ord=2, dim=-1, keepdim=True)
+        # BatchNorm over genes + Dropout1d(0.5), which on a 2-D input drops whole droplet rows (torch 2.11):
+        # one fused kernel (csrc/bn0.cu) writing a 16-byte-row buffer the tensor-core GEMMs can read through TMA.
+        B = inp.feats.shape[0]
+        if self.training and row_keep_scale is None:
+            row_keep_scale = torch.bernoulli(torch.full((B,), 0.5, device=inp.feats.device)) * 2.0
+        x_in = bn0_dropout(inp.x_lognorm, self.batchnorm0, row_keep_scale, self.training, G)
+        znorm = torch.linalg.vector_norm(z.detach().reshape(B, -1), ord=2, dim=-1, keepdim=True)
         p_feat = torch.cat((log_sum, log_nnz, overlap, znorm), dim=-1)
         e_feat = torch.cat((log_sum, log_nnz, eps_overlap, znorm), dim=-1)
 
-        def first_layer(lin: nn.Linear, feat):
-            # Linear(cat(feat, x_in)) split into the large gene block and the 4 feature columns
-            return linear_big(x_in, lin.weight, lin.bias, n_in=G, col_offset=4) + feat @ lin.weight[:, :4].t()
-
-        x_ = self.softplus(self.batchnorm1(first_layer(self.layer1, p_feat)))
+        # Linear(cat(feat, x_in)) of both towers: the large gene block through the tensor-core GEMM (shared input),
+        # the 4 feature columns as a rank-4 update
+        e = self.eps_network[0]
+        h1, he = multi_linear_big(x_in, [(self.layer1, p_feat), (e, e_feat)], n_in=G, col_offset=4)
+        x_ = self.softplus(self.batchnorm1(h1))
         x_ = self.softplus(self.batchnorm2(self.layer2(torch.cat((p_feat, x_), dim=-1))))
         p_out = self.layer3(torch.cat((p_feat, x_), dim=-1)).squeeze(-1)
 
-        e = self.eps_network[0]
-        h = first_layer(e, e_feat)
+        h = he
         for mod in list(self.eps_network)[1:]:
             h = mod(h)
         eps_out = h.squeeze(-1)
@@ -295,7 +293,7 @@ class Decoder(FullyConnectedNetwork):
 
     def logits(self, z: torch.Tensor) -> torch.Tensor:
         lin = self.out_linear
-        return linear_big(self.hidden(z), lin.weight, lin.bias, n_in=lin.in_features, wide_output=True)
+        return torch.nn.functional.linear(self.hidden(z), lin.weight, lin.bias)
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:
         return self.softmax(self.logits(z))

@@ -70,6 +70,17 @@ int cb_colsum_rows(const float* in, int n_rows, int n_cols, long long ld, float*
 int cb_row_logsumexp(const float* in, int n_rows, int n_cols, long long ld, float* lse, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * A4  self.dropout50(self.batchnorm0(x)) of EncodeNonZLatents.forward (vae/encoder.py:239,279), forward + backward.
+ * x / y / dy are [n_rows, ld] fp32; keep[n_rows] is the Dropout1d row realisation (0 or 2; NULL = none);
+ * running_mean/var are updated in training mode (momentum 0.1, unbiased variance, as nn.BatchNorm1d).           */
+int cb_bn0_forward(const float* x, long long ldx, int n_rows, int n_genes, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, const float* keep, int training, float momentum, float eps,
+                   float* y, long long ldy, float* save_mean, float* save_rstd, void* stream);
+int cb_bn0_backward(const float* x, long long ldx, const float* dy, long long lddy, int n_rows, int n_genes,
+                    const float* keep, const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * A3-A5  the large contractions of EncodeZ / EncodeNonZLatents / Decoder (vae/encoder.py:97-125, 211-228, 279-298;
  * vae/decoder.py:41-47) and their backward, on tcgen05 tensor cores (TF32 multiply, fp32 accumulate in TMEM).
  *   C[M, N] (=, +=) A[M, K] * B[N, K]^T (+ bias[N])

@@ -442,3 +442,34 @@ def test_posterior_coo_vs_dense_oracle(ops, scale, n_max):
     for k, v in off_got.items():
         assert off_ref.get(k) == v
     assert set(off_ref) - set(off_got) <= {k for (k, cc), v in ref.items() if edge(v)}
+
+
+# ------------------------------------------------------------------------------------------------- BN0
+@pytest.mark.parametrize("training", [True, False])
+def test_bn0_dropout_matches_torch_batchnorm(ops, training):
+    from cellbender_b200 import gemm
+
+    torch.manual_seed(0)
+    B, G = 37, 203
+    x = ops.alloc_rows(B, G, DEV)
+    x[:, :G] = torch.rand(B, G, device=DEV) * 0.01
+    bn = torch.nn.BatchNorm1d(G).to(DEV)
+    bn.weight.data.uniform_(0.5, 1.5), bn.bias.data.normal_(0, 0.1)
+    bn.running_mean.normal_(0, 0.01), bn.running_var.uniform_(0.5, 1.5)
+    ref_bn = torch.nn.BatchNorm1d(G).to(DEV).double()
+    ref_bn.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in bn.state_dict().items()})
+    bn.train(training), ref_bn.train(training)
+    keep = (torch.bernoulli(torch.full((B,), 0.5, device=DEV)) * 2.0) if training else None
+    y = gemm.bn0_dropout(x, bn, keep, training, G)
+    yr = ref_bn(x[:, :G].double())
+    if training:
+        yr = yr * keep.double().unsqueeze(-1)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().cpu().numpy(), rtol=2e-5, atol=2e-6)
+    w = torch.randn(B, G, device=DEV)
+    (y * w).sum().backward()
+    (yr * w.double()).sum().backward()
+    np.testing.assert_allclose(bn.weight.grad.cpu().numpy(), ref_bn.weight.grad.cpu().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(bn.bias.grad.cpu().numpy(), ref_bn.bias.grad.cpu().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(bn.running_mean.cpu().numpy(), ref_bn.running_mean.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(bn.running_var.cpu().numpy(), ref_bn.running_var.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    assert int(bn.num_batches_tracked) == int(ref_bn.num_batches_tracked)
