@@ -4,5 +4,5 @@ LAUNCHES = {
     "cb_colsum_rows": 1, "cb_row_logsumexp": 1, "cb_clipped_adam_step": 2, "cb_posterior_noise_window": 1,
     "cb_posterior_entry_index": 1, "cb_posterior_compact": 1, "cb_exclusive_scan_i32": 3, "cb_segment_heads": 1,
     "cb_segment_starts": 1, "cb_segment_estimate": 1, "cb_csr_from_segments": 1, "cb_mckp_gene_deficit": 2,
-    "cb_mckp_candidates": 1, "cb_mckp_compact": 1, "cb_mckp_select": 1, "cb_mckp_finalize": 1, "cb_gemm_tf32": 1, "cb_bn0_forward": 1, "cb_bn0_backward": 1,
+    "cb_mckp_candidates": 1, "cb_mckp_compact": 1, "cb_mckp_select": 1, "cb_mckp_finalize": 1, "cb_gemm_tf32": 1, "cb_gemm_tf32_pair": 1, "cb_bn0_forward": 1, "cb_bn0_backward": 1,
 }

@@ -125,7 +125,8 @@ struct GemmParams {
   const float* bias;     // [N] or nullptr (direct path only; the reduce kernel adds it on the split path)
   long long ldc;
   int M, N, K;
-  int k_blocks_total;    // ceil(K / 32)
+  int k_blocks_total;    // ceil(K / 32) (+ ceil(K2 / 32) with a second operand pair)
+  int k_blocks_first;    // k-blocks of the first operand pair
   int k_blocks_per_split;
   int split_k;
   int accumulate;        // C += ... (direct path)
@@ -135,7 +136,8 @@ struct GemmParams {
 // MT = accumulators of 128 rows per CTA, BN = tile width; MT * BN <= 512 TMEM columns.
 template <int MT, int BN, bool A_MN, bool B_MN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b2, GemmParams p) {
   constexpr uint32_t kABytes = MT * kBlockM * kBlockK * 4;  // per stage
   constexpr uint32_t kBBytes = BN * kBlockK * 4;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
@@ -182,20 +184,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint8_t* a_dst = smem + s * kStageBytes;
         uint8_t* b_dst = a_dst + kABytes;
         mbar_expect_tx(&full_bar[s], kStageBytes);
-        const int k0 = (kb_begin + i) * kBlockK;
+        // k-blocks [0, k_blocks_first) come from operand pair 1, the rest from pair 2 (C = A1 B1^T + A2 B2^T)
+        const int kb = kb_begin + i;
+        const bool second = kb >= p.k_blocks_first;
+        const CUtensorMap* ma = second ? &tmap_a2 : &tmap_a;
+        const CUtensorMap* mb = second ? &tmap_b2 : &tmap_b;
+        const int k0 = (second ? kb - p.k_blocks_first : kb) * kBlockK;
         if (!A_MN) {
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) tma_load_2d(&tmap_a, &full_bar[s], a_dst + mt * 16384, k0, m0 + mt * kBlockM);
+          for (int mt = 0; mt < MT; ++mt) tma_load_2d(ma, &full_bar[s], a_dst + mt * 16384, k0, m0 + mt * kBlockM);
         } else {
 #pragma unroll
-          for (int j = 0; j < MT * 4; ++j) tma_load_2d(&tmap_a, &full_bar[s], a_dst + j * 4096, m0 + j * 32, k0);
+          for (int j = 0; j < MT * 4; ++j) tma_load_2d(ma, &full_bar[s], a_dst + j * 4096, m0 + j * 32, k0);
         }
         if (!B_MN) {
 #pragma unroll
-          for (int j = 0; j < BN / 128; ++j) tma_load_2d(&tmap_b, &full_bar[s], b_dst + j * 16384, k0, n0 + j * 128);
+          for (int j = 0; j < BN / 128; ++j) tma_load_2d(mb, &full_bar[s], b_dst + j * 16384, k0, n0 + j * 128);
         } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_2d(&tmap_b, &full_bar[s], b_dst + j * 4096, n0 + j * 32, k0);
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(mb, &full_bar[s], b_dst + j * 4096, n0 + j * 32, k0);
         }
       }
     }
@@ -330,7 +337,8 @@ static int make_tmap(CUtensorMap* map, const float* base, long long rows, long l
 }
 
 template <int MT, int BN, bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                  const GemmParams& p, cudaStream_t st) {
   constexpr int kStage = (MT * kBlockM + BN) * kBlockK * 4;
   constexpr int STAGES = (kStage <= 48 * 1024) ? 4 : 3;
   const int smem = STAGES * kStage + 1024;
@@ -341,7 +349,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
     configured = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + MT * kBlockM - 1) / (MT * kBlockM), p.split_k);
-  kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, p);
+  kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, ta2, tb2, p);
   return 0;
 }
 
@@ -366,20 +374,24 @@ extern "C" int cb_gemm_tf32_suggest_split(int M, int N, int K) {
   return int(s < 1 ? 1 : s);
 }
 
-extern "C" int cb_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C,
-                            long long ldc, int M, int N, int K, const float* bias, int accumulate, int split_k,
-                            float* workspace, long long workspace_elems, void* stream) {
+extern "C" int cb_gemm_tf32_pair(const float* A, long long lda, const float* B, long long ldb, int K, const float* A2,
+                                 long long lda2, const float* B2, long long ldb2, int K2, int a_mn, int b_mn, float* C,
+                                 long long ldc, int M, int N, const float* bias, int accumulate, int split_k,
+                                 float* workspace, long long workspace_elems, void* stream) {
   using namespace cb;
-  CB_REQUIRE(M > 0 && N > 0 && K > 0, "cb_gemm_tf32: bad shape M=%d N=%d K=%d", M, N, K);
-  CB_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0, "cb_gemm_tf32: lda=%lld / ldb=%lld must be multiples of 4 (TMA needs 16-byte rows)",
-             lda, ldb);
-  CB_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0, "cb_gemm_tf32: operands must be 16-byte aligned");
+  CB_REQUIRE(M > 0 && N > 0 && K > 0 && K2 >= 0, "cb_gemm_tf32: bad shape M=%d N=%d K=%d K2=%d", M, N, K, K2);
+  CB_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && (lda2 & 3) == 0 && (ldb2 & 3) == 0,
+             "cb_gemm_tf32: leading dimensions must be multiples of 4 (TMA needs 16-byte rows)");
+  CB_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(A2) |
+               reinterpret_cast<uintptr_t>(B2)) & 15) == 0, "cb_gemm_tf32: operands must be 16-byte aligned");
   if (split_k < 1) split_k = 1;
-  const int kb_total = (K + kBlockK - 1) / kBlockK;
+  const int kb_first = (K + kBlockK - 1) / kBlockK;
+  const int kb_total = kb_first + (K2 > 0 ? (K2 + kBlockK - 1) / kBlockK : 0);
   if (split_k > kb_total) split_k = kb_total;
   GemmParams p;
   p.C = C, p.workspace = workspace, p.bias = bias, p.ldc = ldc, p.M = M, p.N = N, p.K = K;
   p.k_blocks_total = kb_total;
+  p.k_blocks_first = kb_first;
   p.k_blocks_per_split = (kb_total + split_k - 1) / split_k;
   split_k = (kb_total + p.k_blocks_per_split - 1) / p.k_blocks_per_split;  // every split owns >= 1 k-block
   p.split_k = split_k;
@@ -390,12 +402,19 @@ extern "C" int cb_gemm_tf32(const float* A, long long lda, int a_mn, const float
                "cb_gemm_tf32: workspace too small (%lld < %lld)", workspace_elems, (long long)split_k * p.Mpad * p.Npad);
     p.bias = nullptr;
   }
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, ta2, tb2;
   // K-major operand: tensor [rows = M|N, cols = K], box 32 x 128 rows.  MN-major: tensor [rows = K, cols = M|N], box 32 x 32 rows.
   int e = a_mn ? make_tmap(&ta, A, K, M, lda, 32, true) : make_tmap(&ta, A, M, K, lda, 128, false);
   CB_REQUIRE(e == 0, "cb_gemm_tf32: cuTensorMapEncodeTiled failed for A (code %d)", e);
   e = b_mn ? make_tmap(&tb, B, K, N, ldb, 32, true) : make_tmap(&tb, B, N, K, ldb, 128, false);
   CB_REQUIRE(e == 0, "cb_gemm_tf32: cuTensorMapEncodeTiled failed for B (code %d)", e);
+  ta2 = ta, tb2 = tb;
+  if (K2 > 0) {
+    e = a_mn ? make_tmap(&ta2, A2, K2, M, lda2, 32, true) : make_tmap(&ta2, A2, M, K2, lda2, 128, false);
+    CB_REQUIRE(e == 0, "cb_gemm_tf32: cuTensorMapEncodeTiled failed for A2 (code %d)", e);
+    e = b_mn ? make_tmap(&tb2, B2, K2, N, ldb2, 32, true) : make_tmap(&tb2, B2, N, K2, ldb2, 128, false);
+    CB_REQUIRE(e == 0, "cb_gemm_tf32: cuTensorMapEncodeTiled failed for B2 (code %d)", e);
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const bool two = M > 128;
   // tile choice: MT = 2 accumulators when M > 128; BN = 256 only with a single accumulator
@@ -403,10 +422,10 @@ extern "C" int cb_gemm_tf32(const float* A, long long lda, int a_mn, const float
   int rc = 0;
 #define CB_DISPATCH(MT, BN)                                                              \
   do {                                                                                   \
-    if (!a_mn && !b_mn) rc = launch<MT, BN, false, false>(ta, tb, p, st);                 \
-    else if (!a_mn && b_mn) rc = launch<MT, BN, false, true>(ta, tb, p, st);              \
-    else if (a_mn && !b_mn) rc = launch<MT, BN, true, false>(ta, tb, p, st);              \
-    else rc = launch<MT, BN, true, true>(ta, tb, p, st);                                  \
+    if (!a_mn && !b_mn) rc = launch<MT, BN, false, false>(ta, tb, ta2, tb2, p, st);       \
+    else if (!a_mn && b_mn) rc = launch<MT, BN, false, true>(ta, tb, ta2, tb2, p, st);    \
+    else if (a_mn && !b_mn) rc = launch<MT, BN, true, false>(ta, tb, ta2, tb2, p, st);    \
+    else rc = launch<MT, BN, true, true>(ta, tb, ta2, tb2, p, st);                        \
   } while (0)
   if (two) CB_DISPATCH(2, 128);
   else if (wide) CB_DISPATCH(1, 256);
@@ -418,4 +437,11 @@ extern "C" int cb_gemm_tf32(const float* A, long long lda, int a_mn, const float
     splitk_reduce_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(workspace, split_k, p.Mpad, p.Npad, C, ldc, M, N, bias, accumulate);
   }
   return cb::check_launch("cb_gemm_tf32");
+}
+
+extern "C" int cb_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C,
+                            long long ldc, int M, int N, int K, const float* bias, int accumulate, int split_k,
+                            float* workspace, long long workspace_elems, void* stream) {
+  return cb_gemm_tf32_pair(A, lda, B, ldb, K, A, lda, B, ldb, 0, a_mn, b_mn, C, ldc, M, N, bias, accumulate, split_k, workspace,
+                           workspace_elems, stream);
 }

@@ -29,11 +29,16 @@ def set_backend(name: str):
     BACKEND = name
 
 
-def _grad_target(weight: torch.Tensor) -> torch.Tensor:
+def _grad_target(weight: torch.Tensor):
+    """(buffer the weight gradient is written to, what backward returns to autograd).  When the optimizer has given
+    the parameter a view of its flat gradient buffer, the GEMM writes there and autograd is handed None (so that
+    AccumulateGrad neither clones nor re-accumulates 68 MB); ``_cb_grad_direct`` tells ``collect_grads`` about it."""
     gv = getattr(weight, "_cb_grad_view", None)
     if gv is None:
-        gv = torch.empty_like(weight)
-    return gv
+        t = torch.empty_like(weight)
+        return t, t
+    weight._cb_grad_direct = True
+    return gv, None
 
 
 def _tma_ok(t: torch.Tensor) -> bool:
@@ -82,12 +87,12 @@ class _MultiLinearBig(torch.autograd.Function):
             H = w.shape[0]
             dw = db = dfeat = None
             if ctx.needs_input_grad[3 + 3 * i + 1]:
-                dw = _grad_target(w)
+                dw_buf, dw = _grad_target(w)
                 # dW[H, n_in] = dy^T[H, B] . x[B, n_in]: both operands stored with the reduction dim (B) as rows
-                ops.gemm_tf32(dy, x, H, n_in, B, a_mn=True, b_mn=True, out=dw[:, off:off + n_in], split_k=1)
+                ops.gemm_tf32(dy, x, H, n_in, B, a_mn=True, b_mn=True, out=dw_buf[:, off:off + n_in], split_k=1)
                 if off:
-                    dw[:, :off] = dy.t() @ feat
-            if need_dx:
+                    dw_buf[:, :off] = dy.t() @ feat
+            if need_dx and n != 2:
                 # dx[B, n_in] (+)= dy[B, H] . W[H, n_in]
                 ops.gemm_tf32(dy, w[:, off:off + n_in], B, n_in, H, b_mn=True, out=dx, accumulate=not first, split_k=1)
                 first = False
@@ -96,6 +101,11 @@ class _MultiLinearBig(torch.autograd.Function):
             if feat is not None and ctx.needs_input_grad[3 + 3 * i]:
                 dfeat = dy @ w[:, :off]
             grads += [dfeat, dw, db]
+        if need_dx and n == 2:
+            # dx = dy_0 . W_0 + dy_1 . W_1 in ONE launch: both products accumulate in the same TMEM tile
+            w0, w1 = weights
+            ops.gemm_tf32(dys[0].contiguous(), w0[:, off:off + n_in], B, n_in, w0.shape[0], b_mn=True, out=dx, split_k=1,
+                          a2=dys[1].contiguous(), b2=w1[:, off:off + n_in], K2=w1.shape[0])
         return (dx, None, None, *grads)
 
 

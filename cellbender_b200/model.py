@@ -158,8 +158,8 @@ class _ObsTerm(torch.autograd.Function):
         if gemm.BACKEND == "tcgen05":
             B, H = h_dec.shape
             d_h = ops.gemm_tf32(dlogits, w_out, B, H, G, b_mn=True) * g          # dlogits[B,G] . Wd[G,H], split-K
-            d_w = gemm._grad_target(w_out)
-            ops.gemm_tf32(dlogits, h_dec.contiguous(), G, H, B, a_mn=True, b_mn=True, out=d_w, split_k=1)  # dlogits^T . h
+            d_w_buf, d_w = gemm._grad_target(w_out)
+            ops.gemm_tf32(dlogits, h_dec.contiguous(), G, H, B, a_mn=True, b_mn=True, out=d_w_buf, split_k=1)  # dlogits^T . h
         else:
             d_h = (dl @ w_out) * g
             d_w = dl.t() @ h_dec  # [G, H]

@@ -288,7 +288,8 @@ _GEMM_WS = {}
 
 def gemm_tf32(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
               out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, accumulate: bool = False,
-              split_k: Optional[int] = None) -> torch.Tensor:
+              split_k: Optional[int] = None, a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None,
+              K2: int = 0) -> torch.Tensor:
     """C[M,N] (=,+=) A[M,K] @ B[N,K]^T (+ bias) through cb_gemm_tf32.
 
     a: stored [M, >=K] (a_mn=False) or [K, >=M] (a_mn=True), last dim contiguous, row stride % 4 == 0; same for b."""
@@ -299,7 +300,7 @@ def gemm_tf32(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn: bo
     if out is None:
         out = torch.empty((M, round_up(N, 4)), dtype=torch.float32, device=dev)[:, :N]
     if split_k is None:
-        split_k = int(L.raw("cb_gemm_tf32_suggest_split")(M, N, K))
+        split_k = int(L.raw("cb_gemm_tf32_suggest_split")(M, N, K + K2))
     ws_elems = int(L.raw("cb_gemm_tf32_workspace_elems")(M, N, split_k))
     ws = None
     if ws_elems:
@@ -308,6 +309,12 @@ def gemm_tf32(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn: bo
         if ws is None or ws.numel() < ws_elems:
             ws = torch.empty(ws_elems, dtype=torch.float32, device=dev)
             _GEMM_WS[key] = ws
-    L.call("cb_gemm_tf32", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out), out.stride(0), M, N, K,
-           ptr(bias), int(accumulate), split_k, ptr(ws), ws_elems, current_stream())
+    if a2 is None:
+        L.call("cb_gemm_tf32", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out), out.stride(0), M, N, K,
+               ptr(bias), int(accumulate), split_k, ptr(ws), ws_elems, current_stream())
+    else:  # C = A B^T + A2 B2^T in one launch (shared TMEM accumulator)
+        assert a2.stride(-1) == 1 and b2.stride(-1) == 1 and K2 > 0
+        L.call("cb_gemm_tf32_pair", ptr(a), a.stride(0), ptr(b), b.stride(0), K, ptr(a2), a2.stride(0), ptr(b2), b2.stride(0), K2,
+               int(a_mn), int(b_mn), ptr(out), out.stride(0), M, N, ptr(bias), int(accumulate), split_k, ptr(ws), ws_elems,
+               current_stream())
     return out

@@ -89,13 +89,15 @@ class FlatClippedAdam:
     def zero_grad(self):
         for p in self.params:
             p.grad = None
+            p._cb_grad_direct = False
 
     def collect_grads(self):
         """Gather the autograd-produced gradients into the flat buffer (missing gradient = 0)."""
         src, dst = [], []
         for p, gv in zip(self.params, self.grad_views):
             if p.grad is None:
-                gv.zero_()
+                if not getattr(p, "_cb_grad_direct", False):  # else: a GEMM epilogue already wrote this gradient
+                    gv.zero_()
             elif p.grad.data_ptr() != gv.data_ptr():
                 src.append(p.grad)
                 dst.append(gv)

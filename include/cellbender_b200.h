@@ -91,6 +91,12 @@ int cb_bn0_backward(const float* x, long long ldx, const float* dy, long long ld
  * (cb_gemm_tf32_workspace_elems floats), summed in a fixed order.                                            */
 long long cb_gemm_tf32_workspace_elems(int M, int N, int split_k);
 int cb_gemm_tf32_suggest_split(int M, int N, int K);
+/* C = A B^T + A2 B2^T (two operand pairs share one TMEM accumulator; K2 = 0 disables the second pair): the input
+ * gradient of two layers that read the same input, dx = dy1 W1 + dy2 W2, in one launch with no read-modify-write. */
+int cb_gemm_tf32_pair(const float* A, long long lda, const float* B, long long ldb, int K, const float* A2,
+                      long long lda2, const float* B2, long long ldb2, int K2, int a_mn, int b_mn, float* C,
+                      long long ldc, int M, int N, const float* bias, int accumulate, int split_k, float* workspace,
+                      long long workspace_elems, void* stream);
 int cb_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C,
                  long long ldc, int M, int N, int K, const float* bias, int accumulate, int split_k, float* workspace,
                  long long workspace_elems, void* stream);

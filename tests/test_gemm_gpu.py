@@ -62,3 +62,19 @@ def test_gemm_training_step_shapes():
     _check(H, G, Bn, True, True, split_k=1)           # dW = dY^T[H,B] . X[B,G]                (both MN-major)
     _check(G, H, Bn, True, True, split_k=1)           # dWd = dlogits^T[G,B] . h[B,H]
     _check(Bn, G, H, False, True, split_k=1)          # dX = dY[B,H] . W[H,G]                  (B MN-major)
+
+
+def test_gemm_two_operand_pairs_share_the_accumulator():
+    """C = A1 B1^T + A2 B2^T in one launch (dx of two layers reading the same input)."""
+    from cellbender_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(3)
+    B, H, G = 255, 512, 33538
+    dy1, dy2 = torch.randn(B, H, device=DEV, generator=g), torch.randn(B, H, device=DEV, generator=g)
+    ld = ops.round_up(G + 4, 4)
+    W1, W2 = torch.randn(H, ld, device=DEV, generator=g), torch.randn(H, ld, device=DEV, generator=g)
+    out = ops.alloc_rows(B, G, DEV)
+    ops.gemm_tf32(dy1, W1[:, 4:4 + G], B, G, H, b_mn=True, out=out[:, :G], split_k=1, a2=dy2, b2=W2[:, 4:4 + G], K2=H)
+    ref = _tf32_trunc(dy1).double() @ _tf32_trunc(W1[:, 4:4 + G].contiguous()).double() \\
+        + _tf32_trunc(dy2).double() @ _tf32_trunc(W2[:, 4:4 + G].contiguous()).double()
+    assert float((out[:, :G].double() - ref).abs().max()) / float(ref.abs().max()) < 2e-5
