@@ -54,30 +54,29 @@ def broadcast_encoder_offsets(model):
     enc.offset = {"logit_p": float(t[0]), "epsilon": float(t[1])}
 
 
+def all_gather_varlen(t: torch.Tensor, world_size: int) -> torch.Tensor:
+    """Concatenate 1-D tensors of different lengths from all ranks, in rank order (pads to the longest piece)."""
+    if world_size <= 1:
+        return t
+    n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world_size)]
+    dist.all_gather(sizes, n)
+    n_max = int(max(int(s) for s in sizes))
+    buf = torch.zeros(n_max, dtype=t.dtype, device=t.device)
+    buf[: t.numel()] = t
+    outs = [torch.zeros_like(buf) for _ in range(world_size)]
+    dist.all_gather(outs, buf)
+    return torch.cat([o[: int(s)] for o, s in zip(outs, sizes)])
+
+
 def gather_posterior(piece, world_size: int):
     """All-gather the ranks' DevicePosteriorCOO pieces (variable length) and concatenate in rank order."""
     from .estimation import DevicePosteriorCOO
 
     if world_size <= 1:
         return piece
-    dev = piece.m.device
-    sizes = torch.tensor([piece.m.numel(), piece.off_m.numel()], dtype=torch.int64, device=dev)
-    all_sizes = [torch.zeros_like(sizes) for _ in range(world_size)]
-    dist.all_gather(all_sizes, sizes)
-    n_max = int(max(s[0] for s in all_sizes))
-    o_max = int(max(s[1] for s in all_sizes))
-
-    def gather(t: torch.Tensor, n_pad: int, counts: List[int]):
-        buf = torch.zeros(n_pad, dtype=t.dtype, device=dev)
-        buf[: t.numel()] = t
-        outs = [torch.zeros_like(buf) for _ in range(world_size)]
-        dist.all_gather(outs, buf)
-        return torch.cat([o[:c] for o, c in zip(outs, counts)])
-
-    nc = [int(s[0]) for s in all_sizes]
-    oc = [int(s[1]) for s in all_sizes]
-    out = DevicePosteriorCOO(gather(piece.m, n_max, nc), gather(piece.c, n_max, nc), gather(piece.log_prob, n_max, nc),
-                             gather(piece.off_m, o_max, oc), gather(piece.off_v, o_max, oc), piece.n_cols)
+    g = lambda t: all_gather_varlen(t, world_size)
+    out = DevicePosteriorCOO(g(piece.m), g(piece.c), g(piece.log_prob), g(piece.off_m), g(piece.off_v), piece.n_cols)
     out.ensure_sorted()
     if out.off_m.numel() > 1:
         o = torch.argsort(out.off_m)

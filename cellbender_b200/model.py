@@ -111,6 +111,11 @@ class ParamStore(nn.Module):
     def __getitem__(self, name):
         return self.get(name)
 
+    def all(self) -> Dict[str, torch.Tensor]:
+        """Every constrained value, computed once (one step reads each several times; the stick-breaking transform of
+        chi_ambient alone is ~15 kernels)."""
+        return {k: self.get(k) for k in self.unconstrained.keys()}
+
 
 def _masked_lower_median(values: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """values[mask].median() (torch.median = lower median) without a host sync: sort with +inf padding and
@@ -257,8 +262,10 @@ class RemoveBackgroundPyroModel(nn.Module):
         ps.setup("phi_scale", self.phi_scale_prior, constraints.positive)
         self.param_store = ps
         self.to(dev)
+        self._d_empty_loc_now = None
         if "other" in encoder:
-            encoder["other"].d_empty_loc_fn = lambda: self.param_store["d_empty_loc"]
+            encoder["other"].d_empty_loc_fn = lambda: (self._d_empty_loc_now if self._d_empty_loc_now is not None
+                                                       else self.param_store["d_empty_loc"])
         self._obs_ctx = None
         self._bufs: Dict[int, dict] = {}
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -285,9 +292,9 @@ class RemoveBackgroundPyroModel(nn.Module):
         return self._bufs[key]
 
     # ---- the ELBO --------------------------------------------------------------------------------------
-    def draw_guide_samples(self, inp: EncoderInputs, enc: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    def draw_guide_samples(self, inp: EncoderInputs, enc: Dict[str, torch.Tensor], ps=None) -> Dict[str, torch.Tensor]:
         """rsample every continuous guide site, in the guide's order (model.py:506-567)."""
-        ps = self.param_store
+        ps = self.param_store if ps is None else ps
         B = inp.feats.shape[0]
         phi_loc, phi_scale = ps["phi_loc"], ps["phi_scale"]
         s = {"phi": Gamma(phi_loc.pow(2) / phi_scale.pow(2), phi_loc / phi_scale.pow(2)).rsample()}
@@ -303,16 +310,18 @@ class RemoveBackgroundPyroModel(nn.Module):
 
     def elbo_terms(self, csr: ops.DeviceCSR, row_ids: torch.Tensor, inp: EncoderInputs,
                    samples: Optional[Dict[str, torch.Tensor]] = None, row_keep_scale: Optional[torch.Tensor] = None,
-                   sampler=None) -> Dict[str, torch.Tensor]:
+                   sampler=None, params: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """All terms of the ELBO for one minibatch.  Returns a dict of scalar tensors whose
         sum is the ELBO, plus 'loss' = -ELBO.  ``samples``/``sampler`` let tests inject fixed noise."""
-        ps = self.param_store
+        ps = self.param_store.all() if params is None else params
         B = inp.feats.shape[0]
         chi_ambient = ps["chi_ambient"]
+        self._d_empty_loc_now = ps["d_empty_loc"]
         enc = self.encoder(x=inp, chi_ambient=chi_ambient.detach(), cell_prior_log=self.d_cell_loc_prior,
                            row_keep_scale=row_keep_scale)
+        self._d_empty_loc_now = None
         if samples is None:
-            samples = (sampler or self.draw_guide_samples)(inp, enc)
+            samples = sampler(inp, enc) if sampler is not None else self.draw_guide_samples(inp, enc, ps)
         phi, d_empty, v, z, d_cell, epsilon = (samples[k] for k in ("phi", "d_empty", "p_logit_reg", "z", "d_cell", "epsilon"))
         rho = samples["rho"] if self.include_rho else torch.zeros_like(d_cell)
         p_y = enc["p_y"]

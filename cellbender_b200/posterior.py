@@ -20,7 +20,7 @@ import scipy.sparse as sp
 import torch
 from torch.distributions import Beta, Gamma, LogNormal, Normal
 
-from . import consts, ops
+from . import consts, gemm, ops
 from .estimation import DevicePosteriorCOO, EstimationMethod, IndexConverter
 from .model import RemoveBackgroundPyroModel
 from .vae import EncoderInputs
@@ -168,9 +168,11 @@ class Posterior:
     @torch.no_grad()
     def device_posterior(self, n_samples: int = 20, y_map: bool = True, n_counts_max: int = 20,
                          smallest_log_probability: float = -10.0, cell_subset: Optional[np.ndarray] = None,
-                         lambda_multiplier: float = 1.0) -> DevicePosteriorCOO:
+                         lambda_multiplier: float = 1.0, seed: Optional[int] = None) -> DevicePosteriorCOO:
         """The posterior COO, computed and left on the device.  ``cell_subset`` (indices into the p > 0.5 cell list)
-        restricts the computation (used for barcode sharding across GPUs)."""
+        restricts the computation (used for barcode sharding across GPUs).  ``seed``: reseed the generator per chunk
+        with seed + first cell index, which makes the Monte-Carlo draws a function of the cell chunk only (sharded and
+        unsharded runs then agree bit for bit when shard boundaries fall on chunk boundaries)."""
         m = self.vi_model
         csr = self._device_csr()
         G = csr.n_genes
@@ -212,13 +214,19 @@ class Posterior:
             idx = sel[start:start + self.cells_per_chunk]
             rows = torch.as_tensor(cell_rows_all[idx], device=self.device)
             Bc = rows.numel()
+            if seed is not None:
+                torch.manual_seed(int(seed) + int(idx[0]))
             _, enc = self._encode(rows)
             z, a_mu, c_a, c_b, alpha = self.sample_rate_coefficients(enc, S, y_map=y_map)
             h = m.decoder.hidden(z.reshape(S * Bc, -1))
             if logits is None or logits.shape[0] < S * Bc:
                 logits = torch.zeros((S * self.cells_per_chunk, ld), device=self.device)
             lg = logits[: S * Bc]
-            torch.addmm(lin.bias, h, lin.weight.t(), out=lg[:, :G])  # ONE decoder GEMM for all samples of the chunk
+            # ONE decoder GEMM for all samples of the chunk ([S * Bc, 512] x [512, G])
+            if gemm.BACKEND == "tcgen05":
+                ops.gemm_tf32(h.contiguous(), lin.weight, S * Bc, G, lin.weight.shape[1], out=lg[:, :G], bias=lin.bias, split_k=1)
+            else:
+                torch.addmm(lin.bias, h, lin.weight.t(), out=lg[:, :G])
             lse = ops.row_logsumexp(lg, G)
             idx_t = torch.as_tensor(idx, device=self.device)
             pieces.append(ops.posterior_coo(

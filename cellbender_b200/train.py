@@ -60,8 +60,10 @@ class SVI:
         return (chi / torch.linalg.vector_norm(chi)).contiguous()
 
     def loss_terms(self, batch):
-        inp = batch.encoder_inputs(self._ambient_unit_vector())
-        return self.model.elbo_terms(batch.loader.csr, batch.row_ids, inp)
+        params = self.model.param_store.all()  # every pyro.param transform once per step
+        chi = params["chi_ambient"].detach()
+        inp = batch.encoder_inputs((chi / torch.linalg.vector_norm(chi)).contiguous())
+        return self.model.elbo_terms(batch.loader.csr, batch.row_ids, inp, params=params)
 
     def _step_eager(self, batch) -> torch.Tensor:
         self.optim.zero_grad()

@@ -1,0 +1,71 @@
+"""N > 1 host logic on the CPU with gloo, world_size 2: shard arithmetic, the gradient exchange (SUM all-reduce of the
+flat buffer), the encoder-offset broadcast and the variable-length gather of posterior pieces.  (The kernels themselves
+need a GPU; the multi-GPU numbers come from `gpurun --gpus N` runs of bench.py / tests/test_multi_gpu.py.)"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cellbender_b200 import dp
+
+
+def test_shards_are_disjoint_and_complete():
+    for n, w in ((22500, 2), (22500, 8), (7, 4), (8000, 3)):
+        rows = [dp.shard_rows(n, r, w) for r in range(w)]
+        cells = [dp.shard_cells(n, r, w) for r in range(w)]
+        for parts in (rows, cells):
+            cat = np.concatenate(parts)
+            assert cat.size == n and np.array_equal(np.sort(cat), np.arange(n))
+        assert all(np.all(np.diff(c) == 1) for c in cells if c.size > 1)  # contiguous -> COO pieces stay (m, c)-sorted
+        assert max(len(r) for r in rows) - min(len(r) for r in rows) <= 1
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # variable-length gather keeps rank order
+        t = torch.arange(3 + 2 * rank, dtype=torch.int64) + 100 * rank
+        got = dp.all_gather_varlen(t, world)
+        # gradient exchange: SUM of the flat buffers
+        class Opt:  # the two attributes the hook touches
+            flat_g = torch.full((5,), float(rank + 1))
+
+        class Svi:
+            optim = Opt()
+            after_backward = None
+
+        svi = dp.attach(Svi(), world)
+        svi.after_backward(svi.optim)
+        # encoder offsets broadcast from rank 0
+        class Enc:
+            offset = {"logit_p": 1.5, "epsilon": -0.25} if rank == 0 else None
+
+        class Model:
+            device = "cpu"
+            encoder = {"other": Enc()}
+
+        m = Model()
+        dp.broadcast_encoder_offsets(m)
+        q.put((rank, got.tolist(), Svi.optim.flat_g.tolist(), m.encoder["other"].offset))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_exchange_on_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    expect = list(range(3)) + [100 + i for i in range(5)]
+    for rank, gathered, flat_g, offset in res:
+        assert gathered == expect
+        assert flat_g == [3.0] * 5  # 1 + 2
+        assert offset == {"logit_p": 1.5, "epsilon": -0.25}

@@ -75,6 +75,6 @@ def test_gemm_two_operand_pairs_share_the_accumulator():
     W1, W2 = torch.randn(H, ld, device=DEV, generator=g), torch.randn(H, ld, device=DEV, generator=g)
     out = ops.alloc_rows(B, G, DEV)
     ops.gemm_tf32(dy1, W1[:, 4:4 + G], B, G, H, b_mn=True, out=out[:, :G], split_k=1, a2=dy2, b2=W2[:, 4:4 + G], K2=H)
-    ref = _tf32_trunc(dy1).double() @ _tf32_trunc(W1[:, 4:4 + G].contiguous()).double() \\
+    ref = _tf32_trunc(dy1).double() @ _tf32_trunc(W1[:, 4:4 + G].contiguous()).double() \
         + _tf32_trunc(dy2).double() @ _tf32_trunc(W2[:, 4:4 + G].contiguous()).double()
     assert float((out[:, :G].double() - ref).abs().max()) / float(ref.abs().max()) < 2e-5

@@ -1,0 +1,82 @@
+"""-m gpu, needs >= 2 GPUs (skipped otherwise): data-parallel training keeps replicas identical; barcode-sharded
+posterior + gather equals the single-GPU posterior."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _dataset():
+    from cellbender_b200 import synth
+
+    sim = synth.simulate_dataset(n_genes=256, cells_of_each_type=[100, 100], n_droplets=1500, cell_mean_umi=2000.0,
+                                 empty_mean_umi=60.0, dirichlet_alpha=0.5, seed=0, device="cpu", cell_chunk=128)
+    return synth.prepare_dataset(sim, expected_cells=200, total_droplets_included=500)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    try:
+        from cellbender_b200 import dp, run
+        from cellbender_b200.posterior import Posterior
+
+        ds = _dataset()
+        args = run.default_args(epochs=3, z_dim=8, z_hidden_dims=[32], learning_rate=1e-3)
+        model, opt, svi, tl, te = run.setup_inference(ds, args, device=dev, rank=rank, world_size=world)
+        dp.attach(svi, world)
+        model.train()
+        p0 = opt.flat_p.clone()
+        n = 0
+        for _ in range(2):
+            for b in tl:
+                svi.step(b)
+                if n == 0:
+                    svi.sync_offsets()
+                n += 1
+        torch.cuda.synchronize()
+        flat = opt.flat_p.detach().clone()
+        others = [torch.zeros_like(flat) for _ in range(world)]
+        dist.all_gather(others, flat)
+        same = all(torch.equal(others[0], o) for o in others)
+        moved = float((flat - p0).abs().max())
+        # posterior: shards + gather vs everything on one rank, seeded per chunk, shard boundaries on chunk boundaries
+        model.eval()
+        post = Posterior(ds, model, cells_per_chunk=32)
+        n_cells = 128
+        post._latents = {"p": np.concatenate([np.ones(n_cells), np.zeros(ds.analyzed_barcode_inds.size - n_cells)])}
+        piece = post.device_posterior(cell_subset=dp.shard_cells(n_cells, rank, world), seed=7, n_samples=4)
+        full = dp.gather_posterior(piece, world)
+        ok_post = None
+        if rank == 0:
+            ref = post.device_posterior(seed=7, n_samples=4)
+            ok_post = (torch.equal(ref.m, full.m) and torch.equal(ref.c, full.c) and torch.equal(ref.log_prob, full.log_prob)
+                       and torch.equal(ref.off_m, full.off_m) and torch.equal(ref.off_v, full.off_v) and ref.m.numel() > 1000)
+        q.put((rank, same, moved, ok_post, len(svi._graphs)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_data_parallel_replicas_stay_identical_and_sharded_posterior_matches():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=600) for _ in range(world))
+    [p.join(timeout=120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, same, moved, ok_post, n_graphs in res:
+        assert same, "parameter replicas diverged"
+        assert moved > 0
+        assert n_graphs >= 1  # the all-reduce was captured inside the CUDA graph
+    assert res[0][3] is True
