@@ -4,9 +4,10 @@ single-GPU only ("CellBender only makes use of 1 GPU", docs/source/troubleshooti
 surface; SURVEY.md section 8e states the semantics.
 
 Training (data parallel): every rank holds the full parameter set and the surely-empty droplets, and a disjoint
-shard of the analysed droplets (``shard_rows``).  Each step every rank runs its own 255-droplet minibatch; the ELBO is
+shard of the analysed droplets (``shard_rows``).  Each step every rank runs its own 255-droplet minibatch (forward + backward as one CUDA-graph replay); the ELBO is
 a plain SUM over droplets (train.py:56-63), so the exchange is ONE all-reduce(SUM) of the flat fp32 gradient buffer
-(69.4 M values at the PBMC8k shape), after which every rank applies the identical fused ClippedAdam update.
+(69.4 M values at the PBMC8k shape), issued eagerly between graph replays, after which every rank applies the
+identical fused ClippedAdam update.
 Stated consequences: the global minibatch is 255 x world_size droplets; an epoch is n_batches(shard) steps, so
 OneCycleLR's total_steps shrinks by world_size; BatchNorm statistics, Dropout1d masks, epsilon medians and the
 reparameterisation noise are per-rank (different CUDA seeds per rank); the encoder's first-forward offset heuristic

@@ -65,16 +65,20 @@ class SVI:
         inp = batch.encoder_inputs((chi / torch.linalg.vector_norm(chi)).contiguous())
         return self.model.elbo_terms(batch.loader.csr, batch.row_ids, inp, params=params)
 
-    def _step_eager(self, batch) -> torch.Tensor:
+    def _forward_backward(self, batch) -> torch.Tensor:
         self.optim.zero_grad()
         terms = self.loss_terms(batch)
         loss = terms["loss"]
         loss.backward()
         self.optim.collect_grads()
+        return loss.detach()
+
+    def _step_eager(self, batch) -> torch.Tensor:
+        loss = self._forward_backward(batch)
         if self.after_backward is not None:
             self.after_backward(self.optim)
         self.optim.step()
-        return loss.detach()
+        return loss
 
     def step(self, batch: MiniBatch) -> torch.Tensor:
         """One training step; returns the loss (-ELBO, summed over the minibatch) as a 0-dim device tensor."""
@@ -93,7 +97,12 @@ class SVI:
                              f"{self.optim.total_steps}")
         graph.replay()
         _cabi.lib().launch_count += n_launch  # kernels of ours inside the replayed graph
-        self.optim.host_steps += 1
+        if self.after_backward is not None:
+            # data parallel: the gradient all-reduce (NCCL) and the fused Adam run eagerly between graph replays
+            self.after_backward(self.optim)
+            self.optim.step()
+        else:
+            self.optim.host_steps += 1
         return loss
 
     def _capture(self, batch: MiniBatch):
@@ -103,15 +112,17 @@ class SVI:
         snap_p, snap_m, snap_v = self.optim.flat_p.clone(), self.optim.flat_m.clone(), self.optim.flat_v.clone()
         snap_step, host_steps = self.optim.step_count.clone(), self.optim.host_steps
         bn_state = {k: v.clone() for k, v in self.model.state_dict().items() if "running_" in k or "num_batches" in k}
+        # single GPU: the whole step is one graph.  Data parallel: forward + backward + gradient collection only.
+        body = self._step_eager if self.after_backward is None else self._forward_backward
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            self._step_eager(static)
+            body(static)
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         n0 = _cabi.lib().launch_count
         with torch.cuda.graph(graph):
-            loss = self._step_eager(static)
+            loss = body(static)
         n_launch = _cabi.lib().launch_count - n0
         _cabi.lib().launch_count = n0  # capture records launches, it does not run them
         with torch.no_grad():

@@ -72,11 +72,11 @@ def test_data_parallel_replicas_stay_identical_and_sharded_posterior_matches():
     port = 29700 + os.getpid() % 2000
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     [p.start() for p in procs]
-    res = sorted(q.get(timeout=600) for _ in range(world))
-    [p.join(timeout=120) for p in procs]
+    res = sorted(q.get(timeout=150) for _ in range(world))
+    [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     for rank, same, moved, ok_post, n_graphs in res:
         assert same, "parameter replicas diverged"
         assert moved > 0
-        assert n_graphs >= 1  # the all-reduce was captured inside the CUDA graph
+        assert n_graphs >= 1  # forward + backward ran as CUDA-graph replays around the eager all-reduce
     assert res[0][3] is True
