@@ -10,7 +10,8 @@ a plain SUM over droplets (train.py:56-63), so the exchange is ONE all-reduce(SU
 identical fused ClippedAdam update.
 Stated consequences: the global minibatch is 255 x world_size droplets; an epoch is n_batches(shard) steps, so
 OneCycleLR's total_steps shrinks by world_size; BatchNorm statistics, Dropout1d masks, epsilon medians and the
-reparameterisation noise are per-rank (different CUDA seeds per rank); the encoder's first-forward offset heuristic
+reparameterisation noise are per-rank (different CUDA seeds per rank; ``sync_buffers`` averages the BN running
+statistics before evaluation); the encoder's first-forward offset heuristic
 (encoder.py:300-309) is computed on rank 0 and broadcast.
 
 Posterior / estimation: ``shard_cells`` splits the p > 0.5 cell list into contiguous ranges; ranks compute their COO
@@ -45,6 +46,21 @@ def attach(svi, world_size: int):
     svi.after_backward = lambda opt: dist.all_reduce(opt.flat_g, op=dist.ReduceOp.SUM)
     svi.sync_offsets = lambda: broadcast_encoder_offsets(svi.model)
     return svi
+
+
+@torch.no_grad()
+def sync_buffers(model, world_size: int):
+    """Average the BatchNorm running statistics over ranks (they are updated from per-rank minibatches and are not part
+    of the gradient exchange).  Call at the end of an epoch / before the posterior so every rank holds the same eval
+    model; ``num_batches_tracked`` takes the maximum."""
+    if world_size <= 1:
+        return
+    for _, buf in model.named_buffers():
+        if buf.is_floating_point():
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            buf.div_(world_size)
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.MAX)
 
 
 def broadcast_encoder_offsets(model):

@@ -48,6 +48,7 @@ def _worker(rank, world, port, q):
         same = all(torch.equal(others[0], o) for o in others)
         moved = float((flat - p0).abs().max())
         # posterior: shards + gather vs everything on one rank, seeded per chunk, shard boundaries on chunk boundaries
+        dp.sync_buffers(model, world)
         model.eval()
         post = Posterior(ds, model, cells_per_chunk=32)
         n_cells = 128
