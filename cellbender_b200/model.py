@@ -10,7 +10,7 @@ is absent, PARITY OF THE ELBO IS UNPINNED against pyro itself -- it is pinned ag
 (oracle/elbo.py), term by term.
 
 Parameter handling mirrors pyro's param store: every ``pyro.param`` site is an UNCONSTRAINED nn.Parameter plus a
-``torch.distributions.transform_to(constraint)`` (exp / sigmoid-interval / stick-breaking), which is what pyro
+``torch.distributions.transform_to(constraint)`` (exp / sigmoid-interval / softmax), which is what pyro
 optimises (model.py:245-249, 468-513).
 """
 import math
@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.distributions import Beta, Gamma, LogNormal, Normal, constraints, transform_to
 
-from . import consts, gemm, ops
+from . import consts, gemm, latent, ops
 from .exceptions import NanException
 from .vae import CompositeEncoder, EncoderInputs
 
@@ -130,7 +130,8 @@ def _masked_lower_median(values: torch.Tensor, mask: torch.Tensor) -> torch.Tens
 class _ObsTerm(torch.autograd.Function):
     """sum_b sum_k w[b,k] * L[b,k] with L = (L_y1, L_y0, L_E) of the fused observation kernel.  All gradients
     are produced by the same launch that produces the value, so backward only hands them out (upstream
-    gradient must be the scalar 1 that ``loss.backward()`` supplies; it is applied to the small tensors)."""
+    gradient must be the scalar 1 that ``loss.backward()`` supplies; it is applied to the small tensors).
+    ``w`` = d loss / d L are the enumeration weights -(q1, q0, 0.01 q0); their gradient L carries d/d p_y."""
 
     @staticmethod
     def forward(ctx, h_dec, w_out, b_out, chi_ambient, coef, alpha, w, model):
@@ -143,7 +144,8 @@ class _ObsTerm(torch.autograd.Function):
         else:
             torch.addmm(b_out, h_dec, w_out.t(), out=logits[:, :G])  # library fp32 GEMM (parity-test back-end)
         chi_a = bufs["chi_a"]
-        chi_a[:G].copy_(chi_ambient)
+        if chi_ambient.data_ptr() != chi_a.data_ptr():
+            chi_a[:G].copy_(chi_ambient)
         oo = bufs["obs_out"]
         out = ops.elbo_obs(csr, row_ids, logits, chi_a, bufs["chi_b"], coef.contiguous(), alpha.reshape(1).contiguous(),
                            w.contiguous(), out={"sums": oo["sums"][:B], "dlogits": oo["dlogits"][:B], "qamb": oo["qamb"][:B],
@@ -152,6 +154,7 @@ class _ObsTerm(torch.autograd.Function):
         L = sums[:, :3]
         ctx.save_for_backward(h_dec, w_out, sums, w, out["dlogits"], out["dchi_ambient"])
         ctx.G = G
+        ctx.alpha_shape = alpha.shape
         ctx.mark_non_differentiable(L)
         return (w * L).sum(), L
 
@@ -172,8 +175,9 @@ class _ObsTerm(torch.autograd.Function):
         w1, w0, wE = w[:, 0], w[:, 1], w[:, 2]
         d_coef = torch.stack((w1 * sums[:, 3], w1 * sums[:, 4], w1 * sums[:, 5], w0 * sums[:, 7], w0 * sums[:, 8],
                               wE * sums[:, 10], wE * sums[:, 11]), dim=1) * g
-        d_alpha = ((w1 * sums[:, 6] + w0 * sums[:, 9]).sum() * g).reshape(())
-        return d_h, d_w, d_b, dchi_amb * g, d_coef, d_alpha, None, None
+        d_alpha = ((w1 * sums[:, 6] + w0 * sums[:, 9]).sum() * g).reshape(ctx.alpha_shape)
+        d_weights = (sums[:, :3] * g) if ctx.needs_input_grad[6] else None
+        return d_h, d_w, d_b, dchi_amb * g, d_coef, d_alpha, d_weights, None
 
 
 class RemoveBackgroundPyroModel(nn.Module):
@@ -243,6 +247,10 @@ class RemoveBackgroundPyroModel(nn.Module):
         self.empty_UMI_threshold = scalar(empty_UMI_threshold)
         self.rho_alpha_prior = scalar(rho_alpha_prior)
         self.rho_beta_prior = scalar(rho_beta_prior)
+        # the same priors as python floats: by-value arguments of the fused latent kernels (latent.host_consts)
+        self._host = {k: float(getattr(self, k)) for k in (
+            "d_cell_loc_prior", "d_cell_scale_prior", "epsilon_prior", "phi_conc_prior", "phi_rate_prior", "rho_alpha_prior",
+            "rho_beta_prior", "d_empty_loc_prior", "d_empty_scale_prior", "p_logit_prior", "empty_UMI_threshold")}
         # python-float distribution arguments would be host->device copies inside a captured CUDA graph
         self._k = {"p_logit_scale": scalar(consts.P_LOGIT_SCALE), "reg_logit_mean": scalar(consts.REG_LOGIT_MEAN),
                    "neg_reg_logit_mean": scalar(-consts.REG_LOGIT_MEAN), "reg_logit_soft_scale": scalar(consts.REG_LOGIT_SOFT_SCALE),
@@ -285,109 +293,54 @@ class RemoveBackgroundPyroModel(nn.Module):
             chi_b[:G] = self.avg_gene_expression
             self._bufs[key] = {
                 "cap": cap, "logits": torch.zeros((cap, ld), device=dev), "chi_a": torch.zeros(ld, device=dev),
-                "chi_b": chi_b,
+                "chi_unit": torch.zeros(ld, device=dev), "chi_b": chi_b,
                 "obs_out": {"sums": torch.empty((cap, 12), device=dev), "dlogits": torch.zeros((cap, ld), device=dev),
                             "qamb": torch.empty((cap, ld), device=dev), "dchi_ambient": torch.empty(G, device=dev),
                             "lse": torch.empty(cap, device=dev), "nan_flag": self.nan_flag}}
         return self._bufs[key]
 
     # ---- the ELBO --------------------------------------------------------------------------------------
-    def draw_guide_samples(self, inp: EncoderInputs, enc: Dict[str, torch.Tensor], ps=None) -> Dict[str, torch.Tensor]:
-        """rsample every continuous guide site, in the guide's order (model.py:506-567)."""
-        ps = self.param_store if ps is None else ps
-        B = inp.feats.shape[0]
-        phi_loc, phi_scale = ps["phi_loc"], ps["phi_scale"]
-        s = {"phi": Gamma(phi_loc.pow(2) / phi_scale.pow(2), phi_loc / phi_scale.pow(2)).rsample()}
-        if self.include_rho:
-            s["rho"] = Beta(ps["rho_alpha"], ps["rho_beta"]).expand([B]).rsample()
-        s["d_empty"] = LogNormal(ps["d_empty_loc"], ps["d_empty_scale"]).expand([B]).rsample()
-        s["p_logit_reg"] = Normal(enc["p_y"], self._k["p_logit_scale"]).rsample()
-        s["z"] = Normal(enc["z"]["loc"], enc["z"]["scale"]).rsample()
-        prob = enc["p_y"].sigmoid().detach()
-        s["d_cell"] = LogNormal(prob * enc["d_loc"] + (1 - prob) * self.d_cell_loc_prior, ps["d_cell_scale"]).rsample()
-        s["epsilon"] = Gamma((prob * enc["epsilon"] + (1 - prob)) * self.epsilon_prior, self.epsilon_prior).rsample()
-        return s
+    def ambient(self, B: int = 8):
+        """(chi_ambient [G] with autograd history to the unconstrained parameter, chi_ambient / ||chi_ambient||_2):
+        ``pyro.param("chi_ambient", constraint=simplex)`` (model.py:245-249) and the unit vector of the encoder's
+        ambient-overlap feature (vae/encoder.py:266-270), from one kernel, written into the step's work buffers."""
+        bufs = self._work_buffers(B)
+        G = self.n_genes
+        chi = latent.simplex_param(self.param_store.unconstrained["chi_ambient"], bufs)
+        return chi, bufs["chi_unit"][:G]
 
     def elbo_terms(self, csr: ops.DeviceCSR, row_ids: torch.Tensor, inp: EncoderInputs,
-                   samples: Optional[Dict[str, torch.Tensor]] = None, row_keep_scale: Optional[torch.Tensor] = None,
-                   sampler=None, params: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+                   noise: Optional[Dict[str, torch.Tensor]] = None, row_keep_scale: Optional[torch.Tensor] = None,
+                   chi_ambient: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """All terms of the ELBO for one minibatch.  Returns a dict of scalar tensors whose
-        sum is the ELBO, plus 'loss' = -ELBO.  ``samples``/``sampler`` let tests inject fixed noise."""
-        ps = self.param_store.all() if params is None else params
+        sum is the ELBO, plus 'loss' = -ELBO.  ``noise`` lets tests inject fixed base randomness
+        (keys z, d_cell, d_empty, p_logit_reg: standard normals; phi, epsilon: standard-gamma draws at the current
+        concentrations; rho: the Beta draw)."""
         B = inp.feats.shape[0]
-        chi_ambient = ps["chi_ambient"]
-        self._d_empty_loc_now = ps["d_empty_loc"]
-        enc = self.encoder(x=inp, chi_ambient=chi_ambient.detach(), cell_prior_log=self.d_cell_loc_prior,
-                           row_keep_scale=row_keep_scale)
+        if chi_ambient is None:
+            chi_ambient, _ = self.ambient(B)
+        d_empty_loc = self.param_store["d_empty_loc"].detach()
+        self._d_empty_loc_now = d_empty_loc
+        z_loc, z_log_scale = self.encoder["z"].forward_raw(inp)
+        p_out, eps_out, _ = self.encoder["other"].forward_raw(inp, chi_ambient.detach(), z_loc.detach(),
+                                                              row_keep_scale=row_keep_scale)
         self._d_empty_loc_now = None
-        if samples is None:
-            samples = sampler(inp, enc) if sampler is not None else self.draw_guide_samples(inp, enc, ps)
-        phi, d_empty, v, z, d_cell, epsilon = (samples[k] for k in ("phi", "d_empty", "p_logit_reg", "z", "d_cell", "epsilon"))
-        rho = samples["rho"] if self.include_rho else torch.zeros_like(d_cell)
-        p_y = enc["p_y"]
-        log_q1, log_q0 = F.logsigmoid(p_y), F.logsigmoid(-p_y)
-        q1, q0 = log_q1.exp(), log_q0.exp()
-        prob = p_y.sigmoid().detach()
-        counts = inp.counts
-        t: Dict[str, torch.Tensor] = {}
-
-        # global phi
-        phi_loc, phi_scale = ps["phi_loc"], ps["phi_scale"]
-        t["phi"] = (Gamma(self.phi_conc_prior, self.phi_rate_prior).log_prob(phi)
-                    - Gamma(phi_loc.pow(2) / phi_scale.pow(2), phi_loc / phi_scale.pow(2)).log_prob(phi))
-        # z: model side unmasked, guide side masked by y (model.py:262-264, 553-555)
-        t["z"] = (Normal(self.z_loc_prior, self.z_scale_prior).log_prob(z).sum(-1).sum()
-                  - (q1 * Normal(enc["z"]["loc"], enc["z"]["scale"]).log_prob(z).sum(-1)).sum())
-        d_cell_loc_gated = prob * enc["d_loc"] + (1 - prob) * self.d_cell_loc_prior
-        t["d_cell"] = (LogNormal(self.d_cell_loc_prior, self.d_cell_scale_prior).log_prob(d_cell)
-                       - LogNormal(d_cell_loc_gated, ps["d_cell_scale"]).log_prob(d_cell)).sum()
-        if self.include_rho:
-            t["rho"] = (Beta(self.rho_alpha_prior, self.rho_beta_prior).log_prob(rho)
-                        - Beta(ps["rho_alpha"], ps["rho_beta"]).log_prob(rho)).sum()
-        eps_gated = prob * enc["epsilon"] + (1 - prob)
-        t["epsilon"] = (Gamma(self.epsilon_prior, self.epsilon_prior).log_prob(epsilon)
-                        - Gamma(eps_gated * self.epsilon_prior, self.epsilon_prior).log_prob(epsilon)).sum()
-        t["d_empty"] = (LogNormal(self.d_empty_loc_prior, self.d_empty_scale_prior).log_prob(d_empty)
-                        - LogNormal(ps["d_empty_loc"], ps["d_empty_scale"]).log_prob(d_empty)).sum()
-        # y: enumerated in the guide (model.py:295-301, 547)
-        plp = get_p_logit_prior(counts.log(), self.d_cell_loc_prior, self.empty_UMI_threshold, self.p_logit_prior)
-        t["y"] = (q1 * (F.logsigmoid(plp) - log_q1) + q0 * (F.logsigmoid(-plp) - log_q0)).sum()
-        t["p_logit_reg"] = (Normal(self.p_logit_prior, self._k["p_logit_scale"]).log_prob(v)
-                            - Normal(p_y, self._k["p_logit_scale"]).log_prob(v)).sum()
+        # guide samples, rate coefficients, enumeration weights and every non-observation term: one kernel
+        z, coef, alpha, w, loss_local, terms, enc_out = latent.latent_stage(self, p_out, eps_out, z_loc, z_log_scale,
+                                                                            inp.feats, noise)
+        t: Dict[str, torch.Tensor] = {name: terms[i] for i, name in enumerate(latent.TERM_NAMES)}
+        if not self.include_rho:
+            del t["rho"]
 
         # observation terms: decoder output layer + fused likelihood kernel
-        alpha = phi.reciprocal() + consts.NBPC_ALPHA_EPS_SAFEGAURD
-        coef = rate_coefficients(self.model_type, epsilon, d_cell, d_empty, rho)
-        w = -torch.stack((q1, q0, consts.REG_SCALE_AMBIENT_EXPRESSION * q0), dim=1)  # d(-ELBO)/dL
         h_dec = self.decoder.hidden(z)
         lin = self.decoder.out_linear
         self._obs_ctx = (csr, row_ids, self._work_buffers(B))
-        neg_obs, L = _ObsTerm.apply(h_dec, lin.weight, lin.bias, chi_ambient, coef, alpha, w.detach(), self)
-        dice = (w * L).sum()  # carries d/d p_y through the enumeration weights; value cancels below
-        t["obs"] = -(neg_obs + dice - dice.detach())
+        neg_obs, L = _ObsTerm.apply(h_dec, lin.weight, lin.bias, chi_ambient, coef, alpha, w, self)
+        t["obs"] = -neg_obs
         self._last_L = L
-
-        # soft semi-supervision of p_y (no gradient: p_passback is detached; model.py:400-427)
-        p_det = p_y.detach()
-        empty_m = counts < self.counts_crossover
-        cell_m = counts >= self.counts_crossover
-        t["obs_probably_empty_y"] = consts.REG_SCALE_SOFT_SUPERVISION * torch.where(
-            empty_m, Normal(self._k["neg_reg_logit_mean"], self._k["reg_logit_soft_scale"]).log_prob(p_det),
-            torch.zeros_like(p_det)).sum()
-        t["obs_probably_cell_y"] = consts.REG_SCALE_SOFT_SUPERVISION * torch.where(
-            cell_m, Normal(self._k["reg_logit_mean"], self._k["reg_logit_soft_scale"]).log_prob(p_det),
-            torch.zeros_like(p_det)).sum()
-        # epsilon medians (model.py:429-443)
-        surely_cell = counts >= self.d_cell_loc_prior.exp()
-        one = self._k["one"]
-        med_cell = _masked_lower_median(epsilon, cell_m)
-        t["epsilon_mean"] = torch.where(surely_cell.sum() >= 2, Normal(med_cell, self._k["eps_median_scale"]).log_prob(one),
-                                        torch.zeros_like(one))
-        t["epsilon_empty_mean"] = Normal(_masked_lower_median(epsilon, empty_m), self._k["eps_median_scale"]).log_prob(one)
-
-        elbo = sum(t.values())
-        t["loss"] = -elbo
-        t["_enc"] = enc  # for callers that need p_y etc.
+        t["loss"] = loss_local + neg_obs
+        t["_enc"] = {"p_y": enc_out[:, 0], "d_loc": enc_out[:, 1], "epsilon": enc_out[:, 2]}
         return t
 
     def check_nan(self):

@@ -56,14 +56,14 @@ class SVI:
     def _ambient_unit_vector(self) -> torch.Tensor:
         """x_ambient / ||x_ambient||_2 of EncodeNonZLatents.forward (vae/encoder.py:266-270); the d_empty factor
         cancels in the normalisation."""
-        chi = self.model.param_store["chi_ambient"].detach()
-        return (chi / torch.linalg.vector_norm(chi)).contiguous()
+        with torch.no_grad():
+            return self.model.ambient()[1]
 
-    def loss_terms(self, batch):
-        params = self.model.param_store.all()  # every pyro.param transform once per step
-        chi = params["chi_ambient"].detach()
-        inp = batch.encoder_inputs((chi / torch.linalg.vector_norm(chi)).contiguous())
-        return self.model.elbo_terms(batch.loader.csr, batch.row_ids, inp, params=params)
+    def loss_terms(self, batch, noise=None, row_keep_scale=None):
+        chi_ambient, unit = self.model.ambient(batch.n)  # simplex transform of the parameter + unit vector: one kernel
+        inp = batch.encoder_inputs(unit)
+        return self.model.elbo_terms(batch.loader.csr, batch.row_ids, inp, noise=noise, row_keep_scale=row_keep_scale,
+                                     chi_ambient=chi_ambient)
 
     def _forward_backward(self, batch) -> torch.Tensor:
         self.optim.zero_grad()

@@ -129,8 +129,8 @@ class EncodeZ(FullyConnectedNetwork):
         self.loc_out = nn.Linear(hidden_dims[-1], output_dim)
         self.sig_out = nn.Linear(hidden_dims[-1], output_dim)
 
-    def forward(self, x, **kwargs) -> Dict[str, torch.Tensor]:
-        inp = _as_inputs(x, self.input_dim)
+    def forward_raw(self, inp: EncoderInputs):
+        """(loc, log_scale) [B, Z]: the two output Linears before ``exp`` (what the fused latent kernel consumes)."""
         assert self.transform == "normalize", "the B200 path implements input_transform='normalize' (run.py:707)"
         first = self.network[0].layer
         lin = first[0]
@@ -139,9 +139,11 @@ class EncodeZ(FullyConnectedNetwork):
             h = mod(h)
         for layer in list(self.network)[1:]:
             h = layer(h)
-        loc = self.loc_out(h)
-        scale = torch.exp(self.sig_out(h))
-        return {"loc": loc.squeeze(), "scale": scale.squeeze()}
+        return self.loc_out(h), self.sig_out(h)
+
+    def forward(self, x, **kwargs) -> Dict[str, torch.Tensor]:
+        loc, log_scale = self.forward_raw(_as_inputs(x, self.input_dim))
+        return {"loc": loc.squeeze(), "scale": torch.exp(log_scale).squeeze()}
 
 
 class EncodeNonZLatents(nn.Module):
@@ -186,8 +188,11 @@ class EncodeNonZLatents(nn.Module):
             raise RuntimeError("EncodeNonZLatents.d_empty_loc_fn is not set (the model object sets it)")
         return self.d_empty_loc_fn().detach().to(device)
 
-    def forward(self, x, chi_ambient: Optional[torch.Tensor], z: torch.Tensor, row_keep_scale: Optional[torch.Tensor] = None,
-                **kwargs) -> Dict[str, torch.Tensor]:
+    def forward_raw(self, x, chi_ambient: Optional[torch.Tensor], z: torch.Tensor,
+                    row_keep_scale: Optional[torch.Tensor] = None):
+        """Raw outputs of the two towers, ``layer3(...)`` and ``eps_network(...)`` [B], before the offset / gating
+        algebra of encoder.py:300-340 (which the fused latent kernel applies on the training path).  Returns
+        (p_out, eps_out, inputs)."""
         assert self.transform == "log_normalize", "the B200 path implements input_transform='log_normalize' (run.py:717)"
         G = self.n_genes
         d_empty_loc = self._d_empty_loc(z.device) if chi_ambient is not None else None
@@ -225,14 +230,20 @@ class EncodeNonZLatents(nn.Module):
             h = mod(h)
         eps_out = h.squeeze(-1)
 
-        ls = log_sum.squeeze(-1)
-        if self.offset is None:
+        if self.offset is None:  # data-dependent module state fixed by the first minibatch (encoder.py:300-309)
+            ls = log_sum.squeeze(-1)
             self.offset = dict()
             cells = ls > self.log_count_crossover
             assert cells.sum() > 4, "Fewer than 4 cells passed to encoder minibatch"
             self.offset["logit_p"] = p_out.mean().item()
             self.offset["epsilon"] = eps_out[cells].mean().item()
+        return p_out, eps_out, inp
 
+    def forward(self, x, chi_ambient: Optional[torch.Tensor], z: torch.Tensor, row_keep_scale: Optional[torch.Tensor] = None,
+                **kwargs) -> Dict[str, torch.Tensor]:
+        p_out, eps_out, inp = self.forward_raw(x, chi_ambient, z, row_keep_scale)
+        counts = inp.feats[:, 0:1]
+        ls = counts.log1p().squeeze(-1)
         dlt = ls - self.log_count_crossover
         p_y_logit = (p_out - self.offset["logit_p"]) + dlt.abs().pow(0.5) * torch.sign(dlt) * 10.0
         beta = 50.0

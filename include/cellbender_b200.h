@@ -102,6 +102,64 @@ int cb_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long l
                  long long workspace_elems, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * A4(tail)+A9  the per-droplet latent algebra of RemoveBackgroundPyroModel.model / .guide (model.py:232-445, 447-574),
+ * the output shaping of EncodeNonZLatents.forward (vae/encoder.py:300-340), the constraint transforms of the scalar
+ * pyro.param sites (model.py:468-513) and the autograd backward of all of it, as one-CTA kernels.
+ *   feats[n_rows, 4]        row features of cb_csr_gather_rows (col 0 = total counts)
+ *   p_out/eps_out[n_rows]   raw outputs of EncodeNonZLatents.layer3 / eps_network (before offset and gating)
+ *   z_loc/z_log_scale[n_rows, ldz]  EncodeZ.loc_out / sig_out outputs (scale = exp(log_scale), encoder.py:121-124)
+ *   u_*                     UNCONSTRAINED scalar parameters (device, 1 element each; u_rho_* NULL for model 'ambient')
+ *   consts_h[cb_latent_num_consts()]  HOST array: log_count_crossover, prior_log_cell_counts, empty_log_count_threshold,
+ *                           offset_logit_p, d_cell_loc_prior, d_cell_scale_prior, epsilon_prior, phi_conc_prior,
+ *                           phi_rate_prior, rho_alpha_prior, rho_beta_prior, d_empty_loc_prior, d_empty_scale_prior,
+ *                           p_logit_prior, empty_UMI_threshold, counts_crossover, rho_param_min, rho_param_max,
+ *                           model_type (0 ambient, 1 swapping, 2 full)
+ * cb_latent_prepare  -> conc_gamma[1 + 3 n_rows] = (phi conc, epsilon conc[n_rows], rho_alpha x n_rows, rho_beta x n_rows):
+ *                       the concentrations at which the caller draws standard-gamma samples (Gamma.rsample / Beta.rsample);
+ *                       conc_beta/total_beta[n_rows, 2] = (alpha, beta) and alpha + beta, operands of the Dirichlet
+ *                       implicit gradient.
+ * cb_latent_beta_sample  clamps the draws to >= FLT_MIN and forms xx[n_rows, 2] = (rho, 1 - rho), rho = ga / (ga + gb).
+ * cb_latent_forward  noise_z[n_rows, z_dim], noise_row[n_rows, 3] (d_cell, d_empty, p_logit_reg) standard normals;
+ *                       gamma_draws[1 + n_rows] (phi, epsilon) ->
+ *                       z_out[n_rows, z_dim], coef[n_rows, 7] / alpha[1] / w[n_rows, 3] (operands of cb_elbo_obs_fwd_bwd),
+ *                       terms[cb_latent_num_terms()] = phi, z, d_cell, rho, epsilon, d_empty, y, p_logit_reg,
+ *                       obs_probably_empty_y, obs_probably_cell_y, epsilon_mean, epsilon_empty_mean; loss_local[1] = -(their sum);
+ *                       enc_out[n_rows, 4] = p_y, d_loc, epsilon (encoder), epsilon (sample); med_idx[2] median rows.
+ * cb_latent_backward gamma_grad[1 + n_rows] = torch._standard_gamma_grad(conc, draw); dirichlet_grad[n_rows, 2] =
+ *                       torch._dirichlet_grad(xx, conc_beta, total_beta); d_z/d_coef/d_alpha/d_w = d loss / d (outputs)
+ *                       (any may be NULL = 0); g_local[1] = d loss / d loss_local (NULL = 1) ->
+ *                       d_p_out, d_eps_out [n_rows]; d_z_loc, d_z_log_scale [n_rows, lddz]; g_* = d loss / d u_* (NULL ok). */
+int cb_latent_num_consts(void);
+int cb_latent_num_terms(void);
+int cb_latent_prepare(const float* feats, const float* p_out, const float* eps_out, int n_rows,
+                      const float* u_d_cell_scale, const float* u_d_empty_loc, const float* u_d_empty_scale,
+                      const float* u_rho_alpha, const float* u_rho_beta, const float* u_phi_loc, const float* u_phi_scale,
+                      const float* consts_h, float* conc_gamma, float* conc_beta, float* total_beta, void* stream);
+int cb_latent_beta_sample(float* gamma_draws, int n_rows, float* xx, void* stream);
+int cb_latent_forward(const float* feats, const float* p_out, const float* eps_out, const float* z_loc,
+                      const float* z_log_scale, long long ldz, int n_rows, int z_dim, const float* noise_z,
+                      const float* noise_row, const float* gamma_draws, const float* xx, const float* u_d_cell_scale,
+                      const float* u_d_empty_loc, const float* u_d_empty_scale, const float* u_rho_alpha,
+                      const float* u_rho_beta, const float* u_phi_loc, const float* u_phi_scale, const float* consts_h,
+                      float* z_out, float* coef, float* alpha, float* w, float* terms, float* loss_local, float* enc_out,
+                      int* med_idx, void* stream);
+int cb_latent_backward(const float* feats, const float* p_out, const float* eps_out, const float* z_loc,
+                       const float* z_log_scale, long long ldz, int n_rows, int z_dim, const float* noise_z,
+                       const float* noise_row, const float* gamma_draws, const float* xx, const float* gamma_grad,
+                       const float* dirichlet_grad, const int* med_idx, const float* u_d_cell_scale,
+                       const float* u_d_empty_loc, const float* u_d_empty_scale, const float* u_rho_alpha,
+                       const float* u_rho_beta, const float* u_phi_loc, const float* u_phi_scale, const float* consts_h,
+                       const float* d_z, const float* d_coef, const float* d_alpha, const float* d_w, const float* g_local,
+                       float* d_p_out, float* d_eps_out, float* d_z_loc, float* d_z_log_scale, long long lddz,
+                       float* g_d_cell_scale, float* g_d_empty_loc, float* g_d_empty_scale, float* g_rho_alpha,
+                       float* g_rho_beta, float* g_phi_loc, float* g_phi_scale, void* stream);
+/* transform_to(constraints.simplex) of the chi_ambient parameter (model.py:245-249, 486-490): torch's
+ * SoftmaxTransform.  u[n] -> y[n] = softmax(u) (+ y_unit = y / ||y||_2, the encoder's ambient unit vector,
+ * vae/encoder.py:266-270; may be NULL); backward: grad_u = y * (grad_y - <grad_y, y>).                          */
+int cb_simplex_forward(const float* u, int n, float* y, float* y_unit, void* stream);
+int cb_simplex_backward(int n, const float* y, const float* grad_y, float* grad_u, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * K8  fused ClippedAdam + OneCycleLR over one flat buffer.  Replaces get_optimizer (run.py:593-629) and the
  * per-parameter optimizer/scheduler steps at train.py:56-60.  lr_table/beta1_table[table_len] hold torch
  * OneCycleLR's per-step values; *step_ptr (device int64) counts completed steps and is incremented here.       */

@@ -473,3 +473,38 @@ def test_bn0_dropout_matches_torch_batchnorm(ops, training):
     np.testing.assert_allclose(bn.running_mean.cpu().numpy(), ref_bn.running_mean.cpu().numpy(), rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(bn.running_var.cpu().numpy(), ref_bn.running_var.cpu().numpy(), rtol=1e-5, atol=1e-7)
     assert int(bn.num_batches_tracked) == int(ref_bn.num_batches_tracked)
+
+
+# ------------------------------------------------------------------------------- simplex parameter transform
+@pytest.mark.parametrize("G", [2, 33, 1025, 33538])
+def test_simplex_param_matches_torch_transform(ops, G):
+    """cb_simplex_forward / _backward vs torch's transform_to(constraints.simplex) (what pyro.param applies to
+    chi_ambient, model.py:245-249) evaluated in fp64: value, unit vector and the vector-Jacobian product."""
+    from torch.distributions import constraints, transform_to
+
+    from cellbender_b200 import latent
+
+    gen = torch.Generator().manual_seed(G)
+    chi0 = torch.distributions.Dirichlet(torch.full((G,), 0.3)).sample().double().clamp_min(1e-12)
+    chi0 = chi0 / chi0.sum()
+    u32 = (transform_to(constraints.simplex).inv(chi0) + 0.1 * torch.randn(G, generator=gen, dtype=torch.float64)).float()
+    u64 = u32.double().requires_grad_(True)
+    y64 = transform_to(constraints.simplex)(u64)
+    gy = torch.randn(G, generator=gen, dtype=torch.float64)
+    (y64 * gy).sum().backward()
+
+    u = u32.to(DEV).requires_grad_(True)
+    ld = (G + 3) // 4 * 4
+    bufs = {"chi_a": torch.zeros(ld, device=DEV), "chi_unit": torch.zeros(ld, device=DEV)}
+    y = latent.simplex_param(u, bufs)
+    assert y.shape == (G,) and y.data_ptr() == bufs["chi_a"].data_ptr()
+    (y * gy.float().to(DEV)).sum().backward()
+    np.testing.assert_allclose(y.detach().cpu().numpy(), y64.detach().numpy(), rtol=2e-6, atol=1e-30)
+    assert abs(float(y.sum()) - 1.0) < 1e-5
+    unit_ref = y64.detach() / y64.detach().norm()
+    np.testing.assert_allclose(bufs["chi_unit"][:G].cpu().numpy(), unit_ref.numpy(), rtol=2e-6, atol=1e-30)
+    scale = float(u64.grad.abs().max())
+    assert float((u.grad.double().cpu() - u64.grad).abs().max()) <= 1e-5 * scale + 3e-7 * float(gy.abs().max())  # y is stored in fp32
+    # without persistent buffers the op allocates its own output
+    y2 = latent.simplex_param(u.detach())
+    assert torch.equal(y2, y.detach())

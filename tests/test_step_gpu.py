@@ -51,13 +51,21 @@ def _oracle_inputs(model, offset):
     return params, buffers, cfg
 
 
+def _grad_of(p):
+    """Gradient of a parameter: kernels that own a gradient (GEMM epilogues, the latent / simplex backward) write it
+    straight into the optimizer's flat buffer (``_cb_grad_view``) and leave ``.grad`` unset."""
+    if getattr(p, "_cb_grad_direct", False):
+        return p._cb_grad_view.detach().double().cpu().clone()
+    return None if p.grad is None else p.grad.detach().double().cpu()
+
+
 def _product_param_grads(model):
     out = {}
     for pre, mod in (("enc_z.", model.encoder["z"]), ("enc_o.", model.encoder["other"]), ("dec.", model.decoder)):
         for k, v in mod.named_parameters():
-            out[pre + k] = None if v.grad is None else v.grad.detach().double().cpu()
+            out[pre + k] = _grad_of(v)
     for k, v in model.param_store.unconstrained.items():
-        out["ps." + k] = None if v.grad is None else v.grad.detach().double().cpu()
+        out["ps." + k] = _grad_of(v)
     return out
 
 
@@ -109,25 +117,10 @@ def _elbo_parity(training, backend, rtol_terms, rtol_grads):
                 "rho_alpha": ps["rho_alpha"].cpu(), "rho_beta": ps["rho_beta"].cpu()}
     noise = oelbo.draw_noise(B, Z, conc, generator=g)
 
-    def sampler(inp_, enc):
-        n = {k: v.to(DEV) for k, v in noise.items()}
-        ps_ = model.param_store
-        pl, psc = ps_["phi_loc"], ps_["phi_scale"]
-        prob = enc["p_y"].sigmoid().detach()
-        return {
-            "phi": oelbo.gamma_rsample(pl ** 2 / psc ** 2, pl / psc ** 2, n["phi"]),
-            "rho": oelbo.beta_rsample(ps_["rho_alpha"], ps_["rho_beta"], n["rho"]),
-            "d_empty": torch.exp(ps_["d_empty_loc"] + ps_["d_empty_scale"] * n["d_empty"]),
-            "p_logit_reg": enc["p_y"] + 2.0 * n["p_logit_reg"],
-            "z": enc["z"]["loc"] + enc["z"]["scale"] * n["z"],
-            "d_cell": torch.exp(prob * enc["d_loc"] + (1 - prob) * model.d_cell_loc_prior + ps_["d_cell_scale"] * n["d_cell"]),
-            "epsilon": oelbo.gamma_rsample((prob * enc["epsilon"] + 1 - prob) * model.epsilon_prior, model.epsilon_prior,
-                                           n["epsilon"]),
-        }
-
     opt.zero_grad()
-    terms = model.elbo_terms(batch.loader.csr, batch.row_ids, inp, sampler=sampler,
-                             row_keep_scale=None if keep is None else keep.to(DEV))
+    chi_ambient, _ = model.ambient(B)
+    terms = model.elbo_terms(batch.loader.csr, batch.row_ids, inp, noise={k: v.to(DEV) for k, v in noise.items()},
+                             row_keep_scale=None if keep is None else keep.to(DEV), chi_ambient=chi_ambient)
     terms["loss"].backward()
     model.check_nan()
     got = _product_param_grads(model)
