@@ -34,7 +34,7 @@ def _grad_target(weight: torch.Tensor):
     the parameter a view of its flat gradient buffer, the GEMM writes there and autograd is handed None (so that
     AccumulateGrad neither clones nor re-accumulates 68 MB); ``_cb_grad_direct`` tells ``collect_grads`` about it."""
     gv = getattr(weight, "_cb_grad_view", None)
-    if gv is None:
+    if gv is None or not weight.requires_grad:
         t = torch.empty_like(weight)
         return t, t
     weight._cb_grad_direct = True
@@ -65,6 +65,7 @@ class _MultiLinearBig(torch.autograd.Function):
             ys.append(y)
         ctx.save_for_backward(x, *[t for t in feats if t is not None], *weights)
         ctx.meta = (len(weights), n_in, col_offset, [f is not None for f in feats], [b is not None for b in biases])
+        ctx.biases = biases  # the nn.Parameter objects (they carry the optimizer's gradient views)
         return tuple(ys)
 
     @staticmethod
@@ -97,7 +98,8 @@ class _MultiLinearBig(torch.autograd.Function):
                 ops.gemm_tf32(dy, w[:, off:off + n_in], B, n_in, H, b_mn=True, out=dx, accumulate=not first, split_k=1)
                 first = False
             if has_bias[i] and ctx.needs_input_grad[3 + 3 * i + 2]:
-                db = dy.sum(0)
+                db_buf, db = _grad_target(ctx.biases[i])
+                ops.colsum_rows(dy, H, out=db_buf)
             if feat is not None and ctx.needs_input_grad[3 + 3 * i]:
                 dfeat = dy @ w[:, :off]
             grads += [dfeat, dw, db]
@@ -109,28 +111,37 @@ class _MultiLinearBig(torch.autograd.Function):
         return (dx, None, None, *grads)
 
 
-def multi_linear_big(x: torch.Tensor, layers, n_in: int, col_offset: int = 0):
+def multi_linear_big(x: torch.Tensor, layers, n_in: int, col_offset: int = 0, bias_grad_elsewhere: bool = False):
     """``layers`` = [(nn.Linear, feat or None), ...] applied to the same wide input x; returns a tuple of outputs.
-    x may carry padding columns beyond n_in (16-byte-aligned rows from the gather / BN kernels)."""
+    x may carry padding columns beyond n_in (16-byte-aligned rows from the gather / BN kernels).
+    ``bias_grad_elsewhere``: the layer feeds ``bn_act`` which also produces the Linear bias gradient (the column sums
+    of its input gradient), so no separate reduction over dy is launched here."""
     ws = [lin.weight for lin, _ in layers]
     use_tc = (BACKEND == "tcgen05" and _tma_ok(x) and all(_tma_ok(w) for w in ws)
               and all((w.data_ptr() + 4 * col_offset) % 16 == 0 for w in ws))
     if use_tc:
         args = []
         for lin, feat in layers:
-            args += [feat, lin.weight, lin.bias]
+            bias = lin.bias
+            if bias is not None and bias_grad_elsewhere and torch.is_grad_enabled():
+                bias = bias.detach()
+            args += [feat, lin.weight, bias]
         return _MultiLinearBig.apply(x, n_in, col_offset, *args)
     outs = []
     for lin, feat in layers:
-        y = F.linear(x[:, :n_in], lin.weight[:, col_offset:col_offset + n_in], lin.bias)
+        bias = lin.bias
+        if bias is not None and bias_grad_elsewhere and torch.is_grad_enabled():
+            bias = bias.detach()
+        y = F.linear(x[:, :n_in], lin.weight[:, col_offset:col_offset + n_in], bias)
         if feat is not None:
             y = y + feat @ lin.weight[:, :col_offset].t()
         outs.append(y)
     return tuple(outs)
 
 
-def linear_big(x: torch.Tensor, lin: torch.nn.Linear, n_in: int, col_offset: int = 0, feat: Optional[torch.Tensor] = None):
-    return multi_linear_big(x, [(lin, feat)], n_in, col_offset)[0]
+def linear_big(x: torch.Tensor, lin: torch.nn.Linear, n_in: int, col_offset: int = 0, feat: Optional[torch.Tensor] = None,
+               bias_grad_elsewhere: bool = False):
+    return multi_linear_big(x, [(lin, feat)], n_in, col_offset, bias_grad_elsewhere)[0]
 
 
 class _BN0Dropout(torch.autograd.Function):
@@ -171,3 +182,60 @@ def bn0_dropout(x: torch.Tensor, bn: torch.nn.BatchNorm1d, keep: Optional[torch.
                                  bn.momentum if bn.momentum is not None else 0.1, bn.eps, n_genes)
     y = bn(x[:, :n_genes])
     return y * keep.unsqueeze(-1) if (training and keep is not None) else y
+
+
+ACT_CODE = {None: 0, "identity": 0, "softplus": 1, "relu": 2}
+
+
+class _BNAct(torch.autograd.Function):
+    """act(batchnorm(x)) for the [B, 512] hidden layers through cb_bn_act_forward / _backward (csrc/bn_act.cu).
+    gamma / beta gradients -- and, when ``bias`` is given, the gradient of the Linear bias that produced x -- are
+    written straight into the optimizer's flat gradient buffer."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, act: int, training: bool, bias):
+        B, N = x.shape
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        y = torch.empty((B, N), dtype=torch.float32, device=x.device)
+        mean = torch.empty(N, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(N, dtype=torch.float32, device=x.device)
+        momentum = bn.momentum if bn.momentum is not None else 0.1
+        lib().call("cb_bn_act_forward", ptr(x), x.stride(0), B, N, ptr(gamma), ptr(beta), ptr(bn.running_mean),
+                   ptr(bn.running_var), ptr(bn.num_batches_tracked) if training else None, int(training), float(momentum),
+                   float(bn.eps), act, ptr(y), y.stride(0), ptr(mean), ptr(rstd), current_stream())
+        ctx.save_for_backward(x, mean, rstd)
+        ctx.params = (gamma, beta, bias)
+        ctx.meta = (act, training)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd = ctx.saved_tensors
+        gamma, beta, bias = ctx.params
+        act, training = ctx.meta
+        B, N = x.shape
+        if dy.stride(1) != 1:
+            dy = dy.contiguous()
+        dx = torch.empty((B, N), dtype=torch.float32, device=x.device)
+        dg_buf, dg = _grad_target(gamma)
+        db_buf, db = _grad_target(beta)
+        dbias_buf = None
+        if bias is not None and bias.requires_grad:
+            dbias_buf, dbias = _grad_target(bias)
+            if dbias is not None:  # no flat gradient view: hand the gradient to the parameter directly
+                bias.grad = dbias
+        lib().call("cb_bn_act_backward", ptr(x), x.stride(0), ptr(dy), dy.stride(0), B, N, ptr(gamma), ptr(beta), ptr(mean),
+                   ptr(rstd), int(training), act, ptr(dx), dx.stride(0), ptr(dg_buf), ptr(db_buf), ptr(dbias_buf),
+                   current_stream())
+        return dx, dg, db, None, None, None, None
+
+
+def bn_act(x: torch.Tensor, bn: torch.nn.BatchNorm1d, act: Optional[str], training: bool,
+           bias_of: Optional[torch.nn.Linear] = None) -> torch.Tensor:
+    """``act(bn(x))`` in one kernel each way.  ``bias_of``: the nn.Linear that produced ``x`` when its bias gradient
+    should come out of this op's backward (pair with ``bias_grad_elsewhere=True`` on that layer)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):
+        raise RuntimeError("cellbender_b200 ops require 2-D fp32 CUDA tensors (no CPU fallback)")
+    bias = bias_of.bias if (bias_of is not None and bias_of.bias is not None and torch.is_grad_enabled()) else None
+    return _BNAct.apply(x, bn.weight, bn.bias, bn, ACT_CODE[act], training, bias)

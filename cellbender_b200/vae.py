@@ -20,7 +20,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import consts
-from .gemm import bn0_dropout, linear_big, multi_linear_big
+from . import gemm
+from .gemm import bn0_dropout, bn_act, linear_big, multi_linear_big
 
 
 @dataclass
@@ -139,7 +140,8 @@ class EncodeZ(FullyConnectedNetwork):
             h = mod(h)
         for layer in list(self.network)[1:]:
             h = layer(h)
-        return self.loc_out(h), self.sig_out(h)
+        # both heads read the same hidden activations: one node, one paired input-gradient GEMM
+        return multi_linear_big(h, [(self.loc_out, None), (self.sig_out, None)], n_in=h.shape[1])
 
     def forward(self, x, **kwargs) -> Dict[str, torch.Tensor]:
         loc, log_scale = self.forward_raw(_as_inputs(x, self.input_dim))
@@ -220,15 +222,18 @@ class EncodeNonZLatents(nn.Module):
         # Linear(cat(feat, x_in)) of both towers: the large gene block through the tensor-core GEMM (shared input),
         # the 4 feature columns as a rank-4 update
         e = self.eps_network[0]
-        h1, he = multi_linear_big(x_in, [(self.layer1, p_feat), (e, e_feat)], n_in=G, col_offset=4)
-        x_ = self.softplus(self.batchnorm1(h1))
-        x_ = self.softplus(self.batchnorm2(self.layer2(torch.cat((p_feat, x_), dim=-1))))
+        h1, he = multi_linear_big(x_in, [(self.layer1, p_feat), (e, e_feat)], n_in=G, col_offset=4, bias_grad_elsewhere=True)
+        # hidden layers: Linear (tensor-core GEMM + rank-4 feature update) -> fused BatchNorm + Softplus kernel
+        x_ = bn_act(h1, self.batchnorm1, "softplus", self.training, bias_of=self.layer1)
+        h2 = linear_big(x_, self.layer2, n_in=x_.shape[1], col_offset=4, feat=p_feat, bias_grad_elsewhere=True)
+        x_ = bn_act(h2, self.batchnorm2, "softplus", self.training, bias_of=self.layer2)
         p_out = self.layer3(torch.cat((p_feat, x_), dim=-1)).squeeze(-1)
 
-        h = he
-        for mod in list(self.eps_network)[1:]:
-            h = mod(h)
-        eps_out = h.squeeze(-1)
+        eps_bn1, eps_lin2, eps_bn2, eps_lin3 = self.eps_network[1], self.eps_network[3], self.eps_network[4], self.eps_network[6]
+        h = bn_act(he, eps_bn1, "softplus", self.training, bias_of=e)
+        h = linear_big(h, eps_lin2, n_in=h.shape[1], bias_grad_elsewhere=True)
+        h = bn_act(h, eps_bn2, "softplus", self.training, bias_of=eps_lin2)
+        eps_out = eps_lin3(h).squeeze(-1)
 
         if self.offset is None:  # data-dependent module state fixed by the first minibatch (encoder.py:300-309)
             ls = log_sum.squeeze(-1)
@@ -295,7 +300,14 @@ class Decoder(FullyConnectedNetwork):
         """Everything before the final 512 -> G Linear."""
         h = z
         for layer in list(self.network)[:-1]:
-            h = layer(h)
+            mods = list(layer.layer)
+            if (len(mods) == 3 and isinstance(mods[0], nn.Linear) and isinstance(mods[1], nn.BatchNorm1d)
+                    and isinstance(mods[2], nn.ReLU) and h.is_cuda):
+                # Linear -> BatchNorm1d -> ReLU (vae/base.py:66-79): tensor-core GEMM + one fused kernel
+                h = linear_big(h.contiguous(), mods[0], n_in=mods[0].in_features, bias_grad_elsewhere=True)
+                h = bn_act(h, mods[1], "relu", self.training, bias_of=mods[0])
+            else:
+                h = layer(h)
         return h
 
     @property

@@ -81,6 +81,21 @@ int cb_bn0_backward(const float* x, long long ldx, const float* dy, long long ld
                     void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * A4/A5  nn.BatchNorm1d + activation of the hidden layers ([n_rows, n_cols = 512]): EncodeNonZLatents.batchnorm1/2 +
+ * softplus (vae/encoder.py:283-289), eps_network BatchNorm1d + Softplus (vae/encoder.py:219-228), the Decoder's
+ * FullyConnectedLayer BatchNorm1d(momentum 0.01, eps 1e-3) + ReLU (vae/base.py:66-79); forward and backward.
+ * act: 0 identity, 1 softplus, 2 relu.  training = 1: minibatch statistics, running stats and *num_batches_tracked
+ * (may be NULL) updated.  backward: dx [n_rows, lddx], dgamma, dbeta [n_cols]; dbias (may be NULL) = column sums of dx,
+ * the gradient of the Linear bias that fed the BatchNorm.                                                       */
+int cb_bn_act_forward(const float* x, long long ldx, int n_rows, int n_cols, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, long long* num_batches_tracked, int training,
+                      float momentum, float eps, int act, float* y, long long ldy, float* save_mean, float* save_rstd,
+                      void* stream);
+int cb_bn_act_backward(const float* x, long long ldx, const float* dy, long long lddy, int n_rows, int n_cols,
+                       const float* gamma, const float* beta, const float* save_mean, const float* save_rstd, int training,
+                       int act, float* dx, long long lddx, float* dgamma, float* dbeta, float* dbias, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * A3-A5  the large contractions of EncodeZ / EncodeNonZLatents / Decoder (vae/encoder.py:97-125, 211-228, 279-298;
  * vae/decoder.py:41-47) and their backward, on tcgen05 tensor cores (TF32 multiply, fp32 accumulate in TMEM).
  *   C[M, N] (=, +=) A[M, K] * B[N, K]^T (+ bias[N])

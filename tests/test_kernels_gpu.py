@@ -508,3 +508,43 @@ def test_simplex_param_matches_torch_transform(ops, G):
     # without persistent buffers the op allocates its own output
     y2 = latent.simplex_param(u.detach())
     assert torch.equal(y2, y.detach())
+
+
+# ------------------------------------------------------------------------------- hidden-layer BatchNorm + activation
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("act", ["softplus", "relu", None])
+@pytest.mark.parametrize("B,N", [(255, 512), (7, 40), (64, 33)])
+def test_bn_act_matches_torch(ops, training, act, B, N):
+    """cb_bn_act_forward / _backward vs nn.BatchNorm1d + activation in fp64 (values, running statistics, input /
+    gamma / beta gradients and the column sums of dx handed to the preceding Linear's bias)."""
+    from cellbender_b200 import gemm
+
+    gen = torch.Generator().manual_seed(B * 1000 + N)
+    x64 = (torch.randn(B, N, generator=gen, dtype=torch.float64) * 3 + 1.5).requires_grad_(True)
+    bn64 = torch.nn.BatchNorm1d(N, momentum=0.01, eps=1e-3).double()
+    with torch.no_grad():
+        bn64.weight.copy_(torch.rand(N, generator=gen, dtype=torch.float64) + 0.5)
+        bn64.bias.copy_(torch.randn(N, generator=gen, dtype=torch.float64))
+        bn64.running_mean.copy_(torch.randn(N, generator=gen, dtype=torch.float64))
+        bn64.running_var.copy_(torch.rand(N, generator=gen, dtype=torch.float64) + 0.5)
+    bn = torch.nn.BatchNorm1d(N, momentum=0.01, eps=1e-3).to(DEV)
+    bn.load_state_dict({k: v.float() for k, v in bn64.state_dict().items()})
+    bn64.train(training), bn.train(training)
+    f = {"softplus": torch.nn.functional.softplus, "relu": torch.relu, None: lambda t: t}[act]
+    y64 = f(bn64(x64))
+    gy = torch.randn(B, N, generator=gen, dtype=torch.float64)
+    (y64 * gy).sum().backward()
+
+    lin = torch.nn.Linear(3, N).to(DEV)  # only its bias is used: receives the column sums of dx
+    x = x64.detach().float().to(DEV).requires_grad_(True)
+    y = gemm.bn_act(x, bn, act, training, bias_of=lin)
+    (y * gy.float().to(DEV)).sum().backward()
+    tol = dict(rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), y64.detach().numpy(), **tol)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), x64.grad.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(bn.weight.grad.cpu().numpy(), bn64.weight.grad.numpy(), rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(bn.bias.grad.cpu().numpy(), bn64.bias.grad.numpy(), rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(lin.bias.grad.cpu().numpy(), x64.grad.sum(0).numpy(), rtol=1e-4, atol=3e-4)
+    np.testing.assert_allclose(bn.running_mean.cpu().numpy(), bn64.running_mean.numpy(), **tol)
+    np.testing.assert_allclose(bn.running_var.cpu().numpy(), bn64.running_var.numpy(), **tol)
+    assert int(bn.num_batches_tracked) == int(bn64.num_batches_tracked)
