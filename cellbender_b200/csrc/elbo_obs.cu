@@ -68,7 +68,32 @@ __device__ __forceinline__ void obs_element(float v, float chi, float ca, float 
   q_out = c.w1 * c.cA1 * o1.dlam + c.w0 * c.cA0 * o0.dlam + c.wE * c.cAE * dE;
 }
 
-__global__ void __launch_bounds__(kObsThreads) elbo_obs_kernel(
+// contributions of one gene WITHOUT a stored count (x == 0)
+__device__ __forceinline__ void obs_zero_element(float chi, float ca, float cb_, const RowCoef& c, float inv_alpha,
+                                                 float (&acc)[kNumSums], float& p_out, float& q_out) {
+  const float mu1 = fmaf(c.a_mu1, chi, 1e-10f);
+  const float lam1 = fmaf(c.cA1, ca, fmaf(c.cB1, cb_, 1e-10f));
+  const float lam0 = fmaf(c.cA0, ca, fmaf(c.cB0, cb_, 1e-10f));
+  const float lamE = fmaf(c.cAE, ca, fmaf(c.cBE, cb_, 1e-10f));
+  const NbpcOut o1 = nbpc_zero(mu1, inv_alpha, lam1);
+  const NbpcOut o0 = nbpc_zero(1e-10f, inv_alpha, lam0);
+  acc[0] += o1.L;
+  acc[1] += o0.L;
+  acc[2] -= lamE;  // Poisson(0; lamE)
+  acc[3] += o1.dmu * chi;
+  acc[4] += o1.dlam * ca;
+  acc[5] += o1.dlam * cb_;
+  acc[6] += o1.dalpha;
+  acc[7] += o0.dlam * ca;
+  acc[8] += o0.dlam * cb_;
+  acc[9] += o0.dalpha;
+  acc[10] -= ca;
+  acc[11] -= cb_;
+  p_out = o1.dmu * chi;
+  q_out = c.w1 * c.cA1 * o1.dlam + c.w0 * c.cA0 * o0.dlam - c.wE * c.cAE;
+}
+
+__global__ void __launch_bounds__(kObsThreads, 2) elbo_obs_kernel(
     const long long* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ data,
     const long long* __restrict__ row_ids, int G, const float* __restrict__ logits, long long ldl,
     const float* __restrict__ chi_amb, const float* __restrict__ chi_bar, const float* __restrict__ coef,
@@ -92,6 +117,7 @@ __global__ void __launch_bounds__(kObsThreads) elbo_obs_kernel(
   c.cB0 = coef[b * 7 + 4], c.cAE = coef[b * 7 + 5], c.cBE = coef[b * 7 + 6];
   c.w1 = w[b * 3 + 0], c.w0 = w[b * 3 + 1], c.wE = w[b * 3 + 2];
   c.alpha = alpha[0];
+  const float inv_alpha = 1.0f / c.alpha;
 
   // ---- phase 0: bitmap of genes with a stored count ----
   for (int i = threadIdx.x; i < nwords; i += blockDim.x) bitmap[i] = 0u;
@@ -135,14 +161,14 @@ __global__ void __launch_bounds__(kObsThreads) elbo_obs_kernel(
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       pp[k] = 0.f, qq[k] = 0.f;
-      if (!((bits >> k) & 1u)) obs_element(0.0f, expf(ll[k] - lse), aa[k], bb[k], c, acc, pp[k], qq[k]);
+      if (!((bits >> k) & 1u)) obs_zero_element(expf(ll[k] - lse), aa[k], bb[k], c, inv_alpha, acc, pp[k], qq[k]);
     }
     *reinterpret_cast<float4*>(drow + g0) = make_float4(pp[0], pp[1], pp[2], pp[3]);
     *reinterpret_cast<float4*>(qrow + g0) = make_float4(qq[0], qq[1], qq[2], qq[3]);
   }
   for (int g = 4 * G4 + threadIdx.x; g < G; g += blockDim.x) {
     float p = 0.f, q = 0.f;
-    if (!((bitmap[g >> 5] >> (g & 31)) & 1u)) obs_element(0.0f, expf(lrow[g] - lse), chi_amb[g], chi_bar[g], c, acc, p, q);
+    if (!((bitmap[g >> 5] >> (g & 31)) & 1u)) obs_zero_element(expf(lrow[g] - lse), chi_amb[g], chi_bar[g], c, inv_alpha, acc, p, q);
     drow[g] = p;
     qrow[g] = q;
   }
@@ -187,21 +213,35 @@ __global__ void __launch_bounds__(kObsThreads) elbo_obs_kernel(
     drow[g] = scale * (drow[g] - expf(lrow[g] - lse) * s_mu_chi);
 }
 
-// Deterministic column sum of a [R, ld] matrix: out[g] = sum_r in[r, g].  One thread per column.
-__global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restrict__ in, int R, int G, long long ld,
-                                                          float* __restrict__ out) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= G) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int r = 0;
-  for (; r + 4 <= R; r += 4) {
-    a0 += in[(long long)(r + 0) * ld + g];
-    a1 += in[(long long)(r + 1) * ld + g];
-    a2 += in[(long long)(r + 2) * ld + g];
-    a3 += in[(long long)(r + 3) * ld + g];
+// Deterministic column sum of a [R, ld] matrix: out[g] = sum_r in[r, g].  A CTA owns 32 adjacent columns; its 1024
+// threads are 32 row groups x 32 columns (coalesced 128-byte row segments, 8 independent loads in flight per thread);
+// the row groups are combined in shared memory in a fixed order.
+constexpr int kColsumCols = 32, kColsumGroups = 32, kColsumUnroll = 8;
+__global__ void __launch_bounds__(kColsumCols* kColsumGroups) colsum_rows_kernel(const float* __restrict__ in, int R, int G,
+                                                                                long long ld, float* __restrict__ out) {
+  __shared__ float s[kColsumGroups][kColsumCols + 1];
+  const int c = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int g = blockIdx.x * kColsumCols + c;
+  const bool ok = g < G;
+  float acc = 0.f;
+  for (int r0 = grp; r0 < R; r0 += kColsumGroups * kColsumUnroll) {
+    float v[kColsumUnroll];
+#pragma unroll
+    for (int i = 0; i < kColsumUnroll; ++i) {
+      const int r = r0 + i * kColsumGroups;
+      v[i] = (ok && r < R) ? in[(long long)r * ld + g] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < kColsumUnroll; ++i) acc += v[i];
   }
-  for (; r < R; ++r) a0 += in[(long long)r * ld + g];
-  out[g] = (a0 + a1) + (a2 + a3);
+  s[grp][c] = acc;
+  __syncthreads();
+  if (grp == 0 && ok) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < kColsumGroups; ++i) t += s[i][c];
+    out[g] = t;
+  }
 }
 
 // Row logsumexp of a [R, ld] matrix (used by the posterior pass).
@@ -253,7 +293,8 @@ extern "C" int cb_elbo_obs_fwd_bwd(const long long* indptr, const int* indices, 
 
 extern "C" int cb_colsum_rows(const float* in, int n_rows, int n_cols, long long ld, float* out, void* stream) {
   CB_REQUIRE(n_rows >= 0 && n_cols > 0 && ld >= n_cols, "cb_colsum_rows: bad shape [%d, %d] ld=%lld", n_rows, n_cols, ld);
-  cb::colsum_rows_kernel<<<(n_cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(in, n_rows, n_cols, ld, out);
+  cb::colsum_rows_kernel<<<(n_cols + cb::kColsumCols - 1) / cb::kColsumCols, cb::kColsumCols * cb::kColsumGroups, 0,
+                           (cudaStream_t)stream>>>(in, n_rows, n_cols, ld, out);
   return cb::check_launch("cb_colsum_rows");
 }
 

@@ -134,8 +134,11 @@ struct GemmParams {
 };
 
 // MT = accumulators of 128 rows per CTA, BN = tile width; MT * BN <= 512 TMEM columns.
-template <int MT, int BN, bool A_MN, bool B_MN, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// MINB = CTAs per SM the launch is sized for: short-K products (weight gradients: K = 255 droplets; the hidden layers)
+// run two CTAs per SM with a 2-stage ring (2 x 256 TMEM columns, 2 x 97 KB of shared memory), so one CTA's epilogue
+// overlaps the other's loads -- each CTA lives for only ~8 k-blocks.
+template <int MT, int BN, bool A_MN, bool B_MN, int STAGES, int MINB>
+__global__ void __launch_bounds__(kGemmThreads, MINB)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b2, GemmParams p) {
   constexpr uint32_t kABytes = MT * kBlockM * kBlockK * 4;  // per stage
@@ -336,13 +339,12 @@ static int make_tmap(CUtensorMap* map, const float* base, long long rows, long l
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 
-template <int MT, int BN, bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
-                  const GemmParams& p, cudaStream_t st) {
+template <int MT, int BN, bool A_MN, bool B_MN, int STAGES, int MINB>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                      const GemmParams& p, cudaStream_t st) {
   constexpr int kStage = (MT * kBlockM + BN) * kBlockK * 4;
-  constexpr int STAGES = (kStage <= 48 * 1024) ? 4 : 3;
   const int smem = STAGES * kStage + 1024;
-  auto kern = gemm_tf32_kernel<MT, BN, A_MN, B_MN, STAGES>;
+  auto kern = gemm_tf32_kernel<MT, BN, A_MN, B_MN, STAGES, MINB>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 3;
@@ -351,6 +353,16 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   dim3 grid((p.N + BN - 1) / BN, (p.M + MT * kBlockM - 1) / (MT * kBlockM), p.split_k);
   kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, ta2, tb2, p);
   return 0;
+}
+
+template <int MT, int BN, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                  const GemmParams& p, cudaStream_t st) {
+  constexpr int kStage = (MT * kBlockM + BN) * kBlockK * 4;
+  constexpr int kDeep = (kStage <= 48 * 1024) ? 4 : 3;
+  if (p.k_blocks_per_split <= 16 && MT * BN <= 256)  // short K: two co-resident CTAs per SM, 2-stage ring each
+    return launch_cfg<MT, BN, A_MN, B_MN, 2, 2>(ta, tb, ta2, tb2, p, st);
+  return launch_cfg<MT, BN, A_MN, B_MN, kDeep, 1>(ta, tb, ta2, tb2, p, st);
 }
 
 }  // namespace cb

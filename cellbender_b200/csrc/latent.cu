@@ -14,16 +14,23 @@
 //   simplex_forward / simplex_backward   transform_to(constraints.simplex) (torch SoftmaxTransform) of the
 //                    chi_ambient parameter (model.py:245-249, 486-490) and its vector-Jacobian product
 //
-// All scalar algebra runs in fp64 registers (a few hundred values per step); inputs and outputs are fp32.
+// The per-droplet algebra runs in fp32 registers (type R below), sums over droplets in fp64; inputs and outputs are fp32.
 // The implicit reparameterisation gradients of the Gamma and Beta samples (torch._standard_gamma_grad,
 // torch._dirichlet_grad -- what Gamma.rsample / Beta.rsample differentiate through) are passed in as factors.
 #include "common.cuh"
 
 namespace cb {
 
-constexpr double kHalfLog2Pi = 0.91893853320467274178;
-constexpr double kFltTiny = 1.17549435e-38;
-constexpr double kFltEps = 1.1920928955078125e-07;
+// Arithmetic type of the per-droplet algebra.  fp32 matches the reference (torch fp32) and keeps the one-CTA kernels
+// short; sums over droplets are accumulated in fp64 either way.  -DCB_LATENT_FP64 switches everything to fp64.
+#ifdef CB_LATENT_FP64
+using R = double;
+#else
+using R = float;
+#endif
+constexpr R kHalfLog2Pi = R(0.91893853320467274178);
+constexpr R kFltTiny = R(1.17549435e-38);
+constexpr R kFltEps = R(1.1920928955078125e-07);
 
 struct LatentConsts {
   float log_count_crossover, prior_log_cell_counts, empty_log_count_threshold, offset_logit_p;
@@ -40,80 +47,80 @@ struct ScalarGrads {
   float *d_cell_scale, *d_empty_loc, *d_empty_scale, *rho_alpha, *rho_beta, *phi_loc, *phi_scale;
 };
 
-__device__ __forceinline__ double sigmoid_d(double x) { return 1.0 / (1.0 + exp(-x)); }
-__device__ __forceinline__ double logsigmoid_d(double x) { return fmin(x, 0.0) - log1p(exp(-fabs(x))); }
+__device__ __forceinline__ R sigmoid_d(R x) { return R(1.0) / (R(1.0) + exp(-x)); }
+__device__ __forceinline__ R logsigmoid_d(R x) { return fmin(x, R(0.0)) - log1p(exp(-fabs(x))); }
 // torch.nn.Softplus(beta=1, threshold=20) and its derivative
-__device__ __forceinline__ double softplus_d(double x) { return x > 20.0 ? x : log1p(exp(x)); }
-__device__ __forceinline__ double softplus_grad_d(double x) { return x > 20.0 ? 1.0 : sigmoid_d(x); }
-__device__ __forceinline__ double clipped_sigmoid_d(double x) {
-  return fmin(fmax(sigmoid_d(x), kFltTiny), 1.0 - kFltEps);  // torch.distributions.transforms._clipped_sigmoid (fp32)
+__device__ __forceinline__ R softplus_d(R x) { return x > R(20.0) ? x : log1p(exp(x)); }
+__device__ __forceinline__ R softplus_grad_d(R x) { return x > R(20.0) ? R(1.0) : sigmoid_d(x); }
+__device__ __forceinline__ R clipped_sigmoid_d(R x) {
+  return fmin(fmax(sigmoid_d(x), kFltTiny), R(1.0) - kFltEps);  // torch.distributions.transforms._clipped_sigmoid (fp32)
 }
-__device__ double digamma_d(double x) {
-  double r = 0.0;
-  while (x < 6.0) {
-    r -= 1.0 / x;
-    x += 1.0;
+__device__ R digamma_d(R x) {
+  R r = R(0.0);
+  while (x < R(6.0)) {
+    r -= R(1.0) / x;
+    x += R(1.0);
   }
-  const double f = 1.0 / (x * x);
-  return r + log(x) - 0.5 / x - f * (1.0 / 12.0 - f * (1.0 / 120.0 - f * (1.0 / 252.0 - f * (1.0 / 240.0 - f / 132.0))));
+  const R f = R(1.0) / (x * x);
+  return r + log(x) - R(0.5) / x - f * (R(1.0) / R(12.0) - f * (R(1.0) / R(120.0) - f * (R(1.0) / R(252.0) - f * (R(1.0) / R(240.0) - f / R(132.0)))));
 }
-__device__ __forceinline__ double xlogy_d(double x, double y) { return x == 0.0 ? 0.0 : x * log(y); }
+__device__ __forceinline__ R xlogy_d(R x, R y) { return x == R(0.0) ? R(0.0) : x * log(y); }
 
 struct Globals {  // constrained scalar parameters and what derives from them
-  double dcs, del, des, ra, rb, pl, psc, phi_conc, phi_rate;
-  double sra, srb;  // clipped sigmoids behind rho_alpha / rho_beta
-  double d_empty_enc;  // exp(d_empty_loc): what EncodeNonZLatents subtracts from the counts (vae/encoder.py:330)
+  R dcs, del, des, ra, rb, pl, psc, phi_conc, phi_rate;
+  R sra, srb;  // clipped sigmoids behind rho_alpha / rho_beta
+  R d_empty_enc;  // exp(d_empty_loc): what EncodeNonZLatents subtracts from the counts (vae/encoder.py:330)
   bool has_rho;
 };
 
 __device__ Globals load_globals(const ScalarParams& p, const LatentConsts& k) {
   Globals g;
-  g.dcs = exp(double(p.d_cell_scale[0]));
-  g.del = exp(double(p.d_empty_loc[0]));
-  g.des = exp(double(p.d_empty_scale[0]));
+  g.dcs = exp(R(p.d_cell_scale[0]));
+  g.del = exp(R(p.d_empty_loc[0]));
+  g.des = exp(R(p.d_empty_scale[0]));
   g.has_rho = (p.rho_alpha != nullptr) && (k.model_type != 0.f);
-  g.sra = g.srb = 0.0;
-  g.ra = g.rb = 1.0;
+  g.sra = g.srb = R(0.0);
+  g.ra = g.rb = R(1.0);
   if (g.has_rho) {
-    const double lo = k.rho_param_min, hi = k.rho_param_max;
-    g.sra = clipped_sigmoid_d(double(p.rho_alpha[0]));
-    g.srb = clipped_sigmoid_d(double(p.rho_beta[0]));
+    const R lo = k.rho_param_min, hi = k.rho_param_max;
+    g.sra = clipped_sigmoid_d(R(p.rho_alpha[0]));
+    g.srb = clipped_sigmoid_d(R(p.rho_beta[0]));
     g.ra = lo + (hi - lo) * g.sra;
     g.rb = lo + (hi - lo) * g.srb;
   }
   g.d_empty_enc = exp(g.del);
-  g.pl = exp(double(p.phi_loc[0]));
-  g.psc = exp(double(p.phi_scale[0]));
+  g.pl = exp(R(p.phi_loc[0]));
+  g.psc = exp(R(p.phi_scale[0]));
   g.phi_conc = (g.pl / g.psc) * (g.pl / g.psc);
   g.phi_rate = g.pl / (g.psc * g.psc);
   return g;
 }
 
 struct EncRow {  // EncodeNonZLatents output shaping (vae/encoder.py:300-340) for one droplet
-  double counts, p_y, dpy_dpout, eps_enc, deps_dout, d_loc, ddloc_deps, prob, q1, q0, lq1, lq0;
+  R counts, p_y, dpy_dpout, eps_enc, deps_dout, d_loc, ddloc_deps, prob, q1, q0, lq1, lq0;
 };
 
-__device__ EncRow shape_encoder_row(float counts_f, float p_out, float eps_out, double d_empty_enc, const LatentConsts& k) {
+__device__ EncRow shape_encoder_row(float counts_f, float p_out, float eps_out, R d_empty_enc, const LatentConsts& k) {
   EncRow r;
-  const double c = counts_f;
+  const R c = counts_f;
   r.counts = c;
-  const double ls = log1p(c);
-  const double dlt = ls - double(k.log_count_crossover);
-  const double sgn = (dlt > 0.0) - (dlt < 0.0);
-  double p = (double(p_out) - double(k.offset_logit_p)) + sqrt(fabs(dlt)) * sgn * 10.0;
-  const double a1 = sigmoid_d(50.0 * (ls - double(k.prior_log_cell_counts)));
-  p = (1.0 - a1) * p + a1 * 10.0;
-  const double a0 = sigmoid_d(50.0 * (ls - double(k.empty_log_count_threshold)));
-  r.p_y = a0 * p + (1.0 - a0) * (-10.0);
-  r.dpy_dpout = a0 * (1.0 - a1);
-  const double s = sigmoid_d(double(eps_out) * 0.2 - 1.0986122886681098);
-  r.eps_enc = 2.0 * s + 0.5;
-  r.deps_dout = 2.0 * s * (1.0 - s) * 0.2;
-  const double u = c / (r.eps_enc + 1e-2) - d_empty_enc;
-  const double spu = softplus_d(u) + 1e-10;
-  const double t = log(spu) - double(k.log_count_crossover);
-  r.d_loc = softplus_d(t) + double(k.log_count_crossover);
-  r.ddloc_deps = softplus_grad_d(t) * (1.0 / spu) * softplus_grad_d(u) * (-c / ((r.eps_enc + 1e-2) * (r.eps_enc + 1e-2)));
+  const R ls = log1p(c);
+  const R dlt = ls - R(k.log_count_crossover);
+  const R sgn = (dlt > R(0.0)) - (dlt < R(0.0));
+  R p = (R(p_out) - R(k.offset_logit_p)) + sqrt(fabs(dlt)) * sgn * R(10.0);
+  const R a1 = sigmoid_d(R(50.0) * (ls - R(k.prior_log_cell_counts)));
+  p = (R(1.0) - a1) * p + a1 * R(10.0);
+  const R a0 = sigmoid_d(R(50.0) * (ls - R(k.empty_log_count_threshold)));
+  r.p_y = a0 * p + (R(1.0) - a0) * (-R(10.0));
+  r.dpy_dpout = a0 * (R(1.0) - a1);
+  const R s = sigmoid_d(R(eps_out) * R(0.2) - R(1.0986122886681098));
+  r.eps_enc = R(2.0) * s + R(0.5);
+  r.deps_dout = R(2.0) * s * (R(1.0) - s) * R(0.2);
+  const R u = c / (r.eps_enc + R(1e-2)) - d_empty_enc;
+  const R spu = softplus_d(u) + R(1e-10);
+  const R t = log(spu) - R(k.log_count_crossover);
+  r.d_loc = softplus_d(t) + R(k.log_count_crossover);
+  r.ddloc_deps = softplus_grad_d(t) * (R(1.0) / spu) * softplus_grad_d(u) * (-c / ((r.eps_enc + R(1e-2)) * (r.eps_enc + R(1e-2))));
   r.prob = sigmoid_d(r.p_y);
   r.lq1 = logsigmoid_d(r.p_y);
   r.lq0 = logsigmoid_d(-r.p_y);
@@ -122,68 +129,68 @@ __device__ EncRow shape_encoder_row(float counts_f, float p_out, float eps_out, 
   return r;
 }
 
-__device__ __forceinline__ double p_logit_prior_row(double counts, const LatentConsts& k) {  // model.py:577-592
-  const double lc = log(counts);
-  const double thresh = (log(double(k.empty_umi_threshold)) + double(k.d_cell_loc_prior)) / 2.0;
-  double p = k.p_logit_prior;
-  if (lc <= thresh) p = -100.0;
-  if (lc >= double(k.d_cell_loc_prior)) p = 10.0;
+__device__ __forceinline__ R p_logit_prior_row(R counts, const LatentConsts& k) {  // model.py:577-592
+  const R lc = log(counts);
+  const R thresh = (log(R(k.empty_umi_threshold)) + R(k.d_cell_loc_prior)) / R(2.0);
+  R p = k.p_logit_prior;
+  if (lc <= thresh) p = -R(100.0);
+  if (lc >= R(k.d_cell_loc_prior)) p = R(10.0);
   return p;
 }
 
 struct SampleRow {  // the reparameterised guide samples of one droplet
-  double rho, lde, d_empty, lx, d_cell, eps_conc, epsilon, n_dc, n_de, n_v;
+  R rho, lde, d_empty, lx, d_cell, eps_conc, epsilon, n_dc, n_de, n_v;
 };
 
 __device__ SampleRow sample_row(const EncRow& e, const Globals& g, const LatentConsts& k, const float* n_row3, float g_eps,
                                 const float* xx2) {
   SampleRow s;
   s.n_dc = n_row3[0], s.n_de = n_row3[1], s.n_v = n_row3[2];
-  s.rho = g.has_rho ? double(xx2[0]) : 0.0;
+  s.rho = g.has_rho ? R(xx2[0]) : R(0.0);
   s.lde = g.del + g.des * s.n_de;
   s.d_empty = exp(s.lde);
-  const double gated = e.prob * e.d_loc + (1.0 - e.prob) * double(k.d_cell_loc_prior);
+  const R gated = e.prob * e.d_loc + (R(1.0) - e.prob) * R(k.d_cell_loc_prior);
   s.lx = gated + g.dcs * s.n_dc;
   s.d_cell = exp(s.lx);
-  s.eps_conc = (e.prob * e.eps_enc + (1.0 - e.prob)) * double(k.epsilon_prior);
-  s.epsilon = fmax(double(g_eps) / double(k.epsilon_prior), kFltTiny);
+  s.eps_conc = (e.prob * e.eps_enc + (R(1.0) - e.prob)) * R(k.epsilon_prior);
+  s.epsilon = fmax(R(g_eps) / R(k.epsilon_prior), kFltTiny);
   return s;
 }
 
-// block-wide sum of N doubles per thread (result in every thread); smem: N * 32 doubles
+// block-wide sum of N Rs per thread (result in every thread); smem: N * 32 Rs
 template <int N>
 __device__ void block_sum_d(double (&v)[N], double* smem) { block_sum<double, N>(v, smem); }
 
-// lower median (torch.median) of vals[i] over mask[i] != 0: index of the element of rank (k-1)/2 in (value, index)
-// order, or -1 when the mask is empty.  O(B^2 / threads) rank counting; result broadcast through smem_idx.
-__device__ int masked_lower_median_index(const float* vals, const unsigned char* mask, unsigned char bit, int B, int* smem_idx,
-                                         int* smem_cnt) {
-  if (threadIdx.x == 0) {
-    *smem_idx = -1;
-    int kcount = 0;
-    for (int i = 0; i < B; ++i) kcount += (mask[i] & bit) ? 1 : 0;
-    *smem_cnt = kcount;
-  }
+// Lower medians (torch.median) of vals over the two disjoint droplet classes mask bit 1 (probable empties) and bit 2
+// (probable cells): index of the element of rank (k-1)/2 in (value, index) order within its class, -1 for an empty
+// class.  Every droplet belongs to exactly one class, so one O(B^2 / threads) rank-counting sweep finds both.
+// res[0] = cells, res[1] = empties, res[2] = number of droplets with mask bit 4 (surely cells).
+__device__ void class_medians(const float* vals, const unsigned char* mask, int B, int* res, int* cnt) {
+  if (threadIdx.x < 3) res[threadIdx.x] = (threadIdx.x == 2) ? 0 : -1;
+  if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
   __syncthreads();
-  const int kcount = *smem_cnt;
-  if (kcount > 0) {
-    const int want = (kcount - 1) / 2;
-    for (int i = threadIdx.x; i < B; i += blockDim.x) {
-      if (!(mask[i] & bit)) continue;
-      const float vi = vals[i];
-      int rank = 0;
-      for (int j = 0; j < B; ++j) {
-        if (!(mask[j] & bit)) continue;
-        const float vj = vals[j];
-        rank += (vj < vi) || (vj == vi && j < i);
-      }
-      if (rank == want) *smem_idx = i;
+  int c_cell = 0, c_empty = 0, c_sure = 0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const unsigned char m = mask[i];
+    c_cell += (m & 2) ? 1 : 0, c_empty += (m & 1) ? 1 : 0, c_sure += (m & 4) ? 1 : 0;
+  }
+  if (c_cell) atomicAdd(&cnt[0], c_cell);
+  if (c_empty) atomicAdd(&cnt[1], c_empty);
+  if (c_sure) atomicAdd(&res[2], c_sure);
+  __syncthreads();
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const unsigned char bit = mask[i] & 3;
+    const int which = (bit == 2) ? 0 : 1;
+    const int want = (cnt[which] - 1) / 2;
+    const float vi = vals[i];
+    int rank = 0;
+    for (int j = 0; j < B; ++j) {
+      const float vj = vals[j];
+      rank += ((mask[j] & 3) == bit) && ((vj < vi) || (vj == vi && j < i));
     }
+    if (rank == want) res[which] = i;
   }
   __syncthreads();
-  const int found = *smem_idx;
-  __syncthreads();  // the next call resets smem_idx
-  return found;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(256) latent_prepare_kernel(const float* __rest
   if (threadIdx.x == 0 && blockIdx.x == 0) conc_gamma[0] = float(g.phi_conc);
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
     const EncRow e = shape_encoder_row(feats[4 * b], p_out[b], eps_out[b], g.d_empty_enc, k);
-    conc_gamma[1 + b] = float((e.prob * e.eps_enc + (1.0 - e.prob)) * double(k.epsilon_prior));
+    conc_gamma[1 + b] = float((e.prob * e.eps_enc + (R(1.0) - e.prob)) * R(k.epsilon_prior));
     conc_gamma[1 + B + b] = float(g.ra);
     conc_gamma[1 + 2 * B + b] = float(g.rb);
     conc_beta[2 * b] = float(g.ra), conc_beta[2 * b + 1] = float(g.rb);
@@ -208,11 +215,11 @@ __global__ void latent_beta_kernel(float* __restrict__ gdraw, int B, float* __re
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 1 + 3 * B) gdraw[i] = fmaxf(gdraw[i], 1.17549435e-38f);
   if (i < B) {
-    const double ga = fmax(double(gdraw[1 + B + i]), kFltTiny), gb = fmax(double(gdraw[1 + 2 * B + i]), kFltTiny);
-    double x = ga / (ga + gb);
-    x = fmin(fmax(x, kFltTiny), 1.0 - kFltEps);
+    const R ga = fmax(R(gdraw[1 + B + i]), kFltTiny), gb = fmax(R(gdraw[1 + 2 * B + i]), kFltTiny);
+    R x = ga / (ga + gb);
+    x = fmin(fmax(x, kFltTiny), R(1.0) - kFltEps);
     xx[2 * i] = float(x);
-    xx[2 * i + 1] = float(1.0 - x);
+    xx[2 * i + 1] = float(R(1.0) - x);
   }
 }
 
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(256) latent_forward_kernel(
   float* eps_s = zq + B;
   unsigned char* mask = reinterpret_cast<unsigned char*>(eps_s + 2 * B);
   __shared__ double red[T_N * 32];
-  __shared__ int s_idx, s_cnt;
+  __shared__ int s_res[3], s_cnt[2];
 
   const Globals g = load_globals(sp, k);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -241,11 +248,11 @@ __global__ void __launch_bounds__(256) latent_forward_kernel(
   for (int r = wid; r < B; r += nw) {
     double sp_ = 0.0, sq_ = 0.0;
     for (int j = lane; j < Z; j += 32) {
-      const double n = n_z[(long long)r * Z + j], ls = z_ls[r * ldz + j];
-      const double z = double(z_loc[r * ldz + j]) + exp(ls) * n;
+      const R n = n_z[(long long)r * Z + j], ls = z_ls[r * ldz + j];
+      const R z = R(z_loc[r * ldz + j]) + exp(ls) * n;
       z_out[(long long)r * Z + j] = float(z);
-      sp_ += -0.5 * z * z - kHalfLog2Pi;
-      sq_ += -0.5 * n * n - ls - kHalfLog2Pi;
+      sp_ += -R(0.5) * z * z - kHalfLog2Pi;
+      sq_ += -R(0.5) * n * n - ls - kHalfLog2Pi;
     }
     sp_ = warp_sum(sp_), sq_ = warp_sum(sq_);
     if (lane == 0) zprior[r] = float(sp_), zq[r] = float(sq_);
@@ -254,9 +261,9 @@ __global__ void __launch_bounds__(256) latent_forward_kernel(
 
   double acc[T_N];
 #pragma unroll
-  for (int i = 0; i < T_N; ++i) acc[i] = 0.0;
-  const double ep = k.epsilon_prior;
-  const double phi = fmax(double(g_gamma[0]) / g.phi_rate, kFltTiny);
+  for (int i = 0; i < T_N; ++i) acc[i] = R(0.0);
+  const R ep = k.epsilon_prior;
+  const R phi = fmax(R(g_gamma[0]) / g.phi_rate, kFltTiny);
 
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const EncRow e = shape_encoder_row(feats[4 * b], p_out[b], eps_out[b], g.d_empty_enc, k);
@@ -264,73 +271,71 @@ __global__ void __launch_bounds__(256) latent_forward_kernel(
     enc_out[4 * b + 0] = float(e.p_y), enc_out[4 * b + 1] = float(e.d_loc), enc_out[4 * b + 2] = float(e.eps_enc);
     enc_out[4 * b + 3] = float(s.epsilon);
     // rate coefficients (calculate_mu / calculate_lambda, model.py:25-85, factored; obs_empty: rho, d_cell detached, eps = 1)
-    const double r = s.rho, ee = s.epsilon, dc = s.d_cell, de = s.d_empty;
-    const double amb = (k.model_type == 1.f) ? 0.0 : 1.0;  // 'swapping' has no chi_ambient term
+    const R r = s.rho, ee = s.epsilon, dc = s.d_cell, de = s.d_empty;
+    const R amb = (k.model_type == 1.f) ? R(0.0) : R(1.0);  // 'swapping' has no chi_ambient term
     float* cf = coef + 7 * b;
-    cf[0] = float((1.0 - r) * ee * dc);
-    cf[1] = float(amb * ee * (1.0 - r) * de);
+    cf[0] = float((R(1.0) - r) * ee * dc);
+    cf[1] = float(amb * ee * (R(1.0) - r) * de);
     cf[2] = float(ee * r * (dc + de));
-    cf[3] = float(amb * ee * (1.0 - r) * de);
+    cf[3] = float(amb * ee * (R(1.0) - r) * de);
     cf[4] = float(ee * r * de);
-    cf[5] = float(amb * (1.0 - r) * de);
+    cf[5] = float(amb * (R(1.0) - r) * de);
     cf[6] = float(r * de);
-    w_out[3 * b + 0] = float(-e.q1), w_out[3 * b + 1] = float(-e.q0), w_out[3 * b + 2] = float(-0.01 * e.q0);
+    w_out[3 * b + 0] = float(-e.q1), w_out[3 * b + 1] = float(-e.q0), w_out[3 * b + 2] = float(-R(0.01) * e.q0);
 
-    acc[T_Z] += double(zprior[b]) - e.q1 * double(zq[b]);
+    acc[T_Z] += R(zprior[b]) - e.q1 * R(zq[b]);
     {  // d_cell: LogNormal prior vs guide (the -log d_cell of both LogNormal densities cancels)
-      const double dz = (s.lx - double(k.d_cell_loc_prior)) / double(k.d_cell_scale_prior);
-      acc[T_DCELL] += (-0.5 * dz * dz - log(double(k.d_cell_scale_prior))) - (-0.5 * s.n_dc * s.n_dc - log(g.dcs));
+      const R dz = (s.lx - R(k.d_cell_loc_prior)) / R(k.d_cell_scale_prior);
+      acc[T_DCELL] += (-R(0.5) * dz * dz - log(R(k.d_cell_scale_prior))) - (-R(0.5) * s.n_dc * s.n_dc - log(g.dcs));
     }
     if (g.has_rho) {
-      const double a0 = k.rho_alpha_prior, b0 = k.rho_beta_prior, lr = log(r), l1r = log1p(-r);
-      const double prior = xlogy_d(a0 - 1.0, r) + (b0 - 1.0) * l1r + lgamma(a0 + b0) - lgamma(a0) - lgamma(b0);
-      const double guide = (g.ra - 1.0) * lr + (g.rb - 1.0) * l1r + lgamma(g.ra + g.rb) - lgamma(g.ra) - lgamma(g.rb);
+      const R a0 = k.rho_alpha_prior, b0 = k.rho_beta_prior, lr = log(r), l1r = log1p(-r);
+      const R prior = xlogy_d(a0 - R(1.0), r) + (b0 - R(1.0)) * l1r + lgamma(a0 + b0) - lgamma(a0) - lgamma(b0);
+      const R guide = (g.ra - R(1.0)) * lr + (g.rb - R(1.0)) * l1r + lgamma(g.ra + g.rb) - lgamma(g.ra) - lgamma(g.rb);
       acc[T_RHO] += prior - guide;
     }
     {
-      const double le = log(ee);
-      const double prior = ep * log(ep) + (ep - 1.0) * le - ep * ee - lgamma(ep);
-      const double guide = s.eps_conc * log(ep) + (s.eps_conc - 1.0) * le - ep * ee - lgamma(s.eps_conc);
+      const R le = log(ee);
+      const R prior = ep * log(ep) + (ep - R(1.0)) * le - ep * ee - lgamma(ep);
+      const R guide = s.eps_conc * log(ep) + (s.eps_conc - R(1.0)) * le - ep * ee - lgamma(s.eps_conc);
       acc[T_EPS] += prior - guide;
     }
     {
-      const double dz = (s.lde - double(k.d_empty_loc_prior)) / double(k.d_empty_scale_prior);
-      acc[T_DEMPTY] += (-0.5 * dz * dz - log(double(k.d_empty_scale_prior))) - (-0.5 * s.n_de * s.n_de - log(g.des));
+      const R dz = (s.lde - R(k.d_empty_loc_prior)) / R(k.d_empty_scale_prior);
+      acc[T_DEMPTY] += (-R(0.5) * dz * dz - log(R(k.d_empty_scale_prior))) - (-R(0.5) * s.n_de * s.n_de - log(g.des));
     }
     {
-      const double plp = p_logit_prior_row(e.counts, k);
+      const R plp = p_logit_prior_row(e.counts, k);
       acc[T_Y] += e.q1 * (logsigmoid_d(plp) - e.lq1) + e.q0 * (logsigmoid_d(-plp) - e.lq0);
-      const double v = e.p_y + 2.0 * s.n_v, dv = (v - double(k.p_logit_prior)) / 2.0;
-      acc[T_PLR] += (-0.5 * dv * dv) - (-0.5 * s.n_v * s.n_v);
+      const R v = e.p_y + R(2.0) * s.n_v, dv = (v - R(k.p_logit_prior)) / R(2.0);
+      acc[T_PLR] += (-R(0.5) * dv * dv) - (-R(0.5) * s.n_v * s.n_v);
     }
-    const bool is_empty = e.counts < double(k.counts_crossover);
+    const bool is_empty = e.counts < R(k.counts_crossover);
     {  // soft semi-supervision of p_y (model.py:400-427), Normal(+-10, 1).log_prob(p_y), scale 10
-      const double d = is_empty ? (e.p_y + 10.0) : (e.p_y - 10.0);
-      acc[is_empty ? T_SOFT_EMPTY : T_SOFT_CELL] += 10.0 * (-0.5 * d * d - kHalfLog2Pi);
+      const R d = is_empty ? (e.p_y + R(10.0)) : (e.p_y - R(10.0));
+      acc[is_empty ? T_SOFT_EMPTY : T_SOFT_CELL] += R(10.0) * (-R(0.5) * d * d - kHalfLog2Pi);
     }
     eps_s[b] = float(ee);
-    const bool surely_cell = e.counts >= exp(double(k.d_cell_loc_prior));
+    const bool surely_cell = e.counts >= exp(R(k.d_cell_loc_prior));
     mask[b] = (unsigned char)((is_empty ? 1 : 2) | (surely_cell ? 4 : 0));
   }
   if (threadIdx.x == 0) {
-    const double pc0 = k.phi_conc_prior, pr0 = k.phi_rate_prior, lphi = log(phi);
-    const double prior = pc0 * log(pr0) + (pc0 - 1.0) * lphi - pr0 * phi - lgamma(pc0);
-    const double guide = g.phi_conc * log(g.phi_rate) + (g.phi_conc - 1.0) * lphi - g.phi_rate * phi - lgamma(g.phi_conc);
+    const R pc0 = k.phi_conc_prior, pr0 = k.phi_rate_prior, lphi = log(phi);
+    const R prior = pc0 * log(pr0) + (pc0 - R(1.0)) * lphi - pr0 * phi - lgamma(pc0);
+    const R guide = g.phi_conc * log(g.phi_rate) + (g.phi_conc - R(1.0)) * lphi - g.phi_rate * phi - lgamma(g.phi_conc);
     acc[T_PHI] = prior - guide;
-    alpha_out[0] = float(1.0 / phi + 1e-10);
+    alpha_out[0] = float(R(1.0) / phi + R(1e-10));
   }
   __syncthreads();
   // ---- epsilon medians over probable cells / probable empties (model.py:429-443)
-  const int i_cell = masked_lower_median_index(eps_s, mask, 2, B, &s_idx, &s_cnt);
-  const int i_empty = masked_lower_median_index(eps_s, mask, 1, B, &s_idx, &s_cnt);
+  class_medians(eps_s, mask, B, s_res, s_cnt);
   if (threadIdx.x == 0) {
-    int n_surely = 0;
-    for (int i = 0; i < B; ++i) n_surely += (mask[i] & 4) ? 1 : 0;
-    const double lognorm = -log(0.01) - kHalfLog2Pi;
-    const double mc = (i_cell >= 0) ? double(eps_s[i_cell]) : 1.0, me = (i_empty >= 0) ? double(eps_s[i_empty]) : 1.0;
+    const int i_cell = s_res[0], i_empty = s_res[1], n_surely = s_res[2];
+    const R lognorm = -log(R(0.01)) - kHalfLog2Pi;
+    const R mc = (i_cell >= 0) ? R(eps_s[i_cell]) : R(1.0), me = (i_empty >= 0) ? R(eps_s[i_empty]) : R(1.0);
     const bool use_cell = n_surely >= 2;
-    acc[T_EPS_MEAN] = use_cell ? (-0.5 * (1.0 - mc) * (1.0 - mc) / 1e-4 + lognorm) : 0.0;
-    acc[T_EPS_EMPTY_MEAN] = -0.5 * (1.0 - me) * (1.0 - me) / 1e-4 + lognorm;
+    acc[T_EPS_MEAN] = use_cell ? (R(-0.5) * (R(1.0) - mc) * (R(1.0) - mc) / R(1e-4) + lognorm) : R(0.0);
+    acc[T_EPS_EMPTY_MEAN] = R(-0.5) * (R(1.0) - me) * (R(1.0) - me) / R(1e-4) + lognorm;
     med_idx[0] = (use_cell ? i_cell : -1);
     med_idx[1] = i_empty;
   }
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(256) latent_backward_kernel(
 
   const Globals g = load_globals(sp, k);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const double gl = g_local ? double(g_local[0]) : 1.0;  // upstream gradient of the local-terms loss output
+  const R gl = g_local ? R(g_local[0]) : R(1.0);  // upstream gradient of the local-terms loss output
 
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const EncRow e = shape_encoder_row(feats[4 * b], p_out[b], eps_out[b], g.d_empty_enc, k);
@@ -371,14 +376,14 @@ __global__ void __launch_bounds__(256) latent_backward_kernel(
   // ---- z: d loss / d loc, d loss / d log_scale; per-row guide log-density for the d q1 path
   for (int r = wid; r < B; r += nw) {
     double sq_ = 0.0;
-    const double q1 = q1_s[r];
+    const R q1 = q1_s[r];
     for (int j = lane; j < Z; j += 32) {
-      const double n = n_z[(long long)r * Z + j], ls = z_ls[r * ldz + j], s = exp(ls);
-      const double z = double(z_loc[r * ldz + j]) + s * n;
-      const double gz = gl * z + (d_z ? double(d_z[(long long)r * Z + j]) : 0.0);  // -d/dz of the N(0,1) prior term + obs path
+      const R n = n_z[(long long)r * Z + j], ls = z_ls[r * ldz + j], s = exp(ls);
+      const R z = R(z_loc[r * ldz + j]) + s * n;
+      const R gz = gl * z + (d_z ? R(d_z[(long long)r * Z + j]) : R(0.0));  // -d/dz of the N(0,1) prior term + obs path
       d_z_loc[r * lddz + j] = float(gz);
       d_z_ls[r * lddz + j] = float(gz * n * s - gl * q1);
-      sq_ += -0.5 * n * n - ls - kHalfLog2Pi;
+      sq_ += -R(0.5) * n * n - ls - kHalfLog2Pi;
     }
     sq_ = warp_sum(sq_);
     if (lane == 0) zq[r] = float(sq_);
@@ -387,75 +392,75 @@ __global__ void __launch_bounds__(256) latent_backward_kernel(
 
   double ga[7];  // d loss / d (d_cell_scale, d_empty_loc, d_empty_scale, rho_alpha, rho_beta, phi_loc, phi_scale), constrained
 #pragma unroll
-  for (int i = 0; i < 7; ++i) ga[i] = 0.0;
-  const double ep = k.epsilon_prior;
+  for (int i = 0; i < 7; ++i) ga[i] = R(0.0);
+  const R ep = k.epsilon_prior;
   const int i_cell = med_idx[0], i_empty = med_idx[1];
 
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const EncRow e = shape_encoder_row(feats[4 * b], p_out[b], eps_out[b], g.d_empty_enc, k);
     const SampleRow s = sample_row(e, g, k, n_row + 3 * b, g_gamma[1 + b], xx + 2 * b);
-    const double r = s.rho, ee = s.epsilon, dc = s.d_cell, de = s.d_empty;
+    const R r = s.rho, ee = s.epsilon, dc = s.d_cell, de = s.d_empty;
     const bool swapping = (k.model_type == 1.f);
-    double G0 = 0, G1 = 0, G2 = 0, G3 = 0, G4 = 0, G5 = 0, G6 = 0;
+    R G0 = 0, G1 = 0, G2 = 0, G3 = 0, G4 = 0, G5 = 0, G6 = 0;
     if (d_coef) {
       const float* gc = d_coef + 7 * b;
       G0 = gc[0], G2 = gc[2], G4 = gc[4], G6 = gc[6];
       if (!swapping) G1 = gc[1], G3 = gc[3], G5 = gc[5];
     }
-    const double G13 = G1 + G3;
-    double G_e = G0 * (1.0 - r) * dc + G13 * (1.0 - r) * de + G2 * r * (dc + de) + G4 * r * de;
-    double G_r = -G0 * ee * dc - G13 * ee * de + G2 * ee * (dc + de) + G4 * ee * de;
-    const double G_dc = G0 * (1.0 - r) * ee + G2 * ee * r;
-    const double G_de = G13 * ee * (1.0 - r) + (G2 + G4) * ee * r + G5 * (1.0 - r) + G6 * r;
+    const R G13 = G1 + G3;
+    R G_e = G0 * (R(1.0) - r) * dc + G13 * (R(1.0) - r) * de + G2 * r * (dc + de) + G4 * r * de;
+    R G_r = -G0 * ee * dc - G13 * ee * de + G2 * ee * (dc + de) + G4 * ee * de;
+    const R G_dc = G0 * (R(1.0) - r) * ee + G2 * ee * r;
+    const R G_de = G13 * ee * (R(1.0) - r) + (G2 + G4) * ee * r + G5 * (R(1.0) - r) + G6 * r;
     // d_cell
-    double G_lx = G_dc * dc + gl * (s.lx - double(k.d_cell_loc_prior)) / (double(k.d_cell_scale_prior) * double(k.d_cell_scale_prior));
+    R G_lx = G_dc * dc + gl * (s.lx - R(k.d_cell_loc_prior)) / (R(k.d_cell_scale_prior) * R(k.d_cell_scale_prior));
     ga[0] += G_lx * s.n_dc - gl / g.dcs;
-    const double G_dloc = G_lx * e.prob;
+    const R G_dloc = G_lx * e.prob;
     // d_empty
-    const double G_lde = G_de * de + gl * (s.lde - double(k.d_empty_loc_prior)) / (double(k.d_empty_scale_prior) * double(k.d_empty_scale_prior));
+    const R G_lde = G_de * de + gl * (s.lde - R(k.d_empty_loc_prior)) / (R(k.d_empty_scale_prior) * R(k.d_empty_scale_prior));
     ga[1] += G_lde;
     ga[2] += G_lde * s.n_de - gl / g.des;
     // rho
     if (g.has_rho) {
-      const double a0 = k.rho_alpha_prior, b0 = k.rho_beta_prior;
-      const double dt_dr = (a0 - 1.0) / r - (b0 - 1.0) / (1.0 - r) - (g.ra - 1.0) / r + (g.rb - 1.0) / (1.0 - r);
+      const R a0 = k.rho_alpha_prior, b0 = k.rho_beta_prior;
+      const R dt_dr = (a0 - R(1.0)) / r - (b0 - R(1.0)) / (R(1.0) - r) - (g.ra - R(1.0)) / r + (g.rb - R(1.0)) / (R(1.0) - r);
       G_r += -gl * dt_dr;
-      const double psi_ab = digamma_d(g.ra + g.rb);
-      const double dt_da = -(log(r) + psi_ab - digamma_d(g.ra)), dt_db = -(log1p(-r) + psi_ab - digamma_d(g.rb));
-      ga[3] += -gl * dt_da + G_r * double(dgrad[2 * b]) * (1.0 - r);
-      ga[4] += -gl * dt_db - G_r * double(dgrad[2 * b + 1]) * r;
+      const R psi_ab = digamma_d(g.ra + g.rb);
+      const R dt_da = -(log(r) + psi_ab - digamma_d(g.ra)), dt_db = -(log1p(-r) + psi_ab - digamma_d(g.rb));
+      ga[3] += -gl * dt_da + G_r * R(dgrad[2 * b]) * (R(1.0) - r);
+      ga[4] += -gl * dt_db - G_r * R(dgrad[2 * b + 1]) * r;
     }
     // epsilon (+ the two median regularisers)
     G_e += -gl * (ep - s.eps_conc) / ee;
-    if (b == i_cell) G_e += -gl * (1.0 - ee) / 1e-4;
-    if (b == i_empty) G_e += -gl * (1.0 - ee) / 1e-4;
-    const double dt_dconc = -(log(ep) + log(ee) - digamma_d(s.eps_conc));
-    const double G_conc = -gl * dt_dconc + G_e * double(sgg[1 + b]) / ep;
-    const double G_epsenc = G_conc * ep * e.prob + G_dloc * e.ddloc_deps;
+    if (b == i_cell) G_e += -gl * (R(1.0) - ee) / R(1e-4);
+    if (b == i_empty) G_e += -gl * (R(1.0) - ee) / R(1e-4);
+    const R dt_dconc = -(log(ep) + log(ee) - digamma_d(s.eps_conc));
+    const R G_conc = -gl * dt_dconc + G_e * R(sgg[1 + b]) / ep;
+    const R G_epsenc = G_conc * ep * e.prob + G_dloc * e.ddloc_deps;
     d_eps_out[b] = float(G_epsenc * e.deps_dout);
     // p_y
-    const double plp = p_logit_prior_row(e.counts, k);
-    const double q1q0 = e.q1 * e.q0;
-    const double dt_y = q1q0 * ((logsigmoid_d(plp) - e.lq1) - (logsigmoid_d(-plp) - e.lq0));
-    const double dt_plr = -(e.p_y + 2.0 * s.n_v - double(k.p_logit_prior)) / 4.0;
-    const double dt_z = -double(zq[b]) * q1q0;
-    double G_py = -gl * (dt_y + dt_plr + dt_z);
-    if (d_w) G_py += (-double(d_w[3 * b]) + double(d_w[3 * b + 1]) + 0.01 * double(d_w[3 * b + 2])) * q1q0;
+    const R plp = p_logit_prior_row(e.counts, k);
+    const R q1q0 = e.q1 * e.q0;
+    const R dt_y = q1q0 * ((logsigmoid_d(plp) - e.lq1) - (logsigmoid_d(-plp) - e.lq0));
+    const R dt_plr = -(e.p_y + R(2.0) * s.n_v - R(k.p_logit_prior)) / R(4.0);
+    const R dt_z = -R(zq[b]) * q1q0;
+    R G_py = -gl * (dt_y + dt_plr + dt_z);
+    if (d_w) G_py += (-R(d_w[3 * b]) + R(d_w[3 * b + 1]) + R(0.01) * R(d_w[3 * b + 2])) * q1q0;
     d_p_out[b] = float(G_py * e.dpy_dpout);
   }
-  double g_pl = 0.0, g_ps = 0.0;
+  R g_pl = R(0.0), g_ps = R(0.0);
   if (threadIdx.x == 0) {  // phi (global)
-    const double pc0 = k.phi_conc_prior, pr0 = k.phi_rate_prior;
-    const double phi = fmax(double(g_gamma[0]) / g.phi_rate, kFltTiny);
-    const double dt_dphi = (pc0 - 1.0) / phi - pr0 - (g.phi_conc - 1.0) / phi + g.phi_rate;
-    const double G_phi = -gl * dt_dphi + (d_alpha ? double(d_alpha[0]) : 0.0) * (-1.0 / (phi * phi));
-    const double dt_dpc = -(log(g.phi_rate) + log(phi) - digamma_d(g.phi_conc));
-    const double dt_dpr = -(g.phi_conc / g.phi_rate - phi);
-    const double G_pc = -gl * dt_dpc + G_phi * double(sgg[0]) / g.phi_rate;
-    const double G_pr = -gl * dt_dpr - G_phi * phi / g.phi_rate;
-    const double pl = g.pl, ps = g.psc;
-    g_pl = G_pc * 2.0 * pl / (ps * ps) + G_pr / (ps * ps);
-    g_ps = G_pc * (-2.0 * pl * pl / (ps * ps * ps)) + G_pr * (-2.0 * pl / (ps * ps * ps));
+    const R pc0 = k.phi_conc_prior, pr0 = k.phi_rate_prior;
+    const R phi = fmax(R(g_gamma[0]) / g.phi_rate, kFltTiny);
+    const R dt_dphi = (pc0 - R(1.0)) / phi - pr0 - (g.phi_conc - R(1.0)) / phi + g.phi_rate;
+    const R G_phi = -gl * dt_dphi + (d_alpha ? R(d_alpha[0]) : R(0.0)) * (-R(1.0) / (phi * phi));
+    const R dt_dpc = -(log(g.phi_rate) + log(phi) - digamma_d(g.phi_conc));
+    const R dt_dpr = -(g.phi_conc / g.phi_rate - phi);
+    const R G_pc = -gl * dt_dpc + G_phi * R(sgg[0]) / g.phi_rate;
+    const R G_pr = -gl * dt_dpr - G_phi * phi / g.phi_rate;
+    const R pl = g.pl, ps = g.psc;
+    g_pl = G_pc * R(2.0) * pl / (ps * ps) + G_pr / (ps * ps);
+    g_ps = G_pc * (-R(2.0) * pl * pl / (ps * ps * ps)) + G_pr * (-R(2.0) * pl / (ps * ps * ps));
   }
   ga[5] = g_pl, ga[6] = g_ps;
   block_sum_d<7>(ga, red);
@@ -463,9 +468,9 @@ __global__ void __launch_bounds__(256) latent_backward_kernel(
     if (sg.d_cell_scale) sg.d_cell_scale[0] = float(ga[0] * g.dcs);
     if (sg.d_empty_loc) sg.d_empty_loc[0] = float(ga[1] * g.del);
     if (sg.d_empty_scale) sg.d_empty_scale[0] = float(ga[2] * g.des);
-    const double span = double(k.rho_param_max) - double(k.rho_param_min);
-    if (sg.rho_alpha) sg.rho_alpha[0] = g.has_rho ? float(ga[3] * span * g.sra * (1.0 - g.sra)) : 0.f;
-    if (sg.rho_beta) sg.rho_beta[0] = g.has_rho ? float(ga[4] * span * g.srb * (1.0 - g.srb)) : 0.f;
+    const R span = R(k.rho_param_max) - R(k.rho_param_min);
+    if (sg.rho_alpha) sg.rho_alpha[0] = g.has_rho ? float(ga[3] * span * g.sra * (R(1.0) - g.sra)) : 0.f;
+    if (sg.rho_beta) sg.rho_beta[0] = g.has_rho ? float(ga[4] * span * g.srb * (R(1.0) - g.srb)) : 0.f;
     if (sg.phi_loc) sg.phi_loc[0] = float(ga[5] * g.pl);
     if (sg.phi_scale) sg.phi_scale[0] = float(ga[6] * g.psc);
   }

@@ -20,3 +20,12 @@ extern "C" void host_noise_window_pmf(int n_entries, const float* x, const float
     for (int j = 0; j < 32; ++j) prob[i * 32 + j] = p[j];
   }
 }
+
+// the x == 0 specialisation used by the dense pass of the fused observation kernel
+extern "C" void host_nbpc_zero(int n, const float* mu, const float* alpha, const float* lam, float* L, float* dmu,
+                               float* dlam, float* dalpha) {
+  for (int i = 0; i < n; ++i) {
+    cb::NbpcOut o = cb::nbpc_zero(mu[i], 1.0f / alpha[i], lam[i]);
+    L[i] = o.L, dmu[i] = o.dmu, dlam[i] = o.dlam, dalpha[i] = o.dalpha;
+  }
+}
