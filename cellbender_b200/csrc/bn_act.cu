@@ -8,10 +8,10 @@
 // torch runs each of these as 4-5 launches per direction (statistics, update, transform, activation; a 0.55 ms
 // batch_norm_backward_reduce over [255, 33 538]); here it is one launch each way.
 //
-// Layout: x, y, dy, dx are row-major [n_rows, ld].  A CTA owns 32 adjacent columns; its 1024 threads are 32 row
-// groups x 32 columns, so every global access is a coalesced 128-byte row segment, each thread keeps 8 independent
-// loads in flight (the kernels are latency-bound: 255 rows), and the column reductions finish in shared memory in a
-// fixed order (deterministic).
+// Layout: x, y, dy, dx are row-major [n_rows, ld].  A CTA owns 32 adjacent columns; its 256 threads are 8 row groups
+// x 32 columns, so every global access is a coalesced 128-byte row segment, each thread keeps its 32 rows in registers
+// (32 independent loads in flight: the kernels are latency-bound at 255 rows), and the column reductions finish in
+// shared memory in a fixed order (deterministic).
 //   training: mean / biased variance over the rows (two-pass), running stats updated with `momentum` (unbiased
 //             variance), *num_batches_tracked += 1;  y = act(bn(x)) * keep[row]
 //   eval:     running statistics, no dropout; rows are additionally split across blockIdx.y
@@ -23,8 +23,8 @@
 
 namespace cb {
 
-constexpr int kBnCols = 32, kBnGroups = 32, kBnUnroll = 8;
-constexpr int kBnChunk = kBnGroups * kBnUnroll;  // rows covered by one unrolled sweep of a CTA
+constexpr int kBnCols = 32, kBnGroups = 8, kBnUnroll = 32;
+constexpr int kBnChunk = kBnGroups * kBnUnroll;  // rows a CTA holds in registers at once (>= the 255-row minibatch)
 
 __device__ __forceinline__ float act_fwd(float v, int act) {
   if (act == 1) return v > 20.f ? v : log1pf(expf(v));
@@ -37,7 +37,7 @@ __device__ __forceinline__ float act_grad(float v, int act) {
   return 1.f;
 }
 
-// sum of one value per thread over the 32 row groups; result valid in every thread of the column
+// sum of one value per thread over the row groups; result valid in every thread of the column
 __device__ __forceinline__ float group_sum(float v, float (*s)[kBnCols + 1]) {
   const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
   __syncthreads();
@@ -49,6 +49,9 @@ __device__ __forceinline__ float group_sum(float v, float (*s)[kBnCols + 1]) {
   return t;
 }
 
+// Thread (g, c) owns rows g, g + 8, g + 16, ... of column c.  When the minibatch fits one chunk (B <= 256: always on
+// the training path) its rows are loaded ONCE into registers -- 32 independent loads in flight -- and statistics,
+// normalisation and activation all run from there; larger B re-reads the (L2-resident) input per pass.
 __global__ void __launch_bounds__(kBnCols* kBnGroups) bn_act_forward_kernel(
     const float* __restrict__ x, long long ldx, int B, int N, const float* __restrict__ gamma, const float* __restrict__ beta,
     float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
@@ -61,30 +64,37 @@ __global__ void __launch_bounds__(kBnCols* kBnGroups) bn_act_forward_kernel(
   // eval: this CTA normalises rows [row0, row1); training: all rows (gridDim.y == 1)
   const int rows_per_y = (B + gridDim.y - 1) / gridDim.y;
   const int row0 = blockIdx.y * rows_per_y, row1 = min(B, row0 + rows_per_y);
+  const bool single = (row1 - row0) <= kBnChunk;
+  float v[kBnUnroll];
+  if (single) {
+#pragma unroll
+    for (int i = 0; i < kBnUnroll; ++i) {
+      const int r = row0 + g + i * kBnGroups;
+      v[i] = (ok && r < row1) ? x[(long long)r * ldx + col] : 0.f;
+    }
+  }
   float mean = 0.f, rstd = 1.f;
   if (training) {
     float sum = 0.f;
-    for (int r0 = g; r0 < B; r0 += kBnChunk) {
-      float v[kBnUnroll];
+    if (single) {
 #pragma unroll
-      for (int i = 0; i < kBnUnroll; ++i) {
-        const int r = r0 + i * kBnGroups;
-        v[i] = (ok && r < B) ? x[(long long)r * ldx + col] : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < kBnUnroll; ++i) sum += v[i];
+      for (int i = 0; i < kBnUnroll; ++i) sum += v[i];  // rows beyond B hold 0
+    } else if (ok) {
+      for (int r = g; r < B; r += kBnGroups) sum += x[(long long)r * ldx + col];
     }
     mean = group_sum(sum, s) / float(B);
     float ssq = 0.f;
-    for (int r0 = g; r0 < B; r0 += kBnChunk) {
-      float v[kBnUnroll];
+    if (single) {
 #pragma unroll
       for (int i = 0; i < kBnUnroll; ++i) {
-        const int r = r0 + i * kBnGroups;
-        v[i] = (ok && r < B) ? x[(long long)r * ldx + col] - mean : 0.f;
+        const float d = (g + i * kBnGroups < B) ? v[i] - mean : 0.f;
+        ssq += d * d;
       }
-#pragma unroll
-      for (int i = 0; i < kBnUnroll; ++i) ssq += v[i] * v[i];
+    } else if (ok) {
+      for (int r = g; r < B; r += kBnGroups) {
+        const float d = x[(long long)r * ldx + col] - mean;
+        ssq += d * d;
+      }
     }
     ssq = group_sum(ssq, s);
     const float var = ssq / float(B);
@@ -102,18 +112,15 @@ __global__ void __launch_bounds__(kBnCols* kBnGroups) bn_act_forward_kernel(
   if (g == 0 && blockIdx.y == 0) save_mean[col] = mean, save_rstd[col] = rstd;
   const float a = rstd * gamma[col], b0 = beta[col] - mean * a;
   const bool drop = training && keep != nullptr;
-  for (int r0 = row0 + g; r0 < row1; r0 += kBnChunk) {
-    float v[kBnUnroll];
+  if (single) {
 #pragma unroll
     for (int i = 0; i < kBnUnroll; ++i) {
-      const int r = r0 + i * kBnGroups;
-      v[i] = (r < row1) ? x[(long long)r * ldx + col] : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < kBnUnroll; ++i) {
-      const int r = r0 + i * kBnGroups;
+      const int r = row0 + g + i * kBnGroups;
       if (r < row1) y[(long long)r * ldy + col] = act_fwd(fmaf(v[i], a, b0), act) * (drop ? keep[r] : 1.f);
     }
+  } else {
+    for (int r = row0 + g; r < row1; r += kBnGroups)
+      y[(long long)r * ldy + col] = act_fwd(fmaf(x[(long long)r * ldx + col], a, b0), act) * (drop ? keep[r] : 1.f);
   }
 }
 
@@ -129,20 +136,29 @@ __global__ void __launch_bounds__(kBnCols* kBnGroups) bn_act_backward_kernel(
   float mean = 0.f, rstd = 0.f, gm = 0.f, bt = 0.f;
   if (ok) mean = save_mean[col], rstd = save_rstd[col], gm = gamma[col], bt = beta[col];
   const bool drop = training && keep != nullptr;
+  const bool single = B <= kBnChunk;
+  // xh = xhat, dp = d_pre = dy * keep * act'(bn)
+  float xh[kBnUnroll], dp[kBnUnroll];
   float sb = 0.f, sg = 0.f;
-  for (int r0 = g; r0 < B; r0 += kBnChunk) {
-    float xv[kBnUnroll], dv[kBnUnroll];
+  if (single) {
 #pragma unroll
     for (int i = 0; i < kBnUnroll; ++i) {
-      const int r = r0 + i * kBnGroups;
+      const int r = g + i * kBnGroups;
       const bool in = ok && r < B;
-      xv[i] = in ? x[(long long)r * ldx + col] : 0.f;
-      dv[i] = in ? dy[(long long)r * lddy + col] * (drop ? keep[r] : 1.f) : 0.f;
+      xh[i] = in ? x[(long long)r * ldx + col] : mean;
+      dp[i] = in ? dy[(long long)r * lddy + col] * (drop ? keep[r] : 1.f) : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < kBnUnroll; ++i) {
-      const float xhat = (xv[i] - mean) * rstd;
-      const float dpre = dv[i] * act_grad(fmaf(xhat, gm, bt), act);
+      xh[i] = (xh[i] - mean) * rstd;
+      dp[i] *= act_grad(fmaf(xh[i], gm, bt), act);
+      sb += dp[i];
+      sg += dp[i] * xh[i];
+    }
+  } else if (ok) {
+    for (int r = g; r < B; r += kBnGroups) {
+      const float xhat = (x[(long long)r * ldx + col] - mean) * rstd;
+      const float dpre = dy[(long long)r * lddy + col] * (drop ? keep[r] : 1.f) * act_grad(fmaf(xhat, gm, bt), act);
       sb += dpre;
       sg += dpre * xhat;
     }
@@ -153,25 +169,23 @@ __global__ void __launch_bounds__(kBnCols* kBnGroups) bn_act_backward_kernel(
   if (dx == nullptr) return;  // the input is data (batchnorm0): only the affine parameters have gradients
   const float invB = 1.f / float(B);
   float sdx = 0.f;
-  for (int r0 = g; r0 < B; r0 += kBnChunk) {
-    float xv[kBnUnroll], dv[kBnUnroll];
+  if (single) {
 #pragma unroll
     for (int i = 0; i < kBnUnroll; ++i) {
-      const int r = r0 + i * kBnGroups;
-      const bool in = ok && r < B;
-      xv[i] = in ? x[(long long)r * ldx + col] : 0.f;
-      dv[i] = in ? dy[(long long)r * lddy + col] * (drop ? keep[r] : 1.f) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < kBnUnroll; ++i) {
-      const int r = r0 + i * kBnGroups;
+      const int r = g + i * kBnGroups;
       if (ok && r < B) {
-        const float xhat = (xv[i] - mean) * rstd;
-        const float dpre = dv[i] * act_grad(fmaf(xhat, gm, bt), act);
-        const float v = training ? gm * rstd * (dpre - sb * invB - xhat * sg * invB) : gm * rstd * dpre;
+        const float v = training ? gm * rstd * (dp[i] - sb * invB - xh[i] * sg * invB) : gm * rstd * dp[i];
         dx[(long long)r * lddx + col] = v;
         sdx += v;
       }
+    }
+  } else if (ok) {
+    for (int r = g; r < B; r += kBnGroups) {
+      const float xhat = (x[(long long)r * ldx + col] - mean) * rstd;
+      const float dpre = dy[(long long)r * lddy + col] * (drop ? keep[r] : 1.f) * act_grad(fmaf(xhat, gm, bt), act);
+      const float v = training ? gm * rstd * (dpre - sb * invB - xhat * sg * invB) : gm * rstd * dpre;
+      dx[(long long)r * lddx + col] = v;
+      sdx += v;
     }
   }
   if (dbias) {

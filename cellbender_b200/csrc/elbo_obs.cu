@@ -213,10 +213,10 @@ __global__ void __launch_bounds__(kObsThreads, 2) elbo_obs_kernel(
     drow[g] = scale * (drow[g] - expf(lrow[g] - lse) * s_mu_chi);
 }
 
-// Deterministic column sum of a [R, ld] matrix: out[g] = sum_r in[r, g].  A CTA owns 32 adjacent columns; its 1024
-// threads are 32 row groups x 32 columns (coalesced 128-byte row segments, 8 independent loads in flight per thread);
+// Deterministic column sum of a [R, ld] matrix: out[g] = sum_r in[r, g].  A CTA owns 32 adjacent columns; its 256
+// threads are 8 row groups x 32 columns (coalesced 128-byte row segments, 32 independent loads in flight per thread);
 // the row groups are combined in shared memory in a fixed order.
-constexpr int kColsumCols = 32, kColsumGroups = 32, kColsumUnroll = 8;
+constexpr int kColsumCols = 32, kColsumGroups = 8, kColsumUnroll = 32;
 __global__ void __launch_bounds__(kColsumCols* kColsumGroups) colsum_rows_kernel(const float* __restrict__ in, int R, int G,
                                                                                 long long ld, float* __restrict__ out) {
   __shared__ float s[kColsumGroups][kColsumCols + 1];

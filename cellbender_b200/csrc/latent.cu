@@ -225,8 +225,9 @@ __global__ void latent_beta_kernel(float* __restrict__ gdraw, int B, float* __re
 
 enum Term { T_PHI = 0, T_Z, T_DCELL, T_RHO, T_EPS, T_DEMPTY, T_Y, T_PLR, T_SOFT_EMPTY, T_SOFT_CELL, T_EPS_MEAN, T_EPS_EMPTY_MEAN, T_N };
 
-// dynamic smem layout (both kernels): float zprior[B], zq[B], eps[B], q1[B]; uchar mask[B]
-__global__ void __launch_bounds__(256) latent_forward_kernel(
+// dynamic smem layout (both kernels): float zpart_p[B * nchunk], zpart_q[B * nchunk], eps[B], q1[B]; uchar mask[B]
+constexpr int kLatentThreads = 512, kZUnroll = 8;
+__global__ void __launch_bounds__(kLatentThreads) latent_forward_kernel(
     const float* __restrict__ feats, const float* __restrict__ p_out, const float* __restrict__ eps_out,
     const float* __restrict__ z_loc, const float* __restrict__ z_ls, long long ldz, int B, int Z,
     const float* __restrict__ n_z, const float* __restrict__ n_row, const float* __restrict__ g_gamma,
@@ -234,9 +235,10 @@ __global__ void __launch_bounds__(256) latent_forward_kernel(
     float* __restrict__ alpha_out, float* __restrict__ w_out, float* __restrict__ terms, float* __restrict__ loss_local,
     float* __restrict__ enc_out, int* __restrict__ med_idx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* zprior = reinterpret_cast<float*>(smem_raw);
-  float* zq = zprior + B;
-  float* eps_s = zq + B;
+  const int nchunk = (Z + 31) >> 5;
+  float* zpart_p = reinterpret_cast<float*>(smem_raw);  // [B * nchunk] partial sums of the prior log-density
+  float* zpart_q = zpart_p + B * nchunk;                // [B * nchunk] partial sums of the guide log-density
+  float* eps_s = zpart_q + B * nchunk;
   unsigned char* mask = reinterpret_cast<unsigned char*>(eps_s + 2 * B);
   __shared__ double red[T_N * 32];
   __shared__ int s_res[3], s_cnt[2];
@@ -244,18 +246,30 @@ __global__ void __launch_bounds__(256) latent_forward_kernel(
   const Globals g = load_globals(sp, k);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
-  // ---- z = loc + exp(log_scale) * n; per-row sums of the prior and guide log-densities (model.py:262-264, 553-555)
-  for (int r = wid; r < B; r += nw) {
-    double sp_ = 0.0, sq_ = 0.0;
-    for (int j = lane; j < Z; j += 32) {
-      const R n = n_z[(long long)r * Z + j], ls = z_ls[r * ldz + j];
-      const R z = R(z_loc[r * ldz + j]) + exp(ls) * n;
-      z_out[(long long)r * Z + j] = float(z);
-      sp_ += -R(0.5) * z * z - kHalfLog2Pi;
-      sq_ += -R(0.5) * n * n - ls - kHalfLog2Pi;
+  // ---- z = loc + exp(log_scale) * n; sums of the prior and guide log-densities (model.py:262-264, 553-555).
+  // Work unit = (droplet, 32-wide slice of z); every warp keeps kZUnroll units' loads in flight (latency-bound).
+  const int n_units = B * nchunk;
+  for (int u0 = wid * kZUnroll; u0 < n_units; u0 += nw * kZUnroll) {
+    float nn[kZUnroll], ll[kZUnroll], mm[kZUnroll];
+#pragma unroll
+    for (int i = 0; i < kZUnroll; ++i) {
+      const int u = u0 + i, r = u / nchunk, j = (u - r * nchunk) * 32 + lane;
+      const bool in = u < n_units && j < Z;
+      nn[i] = in ? n_z[(long long)r * Z + j] : 0.f;
+      ll[i] = in ? z_ls[r * ldz + j] : 0.f;
+      mm[i] = in ? z_loc[r * ldz + j] : 0.f;
     }
-    sp_ = warp_sum(sp_), sq_ = warp_sum(sq_);
-    if (lane == 0) zprior[r] = float(sp_), zq[r] = float(sq_);
+#pragma unroll
+    for (int i = 0; i < kZUnroll; ++i) {
+      const int u = u0 + i, r = u / nchunk, j = (u - r * nchunk) * 32 + lane;
+      const bool in = u < n_units && j < Z;
+      const R z = R(mm[i]) + exp(R(ll[i])) * R(nn[i]);
+      if (in) z_out[(long long)r * Z + j] = float(z);
+      float sp_ = in ? float(-R(0.5) * z * z - kHalfLog2Pi) : 0.f;
+      float sq_ = in ? float(-R(0.5) * R(nn[i]) * R(nn[i]) - R(ll[i]) - kHalfLog2Pi) : 0.f;
+      sp_ = warp_sum(sp_), sq_ = warp_sum(sq_);
+      if (lane == 0 && u < n_units) zpart_p[u] = sp_, zpart_q[u] = sq_;
+    }
   }
   __syncthreads();
 
@@ -283,7 +297,11 @@ __global__ void __launch_bounds__(256) latent_forward_kernel(
     cf[6] = float(r * de);
     w_out[3 * b + 0] = float(-e.q1), w_out[3 * b + 1] = float(-e.q0), w_out[3 * b + 2] = float(-R(0.01) * e.q0);
 
-    acc[T_Z] += R(zprior[b]) - e.q1 * R(zq[b]);
+    {
+      R zp = R(0.0), zq = R(0.0);
+      for (int c2 = 0; c2 < nchunk; ++c2) zp += R(zpart_p[b * nchunk + c2]), zq += R(zpart_q[b * nchunk + c2]);
+      acc[T_Z] += zp - e.q1 * zq;
+    }
     {  // d_cell: LogNormal prior vs guide (the -log d_cell of both LogNormal densities cancels)
       const R dz = (s.lx - R(k.d_cell_loc_prior)) / R(k.d_cell_scale_prior);
       acc[T_DCELL] += (-R(0.5) * dz * dz - log(R(k.d_cell_scale_prior))) - (-R(0.5) * s.n_dc * s.n_dc - log(g.dcs));
@@ -350,7 +368,7 @@ __global__ void __launch_bounds__(256) latent_forward_kernel(
   }
 }
 
-__global__ void __launch_bounds__(256) latent_backward_kernel(
+__global__ void __launch_bounds__(kLatentThreads) latent_backward_kernel(
     const float* __restrict__ feats, const float* __restrict__ p_out, const float* __restrict__ eps_out,
     const float* __restrict__ z_loc, const float* __restrict__ z_ls, long long ldz, int B, int Z,
     const float* __restrict__ n_z, const float* __restrict__ n_row, const float* __restrict__ g_gamma,
@@ -360,8 +378,9 @@ __global__ void __launch_bounds__(256) latent_backward_kernel(
     const float* __restrict__ g_local, float* __restrict__ d_p_out, float* __restrict__ d_eps_out,
     float* __restrict__ d_z_loc, float* __restrict__ d_z_ls, long long lddz, ScalarGrads sg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* zq = reinterpret_cast<float*>(smem_raw) + B;
-  float* q1_s = zq + 2 * B;
+  const int nchunk = (Z + 31) >> 5;
+  float* zpart_q = reinterpret_cast<float*>(smem_raw) + B * nchunk;  // same layout as the forward kernel
+  float* q1_s = zpart_q + B * nchunk + B;
   __shared__ double red[7 * 32];
 
   const Globals g = load_globals(sp, k);
@@ -373,20 +392,34 @@ __global__ void __launch_bounds__(256) latent_backward_kernel(
     q1_s[b] = float(e.q1);
   }
   __syncthreads();
-  // ---- z: d loss / d loc, d loss / d log_scale; per-row guide log-density for the d q1 path
-  for (int r = wid; r < B; r += nw) {
-    double sq_ = 0.0;
-    const R q1 = q1_s[r];
-    for (int j = lane; j < Z; j += 32) {
-      const R n = n_z[(long long)r * Z + j], ls = z_ls[r * ldz + j], s = exp(ls);
-      const R z = R(z_loc[r * ldz + j]) + s * n;
-      const R gz = gl * z + (d_z ? R(d_z[(long long)r * Z + j]) : R(0.0));  // -d/dz of the N(0,1) prior term + obs path
-      d_z_loc[r * lddz + j] = float(gz);
-      d_z_ls[r * lddz + j] = float(gz * n * s - gl * q1);
-      sq_ += -R(0.5) * n * n - ls - kHalfLog2Pi;
+  // ---- z: d loss / d loc, d loss / d log_scale; guide log-density sums for the d q1 path (units as in the forward)
+  const int n_units = B * nchunk;
+  for (int u0 = wid * kZUnroll; u0 < n_units; u0 += nw * kZUnroll) {
+    float nn[kZUnroll], ll[kZUnroll], mm[kZUnroll], dd[kZUnroll];
+#pragma unroll
+    for (int i = 0; i < kZUnroll; ++i) {
+      const int u = u0 + i, r = u / nchunk, j = (u - r * nchunk) * 32 + lane;
+      const bool in = u < n_units && j < Z;
+      nn[i] = in ? n_z[(long long)r * Z + j] : 0.f;
+      ll[i] = in ? z_ls[r * ldz + j] : 0.f;
+      mm[i] = in ? z_loc[r * ldz + j] : 0.f;
+      dd[i] = (in && d_z) ? d_z[(long long)r * Z + j] : 0.f;
     }
-    sq_ = warp_sum(sq_);
-    if (lane == 0) zq[r] = float(sq_);
+#pragma unroll
+    for (int i = 0; i < kZUnroll; ++i) {
+      const int u = u0 + i, r = u / nchunk, j = (u - r * nchunk) * 32 + lane;
+      const bool in = u < n_units && j < Z;
+      const R n = nn[i], ls = ll[i], sc = exp(ls);
+      const R z = R(mm[i]) + sc * n;
+      const R gz = gl * z + R(dd[i]);  // -d/dz of the N(0,1) prior term + observation path
+      if (in) {
+        d_z_loc[r * lddz + j] = float(gz);
+        d_z_ls[r * lddz + j] = float(gz * n * sc - gl * R(q1_s[r]));
+      }
+      float sq_ = in ? float(-R(0.5) * n * n - ls - kHalfLog2Pi) : 0.f;
+      sq_ = warp_sum(sq_);
+      if (lane == 0 && u < n_units) zpart_q[u] = sq_;
+    }
   }
   __syncthreads();
 
@@ -443,7 +476,9 @@ __global__ void __launch_bounds__(256) latent_backward_kernel(
     const R q1q0 = e.q1 * e.q0;
     const R dt_y = q1q0 * ((logsigmoid_d(plp) - e.lq1) - (logsigmoid_d(-plp) - e.lq0));
     const R dt_plr = -(e.p_y + R(2.0) * s.n_v - R(k.p_logit_prior)) / R(4.0);
-    const R dt_z = -R(zq[b]) * q1q0;
+    R zq = R(0.0);
+    for (int c2 = 0; c2 < nchunk; ++c2) zq += R(zpart_q[b * nchunk + c2]);
+    const R dt_z = -zq * q1q0;
     R G_py = -gl * (dt_y + dt_plr + dt_z);
     if (d_w) G_py += (-R(d_w[3 * b]) + R(d_w[3 * b + 1]) + R(0.01) * R(d_w[3 * b + 2])) * q1q0;
     d_p_out[b] = float(G_py * e.dpy_dpout);
@@ -479,41 +514,98 @@ __global__ void __launch_bounds__(256) latent_backward_kernel(
 // ------------------------------------------------------------------------------------------------------------
 // transform_to(constraints.simplex) = torch's SoftmaxTransform: y = softmax(u) over the G genes (pyro.param
 // "chi_ambient", model.py:245-249, 486-490).  One CTA (G = 33.5k values: 134 KB, latency-bound); sums in fp64.
-constexpr int kSimplexThreads = 1024;
+constexpr int kSimplexThreads = 1024, kSimplexPer = 40;  // register-cached up to 40 960 genes; longer inputs re-read
 
 __global__ void __launch_bounds__(kSimplexThreads) simplex_forward_kernel(const float* __restrict__ u, int n,
                                                                           float* __restrict__ y, float* __restrict__ y_unit) {
   __shared__ float redf[32];
   __shared__ double red[2 * 32];
   const int t = threadIdx.x;
+  const bool cached = n <= kSimplexThreads * kSimplexPer;
+  float v[kSimplexPer];
   float mx = -INFINITY;
-  for (int i = t; i < n; i += kSimplexThreads) mx = fmaxf(mx, u[i]);
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < kSimplexPer; ++i) {
+      const int idx = t + i * kSimplexThreads;
+      v[i] = idx < n ? u[idx] : -INFINITY;
+    }
+#pragma unroll
+    for (int i = 0; i < kSimplexPer; ++i) mx = fmaxf(mx, v[i]);
+  } else {
+    for (int i = t; i < n; i += kSimplexThreads) mx = fmaxf(mx, u[i]);
+  }
   mx = block_max(mx, redf);
   double acc[2] = {0.0, 0.0};  // sum e, sum e^2
-  for (int i = t; i < n; i += kSimplexThreads) {
-    const double e = exp(double(u[i]) - double(mx));
-    acc[0] += e;
-    acc[1] += e * e;
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < kSimplexPer; ++i) {
+      v[i] = expf(v[i] - mx);  // exp(-inf) = 0 for the padding
+      acc[0] += double(v[i]);
+      acc[1] += double(v[i]) * double(v[i]);
+    }
+  } else {
+    for (int i = t; i < n; i += kSimplexThreads) {
+      const double e = double(expf(u[i] - mx));
+      acc[0] += e;
+      acc[1] += e * e;
+    }
   }
   block_sum<double, 2>(acc, red);
-  const double inv = 1.0 / acc[0], inv_unit = 1.0 / sqrt(acc[1]);
-  for (int i = t; i < n; i += kSimplexThreads) {
-    const double e = exp(double(u[i]) - double(mx));
-    y[i] = float(e * inv);
-    if (y_unit) y_unit[i] = float(e * inv_unit);
+  const float inv = float(1.0 / acc[0]), inv_unit = float(1.0 / sqrt(acc[1]));
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < kSimplexPer; ++i) {
+      const int idx = t + i * kSimplexThreads;
+      if (idx < n) {
+        y[idx] = v[i] * inv;
+        if (y_unit) y_unit[idx] = v[i] * inv_unit;
+      }
+    }
+  } else {
+    for (int i = t; i < n; i += kSimplexThreads) {
+      const float e = expf(u[i] - mx);
+      y[i] = e * inv;
+      if (y_unit) y_unit[i] = e * inv_unit;
+    }
   }
 }
 
-// du_k = y_k (gy_k - sum_i gy_i y_i)
+// du_k = y_k (gy_k - sum_i gy_i y_i); two sweeps with 8 independent loads in flight per thread
 __global__ void __launch_bounds__(kSimplexThreads) simplex_backward_kernel(int n, const float* __restrict__ y,
                                                                            const float* __restrict__ gy,
                                                                            float* __restrict__ du) {
   __shared__ double red[32];
   const int t = threadIdx.x;
+  constexpr int U = 8;
   double acc[1] = {0.0};
-  for (int i = t; i < n; i += kSimplexThreads) acc[0] += double(gy[i]) * double(y[i]);
+  for (int i0 = t; i0 < n; i0 += kSimplexThreads * U) {
+    float yv[U], gv[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const int idx = i0 + i * kSimplexThreads;
+      yv[i] = idx < n ? y[idx] : 0.f;
+      gv[i] = idx < n ? gy[idx] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) acc[0] += double(gv[i]) * double(yv[i]);
+  }
   block_sum<double, 1>(acc, red);
-  for (int i = t; i < n; i += kSimplexThreads) du[i] = float(double(y[i]) * (double(gy[i]) - acc[0]));
+  const float dot = float(acc[0]);
+  for (int i0 = t; i0 < n; i0 += kSimplexThreads * U) {
+    float yv[U], gv[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const int idx = i0 + i * kSimplexThreads;
+      yv[i] = idx < n ? y[idx] : 0.f;
+      gv[i] = idx < n ? gy[idx] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const int idx = i0 + i * kSimplexThreads;
+      if (idx < n) du[idx] = yv[i] * (gv[i] - dot);
+    }
+  }
 }
 
 static LatentConsts load_consts(const float* h) {
@@ -523,7 +615,7 @@ static LatentConsts load_consts(const float* h) {
   return k;
 }
 
-static size_t latent_smem(int B) { return size_t(B) * (4 * sizeof(float) + 1) + 16; }
+static size_t latent_smem(int B, int Z) { return size_t(B) * ((2 * ((Z + 31) / 32) + 2) * sizeof(float) + 1) + 16; }
 
 }  // namespace cb
 
@@ -556,9 +648,9 @@ extern "C" int cb_latent_forward(const float* feats, const float* p_out, const f
                                  const float* u_phi_scale, const float* consts_h, float* z_out, float* coef, float* alpha,
                                  float* w, float* terms, float* loss_local, float* enc_out, int* med_idx,
                                  void* stream) {
-  CB_REQUIRE(n_rows > 0 && n_rows <= 8192, "cb_latent_forward: n_rows %d outside (0, 8192]", n_rows);
+  CB_REQUIRE(n_rows > 0 && n_rows <= 2048 && z_dim > 0 && z_dim <= 256, "cb_latent_forward: n_rows %d / z_dim %d out of range", n_rows, z_dim);
   cb::ScalarParams sp{u_d_cell_scale, u_d_empty_loc, u_d_empty_scale, u_rho_alpha, u_rho_beta, u_phi_loc, u_phi_scale};
-  cb::latent_forward_kernel<<<1, 256, cb::latent_smem(n_rows), (cudaStream_t)stream>>>(
+  cb::latent_forward_kernel<<<1, cb::kLatentThreads, cb::latent_smem(n_rows, z_dim), (cudaStream_t)stream>>>(
       feats, p_out, eps_out, z_loc, z_log_scale, ldz, n_rows, z_dim, noise_z, noise_row, gamma_draws, xx, sp,
       cb::load_consts(consts_h), z_out, coef, alpha, w, terms, loss_local, enc_out, med_idx);
   return cb::check_launch("cb_latent_forward");
@@ -575,10 +667,10 @@ extern "C" int cb_latent_backward(const float* feats, const float* p_out, const 
                                   float* d_eps_out, float* d_z_loc, float* d_z_log_scale, long long lddz,
                                   float* g_d_cell_scale, float* g_d_empty_loc, float* g_d_empty_scale, float* g_rho_alpha,
                                   float* g_rho_beta, float* g_phi_loc, float* g_phi_scale, void* stream) {
-  CB_REQUIRE(n_rows > 0 && n_rows <= 8192, "cb_latent_backward: n_rows %d outside (0, 8192]", n_rows);
+  CB_REQUIRE(n_rows > 0 && n_rows <= 2048 && z_dim > 0 && z_dim <= 256, "cb_latent_backward: n_rows %d / z_dim %d out of range", n_rows, z_dim);
   cb::ScalarParams sp{u_d_cell_scale, u_d_empty_loc, u_d_empty_scale, u_rho_alpha, u_rho_beta, u_phi_loc, u_phi_scale};
   cb::ScalarGrads sg{g_d_cell_scale, g_d_empty_loc, g_d_empty_scale, g_rho_alpha, g_rho_beta, g_phi_loc, g_phi_scale};
-  cb::latent_backward_kernel<<<1, 256, cb::latent_smem(n_rows), (cudaStream_t)stream>>>(
+  cb::latent_backward_kernel<<<1, cb::kLatentThreads, cb::latent_smem(n_rows, z_dim), (cudaStream_t)stream>>>(
       feats, p_out, eps_out, z_loc, z_log_scale, ldz, n_rows, z_dim, noise_z, noise_row, gamma_draws, xx, gamma_grad,
       dirichlet_grad, med_idx, sp, cb::load_consts(consts_h), d_z, d_coef, d_alpha, d_w, g_local, d_p_out, d_eps_out, d_z_loc,
       d_z_log_scale, lddz, sg);
