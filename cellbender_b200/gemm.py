@@ -59,9 +59,14 @@ class _MultiLinearBig(torch.autograd.Function):
         B = x.shape[0]
         ys = []
         for feat, w, b in zip(feats, weights, biases):
-            y = ops.gemm_tf32(x, w[:, col_offset:col_offset + n_in], B, w.shape[0], n_in, bias=b)
-            if feat is not None:
-                y = torch.addmm(y, feat, w[:, :col_offset].t())
+            if feat is not None and col_offset % 4 == 0 and feat.is_contiguous() and feat.shape[1] == col_offset:
+                # Linear(cat(feat, x)): the few feature columns ride along as a second operand pair (one extra k-block)
+                y = ops.gemm_tf32(x, w[:, col_offset:col_offset + n_in], B, w.shape[0], n_in, bias=b,
+                                  a2=feat, b2=w[:, :col_offset], K2=col_offset)
+            else:
+                y = ops.gemm_tf32(x, w[:, col_offset:col_offset + n_in], B, w.shape[0], n_in, bias=b)
+                if feat is not None:
+                    y = torch.addmm(y, feat, w[:, :col_offset].t())
             ys.append(y)
         ctx.save_for_backward(x, *[t for t in feats if t is not None], *weights)
         ctx.meta = (len(weights), n_in, col_offset, [f is not None for f in feats], [b is not None for b in biases])
@@ -77,37 +82,60 @@ class _MultiLinearBig(torch.autograd.Function):
         weights = saved
         B = x.shape[0]
         need_dx = ctx.needs_input_grad[0]
-        dx = None
-        if need_dx:
-            dx = ops.alloc_rows(B, n_in, x.device, zero=False)[:, :n_in]
-        grads = []
-        first = True
+        dys = [d.contiguous() for d in dys]
+        dx = ops.alloc_rows(B, n_in, x.device, zero=False)[:, :n_in] if need_dx else None
+        # every output buffer is allocated here, on the calling stream, before any fork
+        targets = []
         for i in range(n):
-            dy = dys[i].contiguous()
-            w, feat = weights[i], feats[i]
-            H = w.shape[0]
-            dw = db = dfeat = None
-            if ctx.needs_input_grad[3 + 3 * i + 1]:
-                dw_buf, dw = _grad_target(w)
-                # dW[H, n_in] = dy^T[H, B] . x[B, n_in]: both operands stored with the reduction dim (B) as rows
-                ops.gemm_tf32(dy, x, H, n_in, B, a_mn=True, b_mn=True, out=dw_buf[:, off:off + n_in], split_k=1)
-                if off:
-                    dw_buf[:, :off] = dy.t() @ feat
-            if need_dx and n != 2:
-                # dx[B, n_in] (+)= dy[B, H] . W[H, n_in]
-                ops.gemm_tf32(dy, w[:, off:off + n_in], B, n_in, H, b_mn=True, out=dx, accumulate=not first, split_k=1)
-                first = False
-            if has_bias[i] and ctx.needs_input_grad[3 + 3 * i + 2]:
-                db_buf, db = _grad_target(ctx.biases[i])
-                ops.colsum_rows(dy, H, out=db_buf)
-            if feat is not None and ctx.needs_input_grad[3 + 3 * i]:
-                dfeat = dy @ w[:, :off]
-            grads += [dfeat, dw, db]
-        if need_dx and n == 2:
-            # dx = dy_0 . W_0 + dy_1 . W_1 in ONE launch: both products accumulate in the same TMEM tile
-            w0, w1 = weights
-            ops.gemm_tf32(dys[0].contiguous(), w0[:, off:off + n_in], B, n_in, w0.shape[0], b_mn=True, out=dx, split_k=1,
-                          a2=dys[1].contiguous(), b2=w1[:, off:off + n_in], K2=w1.shape[0])
+            w = weights[i]
+            dw_t = _grad_target(w) if ctx.needs_input_grad[3 + 3 * i + 1] else None
+            db_t = _grad_target(ctx.biases[i]) if (has_bias[i] and ctx.needs_input_grad[3 + 3 * i + 2]) else None
+            targets.append((dw_t, db_t))
+
+        def parameter_gradients():
+            for i in range(n):
+                dy, w, feat = dys[i], weights[i], feats[i]
+                H = w.shape[0]
+                dw_t, db_t = targets[i]
+                if dw_t is not None:
+                    # dW[H, n_in] = dy^T[H, B] . x[B, n_in]: both operands stored with the reduction dim (B) as rows
+                    ops.gemm_tf32(dy, x, H, n_in, B, a_mn=True, b_mn=True, out=dw_t[0][:, off:off + n_in], split_k=1)
+                    if off:
+                        dw_t[0][:, :off] = dy.t() @ feat
+                if db_t is not None:
+                    ops.colsum_rows(dy, H, out=db_t[0])
+
+        # the weight-gradient products and the input-gradient product are independent: fork the former onto a side
+        # stream (parallel branches of the captured step graph), join before returning
+        fork = need_dx and any(t[0] is not None or t[1] is not None for t in targets)
+        main = torch.cuda.current_stream()
+        if fork:
+            side = ops.side_stream(x.device, 0)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                parameter_gradients()
+        else:
+            parameter_gradients()
+        if need_dx:
+            if n == 2:
+                # dx = dy_0 . W_0 + dy_1 . W_1 in ONE launch: both products accumulate in the same TMEM tile
+                w0, w1 = weights
+                ops.gemm_tf32(dys[0], w0[:, off:off + n_in], B, n_in, w0.shape[0], b_mn=True, out=dx, split_k=1,
+                              a2=dys[1], b2=w1[:, off:off + n_in], K2=w1.shape[0])
+            else:
+                for i in range(n):  # dx[B, n_in] (+)= dy[B, H] . W[H, n_in]
+                    w = weights[i]
+                    ops.gemm_tf32(dys[i], w[:, off:off + n_in], B, n_in, w.shape[0], b_mn=True, out=dx, accumulate=i > 0,
+                                  split_k=1)
+        grads = []
+        for i in range(n):
+            dfeat = None
+            if feats[i] is not None and ctx.needs_input_grad[3 + 3 * i]:
+                dfeat = dys[i] @ weights[i][:, :off]
+            grads += [dfeat, targets[i][0][1] if targets[i][0] is not None else None,
+                      targets[i][1][1] if targets[i][1] is not None else None]
+        if fork:
+            main.wait_stream(side)
         return (dx, None, None, *grads)
 
 

@@ -12,7 +12,7 @@ from typing import Dict, Optional
 
 import torch
 
-from . import consts
+from . import consts, ops
 from ._cabi import current_stream, lib, ptr
 
 TERM_NAMES = ("phi", "z", "d_cell", "rho", "epsilon", "d_empty", "y", "p_logit_reg", "obs_probably_empty_y",
@@ -97,9 +97,22 @@ class _LatentStage(torch.autograd.Function):
             rho = noise["rho"].to(**f32) if "rho" in noise else torch.full((B,), 0.5, **f32)
             xx = torch.stack((rho, 1 - rho), dim=1).contiguous()
         sgg = dgrad = None
+        ctx.grads_ready = None
         if need_grad:
-            sgg = torch._standard_gamma_grad(conc_gamma[:1 + B], gdraw[:1 + B])
-            dgrad = torch._dirichlet_grad(xx, conc_beta, total_beta)
+            # The implicit reparameterisation gradients are needed only by the backward kernel.  torch's elementwise
+            # kernels for them are slow, serial chains (~70 us for 2 x 255 values), so they run on a side stream and
+            # overlap the decoder GEMM and the likelihood kernel; backward waits on `grads_ready`.  Their inputs stay
+            # alive (saved for backward) and their outputs are first read after that wait, so no allocation crosses
+            # streams unsynchronised.
+            main = torch.cuda.current_stream()
+            side = ops.side_stream(dev, 1)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                sgg = torch._standard_gamma_grad(conc_gamma[:1 + B], gdraw[:1 + B])
+                dgrad = torch._dirichlet_grad(xx, conc_beta, total_beta)
+                ctx.grads_ready = torch.cuda.Event()
+                ctx.grads_ready.record(side)
+            sgg.record_stream(main), dgrad.record_stream(main)
 
         z = torch.empty((B, Z), **f32)
         coef = torch.empty((B, 7), **f32)
@@ -123,6 +136,8 @@ class _LatentStage(torch.autograd.Function):
     def backward(ctx, d_z, d_coef, d_alpha, d_w, g_local, _terms, _enc):
         feats, p_out, eps_out, z_loc, z_ls, n_z, n_row, gdraw, xx, sgg, dgrad, med_idx = ctx.saved_tensors
         model = ctx.model
+        if ctx.grads_ready is not None:
+            torch.cuda.current_stream().wait_event(ctx.grads_ready)
         B, Z = z_loc.shape
         f32 = dict(dtype=torch.float32, device=feats.device)
         c = lambda t: None if t is None else t.contiguous()

@@ -155,6 +155,7 @@ class _ObsTerm(torch.autograd.Function):
         ctx.save_for_backward(h_dec, w_out, sums, w, out["dlogits"], out["dchi_ambient"])
         ctx.G = G
         ctx.alpha_shape = alpha.shape
+        ctx.bias_param = b_out  # the nn.Parameter object (it carries the optimizer's gradient view)
         ctx.mark_non_differentiable(L)
         return (w * L).sum(), L
 
@@ -165,13 +166,21 @@ class _ObsTerm(torch.autograd.Function):
         dl = dlogits[:, :G]
         if gemm.BACKEND == "tcgen05":
             B, H = h_dec.shape
-            d_h = ops.gemm_tf32(dlogits, w_out, B, H, G, b_mn=True) * g          # dlogits[B,G] . Wd[G,H], split-K
+            h_c = h_dec.contiguous()
             d_w_buf, d_w = gemm._grad_target(w_out)
-            ops.gemm_tf32(dlogits, h_dec.contiguous(), G, H, B, a_mn=True, b_mn=True, out=d_w_buf, split_k=1)  # dlogits^T . h
+            d_b_buf, d_b = gemm._grad_target(ctx.bias_param)
+            # decoder weight / bias gradients on a side stream, the hidden-activation gradient on this one
+            main, side = torch.cuda.current_stream(), ops.side_stream(dlogits.device, 0)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ops.gemm_tf32(dlogits, h_c, G, H, B, a_mn=True, b_mn=True, out=d_w_buf, split_k=1)  # dlogits^T . h
+                ops.colsum_rows(dlogits, G, out=d_b_buf)
+            d_h = ops.gemm_tf32(dlogits, w_out, B, H, G, b_mn=True) * g          # dlogits[B,G] . Wd[G,H], split-K
+            main.wait_stream(side)
         else:
             d_h = (dl @ w_out) * g
             d_w = dl.t() @ h_dec  # [G, H]
-        d_b = ops.colsum_rows(dlogits, G)
+            d_b = ops.colsum_rows(dlogits, G)
         w1, w0, wE = w[:, 0], w[:, 1], w[:, 2]
         d_coef = torch.stack((w1 * sums[:, 3], w1 * sums[:, 4], w1 * sums[:, 5], w0 * sums[:, 7], w0 * sums[:, 8],
                               wE * sums[:, 10], wE * sums[:, 11]), dim=1) * g

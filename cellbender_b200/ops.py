@@ -22,6 +22,21 @@ def _req_cuda(*ts):
             raise RuntimeError("cellbender_b200 ops require CUDA tensors (no CPU fallback)")
 
 
+_SIDE_STREAMS = {}
+
+
+def side_stream(device, idx: int = 0) -> "torch.cuda.Stream":
+    """A persistent auxiliary stream per (device, idx).  Independent kernels of one step (the weight-gradient and
+    input-gradient products of a layer; torch's slow reparameterisation-gradient kernels) are forked onto it and joined
+    again, which under CUDA-graph capture becomes parallel branches of the step graph.  Callers keep every tensor that
+    crosses streams alive until the join, so the caching allocator never recycles one early."""
+    d = torch.device(device)
+    key = (d.index if d.index is not None else torch.cuda.current_device(), idx)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key[0])
+    return _SIDE_STREAMS[key]
+
+
 def alloc_rows(n_rows: int, n_cols: int, device, zero: bool = True) -> torch.Tensor:
     """Row-major [n_rows, ld] fp32 with ld % 4 == 0; use ``[:, :n_cols]`` for the logical matrix."""
     ld = round_up(n_cols, 4)
