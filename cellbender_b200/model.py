@@ -156,11 +156,12 @@ class _ObsTerm(torch.autograd.Function):
         ctx.G = G
         ctx.alpha_shape = alpha.shape
         ctx.bias_param = b_out  # the nn.Parameter object (it carries the optimizer's gradient view)
-        ctx.mark_non_differentiable(L)
-        return (w * L).sum(), L
+        neg_obs, obs = ops.obs_loss(sums, w)  # sum_b w . L and its negative (the 'obs' ELBO term)
+        ctx.mark_non_differentiable(L, obs)
+        return neg_obs, L, obs
 
     @staticmethod
-    def backward(ctx, g, _gL):
+    def backward(ctx, g, _gL, _gobs):
         h_dec, w_out, sums, w, dlogits, dchi_amb = ctx.saved_tensors
         G = ctx.G
         dl = dlogits[:, :G]
@@ -181,11 +182,8 @@ class _ObsTerm(torch.autograd.Function):
             d_h = (dl @ w_out) * g
             d_w = dl.t() @ h_dec  # [G, H]
             d_b = ops.colsum_rows(dlogits, G)
-        w1, w0, wE = w[:, 0], w[:, 1], w[:, 2]
-        d_coef = torch.stack((w1 * sums[:, 3], w1 * sums[:, 4], w1 * sums[:, 5], w0 * sums[:, 7], w0 * sums[:, 8],
-                              wE * sums[:, 10], wE * sums[:, 11]), dim=1) * g
-        d_alpha = ((w1 * sums[:, 6] + w0 * sums[:, 9]).sum() * g).reshape(ctx.alpha_shape)
-        d_weights = (sums[:, :3] * g) if ctx.needs_input_grad[6] else None
+        d_coef, d_alpha, d_weights = ops.obs_small_grads(sums, w, g.contiguous(), want_dw=ctx.needs_input_grad[6])
+        d_alpha = d_alpha.reshape(ctx.alpha_shape)
         return d_h, d_w, d_b, dchi_amb * g, d_coef, d_alpha, d_weights, None
 
 
@@ -345,8 +343,8 @@ class RemoveBackgroundPyroModel(nn.Module):
         h_dec = self.decoder.hidden(z)
         lin = self.decoder.out_linear
         self._obs_ctx = (csr, row_ids, self._work_buffers(B))
-        neg_obs, L = _ObsTerm.apply(h_dec, lin.weight, lin.bias, chi_ambient, coef, alpha, w, self)
-        t["obs"] = -neg_obs
+        neg_obs, L, obs = _ObsTerm.apply(h_dec, lin.weight, lin.bias, chi_ambient, coef, alpha, w, self)
+        t["obs"] = obs
         self._last_L = L
         t["loss"] = loss_local + neg_obs
         t["_enc"] = {"p_y": enc_out[:, 0], "d_loc": enc_out[:, 1], "epsilon": enc_out[:, 2]}

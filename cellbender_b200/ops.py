@@ -333,3 +333,85 @@ def gemm_tf32(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn: bo
                int(a_mn), int(b_mn), ptr(out), out.stride(0), M, N, ptr(bias), int(accumulate), split_k, ptr(ws), ws_elems,
                current_stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# small per-droplet ops (csrc/small_ops.cu)
+# ------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def encoder_features(feats: torch.Tensor, z: torch.Tensor, d_empty_loc: Optional[torch.Tensor]):
+    """(p_feat, e_feat) [B, 4] of EncodeNonZLatents.forward (vae/encoder.py:250-287); ``d_empty_loc`` = constrained
+    pyro.param value (0-dim / 1-element tensor) or None when no ambient profile is given.  Inputs are data: no gradient."""
+    _req_cuda(feats, z, d_empty_loc)
+    B = feats.shape[0]
+    z = z.detach().reshape(B, -1).contiguous()
+    p_feat = torch.empty((B, 4), dtype=torch.float32, device=feats.device)
+    e_feat = torch.empty((B, 4), dtype=torch.float32, device=feats.device)
+    _cabi.lib().call("cb_encoder_features", ptr(feats.contiguous()), ptr(z), z.stride(0), B, z.shape[1],
+                     ptr(d_empty_loc.detach().float().contiguous()) if d_empty_loc is not None else None, ptr(p_feat), ptr(e_feat),
+                     current_stream())
+    return p_feat, e_feat
+
+
+class _Head(torch.autograd.Function):
+    """Linear(F + N -> 1)(cat(feat, x)).squeeze(-1) through cb_head_forward / _backward; weight and bias gradients go
+    straight into the optimizer's flat gradient buffer when the parameters carry a view of it."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, feat):
+        B, N = x.shape
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        F_ = 0 if feat is None else feat.shape[1]
+        out = torch.empty(B, dtype=torch.float32, device=x.device)
+        _cabi.lib().call("cb_head_forward", ptr(x), x.stride(0), ptr(feat), F_, B, N, ptr(weight), ptr(bias), ptr(out),
+                         current_stream())
+        ctx.save_for_backward(x, weight) if feat is None else ctx.save_for_backward(x, weight, feat)
+        ctx.params = (weight, bias)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        from .gemm import _grad_target
+
+        saved = ctx.saved_tensors
+        x, weight = saved[0], saved[1]
+        feat = saved[2] if len(saved) > 2 else None
+        w_param, b_param = ctx.params
+        B, N = x.shape
+        F_ = 0 if feat is None else feat.shape[1]
+        dx = torch.empty((B, N), dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
+        dw_buf, dw = _grad_target(w_param)
+        db_buf, db = (None, None)
+        if b_param is not None and ctx.needs_input_grad[2]:
+            db_buf, db = _grad_target(b_param)
+        _cabi.lib().call("cb_head_backward", ptr(x), x.stride(0), ptr(feat), F_, B, N, ptr(weight), ptr(d_out.contiguous()),
+                         ptr(dx), dx.stride(0) if dx is not None else 0, ptr(dw_buf), ptr(db_buf), current_stream())
+        return dx, dw, db, None
+
+
+def head(x: torch.Tensor, lin: torch.nn.Linear, feat: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``lin(cat(feat, x)).squeeze(-1)`` for a one-output nn.Linear whose first feat.shape[1] input columns are features."""
+    _req_cuda(x, feat)
+    assert lin.out_features == 1 and lin.weight.is_contiguous()
+    return _Head.apply(x, lin.weight, lin.bias, None if feat is None else feat.contiguous())
+
+
+def obs_loss(sums: torch.Tensor, w: torch.Tensor):
+    """(sum_b w . L, its negative) as two 0-dim tensors (cb_obs_loss)."""
+    B = sums.shape[0]
+    loss = torch.empty((), dtype=torch.float32, device=sums.device)
+    neg = torch.empty((), dtype=torch.float32, device=sums.device)
+    _cabi.lib().call("cb_obs_loss", ptr(sums), sums.stride(0), ptr(w), B, ptr(loss), ptr(neg), current_stream())
+    return loss, neg
+
+
+def obs_small_grads(sums: torch.Tensor, w: torch.Tensor, g: Optional[torch.Tensor], want_dw: bool = True):
+    """(d_coef [B, 7], d_alpha [1], d_w [B, 3] or None) of loss = g * sum_b w . L (cb_obs_small_grads)."""
+    B = sums.shape[0]
+    f32 = dict(dtype=torch.float32, device=sums.device)
+    d_coef, d_alpha = torch.empty((B, 7), **f32), torch.empty(1, **f32)
+    d_w = torch.empty((B, 3), **f32) if want_dw else None
+    _cabi.lib().call("cb_obs_small_grads", ptr(sums), sums.stride(0), ptr(w), ptr(g), B, ptr(d_coef), ptr(d_alpha), ptr(d_w),
+                     current_stream())
+    return d_coef, d_alpha, d_w

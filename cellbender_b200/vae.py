@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import consts
-from . import gemm
+from . import gemm, ops
 from .gemm import bn0_dropout, bn_act, linear_big, multi_linear_big
 
 
@@ -199,25 +199,17 @@ class EncodeNonZLatents(nn.Module):
         G = self.n_genes
         d_empty_loc = self._d_empty_loc(z.device) if chi_ambient is not None else None
         inp = _as_inputs(x, G, chi_ambient, d_empty_loc)
-        counts = inp.feats[:, 0:1]
-        log_sum = counts.log1p()
-        log_nnz = inp.feats[:, 1:2].log1p()
-        if chi_ambient is not None:
-            overlap = -0.5 * (torch.clamp(log_sum - d_empty_loc, min=0.0) / 0.1).pow(2)
-            eps_overlap = inp.feats[:, 2:3]
-        else:
-            overlap = torch.zeros_like(counts)
-            eps_overlap = torch.zeros_like(counts)
+        # hand-made features (encoder.py:250-287): log1p(counts), log1p(nnz), overlap with the empty-droplet size /
+        # ambient dot product, ||z||_2 -- one kernel instead of ~15 elementwise launches
+        p_feat, e_feat = ops.encoder_features(inp.feats, z, d_empty_loc)
+        log_sum = p_feat[:, 0:1]
 
         # BatchNorm over genes + Dropout1d(0.5), which on a 2-D input drops whole droplet rows (torch 2.11):
         # one fused kernel (csrc/bn0.cu) writing a 16-byte-row buffer the tensor-core GEMMs can read through TMA.
         B = inp.feats.shape[0]
         if self.training and row_keep_scale is None:
-            row_keep_scale = torch.bernoulli(torch.full((B,), 0.5, device=inp.feats.device)) * 2.0
+            row_keep_scale = torch.empty(B, device=inp.feats.device).bernoulli_(0.5).mul_(2.0)
         x_in = bn0_dropout(inp.x_lognorm, self.batchnorm0, row_keep_scale, self.training, G)
-        znorm = torch.linalg.vector_norm(z.detach().reshape(B, -1), ord=2, dim=-1, keepdim=True)
-        p_feat = torch.cat((log_sum, log_nnz, overlap, znorm), dim=-1)
-        e_feat = torch.cat((log_sum, log_nnz, eps_overlap, znorm), dim=-1)
 
         # Linear(cat(feat, x_in)) of both towers: the large gene block through the tensor-core GEMM (shared input),
         # the 4 feature columns as a rank-4 update
@@ -227,13 +219,13 @@ class EncodeNonZLatents(nn.Module):
         x_ = bn_act(h1, self.batchnorm1, "softplus", self.training, bias_of=self.layer1)
         h2 = linear_big(x_, self.layer2, n_in=x_.shape[1], col_offset=4, feat=p_feat, bias_grad_elsewhere=True)
         x_ = bn_act(h2, self.batchnorm2, "softplus", self.training, bias_of=self.layer2)
-        p_out = self.layer3(torch.cat((p_feat, x_), dim=-1)).squeeze(-1)
+        p_out = ops.head(x_, self.layer3, p_feat)
 
         eps_bn1, eps_lin2, eps_bn2, eps_lin3 = self.eps_network[1], self.eps_network[3], self.eps_network[4], self.eps_network[6]
         h = bn_act(he, eps_bn1, "softplus", self.training, bias_of=e)
         h = linear_big(h, eps_lin2, n_in=h.shape[1], bias_grad_elsewhere=True)
         h = bn_act(h, eps_bn2, "softplus", self.training, bias_of=eps_lin2)
-        eps_out = eps_lin3(h).squeeze(-1)
+        eps_out = ops.head(h, eps_lin3)
 
         if self.offset is None:  # data-dependent module state fixed by the first minibatch (encoder.py:300-309)
             ls = log_sum.squeeze(-1)

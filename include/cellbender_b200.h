@@ -96,6 +96,27 @@ int cb_bn_act_backward(const float* x, long long ldx, const float* dy, long long
                        int act, float* dx, long long lddx, float* dgamma, float* dbeta, float* dbias, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * A4  small per-droplet pieces of EncodeNonZLatents.forward (vae/encoder.py:250-293) and of the observation term.
+ * cb_encoder_features: feats[n_rows, 4] (cb_csr_gather_rows), z[n_rows, ldz] (EncodeZ loc) ->
+ *     p_feat[n_rows, 4] = log1p(sum), log1p(nnz), -0.5 (max(log1p(sum) - d_empty_loc, 0) / 0.1)^2, ||z||_2
+ *     e_feat[n_rows, 4] = log1p(sum), log1p(nnz), dot(x, ambient unit vector), ||z||_2
+ *     d_empty_loc[1]: CONSTRAINED pyro.param value (encoder.py:262); NULL = no ambient profile (features 2 are 0).
+ * cb_head_forward / _backward: out[r] = bias + <w, cat(feat[r, :n_feat], x[r, :n_cols])>, the Linear(.. -> 1) heads
+ *     layer3 (encoder.py:216) and eps_network[-1] (encoder.py:227); backward: dx[n_rows, lddx] (may be NULL),
+ *     dw[n_feat + n_cols], dbias[1] (may be NULL).
+ * cb_obs_loss: loss[1] = sum_b w[b, :] . sums[b, 0:3], neg_loss[1] = -loss (may be NULL)  (sums of cb_elbo_obs_fwd_bwd).
+ * cb_obs_small_grads: g_up[1] (NULL = 1) upstream gradient -> d_coef[n_rows, 7], d_alpha[1], d_w[n_rows, 3] (may be NULL). */
+int cb_encoder_features(const float* feats, const float* z, long long ldz, int n_rows, int z_dim, const float* d_empty_loc,
+                        float* p_feat, float* e_feat, void* stream);
+int cb_head_forward(const float* x, long long ldx, const float* feat, int n_feat, int n_rows, int n_cols, const float* w,
+                    const float* bias, float* out, void* stream);
+int cb_head_backward(const float* x, long long ldx, const float* feat, int n_feat, int n_rows, int n_cols, const float* w,
+                     const float* d_out, float* dx, long long lddx, float* dw, float* dbias, void* stream);
+int cb_obs_loss(const float* sums, int ld_sums, const float* w, int n_rows, float* loss, float* neg_loss, void* stream);
+int cb_obs_small_grads(const float* sums, int ld_sums, const float* w, const float* g_up, int n_rows, float* d_coef,
+                       float* d_alpha, float* d_w, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * A3-A5  the large contractions of EncodeZ / EncodeNonZLatents / Decoder (vae/encoder.py:97-125, 211-228, 279-298;
  * vae/decoder.py:41-47) and their backward, on tcgen05 tensor cores (TF32 multiply, fp32 accumulate in TMEM).
  *   C[M, N] (=, +=) A[M, K] * B[N, K]^T (+ bias[N])

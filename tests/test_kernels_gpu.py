@@ -548,3 +548,50 @@ def test_bn_act_matches_torch(ops, training, act, B, N):
     np.testing.assert_allclose(bn.running_mean.cpu().numpy(), bn64.running_mean.numpy(), **tol)
     np.testing.assert_allclose(bn.running_var.cpu().numpy(), bn64.running_var.numpy(), **tol)
     assert int(bn.num_batches_tracked) == int(bn64.num_batches_tracked)
+
+
+# ------------------------------------------------------------------------------- small per-droplet ops
+@pytest.mark.parametrize("B,N,F", [(255, 512, 4), (9, 40, 0), (300, 33, 4)])
+def test_head_matches_linear_on_concatenated_input(ops, B, N, F):
+    """cb_head_forward / _backward vs nn.Linear(F + N, 1)(cat(feat, x)) in fp64 (EncodeNonZLatents.layer3 and the last
+    eps_network layer, vae/encoder.py:216,227,291-293)."""
+    gen = torch.Generator().manual_seed(B + N)
+    lin64 = torch.nn.Linear(F + N, 1).double()
+    x64 = torch.randn(B, N, generator=gen, dtype=torch.float64, requires_grad=True)
+    feat64 = torch.randn(B, F, generator=gen, dtype=torch.float64) if F else None
+    inp = torch.cat((feat64, x64), dim=-1) if F else x64
+    out64 = lin64(inp).squeeze(-1)
+    go = torch.randn(B, generator=gen, dtype=torch.float64)
+    (out64 * go).sum().backward()
+
+    lin = torch.nn.Linear(F + N, 1).to(DEV)
+    lin.load_state_dict({k: v.float() for k, v in lin64.state_dict().items()})
+    x = x64.detach().float().to(DEV).requires_grad_(True)
+    feat = feat64.float().to(DEV) if F else None
+    out = ops.head(x, lin, feat)
+    assert out.shape == (B,)
+    (out * go.float().to(DEV)).sum().backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), out64.detach().numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), x64.grad.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(lin.weight.grad.cpu().numpy(), lin64.weight.grad.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(lin.bias.grad.cpu().numpy(), lin64.bias.grad.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_encoder_features_match_reference_formulas(ops):
+    """cb_encoder_features vs the feature algebra of EncodeNonZLatents.forward (vae/encoder.py:250-287)."""
+    gen = torch.Generator().manual_seed(1)
+    B, Z = 77, 64
+    feats = torch.stack((torch.randint(0, 50000, (B,), generator=gen).float(), torch.randint(0, 5000, (B,), generator=gen).float(),
+                         torch.rand(B, generator=gen) * 100, torch.randint(0, 900, (B,), generator=gen).float()), dim=1)
+    z = torch.randn(B, Z, generator=gen)
+    d_empty_loc = torch.tensor(4.3)
+    log_sum, log_nnz = feats[:, 0].double().log1p(), feats[:, 1].double().log1p()
+    overlap = -0.5 * (torch.clamp(log_sum - 4.3, min=0.0) / 0.1) ** 2
+    znorm = z.double().norm(dim=-1)
+    p_ref = torch.stack((log_sum, log_nnz, overlap, znorm), dim=1)
+    e_ref = torch.stack((log_sum, log_nnz, feats[:, 2].double(), znorm), dim=1)
+    p, e = ops.encoder_features(feats.to(DEV), z.to(DEV), d_empty_loc.to(DEV))
+    np.testing.assert_allclose(p.cpu().numpy(), p_ref.numpy(), rtol=2e-5, atol=1e-5)  # overlap squares a difference / 0.1
+    np.testing.assert_allclose(e.cpu().numpy(), e_ref.numpy(), rtol=2e-6, atol=1e-6)
+    p0, e0 = ops.encoder_features(feats.to(DEV), z.to(DEV), None)
+    assert float(p0[:, 2].abs().max()) == 0.0 and float(e0[:, 2].abs().max()) == 0.0
