@@ -23,6 +23,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram bytes of one clipped_adam_kernel launch at the PBMC8k shape from the committed ncu --set full capture
+# (profiles/r01_step_kernels_ncu_summary.txt: 1.111406 GB read + 781.773 MB written)
+ADAM_NCU_DRAM_BYTES = 1.111406e9 + 781.773312e6
 METRIC = "train_s_per_epoch"
 UNIT = "s/epoch"
 WORKLOAD = "pbmc8k"
@@ -88,7 +91,10 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------------------
 # reference-style CPU arm (oracle port of the reference step; the oracle is only ever the baseline / the checker)
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(ds, n_steps: int, warmup: int, z_dim=64, hidden=512):
+def cpu_reference_steps(ds, n_steps: int, warmup: int, z_dim=64, hidden=512, device="cpu"):
+    """Seconds per reference-style training step (oracle/train_step.py) on ``device``: the reference's host loader
+    (scipy slicing + densify; plus, on a GPU, the 34 MB H2D copy of every dense minibatch, dataprep.py:291-292), the
+    dense eager fp32 ELBO with the reference's own likelihood formula, autograd, per-tensor ClippedAdam."""
     import torch
 
     from oracle import dataprep as odp
@@ -98,14 +104,29 @@ def cpu_reference_steps(ds, n_steps: int, warmup: int, z_dim=64, hidden=512):
     np.random.seed(1234)
     cm, em = ds.get_count_matrix(), ds.get_count_matrix_empties()
     loader = odp.HostLoader(cm, em, batch_size=256)
-    params, buffers = ots.init_state(cm.shape[1], z_dim, hidden, ds.priors)
-    cfg = ots.make_cfg(ds.priors, ds.empty_UMI_threshold)
+    params, buffers = ots.init_state(cm.shape[1], z_dim, hidden, ds.priors, device=device)
+    cfg = ots.make_cfg(ds.priors, ds.empty_UMI_threshold, device=device)
     opt = ots.ClippedAdamPerTensor(params, 1e-4)
+    on_gpu = str(device).startswith("cuda")
+
+    def one():
+        while True:
+            try:
+                x = next(loader)
+                break
+            except StopIteration:  # end of an epoch: the loader reshuffles and starts over
+                continue
+        ots.reference_step(x.to(device), params, buffers, cfg, opt, z_dim)  # returns loss.item(): syncs
+
     for _ in range(warmup):
-        ots.reference_step(next(loader), params, buffers, cfg, opt, z_dim)
+        one()
+    if on_gpu:
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(n_steps):
-        ots.reference_step(next(loader), params, buffers, cfg, opt, z_dim)  # loader time included, as in train_epoch
+        one()  # loader time included, as in train_epoch
+    if on_gpu:
+        torch.cuda.synchronize()
     return (time.perf_counter() - t0) / n_steps
 
 
@@ -123,8 +144,8 @@ def run_reference(args):
 
     ds = synth.make_config_dataset(args.workload, device="cpu" if not _cuda() else None)
     spe = steps_per_epoch(ds)
-    k = max(1, min(args.steps, 4))  # bounded sample: each CPU step is seconds at this shape
-    w = max(1, min(args.warmup, 1))
+    k = max(1, min(args.steps, 30))  # bounded sample: each CPU step is ~0.5-1 s at this shape
+    w = max(1, min(args.warmup, 3))
     s_step = cpu_reference_steps(ds, k, w)
     value = s_step * spe
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": w,
@@ -291,13 +312,17 @@ def run_b200(args):
         post._latents = {"p": np.concatenate([np.ones(n_cells), np.zeros(ds.analyzed_barcode_inds.size - n_cells)]), "z": None,
                          "d": None, "epsilon": None, "phi_loc_scale": None}
         post.device_posterior(cell_subset=np.arange(128))  # warm-up
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        dp_ = post.device_posterior()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        post.device_posterior()
+        times = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dp_ = post.device_posterior()
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        dt = float(np.median(times))
         posterior = {"droplets_per_s": n_cells / dt, "cells": n_cells, "n_samples": 20, "coo_entries": int(dp_.m.numel()),
-                     "seconds": dt}
+                     "seconds": dt, "timing": "median of 3 passes over the same 1024 cells (encoder once, 20 latent samples, COO)"}
         model.train()
 
     if rank != 0:
@@ -307,12 +332,20 @@ def run_b200(args):
 
     # ---- CPU baseline: the reference-style port on this box's host cores, bounded sample ----
     cpu = None
+    torch_cuda = None
     if not args.no_cpu_baseline and world == 1:
-        k_cpu = 3
-        s_step = cpu_reference_steps(ds, k_cpu, 1)
+        k_cpu = 16
+        s_step = cpu_reference_steps(ds, k_cpu, 2)
         cpu = {"value": s_step * spe_global, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                "sample": f"{k_cpu} minibatch steps of the {args.workload} shape on the host (reference loader + dense eager "
                          f"fp32 ELBO + per-tensor ClippedAdam; pyro overhead excluded), x {spe_global} steps/epoch"}
+        # the reference's torch-CUDA path, same stand-in on this GPU: a LOWER bound on the real
+        # `--cuda` step time because pyro's tracing / enumeration Python overhead is not in it
+        k_gpu = 20
+        s_gpu = cpu_reference_steps(ds, k_gpu, 3, device=dev)
+        torch_cuda = {"value": s_gpu * spe_global, "unit": UNIT, "ms_per_step": s_gpu * 1e3, "kind": "port",
+                      "sample": f"{k_gpu} steps: reference host loader + 34 MB H2D per minibatch + dense eager torch fp32 ELBO "
+                                f"(reference modules' arithmetic) + per-tensor ClippedAdam on the same B200; pyro overhead excluded"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
@@ -328,12 +361,14 @@ def run_b200(args):
                 "note": "counts are device-resident (uploaded once); per step only the 255 row ids go host->device"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "clipped_adam_kernel", "achieved": adam_gbs, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": adam_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": adam_gbs / peaks["hbm_gbs"], "traffic": ADAM_NCU_DRAM_BYTES, "peak_source": peak_src,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of clipped_adam_kernel, ncu --set full, "
+                                       "profiles/r01_step_kernels_ncu_summary.txt",
                      "algorithmic_bytes_per_launch": adam_bytes, "ms_per_launch": adam_ms},
         "kernels": {"elbo_obs_kernel": {"ms": obs_ms, "algorithmic_bytes": obs_bytes,
                                         "achieved_GBps": obs_bytes / (obs_ms * 1e-3) / 1e9,
                                         "elements_per_s": 2.0 * Bn * Gn / (obs_ms * 1e-3)}},
-        "cpu_baseline": cpu, "posterior": posterior,
+        "cpu_baseline": cpu, "reference_torch_cuda": torch_cuda, "posterior": posterior,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

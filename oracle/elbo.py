@@ -107,7 +107,7 @@ class _NbpcMp(torch.autograd.Function):
 
 
 def _masked_median(values, mask):
-    return values[mask].median() if bool(mask.any()) else torch.ones((), dtype=values.dtype)
+    return values[mask].median() if bool(mask.any()) else torch.ones((), dtype=values.dtype, device=values.device)
 
 
 def elbo(x: torch.Tensor, params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor], cfg: Dict, noise: Dict,
@@ -122,7 +122,8 @@ def elbo(x: torch.Tensor, params: Dict[str, torch.Tensor], buffers: Dict[str, to
     sd = {**params, **buffers}
     ps = {k[3:]: transform_to(CONSTRAINTS[k[3:]])(v) for k, v in params.items() if k.startswith("ps.")}
     sub = lambda pre: {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
-    c = lambda v: torch.as_tensor(v, dtype=dt)
+    dev = x.device
+    c = lambda v: torch.as_tensor(v, dtype=dt, device=dev)
     B = x.shape[0]
     chi_ambient = ps["chi_ambient"]
     chi_bar = c(cfg["chi_bar"])
@@ -169,17 +170,17 @@ def elbo(x: torch.Tensor, params: Dict[str, torch.Tensor], buffers: Dict[str, to
 
     alpha = phi.reciprocal() + EPS
     like = (lambda val, mu, al, lam: _NbpcMp.apply(val, mu, al, lam)) if likelihood == "mp" else onb.nbpc_approx_log_prob
-    obs = torch.zeros((), dtype=dt)
+    obs = torch.zeros((), dtype=dt, device=dev)
     for yv, q in ((1.0, q1), (0.0, q0)):
-        y = torch.full((B,), yv, dtype=dt)
+        y = torch.full((B,), yv, dtype=dt, device=dev)
         mu = onb.calculate_mu(model_type, epsilon=epsilon, d_cell=d_cell, chi=chi, y=y, rho=rho)
         lam = onb.calculate_lambda(model_type, epsilon=epsilon, chi_ambient=chi_ambient, d_empty=d_empty, y=y,
                                    d_cell=d_cell, rho=rho, chi_bar=chi_bar)
         L = like(x, mu + EPS, alpha, lam + EPS).sum(-1)
         obs = obs + (q * L).sum()
     # empty-droplet regulariser (model.py:374-398): epsilon = 1, y = 0, rho and d_cell detached, mask y == 0, scale 0.01
-    lam_e = onb.calculate_lambda(model_type, epsilon=torch.ones(B, dtype=dt), chi_ambient=chi_ambient, d_empty=d_empty,
-                                 y=torch.zeros(B, dtype=dt), d_cell=d_cell.detach(), rho=rho.detach(), chi_bar=chi_bar) + EPS
+    lam_e = onb.calculate_lambda(model_type, epsilon=torch.ones(B, dtype=dt, device=dev), chi_ambient=chi_ambient, d_empty=d_empty,
+                                 y=torch.zeros(B, dtype=dt, device=dev), d_cell=d_cell.detach(), rho=rho.detach(), chi_bar=chi_bar) + EPS
     LE = (torch.xlogy(x, lam_e) - lam_e - torch.lgamma(x + 1)).sum(-1)
     t["obs"] = obs + REG_SCALE_AMBIENT_EXPRESSION * (q0 * LE).sum()
 
@@ -192,9 +193,9 @@ def elbo(x: torch.Tensor, params: Dict[str, torch.Tensor], buffers: Dict[str, to
     t["obs_probably_cell_y"] = REG_SCALE_SOFT_SUPERVISION * torch.where(
         cell_m, Normal(REG_LOGIT_MEAN, REG_LOGIT_SOFT_SCALE).log_prob(p_det), zero).sum()
     surely_cell = counts >= torch.exp(d_cell_loc_prior)
-    one = torch.ones((), dtype=dt)
+    one = torch.ones((), dtype=dt, device=dev)
     t["epsilon_mean"] = Normal(_masked_median(epsilon, cell_m), 0.01).log_prob(one) if int(surely_cell.sum()) >= 2 \
-        else torch.zeros((), dtype=dt)
+        else torch.zeros((), dtype=dt, device=dev)
     t["epsilon_empty_mean"] = Normal(_masked_median(epsilon, empty_m), 0.01).log_prob(one)
     t["loss"] = -sum(t.values())
     t["_p_y"] = p_y

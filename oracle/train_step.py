@@ -15,7 +15,7 @@ import torch
 from . import elbo as oelbo
 
 
-def init_state(n_genes: int, z_dim: int, hidden: int, priors: Dict, seed: int = 1234, dtype=torch.float32):
+def init_state(n_genes: int, z_dim: int, hidden: int, priors: Dict, seed: int = 1234, dtype=torch.float32, device="cpu"):
     """Random-init parameters of the reference architecture (torch default inits), as plain tensors keyed like the
     reference's state_dicts."""
     torch.manual_seed(seed)
@@ -47,13 +47,13 @@ def init_state(n_genes: int, z_dim: int, hidden: int, priors: Dict, seed: int = 
             "phi_loc": torch.tensor(0.2, dtype=dtype), "phi_scale": torch.tensor(0.2, dtype=dtype)}
     for k, v in init.items():
         params["ps." + k] = transform_to(oelbo.CONSTRAINTS[k]).inv(v)
-    for v in params.values():
-        v.requires_grad_(True)
+    params = {k: v.detach().to(device).requires_grad_(True) for k, v in params.items()}
+    buffers = {k: v.to(device) for k, v in buffers.items()}
     return params, buffers
 
 
-def make_cfg(priors: Dict, empty_UMI_threshold: float, offset=None):
-    return dict(chi_bar=torch.as_tensor(priors["chi_bar"]), log_count_crossover=float(priors["log_counts_crossover"]),
+def make_cfg(priors: Dict, empty_UMI_threshold: float, offset=None, device="cpu"):
+    return dict(chi_bar=torch.as_tensor(priors["chi_bar"]).to(device), log_count_crossover=float(priors["log_counts_crossover"]),
                 prior_log_cell_counts=float(np.log1p(priors["cell_counts"])),
                 empty_log_count_threshold=float(np.log1p(empty_UMI_threshold)), offset=offset or {"logit_p": 0.0, "epsilon": 0.0},
                 d_cell_loc_prior=float(np.log1p(priors["cell_counts"])), d_cell_scale_prior=float(priors["d_std"]),
@@ -84,14 +84,16 @@ class ClippedAdamPerTensor:
 
 
 def reference_step(x: torch.Tensor, params, buffers, cfg, optimizer: ClippedAdamPerTensor, z_dim: int) -> float:
-    """One host training step on the dense minibatch x [B, G] (float32)."""
-    B = x.shape[0]
+    """One reference-style training step on the dense minibatch x [B, G] (float32), on x's device (the host for the
+    CPU baseline; a GPU for the "reference torch-CUDA path" stand-in, where x arrives by a per-step H2D copy exactly as
+    the reference's loader delivers it, dataprep.py:291-292)."""
+    B, dev = x.shape[0], x.device
     with torch.no_grad():
         ps = {k[3:]: torch.distributions.transform_to(oelbo.CONSTRAINTS[k[3:]])(v) for k, v in params.items() if k.startswith("ps.")}
-        conc = {"phi": ps["phi_loc"] ** 2 / ps["phi_scale"] ** 2, "epsilon": torch.full((B,), 50.0),
+        conc = {"phi": ps["phi_loc"] ** 2 / ps["phi_scale"] ** 2, "epsilon": torch.full((B,), 50.0, device=dev),
                 "rho_alpha": ps["rho_alpha"], "rho_beta": ps["rho_beta"]}
-    noise = oelbo.draw_noise(B, z_dim, conc)
-    keep = torch.bernoulli(torch.full((B,), 0.5)) * 2.0
+    noise = oelbo.draw_noise(B, z_dim, conc, device=dev)
+    keep = torch.bernoulli(torch.full((B,), 0.5, device=dev)) * 2.0
     terms = oelbo.elbo(x, params, buffers, cfg, noise, keep, training=True, likelihood="reference")
     terms["loss"].backward()
     optimizer.step()

@@ -68,7 +68,7 @@ def encode_nonz(x, chi_ambient, z_loc, sd: Dict[str, torch.Tensor], *, d_empty_l
     counts = x.sum(dim=-1, keepdim=True)
     log_sum = counts.log1p()
     log_nnz = (x > 0).sum(dim=-1, keepdim=True).to(x.dtype).log1p()
-    d_empty_loc = torch.as_tensor(d_empty_loc, dtype=x.dtype)
+    d_empty_loc = torch.as_tensor(d_empty_loc, dtype=x.dtype, device=x.device)
     overlap = -0.5 * (torch.clamp(log_sum - d_empty_loc, min=0.0) / 0.1).pow(2)
     x_amb = d_empty_loc.exp() * chi_ambient.unsqueeze(0)
     x_amb_norm = x_amb / torch.linalg.vector_norm(x_amb, ord=2, dim=-1, keepdim=True)
