@@ -62,12 +62,70 @@ __global__ void __launch_bounds__(256) clipped_adam_kernel(float* __restrict__ p
 
 __global__ void advance_step_kernel(long long* step_ptr) { *step_ptr += 1; }
 
+// the same update on a [rows, cols] sub-block of a [rows, ld] matrix (the few feature columns of a weight matrix whose
+// gene block is updated inside the weight-gradient GEMM epilogue)
+__global__ void __launch_bounds__(256) clipped_adam_2d_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                              float* __restrict__ m, float* __restrict__ v, int rows, int cols,
+                                                              long long ld, const float* __restrict__ lr_table,
+                                                              const float* __restrict__ beta1_table, long long table_len,
+                                                              const long long* __restrict__ step_ptr, float beta2, float eps,
+                                                              float clip) {
+  const long long t0 = *step_ptr;
+  const long long ti = t0 < table_len ? t0 : table_len - 1;
+  const float lr = lr_table[ti], b1 = beta1_table[ti];
+  const double t = double(t0 + 1);
+  const float step_size = float(double(lr) * sqrt(1.0 - pow(double(beta2), t)) / (1.0 - pow(double(b1), t)));
+  const float omb1 = 1.0f - b1, omb2 = 1.0f - beta2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)rows * cols; i += (long long)gridDim.x * blockDim.x) {
+    const long long idx = (i / cols) * ld + (i % cols);
+    const float gc = fminf(fmaxf(g[idx], -clip), clip);
+    const float mk = b1 * m[idx] + omb1 * gc;
+    const float vk = beta2 * v[idx] + omb2 * gc * gc;
+    m[idx] = mk, v[idx] = vk;
+    p[idx] -= step_size * mk / (sqrtf(vk) + eps);
+  }
+}
+
 }  // namespace cb
+
+static int adam_range(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
+                      const float* beta1_table, long long table_len, long long* step_ptr, float beta2, float eps, float clip,
+                      float grad_scale, int advance, void* stream);
 
 extern "C" int cb_clipped_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
                                     const float* beta1_table, long long table_len, long long* step_ptr, float beta2,
                                     float eps, float clip, float grad_scale, void* stream) {
-  CB_REQUIRE(n > 0 && table_len > 0, "cb_clipped_adam_step: bad sizes n=%lld table_len=%lld", n, table_len);
+  return adam_range(p, g, m, v, n, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip, grad_scale, 1, stream);
+}
+
+// One contiguous range of the flat buffers without advancing the step counter (n = 0: nothing to update); with
+// advance != 0 the counter is incremented after the range.  Used when parts of the buffer are updated elsewhere
+// (cb_gemm_tf32_dw_adam) and the rest is swept range by range.
+extern "C" int cb_clipped_adam_range(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
+                                     const float* beta1_table, long long table_len, long long* step_ptr, float beta2,
+                                     float eps, float clip, int advance, void* stream) {
+  return adam_range(p, g, m, v, n, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip, 1.0f, advance, stream);
+}
+
+extern "C" int cb_clipped_adam_2d(float* p, const float* g, float* m, float* v, int rows, int cols, long long ld,
+                                  const float* lr_table, const float* beta1_table, long long table_len,
+                                  const long long* step_ptr, float beta2, float eps, float clip, void* stream) {
+  CB_REQUIRE(rows > 0 && cols > 0 && ld >= cols && table_len > 0, "cb_clipped_adam_2d: bad shape [%d, %d] ld=%lld", rows, cols, ld);
+  const long long n = (long long)rows * cols;
+  cb::clipped_adam_2d_kernel<<<unsigned((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, rows, cols, ld, lr_table,
+                                                                                         beta1_table, table_len, step_ptr, beta2,
+                                                                                         eps, clip);
+  return cb::check_launch("cb_clipped_adam_2d");
+}
+
+static int adam_range(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
+                      const float* beta1_table, long long table_len, long long* step_ptr, float beta2, float eps, float clip,
+                      float grad_scale, int advance, void* stream) {
+  CB_REQUIRE(n >= 0 && table_len > 0, "cb_clipped_adam_step: bad sizes n=%lld table_len=%lld", n, table_len);
+  if (n == 0) {
+    if (advance) cb::advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_ptr);
+    return cb::check_launch("cb_clipped_adam_step");
+  }
   for (const void* q : {(const void*)p, (const void*)g, (const void*)m, (const void*)v})
     CB_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0, "cb_clipped_adam_step: buffers must be 16-byte aligned");
   const long long n4 = (n + 3) / 4;
@@ -77,6 +135,6 @@ extern "C" int cb_clipped_adam_step(float* p, const float* g, float* m, float* v
   cb::clipped_adam_kernel<<<unsigned(blocks), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_table, beta1_table,
                                                                               table_len, step_ptr, beta2, eps, clip,
                                                                               grad_scale);
-  cb::advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_ptr);
+  if (advance) cb::advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_ptr);
   return cb::check_launch("cb_clipped_adam_step");
 }

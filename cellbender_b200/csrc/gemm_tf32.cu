@@ -131,7 +131,40 @@ struct GemmParams {
   int split_k;
   int accumulate;        // C += ... (direct path)
   long long Mpad, Npad;
+  // optional fused optimizer epilogue (weight-gradient products only): instead of storing the gradient tile, apply the
+  // ClippedAdam update (csrc/adam.cu) to the parameter / moment tiles that share C's indexing -- the 68.7 MB gradient
+  // of a G x 512 layer is then never written to, nor read back from, HBM.
+  float* adam_p;         // nullptr = plain store
+  float* adam_m;
+  float* adam_v;
+  const float* lr_table;
+  const float* beta1_table;
+  long long table_len;
+  const long long* step_ptr;
+  float beta2, eps, clip;
 };
+
+struct AdamCoef {
+  float b1, omb1, b2, omb2, step_size, eps, clip;
+};
+__device__ __forceinline__ AdamCoef adam_coef(const GemmParams& p) {
+  const long long t0 = *p.step_ptr;
+  const long long ti = t0 < p.table_len ? t0 : p.table_len - 1;
+  const float lr = p.lr_table[ti], b1 = p.beta1_table[ti];
+  const double t = double(t0 + 1);
+  AdamCoef c;
+  c.b1 = b1, c.omb1 = 1.0f - b1, c.b2 = p.beta2, c.omb2 = 1.0f - p.beta2;
+  c.step_size = float(double(lr) * sqrt(1.0 - pow(double(p.beta2), t)) / (1.0 - pow(double(b1), t)));
+  c.eps = p.eps, c.clip = p.clip;
+  return c;
+}
+// the arithmetic of clipped_adam_kernel (csrc/adam.cu), element for element
+__device__ __forceinline__ void adam_update(float g, float& pw, float& m, float& v, const AdamCoef& c) {
+  const float gc = fminf(fmaxf(g, -c.clip), c.clip);
+  m = c.b1 * m + c.omb1 * gc;
+  v = c.b2 * v + c.omb2 * gc * gc;
+  pw -= c.step_size * m / (sqrtf(v) + c.eps);
+}
 
 // MT = accumulators of 128 rows per CTA, BN = tile width; MT * BN <= 512 TMEM columns.
 // MINB = CTAs per SM the launch is sized for: short-K products (weight gradients: K = 255 droplets; the hidden layers)
@@ -237,14 +270,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       umma_commit(&accum_bar);  // accumulator complete
     }
   } else {
-    // ======================= epilogue: TMEM -> registers -> global =======================
+    // ======================= epilogue: TMEM -> registers -> shared -> global =======================
+    // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns).  Storing that directly makes each
+    // warp instruction touch 32 different rows (32 sectors, 16 bytes used of each).  Instead every warp transposes its
+    // 32 x 32 sub-tile through a private staging buffer (carved out of the now idle operand ring: all MMAs have
+    // completed), after which one warp instruction covers 4 rows x 128 contiguous bytes.
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const bool to_ws = p.split_k > 1;
+    constexpr int kStg = 36;  // staging row pitch in floats: 16-byte aligned rows, conflict-free float4 phases
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * kStg);
+    const int cc = 4 * (lane & 7), rsub = lane >> 3;
+    AdamCoef ac;
+    if (p.adam_p != nullptr) ac = adam_coef(p);
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
-      const int row = m0 + mt * kBlockM + q * 32 + lane;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         float v[32];
@@ -254,37 +295,57 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        const int col = n0 + c;
-        if (to_ws) {
-          float* dst = p.workspace + ((long long)split * p.Mpad + row) * p.Npad + col;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else if (row < p.M && col < p.N) {
-          float* dst = p.C + (long long)row * p.ldc + col;
-          const int nv = min(32, p.N - col);
-          if (nv == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * kStg + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int col = n0 + c + cc;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-              if (p.bias != nullptr) {
-                const float4 b = *reinterpret_cast<const float4*>(p.bias + col + i);
-                o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
-              }
-              if (p.accumulate) {
-                const float4 old = *reinterpret_cast<const float4*>(dst + i);
-                o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
-              }
-              *reinterpret_cast<float4*>(dst + i) = o;
+        for (int rr = 0; rr < 8; ++rr) {
+          const int rl = rr * 4 + rsub;
+          float4 o = *reinterpret_cast<const float4*>(stg + rl * kStg + cc);
+          const int row = m0 + mt * kBlockM + q * 32 + rl;
+          if (to_ws) {
+            *reinterpret_cast<float4*>(p.workspace + ((long long)split * p.Mpad + row) * p.Npad + col) = o;
+            continue;
+          }
+          if (row >= p.M || col >= p.N) continue;
+          const long long off = (long long)row * p.ldc + col;
+          const int nv = min(4, p.N - col);
+          float ov[4] = {o.x, o.y, o.z, o.w};
+          if (p.adam_p != nullptr) {
+            float* pp = p.adam_p + off;
+            float* pm = p.adam_m + off;
+            float* pv = p.adam_v + off;
+            if (nv == 4 && ((reinterpret_cast<uintptr_t>(pp) | reinterpret_cast<uintptr_t>(pm) | reinterpret_cast<uintptr_t>(pv)) & 15) == 0) {
+              float4 w4 = *reinterpret_cast<float4*>(pp), m4 = *reinterpret_cast<float4*>(pm), v4 = *reinterpret_cast<float4*>(pv);
+              adam_update(ov[0], w4.x, m4.x, v4.x, ac);
+              adam_update(ov[1], w4.y, m4.y, v4.y, ac);
+              adam_update(ov[2], w4.z, m4.z, v4.z, ac);
+              adam_update(ov[3], w4.w, m4.w, v4.w, ac);
+              *reinterpret_cast<float4*>(pp) = w4, *reinterpret_cast<float4*>(pm) = m4, *reinterpret_cast<float4*>(pv) = v4;
+            } else {
+              for (int i = 0; i < nv; ++i) adam_update(ov[i], pp[i], pm[i], pv[i], ac);
             }
+            continue;
+          }
+          float* dst = p.C + off;
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < nv) ov[i] += p.bias[col + i];
+          }
+          if (nv == 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            if (p.accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(dst);
+              ov[0] += old.x, ov[1] += old.y, ov[2] += old.z, ov[3] += old.w;
+            }
+            *reinterpret_cast<float4*>(dst) = make_float4(ov[0], ov[1], ov[2], ov[3]);
           } else {
-            for (int i = 0; i < nv; ++i) {
-              float o = v[i];
-              if (p.bias != nullptr) o += p.bias[col + i];
-              if (p.accumulate) o += dst[i];
-              dst[i] = o;
-            }
+            for (int i = 0; i < nv; ++i) dst[i] = p.accumulate ? dst[i] + ov[i] : ov[i];
           }
         }
+        __syncwarp();  // the staging buffer is rewritten by the next chunk
       }
     }
     tc_fence_before();
@@ -386,10 +447,20 @@ extern "C" int cb_gemm_tf32_suggest_split(int M, int N, int K) {
   return int(s < 1 ? 1 : s);
 }
 
-extern "C" int cb_gemm_tf32_pair(const float* A, long long lda, const float* B, long long ldb, int K, const float* A2,
-                                 long long lda2, const float* B2, long long ldb2, int K2, int a_mn, int b_mn, float* C,
-                                 long long ldc, int M, int N, const float* bias, int accumulate, int split_k,
-                                 float* workspace, long long workspace_elems, void* stream) {
+namespace cb {
+struct AdamArgs {
+  float *p, *m, *v;
+  const float *lr_table, *beta1_table;
+  long long table_len;
+  const long long* step_ptr;
+  float beta2, eps, clip;
+};
+}  // namespace cb
+
+static int gemm_tf32_impl(const float* A, long long lda, const float* B, long long ldb, int K, const float* A2,
+                          long long lda2, const float* B2, long long ldb2, int K2, int a_mn, int b_mn, float* C,
+                          long long ldc, int M, int N, const float* bias, int accumulate, int split_k,
+                          float* workspace, long long workspace_elems, const cb::AdamArgs* adam, void* stream) {
   using namespace cb;
   CB_REQUIRE(M > 0 && N > 0 && K > 0 && K2 >= 0, "cb_gemm_tf32: bad shape M=%d N=%d K=%d K2=%d", M, N, K, K2);
   CB_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && (lda2 & 3) == 0 && (ldb2 & 3) == 0,
@@ -408,6 +479,14 @@ extern "C" int cb_gemm_tf32_pair(const float* A, long long lda, const float* B, 
   split_k = (kb_total + p.k_blocks_per_split - 1) / p.k_blocks_per_split;  // every split owns >= 1 k-block
   p.split_k = split_k;
   p.accumulate = accumulate;
+  p.adam_p = p.adam_m = p.adam_v = nullptr;
+  p.lr_table = p.beta1_table = nullptr, p.table_len = 0, p.step_ptr = nullptr, p.beta2 = p.eps = p.clip = 0.f;
+  if (adam != nullptr) {
+    CB_REQUIRE(split_k <= 1 && bias == nullptr && !accumulate,
+               "cb_gemm_tf32_dw_adam: the fused optimizer epilogue needs split_k = 1, no bias, no accumulation");
+    p.adam_p = adam->p, p.adam_m = adam->m, p.adam_v = adam->v, p.lr_table = adam->lr_table, p.beta1_table = adam->beta1_table;
+    p.table_len = adam->table_len, p.step_ptr = adam->step_ptr, p.beta2 = adam->beta2, p.eps = adam->eps, p.clip = adam->clip;
+  }
   p.Mpad = (M + 255) / 256 * 256, p.Npad = (N + 255) / 256 * 256;
   if (split_k > 1) {
     CB_REQUIRE(workspace != nullptr && workspace_elems >= (long long)split_k * p.Mpad * p.Npad,
@@ -451,9 +530,30 @@ extern "C" int cb_gemm_tf32_pair(const float* A, long long lda, const float* B, 
   return cb::check_launch("cb_gemm_tf32");
 }
 
+extern "C" int cb_gemm_tf32_pair(const float* A, long long lda, const float* B, long long ldb, int K, const float* A2,
+                                 long long lda2, const float* B2, long long ldb2, int K2, int a_mn, int b_mn, float* C,
+                                 long long ldc, int M, int N, const float* bias, int accumulate, int split_k,
+                                 float* workspace, long long workspace_elems, void* stream) {
+  return gemm_tf32_impl(A, lda, B, ldb, K, A2, lda2, B2, ldb2, K2, a_mn, b_mn, C, ldc, M, N, bias, accumulate, split_k, workspace,
+                        workspace_elems, nullptr, stream);
+}
+
 extern "C" int cb_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C,
                             long long ldc, int M, int N, int K, const float* bias, int accumulate, int split_k,
                             float* workspace, long long workspace_elems, void* stream) {
-  return cb_gemm_tf32_pair(A, lda, B, ldb, K, A, lda, B, ldb, 0, a_mn, b_mn, C, ldc, M, N, bias, accumulate, split_k, workspace,
-                           workspace_elems, stream);
+  return gemm_tf32_impl(A, lda, B, ldb, K, A, lda, B, ldb, 0, a_mn, b_mn, C, ldc, M, N, bias, accumulate, split_k, workspace,
+                        workspace_elems, nullptr, stream);
+}
+
+// Weight-gradient product with the optimizer fused into the epilogue:  G = A B^T (never stored), then the
+// ClippedAdam update of cb_clipped_adam_step applied to param / exp_avg / exp_avg_sq, which are indexed like C
+// ([M, ldc] with the same leading dimension).  *step_ptr is read, not advanced.
+extern "C" int cb_gemm_tf32_dw_adam(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn,
+                                    long long ldc, int M, int N, int K, float* param, float* exp_avg, float* exp_avg_sq,
+                                    const float* lr_table, const float* beta1_table, long long table_len,
+                                    const long long* step_ptr, float beta2, float eps, float clip, void* stream) {
+  CB_REQUIRE(param != nullptr && exp_avg != nullptr && exp_avg_sq != nullptr && lr_table != nullptr && beta1_table != nullptr &&
+                 step_ptr != nullptr && table_len > 0, "cb_gemm_tf32_dw_adam: optimizer state pointers must not be NULL");
+  cb::AdamArgs a{param, exp_avg, exp_avg_sq, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip};
+  return gemm_tf32_impl(A, lda, B, ldb, K, A, lda, B, ldb, 0, a_mn, b_mn, param, ldc, M, N, nullptr, 0, 1, nullptr, 0, &a, stream);
 }

@@ -21,6 +21,9 @@ from . import ops
 from ._cabi import current_stream, lib, ptr
 
 BACKEND = "tcgen05"
+# optimizer whose update is fused into the weight-gradient GEMM epilogues during the current backward pass (set by
+# train.SVI around loss.backward(); None = gradients are written to the flat gradient buffer as usual)
+FUSED_OPT = None
 
 
 def set_backend(name: str):
@@ -39,6 +42,12 @@ def _grad_target(weight: torch.Tensor):
         return t, t
     weight._cb_grad_direct = True
     return gv, None
+
+
+def fused_update_applies(w: torch.Tensor) -> bool:
+    opt = FUSED_OPT
+    return (opt is not None and BACKEND == "tcgen05" and getattr(w, "_cb_block", None) is not None
+            and getattr(w, "_cb_grad_view", None) is not None and w.requires_grad)
 
 
 def _tma_ok(t: torch.Tensor) -> bool:
@@ -71,6 +80,7 @@ class _MultiLinearBig(torch.autograd.Function):
         ctx.save_for_backward(x, *[t for t in feats if t is not None], *weights)
         ctx.meta = (len(weights), n_in, col_offset, [f is not None for f in feats], [b is not None for b in biases])
         ctx.biases = biases  # the nn.Parameter objects (they carry the optimizer's gradient views)
+        ctx.weights_p = weights
         return tuple(ys)
 
     @staticmethod
@@ -80,6 +90,7 @@ class _MultiLinearBig(torch.autograd.Function):
         x = saved.pop(0)
         feats = [saved.pop(0) if h else None for h in has_feat]
         weights = saved
+        weights_p = ctx.weights_p
         B = x.shape[0]
         need_dx = ctx.needs_input_grad[0]
         dys = [d.contiguous() for d in dys]
@@ -88,7 +99,7 @@ class _MultiLinearBig(torch.autograd.Function):
         targets = []
         for i in range(n):
             w = weights[i]
-            dw_t = _grad_target(w) if ctx.needs_input_grad[3 + 3 * i + 1] else None
+            dw_t = _grad_target(weights_p[i]) if ctx.needs_input_grad[3 + 3 * i + 1] else None
             db_t = _grad_target(ctx.biases[i]) if (has_bias[i] and ctx.needs_input_grad[3 + 3 * i + 2]) else None
             targets.append((dw_t, db_t))
 
@@ -99,22 +110,27 @@ class _MultiLinearBig(torch.autograd.Function):
                 dw_t, db_t = targets[i]
                 if dw_t is not None:
                     # dW[H, n_in] = dy^T[H, B] . x[B, n_in]: both operands stored with the reduction dim (B) as rows
-                    ops.gemm_tf32(dy, x, H, n_in, B, a_mn=True, b_mn=True, out=dw_t[0][:, off:off + n_in], split_k=1)
+                    if fused[i]:
+                        FUSED_OPT.fused_dw(weights_p[i], dy, x, H, n_in, B, off)  # ... and W -= Adam(dW) in the epilogue
+                    else:
+                        ops.gemm_tf32(dy, x, H, n_in, B, a_mn=True, b_mn=True, out=dw_t[0][:, off:off + n_in], split_k=1)
                     if off:
                         dw_t[0][:, :off] = dy.t() @ feat
                 if db_t is not None:
                     ops.colsum_rows(dy, H, out=db_t[0])
 
         # the weight-gradient products and the input-gradient product are independent: fork the former onto a side
-        # stream (parallel branches of the captured step graph), join before returning
-        fork = need_dx and any(t[0] is not None or t[1] is not None for t in targets)
+        # stream (parallel branches of the captured step graph), join before returning -- unless a weight is updated
+        # inside its gradient GEMM: then the input-gradient product (a reader of the OLD weights) must come first
+        fused = [targets[i][0] is not None and fused_update_applies(weights_p[i]) for i in range(n)]
+        fork = need_dx and not any(fused) and any(t[0] is not None or t[1] is not None for t in targets)
         main = torch.cuda.current_stream()
         if fork:
             side = ops.side_stream(x.device, 0)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 parameter_gradients()
-        else:
+        elif not any(fused):
             parameter_gradients()
         if need_dx:
             if n == 2:
@@ -127,6 +143,8 @@ class _MultiLinearBig(torch.autograd.Function):
                     w = weights[i]
                     ops.gemm_tf32(dys[i], w[:, off:off + n_in], B, n_in, w.shape[0], b_mn=True, out=dx, accumulate=i > 0,
                                   split_k=1)
+        if any(fused):
+            parameter_gradients()  # after the readers of the old weights
         grads = []
         for i in range(n):
             dfeat = None

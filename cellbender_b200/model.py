@@ -155,7 +155,8 @@ class _ObsTerm(torch.autograd.Function):
         ctx.save_for_backward(h_dec, w_out, sums, w, out["dlogits"], out["dchi_ambient"])
         ctx.G = G
         ctx.alpha_shape = alpha.shape
-        ctx.bias_param = b_out  # the nn.Parameter object (it carries the optimizer's gradient view)
+        ctx.bias_param = b_out  # the nn.Parameter objects (they carry the optimizer's gradient views)
+        ctx.w_param = w_out
         neg_obs, obs = ops.obs_loss(sums, w)  # sum_b w . L and its negative (the 'obs' ELBO term)
         ctx.mark_non_differentiable(L, obs)
         return neg_obs, L, obs
@@ -168,16 +169,25 @@ class _ObsTerm(torch.autograd.Function):
         if gemm.BACKEND == "tcgen05":
             B, H = h_dec.shape
             h_c = h_dec.contiguous()
-            d_w_buf, d_w = gemm._grad_target(w_out)
+            w_param = ctx.w_param
+            d_w_buf, d_w = gemm._grad_target(w_param)
             d_b_buf, d_b = gemm._grad_target(ctx.bias_param)
-            # decoder weight / bias gradients on a side stream, the hidden-activation gradient on this one
-            main, side = torch.cuda.current_stream(), ops.side_stream(dlogits.device, 0)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                ops.gemm_tf32(dlogits, h_c, G, H, B, a_mn=True, b_mn=True, out=d_w_buf, split_k=1)  # dlogits^T . h
+            main = torch.cuda.current_stream()
+            if gemm.fused_update_applies(w_param):
+                # the hidden-activation gradient reads the OLD decoder weights: issue it first, then the weight-gradient
+                # GEMM whose epilogue applies the optimizer update in place
+                d_h = ops.gemm_tf32(dlogits, w_out, B, H, G, b_mn=True) * g
+                gemm.FUSED_OPT.fused_dw(w_param, dlogits, h_c, G, H, B, 0)
                 ops.colsum_rows(dlogits, G, out=d_b_buf)
-            d_h = ops.gemm_tf32(dlogits, w_out, B, H, G, b_mn=True) * g          # dlogits[B,G] . Wd[G,H], split-K
-            main.wait_stream(side)
+            else:
+                # decoder weight / bias gradients on a side stream, the hidden-activation gradient on this one
+                side = ops.side_stream(dlogits.device, 0)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    ops.gemm_tf32(dlogits, h_c, G, H, B, a_mn=True, b_mn=True, out=d_w_buf, split_k=1)  # dlogits^T . h
+                    ops.colsum_rows(dlogits, G, out=d_b_buf)
+                d_h = ops.gemm_tf32(dlogits, w_out, B, H, G, b_mn=True) * g          # dlogits[B,G] . Wd[G,H], split-K
+                main.wait_stream(side)
         else:
             d_h = (dl @ w_out) * g
             d_w = dl.t() @ h_dec  # [G, H]

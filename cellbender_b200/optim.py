@@ -71,6 +71,8 @@ class FlatClippedAdam:
                 view.copy_(p.data)
                 p.data = view
                 p._cb_grad_view = gview  # GEMM epilogues write weight gradients here directly (gemm.py)
+                if ld is not None:
+                    p._cb_block = (o, p.shape[0], ld, p.shape[1])  # [rows, ld] block of the flat buffers
                 self.grad_views.append(gview)
         self.learning_rate = learning_rate
         self.total_steps = total_steps
@@ -85,8 +87,14 @@ class FlatClippedAdam:
         self.beta2, self.eps, self.clip = betas[1], eps, clip_norm
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)  # optimizer steps taken (device side)
         self.host_steps = 0
+        # Single-GPU training applies the update of the four G x 512 weight matrices (99 % of the parameters) inside the
+        # epilogue of their weight-gradient GEMM (cb_gemm_tf32_dw_adam): their gradients never travel to HBM and back.
+        # Data-parallel training needs the gradients for the all-reduce and switches this off (dp.attach).
+        self.fuse_weight_updates = True
+        self._fused_done: List[tuple] = []
 
     def zero_grad(self):
+        self._fused_done = []
         for p in self.params:
             p.grad = None
             p._cb_grad_direct = False
@@ -104,13 +112,51 @@ class FlatClippedAdam:
         if src:
             torch._foreach_copy_(dst, src)
 
+    def fused_dw(self, w: nn.Parameter, dy: torch.Tensor, x: torch.Tensor, rows: int, n_in: int, n_batch: int, col_offset: int):
+        """dW[rows, n_in] = dy^T x with the ClippedAdam update of W[:, col_offset:col_offset + n_in] applied in the GEMM
+        epilogue.  The caller guarantees that every reader of the OLD weights (input-gradient products) was issued before."""
+        from ._cabi import current_stream, lib
+
+        o, n_rows, ld, cols = w._cb_block
+        assert n_rows == rows and col_offset + n_in <= cols
+        byte = 4 * (o + col_offset)
+        lib().call("cb_gemm_tf32_dw_adam", dy.data_ptr(), dy.stride(0), 1, x.data_ptr(), x.stride(0), 1, ld, rows, n_in, n_batch,
+                   self.flat_p.data_ptr() + byte, self.flat_m.data_ptr() + byte, self.flat_v.data_ptr() + byte,
+                   self.lr_table.data_ptr(), self.beta1_table.data_ptr(), self.lr_table.numel(), self.step_count.data_ptr(),
+                   float(self.beta2), float(self.eps), float(self.clip), current_stream())
+        w._cb_grad_direct = True
+        self._fused_done.append((o, n_rows, ld, cols, col_offset))
+
     def step(self, grad_scale: float = 1.0):
         """One ClippedAdam step over the flat buffers + one scheduler step."""
         if not self.constant_learning_rate and self.host_steps >= self.total_steps:
             raise ValueError(f"Tried to step {self.host_steps + 1} times. The specified number of total steps is "
                              f"{self.total_steps}")
-        ops.clipped_adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_table, self.beta1_table,
-                              self.step_count, beta2=self.beta2, eps=self.eps, clip=self.clip, grad_scale=grad_scale)
+        if self._fused_done:
+            # blocks already updated by their weight-gradient GEMM: sweep the ranges between them, plus the few feature
+            # columns in front of each gene block (their gradient went to the flat buffer the usual way)
+            from ._cabi import current_stream, lib
+
+            assert grad_scale == 1.0, "fused weight updates do not support gradient rescaling"
+            L, st = lib(), current_stream()
+            tab = (self.lr_table.data_ptr(), self.beta1_table.data_ptr(), self.lr_table.numel(), self.step_count.data_ptr(),
+                   float(self.beta2), float(self.eps), float(self.clip))
+            at = lambda t, off: t.data_ptr() + 4 * off
+            cur = 0
+            for o, rows, ld, cols, off in sorted(self._fused_done):
+                assert o >= cur, "fused blocks overlap"
+                L.call("cb_clipped_adam_range", at(self.flat_p, cur), at(self.flat_g, cur), at(self.flat_m, cur),
+                       at(self.flat_v, cur), o - cur, *tab, 0, st)
+                if off:
+                    L.call("cb_clipped_adam_2d", at(self.flat_p, o), at(self.flat_g, o), at(self.flat_m, o), at(self.flat_v, o),
+                           rows, off, ld, *tab, st)
+                cur = o + rows * ld
+            L.call("cb_clipped_adam_range", at(self.flat_p, cur), at(self.flat_g, cur), at(self.flat_m, cur), at(self.flat_v, cur),
+                   self.n - cur, *tab, 1, st)
+            self._fused_done = []
+        else:
+            ops.clipped_adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_table, self.beta1_table,
+                                  self.step_count, beta2=self.beta2, eps=self.eps, clip=self.clip, grad_scale=grad_scale)
         self.host_steps += 1
 
     def get_last_lr(self) -> List[float]:

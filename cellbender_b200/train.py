@@ -66,10 +66,18 @@ class SVI:
                                      chi_ambient=chi_ambient)
 
     def _forward_backward(self, batch) -> torch.Tensor:
+        from . import gemm
+
         self.optim.zero_grad()
         terms = self.loss_terms(batch)
         loss = terms["loss"]
-        loss.backward()
+        # single GPU: the large weight matrices are updated inside their weight-gradient GEMMs (optim.fused_dw)
+        fuse = self.after_backward is None and self.optim.fuse_weight_updates and self.model.training
+        gemm.FUSED_OPT = self.optim if fuse else None
+        try:
+            loss.backward()
+        finally:
+            gemm.FUSED_OPT = None
         self.optim.collect_grads()
         return loss.detach()
 

@@ -136,6 +136,13 @@ int cb_gemm_tf32_pair(const float* A, long long lda, const float* B, long long l
 int cb_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C,
                  long long ldc, int M, int N, int K, const float* bias, int accumulate, int split_k, float* workspace,
                  long long workspace_elems, void* stream);
+/* Weight-gradient product with the optimizer step fused into its epilogue (train.py:56-60 after loss.backward()):
+ * G = A B^T is never stored; param / exp_avg / exp_avg_sq ([M, ldc], indexed like the gradient would be) receive the
+ * ClippedAdam update of cb_clipped_adam_step with the lr / beta1 of step *step_ptr (read, not advanced).          */
+int cb_gemm_tf32_dw_adam(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, long long ldc,
+                         int M, int N, int K, float* param, float* exp_avg, float* exp_avg_sq, const float* lr_table,
+                         const float* beta1_table, long long table_len, const long long* step_ptr, float beta2, float eps,
+                         float clip, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * A4(tail)+A9  the per-droplet latent algebra of RemoveBackgroundPyroModel.model / .guide (model.py:232-445, 447-574),
@@ -202,6 +209,14 @@ int cb_simplex_backward(int n, const float* y, const float* grad_y, float* grad_
 int cb_clipped_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
                          const float* beta1_table, long long table_len, long long* step_ptr, float beta2, float eps,
                          float clip, float grad_scale, void* stream);
+/* the same update on one contiguous range (step counter advanced only if advance != 0; n = 0 allowed) and on a
+ * [rows, cols] sub-block of a [rows, ld] matrix: the parts of the flat buffer NOT covered by cb_gemm_tf32_dw_adam.  */
+int cb_clipped_adam_range(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
+                          const float* beta1_table, long long table_len, long long* step_ptr, float beta2, float eps,
+                          float clip, int advance, void* stream);
+int cb_clipped_adam_2d(float* p, const float* g, float* m, float* v, int rows, int cols, long long ld, const float* lr_table,
+                       const float* beta1_table, long long table_len, const long long* step_ptr, float beta2, float eps,
+                       float clip, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * A10-A12  posterior noise-count log-probability over the stored (non-zero) counts.  Replaces
