@@ -29,6 +29,8 @@
 namespace cb {
 
 constexpr int kGemmThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int kAdamThreads = 320;  // + warps 6..9: helpers of the fused optimizer epilogue
+constexpr int kTilePitch = 132;    // floats per staged gradient-tile row (128 + 4: 16-byte rows, conflict-free float4 phases)
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;  // 32 fp32 = 128 B = one swizzle row
 constexpr int kUmmaK = 8;    // tf32: 32 B per MMA along K
@@ -170,8 +172,10 @@ __device__ __forceinline__ void adam_update(float g, float& pw, float& m, float&
 // MINB = CTAs per SM the launch is sized for: short-K products (weight gradients: K = 255 droplets; the hidden layers)
 // run two CTAs per SM with a 2-stage ring (2 x 256 TMEM columns, 2 x 97 KB of shared memory), so one CTA's epilogue
 // overlaps the other's loads -- each CTA lives for only ~8 k-blocks.
-template <int MT, int BN, bool A_MN, bool B_MN, int STAGES, int MINB>
-__global__ void __launch_bounds__(kGemmThreads, MINB)
+// ADAM = the fused-optimizer variant (weight-gradient products of the large layers): four extra helper warps, and in
+// the epilogue ALL warps of the CTA sweep the gradient tile (staged in shared memory) over param / exp_avg / exp_avg_sq.
+template <int MT, int BN, bool A_MN, bool B_MN, int STAGES, int MINB, bool ADAM = false>
+__global__ void __launch_bounds__(ADAM ? kAdamThreads : kGemmThreads, MINB)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b2, GemmParams p) {
   constexpr uint32_t kABytes = MT * kBlockM * kBlockK * 4;  // per stage
@@ -269,21 +273,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       umma_commit(&accum_bar);  // accumulator complete
     }
-  } else {
-    // ======================= epilogue: TMEM -> registers -> shared -> global =======================
-    // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns).  Storing that directly makes each
-    // warp instruction touch 32 different rows (32 sectors, 16 bytes used of each).  Instead every warp transposes its
-    // 32 x 32 sub-tile through a private staging buffer (carved out of the now idle operand ring: all MMAs have
-    // completed), after which one warp instruction covers 4 rows x 128 contiguous bytes.
+  } else if (!ADAM && warp < 6) {
+    // ======================= epilogue: TMEM -> registers (-> shared) -> global =======================
+    // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns).
+    //  * plain output: each thread stores its 128 contiguous bytes (8 x st.v4, fire-and-forget);
+    //  * split-K partial tiles and the fused optimizer update: every warp first transposes its 32 x 32 sub-tile through
+    //    a private staging buffer (carved out of the now idle operand ring: all MMAs have completed), after which one
+    //    warp instruction covers 4 rows x 128 contiguous bytes -- the read-modify-write of param / exp_avg / exp_avg_sq
+    //    then moves whole 128-byte lines, and all its loads are issued before the first store.
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const bool to_ws = p.split_k > 1;
+    const bool staged = to_ws;
     constexpr int kStg = 36;  // staging row pitch in floats: 16-byte aligned rows, conflict-free float4 phases
     float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * kStg);
     const int cc = 4 * (lane & 7), rsub = lane >> 3;
-    AdamCoef ac;
-    if (p.adam_p != nullptr) ac = adam_coef(p);
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll 1
@@ -295,60 +300,137 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
+        if (!staged) {
+          const int row = m0 + mt * kBlockM + q * 32 + lane;
+          const int col = n0 + c;
+          if (row < p.M && col < p.N) {
+            float* dst = p.C + (long long)row * p.ldc + col;
+            const int nv = min(32, p.N - col);
+            if (nv == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                if (p.bias != nullptr) {
+                  const float4 b = *reinterpret_cast<const float4*>(p.bias + col + i);
+                  o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
+                }
+                if (p.accumulate) {
+                  const float4 old = *reinterpret_cast<const float4*>(dst + i);
+                  o.x += old.x, o.y += old.y, o.z += old.z, o.w += old.w;
+                }
+                *reinterpret_cast<float4*>(dst + i) = o;
+              }
+            } else {
+              for (int i = 0; i < nv; ++i) {
+                float o = v[i];
+                if (p.bias != nullptr) o += p.bias[col + i];
+                if (p.accumulate) o += dst[i];
+                dst[i] = o;
+              }
+            }
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4*>(stg + lane * kStg + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
         const int col = n0 + c + cc;
+        const int row0 = m0 + mt * kBlockM + q * 32 + rsub;  // this lane's rows: row0 + 4 rr
+        if (to_ws) {
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-          const int rl = rr * 4 + rsub;
-          float4 o = *reinterpret_cast<const float4*>(stg + rl * kStg + cc);
-          const int row = m0 + mt * kBlockM + q * 32 + rl;
-          if (to_ws) {
-            *reinterpret_cast<float4*>(p.workspace + ((long long)split * p.Mpad + row) * p.Npad + col) = o;
-            continue;
-          }
-          if (row >= p.M || col >= p.N) continue;
-          const long long off = (long long)row * p.ldc + col;
-          const int nv = min(4, p.N - col);
-          float ov[4] = {o.x, o.y, o.z, o.w};
-          if (p.adam_p != nullptr) {
-            float* pp = p.adam_p + off;
-            float* pm = p.adam_m + off;
-            float* pv = p.adam_v + off;
-            if (nv == 4 && ((reinterpret_cast<uintptr_t>(pp) | reinterpret_cast<uintptr_t>(pm) | reinterpret_cast<uintptr_t>(pv)) & 15) == 0) {
-              float4 w4 = *reinterpret_cast<float4*>(pp), m4 = *reinterpret_cast<float4*>(pm), v4 = *reinterpret_cast<float4*>(pv);
-              adam_update(ov[0], w4.x, m4.x, v4.x, ac);
-              adam_update(ov[1], w4.y, m4.y, v4.y, ac);
-              adam_update(ov[2], w4.z, m4.z, v4.z, ac);
-              adam_update(ov[3], w4.w, m4.w, v4.w, ac);
-              *reinterpret_cast<float4*>(pp) = w4, *reinterpret_cast<float4*>(pm) = m4, *reinterpret_cast<float4*>(pv) = v4;
-            } else {
-              for (int i = 0; i < nv; ++i) adam_update(ov[i], pp[i], pm[i], pv[i], ac);
-            }
-            continue;
-          }
-          float* dst = p.C + off;
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (i < nv) ov[i] += p.bias[col + i];
-          }
-          if (nv == 4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-            if (p.accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(dst);
-              ov[0] += old.x, ov[1] += old.y, ov[2] += old.z, ov[3] += old.w;
-            }
-            *reinterpret_cast<float4*>(dst) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-          } else {
-            for (int i = 0; i < nv; ++i) dst[i] = p.accumulate ? dst[i] + ov[i] : ov[i];
+          for (int rr = 0; rr < 8; ++rr) {
+            const float4 o = *reinterpret_cast<const float4*>(stg + (rr * 4 + rsub) * kStg + cc);
+            *reinterpret_cast<float4*>(p.workspace + ((long long)split * p.Mpad + row0 + 4 * rr) * p.Npad + col) = o;
           }
         }
         __syncwarp();  // the staging buffer is rewritten by the next chunk
       }
     }
     tc_fence_before();
+  }
+  if constexpr (ADAM) {
+    // ======================= fused optimizer epilogue (all warps) =======================
+    // The four TMEM-drain warps stage one 128 x BN accumulator tile (= the weight-gradient tile, never written to
+    // HBM) in the idle operand ring; then every warp of the CTA takes rows of it: one warp instruction moves one
+    // 512-byte row segment of param / exp_avg / exp_avg_sq, four rows (12 loads) in flight per warp.
+    static_assert(!ADAM || BN == 128, "the fused optimizer epilogue is written for 128-wide tiles");
+    __syncwarp();  // producer / issuer warps: lane 0 ran the pipeline loop
+    const bool drain = warp >= 2 && warp < 6;
+    const int q = warp & 3;
+    if (drain) {
+      mbar_wait(&accum_bar, 0);
+      tc_fence_after();
+    }
+    float* tile = reinterpret_cast<float*>(smem);
+    const AdamCoef ac = adam_coef(p);
+    const int nwarps = blockDim.x >> 5;
+    const int col = n0 + 4 * lane;
+    const bool vec = (col + 3 < p.N) && ((p.ldc & 3) == 0) &&
+                     (((reinterpret_cast<uintptr_t>(p.adam_p) | reinterpret_cast<uintptr_t>(p.adam_m) |
+                        reinterpret_cast<uintptr_t>(p.adam_v)) & 15) == 0);
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      if (drain) {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          float v[32];
+          if (n_kb > 0) {
+            tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(mt * BN + c), v);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          float* dst = tile + (q * 32 + lane) * kTilePitch + c;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(int(blockDim.x)) : "memory");  // tile staged
+      const int row_base = m0 + mt * kBlockM;
+#pragma unroll 1
+      for (int r0 = warp; r0 < kBlockM; r0 += 4 * nwarps) {
+        if (vec) {
+          float4 w4[4], m4[4], v4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {  // all loads first
+            const int r = r0 + u * nwarps;
+            if (r < kBlockM && row_base + r < p.M) {
+              const long long off = (long long)(row_base + r) * p.ldc + col;
+              w4[u] = *reinterpret_cast<const float4*>(p.adam_p + off);
+              m4[u] = *reinterpret_cast<const float4*>(p.adam_m + off);
+              v4[u] = *reinterpret_cast<const float4*>(p.adam_v + off);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * nwarps;
+            if (r < kBlockM && row_base + r < p.M) {
+              const float4 g4 = *reinterpret_cast<const float4*>(tile + r * kTilePitch + 4 * lane);
+              adam_update(g4.x, w4[u].x, m4[u].x, v4[u].x, ac);
+              adam_update(g4.y, w4[u].y, m4[u].y, v4[u].y, ac);
+              adam_update(g4.z, w4[u].z, m4[u].z, v4[u].z, ac);
+              adam_update(g4.w, w4[u].w, m4[u].w, v4[u].w, ac);
+              const long long off = (long long)(row_base + r) * p.ldc + col;
+              *reinterpret_cast<float4*>(p.adam_p + off) = w4[u];
+              *reinterpret_cast<float4*>(p.adam_m + off) = m4[u];
+              *reinterpret_cast<float4*>(p.adam_v + off) = v4[u];
+            }
+          }
+        } else if (col < p.N) {  // ragged right edge / unaligned buffers
+          const int nv = min(4, p.N - col);
+          for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * nwarps;
+            if (r >= kBlockM || row_base + r >= p.M) continue;
+            const long long off = (long long)(row_base + r) * p.ldc + col;
+            for (int i = 0; i < nv; ++i)
+              adam_update(tile[r * kTilePitch + 4 * lane + i], p.adam_p[off + i], p.adam_m[off + i], p.adam_v[off + i], ac);
+          }
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(int(blockDim.x)) : "memory");  // tile consumed before it is overwritten
+    }
+    if (drain) tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
@@ -400,19 +482,19 @@ static int make_tmap(CUtensorMap* map, const float* base, long long rows, long l
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 
-template <int MT, int BN, bool A_MN, bool B_MN, int STAGES, int MINB>
+template <int MT, int BN, bool A_MN, bool B_MN, int STAGES, int MINB, bool ADAM = false>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
                       const GemmParams& p, cudaStream_t st) {
   constexpr int kStage = (MT * kBlockM + BN) * kBlockK * 4;
   const int smem = STAGES * kStage + 1024;
-  auto kern = gemm_tf32_kernel<MT, BN, A_MN, B_MN, STAGES, MINB>;
+  auto kern = gemm_tf32_kernel<MT, BN, A_MN, B_MN, STAGES, MINB, ADAM>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 3;
     configured = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + MT * kBlockM - 1) / (MT * kBlockM), p.split_k);
-  kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, ta2, tb2, p);
+  kern<<<grid, ADAM ? kAdamThreads : kGemmThreads, smem, st>>>(ta, tb, ta2, tb2, p);
   return 0;
 }
 
@@ -518,7 +600,13 @@ static int gemm_tf32_impl(const float* A, long long lda, const float* B, long lo
     else if (a_mn && !b_mn) rc = launch<MT, BN, true, false>(ta, tb, ta2, tb2, p, st);    \
     else rc = launch<MT, BN, true, true>(ta, tb, ta2, tb2, p, st);                        \
   } while (0)
-  if (two) CB_DISPATCH(2, 128);
+  if (adam != nullptr) {
+    // fused optimizer epilogue: instantiated for the weight-gradient layout (both operands stored with the reduction
+    // dimension as rows), 256 x 128 tiles, short K (two CTAs per SM)
+    CB_REQUIRE(a_mn && b_mn && M > 128 && p.k_blocks_per_split <= 16,
+               "cb_gemm_tf32_dw_adam: needs a_mn = b_mn = 1, M > 128 and K <= 512 (got M=%d K=%d)", M, K);
+    rc = launch_cfg<2, 128, true, true, 2, 2, true>(ta, tb, ta2, tb2, p, st);
+  } else if (two) CB_DISPATCH(2, 128);
   else if (wide) CB_DISPATCH(1, 256);
   else CB_DISPATCH(1, 128);
 #undef CB_DISPATCH

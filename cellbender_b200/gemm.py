@@ -24,6 +24,9 @@ BACKEND = "tcgen05"
 # optimizer whose update is fused into the weight-gradient GEMM epilogues during the current backward pass (set by
 # train.SVI around loss.backward(); None = gradients are written to the flat gradient buffer as usual)
 FUSED_OPT = None
+# only matrices with at least this many elements take the fused path: the epilogue needs many CTAs to stream the
+# optimizer state at HBM speed (a 512 x 512 layer has 8 tiles; its fused update is slower than the separate sweep)
+FUSED_MIN_NUMEL = 1 << 22
 
 
 def set_backend(name: str):
@@ -47,7 +50,8 @@ def _grad_target(weight: torch.Tensor):
 def fused_update_applies(w: torch.Tensor) -> bool:
     opt = FUSED_OPT
     return (opt is not None and BACKEND == "tcgen05" and getattr(w, "_cb_block", None) is not None
-            and getattr(w, "_cb_grad_view", None) is not None and w.requires_grad)
+            and getattr(w, "_cb_grad_view", None) is not None and w.requires_grad and w.numel() >= FUSED_MIN_NUMEL
+            and w.shape[0] > 128)
 
 
 def _tma_ok(t: torch.Tensor) -> bool:

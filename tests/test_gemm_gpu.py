@@ -78,3 +78,47 @@ def test_gemm_two_operand_pairs_share_the_accumulator():
     ref = _tf32_trunc(dy1).double() @ _tf32_trunc(W1[:, 4:4 + G].contiguous()).double() \
         + _tf32_trunc(dy2).double() @ _tf32_trunc(W2[:, 4:4 + G].contiguous()).double()
     assert float((out[:, :G].double() - ref).abs().max()) / float(ref.abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,off", [(512, 256, 4), (256, 512, 0), (512, 33538, 4), (33538, 512, 0), (300, 250, 0)])
+def test_weight_gradient_gemm_with_fused_clipped_adam(M, N, off):
+    """cb_gemm_tf32_dw_adam: W[:, off:off+N] -= Adam(dY^T X) inside the GEMM epilogue must equal the unfused sequence
+    (cb_gemm_tf32 into a gradient buffer, then cb_clipped_adam_step over it), element for element; columns outside
+    [off, off + N) and the padding stay untouched."""
+    from cellbender_b200 import _cabi, ops
+
+    K = 255
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    ld = ops.round_up(off + N, 4)
+    dy = torch.randn(K, ops.round_up(M, 4), device=DEV, generator=g)
+    x = torch.randn(K, ops.round_up(N, 4), device=DEV, generator=g)
+    p0 = torch.randn(M, ld, device=DEV, generator=g)
+    m0 = torch.randn(M, ld, device=DEV, generator=g) * 0.1
+    v0 = torch.rand(M, ld, device=DEV, generator=g) * 0.01
+    lr_table = torch.tensor([1e-3, 2e-3, 3e-3], device=DEV)
+    b1_table = torch.tensor([0.95, 0.9, 0.85], device=DEV)
+    step = torch.tensor([1], dtype=torch.int64, device=DEV)
+
+    # unfused reference: gradient to memory, then the flat Adam sweep over the [M, N] block (row by row)
+    grad = torch.zeros(M, ld, device=DEV)
+    ops.gemm_tf32(dy, x, M, N, K, a_mn=True, b_mn=True, out=grad[:, off:off + N], split_k=1)
+    p_ref, m_ref, v_ref = p0.clone(), m0.clone(), v0.clone()
+    pr, mr, vr, gr = (t[:, off:off + N].contiguous().reshape(-1) for t in (p_ref, m_ref, v_ref, grad))
+    step_ref = step.clone()
+    ops.clipped_adam_step(pr, gr, mr, vr, lr_table, b1_table, step_ref, beta2=0.999, eps=1e-8, clip=10.0)
+    for dst, src in ((p_ref, pr), (m_ref, mr), (v_ref, vr)):
+        dst[:, off:off + N] = src.view(M, N)
+
+    p, m, v = p0.clone(), m0.clone(), v0.clone()
+    byte = 4 * off
+    _cabi.lib().call("cb_gemm_tf32_dw_adam", dy.data_ptr(), dy.stride(0), 1, x.data_ptr(), x.stride(0), 1, ld, M, N, K,
+                     p.data_ptr() + byte, m.data_ptr() + byte, v.data_ptr() + byte, lr_table.data_ptr(), b1_table.data_ptr(), 3,
+                     step.data_ptr(), 0.999, 1e-8, 10.0, _cabi.current_stream())
+    torch.cuda.synchronize()
+    assert int(step) == 1  # read, not advanced
+    for got, ref, name in ((p, p_ref, "param"), (m, m_ref, "exp_avg"), (v, v_ref, "exp_avg_sq")):
+        diff = (got - ref).abs()
+        bad = int((diff > 1e-6 * (1 + ref.abs())).sum())
+        rows_bad = torch.nonzero((diff > 1e-6 * (1 + ref.abs())).any(dim=1)).flatten()[:8].tolist()
+        assert bad == 0, (name, bad, float(diff.max()), rows_bad)
+    assert float((p - p0).abs().max()) > 0
