@@ -87,10 +87,13 @@ class FlatClippedAdam:
         self.beta2, self.eps, self.clip = betas[1], eps, clip_norm
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)  # optimizer steps taken (device side)
         self.host_steps = 0
-        # Single-GPU training applies the update of the four G x 512 weight matrices (99 % of the parameters) inside the
-        # epilogue of their weight-gradient GEMM (cb_gemm_tf32_dw_adam): their gradients never travel to HBM and back.
-        # Data-parallel training needs the gradients for the all-reduce and switches this off (dp.attach).
-        self.fuse_weight_updates = True
+        # Optional: apply the update of the four G x 512 weight matrices (99 % of the parameters) inside the epilogue of
+        # their weight-gradient GEMM (cb_gemm_tf32_dw_adam), so that their gradients never travel to HBM and back
+        # (-25 % of a step's HBM bytes).  Correct (tests/test_gemm_gpu.py, tests/test_step_gpu.py) but OFF by default:
+        # measured on B200 (r01) the fused kernel takes 122-143 us per matrix against 55 us (GEMM) + 76 us (its share of
+        # the Adam sweep) unfused, because the co-resident CTAs run their GEMM and optimizer phases in lockstep instead
+        # of overlapping them; a persistent, TMEM-double-buffered variant is the next step.
+        self.fuse_weight_updates = False
         self._fused_done: List[tuple] = []
 
     def zero_grad(self):

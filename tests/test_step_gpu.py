@@ -251,7 +251,7 @@ def test_fused_weight_update_equals_separate_adam(use_graph):
     for k in range(2):
         for a, b, name in zip(states[True][k], states[False][k], ("param", "exp_avg", "exp_avg_sq")):
             err = float((a - b).abs().max())
-            assert err <= 1e-7 * max(1.0, float(b.abs().max())), (k, name, err)
+            assert err <= 1e-6 * max(1.0, float(b.abs().max())), (k, name, err)
     # later steps (graph replays included): the weight matrices themselves stay together
     pa, pb = states[True][-1][0], states[False][-1][0]
     for p_, o in zip(opt.params, opt.offsets):
