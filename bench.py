@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--no-posterior", action="store_true")
     ap.add_argument("--posterior-cells", type=int, default=8000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--short-warmup", action="store_true", help="profiling runs: skip the epoch-long graph warm-up")
     return ap.parse_args()
 
 
@@ -248,7 +249,7 @@ def run_b200(args):
     # step graph of every minibatch size (the last minibatch of an epoch is smaller) is captured outside the timed region
     for b in fresh_batches(max(args.warmup, 3)):
         svi.step(b)
-    while True:
+    while not args.short_warmup:
         try:
             svi.step(next(train_loader))
         except StopIteration:
