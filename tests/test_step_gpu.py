@@ -237,7 +237,13 @@ def test_fused_weight_update_equals_separate_adam(use_graph):
             blocks = [p for p in opt.params if getattr(p, "_cb_block", None) is not None]
             assert len(blocks) >= 4  # the G x 512 matrices (and the 512 x 516 / 512 x 512 hidden layers) qualify
             model.train()
-            it, snaps = iter(tl), []
+            snaps = []
+
+            def batches():
+                while True:  # the loader raises StopIteration at the end of every epoch and reshuffles
+                    yield from tl
+
+            it = batches()
             for _ in range(n_steps):
                 svi.step(next(it))
                 torch.cuda.synchronize()
