@@ -230,4 +230,93 @@ CB_HD NbpcOut nbpc_zero(float mu, float inv_alpha, float lam) {
   return o;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Exact NB(mu, alpha) (+) Poisson(lam) convolution by direct summation: NegativeBinomialPoissonConv.log_prob
+// (reference distributions/NegativeBinomialPoissonConv.py:89-154; selected by consts.USE_EXACT_LOG_PROB, off by
+// default).  L(v) = logsumexp_{k=0..max_poisson} [ Poisson(low + k; lam) + NB(v - low - k; mu, alpha) ],
+// low = clamp(min(int(lam - max_poisson/2), int(v - max_poisson)), 0), terms with a negative NB count dropped.
+// The reference's closed forms for v = 0 and v = 1 are this sum with one and two terms.
+// One lgamma triple (in fp64) starts the two pmf recurrences; every further term costs two logs.  The gradients are
+// the softmax-weighted term gradients, accumulated in the same pass (running-max rescaling).
+// ---------------------------------------------------------------------------------------------------------------
+CB_HD double digamma_f64(double x) {
+  double r = 0.0;
+  while (x < 6.0) {
+    r -= 1.0 / x;
+    x += 1.0;
+  }
+  const double f = 1.0 / (x * x);
+  return r + log(x) - 0.5 / x - f * (1.0 / 12.0 - f * (1.0 / 120.0 - f * (1.0 / 252.0 - f * (1.0 / 240.0 - f / 132.0))));
+}
+
+template <bool GRAD>
+CB_HD NbpcOut nbpc_exact_eval(float v, float mu, float alpha, float lam, int max_poisson) {
+  NbpcOut o;
+  o.dmu = 0.f, o.dlam = 0.f, o.dalpha = 0.f;
+  int low = int(lam - 0.5f * float(max_poisson));
+  const int low2 = int(v - float(max_poisson));
+  low = low < low2 ? low : low2;
+  low = low < 0 ? 0 : low;
+  const int vi = int(v);
+  if (low > vi) {  // every NB count would be negative: the reference's table is all -inf
+    o.L = -INFINITY;
+    return o;
+  }
+  const int n_terms = (vi - low < max_poisson ? vi - low : max_poisson) + 1;
+  const double a = alpha, m = mu, l = lam;
+  const double log_l = log(l), lar = log(a) - log(a + m), lmr = log(m) - log(a + m);
+  double nb = double(vi - low), pois = double(low);
+  // first term, directly
+  double lp = pois * log_l - l - lgamma(pois + 1.0);
+  double ln = lgamma(nb + a) - lgamma(nb + 1.0) - lgamma(a) + a * lar + nb * lmr;
+  double dig = 0.0;  // psi(nb + alpha) - psi(alpha)
+  if (GRAD) {
+    if (nb <= 64.0) {
+      for (int i = 0; i < int(nb); ++i) dig += 1.0 / (a + double(i));
+    } else {
+      dig = digamma_f64(nb + a) - digamma_f64(a);
+    }
+  }
+  double mx = lp + ln, s = 1.0;
+  double gl = 0.0, gm = 0.0, ga = 0.0;
+  const double inv_apm = 1.0 / (a + m);
+  if (GRAD) {
+    gl = pois / l - 1.0;
+    gm = nb / m - (a + nb) * inv_apm;
+    ga = dig + lar + 1.0 - (a + nb) * inv_apm;
+  }
+  for (int k = 1; k < n_terms; ++k) {
+    // Poisson(pois + 1) from Poisson(pois); NB(nb - 1) from NB(nb)
+    lp += log_l - double(logf(float(pois + 1.0)));
+    ln -= double(logf(float((nb - 1.0 + a) / nb))) + lmr;
+    if (GRAD) dig -= 1.0 / (a + nb - 1.0);
+    pois += 1.0;
+    nb -= 1.0;
+    const double t = lp + ln;
+    double w;
+    if (t > mx) {
+      const double r = exp(mx - t);
+      s = s * r + 1.0;
+      if (GRAD) gl *= r, gm *= r, ga *= r;
+      mx = t;
+      w = 1.0;
+    } else {
+      w = exp(t - mx);
+      s += w;
+    }
+    if (GRAD) {
+      gl += w * (pois / l - 1.0);
+      gm += w * (nb / m - (a + nb) * inv_apm);
+      ga += w * (dig + lar + 1.0 - (a + nb) * inv_apm);
+    }
+  }
+  o.L = float(mx + log(s));
+  if (GRAD) {
+    const double inv_s = 1.0 / s;
+    o.dlam = float(gl * inv_s), o.dmu = float(gm * inv_s), o.dalpha = float(ga * inv_s);
+  }
+  return o;
+}
+
 }  // namespace cb

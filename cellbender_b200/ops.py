@@ -114,8 +114,11 @@ def _as3(*ts):
 
 
 class _NbpcApproxLogProb(torch.autograd.Function):
+    """log_prob of NegativeBinomialPoissonConvApprox (max_poisson < 0) or of the exact convolution
+    NegativeBinomialPoissonConv (max_poisson >= 0: number of Poisson terms - 1)."""
+
     @staticmethod
-    def forward(ctx, value, mu, alpha, lam):
+    def forward(ctx, value, mu, alpha, lam, max_poisson=-1):
         _req_cuda(value, mu, alpha, lam)
         args = [t.float() for t in (value, mu, alpha, lam)]
         shape, shape3, args = _as3(*args)
@@ -126,10 +129,14 @@ class _NbpcApproxLogProb(torch.autograd.Function):
         out = torch.empty(shape3, dtype=torch.float32, device=value.device)
         flag = torch.zeros(1, dtype=torch.int32, device=value.device)
         E, B, G = shape3
-        _cabi.lib().call(
-            "cb_nbpc_approx_log_prob_fwd", ptr(packed[0][0]), ctypes.addressof(sarr[0]), ptr(packed[1][0]),
-            ctypes.addressof(sarr[1]), ptr(packed[2][0]), ctypes.addressof(sarr[2]), ptr(packed[3][0]),
-            ctypes.addressof(sarr[3]), ptr(out), E, B, G, ptr(flag), current_stream())
+        operands = (ptr(packed[0][0]), ctypes.addressof(sarr[0]), ptr(packed[1][0]), ctypes.addressof(sarr[1]),
+                    ptr(packed[2][0]), ctypes.addressof(sarr[2]), ptr(packed[3][0]), ctypes.addressof(sarr[3]))
+        if max_poisson < 0:
+            _cabi.lib().call("cb_nbpc_approx_log_prob_fwd", *operands, ptr(out), E, B, G, ptr(flag), current_stream())
+        else:
+            _cabi.lib().call("cb_nbpc_exact_log_prob_fwd", *operands, ptr(out), E, B, G, int(max_poisson), ptr(flag),
+                             current_stream())
+        ctx.max_poisson = max_poisson
         ctx.save_for_backward(*[p[0] for p in packed])
         ctx.strides = [p[1] for p in packed]
         ctx.shape, ctx.shape3 = shape, shape3
@@ -146,15 +153,17 @@ class _NbpcApproxLogProb(torch.autograd.Function):
         E, B, G = ctx.shape3
         go = grad_out.reshape(ctx.shape3).contiguous().float()
         dmu, dlam, dal = (torch.empty(ctx.shape3, dtype=torch.float32, device=go.device) for _ in range(3))
-        _cabi.lib().call(
-            "cb_nbpc_approx_log_prob_bwd", ptr(v3), ctypes.addressof(sarr[0]), ptr(m3), ctypes.addressof(sarr[1]),
-            ptr(a3), ctypes.addressof(sarr[2]), ptr(l3), ctypes.addressof(sarr[3]), ptr(go), ptr(dmu), ptr(dlam),
-            ptr(dal), E, B, G, current_stream())
+        operands = (ptr(v3), ctypes.addressof(sarr[0]), ptr(m3), ctypes.addressof(sarr[1]), ptr(a3), ctypes.addressof(sarr[2]),
+                    ptr(l3), ctypes.addressof(sarr[3]), ptr(go), ptr(dmu), ptr(dlam), ptr(dal), E, B, G)
+        if ctx.max_poisson < 0:
+            _cabi.lib().call("cb_nbpc_approx_log_prob_bwd", *operands, current_stream())
+        else:
+            _cabi.lib().call("cb_nbpc_exact_log_prob_bwd", *operands, int(ctx.max_poisson), current_stream())
 
         def red(g, shp):
             return g.reshape(ctx.shape).sum_to_size(shp) if tuple(shp) != tuple(ctx.shape) else g.reshape(ctx.shape)
 
-        return None, red(dmu, ctx.in_shapes[1]), red(dal, ctx.in_shapes[2]), red(dlam, ctx.in_shapes[3])
+        return None, red(dmu, ctx.in_shapes[1]), red(dal, ctx.in_shapes[2]), red(dlam, ctx.in_shapes[3]), None
 
 
 def nbpc_approx_log_prob(value, mu, alpha, lam, check_nan: bool = True):
@@ -162,6 +171,17 @@ def nbpc_approx_log_prob(value, mu, alpha, lam, check_nan: bool = True):
     reference (...ConvApprox.py:105-143).  Raises NanException like the reference when a NaN appears."""
     alpha = torch.as_tensor(alpha, dtype=torch.float32, device=mu.device)
     out = _NbpcApproxLogProb.apply(value, mu, alpha, lam)
+    if check_nan and bool(torch.isnan(out.sum())):
+        bad = [n for n, t in (("mu", mu), ("alpha", alpha), ("lam", lam)) if bool(torch.isnan(t.log().sum()))]
+        raise NanException(param=", ".join(bad))
+    return out
+
+
+def nbpc_exact_log_prob(value, mu, alpha, lam, max_poisson: int = 100, check_nan: bool = True):
+    """log_prob of NegativeBinomialPoissonConv(mu, alpha, lam, max_poisson) at `value`: the exact NB (+) Poisson
+    convolution (reference distributions/NegativeBinomialPoissonConv.py:89-154), differentiable in mu, alpha, lam."""
+    alpha = torch.as_tensor(alpha, dtype=torch.float32, device=mu.device)
+    out = _NbpcApproxLogProb.apply(value, mu, alpha, lam, int(max_poisson))
     if check_nan and bool(torch.isnan(out.sum())):
         bad = [n for n, t in (("mu", mu), ("alpha", alpha), ("lam", lam)) if bool(torch.isnan(t.log().sum()))]
         raise NanException(param=", ".join(bad))

@@ -50,6 +50,19 @@ int cb_nbpc_approx_log_prob_bwd(const float* value, const long long* sv, const f
                                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * A8  NegativeBinomialPoissonConv.log_prob(value)  (distributions/NegativeBinomialPoissonConv.py:89-154): the exact
+ * NB (+) Poisson convolution, logsumexp over max_poisson + 1 (reference: 101) Poisson counts starting at
+ * clamp(min(int(lam - max_poisson/2), int(value - max_poisson)), 0); used when consts.USE_EXACT_LOG_PROB is set.
+ * Same operand conventions as cb_nbpc_approx_log_prob_fwd/_bwd.                                                */
+int cb_nbpc_exact_log_prob_fwd(const float* value, const long long* sv, const float* mu, const long long* sm,
+                               const float* alpha, const long long* sa, const float* lam, const long long* sl,
+                               float* out, int E, int B, int G, int max_poisson, int* nan_flag, void* stream);
+int cb_nbpc_exact_log_prob_bwd(const float* value, const long long* sv, const float* mu, const long long* sm,
+                               const float* alpha, const long long* sa, const float* lam, const long long* sl,
+                               const float* grad_out, float* dmu, float* dlam, float* dalpha, int E, int B, int G,
+                               int max_poisson, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * A5(softmax)+A6+A7+K7  observation terms of the ELBO, forward and backward fused.  Replaces, per svi.step:
  * Decoder softmax (vae/decoder.py:46-47), calculate_mu/calculate_lambda with y enumerated (model.py:25-85,308-320),
  * NBPCapprox(...).to_event(1).log_prob(x) (model.py:338-346), the Poisson "obs_empty" site (model.py:374-398) and

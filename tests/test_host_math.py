@@ -104,3 +104,62 @@ def test_noise_window_fp32_math_vs_float64(hostlib, golden_dir, tag):
     keep = ref >= -10.0  # the posterior keeps log prob >= -10 (posterior.py:426,533)
     err = np.abs(mine - ref)[keep] / np.maximum(np.abs(ref[keep]), 1.0)
     assert err.max() < 1e-5, err.max()
+
+
+def test_nbpc_exact_convolution_vs_float64_and_reference_golden(hostlib, golden_dir):
+    """nbpc_exact_eval (the kernel math of cb_nbpc_exact_log_prob_fwd/_bwd, run on the host) against (a) a float64
+    evaluation of NegativeBinomialPoissonConv.log_prob's definition (scipy gammaln / logsumexp over the same 101-term
+    window), (b) the unmodified reference's own output on the golden inputs (which evaluates its count tables' lgamma
+    in float32, ...Conv.py:138-141, hence the looser bound for large counts), (c) float64 autograd of the oracle
+    restatement for the three gradients."""
+    from scipy.special import gammaln, logsumexp
+
+    from oracle import nbpc as onb
+
+    g = np.load(os.path.join(golden_dir, "nbpc.npz"))
+    mask = g["exact_mask"].astype(bool)
+    v, mu, al, lam = (np.ascontiguousarray(g[k][mask], dtype=np.float32) for k in ("value", "mu", "alpha", "lam"))
+    n = v.size
+    assert n > 200 and (v == 0).any() and (v == 1).any() and (v > 100).any()
+    L, dmu, dlam, dal = (np.zeros(n, np.float32) for _ in range(4))
+    hostlib.host_nbpc_exact(n, _p(v), _p(mu), _p(al), _p(lam), 100, _p(L), _p(dmu), _p(dlam), _p(dal))
+
+    v64, mu64, al64, lam64 = (a.astype(np.float64) for a in (v, mu, al, lam))
+    low = np.clip(np.minimum((lam - np.float32(50.0)).astype(np.int32), (v - np.float32(100.0)).astype(np.int32)), 0, None)
+    k = np.arange(101)[None, :]
+    pois = low[:, None] + k
+    nb = v64[:, None] - pois
+    ok = nb >= 0
+    nbc = np.where(ok, nb, 0.0)
+    a_, m_, l_ = al64[:, None], mu64[:, None], lam64[:, None]
+    terms = (pois * np.log(l_) - l_ - gammaln(pois + 1.0)
+             + gammaln(nbc + a_) - gammaln(nbc + 1.0) - gammaln(a_) + a_ * (np.log(a_) - np.log(a_ + m_))
+             + nbc * (np.log(m_) - np.log(a_ + m_)))
+    ref = logsumexp(np.where(ok, terms, -np.inf), axis=1)
+    err = np.abs(L - ref) / np.maximum(np.abs(ref), 1.0)
+    assert err.max() < 2e-6, err.max()
+
+    ref_golden = g["exact_f64"]  # already restricted to exact_mask: the reference itself (float32 lgamma of the count tables inside)
+    err_g = np.abs(L - ref_golden) / np.maximum(np.abs(ref_golden), 1.0)
+    assert err_g[v <= 64].max() < 1e-5, err_g[v <= 64].max()
+    assert err_g.max() < 1e-3, err_g.max()
+
+    # gradients: softmax-weighted term gradients in float64 (analytic), all counts
+    from scipy.special import digamma
+
+    wgt = np.where(ok, np.exp(terms - ref[:, None]), 0.0)
+    g_lam = (wgt * (pois / l_ - 1.0)).sum(1)
+    g_mu = (wgt * (nbc / m_ - (a_ + nbc) / (a_ + m_))).sum(1)
+    g_al = (wgt * (digamma(nbc + a_) - digamma(a_) + np.log(a_ / (a_ + m_)) + 1.0 - (a_ + nbc) / (a_ + m_))).sum(1)
+    for name, mine, r in (("dmu", dmu, g_mu), ("dlam", dlam, g_lam), ("dalpha", dal, g_al)):
+        e = np.abs(mine - r) / np.maximum(np.abs(r), 1e-3)
+        assert e.max() < 1e-4, (name, e.max())  # fp32 logs inside the 101-term pmf recurrences
+    # and the oracle restatement's float64 autograd agrees where its float32 count-table lgamma is harmless
+    t = lambda a: torch.tensor(a, dtype=torch.float64, requires_grad=True)
+    mu_t, al_t, lam_t = t(mu64), t(al64), t(lam64)
+    onb.nbpc_exact_log_prob(torch.tensor(v64), mu_t, al_t, lam_t).sum().backward()
+    small = v <= 16
+    for name, mine, r in (("dmu", dmu, mu_t.grad), ("dlam", dlam, lam_t.grad), ("dalpha", dal, al_t.grad)):
+        r = r.numpy()
+        e = np.abs(mine - r) / np.maximum(np.abs(r), 1e-3)
+        assert e[small].max() < 1e-3, (name, e[small].max())

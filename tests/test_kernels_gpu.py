@@ -595,3 +595,38 @@ def test_encoder_features_match_reference_formulas(ops):
     np.testing.assert_allclose(e.cpu().numpy(), e_ref.numpy(), rtol=2e-6, atol=1e-6)
     p0, e0 = ops.encoder_features(feats.to(DEV), z.to(DEV), None)
     assert float(p0[:, 2].abs().max()) == 0.0 and float(e0[:, 2].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------- exact NB (+) Poisson convolution
+def test_nbpc_exact_log_prob_vs_reference_golden_and_float64(ops, golden_dir):
+    """cb_nbpc_exact_log_prob_fwd/_bwd (A8: NegativeBinomialPoissonConv.log_prob, consts.USE_EXACT_LOG_PROB) against the
+    unmodified reference's output on the golden inputs and float64 autograd of the oracle restatement, with the
+    broadcasting the reference uses ([2, B, G] rates, [B, G] counts, scalar alpha)."""
+    g = np.load(os.path.join(golden_dir, "nbpc.npz"))
+    mask = g["exact_mask"].astype(bool)
+    v, mu, al, lam = (torch.tensor(np.ascontiguousarray(g[k][mask], dtype=np.float32), device=DEV) for k in ("value", "mu", "alpha", "lam"))
+    out = ops.nbpc_exact_log_prob(v, mu, al, lam)
+    ref = g["exact_f64"]
+    err = np.abs(out.cpu().numpy() - ref) / np.maximum(np.abs(ref), 1.0)
+    small = (v <= 64).cpu().numpy()
+    assert err[small].max() < 1e-5, err[small].max()
+    assert err.max() < 1e-3, err.max()  # the reference evaluates lgamma of its count tables in float32 (...Conv.py:138-141)
+
+    gen = torch.Generator().manual_seed(0)
+    B, G = 6, 40
+    x = torch.poisson(torch.rand(B, G, generator=gen) * 6.0, generator=gen)
+    mu2 = (torch.rand(2, B, G, generator=gen) * 4 + 0.05).double().requires_grad_(True)
+    lam2 = (torch.rand(2, B, G, generator=gen) * 2 + 0.01).double().requires_grad_(True)
+    alpha = torch.tensor(3.7, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(2, B, G, generator=gen, dtype=torch.float64)
+    ref2 = onb.nbpc_exact_log_prob(x.double(), mu2, alpha, lam2)
+    (ref2 * w).sum().backward()
+    mu_c, lam_c = mu2.detach().float().to(DEV).requires_grad_(True), lam2.detach().float().to(DEV).requires_grad_(True)
+    al_c = alpha.detach().float().to(DEV).requires_grad_(True)
+    got = ops.nbpc_exact_log_prob(x.to(DEV), mu_c, al_c, lam_c)
+    assert got.shape == (2, B, G)
+    (got * w.float().to(DEV)).sum().backward()
+    np.testing.assert_allclose(got.detach().cpu().numpy(), ref2.detach().numpy(), rtol=1e-5, atol=1e-5)
+    for mine, r in ((mu_c.grad, mu2.grad), (lam_c.grad, lam2.grad), (al_c.grad, alpha.grad)):
+        scale = float(r.abs().max())
+        assert float((mine.double().cpu() - r).abs().max()) <= 1e-4 * scale

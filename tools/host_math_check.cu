@@ -29,3 +29,12 @@ extern "C" void host_nbpc_zero(int n, const float* mu, const float* alpha, const
     L[i] = o.L, dmu[i] = o.dmu, dlam[i] = o.dlam, dalpha[i] = o.dalpha;
   }
 }
+
+// the exact NB (+) Poisson convolution (NegativeBinomialPoissonConv.log_prob)
+extern "C" void host_nbpc_exact(int n, const float* v, const float* mu, const float* alpha, const float* lam, int max_poisson,
+                                float* L, float* dmu, float* dlam, float* dalpha) {
+  for (int i = 0; i < n; ++i) {
+    cb::NbpcOut o = cb::nbpc_exact_eval<true>(v[i], mu[i], alpha[i], lam[i], max_poisson);
+    L[i] = o.L, dmu[i] = o.dmu, dlam[i] = o.dlam, dalpha[i] = o.dalpha;
+  }
+}
