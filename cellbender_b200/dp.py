@@ -44,8 +44,41 @@ def attach(svi, world_size: int):
     torch.manual_seed(1234 + 104729 * rank)
     torch.cuda.manual_seed(1234 + 104729 * rank)
     svi.after_backward = lambda opt: dist.all_reduce(opt.flat_g, op=dist.ReduceOp.SUM)
+    if getattr(getattr(svi.optim, "flat_g", None), "is_cuda", False):
+        svi.optim.fuse_weight_updates = False  # the gradients are needed for the exchange
+        svi.exchange_and_step = lambda opt: allreduce_and_step(opt)
     svi.sync_offsets = lambda: broadcast_encoder_offsets(svi.model)
     return svi
+
+
+def chunk_bounds(n: int, n_chunks: int, align: int = 4):
+    """[(begin, end)] covering [0, n) in n_chunks nearly equal pieces whose interior boundaries are multiples of
+    ``align`` elements (16-byte alignment of the fp32 buffers for the vectorised Adam kernel)."""
+    cuts = [0] + [min(n, (i * n // n_chunks) // align * align) for i in range(1, n_chunks)] + [n]
+    return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+
+@torch.no_grad()
+def allreduce_and_step(opt, n_chunks: int = 8):
+    """The exchange step of data-parallel training, pipelined: the flat gradient buffer is all-reduced in ``n_chunks``
+    pieces (queued back to back on NCCL's stream) and the ClippedAdam sweep of piece i runs on the compute stream as
+    soon as piece i has arrived, i.e. while pieces i+1.. are still on the NVLink fabric.  Same arithmetic as
+    ``all_reduce(flat_g)`` followed by ``opt.step()``."""
+    from ._cabi import current_stream, lib
+
+    if not opt.constant_learning_rate and opt.host_steps >= opt.total_steps:
+        raise ValueError(f"Tried to step {opt.host_steps + 1} times. The specified number of total steps is {opt.total_steps}")
+    bounds = chunk_bounds(opt.n, n_chunks)
+    works = [dist.all_reduce(opt.flat_g[a:b], op=dist.ReduceOp.SUM, async_op=True) for a, b in bounds]
+    L, st = lib(), current_stream()
+    tab = (opt.lr_table.data_ptr(), opt.beta1_table.data_ptr(), opt.lr_table.numel(), opt.step_count.data_ptr(),
+           float(opt.beta2), float(opt.eps), float(opt.clip))
+    for i, ((a, b), w) in enumerate(zip(bounds, works)):
+        w.wait()  # makes the compute stream wait for this piece only
+        at = lambda t: t.data_ptr() + 4 * a
+        L.call("cb_clipped_adam_range", at(opt.flat_p), at(opt.flat_g), at(opt.flat_m), at(opt.flat_v), b - a, *tab,
+               1 if i == len(bounds) - 1 else 0, st)
+    opt.host_steps += 1
 
 
 @torch.no_grad()

@@ -52,6 +52,7 @@ class SVI:
         self._graphs = {}
         self._eager_steps = 0
         self.after_backward = None  # hook(optim): e.g. the data-parallel gradient all-reduce (dp.attach)
+        self.exchange_and_step = None  # hook(optim): all-reduce pipelined with the optimizer sweep (dp.attach)
 
     def _ambient_unit_vector(self) -> torch.Tensor:
         """x_ambient / ||x_ambient||_2 of EncodeNonZLatents.forward (vae/encoder.py:266-270); the d_empty factor
@@ -83,10 +84,16 @@ class SVI:
 
     def _step_eager(self, batch) -> torch.Tensor:
         loss = self._forward_backward(batch)
+        self._exchange_and_step()
+        return loss
+
+    def _exchange_and_step(self):
+        if self.exchange_and_step is not None:
+            self.exchange_and_step(self.optim)  # chunked all-reduce overlapped with the Adam sweep of earlier chunks
+            return
         if self.after_backward is not None:
             self.after_backward(self.optim)
         self.optim.step()
-        return loss
 
     def step(self, batch: MiniBatch) -> torch.Tensor:
         """One training step; returns the loss (-ELBO, summed over the minibatch) as a 0-dim device tensor."""
@@ -107,8 +114,7 @@ class SVI:
         _cabi.lib().launch_count += n_launch  # kernels of ours inside the replayed graph
         if self.after_backward is not None:
             # data parallel: the gradient all-reduce (NCCL) and the fused Adam run eagerly between graph replays
-            self.after_backward(self.optim)
-            self.optim.step()
+            self._exchange_and_step()
         else:
             self.optim.host_steps += 1
         return loss

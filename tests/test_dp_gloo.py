@@ -55,6 +55,15 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def test_chunk_bounds_cover_the_buffer_with_aligned_cuts():
+    for n, k in ((69_441_234, 8), (1000, 8), (7, 8), (4096, 1), (17, 3)):
+        b = dp.chunk_bounds(n, k)
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(x[1] == y[0] for x, y in zip(b[:-1], b[1:]))
+        assert all(x[0] % 4 == 0 for x in b)
+        assert all(x[1] > x[0] for x in b)
+
+
 def test_two_rank_exchange_on_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
