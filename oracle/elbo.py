@@ -131,7 +131,8 @@ def elbo(x: torch.Tensor, params: Dict[str, torch.Tensor], buffers: Dict[str, to
     # ---------------- guide (model.py:447-574) ----------------
     phi_conc, phi_rate = ps["phi_loc"].pow(2) / ps["phi_scale"].pow(2), ps["phi_loc"] / ps["phi_scale"].pow(2)
     phi = gamma_rsample(phi_conc, phi_rate, noise["phi"])
-    rho = beta_rsample(ps["rho_alpha"], ps["rho_beta"], noise["rho"])
+    include_rho = model_type in ("full", "swapping")  # model.py:140-141: rho exists only for these model types
+    rho = beta_rsample(ps["rho_alpha"], ps["rho_beta"], noise["rho"]) if include_rho else torch.zeros(x.shape[0], dtype=dt, device=x.device)
     d_empty = torch.exp(ps["d_empty_loc"] + ps["d_empty_scale"] * noise["d_empty"])
     zz = ovae.encode_z(x, sub("enc_z."))
     enc = ovae.encode_nonz(x, chi_ambient.detach(), zz["loc"].detach(), sub("enc_o."), d_empty_loc=ps["d_empty_loc"].detach(),
@@ -159,8 +160,9 @@ def elbo(x: torch.Tensor, params: Dict[str, torch.Tensor], buffers: Dict[str, to
     t["z"] = (Normal(0.0, 1.0).log_prob(z).sum(-1).sum() - (q1 * Normal(zz["loc"], zz["scale"]).log_prob(z).sum(-1)).sum())
     t["d_cell"] = (LogNormal(d_cell_loc_prior, c(cfg["d_cell_scale_prior"])).log_prob(d_cell)
                    - LogNormal(d_cell_loc_gated, ps["d_cell_scale"]).log_prob(d_cell)).sum()
-    t["rho"] = (Beta(c(cfg["rho_alpha_prior"]), c(cfg["rho_beta_prior"])).log_prob(rho)
-                - Beta(ps["rho_alpha"], ps["rho_beta"]).log_prob(rho)).sum()
+    if include_rho:
+        t["rho"] = (Beta(c(cfg["rho_alpha_prior"]), c(cfg["rho_beta_prior"])).log_prob(rho)
+                    - Beta(ps["rho_alpha"], ps["rho_beta"]).log_prob(rho)).sum()
     t["epsilon"] = (Gamma(eps_prior, eps_prior).log_prob(epsilon) - Gamma(eps_gated * eps_prior, eps_prior).log_prob(epsilon)).sum()
     t["d_empty"] = (LogNormal(c(cfg["d_empty_loc_prior"]), c(cfg["d_empty_scale_prior"])).log_prob(d_empty)
                     - LogNormal(ps["d_empty_loc"], ps["d_empty_scale"]).log_prob(d_empty)).sum()
