@@ -206,6 +206,72 @@ __global__ void __launch_bounds__(256) segment_estimate_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// PRq posterior regularisation (reference posterior.py:1002-1225): per m-segment
+//   target = log(mean + alpha * std) of the noise-count posterior (dense column index c as the count, fp32 c times
+//            fp64 probabilities, as _log_mean_plus_alpha_std evaluates it)
+//   beta   = bisection on [-100, 100] (torch_binary_search, posterior.py:1654-1746: fp32 bracket, midpoint, stop when
+//            |violation| < tol, lower bound moves when violation < -tol, upper when > tol, at most max_iter rounds) of
+//            violation(beta) = LSE_c(log n_c + lp_c + beta n_c) - LSE_c(lp_c + beta n_c) - target,  n_c = c + offset_m
+//            (n_c, log n_c and beta n_c in fp32, the sums in fp64: the reference's dtype flow)
+//   output = lp_c + beta n_c - LSE_c(lp_c + beta n_c);  keep[entry] = exp(output) != 0 in fp64.
+// The reference iterates all segments of a chunk until ALL have converged; a converged segment's bracket no longer
+// moves, so per-segment loops give the same beta.  One thread per segment, at most ~20 entries each.
+__global__ void __launch_bounds__(256) prq_regularize_kernel(
+    const long long* __restrict__ m, const int* __restrict__ c, const float* __restrict__ lp,
+    const long long* __restrict__ seg_start, long long n_seg, long long n_entries, const long long* __restrict__ off_m,
+    const int* __restrict__ off_v, long long n_off, double alpha, double tol, int max_iter, double* __restrict__ log_target,
+    float* __restrict__ beta_out, double* __restrict__ lp_out, int* __restrict__ keep) {
+  const long long sidx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (sidx >= n_seg) return;
+  const long long a = seg_start[sidx];
+  const long long b = (sidx + 1 < n_seg) ? seg_start[sidx + 1] : n_entries;
+  const int off = lookup_offset(off_m, off_v, n_off, m[a]);
+  double mean = 0.0;
+  for (long long i = a; i < b; ++i) mean += double(float(c[i])) * exp(double(lp[i]));
+  double var = 0.0;
+  for (long long i = a; i < b; ++i) {
+    const double d = double(float(c[i])) - mean;
+    var += d * d * exp(double(lp[i]));
+  }
+  const double target = log(mean + alpha * sqrt(var));
+  if (log_target != nullptr) log_target[sidx] = target;
+
+  float lo = -100.0f, hi = 100.0f, beta = 0.0f;
+  for (int it = 0; it < max_iter; ++it) {
+    beta = (lo + hi) * 0.5f;
+    double mx_n = -INFINITY, mx_d = -INFINITY;
+    for (long long i = a; i < b; ++i) {
+      const float n = float(c[i] + off);
+      const double td = double(lp[i]) + double(beta * n), tn = double(logf(n)) + td;
+      mx_n = fmax(mx_n, tn), mx_d = fmax(mx_d, td);
+    }
+    double s_n = 0.0, s_d = 0.0;
+    for (long long i = a; i < b; ++i) {
+      const float n = float(c[i] + off);
+      const double td = double(lp[i]) + double(beta * n), tn = double(logf(n)) + td;
+      if (mx_n > -INFINITY) s_n += exp(tn - mx_n);
+      s_d += exp(td - mx_d);
+    }
+    const double lse_n = (mx_n > -INFINITY) ? mx_n + log(s_n) : -INFINITY;
+    const double outcome = lse_n - (mx_d + log(s_d)) - target;  // may be inf / nan exactly as in torch
+    if (fabs(0.0 - outcome) < tol) break;
+    if (outcome < -tol) lo = beta;
+    if (outcome > tol) hi = beta;
+  }
+  if (beta_out != nullptr) beta_out[sidx] = beta;
+  double mx = -INFINITY;
+  for (long long i = a; i < b; ++i) mx = fmax(mx, double(lp[i]) + double(beta * float(c[i] + off)));
+  double z = 0.0;
+  for (long long i = a; i < b; ++i) z += exp(double(lp[i]) + double(beta * float(c[i] + off)) - mx);
+  const double lse = mx + log(z);
+  for (long long i = a; i < b; ++i) {
+    const double v = double(lp[i]) + double(beta * float(c[i] + off)) - lse;
+    lp_out[i] = v;
+    keep[i] = (exp(v) != 0.0) ? 1 : 0;
+  }
+}
+
 // CSR row pointer of the [n_rows, n_cols] output: indptr[r] = lower_bound(seg_m, r * n_cols)
 __global__ void __launch_bounds__(256) csr_indptr_kernel(const long long* __restrict__ seg_m, long long n_seg,
                                                          long long n_rows, long long n_cols,
@@ -349,6 +415,18 @@ extern "C" int cb_segment_estimate(int mode, const long long* m, const int* c, c
   cb::segment_estimate_kernel<<<cb::blocks_for(n_seg), 256, 0, (cudaStream_t)stream>>>(
       mode, m, c, lp, seg_start, n_seg, n_entries, off_m, off_v, n_off, q, n_cols, seed, seg_m, out_i, out_f, map_pos);
   return cb::check_launch("cb_segment_estimate");
+}
+
+extern "C" int cb_prq_regularize(const long long* m, const int* c, const float* lp, const long long* seg_start,
+                                 long long n_seg, long long n_entries, const long long* off_m, const int* off_v,
+                                 long long n_off, double alpha, double target_tolerance, int max_iterations,
+                                 double* log_target, float* beta_out, double* lp_out, int* keep, void* stream) {
+  if (n_seg == 0) return 0;
+  CB_REQUIRE(target_tolerance > 0.0 && max_iterations > 0, "cb_prq_regularize: target_tolerance should be > 0.");
+  cb::prq_regularize_kernel<<<cb::blocks_for(n_seg), 256, 0, (cudaStream_t)stream>>>(
+      m, c, lp, seg_start, n_seg, n_entries, off_m, off_v, n_off, alpha, target_tolerance, max_iterations, log_target,
+      beta_out, lp_out, keep);
+  return cb::check_launch("cb_prq_regularize");
 }
 
 extern "C" int cb_csr_from_segments(const long long* seg_m, long long n_seg, long long n_rows, long long n_cols,

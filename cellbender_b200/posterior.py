@@ -246,6 +246,26 @@ class Posterior:
             self._device_posterior = post
         return post
 
+    # ---- posterior regularisation (posterior.py:332-378) ----------------------------------------------------
+    def regularize_posterior(self, regularization, **kwargs) -> sp.coo_matrix:
+        """Do posterior regularization (``regularization`` = regularization.PRq); caches like the reference."""
+        cached = self._noise_count_regularized_posterior_kwargs
+        if cached is not None:
+            same = all((v == regularization.name()) if k == "method" else (k in kwargs and kwargs[k] == v)
+                       for k, v in cached.items())
+            if same:
+                logger.debug("Regularized posterior is already cached")
+                return self._noise_count_regularized_posterior_coo
+        if self._noise_count_posterior_coo is None:
+            self.cell_noise_count_posterior_coo()
+        self._noise_count_regularized_posterior_coo = regularization.regularize(
+            noise_count_posterior_coo=self._noise_count_posterior_coo,
+            noise_offsets=self._noise_count_posterior_coo_offsets, index_converter=self.index_converter, **kwargs)
+        kwargs.update({"method": regularization.name()})
+        kwargs.pop("raw_count_matrix", None)
+        self._noise_count_regularized_posterior_kwargs = kwargs
+        return self._noise_count_regularized_posterior_coo
+
     # ---- denoised counts (posterior.py:282-330) --------------------------------------------------------------
     def compute_denoised_counts(self, estimator_constructor: "type[EstimationMethod]", **kwargs) -> sp.csc_matrix:
         if self._noise_count_posterior_coo is None and self._device_posterior is None:

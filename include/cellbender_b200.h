@@ -276,6 +276,14 @@ int cb_segment_estimate(int mode, const long long* m, const int* c, const float*
                         long long* map_pos, void* stream);
 int cb_csr_from_segments(const long long* seg_m, long long n_seg, long long n_rows, long long n_cols, long long* indptr,
                          int* col, void* stream);
+/* PRq posterior regularisation (posterior.py:1002-1225: PRq._compute_log_target_dict, torch_binary_search over
+ * PRq._get_alpha_log_constraint_violation_given_beta, renormalisation) over the (m, c)-sorted posterior COO, one
+ * thread per m-segment.  log_target[n_seg] (may be NULL) = log(mean + alpha std); beta_out[n_seg] (may be NULL);
+ * lp_out[n_entries] = regularised log prob (fp64 like the reference); keep[n_entries] = exp(lp_out) != 0.        */
+int cb_prq_regularize(const long long* m, const int* c, const float* lp, const long long* seg_start, long long n_seg,
+                      long long n_entries, const long long* off_m, const int* off_v, long long n_off, double alpha,
+                      double target_tolerance, int max_iterations, double* log_target, float* beta_out, double* lp_out,
+                      int* keep, void* stream);
 int cb_mckp_gene_deficit(const long long* seg_m, const int* map_val, long long n_seg, const double* target,
                          long long n_genes, long long* gene_sum, long long* deficit, void* stream);
 int cb_mckp_candidates(const long long* m, const int* c, const float* lp, const int* seg_of, const long long* map_pos,

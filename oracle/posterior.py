@@ -108,3 +108,58 @@ def posterior_coo_for_batch(data, samples, barcode_inds_all, gene_inds_all, tota
     off = off.numpy().astype(np.int64)
     offsets: Dict[int, int] = {int(k): int(v) for k, v in zip(m[off != 0], off[off != 0])}
     return m, c_i.numpy().astype(np.int32), lp.numpy(), offsets
+
+
+# ----------------------------------------------------------------------------------------------------
+# PRq posterior regularisation (posterior.py:1002-1225) and torch_binary_search (posterior.py:1654-1746),
+# restated per m-segment in numpy.  Pinned by tests/golden/prq.npz (unmodified reference, tools/make_golden.py).
+# dtype flow of the reference: dense log prob float64; counts n_c = c + offset, log n_c and beta * n_c float32;
+# bisection bracket float32; target log(mean + alpha std) float64 with float32 column indices.
+# ----------------------------------------------------------------------------------------------------
+def prq_regularize(rows, cols, data, offsets: Dict[int, int], alpha: float, target_tolerance: float = 0.001,
+                   max_iterations: int = 100):
+    """Returns (m, c, log_prob_reg float64) sorted by (m, c), and {m: log target}."""
+    rows, cols = np.asarray(rows).astype(np.int64), np.asarray(cols).astype(np.int64)
+    data = np.asarray(data).astype(np.float64)
+    order = np.lexsort((cols, rows))
+    rows, cols, data = rows[order], cols[order], data[order]
+    out_m, out_c, out_lp, targets = [], [], [], {}
+    starts = np.flatnonzero(np.r_[True, rows[1:] != rows[:-1]])
+    ends = np.r_[starts[1:], rows.size]
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        for a, b in zip(starts, ends):
+            m = int(rows[a])
+            c, lp = cols[a:b], data[a:b]
+            prob = np.exp(lp)
+            cf = c.astype(np.float32).astype(np.float64)
+            mean = float((cf * prob).sum())
+            std = float(np.sqrt((((cf - mean) ** 2) * prob).sum()))
+            target = np.log(np.float64(mean + alpha * std))
+            targets[m] = float(target)
+            n32 = (c + offsets.get(m, 0)).astype(np.float32)
+            logn = np.log(n32).astype(np.float64)  # float32 log, promoted
+            lo, hi, beta = np.float32(-100.0), np.float32(100.0), np.float32(0.0)
+            for _ in range(max_iterations):
+                beta = np.float32((lo + hi) * np.float32(0.5))
+                td = lp + (beta * n32).astype(np.float64)
+                outcome = _lse(logn + td) - _lse(td) - target
+                if abs(0.0 - outcome) < target_tolerance:
+                    break
+                if outcome < -target_tolerance:
+                    lo = beta
+                if outcome > target_tolerance:
+                    hi = beta
+            reg = lp + (beta * n32).astype(np.float64)
+            reg = reg - _lse(reg)
+            keep = np.exp(reg) != 0
+            out_m += [m] * int(keep.sum())
+            out_c += c[keep].tolist()
+            out_lp += reg[keep].tolist()
+    return np.array(out_m, dtype=np.int64), np.array(out_c, dtype=np.int32), np.array(out_lp, dtype=np.float64), targets
+
+
+def _lse(v):
+    mx = np.max(v)
+    if not np.isfinite(mx):
+        return mx
+    return mx + np.log(np.exp(v - mx).sum())

@@ -630,3 +630,89 @@ def test_nbpc_exact_log_prob_vs_reference_golden_and_float64(ops, golden_dir):
     for mine, r in ((mu_c.grad, mu2.grad), (lam_c.grad, lam2.grad), (al_c.grad, alpha.grad)):
         scale = float(r.abs().max())
         assert float((mine.double().cpu() - r).abs().max()) <= 1e-4 * scale
+
+
+# ------------------------------------------------------------------------------- PRq posterior regularisation
+@pytest.mark.parametrize("tag", ["fixture", "rand0", "rand1", "rand2"])
+def test_prq_matches_reference_golden(ops, golden_dir, tag):
+    """regularization.PRq (cb_prq_regularize) vs PRq.regularize / _compute_log_target_dict of the unmodified reference
+    (posterior.py:1002-1225): same kept entries, regularised log probs to 1e-6, targets to 1e-9, for alpha 0, 1, 2."""
+    from cellbender_b200.regularization import PRq
+
+    g = np.load(os.path.join(golden_dir, "prq.npz"))
+    shape = tuple(int(v) for v in g[f"{tag}_shape"])
+    coo = sp.coo_matrix((g[f"{tag}_data"], (g[f"{tag}_row"], g[f"{tag}_col"])), shape=shape)
+    offsets = dict(zip(g[f"{tag}_off_m"].tolist(), g[f"{tag}_off_v"].tolist()))
+    for alpha in (0.0, 1.0, 2.0):
+        key = f"{tag}_a{alpha:g}"
+        tgt = PRq._compute_log_target_dict(noise_count_posterior_coo=coo, alpha=alpha)
+        ref_t = dict(zip(g[key + "_target_m"].tolist(), g[key + "_target"].tolist()))
+        assert set(tgt) == set(ref_t)
+        for k_, v in ref_t.items():
+            assert (np.isneginf(v) and np.isneginf(tgt[k_])) or abs(v - tgt[k_]) < 1e-6, (k_, v, tgt[k_])
+        reg = PRq.regularize(noise_count_posterior_coo=coo, noise_offsets=offsets, alpha=alpha, device=DEV, target_tolerance=0.001)
+        assert reg.shape == shape and reg.data.dtype == np.float64
+        np.testing.assert_array_equal(reg.row, g[key + "_row"])
+        np.testing.assert_array_equal(reg.col, g[key + "_col"])
+        np.testing.assert_allclose(reg.data, g[key + "_data"], rtol=1e-6, atol=1e-6)
+
+
+def test_prq_large_random_vs_oracle_and_mean_targets(ops):
+    """A larger posterior (thousands of segments, offsets, holes): kernel vs the numpy oracle entry by entry, and the
+    reference test's own criterion (tests/test_posterior.py:78-137): regularised means hit mean + alpha * std."""
+    from cellbender_b200.estimation import DevicePosteriorCOO
+    from cellbender_b200.regularization import PRq
+
+    rng = np.random.default_rng(5)
+    rows, cols, vals, offsets = [], [], [], {}
+    n_m, n_c = 3000, 20
+    for m in range(n_m):
+        k = int(rng.integers(1, n_c + 1))
+        lp = rng.normal(size=k) * 2.0
+        lp = lp - np.log(np.exp(lp).sum())
+        keep = lp >= -7
+        keep[np.argmax(lp)] = True
+        for c in np.flatnonzero(keep):
+            rows.append(m * 7 + 3), cols.append(c), vals.append(lp[c])
+        if rng.random() < 0.3:
+            offsets[m * 7 + 3] = int(rng.integers(1, 5))
+    coo = sp.coo_matrix((np.array(vals, np.float32), (np.array(rows), np.array(cols))), shape=(n_m * 7 + 10, n_c))
+    alpha = 1.0
+    m_o, c_o, lp_o, _ = opost.prq_regularize(coo.row, coo.col, coo.data, offsets, alpha)
+    reg = PRq.regularize(noise_count_posterior_coo=coo, noise_offsets=offsets, alpha=alpha, device=DEV)
+    np.testing.assert_array_equal(reg.row, m_o)
+    np.testing.assert_array_equal(reg.col, c_o)
+    np.testing.assert_allclose(reg.data, lp_o, rtol=1e-6, atol=1e-6)
+    # device-to-device variant keeps (m, c) order and feeds the estimators
+    dev_reg = PRq.regularize_device(DevicePosteriorCOO.from_scipy(coo, offsets, DEV), alpha=alpha)
+    assert torch.equal(dev_reg.m.cpu(), torch.as_tensor(m_o)) and dev_reg.log_prob.dtype == torch.float32
+    # means: E_reg[n] == E[n] + alpha std[n] wherever that target is reachable (n = c + offset enters the tilt only)
+    dense = np.full((n_m, n_c), -np.inf)
+    dense[(coo.row - 3) // 7, coo.col] = coo.data
+    cnt = np.arange(n_c)[None, :]
+    p_in = np.exp(dense)
+    mean_in = (p_in * cnt).sum(1)
+    std_in = np.sqrt((p_in * (cnt - mean_in[:, None]) ** 2).sum(1))
+    dreg = np.full((n_m, n_c), -np.inf)
+    dreg[(reg.row - 3) // 7, reg.col] = reg.data
+    off_arr = np.array([offsets.get(m * 7 + 3, 0) for m in range(n_m)])
+    mean_reg_n = (np.exp(dreg) * (cnt + off_arr[:, None])).sum(1)  # the constraint is on E[c + offset]
+    target = mean_in + alpha * std_in
+    multi = (np.isfinite(dense).sum(1) > 1) & (target > 0)
+    reachable = multi & (target < (np.where(np.isfinite(dense), cnt + off_arr[:, None], -1).max(1) - 1e-3)) \
+        & (target > (np.where(np.isfinite(dense), cnt + off_arr[:, None], 10 ** 6).min(1) + 1e-3))
+    assert reachable.sum() > 500
+    np.testing.assert_allclose(mean_reg_n[reachable], target[reachable], rtol=2e-3, atol=2e-3)
+
+
+def test_torch_binary_search_matches_reference_golden(golden_dir):
+    from cellbender_b200.regularization import torch_binary_search
+
+    g = np.load(os.path.join(golden_dir, "prq.npz"))
+    tgt = torch.tensor(g["bsearch_target"], device=DEV)
+    out = torch_binary_search(evaluate_outcome_given_value=lambda x: x ** 2, target_outcome=tgt,
+                              init_range=torch.tensor([0.0, 100.0], device=DEV).unsqueeze(0).expand(4, 2),
+                              target_tolerance=0.001, max_iterations=100)
+    np.testing.assert_array_equal(out.cpu().numpy(), g["bsearch_out"])
+    with pytest.raises(AssertionError):
+        torch_binary_search(lambda x: x, tgt, torch.zeros(4, 2, device=DEV), target_tolerance=0.0)

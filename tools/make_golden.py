@@ -33,7 +33,9 @@ from cellbender.remove_background.model import calculate_lambda, calculate_mu, g
 from cellbender.remove_background.posterior import (  # noqa: E402
     IndexConverter,
     Posterior,
+    PRq,
     compute_mean_target_removal_as_function,
+    torch_binary_search,
 )
 from cellbender.remove_background.sparse_utils import dense_to_sparse_op_torch  # noqa: E402
 from cellbender.remove_background.vae.decoder import Decoder  # noqa: E402
@@ -208,6 +210,40 @@ def golden_estimation():
     np.savez_compressed(os.path.join(OUT, "estimation.npz"), **res)
 
 
+def golden_prq():
+    """PRq.regularize (posterior.py:1002-1225) of the unmodified reference on its own test fixture and on random
+    posteriors with holes and offsets, alpha in {0, 1, 2}; plus torch_binary_search on the reference test's function."""
+    res = {}
+    coo, offsets = _fixture_posterior()
+    cases = {"fixture": (coo, offsets)}
+    rng = np.random.default_rng(11)
+    for i in range(3):
+        nc, ng = int(rng.integers(3, 9)), int(rng.integers(4, 12))
+        cases[f"rand{i}"] = _random_posterior(rng, nc, ng)
+    for tag, (coo, offsets) in cases.items():
+        res[f"{tag}_row"], res[f"{tag}_col"], res[f"{tag}_data"] = coo.row.astype(np.int64), coo.col.astype(np.int32), coo.data
+        res[f"{tag}_shape"] = np.array(coo.shape)
+        off_m = np.array(sorted(offsets.keys()), dtype=np.int64)
+        res[f"{tag}_off_m"], res[f"{tag}_off_v"] = off_m, np.array([offsets[m] for m in off_m], dtype=np.int32)
+        for alpha in (0.0, 1.0, 2.0):
+            tgt = PRq._compute_log_target_dict(noise_count_posterior_coo=coo, alpha=alpha)
+            res[f"{tag}_a{alpha:g}_target_m"] = np.array(list(tgt.keys()), dtype=np.int64)
+            res[f"{tag}_a{alpha:g}_target"] = np.array(list(tgt.values()), dtype=np.float64)
+            reg = PRq.regularize(noise_count_posterior_coo=coo, noise_offsets=offsets, alpha=alpha, device="cpu",
+                                 target_tolerance=0.001)
+            order = np.lexsort((reg.col, reg.row))
+            res[f"{tag}_a{alpha:g}_row"] = reg.row[order].astype(np.int64)
+            res[f"{tag}_a{alpha:g}_col"] = reg.col[order].astype(np.int32)
+            res[f"{tag}_a{alpha:g}_data"] = np.asarray(reg.data, dtype=np.float64)[order]
+    # torch_binary_search (tests/test_posterior.py:280-330 style): monotone function, per-element targets
+    x0 = torch.tensor([0.3, 2.0, 7.5, 40.0])
+    out = torch_binary_search(evaluate_outcome_given_value=lambda x: x ** 2, target_outcome=x0 ** 2,
+                              init_range=torch.tensor([0.0, 100.0]).unsqueeze(0).expand(4, 2), target_tolerance=0.001,
+                              max_iterations=100)
+    res["bsearch_target"], res["bsearch_out"] = (x0 ** 2).numpy(), out.numpy()
+    np.savez_compressed(os.path.join(OUT, "prq.npz"), **res)
+
+
 def golden_vae():
     torch.manual_seed(21)
     G, H, Z, B = 40, 16, 6, 12
@@ -272,6 +308,10 @@ def golden_dataloader():
 
 
 if __name__ == "__main__":
+    if "--only-prq" in sys.argv:
+        golden_prq()
+        sys.exit(0)
+    golden_prq()
     golden_nbpc()
     golden_rates()
     golden_posterior()
