@@ -272,6 +272,33 @@ __global__ void __launch_bounds__(256) prq_regularize_kernel(
   }
 }
 
+// Exponential tilt of every m-segment with a GIVEN factor (PRmu._chunked_compute_regularized_posterior, reference
+// posterior.py:1305-1393): out_c = lp_c + beta n_c - LSE_c(lp_c + beta n_c), n_c = c + offset_m (fp32 product, fp64
+// sums), beta = beta[0] (one overall factor) or beta[gene of m] (per-gene mode); keep = exp(out) != 0 in fp64.
+__global__ void __launch_bounds__(256) posterior_tilt_kernel(
+    const long long* __restrict__ m, const int* __restrict__ c, const float* __restrict__ lp,
+    const long long* __restrict__ seg_start, long long n_seg, long long n_entries, const long long* __restrict__ off_m,
+    const int* __restrict__ off_v, long long n_off, const float* __restrict__ beta, long long n_beta,
+    long long total_n_genes, double* __restrict__ lp_out, int* __restrict__ keep) {
+  const long long sidx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (sidx >= n_seg) return;
+  const long long a = seg_start[sidx];
+  const long long b = (sidx + 1 < n_seg) ? seg_start[sidx + 1] : n_entries;
+  const long long key = m[a];
+  const int off = lookup_offset(off_m, off_v, n_off, key);
+  const float bt = (n_beta == 1) ? beta[0] : beta[key % total_n_genes];
+  double mx = -INFINITY;
+  for (long long i = a; i < b; ++i) mx = fmax(mx, double(lp[i]) + double(bt * float(c[i] + off)));
+  double z = 0.0;
+  for (long long i = a; i < b; ++i) z += exp(double(lp[i]) + double(bt * float(c[i] + off)) - mx);
+  const double lse = mx + log(z);
+  for (long long i = a; i < b; ++i) {
+    const double v = double(lp[i]) + double(bt * float(c[i] + off)) - lse;
+    lp_out[i] = v;
+    keep[i] = (exp(v) != 0.0) ? 1 : 0;
+  }
+}
+
 // CSR row pointer of the [n_rows, n_cols] output: indptr[r] = lower_bound(seg_m, r * n_cols)
 __global__ void __launch_bounds__(256) csr_indptr_kernel(const long long* __restrict__ seg_m, long long n_seg,
                                                          long long n_rows, long long n_cols,
@@ -427,6 +454,18 @@ extern "C" int cb_prq_regularize(const long long* m, const int* c, const float* 
       m, c, lp, seg_start, n_seg, n_entries, off_m, off_v, n_off, alpha, target_tolerance, max_iterations, log_target,
       beta_out, lp_out, keep);
   return cb::check_launch("cb_prq_regularize");
+}
+
+extern "C" int cb_posterior_tilt(const long long* m, const int* c, const float* lp, const long long* seg_start,
+                                 long long n_seg, long long n_entries, const long long* off_m, const int* off_v,
+                                 long long n_off, const float* beta, long long n_beta, long long total_n_genes,
+                                 double* lp_out, int* keep, void* stream) {
+  if (n_seg == 0) return 0;
+  CB_REQUIRE(n_beta == 1 || n_beta == total_n_genes, "cb_posterior_tilt: beta must hold 1 or total_n_genes (%lld) values, got %lld",
+             total_n_genes, n_beta);
+  cb::posterior_tilt_kernel<<<cb::blocks_for(n_seg), 256, 0, (cudaStream_t)stream>>>(
+      m, c, lp, seg_start, n_seg, n_entries, off_m, off_v, n_off, beta, n_beta, total_n_genes, lp_out, keep);
+  return cb::check_launch("cb_posterior_tilt");
 }
 
 extern "C" int cb_csr_from_segments(const long long* seg_m, long long n_seg, long long n_rows, long long n_cols,

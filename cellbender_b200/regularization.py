@@ -6,7 +6,9 @@ PRq: approximate noise-CDF quantile targeting -- every (cell, gene) posterior p(
 the per-entry beta that moves its mean to mean + alpha * std.  The reference densifies ~1 GB chunks and runs a
 vectorised bisection until every row of the chunk has converged; here one thread owns one (cell, gene) segment of the
 device-resident COO and runs its own bisection (csrc/estimation.cu: prq_regularize_kernel), which gives the same beta
-because a converged row's bracket no longer moves.  PRmu / PRmu_gene are not implemented (raise).
+because a converged row's bracket no longer moves.
+PRmu / PRmu_gene: approximate mean targeting -- one overall (or per-gene) tilt factor found by bisection on the MAP noise
+counts of a random subset of cells; the tilt, the MAP and the per-gene sums all run on the device-resident COO.
 """
 from abc import ABC, abstractmethod
 from typing import Callable, Dict, Optional
@@ -98,16 +100,106 @@ class PRq(PosteriorRegularization):
 
 
 class PRmu(PosteriorRegularization):
-    """Approximate noise mean targeting (posterior.py:1228-1530).  Not on the B200 path yet."""
+    r"""Approximate noise mean targeting (posterior.py:1228-1530): one tilt factor beta (overall, the v0.2.0
+    behaviour) or one per gene, found by bisection so that the MAP noise counts of the regularised posterior, summed over
+    a random subset of cells, equal E[noise] + nFPR * raw counts."""
 
     @staticmethod
     def name():
         return "PRmu"
 
     @staticmethod
-    def regularize(noise_count_posterior_coo, noise_offsets, **kwargs):
-        raise NotImplementedError("PRmu / PRmu_gene posterior regularisation is not implemented on the B200 path "
-                                  "(SURVEY.md section 8f rank 3); PRq is")
+    def _tilt_device(p: DevicePosteriorCOO, beta: torch.Tensor, total_n_genes: int):
+        """(regularised log prob fp64 [n_entries], keep mask) of ``p`` tilted by ``beta`` ([1] or [total_n_genes])."""
+        seg = _segments(p)
+        n, dev = p.m.numel(), p.m.device
+        beta = beta.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        lp_out = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+        keep = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+        _cabi.lib().call("cb_posterior_tilt", ptr(p.m), ptr(p.c), ptr(p.log_prob), ptr(seg.seg_start), seg.n_seg, n, ptr(p.off_m),
+                         ptr(p.off_v), p.off_m.numel(), ptr(beta), beta.numel(), int(total_n_genes), ptr(lp_out), ptr(keep),
+                         current_stream())
+        return lp_out[:n], keep[:n].bool()
+
+    @staticmethod
+    def _chunked_compute_regularized_posterior(noise_count_posterior_coo, noise_offsets, index_converter, beta: torch.Tensor,
+                                               device: str = "cuda", n_chunks: Optional[int] = None) -> sp.coo_matrix:
+        """posterior.py:1305-1393 (chunks are independent: one pass)."""
+        p = _as_device_posterior(noise_count_posterior_coo, noise_offsets, device)
+        lp, mask = PRmu._tilt_device(p, beta, index_converter.total_n_genes)
+        return sp.coo_matrix((lp[mask].cpu().numpy(), (p.m[mask].cpu().numpy(), p.c[mask].cpu().numpy())),
+                             shape=noise_count_posterior_coo.shape)
+
+    @staticmethod
+    def _subset_posterior_by_cells(p: DevicePosteriorCOO, index_converter, n_cells: int) -> DevicePosteriorCOO:
+        """A random slice of the posterior with ``n_cells`` cells (posterior.py:1395-1427; numpy's global RNG chooses
+        the cells exactly as in the reference)."""
+        G = index_converter.total_n_genes
+        cell_of = torch.div(p.m, G, rounding_mode="floor")
+        unique_cell_inds = torch.unique(cell_of).cpu().numpy()
+        n_cells = min(n_cells, len(unique_cell_inds))
+        chosen = np.random.choice(unique_cell_inds, size=n_cells, replace=False)
+        lut = torch.zeros(index_converter.total_n_cells, dtype=torch.bool, device=p.m.device)
+        lut[torch.as_tensor(chosen, device=p.m.device)] = True
+        mask = lut[cell_of]
+        return DevicePosteriorCOO(p.m[mask].contiguous(), p.c[mask].contiguous(), p.log_prob[mask].contiguous(), p.off_m,
+                                  p.off_v, p.n_cols)
+
+    @staticmethod
+    def _binary_search_for_posterior_regularization_factor(p: DevicePosteriorCOO, index_converter, target_removal: torch.Tensor,
+                                                           shape: int, target_tolerance: float = 100, max_iterations: int = 20,
+                                                           device: str = "cuda") -> torch.Tensor:
+        """posterior.py:1245-1303: MAP noise counts of the tilted subset posterior, summed overall or per gene, as a
+        function of beta; bisection on [-100, 200]."""
+        from .estimation import MODE_MAP, _segment_estimate
+
+        G = index_converter.total_n_genes
+        per_gene = target_removal.dim() > 0 and target_removal.numel() > 1
+
+        def summarize_map_noise_counts(x: torch.Tensor) -> torch.Tensor:
+            lp, mask = PRmu._tilt_device(p, x, G)
+            reg = DevicePosteriorCOO(p.m[mask].contiguous(), p.c[mask].contiguous(), lp[mask].float().contiguous(), p.off_m,
+                                     p.off_v, p.n_cols)
+            seg_m, map_val, _ = _segment_estimate(reg, _segments(reg), MODE_MAP)
+            if per_gene:
+                return torch.zeros(G, dtype=torch.int64, device=p.m.device).index_add_(0, seg_m % G, map_val.long())
+            return map_val.long().sum()
+
+        dev = p.m.device
+        return torch_binary_search(
+            evaluate_outcome_given_value=summarize_map_noise_counts, target_outcome=target_removal.to(dev),
+            init_range=torch.tensor([-100.0, 200.0], device=dev).unsqueeze(0).expand((shape, 2)),
+            target_tolerance=target_tolerance, max_iterations=max_iterations, debug=True)
+
+    @staticmethod
+    @torch.no_grad()
+    def regularize(noise_count_posterior_coo: sp.coo_matrix, noise_offsets: Optional[Dict[int, int]], index_converter=None,
+                   raw_count_matrix: Optional[sp.csr_matrix] = None, fpr: float = 0.01, per_gene: bool = False,
+                   device: str = "cuda", target_tolerance: float = 0.5, n_cells: int = 1000, n_chunks: Optional[int] = None,
+                   **kwargs) -> sp.coo_matrix:
+        """Same signature and return type as the reference (posterior.py:1429-1530)."""
+        from .estimation import compute_mean_target_removal_as_function
+        from .posterior import csr_set_rows_to_zero
+
+        assert index_converter is not None, "index_converter is required for PRmu.regularize"
+        assert raw_count_matrix is not None, "raw_count_matrix is required for PRmu.regularize"
+        p = _as_device_posterior(noise_count_posterior_coo, noise_offsets, device)
+        subset = PRmu._subset_posterior_by_cells(p, index_converter, n_cells)
+        G = index_converter.total_n_genes
+        included = np.unique(torch.div(subset.m, G, rounding_mode="floor").cpu().numpy())
+        excluded = np.setdiff1d(np.arange(raw_count_matrix.shape[0]), included)
+        raw_count_csr_for_cells = csr_set_rows_to_zero(csr=raw_count_matrix, row_inds=excluded)
+        target_fun = compute_mean_target_removal_as_function(
+            noise_count_posterior_coo=subset, noise_offsets=None, index_converter=index_converter,
+            raw_count_csr_for_cells=raw_count_csr_for_cells, n_cells=len(included), device=str(p.m.device), per_gene=per_gene)
+        target_removal = target_fun(fpr) * len(included)
+        shape = G if per_gene else 1
+        beta = PRmu._binary_search_for_posterior_regularization_factor(
+            subset, index_converter, target_removal=target_removal, device=device, target_tolerance=target_tolerance,
+            shape=shape)
+        lp, mask = PRmu._tilt_device(p, beta, G)
+        return sp.coo_matrix((lp[mask].cpu().numpy(), (p.m[mask].cpu().numpy(), p.c[mask].cpu().numpy())),
+                             shape=noise_count_posterior_coo.shape)
 
 
 def torch_binary_search(evaluate_outcome_given_value: Callable[[torch.Tensor], torch.Tensor], target_outcome: torch.Tensor,

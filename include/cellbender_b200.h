@@ -284,6 +284,11 @@ int cb_prq_regularize(const long long* m, const int* c, const float* lp, const l
                       long long n_entries, const long long* off_m, const int* off_v, long long n_off, double alpha,
                       double target_tolerance, int max_iterations, double* log_target, float* beta_out, double* lp_out,
                       int* keep, void* stream);
+/* PRmu's tilt with given factor(s) (posterior.py:1305-1393): beta[n_beta], n_beta = 1 (overall) or total_n_genes
+ * (per-gene: beta[m % total_n_genes]); outputs as cb_prq_regularize.                                              */
+int cb_posterior_tilt(const long long* m, const int* c, const float* lp, const long long* seg_start, long long n_seg,
+                      long long n_entries, const long long* off_m, const int* off_v, long long n_off, const float* beta,
+                      long long n_beta, long long total_n_genes, double* lp_out, int* keep, void* stream);
 int cb_mckp_gene_deficit(const long long* seg_m, const int* map_val, long long n_seg, const double* target,
                          long long n_genes, long long* gene_sum, long long* deficit, void* stream);
 int cb_mckp_candidates(const long long* m, const int* c, const float* lp, const int* seg_of, const long long* map_pos,

@@ -716,3 +716,30 @@ def test_torch_binary_search_matches_reference_golden(golden_dir):
     np.testing.assert_array_equal(out.cpu().numpy(), g["bsearch_out"])
     with pytest.raises(AssertionError):
         torch_binary_search(lambda x: x, tgt, torch.zeros(4, 2, device=DEV), target_tolerance=0.0)
+
+
+@pytest.mark.parametrize("tag", ["case0", "case1"])
+@pytest.mark.parametrize("per_gene", [False, True])
+@pytest.mark.parametrize("fpr", [0.01, 0.3])
+def test_prmu_matches_reference_golden(ops, golden_dir, tag, per_gene, fpr):
+    """regularization.PRmu (cb_posterior_tilt + device MAP + bisection) vs PRmu.regularize of the unmodified reference
+    (posterior.py:1228-1530), overall and per-gene factors: same kept entries, log probs to 1e-6."""
+    from cellbender_b200.estimation import IndexConverter
+    from cellbender_b200.regularization import PRmu
+
+    g = np.load(os.path.join(golden_dir, "prmu.npz"))
+    shape = tuple(int(v) for v in g[f"{tag}_shape"])
+    nc, ng = (int(v) for v in g[f"{tag}_ncng"])
+    coo = sp.coo_matrix((g[f"{tag}_data"], (g[f"{tag}_row"], g[f"{tag}_col"])), shape=shape)
+    offsets = dict(zip(g[f"{tag}_off_m"].tolist(), g[f"{tag}_off_v"].tolist()))
+    raw = sp.csr_matrix(g[f"{tag}_raw"])
+    np.random.seed(0)
+    reg = PRmu.regularize(noise_count_posterior_coo=coo, noise_offsets=offsets, index_converter=IndexConverter(nc, ng),
+                          raw_count_matrix=raw, fpr=fpr, per_gene=per_gene, device=DEV, n_cells=1000)
+    key = f"{tag}_{'gene' if per_gene else 'all'}_f{fpr:g}"
+    assert reg.shape == shape
+    np.testing.assert_array_equal(reg.row, g[key + "_row"])
+    np.testing.assert_array_equal(reg.col, g[key + "_col"])
+    np.testing.assert_allclose(reg.data, g[key + "_data"], rtol=1e-6, atol=1e-6)
+    with pytest.raises(AssertionError):
+        PRmu.regularize(noise_count_posterior_coo=coo, noise_offsets=offsets, raw_count_matrix=raw)

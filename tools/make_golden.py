@@ -33,6 +33,7 @@ from cellbender.remove_background.model import calculate_lambda, calculate_mu, g
 from cellbender.remove_background.posterior import (  # noqa: E402
     IndexConverter,
     Posterior,
+    PRmu,
     PRq,
     compute_mean_target_removal_as_function,
     torch_binary_search,
@@ -244,6 +245,35 @@ def golden_prq():
     np.savez_compressed(os.path.join(OUT, "prq.npz"), **res)
 
 
+def golden_prmu():
+    """PRmu.regularize (posterior.py:1228-1530) of the unmodified reference: overall and per-gene mean targeting on
+    random posteriors with offsets; n_cells >= the number of cells, so the random subset is every cell."""
+    res = {}
+    rng = np.random.default_rng(23)
+    for i in range(2):
+        nc, ng = int(rng.integers(5, 9)), int(rng.integers(6, 12))
+        coo, offsets = _random_posterior(rng, nc, ng, density=0.7)
+        raw = sp.csr_matrix(rng.poisson(6.0, size=(nc, ng)).astype(np.int64))
+        conv = IndexConverter(total_n_cells=nc, total_n_genes=ng)
+        tag = f"case{i}"
+        res[f"{tag}_row"], res[f"{tag}_col"], res[f"{tag}_data"] = coo.row.astype(np.int64), coo.col.astype(np.int32), coo.data
+        res[f"{tag}_shape"], res[f"{tag}_ncng"] = np.array(coo.shape), np.array([nc, ng])
+        off_m = np.array(sorted(offsets.keys()), dtype=np.int64)
+        res[f"{tag}_off_m"], res[f"{tag}_off_v"] = off_m, np.array([offsets[m] for m in off_m], dtype=np.int32)
+        res[f"{tag}_raw"] = np.asarray(raw.todense())
+        for per_gene in (False, True):
+            for fpr in (0.01, 0.3):
+                np.random.seed(0)
+                reg = PRmu.regularize(noise_count_posterior_coo=coo, noise_offsets=offsets, index_converter=conv,
+                                      raw_count_matrix=raw.copy(), fpr=fpr, per_gene=per_gene, device="cpu", n_cells=1000)
+                order = np.lexsort((reg.col, reg.row))
+                key = f"{tag}_{'gene' if per_gene else 'all'}_f{fpr:g}"
+                res[key + "_row"] = reg.row[order].astype(np.int64)
+                res[key + "_col"] = reg.col[order].astype(np.int32)
+                res[key + "_data"] = np.asarray(reg.data, dtype=np.float64)[order]
+    np.savez_compressed(os.path.join(OUT, "prmu.npz"), **res)
+
+
 def golden_vae():
     torch.manual_seed(21)
     G, H, Z, B = 40, 16, 6, 12
@@ -310,8 +340,10 @@ def golden_dataloader():
 if __name__ == "__main__":
     if "--only-prq" in sys.argv:
         golden_prq()
+        golden_prmu()
         sys.exit(0)
     golden_prq()
+    golden_prmu()
     golden_nbpc()
     golden_rates()
     golden_posterior()
