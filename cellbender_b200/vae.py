@@ -24,6 +24,10 @@ from . import gemm, ops
 from .gemm import bn0_dropout, bn_act, linear_big, multi_linear_big
 
 
+# run the two towers of EncodeNonZLatents on separate streams (see forward_raw)
+TOWER_STREAMS = True
+
+
 @dataclass
 class EncoderInputs:
     """Output of the gather kernel for one minibatch (cb_csr_gather_rows)."""
@@ -215,17 +219,34 @@ class EncodeNonZLatents(nn.Module):
         # the 4 feature columns as a rank-4 update
         e = self.eps_network[0]
         h1, he = multi_linear_big(x_in, [(self.layer1, p_feat), (e, e_feat)], n_in=G, col_offset=4, bias_grad_elsewhere=True)
+        # The two towers are independent chains of small, latency-bound launches ([B, 512] tensors): the epsilon tower
+        # runs on an auxiliary stream, the cell-probability tower on the calling one (parallel branches of the captured
+        # step graph; autograd replays each backward node on its forward stream).  Fork: the side stream first waits for
+        # everything issued so far; join: the calling stream waits for the side stream before eps_out is consumed.
+        eps_bn1, eps_lin2, eps_bn2, eps_lin3 = self.eps_network[1], self.eps_network[3], self.eps_network[4], self.eps_network[6]
+
+        def eps_tower():
+            h = bn_act(he, eps_bn1, "softplus", self.training, bias_of=e)
+            h = linear_big(h, eps_lin2, n_in=h.shape[1], bias_grad_elsewhere=True)
+            h = bn_act(h, eps_bn2, "softplus", self.training, bias_of=eps_lin2)
+            return ops.head(h, eps_lin3)
+
+        fork = he.is_cuda and TOWER_STREAMS
+        if fork:
+            main, side = torch.cuda.current_stream(), ops.side_stream(he.device, 2)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                eps_out = eps_tower()
         # hidden layers: Linear (tensor-core GEMM + rank-4 feature update) -> fused BatchNorm + Softplus kernel
         x_ = bn_act(h1, self.batchnorm1, "softplus", self.training, bias_of=self.layer1)
         h2 = linear_big(x_, self.layer2, n_in=x_.shape[1], col_offset=4, feat=p_feat, bias_grad_elsewhere=True)
         x_ = bn_act(h2, self.batchnorm2, "softplus", self.training, bias_of=self.layer2)
         p_out = ops.head(x_, self.layer3, p_feat)
-
-        eps_bn1, eps_lin2, eps_bn2, eps_lin3 = self.eps_network[1], self.eps_network[3], self.eps_network[4], self.eps_network[6]
-        h = bn_act(he, eps_bn1, "softplus", self.training, bias_of=e)
-        h = linear_big(h, eps_lin2, n_in=h.shape[1], bias_grad_elsewhere=True)
-        h = bn_act(h, eps_bn2, "softplus", self.training, bias_of=eps_lin2)
-        eps_out = ops.head(h, eps_lin3)
+        if fork:
+            main.wait_stream(side)
+            he.record_stream(side), e_feat.record_stream(side), eps_out.record_stream(main)
+        else:
+            eps_out = eps_tower()
 
         if self.offset is None:  # data-dependent module state fixed by the first minibatch (encoder.py:300-309)
             ls = log_sum.squeeze(-1)
