@@ -338,9 +338,10 @@ class RemoveBackgroundPyroModel(nn.Module):
             chi_ambient, _ = self.ambient(B)
         d_empty_loc = self.param_store["d_empty_loc"].detach()
         self._d_empty_loc_now = d_empty_loc
+        x_in = self.encoder["other"].normalize_input(inp, row_keep_scale)  # batchnorm0 + dropout, on a side stream
         z_loc, z_log_scale = self.encoder["z"].forward_raw(inp)
         p_out, eps_out, _ = self.encoder["other"].forward_raw(inp, chi_ambient.detach(), z_loc.detach(),
-                                                              row_keep_scale=row_keep_scale)
+                                                              row_keep_scale=row_keep_scale, x_in=x_in)
         self._d_empty_loc_now = None
         # guide samples, rate coefficients, enumeration weights and every non-observation term: one kernel
         z, coef, alpha, w, loss_local, terms, enc_out = latent.latent_stage(self, p_out, eps_out, z_loc, z_log_scale,

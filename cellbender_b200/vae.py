@@ -194,8 +194,25 @@ class EncodeNonZLatents(nn.Module):
             raise RuntimeError("EncodeNonZLatents.d_empty_loc_fn is not set (the model object sets it)")
         return self.d_empty_loc_fn().detach().to(device)
 
+    def normalize_input(self, inp: "EncoderInputs", row_keep_scale: Optional[torch.Tensor] = None):
+        """dropout50(batchnorm0(x)) (encoder.py:239, 279) issued on an auxiliary stream: it depends on the counts only, so
+        it overlaps EncodeZ (and, in backward, its gradient kernel overlaps EncodeZ's weight-gradient GEMM).  Returns a
+        handle for ``forward_raw(x_in=...)``, which joins the stream."""
+        B = inp.feats.shape[0]
+        if self.training and row_keep_scale is None:
+            row_keep_scale = torch.empty(B, device=inp.feats.device).bernoulli_(0.5).mul_(2.0)
+        if not (inp.x_lognorm.is_cuda and TOWER_STREAMS):
+            return bn0_dropout(inp.x_lognorm, self.batchnorm0, row_keep_scale, self.training, self.n_genes), None
+        main, side = torch.cuda.current_stream(), ops.side_stream(inp.feats.device, 3)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            x_in = bn0_dropout(inp.x_lognorm, self.batchnorm0, row_keep_scale, self.training, self.n_genes)
+        if row_keep_scale is not None:
+            row_keep_scale.record_stream(side)
+        return x_in, side
+
     def forward_raw(self, x, chi_ambient: Optional[torch.Tensor], z: torch.Tensor,
-                    row_keep_scale: Optional[torch.Tensor] = None):
+                    row_keep_scale: Optional[torch.Tensor] = None, x_in=None):
         """Raw outputs of the two towers, ``layer3(...)`` and ``eps_network(...)`` [B], before the offset / gating
         algebra of encoder.py:300-340 (which the fused latent kernel applies on the training path).  Returns
         (p_out, eps_out, inputs)."""
@@ -209,11 +226,14 @@ class EncodeNonZLatents(nn.Module):
         log_sum = p_feat[:, 0:1]
 
         # BatchNorm over genes + Dropout1d(0.5), which on a 2-D input drops whole droplet rows (torch 2.11):
-        # one fused kernel (csrc/bn0.cu) writing a 16-byte-row buffer the tensor-core GEMMs can read through TMA.
+        # one fused kernel (csrc/bn_act.cu) writing a 16-byte-row buffer the tensor-core GEMMs can read through TMA.
         B = inp.feats.shape[0]
-        if self.training and row_keep_scale is None:
-            row_keep_scale = torch.empty(B, device=inp.feats.device).bernoulli_(0.5).mul_(2.0)
-        x_in = bn0_dropout(inp.x_lognorm, self.batchnorm0, row_keep_scale, self.training, G)
+        if x_in is None:
+            x_in = self.normalize_input(inp, row_keep_scale)
+        x_in, bn0_stream = x_in
+        if bn0_stream is not None:
+            torch.cuda.current_stream().wait_stream(bn0_stream)
+            x_in.record_stream(torch.cuda.current_stream())
 
         # Linear(cat(feat, x_in)) of both towers: the large gene block through the tensor-core GEMM (shared input),
         # the 4 feature columns as a rank-4 update
