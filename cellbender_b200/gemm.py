@@ -54,6 +54,24 @@ def fused_update_applies(w: torch.Tensor) -> bool:
             and w.shape[0] > 128)
 
 
+_PENDING_JOINS = []
+
+
+def defer_join(side: "torch.cuda.Stream"):
+    """Postpone ``current_stream().wait_stream(side)`` to the end of the running backward pass.  Weight / bias gradients
+    that a forked kernel writes straight into the optimizer's flat gradient buffer have no consumer inside backward, so
+    the calling stream (which carries the critical chain of input-gradient kernels) need not stall for them at the end
+    of the node; the autograd engine's final callback joins every such stream before control returns to the caller."""
+    if not _PENDING_JOINS:
+        def _join_all():
+            main = torch.cuda.current_stream()
+            while _PENDING_JOINS:
+                main.wait_stream(_PENDING_JOINS.pop())
+        torch.autograd.Variable._execution_engine.queue_callback(_join_all)
+    if side not in _PENDING_JOINS:
+        _PENDING_JOINS.append(side)
+
+
 def _tma_ok(t: torch.Tensor) -> bool:
     return (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0
             and t.data_ptr() % 16 == 0)
@@ -157,7 +175,13 @@ class _MultiLinearBig(torch.autograd.Function):
             grads += [dfeat, targets[i][0][1] if targets[i][0] is not None else None,
                       targets[i][1][1] if targets[i][1] is not None else None]
         if fork:
-            main.wait_stream(side)
+            # join now only if autograd receives a tensor produced on the side stream; otherwise at the end of backward
+            if all(g is None for g in grads[1::3]) and all(g is None for g in grads[2::3]):
+                for t in (x, *dys, *[f for f in feats if f is not None]):
+                    t.record_stream(side)  # autograd may release them when this node returns; the fork still reads them
+                defer_join(side)
+            else:
+                main.wait_stream(side)
         return (dx, None, None, *grads)
 
 

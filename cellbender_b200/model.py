@@ -149,7 +149,9 @@ class _ObsTerm(torch.autograd.Function):
         oo = bufs["obs_out"]
         out = ops.elbo_obs(csr, row_ids, logits, chi_a, bufs["chi_b"], coef.contiguous(), alpha.reshape(1).contiguous(),
                            w.contiguous(), out={"sums": oo["sums"][:B], "dlogits": oo["dlogits"][:B], "qamb": oo["qamb"][:B],
-                                                "dchi_ambient": oo["dchi_ambient"], "lse": oo["lse"], "nan_flag": oo["nan_flag"]})
+                                                "dchi_ambient": oo["dchi_ambient"], "lse": oo["lse"], "nan_flag": oo["nan_flag"]},
+                           defer_colsum=any(ctx.needs_input_grad))
+        ctx.dchi_ready = out["dchi_ready"]
         sums = out["sums"]
         L = sums[:, :3]
         ctx.save_for_backward(h_dec, w_out, sums, w, out["dlogits"], out["dchi_ambient"])
@@ -165,6 +167,8 @@ class _ObsTerm(torch.autograd.Function):
     def backward(ctx, g, _gL, _gobs):
         h_dec, w_out, sums, w, dlogits, dchi_amb = ctx.saved_tensors
         G = ctx.G
+        if ctx.dchi_ready is not None:
+            torch.cuda.current_stream().wait_event(ctx.dchi_ready)
         dl = dlogits[:, :G]
         if gemm.BACKEND == "tcgen05":
             B, H = h_dec.shape
@@ -187,7 +191,11 @@ class _ObsTerm(torch.autograd.Function):
                     ops.gemm_tf32(dlogits, h_c, G, H, B, a_mn=True, b_mn=True, out=d_w_buf, split_k=1)  # dlogits^T . h
                     ops.colsum_rows(dlogits, G, out=d_b_buf)
                 d_h = ops.gemm_tf32(dlogits, w_out, B, H, G, b_mn=True) * g          # dlogits[B,G] . Wd[G,H], split-K
-                main.wait_stream(side)
+                if d_w is None and d_b is None:
+                    h_c.record_stream(side), dlogits.record_stream(side)
+                    gemm.defer_join(side)  # both gradients went straight to the flat buffer: join at the end of backward
+                else:
+                    main.wait_stream(side)
         else:
             d_h = (dl @ w_out) * g
             d_w = dl.t() @ h_dec  # [G, H]

@@ -195,7 +195,7 @@ SUM_NAMES = ("L1", "L0", "LE", "dL1_da_mu1", "dL1_dcA1", "dL1_dcB1", "dL1_dalpha
              "dL0_dalpha", "dLE_dcAE", "dLE_dcBE")
 
 
-def elbo_obs(csr: DeviceCSR, row_ids, logits, chi_ambient, chi_bar, coef, alpha, w, *, out=None):
+def elbo_obs(csr: DeviceCSR, row_ids, logits, chi_ambient, chi_bar, coef, alpha, w, *, out=None, defer_colsum: bool = False):
     """cb_elbo_obs_fwd_bwd + cb_colsum_rows.  logits: [B, ld] buffer (ld % 4 == 0) holding G valid columns.
     chi_ambient / chi_bar: fp32 [>= G] 16-byte aligned.  Returns dict(sums [B,12], dlogits [B,ld], dchi_ambient [G],
     lse [B], nan_flag)."""
@@ -222,7 +222,20 @@ def elbo_obs(csr: DeviceCSR, row_ids, logits, chi_ambient, chi_bar, coef, alpha,
     L.call("cb_elbo_obs_fwd_bwd", ptr(csr.indptr), ptr(csr.indices), ptr(csr.data), ptr(row_ids), B, G, ptr(logits), ld,
            ptr(chi_ambient), ptr(chi_bar), ptr(coef), ptr(alpha), ptr(w), ptr(out["sums"]), ptr(out["dlogits"]),
            ptr(out["qamb"]), ld, ptr(out["lse"]), ptr(out["nan_flag"]), st)
-    L.call("cb_colsum_rows", ptr(out["qamb"]), B, G, ld, ptr(out["dchi_ambient"]), st)
+    if not defer_colsum:
+        L.call("cb_colsum_rows", ptr(out["qamb"]), B, G, ld, ptr(out["dchi_ambient"]), st)
+        out["dchi_ready"] = None
+        return out
+    # training step: the column sums (d loss / d chi_ambient) are consumed only at the very end of backward (simplex
+    # VJP), so they are issued on an auxiliary stream; out["dchi_ready"] is the event the consumer must wait for
+    main = torch.cuda.current_stream()
+    side = side_stream(logits.device, 4)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        L.call("cb_colsum_rows", ptr(out["qamb"]), B, G, ld, ptr(out["dchi_ambient"]), current_stream())
+        ev = torch.cuda.Event()
+        ev.record(side)
+    out["dchi_ready"] = ev
     return out
 
 
