@@ -49,7 +49,8 @@ def _grad_target(weight: torch.Tensor):
 
 def fused_update_applies(w: torch.Tensor) -> bool:
     opt = FUSED_OPT
-    return (opt is not None and BACKEND == "tcgen05" and getattr(w, "_cb_block", None) is not None
+    return (opt is not None and getattr(opt, "fuse_weight_updates", False) and BACKEND == "tcgen05"
+            and getattr(w, "_cb_block", None) is not None
             and getattr(w, "_cb_grad_view", None) is not None and w.requires_grad and w.numel() >= FUSED_MIN_NUMEL
             and w.shape[0] > 128)
 
@@ -70,6 +71,12 @@ def defer_join(side: "torch.cuda.Stream"):
         torch.autograd.Variable._execution_engine.queue_callback(_join_all)
     if side not in _PENDING_JOINS:
         _PENDING_JOINS.append(side)
+
+
+def early_update_applies(w: torch.Tensor) -> bool:
+    opt = FUSED_OPT
+    return (opt is not None and getattr(opt, "early_weight_updates", False) and getattr(w, "_cb_block", None) is not None
+            and getattr(w, "_cb_grad_view", None) is not None and w.requires_grad and w.numel() >= FUSED_MIN_NUMEL)
 
 
 def _tma_ok(t: torch.Tensor) -> bool:
@@ -167,6 +174,20 @@ class _MultiLinearBig(torch.autograd.Function):
                                   split_k=1)
         if any(fused):
             parameter_gradients()  # after the readers of the old weights
+        # piecewise optimizer sweep: the large weight blocks of this node are complete -> update them now, on the stream
+        # that produced their gradients, overlapping the rest of backward (the sweep is HBM-bound, backward is not);
+        # it must follow every reader of the OLD weights, i.e. the input-gradient product issued above
+        early = [i for i in range(n) if targets[i][0] is not None and early_update_applies(weights_p[i]) and not fused[i]
+                 and targets[i][0][1] is None]
+        if early:
+            upd_stream = side if fork else main
+            if fork:
+                readers_done = torch.cuda.Event()
+                readers_done.record(main)
+                upd_stream.wait_event(readers_done)
+            with torch.cuda.stream(upd_stream):
+                for i in early:
+                    FUSED_OPT.early_block_update(weights_p[i])
         grads = []
         for i in range(n):
             dfeat = None

@@ -191,6 +191,13 @@ class _ObsTerm(torch.autograd.Function):
                     ops.gemm_tf32(dlogits, h_c, G, H, B, a_mn=True, b_mn=True, out=d_w_buf, split_k=1)  # dlogits^T . h
                     ops.colsum_rows(dlogits, G, out=d_b_buf)
                 d_h = ops.gemm_tf32(dlogits, w_out, B, H, G, b_mn=True) * g          # dlogits[B,G] . Wd[G,H], split-K
+                if d_w is None and gemm.early_update_applies(w_param):
+                    # the decoder weights are no longer read this step: sweep their block now, behind the gradient GEMM
+                    readers_done = torch.cuda.Event()
+                    readers_done.record(main)
+                    side.wait_event(readers_done)
+                    with torch.cuda.stream(side):
+                        gemm.FUSED_OPT.early_block_update(w_param)
                 if d_w is None and d_b is None:
                     h_c.record_stream(side), dlogits.record_stream(side)
                     gemm.defer_join(side)  # both gradients went straight to the flat buffer: join at the end of backward

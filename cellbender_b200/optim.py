@@ -94,6 +94,10 @@ class FlatClippedAdam:
         # the Adam sweep) unfused, because the co-resident CTAs run their GEMM and optimizer phases in lockstep instead
         # of overlapping them; a persistent, TMEM-double-buffered variant is the next step.
         self.fuse_weight_updates = False
+        # Default on a single GPU: the ClippedAdam sweep of each large weight block is issued as soon as that block's
+        # gradient GEMM has finished, on the same (side) stream, so that the HBM-bound sweep overlaps the rest of the
+        # backward pass (which is latency / L2-bound); the sweep at the end of the step covers what is left.
+        self.early_weight_updates = True
         self._fused_done: List[tuple] = []
 
     def zero_grad(self):
@@ -129,6 +133,18 @@ class FlatClippedAdam:
                    float(self.beta2), float(self.eps), float(self.clip), current_stream())
         w._cb_grad_direct = True
         self._fused_done.append((o, n_rows, ld, cols, col_offset))
+
+    def early_block_update(self, w: nn.Parameter):
+        """ClippedAdam sweep of one [rows, ld] weight block of the flat buffers, on the current stream, without advancing
+        the step counter.  The caller guarantees the block's gradient is complete and its old values are no longer read."""
+        from ._cabi import current_stream, lib
+
+        o, rows, ld, cols = w._cb_block
+        at = lambda t: t.data_ptr() + 4 * o
+        lib().call("cb_clipped_adam_range", at(self.flat_p), at(self.flat_g), at(self.flat_m), at(self.flat_v), rows * ld,
+                   self.lr_table.data_ptr(), self.beta1_table.data_ptr(), self.lr_table.numel(), self.step_count.data_ptr(),
+                   float(self.beta2), float(self.eps), float(self.clip), 0, current_stream())
+        self._fused_done.append((o, rows, ld, cols, 0))
 
     def step(self, grad_scale: float = 1.0):
         """One ClippedAdam step over the flat buffers + one scheduler step."""

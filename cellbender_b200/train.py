@@ -73,7 +73,8 @@ class SVI:
         terms = self.loss_terms(batch)
         loss = terms["loss"]
         # single GPU: the large weight matrices are updated inside their weight-gradient GEMMs (optim.fused_dw)
-        fuse = self.after_backward is None and self.optim.fuse_weight_updates and self.model.training
+        fuse = (self.after_backward is None and self.model.training
+                and (self.optim.fuse_weight_updates or getattr(self.optim, "early_weight_updates", False)))
         gemm.FUSED_OPT = self.optim if fuse else None
         try:
             loss.backward()

@@ -221,11 +221,13 @@ def test_training_improves_elbo_graph_and_eager_agree_statistically():
     assert abs(finals[True] - finals[False]) < 0.15 * abs(finals[False])
 
 
+@pytest.mark.parametrize("mode", ["early", "fused"])
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_fused_weight_update_equals_separate_adam(use_graph):
-    """Single-GPU training applies the ClippedAdam update of the large weight matrices inside the epilogue of their
-    weight-gradient GEMM (cb_gemm_tf32_dw_adam).  Same seed, same data: parameters and both moment buffers must equal
-    those of the unfused path (gradient to HBM, one Adam sweep over the whole flat buffer).  Compared after the first
+def test_fused_weight_update_equals_separate_adam(use_graph, mode):
+    """Single-GPU training sweeps the ClippedAdam update of each large weight matrix as soon as its gradient GEMM has
+    finished, overlapping the rest of backward ('early': optim.early_block_update, the default), or applies it inside
+    the epilogue of that GEMM ('fused': cb_gemm_tf32_dw_adam).  Same seed, same data: parameters and both moment buffers
+    must equal those of the plain path (every gradient to HBM, one Adam sweep over the whole flat buffer at the end).  Compared after the first
     steps: biases that feed a BatchNorm have a mathematically zero gradient, Adam normalises their rounding noise to
     O(lr) steps, so later on the two runs drift apart in exactly those (irrelevant) parameters -- as any two runs do."""
     from cellbender_b200 import gemm, run, synth
@@ -241,7 +243,8 @@ def test_fused_weight_update_equals_separate_adam(use_graph):
             ds = synth.prepare_dataset(sim, expected_cells=80, total_droplets_included=300)
             args = run.default_args(epochs=5, z_dim=16, z_hidden_dims=[512], learning_rate=1e-3, use_cuda_graph=use_graph)
             model, opt, svi, tl, _ = run.setup_inference(ds, args, device=DEV)
-            opt.fuse_weight_updates = fuse
+            opt.fuse_weight_updates = fuse and mode == "fused"
+            opt.early_weight_updates = fuse and mode == "early"
             blocks = [p for p in opt.params if getattr(p, "_cb_block", None) is not None]
             assert len(blocks) >= 4  # the G x 512 matrices (and the 512 x 516 / 512 x 512 hidden layers) qualify
             model.train()
