@@ -29,7 +29,6 @@
 namespace cb {
 
 constexpr int kGemmThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
-constexpr int kAdamThreads = 320;  // + warps 6..9: helpers of the fused optimizer epilogue
 constexpr int kTilePitch = 132;    // floats per staged gradient-tile row (128 + 4: 16-byte rows, conflict-free float4 phases)
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;  // 32 fp32 = 128 B = one swizzle row
@@ -172,10 +171,8 @@ __device__ __forceinline__ void adam_update(float g, float& pw, float& m, float&
 // MINB = CTAs per SM the launch is sized for: short-K products (weight gradients: K = 255 droplets; the hidden layers)
 // run two CTAs per SM with a 2-stage ring (2 x 256 TMEM columns, 2 x 97 KB of shared memory), so one CTA's epilogue
 // overlaps the other's loads -- each CTA lives for only ~8 k-blocks.
-// ADAM = the fused-optimizer variant (weight-gradient products of the large layers): four extra helper warps, and in
-// the epilogue ALL warps of the CTA sweep the gradient tile (staged in shared memory) over param / exp_avg / exp_avg_sq.
-template <int MT, int BN, bool A_MN, bool B_MN, int STAGES, int MINB, bool ADAM = false>
-__global__ void __launch_bounds__(ADAM ? kAdamThreads : kGemmThreads, MINB)
+template <int MT, int BN, bool A_MN, bool B_MN, int STAGES, int MINB>
+__global__ void __launch_bounds__(kGemmThreads, MINB)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b2, GemmParams p) {
   constexpr uint32_t kABytes = MT * kBlockM * kBlockK * 4;  // per stage
@@ -273,7 +270,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       umma_commit(&accum_bar);  // accumulator complete
     }
-  } else if (!ADAM && warp < 6) {
+  } else {
     // ======================= epilogue: TMEM -> registers (-> shared) -> global =======================
     // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns).
     //  * plain output: each thread stores its 128 contiguous bytes (8 x st.v4, fire-and-forget);
@@ -349,93 +346,207 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tc_fence_before();
   }
-  if constexpr (ADAM) {
-    // ======================= fused optimizer epilogue (all warps) =======================
-    // The four TMEM-drain warps stage one 128 x BN accumulator tile (= the weight-gradient tile, never written to
-    // HBM) in the idle operand ring; then every warp of the CTA takes rows of it: one warp instruction moves one
-    // 512-byte row segment of param / exp_avg / exp_avg_sq, four rows (12 loads) in flight per warp.
-    static_assert(!ADAM || BN == 128, "the fused optimizer epilogue is written for 128-wide tiles");
-    __syncwarp();  // producer / issuer warps: lane 0 ran the pipeline loop
-    const bool drain = warp >= 2 && warp < 6;
-    const int q = warp & 3;
-    if (drain) {
-      mbar_wait(&accum_bar, 0);
-      tc_fence_after();
-    }
-    float* tile = reinterpret_cast<float*>(smem);
-    const AdamCoef ac = adam_coef(p);
-    const int nwarps = blockDim.x >> 5;
-    const int col = n0 + 4 * lane;
-    const bool vec = (col + 3 < p.N) && ((p.ldc & 3) == 0) &&
-                     (((reinterpret_cast<uintptr_t>(p.adam_p) | reinterpret_cast<uintptr_t>(p.adam_m) |
-                        reinterpret_cast<uintptr_t>(p.adam_v)) & 15) == 0);
-#pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
-      if (drain) {
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          float v[32];
-          if (n_kb > 0) {
-            tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(mt * BN + c), v);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
-          }
-          float* dst = tile + (q * 32 + lane) * kTilePitch + c;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(int(blockDim.x)) : "memory");  // tile staged
-      const int row_base = m0 + mt * kBlockM;
-#pragma unroll 1
-      for (int r0 = warp; r0 < kBlockM; r0 += 4 * nwarps) {
-        if (vec) {
-          float4 w4[4], m4[4], v4[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {  // all loads first
-            const int r = r0 + u * nwarps;
-            if (r < kBlockM && row_base + r < p.M) {
-              const long long off = (long long)(row_base + r) * p.ldc + col;
-              w4[u] = *reinterpret_cast<const float4*>(p.adam_p + off);
-              m4[u] = *reinterpret_cast<const float4*>(p.adam_m + off);
-              v4[u] = *reinterpret_cast<const float4*>(p.adam_v + off);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int r = r0 + u * nwarps;
-            if (r < kBlockM && row_base + r < p.M) {
-              const float4 g4 = *reinterpret_cast<const float4*>(tile + r * kTilePitch + 4 * lane);
-              adam_update(g4.x, w4[u].x, m4[u].x, v4[u].x, ac);
-              adam_update(g4.y, w4[u].y, m4[u].y, v4[u].y, ac);
-              adam_update(g4.z, w4[u].z, m4[u].z, v4[u].z, ac);
-              adam_update(g4.w, w4[u].w, m4[u].w, v4[u].w, ac);
-              const long long off = (long long)(row_base + r) * p.ldc + col;
-              *reinterpret_cast<float4*>(p.adam_p + off) = w4[u];
-              *reinterpret_cast<float4*>(p.adam_m + off) = m4[u];
-              *reinterpret_cast<float4*>(p.adam_v + off) = v4[u];
-            }
-          }
-        } else if (col < p.N) {  // ragged right edge / unaligned buffers
-          const int nv = min(4, p.N - col);
-          for (int u = 0; u < 4; ++u) {
-            const int r = r0 + u * nwarps;
-            if (r >= kBlockM || row_base + r >= p.M) continue;
-            const long long off = (long long)(row_base + r) * p.ldc + col;
-            for (int i = 0; i < nv; ++i)
-              adam_update(tile[r * kTilePitch + 4 * lane + i], p.adam_p[off + i], p.adam_m[off + i], p.adam_v[off + i], ac);
-          }
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(int(blockDim.x)) : "memory");  // tile consumed before it is overwritten
-    }
-    if (drain) tc_fence_before();
-  }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Persistent weight-gradient GEMM with the ClippedAdam sweep fused behind it (cb_gemm_tf32_dw_adam).
+//   G[M, N] = A^T B for MN-major operands (A = dY stored [K, M], B = X stored [K, N], K = minibatch rows <= 512),
+//   then  param / exp_avg / exp_avg_sq [M, ldc]  <-  ClippedAdam(G)   -- G never reaches HBM.
+// One CTA per SM loops over 256 x 128 output tiles.  The accumulators are DOUBLE-BUFFERED in TMEM (2 x 256 columns):
+// while the twelve epilogue warps drain tile i (TMEM -> shared-memory staging tile) and sweep it over the optimizer
+// state (HBM-bound: 24 bytes moved per element), the TMA producer and the MMA issuer already run tile i + 1
+// (L2-bound) -- the two phases that a one-tile-per-CTA kernel executes back to back overlap here.
+//   warp 0: TMA producer   warp 1: MMA issuer   warps 2..5: TMEM drain + sweep   warps 6..13: sweep
+constexpr int kPersistThreads = 448;
+constexpr int kPersistStages = 3;
+constexpr int kPersistEpiThreads = kPersistThreads - 64;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kPersistThreads, 1)
+gemm_dw_adam_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
+  constexpr int MT = 2, BN = 128, STAGES = kPersistStages;
+  constexpr uint32_t kABytes = MT * kBlockM * kBlockK * 4;
+  constexpr uint32_t kBBytes = BN * kBlockK * 4;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kAccCols = MT * BN;  // TMEM columns of one accumulator buffer
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* tile = reinterpret_cast<float*>(smem + STAGES * kStageBytes);  // [128][kTilePitch] gradient staging tile
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (p.N + BN - 1) / BN, tiles_m = (p.M + MT * kBlockM - 1) / (MT * kBlockM);
+  const int n_tiles = tiles_n * tiles_m;
+  const int n_kb = p.k_blocks_total;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_full[0], 1), mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 4), mbar_init(&acc_empty[1], 4);  // one arrival per drain warp
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 2 * kAccCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m0 = (t / tiles_n) * (MT * kBlockM), n0 = (t % tiles_n) * BN;
+      if (lane == 0) {
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* a_dst = smem + s * kStageBytes;
+          uint8_t* b_dst = a_dst + kABytes;
+          mbar_expect_tx(&full_bar[s], kStageBytes);
+          const int k0 = kb * kBlockK;
+#pragma unroll
+          for (int j = 0; j < MT * 4; ++j) tma_load_2d(&tmap_a, &full_bar[s], a_dst + j * 4096, m0 + j * 32, k0);
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(&tmap_b, &full_bar[s], b_dst + j * 4096, n0 + j * 32, k0);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | (uint32_t(BN >> 3) << 17) |
+                             (uint32_t(kBlockM >> 4) << 24);
+      int it = 0, ti = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+        const int buf = ti & 1;
+        mbar_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator buffer
+        tc_fence_after();
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * kStageBytes);
+          const uint32_t b_base = a_base + kABytes;
+#pragma unroll
+          for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
+            const uint64_t bdesc = make_smem_desc(b_base + k4 * 1024, 4096, 512, 1);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t adesc = make_smem_desc(a_base + mt * 16384 + k4 * 1024, 4096, 512, 1);
+              umma_tf32(tmem_base + buf * kAccCols + mt * BN, adesc, bdesc, idesc, (kb > 0 || k4 > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ======================= epilogue: drain + optimizer sweep (warps 2..13) =======================
+    const int ew = warp - 2, n_ew = kPersistEpiThreads / 32;
+    const bool drain = ew < 4;
+    const int q = warp & 3;  // TMEM lane quarter of a drain warp (warps 2,3,4,5 -> 2,3,0,1)
+    const AdamCoef ac = adam_coef(p);
+    int ti = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+      const int m0 = (t / tiles_n) * (MT * kBlockM), n0 = (t % tiles_n) * BN;
+      const int buf = ti & 1;
+      const int col = n0 + 4 * lane;
+      const bool vec = (col + 3 < p.N) && ((p.ldc & 3) == 0) &&
+                       (((reinterpret_cast<uintptr_t>(p.adam_p) | reinterpret_cast<uintptr_t>(p.adam_m) |
+                          reinterpret_cast<uintptr_t>(p.adam_v)) & 15) == 0);
+      if (drain) {
+        mbar_wait(&acc_full[buf], (ti >> 1) & 1);
+        tc_fence_after();
+      }
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        if (drain) {
+#pragma unroll 1
+          for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * kAccCols + mt * BN + c), v);
+            float* dst = tile + (q * 32 + lane) * kTilePitch + c;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (mt == MT - 1) {  // both halves of this accumulator buffer are in registers / shared memory: release it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(kPersistEpiThreads) : "memory");  // staging tile written
+        const int row_base = m0 + mt * kBlockM;
+#pragma unroll 1
+        for (int r0 = ew; r0 < kBlockM; r0 += 4 * n_ew) {
+          if (vec) {
+            float4 w4[4], m4[4], v4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // all loads first
+              const int r = r0 + u * n_ew;
+              if (r < kBlockM && row_base + r < p.M) {
+                const long long off = (long long)(row_base + r) * p.ldc + col;
+                w4[u] = *reinterpret_cast<const float4*>(p.adam_p + off);
+                m4[u] = *reinterpret_cast<const float4*>(p.adam_m + off);
+                v4[u] = *reinterpret_cast<const float4*>(p.adam_v + off);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = r0 + u * n_ew;
+              if (r < kBlockM && row_base + r < p.M) {
+                const float4 g4 = *reinterpret_cast<const float4*>(tile + r * kTilePitch + 4 * lane);
+                adam_update(g4.x, w4[u].x, m4[u].x, v4[u].x, ac);
+                adam_update(g4.y, w4[u].y, m4[u].y, v4[u].y, ac);
+                adam_update(g4.z, w4[u].z, m4[u].z, v4[u].z, ac);
+                adam_update(g4.w, w4[u].w, m4[u].w, v4[u].w, ac);
+                const long long off = (long long)(row_base + r) * p.ldc + col;
+                *reinterpret_cast<float4*>(p.adam_p + off) = w4[u];
+                *reinterpret_cast<float4*>(p.adam_m + off) = m4[u];
+                *reinterpret_cast<float4*>(p.adam_v + off) = v4[u];
+              }
+            }
+          } else if (col < p.N) {  // ragged right edge / unaligned buffers
+            const int nv = min(4, p.N - col);
+            for (int u = 0; u < 4; ++u) {
+              const int r = r0 + u * n_ew;
+              if (r >= kBlockM || row_base + r >= p.M) continue;
+              const long long off = (long long)(row_base + r) * p.ldc + col;
+              for (int i = 0; i < nv; ++i)
+                adam_update(tile[r * kTilePitch + 4 * lane + i], p.adam_p[off + i], p.adam_m[off + i], p.adam_v[off + i], ac);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(kPersistEpiThreads) : "memory");  // staging tile consumed
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * kAccCols);
   }
 }
 
@@ -482,19 +593,19 @@ static int make_tmap(CUtensorMap* map, const float* base, long long rows, long l
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 
-template <int MT, int BN, bool A_MN, bool B_MN, int STAGES, int MINB, bool ADAM = false>
+template <int MT, int BN, bool A_MN, bool B_MN, int STAGES, int MINB>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
                       const GemmParams& p, cudaStream_t st) {
   constexpr int kStage = (MT * kBlockM + BN) * kBlockK * 4;
   const int smem = STAGES * kStage + 1024;
-  auto kern = gemm_tf32_kernel<MT, BN, A_MN, B_MN, STAGES, MINB, ADAM>;
+  auto kern = gemm_tf32_kernel<MT, BN, A_MN, B_MN, STAGES, MINB>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 3;
     configured = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + MT * kBlockM - 1) / (MT * kBlockM), p.split_k);
-  kern<<<grid, ADAM ? kAdamThreads : kGemmThreads, smem, st>>>(ta, tb, ta2, tb2, p);
+  kern<<<grid, kGemmThreads, smem, st>>>(ta, tb, ta2, tb2, p);
   return 0;
 }
 
@@ -601,11 +712,22 @@ static int gemm_tf32_impl(const float* A, long long lda, const float* B, long lo
     else rc = launch<MT, BN, true, true>(ta, tb, ta2, tb2, p, st);                        \
   } while (0)
   if (adam != nullptr) {
-    // fused optimizer epilogue: instantiated for the weight-gradient layout (both operands stored with the reduction
-    // dimension as rows), 256 x 128 tiles, short K (two CTAs per SM)
-    CB_REQUIRE(a_mn && b_mn && M > 128 && p.k_blocks_per_split <= 16,
-               "cb_gemm_tf32_dw_adam: needs a_mn = b_mn = 1, M > 128 and K <= 512 (got M=%d K=%d)", M, K);
-    rc = launch_cfg<2, 128, true, true, 2, 2, true>(ta, tb, ta2, tb2, p, st);
+    // fused optimizer epilogue: the weight-gradient layout (both operands stored with the reduction dimension as
+    // rows), short K; persistent kernel, one CTA per SM
+    CB_REQUIRE(a_mn && b_mn && K2 == 0 && p.k_blocks_total <= 16,
+               "cb_gemm_tf32_dw_adam: needs a_mn = b_mn = 1 and K <= 512 (got K=%d)", K);
+    constexpr int kSmem = kPersistStages * (2 * kBlockM + 128) * kBlockK * 4 + kBlockM * kTilePitch * 4 + 1024;
+    static bool configured = false;
+    if (!configured) {
+      CB_REQUIRE(cudaFuncSetAttribute(gemm_dw_adam_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) ==
+                     cudaSuccess, "cb_gemm_tf32_dw_adam: cannot reserve %d bytes of shared memory", kSmem);
+      configured = true;
+    }
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int n_tiles = ((N + 127) / 128) * ((M + 255) / 256);
+    gemm_dw_adam_persistent_kernel<<<n_tiles < n_sm ? n_tiles : n_sm, kPersistThreads, kSmem, st>>>(ta, tb, p);
   } else if (two) CB_DISPATCH(2, 128);
   else if (wide) CB_DISPATCH(1, 256);
   else CB_DISPATCH(1, 128);

@@ -8,6 +8,7 @@ clamp at +-10 (pyro ClippedAdam ``clip_norm``), beta2 0.999, eps 1e-8, no weight
 ``total_steps`` raises like torch's scheduler does (pinned by the reference's tests/test_train.py:87-108).
 ``constant_learning_rate=True`` gives plain ClippedAdam at ``lr`` with beta1 0.9 (run.py:621-627).
 """
+import os
 from typing import Iterable, List, Optional
 
 import torch
@@ -87,13 +88,14 @@ class FlatClippedAdam:
         self.beta2, self.eps, self.clip = betas[1], eps, clip_norm
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)  # optimizer steps taken (device side)
         self.host_steps = 0
-        # Optional: apply the update of the four G x 512 weight matrices (99 % of the parameters) inside the epilogue of
-        # their weight-gradient GEMM (cb_gemm_tf32_dw_adam), so that their gradients never travel to HBM and back
-        # (-25 % of a step's HBM bytes).  Correct (tests/test_gemm_gpu.py, tests/test_step_gpu.py) but OFF by default:
-        # measured on B200 (r01) the fused kernel takes 122-143 us per matrix against 55 us (GEMM) + 76 us (its share of
-        # the Adam sweep) unfused, because the co-resident CTAs run their GEMM and optimizer phases in lockstep instead
-        # of overlapping them; a persistent, TMEM-double-buffered variant is the next step.
-        self.fuse_weight_updates = False
+        # Optional (CB_FUSE_ADAM=1): apply the update of the four G x 512 weight matrices (99 % of the parameters) inside
+        # the weight-gradient GEMM itself (cb_gemm_tf32_dw_adam: persistent CTAs, TMEM-double-buffered accumulators, the
+        # gradient tile never leaves the SM), which removes the gradient write + read (-25 % of a step's HBM bytes).
+        # Correct (tests/test_gemm_gpu.py, tests/test_step_gpu.py) but OFF by default: measured on B200 (r01) the fused
+        # kernel takes 131-185 us per matrix against 55 us (GEMM) + 76 us (its share of the Adam sweep): the twelve
+        # epilogue warps keep ~72 KB of optimizer state in flight per SM and reach 3.5 TB/s, the stand-alone sweep (2048
+        # threads per SM) reaches 6.2 TB/s.  Next: move the state tiles with TMA.
+        self.fuse_weight_updates = os.environ.get("CB_FUSE_ADAM", "0") == "1"
         # Default on a single GPU: the ClippedAdam sweep of each large weight block is issued as soon as that block's
         # gradient GEMM has finished, on the same (side) stream, so that the HBM-bound sweep overlaps the rest of the
         # backward pass (which is latency / L2-bound); the sweep at the end of the step covers what is left.
