@@ -76,7 +76,7 @@ __device__ __forceinline__ void obs_zero_element(float chi, float ca, float cb_,
   const float lam0 = fmaf(c.cA0, ca, fmaf(c.cB0, cb_, 1e-10f));
   const float lamE = fmaf(c.cAE, ca, fmaf(c.cBE, cb_, 1e-10f));
   const NbpcOut o1 = nbpc_zero(mu1, inv_alpha, lam1);
-  const NbpcOut o0 = nbpc_zero(1e-10f, inv_alpha, lam0);
+  const NbpcOut o0 = nbpc_zero_mu_eps(lam0, -0.5f * 1e-10f * 1e-10f * inv_alpha * inv_alpha);
   acc[0] += o1.L;
   acc[1] += o0.L;
   acc[2] -= lamE;  // Poisson(0; lamE)

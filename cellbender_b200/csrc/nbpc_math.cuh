@@ -231,6 +231,22 @@ CB_HD NbpcOut nbpc_zero(float mu, float inv_alpha, float lam) {
 }
 
 
+// x == 0 with mu equal to the bare safeguard constant mu_eps = 1e-10 (the y = 0 enumeration branch: no cell, model.py:
+// 338-346 adds NBPC_MU_EPS_SAFEGAURD to a zero mean).  Then w = mu_eps^2 / (m alpha) <= 5e-11 / alpha is far below fp32
+// resolution, and nbpc_zero collapses, to fp32 rounding, to
+//   L = -(mu_eps + lam) (1 - w/2) = -(mu_eps + lam),   dL/dlam = -1 + w^2/3 = -1,
+//   dL/dalpha = m h(w) / alpha = -mu_eps^2 / (2 alpha^2) (1 + O(w))
+// (Poisson branch mu_eps < 1e-5 lam: L = -lam, dL/dlam = -1, dL/dalpha = 0, as in the reference.)  dL/dmu is not
+// needed: mu_eps is a constant.  neg_half_mu2_inv_alpha2 = -mu_eps^2 / (2 alpha^2) is computed once per droplet row.
+CB_HD NbpcOut nbpc_zero_mu_eps(float lam, float neg_half_mu2_inv_alpha2) {
+  NbpcOut o;
+  o.dmu = 0.f, o.dlam = -1.f;
+  const bool poisson = 1e-10f < 1e-5f * lam;
+  o.L = poisson ? -lam : -(1e-10f + lam);
+  o.dalpha = poisson ? 0.f : neg_half_mu2_inv_alpha2;
+  return o;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Exact NB(mu, alpha) (+) Poisson(lam) convolution by direct summation: NegativeBinomialPoissonConv.log_prob
 // (reference distributions/NegativeBinomialPoissonConv.py:89-154; selected by consts.USE_EXACT_LOG_PROB, off by

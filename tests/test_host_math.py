@@ -79,6 +79,18 @@ def test_nbpc_zero_count_specialisation_vs_multiprecision(hostlib):
         assert np.max(np.abs(mine - r) / scale) < 1e-4, name
         assert np.max(np.abs(mine - generic) / scale) < 1e-4, name  # and it agrees with the general-count path
 
+    # the y = 0 collapse: mu is exactly the 1e-10 safeguard; lam spans the Poisson-branch boundary (1e-5 lam vs 1e-10)
+    n0 = 3000
+    lam0 = np.exp(rng.uniform(np.log(1e-10), np.log(5.0), n0)).astype(np.float32)
+    al0 = np.exp(rng.uniform(np.log(0.05), np.log(500.0), n0)).astype(np.float32)
+    mu0 = np.full(n0, 1e-10, np.float32)
+    L0, dl0, da0 = (np.zeros(n0, np.float32) for _ in range(3))
+    hostlib.host_nbpc_zero_mu_eps(n0, _p(al0), _p(lam0), _p(L0), _p(dl0), _p(da0))
+    rL, _, rdl, rda = onb.nbpc_approx_mp(np.zeros(n0), mu0.astype(np.float64), al0.astype(np.float64), lam0.astype(np.float64))
+    assert np.max(np.abs(L0 - rL) / np.maximum(np.abs(rL), 1e-30)) < 2e-7  # relative, down to lam = 1e-10
+    assert np.max(np.abs(dl0 - rdl)) < 1e-6
+    assert np.max(np.abs(da0 - rda) / np.maximum(np.abs(rda), 1e-30)) < 1e-5  # values ~1e-20 .. 1e-18: relative
+
 
 @pytest.mark.parametrize("tag", ["big", "small", "huge"])
 def test_noise_window_fp32_math_vs_float64(hostlib, golden_dir, tag):

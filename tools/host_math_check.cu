@@ -38,3 +38,12 @@ extern "C" void host_nbpc_exact(int n, const float* v, const float* mu, const fl
     L[i] = o.L, dmu[i] = o.dmu, dlam[i] = o.dlam, dalpha[i] = o.dalpha;
   }
 }
+
+// ... and its y = 0 collapse (mu = the 1e-10 safeguard constant)
+extern "C" void host_nbpc_zero_mu_eps(int n, const float* alpha, const float* lam, float* L, float* dlam, float* dalpha) {
+  for (int i = 0; i < n; ++i) {
+    const float ia = 1.0f / alpha[i];
+    cb::NbpcOut o = cb::nbpc_zero_mu_eps(lam[i], -0.5f * 1e-10f * 1e-10f * ia * ia);
+    L[i] = o.L, dlam[i] = o.dlam, dalpha[i] = o.dalpha;
+  }
+}
