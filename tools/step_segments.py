@@ -9,7 +9,9 @@ def main(path, verbose=False):
     lines = [l for l in open(path) if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
     names = [r["Kernel Name"] for r in rows]
-    idx = [i for i, n in enumerate(names) if "clipped_adam" in n]
+    # one advance_step_kernel per optimizer step closes a step; the roofline loop of bench.py at the end launches it
+    # back to back, so take the last pair that encloses a whole step
+    idx = [i for i, n in enumerate(names) if "advance_step" in n]
     gaps = [(idx[i], idx[i + 1] - idx[i]) for i in range(len(idx) - 1)]
     big = [g for g in gaps if g[1] > 50]
     a = big[-1][0] + 1
@@ -41,6 +43,17 @@ def main(path, verbose=False):
     if cnt:
         print(f"   ... {cnt} torch kernels, {t:.0f} us")
     print(f"# kernels {len(seg)}  sum {tot:.1f} us  ours {ours:.1f} us  torch {tot - ours:.1f} us")
+    import collections
+
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in seg:
+        n = re.sub(r"[(].*", "", r["Kernel Name"]).replace("void ", "")
+        n = re.sub(r"at::native::|<unnamed>::", "", n)[:70]
+        agg[n][0] += 1
+        agg[n][1] += val(r)
+    print("# share_%   total_us   launches   kernel")
+    for n, (c, t_) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
+        print(f"{100 * t_ / tot:7.2f}  {t_:9.1f}  {c:5d}   {n}")
 
 
 if __name__ == "__main__":
