@@ -5,9 +5,10 @@ surface; SURVEY.md section 8e states the semantics.
 
 Training (data parallel): every rank holds the full parameter set and the surely-empty droplets, and a disjoint
 shard of the analysed droplets (``shard_rows``).  Each step every rank runs its own 255-droplet minibatch (forward + backward as one CUDA-graph replay); the ELBO is
-a plain SUM over droplets (train.py:56-63), so the exchange is ONE all-reduce(SUM) of the flat fp32 gradient buffer
-(69.4 M values at the PBMC8k shape), issued eagerly between graph replays, after which every rank applies the
-identical fused ClippedAdam update.
+a plain SUM over droplets (train.py:56-63), so the exchange is ONE reduction of the flat fp32 gradient buffer
+(69.4 M values at the PBMC8k shape), issued eagerly between graph replays: by default reduce-scatter -> ClippedAdam sweep
+of this rank's 1/world_size shard -> all-gather of the parameters (``reduce_scatter_step``); ``CB_DP_MODE=allreduce``
+selects all-reduce + the full sweep on every rank.
 Stated consequences: the global minibatch is 255 x world_size droplets; an epoch is n_batches(shard) steps, so
 OneCycleLR's total_steps shrinks by world_size; BatchNorm statistics, Dropout1d masks, epsilon medians and the
 reparameterisation noise are per-rank (different CUDA seeds per rank; ``sync_buffers`` averages the BN running
@@ -50,8 +51,13 @@ def attach(svi, world_size: int):
         # measured on 2 x B200 (r01, ms/step): 1 piece 2.04, 2 pieces 2.10, 4 pieces 2.14 -- the Adam sweep is HBM-bound and
         # the NCCL kernels compete for the same HBM, so pipelining them buys nothing; one all-reduce is the default
         n_chunks = int(os.environ.get("CB_DP_CHUNKS", "1"))
+        mode = os.environ.get("CB_DP_MODE", "sharded")
         if n_chunks > 1:
             svi.exchange_and_step = lambda opt: allreduce_and_step(opt, n_chunks)
+        elif mode == "sharded" and svi.optim.n % (4 * world_size) == 0:
+            # default: reduce-scatter -> every rank sweeps 1/world_size of the flat buffers -> all-gather of the
+            # parameters.  Same bytes on the NVLink fabric as the all-reduce, 1/world_size of the 1.9 GB optimizer sweep.
+            svi.exchange_and_step = lambda opt: reduce_scatter_step(opt, world_size, rank)
     svi.sync_offsets = lambda: broadcast_encoder_offsets(svi.model)
     return svi
 
@@ -84,6 +90,39 @@ def allreduce_and_step(opt, n_chunks: int = 8):
         L.call("cb_clipped_adam_range", at(opt.flat_p), at(opt.flat_g), at(opt.flat_m), at(opt.flat_v), b - a, *tab,
                1 if i == len(bounds) - 1 else 0, st)
     opt.host_steps += 1
+
+
+@torch.no_grad()
+def reduce_scatter_step(opt, world_size: int, rank: int):
+    """Data-parallel exchange with a sharded optimizer sweep: reduce_scatter(SUM) of the flat gradient buffer, ClippedAdam on
+    this rank's contiguous shard of param / exp_avg / exp_avg_sq, all_gather of the updated parameter shards (in place).
+    Arithmetic per element is that of ``all_reduce`` + ``opt.step()`` (NCCL's reduction order aside); only this rank's
+    shard of the moment buffers is current -- ``gather_optimizer_state`` completes them before a checkpoint."""
+    from ._cabi import current_stream, lib
+
+    if not opt.constant_learning_rate and opt.host_steps >= opt.total_steps:
+        raise ValueError(f"Tried to step {opt.host_steps + 1} times. The specified number of total steps is {opt.total_steps}")
+    sh = opt.n // world_size
+    a = rank * sh
+    if getattr(opt, "_g_shard", None) is None or opt._g_shard.numel() != sh:
+        opt._g_shard = torch.empty(sh, dtype=torch.float32, device=opt.flat_g.device)
+    dist.reduce_scatter_tensor(opt._g_shard, opt.flat_g, op=dist.ReduceOp.SUM)
+    at = lambda t: t.data_ptr() + 4 * a
+    lib().call("cb_clipped_adam_range", at(opt.flat_p), opt._g_shard.data_ptr(), at(opt.flat_m), at(opt.flat_v), sh,
+               opt.lr_table.data_ptr(), opt.beta1_table.data_ptr(), opt.lr_table.numel(), opt.step_count.data_ptr(),
+               float(opt.beta2), float(opt.eps), float(opt.clip), 1, current_stream())
+    dist.all_gather_into_tensor(opt.flat_p, opt.flat_p[a:a + sh])
+    opt.host_steps += 1
+
+
+@torch.no_grad()
+def gather_optimizer_state(opt, world_size: int, rank: int):
+    """Make the moment buffers complete on every rank after sharded stepping (call before saving a checkpoint)."""
+    if world_size <= 1:
+        return
+    sh = opt.n // world_size
+    for buf in (opt.flat_m, opt.flat_v):
+        dist.all_gather_into_tensor(buf, buf[rank * sh:(rank + 1) * sh].clone())
 
 
 @torch.no_grad()

@@ -54,7 +54,8 @@ class FlatClippedAdam:
             self.offsets.append(off)
             self.lds.append(ld)
             off += (n + 3) // 4 * 4
-        self.n = off
+        self.n = (off + 63) // 64 * 64  # a multiple of 4 x (1, 2, 4, 8, 16) ranks: equal 16-byte-aligned shards (dp.py)
+        off = self.n
         self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(off, dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(off, dtype=torch.float32, device=dev)
