@@ -397,9 +397,15 @@ def run_b200(args):
                                    "noise_counts_removed": int(noise_csr.sum()), "output": "scipy CSR on the host (reference API)"}
         model.train()
 
-    if rank != 0:
+    def shutdown():
         if world > 1:
+            svi._graphs.clear()  # graphs that captured NCCL collectives must go before the process group does
+            torch.cuda.synchronize()
+            dist.barrier()
             dist.destroy_process_group()
+
+    if rank != 0:
+        shutdown()
         return
 
     # ---- CPU baseline: the reference-style port on this box's host cores, bounded sample ----
@@ -443,8 +449,7 @@ def run_b200(args):
         "cpu_baseline": cpu, "reference_torch_cuda": torch_cuda, "posterior": posterior,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 if __name__ == "__main__":

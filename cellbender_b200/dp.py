@@ -51,8 +51,16 @@ def attach(svi, world_size: int):
         # measured on 2 x B200 (r01, ms/step): 1 piece 2.04, 2 pieces 2.10, 4 pieces 2.14 -- the Adam sweep is HBM-bound and
         # the NCCL kernels compete for the same HBM, so pipelining them buys nothing; one all-reduce is the default
         n_chunks = int(os.environ.get("CB_DP_CHUNKS", "1"))
-        mode = os.environ.get("CB_DP_MODE", "sharded")
-        if n_chunks > 1:
+        mode = os.environ.get("CB_DP_MODE", "overlap")
+        if mode == "overlap" and n_chunks <= 1:
+            # default: the reduction of each large gradient block is issued right behind its weight-gradient GEMM, on
+            # that GEMM's side stream, followed by the ClippedAdam sweep of the block -- inside backward and inside the
+            # captured step graph (NCCL collectives capture fine; drop the graphs before destroying the process group) --
+            # so most of the 278 MB exchange overlaps the rest of backward; the small tail is reduced at the end
+            svi.optim.dp_reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            svi.optim.early_weight_updates = True
+            svi.dp_overlap = True
+        elif n_chunks > 1:
             svi.exchange_and_step = lambda opt: allreduce_and_step(opt, n_chunks)
         elif mode == "sharded" and svi.optim.n % (4 * world_size) == 0:
             # default: reduce-scatter -> every rank sweeps 1/world_size of the flat buffers -> all-gather of the

@@ -26,7 +26,7 @@ BACKEND = "tcgen05"
 FUSED_OPT = None
 # only matrices with at least this many elements take the fused path: the epilogue needs many CTAs to stream the
 # optimizer state at HBM speed (a 512 x 512 layer has 8 tiles; its fused update is slower than the separate sweep)
-FUSED_MIN_NUMEL = 1 << 22
+FUSED_MIN_NUMEL = 1 << 22  # = optim.BIG_BLOCK_NUMEL: the blocks the optimizer lays out first
 
 
 def set_backend(name: str):

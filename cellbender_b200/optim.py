@@ -17,6 +17,9 @@ import torch.nn as nn
 from . import ops
 
 
+BIG_BLOCK_NUMEL = 1 << 22  # the G x 512 matrices (17 M elements each at the PBMC8k shape)
+
+
 def one_cycle_tables(learning_rate: float, total_steps: int):
     """Per-step (lr, beta1) of torch.optim.lr_scheduler.OneCycleLR wrapped around an Adam-family optimizer."""
     dummy = torch.optim.Adam([torch.zeros(1, requires_grad=True)], lr=learning_rate, betas=(0.9, 0.999))
@@ -47,13 +50,21 @@ class FlatClippedAdam:
         def padded_ld(p):
             return (p.shape[1] + 3) // 4 * 4 if (p.dim() == 2 and p.numel() >= (1 << 16)) else None
 
-        self.offsets, self.lds, off = [], [], 0
-        for p in self.params:
+        # layout: the few very large matrices first (each one is a unit of the piecewise optimizer sweep and, data
+        # parallel, of the overlapped gradient reduction), everything else behind them in ONE contiguous tail
+        big = [p.dim() == 2 and p.numel() >= BIG_BLOCK_NUMEL for p in self.params]
+        order = [i for i, b in enumerate(big) if b] + [i for i, b in enumerate(big) if not b]
+        self.offsets, self.lds, off = [0] * len(self.params), [None] * len(self.params), 0
+        self.tail_start = 0
+        for i in order:
+            p = self.params[i]
             ld = padded_ld(p)
             n = p.numel() if ld is None else p.shape[0] * ld
-            self.offsets.append(off)
-            self.lds.append(ld)
+            self.offsets[i] = off
+            self.lds[i] = ld
             off += (n + 3) // 4 * 4
+            if big[i]:
+                self.tail_start = off
         self.n = (off + 63) // 64 * 64  # a multiple of 4 x (1, 2, 4, 8, 16) ranks: equal 16-byte-aligned shards (dp.py)
         off = self.n
         self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
@@ -101,6 +112,10 @@ class FlatClippedAdam:
         # gradient GEMM has finished, on the same (side) stream, so that the HBM-bound sweep overlaps the rest of the
         # backward pass (which is latency / L2-bound); the sweep at the end of the step covers what is left.
         self.early_weight_updates = True
+        # data parallel (dp.attach): callable that all-reduces a contiguous slice of the flat gradient buffer.  With it
+        # set, every early block update first reduces that block across ranks (on the side stream of its gradient GEMM,
+        # i.e. overlapped with the rest of backward) and step() reduces what is left before sweeping it.
+        self.dp_reduce = None
         self._fused_done: List[tuple] = []
 
     def zero_grad(self):
@@ -144,6 +159,8 @@ class FlatClippedAdam:
 
         o, rows, ld, cols = w._cb_block
         at = lambda t: t.data_ptr() + 4 * o
+        if self.dp_reduce is not None:
+            self.dp_reduce(self.flat_g[o:o + rows * ld])
         lib().call("cb_clipped_adam_range", at(self.flat_p), at(self.flat_g), at(self.flat_m), at(self.flat_v), rows * ld,
                    self.lr_table.data_ptr(), self.beta1_table.data_ptr(), self.lr_table.numel(), self.step_count.data_ptr(),
                    float(self.beta2), float(self.eps), float(self.clip), 0, current_stream())
@@ -165,6 +182,14 @@ class FlatClippedAdam:
                    float(self.beta2), float(self.eps), float(self.clip))
             at = lambda t, off: t.data_ptr() + 4 * off
             cur = 0
+            if self.dp_reduce is not None:  # reduce the ranges no early block update has covered (normally: the tail)
+                c0 = 0
+                for o, rows, ld, cols, off in sorted(self._fused_done):
+                    if o > c0:
+                        self.dp_reduce(self.flat_g[c0:o])
+                    c0 = o + rows * ld
+                if self.n > c0:
+                    self.dp_reduce(self.flat_g[c0:self.n])
             for o, rows, ld, cols, off in sorted(self._fused_done):
                 assert o >= cur, "fused blocks overlap"
                 L.call("cb_clipped_adam_range", at(self.flat_p, cur), at(self.flat_g, cur), at(self.flat_m, cur),
@@ -177,6 +202,8 @@ class FlatClippedAdam:
                    self.n - cur, *tab, 1, st)
             self._fused_done = []
         else:
+            if self.dp_reduce is not None:
+                self.dp_reduce(self.flat_g)
             ops.clipped_adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_table, self.beta1_table,
                                   self.step_count, beta2=self.beta2, eps=self.eps, clip=self.clip, grad_scale=grad_scale)
         self.host_steps += 1

@@ -53,6 +53,7 @@ class SVI:
         self._eager_steps = 0
         self.after_backward = None  # hook(optim): e.g. the data-parallel gradient all-reduce (dp.attach)
         self.exchange_and_step = None  # hook(optim): all-reduce pipelined with the optimizer sweep (dp.attach)
+        self.dp_overlap = False  # data parallel with the reductions issued inside backward / the step graph (dp.attach)
 
     def _ambient_unit_vector(self) -> torch.Tensor:
         """x_ambient / ||x_ambient||_2 of EncodeNonZLatents.forward (vae/encoder.py:266-270); the d_empty factor
@@ -73,7 +74,7 @@ class SVI:
         terms = self.loss_terms(batch)
         loss = terms["loss"]
         # single GPU: the large weight matrices are updated inside their weight-gradient GEMMs (optim.fused_dw)
-        fuse = (self.after_backward is None and self.model.training
+        fuse = ((self.after_backward is None or self.dp_overlap) and self.model.training
                 and (self.optim.fuse_weight_updates or getattr(self.optim, "early_weight_updates", False)))
         gemm.FUSED_OPT = self.optim if fuse else None
         try:
@@ -89,6 +90,9 @@ class SVI:
         return loss
 
     def _exchange_and_step(self):
+        if self.dp_overlap:
+            self.optim.step()  # reduces whatever the early block updates have not covered, then sweeps it
+            return
         if self.exchange_and_step is not None:
             self.exchange_and_step(self.optim)  # chunked all-reduce overlapped with the Adam sweep of earlier chunks
             return
@@ -113,8 +117,8 @@ class SVI:
                              f"{self.optim.total_steps}")
         graph.replay()
         _cabi.lib().launch_count += n_launch  # kernels of ours inside the replayed graph
-        if self.after_backward is not None:
-            # data parallel: the gradient all-reduce (NCCL) and the fused Adam run eagerly between graph replays
+        if self.after_backward is not None and not self.dp_overlap:
+            # data parallel, exchange outside the graph: all-reduce (NCCL) and the fused Adam run eagerly between replays
             self._exchange_and_step()
         else:
             self.optim.host_steps += 1
@@ -128,7 +132,7 @@ class SVI:
         snap_step, host_steps = self.optim.step_count.clone(), self.optim.host_steps
         bn_state = {k: v.clone() for k, v in self.model.state_dict().items() if "running_" in k or "num_batches" in k}
         # single GPU: the whole step is one graph.  Data parallel: forward + backward + gradient collection only.
-        body = self._step_eager if self.after_backward is None else self._forward_backward
+        body = self._step_eager if (self.after_backward is None or self.dp_overlap) else self._forward_backward
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -61,6 +61,8 @@ def _worker(rank, world, port, q):
             ok_post = (torch.equal(ref.m, full.m) and torch.equal(ref.c, full.c) and torch.equal(ref.log_prob, full.log_prob)
                        and torch.equal(ref.off_m, full.off_m) and torch.equal(ref.off_v, full.off_v) and ref.m.numel() > 1000)
         q.put((rank, same, moved, ok_post, len(svi._graphs)))
+        svi._graphs.clear()  # graphs that captured NCCL collectives must be gone before the process group is destroyed
+        torch.cuda.synchronize()
     finally:
         dist.destroy_process_group()
 
