@@ -51,12 +51,14 @@ def attach(svi, world_size: int):
         # measured on 2 x B200 (r01, ms/step): 1 piece 2.04, 2 pieces 2.10, 4 pieces 2.14 -- the Adam sweep is HBM-bound and
         # the NCCL kernels compete for the same HBM, so pipelining them buys nothing; one all-reduce is the default
         n_chunks = int(os.environ.get("CB_DP_CHUNKS", "1"))
-        mode = os.environ.get("CB_DP_MODE", "overlap")
+        # measured on B200 (r01, ms/step at 2 / 4 GPUs): sharded 1.87 / 1.96, overlap 1.92 / 2.06, allreduce 1.87 / 2.10
+        mode = os.environ.get("CB_DP_MODE", "sharded")
         if mode == "overlap" and n_chunks <= 1:
-            # default: the reduction of each large gradient block is issued right behind its weight-gradient GEMM, on
+            # optional: the reduction of each large gradient block is issued right behind its weight-gradient GEMM, on
             # that GEMM's side stream, followed by the ClippedAdam sweep of the block -- inside backward and inside the
-            # captured step graph (NCCL collectives capture fine; drop the graphs before destroying the process group) --
-            # so most of the 278 MB exchange overlaps the rest of backward; the small tail is reduced at the end
+            # captured step graph (NCCL collectives capture fine; drop the graphs before destroying the process group).
+            # It hides the exchange behind backward but measures slower than the sharded sweep: the NCCL kernels and the
+            # backward kernels compete for the same HBM / L2 bandwidth.
             svi.optim.dp_reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
             svi.optim.early_weight_updates = True
             svi.dp_overlap = True
