@@ -21,6 +21,7 @@
 //
 // Skinny shapes (M = 255 with K = 33 538) are split along K across CTAs; partial tiles go to a workspace with
 // plain stores and a second kernel sums them in a fixed order (deterministic; no floating-point atomics).
+#include <cstdlib>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -65,6 +66,28 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// the same box delivered to the same shared-memory offset (and mbarrier) of every CTA of the cluster named in cta_mask
+__device__ __forceinline__ void tma_load_2d_multicast(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
@@ -171,7 +194,12 @@ __device__ __forceinline__ void adam_update(float g, float& pw, float& m, float&
 // MINB = CTAs per SM the launch is sized for: short-K products (weight gradients: K = 255 droplets; the hidden layers)
 // run two CTAs per SM with a 2-stage ring (2 x 256 TMEM columns, 2 x 97 KB of shared memory), so one CTA's epilogue
 // overlaps the other's loads -- each CTA lives for only ~8 k-blocks.
-template <int MT, int BN, bool A_MN, bool B_MN, int STAGES, int MINB>
+// CLUSTER = 4: the four CTAs that compute the four 128-wide column tiles of the same rows form a thread-block cluster and
+// share the A (activation) tile: each CTA fetches one quarter of it and TMA multicasts that quarter into the shared
+// memory of all four, so the activation matrix crosses the L2 -> SM fabric once instead of four times (the skinny
+// forward products are bound by exactly that traffic).  A stage is released to the producers of all four CTAs by a
+// multicast tcgen05.commit; empty barriers therefore count four arrivals.
+template <int MT, int BN, bool A_MN, bool B_MN, int STAGES, int MINB, int CLUSTER = 1>
 __global__ void __launch_bounds__(kGemmThreads, MINB)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b2, GemmParams p) {
@@ -200,7 +228,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CLUSTER);
     }
     mbar_init(&accum_bar, 1);
     fence_barrier_init();
@@ -210,6 +238,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  static_assert(CLUSTER == 1 || (!A_MN && (MT * kBlockM) % CLUSTER == 0), "multicast is written for K-major A tiles");
+  constexpr uint16_t kClusterMask = uint16_t((1u << CLUSTER) - 1);
+  uint32_t cta_rank = 0;
+  if constexpr (CLUSTER > 1) {
+    cta_rank = cluster_cta_rank();
+    cluster_sync_all();  // every CTA's barriers are initialised before any peer multicasts into them
+  }
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -227,7 +262,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const CUtensorMap* ma = second ? &tmap_a2 : &tmap_a;
         const CUtensorMap* mb = second ? &tmap_b2 : &tmap_b;
         const int k0 = (second ? kb - p.k_blocks_first : kb) * kBlockK;
-        if (!A_MN) {
+        if constexpr (CLUSTER > 1) {
+          // this CTA's quarter of the A tile (rows cta_rank * 64 ..), delivered to all CTAs of the cluster
+          constexpr int kRows = MT * kBlockM / CLUSTER;
+          tma_load_2d_multicast(ma, &full_bar[s], a_dst + cta_rank * (kRows * kBlockK * 4), k0, m0 + int(cta_rank) * kRows,
+                                kClusterMask);
+        } else if constexpr (!A_MN) {
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) tma_load_2d(ma, &full_bar[s], a_dst + mt * 16384, k0, m0 + mt * kBlockM);
         } else {
@@ -266,7 +306,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             umma_tf32(tmem_base + mt * BN, adesc, bdesc, idesc, (i > 0 || k4 > 0) ? 1u : 0u);
           }
         }
-        umma_commit(&empty_bar[s]);  // stage free once these MMAs have read it
+        if (CLUSTER > 1) umma_commit_multicast(&empty_bar[s], kClusterMask);  // every peer writes into this stage
+        else umma_commit(&empty_bar[s]);  // stage free once these MMAs have read it
       }
       umma_commit(&accum_bar);  // accumulator complete
     }
@@ -347,6 +388,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tc_fence_before();
   }
   __syncthreads();
+  if constexpr (CLUSTER > 1) cluster_sync_all();  // no CTA leaves while peers may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -609,6 +651,31 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   return 0;
 }
 
+// cluster-of-4 variant (A tile multicast): the split-K forward shape, grid.x == 4
+template <bool B_MN>
+static int launch_cluster4(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                           const GemmParams& p, cudaStream_t st) {
+  constexpr int MT = 2, BN = 128, STAGES = 4;
+  constexpr int kStage = (MT * kBlockM + BN) * kBlockK * 4;
+  const int smem = STAGES * kStage + 1024;
+  auto kern = gemm_tf32_kernel<MT, BN, false, B_MN, STAGES, 1, 4>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 3;
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((p.N + BN - 1) / BN, (p.M + MT * kBlockM - 1) / (MT * kBlockM), p.split_k);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, ta2, tb2, p) == cudaSuccess ? 0 : 4;
+}
+
 template <int MT, int BN, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
                   const GemmParams& p, cudaStream_t st) {
@@ -687,14 +754,24 @@ static int gemm_tf32_impl(const float* A, long long lda, const float* B, long lo
     p.bias = nullptr;
   }
   CUtensorMap ta, tb, ta2, tb2;
+  // Skinny split-K products with four column tiles (the 512-wide encoder layers and the decoder's dh) can run as
+  // clusters of four CTAs with the A tile multicast (each CTA fetches a 64-row quarter).  Measured on B200 this is
+  // SLOWER for the training step (1.35-1.38 ms against 1.33 ms per step: the products are bound by HBM latency per
+  // CTA, not by L2 -> SM traffic, and 37 four-CTA clusters place worse than 148 free CTAs), so it is opt-in:
+  // CB_GEMM_CLUSTER=1.  Read per call so tests can switch it.
+  const char* cluster_env = getenv("CB_GEMM_CLUSTER");
+  const bool cluster_enabled = cluster_env != nullptr && cluster_env[0] == '1';
+  const bool cluster4 = cluster_enabled && adam == nullptr && !a_mn && M > 128 && M <= 256 && split_k > 1 && (N + 127) / 128 == 4 &&
+                        p.k_blocks_per_split > 16;
+  const int a_box = cluster4 ? 64 : 128;
   // K-major operand: tensor [rows = M|N, cols = K], box 32 x 128 rows.  MN-major: tensor [rows = K, cols = M|N], box 32 x 32 rows.
-  int e = a_mn ? make_tmap(&ta, A, K, M, lda, 32, true) : make_tmap(&ta, A, M, K, lda, 128, false);
+  int e = a_mn ? make_tmap(&ta, A, K, M, lda, 32, true) : make_tmap(&ta, A, M, K, lda, a_box, false);
   CB_REQUIRE(e == 0, "cb_gemm_tf32: cuTensorMapEncodeTiled failed for A (code %d)", e);
   e = b_mn ? make_tmap(&tb, B, K, N, ldb, 32, true) : make_tmap(&tb, B, N, K, ldb, 128, false);
   CB_REQUIRE(e == 0, "cb_gemm_tf32: cuTensorMapEncodeTiled failed for B (code %d)", e);
   ta2 = ta, tb2 = tb;
   if (K2 > 0) {
-    e = a_mn ? make_tmap(&ta2, A2, K2, M, lda2, 32, true) : make_tmap(&ta2, A2, M, K2, lda2, 128, false);
+    e = a_mn ? make_tmap(&ta2, A2, K2, M, lda2, 32, true) : make_tmap(&ta2, A2, M, K2, lda2, a_box, false);
     CB_REQUIRE(e == 0, "cb_gemm_tf32: cuTensorMapEncodeTiled failed for A2 (code %d)", e);
     e = b_mn ? make_tmap(&tb2, B2, K2, N, ldb2, 32, true) : make_tmap(&tb2, B2, N, K2, ldb2, 128, false);
     CB_REQUIRE(e == 0, "cb_gemm_tf32: cuTensorMapEncodeTiled failed for B2 (code %d)", e);
@@ -728,6 +805,8 @@ static int gemm_tf32_impl(const float* A, long long lda, const float* B, long lo
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int n_tiles = ((N + 127) / 128) * ((M + 255) / 256);
     gemm_dw_adam_persistent_kernel<<<n_tiles < n_sm ? n_tiles : n_sm, kPersistThreads, kSmem, st>>>(ta, tb, p);
+  } else if (cluster4) {
+    rc = b_mn ? launch_cluster4<true>(ta, tb, ta2, tb2, p, st) : launch_cluster4<false>(ta, tb, ta2, tb2, p, st);
   } else if (two) CB_DISPATCH(2, 128);
   else if (wide) CB_DISPATCH(1, 256);
   else CB_DISPATCH(1, 128);

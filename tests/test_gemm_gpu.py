@@ -53,6 +53,16 @@ def test_gemm_split_k_bias_accumulate(split_k):
     _check(255, 130, 999, False, False, split_k=1, bias=True, accumulate=True)
 
 
+def test_gemm_cluster_multicast_variant(monkeypatch):
+    """CB_GEMM_CLUSTER=1: the split-K products with four column tiles run as four-CTA clusters with the A tile TMA
+    multicast; same results as the default kernel (both major orders of B, bias, accumulate, ragged K)."""
+    monkeypatch.setenv("CB_GEMM_CLUSTER", "1")
+    _check(255, 512, 5000, False, False, split_k=7, bias=True)
+    _check(255, 512, 5000, False, True, split_k=7, bias=True, accumulate=True)
+    _check(200, 400, 33538, False, False, bias=True)
+    _check(255, 512, 33538, False, True)
+
+
 def test_gemm_training_step_shapes():
     """PBMC8k shapes: G = 33 538 (not a multiple of 4 -> padded leading dimension), B = 255, H = 512."""
     G, Bn, H = 33538, 255, 512
