@@ -22,21 +22,11 @@ from torch.distributions import Beta, Gamma, LogNormal, Normal
 
 from . import consts, gemm, ops
 from .estimation import DevicePosteriorCOO, EstimationMethod, IndexConverter
+from .sparse_utils import csr_set_rows_to_zero, subtract_noise_in_cells  # noqa: F401  (re-exported like the reference)
 from .model import RemoveBackgroundPyroModel
 from .vae import EncoderInputs
 
 logger = logging.getLogger("cellbender")
-
-
-def csr_set_rows_to_zero(csr: sp.csr_matrix, row_inds) -> sp.csr_matrix:
-    """reference sparse_utils.py:58-73 (vectorised)."""
-    csr = csr.tocsr(copy=True)
-    row_inds = np.fromiter(row_inds, dtype=np.int64) if not isinstance(row_inds, np.ndarray) else row_inds
-    mask = np.zeros(csr.shape[0], dtype=bool)
-    mask[row_inds] = True
-    csr.data[np.repeat(mask, np.diff(csr.indptr))] = 0
-    csr.eliminate_zeros()
-    return csr
 
 
 class Posterior:
@@ -268,18 +258,23 @@ class Posterior:
 
     # ---- denoised counts (posterior.py:282-330) --------------------------------------------------------------
     def compute_denoised_counts(self, estimator_constructor: "type[EstimationMethod]", **kwargs) -> sp.csc_matrix:
-        if self._noise_count_posterior_coo is None and self._device_posterior is None:
-            self.cell_noise_count_posterior_coo()
+        """Clean output count matrix: observed counts of the called cells minus the point estimate of their noise.
+        A regularized posterior, once computed, takes priority (posterior.py:297-303)."""
         estimator = estimator_constructor(index_converter=self.index_converter)
-        if self._device_posterior is not None:
-            noise_csr = estimator.estimate_noise(noise_log_prob_coo=self._device_posterior, noise_offsets=None, **kwargs)
-        else:
-            noise_csr = estimator.estimate_noise(noise_log_prob_coo=self._noise_count_posterior_coo,
+        if self._noise_count_regularized_posterior_coo is not None:
+            logger.debug("Using regularized posterior to compute denoised counts")
+            noise_csr = estimator.estimate_noise(noise_log_prob_coo=self._noise_count_regularized_posterior_coo,
                                                  noise_offsets=self._noise_count_posterior_coo_offsets, **kwargs)
-        count_matrix = self.dataset_obj.matrix
+        else:
+            if self._noise_count_posterior_coo is None and self._device_posterior is None:
+                self.cell_noise_count_posterior_coo()
+            if self._device_posterior is not None:
+                noise_csr = estimator.estimate_noise(noise_log_prob_coo=self._device_posterior, noise_offsets=None, **kwargs)
+            else:
+                noise_csr = estimator.estimate_noise(noise_log_prob_coo=self._noise_count_posterior_coo,
+                                                     noise_offsets=self._noise_count_posterior_coo_offsets, **kwargs)
+        # subtract cell noise from the observed counts of the called cells; every other droplet is empty in the output
+        # (posterior.py:315-328), one fused device pass (csrc/csr_combine.cu)
+        count_matrix = self.dataset_obj.matrix  # all barcodes
         cell_inds = np.asarray(self.dataset_obj.analyzed_barcode_inds)[self.latents_map["p"] > consts.CELL_PROB_CUTOFF]
-        empty_logic = np.ones(count_matrix.shape[0], dtype=bool)
-        empty_logic[cell_inds] = False
-        cell_counts = csr_set_rows_to_zero(csr=count_matrix, row_inds=np.flatnonzero(empty_logic))
-        denoised_counts = cell_counts - noise_csr
-        return denoised_counts.tocsc()
+        return subtract_noise_in_cells(count_matrix, noise_csr, cell_inds)

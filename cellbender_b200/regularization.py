@@ -179,7 +179,7 @@ class PRmu(PosteriorRegularization):
                    **kwargs) -> sp.coo_matrix:
         """Same signature and return type as the reference (posterior.py:1429-1530)."""
         from .estimation import compute_mean_target_removal_as_function
-        from .posterior import csr_set_rows_to_zero
+        from .sparse_utils import combine_csr
 
         assert index_converter is not None, "index_converter is required for PRmu.regularize"
         assert raw_count_matrix is not None, "raw_count_matrix is required for PRmu.regularize"
@@ -188,7 +188,7 @@ class PRmu(PosteriorRegularization):
         G = index_converter.total_n_genes
         included = np.unique(torch.div(subset.m, G, rounding_mode="floor").cpu().numpy())
         excluded = np.setdiff1d(np.arange(raw_count_matrix.shape[0]), included)
-        raw_count_csr_for_cells = csr_set_rows_to_zero(csr=raw_count_matrix, row_inds=excluded)
+        raw_count_csr_for_cells = combine_csr(raw_count_matrix, zero_rows=excluded)  # does not touch the caller's matrix
         target_fun = compute_mean_target_removal_as_function(
             noise_count_posterior_coo=subset, noise_offsets=None, index_converter=index_converter,
             raw_count_csr_for_cells=raw_count_csr_for_cells, n_cells=len(included), device=str(p.m.device), per_gene=per_gene)

@@ -1,0 +1,193 @@
+"""Host mirror of the sparse-matrix helpers the reference uses to assemble the output count matrix
+(cellbender/remove_background/sparse_utils.py:58-100, posterior.py:315-328, data/dataset.py:495-528), running on the
+device through csrc/csr_combine.cu.  Same names and argument meaning as the reference; scipy matrices in, scipy
+matrices out.  No CPU fallback: a missing CUDA extension or device raises.
+
+All of them are instances of one row-wise combination
+
+    out[n, g] = row_keep[n] * ( col_a[g] * A[n, g] + sign * col_b[g] * B[n, g] )        (explicit zeros dropped)
+
+evaluated by ``combine_csr`` in two kernel passes plus two prefix scans (integer / byte work, bit-exact).
+"""
+from dataclasses import dataclass
+from typing import Iterable, Optional, Tuple
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _cabi, ops
+from ._cabi import current_stream, ptr
+
+_DTYPE_CODES = {np.dtype(np.int32): 0, np.dtype(np.int64): 1, np.dtype(np.float32): 2, np.dtype(np.float64): 3}
+_TORCH_OF = {0: torch.int32, 1: torch.int64, 2: torch.float32, 3: torch.float64}
+
+
+def _value_dtype(*dtypes) -> np.dtype:
+    """numpy's result type of the operands, widened to one of the four value types the kernels are built for."""
+    dt = np.result_type(*dtypes)
+    if dt in _DTYPE_CODES:
+        return dt
+    if dt.kind in "bui":
+        return np.dtype(np.int32) if np.can_cast(dt, np.int32) else np.dtype(np.int64)
+    if dt.kind == "f":
+        return np.dtype(np.float32) if dt.itemsize <= 4 else np.dtype(np.float64)
+    raise TypeError(f"unsupported sparse value dtype {dt}")
+
+
+@dataclass
+class DeviceSparse:
+    """Canonical CSR on the device: ptr int64[R+1], idx int32[nnz] sorted per row, val in one of the kernel dtypes."""
+
+    ptr: torch.Tensor
+    idx: torch.Tensor
+    val: torch.Tensor
+    shape: Tuple[int, int]
+
+    @property
+    def nnz(self) -> int:
+        return int(self.idx.numel())
+
+    @staticmethod
+    def from_scipy(mat, dtype: np.dtype, device) -> "DeviceSparse":
+        if not isinstance(mat, sp.csr_matrix):
+            mat = sp.csr_matrix(mat)
+        if not mat.has_canonical_format:
+            mat = mat.copy()
+            mat.sum_duplicates()
+        if mat.shape[0] >= 2 ** 31 or mat.shape[1] >= 2 ** 31:
+            raise ValueError("matrix dimensions must fit int32 indices")
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(device, non_blocking=False)
+        return DeviceSparse(up(mat.indptr, np.int64), up(mat.indices, np.int32), up(mat.data, dtype),
+                            (int(mat.shape[0]), int(mat.shape[1])))
+
+    @staticmethod
+    def empty(shape, dtype: np.dtype, device) -> "DeviceSparse":
+        code = _DTYPE_CODES[np.dtype(dtype)]
+        return DeviceSparse(torch.zeros(shape[0] + 1, dtype=torch.int64, device=device),
+                            torch.empty(0, dtype=torch.int32, device=device),
+                            torch.empty(0, dtype=_TORCH_OF[code], device=device), (int(shape[0]), int(shape[1])))
+
+    def to_scipy_csr(self) -> sp.csr_matrix:
+        out = sp.csr_matrix((self.val.cpu().numpy(), self.idx.cpu().numpy(), self.ptr.cpu().numpy()), shape=self.shape)
+        out.has_canonical_format = True  # sorted, duplicate-free by construction
+        return out
+
+    def to_scipy_csc(self) -> sp.csc_matrix:
+        """`.tocsc()` on the device (cb_csr_to_csc); the stable sort of the column indices is torch's radix sort."""
+        dev = self.idx.device
+        n_rows, n_cols = self.shape
+        nnz = self.nnz
+        code = _DTYPE_CODES[np.dtype(str(self.val.dtype).replace("torch.", ""))]
+        sorted_col, order = torch.sort(self.idx, stable=True)
+        col_ptr = torch.empty(n_cols + 1, dtype=torch.int64, device=dev)
+        csc_row = torch.empty(nnz, dtype=torch.int32, device=dev)
+        csc_val = torch.empty_like(self.val)
+        _cabi.lib().call("cb_csr_to_csc", n_rows, n_cols, nnz, ptr(self.ptr), ptr(self.val), code, ptr(order),
+                         ptr(sorted_col), ptr(col_ptr), ptr(csc_row), ptr(csc_val), current_stream())
+        out = sp.csc_matrix((csc_val.cpu().numpy(), csc_row.cpu().numpy(), col_ptr.cpu().numpy()), shape=self.shape)
+        out.has_canonical_format = True
+        return out
+
+
+def _mask(n: int, inds, device, invert: bool = False) -> torch.Tensor:
+    m = np.zeros(n, dtype=np.uint8)
+    inds = np.asarray(list(inds) if not isinstance(inds, np.ndarray) else inds, dtype=np.int64)
+    if inds.size:
+        m[inds] = 1
+    if invert:
+        m = 1 - m
+    return torch.from_numpy(m).to(device)
+
+
+def combine_device(a: DeviceSparse, b: Optional[DeviceSparse], sign: int = 1, row_keep: Optional[torch.Tensor] = None,
+                   col_a: Optional[torch.Tensor] = None, col_b: Optional[torch.Tensor] = None) -> DeviceSparse:
+    """out = row_keep * (col_a * A + sign * col_b * B) on device-resident canonical CSR operands."""
+    ops._req_cuda(a.ptr, a.idx, a.val, row_keep, col_a, col_b)
+    dev = a.idx.device
+    if b is None:
+        b = DeviceSparse(torch.zeros_like(a.ptr), a.idx[:0], a.val[:0], a.shape)
+    if a.shape != b.shape:
+        raise ValueError(f"shape mismatch {a.shape} vs {b.shape}")
+    if a.val.dtype != b.val.dtype:
+        raise TypeError("operands must share one value dtype")
+    for m, n in ((row_keep, a.shape[0]), (col_a, a.shape[1]), (col_b, a.shape[1])):
+        if m is not None and (m.dtype != torch.uint8 or m.numel() != n):
+            raise ValueError("masks are uint8 vectors over rows / columns")
+    code = _DTYPE_CODES[np.dtype(str(a.val.dtype).replace("torch.", ""))]
+    L, st = _cabi.lib(), current_stream()
+    n_rows = a.shape[0]
+    flag_a = torch.empty(a.nnz + 1, dtype=torch.int32, device=dev)
+    flag_b = torch.empty(b.nnz + 1, dtype=torch.int32, device=dev)
+    comb_a = torch.empty_like(a.val)
+    L.call("cb_csr_combine_flags", n_rows, ptr(a.ptr), ptr(a.idx), ptr(a.val), a.nnz, ptr(b.ptr), ptr(b.idx), ptr(b.val),
+           b.nnz, ptr(row_keep), ptr(col_a), ptr(col_b), int(sign), code, ptr(flag_a), ptr(flag_b), ptr(comb_a), st)
+    scan_a, _ = ops.exclusive_scan_i32(flag_a)
+    scan_b, _ = ops.exclusive_scan_i32(flag_b)
+    nnz_out = int((scan_a[-1] + scan_b[-1]).item())
+    out = DeviceSparse(torch.empty(n_rows + 1, dtype=torch.int64, device=dev),
+                       torch.empty(nnz_out, dtype=torch.int32, device=dev),
+                       torch.empty(nnz_out, dtype=a.val.dtype, device=dev), a.shape)
+    L.call("cb_csr_combine_fill", n_rows, ptr(a.ptr), ptr(a.idx), ptr(b.ptr), ptr(b.idx), ptr(b.val), int(sign), code,
+           ptr(flag_a), ptr(flag_b), ptr(scan_a), ptr(scan_b), ptr(comb_a), ptr(out.ptr), ptr(out.idx), ptr(out.val), st)
+    return out
+
+
+def combine_csr(mat_a, mat_b=None, sign: int = 1, keep_rows: Optional[Iterable[int]] = None,
+                zero_rows: Optional[Iterable[int]] = None, cols_a: Optional[Iterable[int]] = None,
+                cols_b_complement: bool = False, device: str = "cuda", fmt: str = "csr"):
+    """scipy in, scipy out.  ``keep_rows`` / ``zero_rows``: rows kept / rows emptied (at most one of them);
+    ``cols_a``: columns taken from A (all when None); ``cols_b_complement``: B contributes only the other columns."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("cellbender_b200.sparse_utils needs a CUDA device (no CPU fallback)")
+    dt = _value_dtype(mat_a.dtype, *(() if mat_b is None else (mat_b.dtype,)))
+    a = DeviceSparse.from_scipy(mat_a, dt, device)
+    b = None if mat_b is None else DeviceSparse.from_scipy(mat_b, dt, device)
+    row_keep = None
+    if keep_rows is not None:
+        row_keep = _mask(a.shape[0], keep_rows, device)
+    elif zero_rows is not None:
+        row_keep = _mask(a.shape[0], zero_rows, device, invert=True)
+    col_a = None if cols_a is None else _mask(a.shape[1], cols_a, device)
+    col_b = (1 - col_a) if (cols_b_complement and col_a is not None) else None
+    out = combine_device(a, b, sign, row_keep, col_a, col_b)
+    return out.to_scipy_csc() if fmt == "csc" else out.to_scipy_csr()
+
+
+# ---- the reference's functions --------------------------------------------------------------------------------
+def csr_set_rows_to_zero(csr, row_inds) -> sp.csr_matrix:
+    """Set all nonzero elements in rows ``row_inds`` to zero (reference sparse_utils.py:58-73).  Happens in place
+    for a csr_matrix input, like the reference; the result is returned as well."""
+    if not isinstance(csr, sp.csr_matrix):
+        try:
+            csr = csr.tocsr()
+        except Exception:
+            raise ValueError("Matrix given must be of CSR format.")
+    out = combine_csr(csr, zero_rows=row_inds)
+    out = out.astype(csr.dtype, copy=False)
+    csr.data, csr.indices, csr.indptr = out.data, out.indices.astype(csr.indices.dtype, copy=False), \
+        out.indptr.astype(csr.indptr.dtype, copy=False)
+    return csr
+
+
+def overwrite_matrix_with_columns_from_another(mat1, mat2, column_inds) -> sp.csc_matrix:
+    """Replace the columns of ``mat1`` that are NOT in ``column_inds`` with the entries of ``mat2``
+    (reference sparse_utils.py:76-100)."""
+    return combine_csr(mat1, mat2, sign=1, cols_a=column_inds, cols_b_complement=True, fmt="csc")
+
+
+def subtract_noise_in_cells(count_matrix, noise_csr, cell_inds) -> sp.csc_matrix:
+    """``csr_set_rows_to_zero(count_matrix, not cells) - noise_csr`` as CSC (reference posterior.py:315-328)."""
+    return combine_csr(count_matrix, noise_csr, sign=-1, keep_rows=cell_inds, fmt="csc")
+
+
+def restore_eliminated_features_in_cells(inferred_count_matrix, raw_count_matrix, analyzed_gene_inds,
+                                         analyzed_barcode_inds, cell_probabilities_analyzed_bcs,
+                                         cell_prob_cutoff: float = 0.5) -> sp.csc_matrix:
+    """SingleCellRNACountsDataset.restore_eliminated_features_in_cells (reference data/dataset.py:495-528): features
+    not used during inference come back from the raw data; droplets with p <= cutoff (and all droplets that were never
+    analysed) are empty in the output.  One fused pass instead of overwrite + csr_set_rows_to_zero."""
+    p_all = np.zeros(raw_count_matrix.shape[0])
+    p_all[np.asarray(analyzed_barcode_inds)] = np.asarray(cell_probabilities_analyzed_bcs)
+    return combine_csr(inferred_count_matrix, raw_count_matrix, sign=1, keep_rows=np.flatnonzero(p_all > cell_prob_cutoff),
+                       cols_a=analyzed_gene_inds, cols_b_complement=True, fmt="csc")

@@ -40,6 +40,13 @@ class PreparedDataset:
     def get_count_matrix_empties(self) -> sp.csr_matrix:
         return self.matrix[self.empty_barcode_inds, :][:, self.analyzed_gene_inds].tocsr()
 
+    def restore_eliminated_features_in_cells(self, inferred_count_matrix, cell_probabilities_analyzed_bcs) -> sp.csc_matrix:
+        """reference data/dataset.py:495-528 (device pass, sparse_utils.restore_eliminated_features_in_cells)."""
+        from .sparse_utils import restore_eliminated_features_in_cells
+
+        return restore_eliminated_features_in_cells(inferred_count_matrix, self.matrix, self.analyzed_gene_inds,
+                                                    self.analyzed_barcode_inds, cell_probabilities_analyzed_bcs)
+
 
 def _coo_rows_from_draws(row_of_draw: torch.Tensor, gene_of_draw: torch.Tensor, n_rows: int, n_genes: int):
     """(row, gene) multiset -> CSR pieces via one sort + unique_consecutive."""

@@ -276,6 +276,28 @@ int cb_segment_estimate(int mode, const long long* m, const int* c, const float*
                         long long* map_pos, void* stream);
 int cb_csr_from_segments(const long long* seg_m, long long n_seg, long long n_rows, long long n_cols, long long* indptr,
                          int* col, void* stream);
+/* Output assembly after the estimators: row-wise combination of two canonical CSR matrices of equal shape,
+ *     out[n,g] = row_keep[n] * ( col_a[g] * A[n,g] + sign * col_b[g] * B[n,g] ),  explicit zeros dropped,
+ * replacing csr_set_rows_to_zero (sparse_utils.py:58-73), overwrite_matrix_with_columns_from_another
+ * (sparse_utils.py:76-100), `cell_counts - noise_csr` (posterior.py:321-326) and
+ * restore_eliminated_features_in_cells (data/dataset.py:495-528).  row_keep[n_rows], col_a[n_cols], col_b[n_cols] are
+ * bytes (NULL = all ones); sign = +1 / -1; dtype: 0 int32, 1 int64, 2 float32, 3 float64 (both value arrays).
+ * Pass 1 writes flag_a[nnz_a + 1], flag_b[nnz_b + 1] (trailing 0) and the combined values comb_a[nnz_a]; the caller
+ * scans both flag arrays over nnz + 1 elements (cb_exclusive_scan_i32) and pass 2 writes out_ptr[n_rows + 1],
+ * out_idx / out_val[scan_a[nnz_a] + scan_b[nnz_b]] with sorted column indices.                                      */
+int cb_csr_combine_flags(long long n_rows, const long long* ptr_a, const int* idx_a, const void* val_a, long long nnz_a,
+                         const long long* ptr_b, const int* idx_b, const void* val_b, long long nnz_b,
+                         const unsigned char* row_keep, const unsigned char* col_a, const unsigned char* col_b, int sign,
+                         int dtype, int* flag_a, int* flag_b, void* comb_a, void* stream);
+int cb_csr_combine_fill(long long n_rows, const long long* ptr_a, const int* idx_a, const long long* ptr_b,
+                        const int* idx_b, const void* val_b, int sign, int dtype, const int* flag_a, const int* flag_b,
+                        const long long* scan_a, const long long* scan_b, const void* comb_a, long long* out_ptr,
+                        int* out_idx, void* out_val, void* stream);
+/* CSR -> CSC (`.tocsc()` at posterior.py:328, dataset.py:528).  order[nnz] = permutation that stably sorts the stored
+ * entries by column, sorted_col[nnz] = idx[order]; outputs col_ptr[n_cols + 1], csc_row[nnz], csc_val[nnz].          */
+int cb_csr_to_csc(long long n_rows, long long n_cols, long long nnz, const long long* ptr, const void* val, int dtype,
+                  const long long* order, const int* sorted_col, long long* col_ptr, int* csc_row, void* csc_val,
+                  void* stream);
 /* PRq posterior regularisation (posterior.py:1002-1225: PRq._compute_log_target_dict, torch_binary_search over
  * PRq._get_alpha_log_constraint_violation_given_beta, renormalisation) over the (m, c)-sorted posterior COO, one
  * thread per m-segment.  log_target[n_seg] (may be NULL) = log(mean + alpha std); beta_out[n_seg] (may be NULL);

@@ -274,6 +274,56 @@ def golden_prmu():
     np.savez_compressed(os.path.join(OUT, "prmu.npz"), **res)
 
 
+def golden_sparse_utils():
+    """Output assembly of the unmodified reference: overwrite_matrix_with_columns_from_another and csr_set_rows_to_zero
+    (sparse_utils.py:58-100) on the cases of tests/test_sparse_utils.py:128-139,170-180 and on larger random count
+    matrices; `cell_counts - noise_csr` (posterior.py:315-328) and restore_eliminated_features_in_cells
+    (data/dataset.py:495-528, called unbound on a namespace carrying the three attributes it reads)."""
+    from types import SimpleNamespace
+
+    from cellbender.remove_background.data.dataset import SingleCellRNACountsDataset
+    from cellbender.remove_background.sparse_utils import csr_set_rows_to_zero, overwrite_matrix_with_columns_from_another
+
+    rng = np.random.RandomState(7)
+    res = {}
+    cases = {
+        "t0": (np.array([[1, 2], [3, 4]]), np.zeros((2, 2), int), [0]),
+        "t1": (np.array([[1, 2], [3, 4], [5, 6]]), np.zeros((3, 2), int), [1]),
+        "t2": (rng.poisson(2.0, size=(10, 10)), rng.poisson(2.0, size=(10, 10)), [0, 1, 2, 3]),
+        "r0": (rng.poisson(0.3, size=(70, 90)), rng.poisson(0.4, size=(70, 90)), sorted(rng.choice(90, 55, replace=False))),
+        "r1": (rng.poisson(0.05, size=(33, 300)), rng.poisson(1.5, size=(33, 300)), sorted(rng.choice(300, 3, replace=False))),
+        "none": (rng.poisson(0.5, size=(9, 12)), rng.poisson(0.5, size=(9, 12)), []),
+    }
+    for tag, (m1, m2, cols) in cases.items():
+        out = overwrite_matrix_with_columns_from_another(sp.csc_matrix(m1), sp.csc_matrix(m2), np.array(cols, dtype=int))
+        res[f"ow_{tag}_m1"], res[f"ow_{tag}_m2"], res[f"ow_{tag}_cols"] = m1, m2, np.array(cols, dtype=np.int64)
+        res[f"ow_{tag}_out"] = np.asarray(out.todense())
+        assert sp.issparse(out) and out.format == "csc"
+    for tag, (m, rows) in {"t0": (np.array([[1, 2], [3, 4]]), [0]), "t1": (np.array([[1, 2], [3, 4], [5, 6]]), [1]),
+                           "r": (rng.poisson(0.4, size=(50, 40)), sorted(rng.choice(50, 21, replace=False)))}.items():
+        out = csr_set_rows_to_zero(sp.csr_matrix(m), rows)
+        res[f"rz_{tag}_m"], res[f"rz_{tag}_rows"], res[f"rz_{tag}_out"] = m, np.array(rows, dtype=np.int64), np.asarray(out.todense())
+        res[f"rz_{tag}_nnz"] = out.nnz
+    # denoise + restore: 60 barcodes x 80 features, 45 analysed barcodes, 50 analysed features
+    raw = rng.poisson(0.6, size=(60, 80))
+    bcs = np.sort(rng.choice(60, 45, replace=False))
+    genes = np.sort(rng.choice(80, 50, replace=False))
+    p = rng.uniform(size=45)
+    p[:3] = [0.5, 0.5000001, 0.4999999]
+    cell_inds = bcs[p > consts.CELL_PROB_CUTOFF]
+    noise = np.zeros_like(raw)
+    sub = np.ix_(cell_inds, genes)
+    noise[sub] = rng.binomial(raw[sub], 0.4)  # noise <= count, only where the posterior exists
+    count_matrix = sp.csr_matrix(raw)
+    empty_inds = set(range(60)) - set(cell_inds)
+    denoised = (csr_set_rows_to_zero(csr=count_matrix.copy(), row_inds=empty_inds) - sp.csr_matrix(noise)).tocsc()
+    ns = SimpleNamespace(data={"matrix": sp.csc_matrix(raw)}, analyzed_gene_inds=genes, analyzed_barcode_inds=bcs)
+    restored = SingleCellRNACountsDataset.restore_eliminated_features_in_cells(ns, denoised, p)
+    res.update(dn_raw=raw, dn_bcs=bcs, dn_genes=genes, dn_p=p, dn_noise=noise, dn_denoised=np.asarray(denoised.todense()),
+               dn_denoised_nnz=denoised.nnz, dn_restored=np.asarray(restored.todense()), dn_restored_nnz=restored.nnz)
+    np.savez_compressed(os.path.join(OUT, "sparse_utils.npz"), **res)
+
+
 def golden_vae():
     torch.manual_seed(21)
     G, H, Z, B = 40, 16, 6, 12
@@ -338,10 +388,14 @@ def golden_dataloader():
 
 
 if __name__ == "__main__":
+    if "--only-sparse" in sys.argv:
+        golden_sparse_utils()
+        sys.exit(0)
     if "--only-prq" in sys.argv:
         golden_prq()
         golden_prmu()
         sys.exit(0)
+    golden_sparse_utils()
     golden_prq()
     golden_prmu()
     golden_nbpc()
