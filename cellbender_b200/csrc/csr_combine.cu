@@ -1,12 +1,12 @@
 // Row-wise combination of two CSR count matrices of equal shape, the output-assembly step after the estimators:
 //
-//     out[n, g] = row_keep[n] * ( col_a[g] * A[n, g]  +  sign * col_b[g] * B[n, g] ),      explicit zeros dropped,
+//     out[n, g] = row_a[n] * col_a[g] * A[n, g]  +  sign * row_b[n] * col_b[g] * B[n, g],      explicit zeros dropped,
 //
 // which covers, in the reference,
-//   * csr_set_rows_to_zero                       (sparse_utils.py:58-73)     B empty, row_keep = not in row_inds
+//   * csr_set_rows_to_zero                       (sparse_utils.py:58-73)     B empty, row_a = not in row_inds
 //   * overwrite_matrix_with_columns_from_another (sparse_utils.py:76-100)    col_a = in column_inds, col_b = its complement
-//   * cell_counts - noise_csr                    (posterior.py:321-326)      sign = -1, row_keep = called cells
-//   * restore_eliminated_features_in_cells       (data/dataset.py:495-528)   the overwrite with row_keep = p > 0.5
+//   * cell_counts - noise_csr                    (posterior.py:321-326)      sign = -1, row_a = called cells (B unmasked)
+//   * restore_eliminated_features_in_cells       (data/dataset.py:495-528)   the overwrite with row_a = row_b = p > 0.5
 // The reference does these with Python loops over every stored index (`[i in set for i in mat.indices]`) and scipy
 // binops on the host.  Integer / byte work, HBM-bound: per stored entry one read of (index, value), one 4-byte flag,
 // one 8-byte scan value and one write of (index, value); no atomics, so the output is deterministic and canonical
@@ -38,21 +38,22 @@ template <typename T>
 __global__ void __launch_bounds__(kCombineThreads)
 csr_combine_flag_kernel(long long n_rows, const long long* __restrict__ ptr_a, const int* __restrict__ idx_a,
                         const T* __restrict__ val_a, const long long* __restrict__ ptr_b, const int* __restrict__ idx_b,
-                        const T* __restrict__ val_b, const unsigned char* __restrict__ row_keep,
-                        const unsigned char* __restrict__ col_a, const unsigned char* __restrict__ col_b, int sign,
+                        const T* __restrict__ val_b, const unsigned char* __restrict__ row_a,
+                        const unsigned char* __restrict__ row_b, const unsigned char* __restrict__ col_a, const unsigned char* __restrict__ col_b, int sign,
                         int* __restrict__ flag_a, int* __restrict__ flag_b, T* __restrict__ comb_a) {
   const long long row = (long long)blockIdx.x * kCombineRowsPerBlock + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int lane = threadIdx.x & 31;
   const long long a0 = ptr_a[row], a1 = ptr_a[row + 1], b0 = ptr_b[row], b1 = ptr_b[row + 1];
-  const bool rk = row_keep == nullptr || row_keep[row] != 0;
+  const bool rk_a = row_a == nullptr || row_a[row] != 0;
+  const bool rk_b = row_b == nullptr || row_b[row] != 0;
   for (long long i = a0 + lane; i < a1; i += 32) {
     const int g = idx_a[i];
     T v = T(0);
-    bool keep = rk && (col_a == nullptr || col_a[g] != 0);
+    bool keep = rk_a && (col_a == nullptr || col_a[g] != 0);
     if (keep) {
       v = val_a[i];
-      if (col_b == nullptr || col_b[g] != 0) {
+      if (rk_b && (col_b == nullptr || col_b[g] != 0)) {
         const long long j = lower_bound_col(idx_b, b0, b1, g);
         if (j < b1 && idx_b[j] == g) v = sign > 0 ? T(v + val_b[j]) : T(v - val_b[j]);
       }
@@ -63,8 +64,8 @@ csr_combine_flag_kernel(long long n_rows, const long long* __restrict__ ptr_a, c
   }
   for (long long j = b0 + lane; j < b1; j += 32) {
     const int g = idx_b[j];
-    bool keep = rk && (col_b == nullptr || col_b[g] != 0) && val_b[j] != T(0);
-    if (keep && (col_a == nullptr || col_a[g] != 0)) {  // absorbed by A's entry of the same column, if A stores one
+    bool keep = rk_b && (col_b == nullptr || col_b[g] != 0) && val_b[j] != T(0);
+    if (keep && rk_a && (col_a == nullptr || col_a[g] != 0)) {  // absorbed by A's entry of the same column, if A stores one
       const long long i = lower_bound_col(idx_a, a0, a1, g);
       if (i < a1 && idx_a[i] == g) keep = false;
     }
@@ -145,8 +146,8 @@ __global__ void csc_col_ptr_kernel(long long nnz, long long n_cols, const int* _
 // index nnz); comb_a[nnz_a] holds the combined values of A's entries.
 extern "C" int cb_csr_combine_flags(long long n_rows, const long long* ptr_a, const int* idx_a, const void* val_a,
                                     long long nnz_a, const long long* ptr_b, const int* idx_b, const void* val_b,
-                                    long long nnz_b, const unsigned char* row_keep, const unsigned char* col_a,
-                                    const unsigned char* col_b, int sign, int dtype, int* flag_a, int* flag_b, void* comb_a,
+                                    long long nnz_b, const unsigned char* row_a, const unsigned char* row_b,
+                                    const unsigned char* col_a, const unsigned char* col_b, int sign, int dtype, int* flag_a, int* flag_b, void* comb_a,
                                     void* stream) {
   CB_REQUIRE(n_rows >= 0 && nnz_a >= 0 && nnz_b >= 0 && (sign == 1 || sign == -1), "cb_csr_combine_flags: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
@@ -155,7 +156,7 @@ extern "C" int cb_csr_combine_flags(long long n_rows, const long long* ptr_a, co
   if (n_rows == 0) return 0;
   const unsigned grid = unsigned((n_rows + cb::kCombineRowsPerBlock - 1) / cb::kCombineRowsPerBlock);
   CB_COMBINE_DISPATCH(dtype, cb::csr_combine_flag_kernel<T><<<grid, cb::kCombineThreads, 0, st>>>(
-                                 n_rows, ptr_a, idx_a, (const T*)val_a, ptr_b, idx_b, (const T*)val_b, row_keep, col_a, col_b,
+                                 n_rows, ptr_a, idx_a, (const T*)val_a, ptr_b, idx_b, (const T*)val_b, row_a, row_b, col_a, col_b,
                                  sign, flag_a, flag_b, (T*)comb_a));
   return cb::check_launch("cb_csr_combine_flags");
 }

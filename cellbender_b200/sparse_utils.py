@@ -5,7 +5,7 @@ matrices out.  No CPU fallback: a missing CUDA extension or device raises.
 
 All of them are instances of one row-wise combination
 
-    out[n, g] = row_keep[n] * ( col_a[g] * A[n, g] + sign * col_b[g] * B[n, g] )        (explicit zeros dropped)
+    out[n, g] = row_a[n] * col_a[g] * A[n, g] + sign * row_b[n] * col_b[g] * B[n, g]      (explicit zeros dropped)
 
 evaluated by ``combine_csr`` in two kernel passes plus two prefix scans (integer / byte work, bit-exact).
 """
@@ -50,7 +50,10 @@ class DeviceSparse:
 
     @staticmethod
     def from_scipy(mat, dtype: np.dtype, device) -> "DeviceSparse":
-        if not isinstance(mat, sp.csr_matrix):
+        """Upload a scipy matrix.  A csc_matrix is uploaded as it is stored (the CSR form of its transpose) and
+        transposed on the device, so no host-side format conversion happens for either layout."""
+        transposed = isinstance(mat, sp.csc_matrix)
+        if not isinstance(mat, (sp.csr_matrix, sp.csc_matrix)):
             mat = sp.csr_matrix(mat)
         if not mat.has_canonical_format:
             mat = mat.copy()
@@ -58,8 +61,9 @@ class DeviceSparse:
         if mat.shape[0] >= 2 ** 31 or mat.shape[1] >= 2 ** 31:
             raise ValueError("matrix dimensions must fit int32 indices")
         up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(device, non_blocking=False)
-        return DeviceSparse(up(mat.indptr, np.int64), up(mat.indices, np.int32), up(mat.data, dtype),
-                            (int(mat.shape[0]), int(mat.shape[1])))
+        shape = (int(mat.shape[1]), int(mat.shape[0])) if transposed else (int(mat.shape[0]), int(mat.shape[1]))
+        out = DeviceSparse(up(mat.indptr, np.int64), up(mat.indices, np.int32), up(mat.data, dtype), shape)
+        return out.transpose() if transposed else out
 
     @staticmethod
     def empty(shape, dtype: np.dtype, device) -> "DeviceSparse":
@@ -68,13 +72,9 @@ class DeviceSparse:
                             torch.empty(0, dtype=torch.int32, device=device),
                             torch.empty(0, dtype=_TORCH_OF[code], device=device), (int(shape[0]), int(shape[1])))
 
-    def to_scipy_csr(self) -> sp.csr_matrix:
-        out = sp.csr_matrix((self.val.cpu().numpy(), self.idx.cpu().numpy(), self.ptr.cpu().numpy()), shape=self.shape)
-        out.has_canonical_format = True  # sorted, duplicate-free by construction
-        return out
-
-    def to_scipy_csc(self) -> sp.csc_matrix:
-        """`.tocsc()` on the device (cb_csr_to_csc); the stable sort of the column indices is torch's radix sort."""
+    def transpose(self) -> "DeviceSparse":
+        """CSR of the transpose (= CSC of this matrix) through cb_csr_to_csc; the stable sort of the column indices is
+        torch's radix sort.  Canonical in, canonical out."""
         dev = self.idx.device
         n_rows, n_cols = self.shape
         nnz = self.nnz
@@ -85,9 +85,19 @@ class DeviceSparse:
         csc_val = torch.empty_like(self.val)
         _cabi.lib().call("cb_csr_to_csc", n_rows, n_cols, nnz, ptr(self.ptr), ptr(self.val), code, ptr(order),
                          ptr(sorted_col), ptr(col_ptr), ptr(csc_row), ptr(csc_val), current_stream())
-        out = sp.csc_matrix((csc_val.cpu().numpy(), csc_row.cpu().numpy(), col_ptr.cpu().numpy()), shape=self.shape)
-        out.has_canonical_format = True
+        return DeviceSparse(col_ptr, csc_row, csc_val, (n_cols, n_rows))
+
+    def _download(self, cls, shape):
+        out = cls((self.val.cpu().numpy(), self.idx.cpu().numpy(), self.ptr.cpu().numpy()), shape=shape)
+        out.has_canonical_format = True  # sorted, duplicate-free by construction
         return out
+
+    def to_scipy_csr(self) -> sp.csr_matrix:
+        return self._download(sp.csr_matrix, self.shape)
+
+    def to_scipy_csc(self) -> sp.csc_matrix:
+        """`.tocsc()` on the device."""
+        return self.transpose()._download(sp.csc_matrix, self.shape)
 
 
 def _mask(n: int, inds, device, invert: bool = False) -> torch.Tensor:
@@ -100,10 +110,11 @@ def _mask(n: int, inds, device, invert: bool = False) -> torch.Tensor:
     return torch.from_numpy(m).to(device)
 
 
-def combine_device(a: DeviceSparse, b: Optional[DeviceSparse], sign: int = 1, row_keep: Optional[torch.Tensor] = None,
-                   col_a: Optional[torch.Tensor] = None, col_b: Optional[torch.Tensor] = None) -> DeviceSparse:
-    """out = row_keep * (col_a * A + sign * col_b * B) on device-resident canonical CSR operands."""
-    ops._req_cuda(a.ptr, a.idx, a.val, row_keep, col_a, col_b)
+def combine_device(a: DeviceSparse, b: Optional[DeviceSparse], sign: int = 1, row_a: Optional[torch.Tensor] = None,
+                   row_b: Optional[torch.Tensor] = None, col_a: Optional[torch.Tensor] = None,
+                   col_b: Optional[torch.Tensor] = None) -> DeviceSparse:
+    """out = row_a * col_a * A + sign * row_b * col_b * B on device-resident canonical CSR operands."""
+    ops._req_cuda(a.ptr, a.idx, a.val, row_a, row_b, col_a, col_b)
     dev = a.idx.device
     if b is None:
         b = DeviceSparse(torch.zeros_like(a.ptr), a.idx[:0], a.val[:0], a.shape)
@@ -111,7 +122,7 @@ def combine_device(a: DeviceSparse, b: Optional[DeviceSparse], sign: int = 1, ro
         raise ValueError(f"shape mismatch {a.shape} vs {b.shape}")
     if a.val.dtype != b.val.dtype:
         raise TypeError("operands must share one value dtype")
-    for m, n in ((row_keep, a.shape[0]), (col_a, a.shape[1]), (col_b, a.shape[1])):
+    for m, n in ((row_a, a.shape[0]), (row_b, a.shape[0]), (col_a, a.shape[1]), (col_b, a.shape[1])):
         if m is not None and (m.dtype != torch.uint8 or m.numel() != n):
             raise ValueError("masks are uint8 vectors over rows / columns")
     code = _DTYPE_CODES[np.dtype(str(a.val.dtype).replace("torch.", ""))]
@@ -121,7 +132,7 @@ def combine_device(a: DeviceSparse, b: Optional[DeviceSparse], sign: int = 1, ro
     flag_b = torch.empty(b.nnz + 1, dtype=torch.int32, device=dev)
     comb_a = torch.empty_like(a.val)
     L.call("cb_csr_combine_flags", n_rows, ptr(a.ptr), ptr(a.idx), ptr(a.val), a.nnz, ptr(b.ptr), ptr(b.idx), ptr(b.val),
-           b.nnz, ptr(row_keep), ptr(col_a), ptr(col_b), int(sign), code, ptr(flag_a), ptr(flag_b), ptr(comb_a), st)
+           b.nnz, ptr(row_a), ptr(row_b), ptr(col_a), ptr(col_b), int(sign), code, ptr(flag_a), ptr(flag_b), ptr(comb_a), st)
     scan_a, _ = ops.exclusive_scan_i32(flag_a)
     scan_b, _ = ops.exclusive_scan_i32(flag_b)
     nnz_out = int((scan_a[-1] + scan_b[-1]).item())
@@ -134,10 +145,12 @@ def combine_device(a: DeviceSparse, b: Optional[DeviceSparse], sign: int = 1, ro
 
 
 def combine_csr(mat_a, mat_b=None, sign: int = 1, keep_rows: Optional[Iterable[int]] = None,
-                zero_rows: Optional[Iterable[int]] = None, cols_a: Optional[Iterable[int]] = None,
-                cols_b_complement: bool = False, device: str = "cuda", fmt: str = "csr"):
-    """scipy in, scipy out.  ``keep_rows`` / ``zero_rows``: rows kept / rows emptied (at most one of them);
-    ``cols_a``: columns taken from A (all when None); ``cols_b_complement``: B contributes only the other columns."""
+                zero_rows: Optional[Iterable[int]] = None, rows_apply_to_b: bool = True,
+                cols_a: Optional[Iterable[int]] = None, cols_b_complement: bool = False, device: str = "cuda",
+                fmt: str = "csr"):
+    """scipy in, scipy out.  ``keep_rows`` / ``zero_rows``: rows kept / rows emptied (at most one of them), in A and,
+    if ``rows_apply_to_b``, in B; ``cols_a``: columns taken from A (all when None); ``cols_b_complement``: B contributes
+    only the other columns."""
     if not torch.cuda.is_available():
         raise RuntimeError("cellbender_b200.sparse_utils needs a CUDA device (no CPU fallback)")
     dt = _value_dtype(mat_a.dtype, *(() if mat_b is None else (mat_b.dtype,)))
@@ -150,7 +163,7 @@ def combine_csr(mat_a, mat_b=None, sign: int = 1, keep_rows: Optional[Iterable[i
         row_keep = _mask(a.shape[0], zero_rows, device, invert=True)
     col_a = None if cols_a is None else _mask(a.shape[1], cols_a, device)
     col_b = (1 - col_a) if (cols_b_complement and col_a is not None) else None
-    out = combine_device(a, b, sign, row_keep, col_a, col_b)
+    out = combine_device(a, b, sign, row_keep, row_keep if rows_apply_to_b else None, col_a, col_b)
     return out.to_scipy_csc() if fmt == "csc" else out.to_scipy_csr()
 
 
@@ -159,6 +172,8 @@ def csr_set_rows_to_zero(csr, row_inds) -> sp.csr_matrix:
     """Set all nonzero elements in rows ``row_inds`` to zero (reference sparse_utils.py:58-73).  Happens in place
     for a csr_matrix input, like the reference; the result is returned as well."""
     if not isinstance(csr, sp.csr_matrix):
+        if sp.issparse(csr):
+            return combine_csr(csr, zero_rows=row_inds).astype(csr.dtype, copy=False)  # format conversion on the device
         try:
             csr = csr.tocsr()
         except Exception:
@@ -178,7 +193,7 @@ def overwrite_matrix_with_columns_from_another(mat1, mat2, column_inds) -> sp.cs
 
 def subtract_noise_in_cells(count_matrix, noise_csr, cell_inds) -> sp.csc_matrix:
     """``csr_set_rows_to_zero(count_matrix, not cells) - noise_csr`` as CSC (reference posterior.py:315-328)."""
-    return combine_csr(count_matrix, noise_csr, sign=-1, keep_rows=cell_inds, fmt="csc")
+    return combine_csr(count_matrix, noise_csr, sign=-1, keep_rows=cell_inds, rows_apply_to_b=False, fmt="csc")
 
 
 def restore_eliminated_features_in_cells(inferred_count_matrix, raw_count_matrix, analyzed_gene_inds,

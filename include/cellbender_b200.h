@@ -277,18 +277,19 @@ int cb_segment_estimate(int mode, const long long* m, const int* c, const float*
 int cb_csr_from_segments(const long long* seg_m, long long n_seg, long long n_rows, long long n_cols, long long* indptr,
                          int* col, void* stream);
 /* Output assembly after the estimators: row-wise combination of two canonical CSR matrices of equal shape,
- *     out[n,g] = row_keep[n] * ( col_a[g] * A[n,g] + sign * col_b[g] * B[n,g] ),  explicit zeros dropped,
+ *     out[n,g] = row_a[n] * col_a[g] * A[n,g] + sign * row_b[n] * col_b[g] * B[n,g],  explicit zeros dropped,
  * replacing csr_set_rows_to_zero (sparse_utils.py:58-73), overwrite_matrix_with_columns_from_another
  * (sparse_utils.py:76-100), `cell_counts - noise_csr` (posterior.py:321-326) and
- * restore_eliminated_features_in_cells (data/dataset.py:495-528).  row_keep[n_rows], col_a[n_cols], col_b[n_cols] are
- * bytes (NULL = all ones); sign = +1 / -1; dtype: 0 int32, 1 int64, 2 float32, 3 float64 (both value arrays).
+ * restore_eliminated_features_in_cells (data/dataset.py:495-528).  row_a[n_rows], row_b[n_rows], col_a[n_cols], col_b[n_cols]
+ * are bytes (NULL = all ones); sign = +1 / -1; dtype: 0 int32, 1 int64, 2 float32, 3 float64 (both value arrays).
  * Pass 1 writes flag_a[nnz_a + 1], flag_b[nnz_b + 1] (trailing 0) and the combined values comb_a[nnz_a]; the caller
  * scans both flag arrays over nnz + 1 elements (cb_exclusive_scan_i32) and pass 2 writes out_ptr[n_rows + 1],
  * out_idx / out_val[scan_a[nnz_a] + scan_b[nnz_b]] with sorted column indices.                                      */
 int cb_csr_combine_flags(long long n_rows, const long long* ptr_a, const int* idx_a, const void* val_a, long long nnz_a,
                          const long long* ptr_b, const int* idx_b, const void* val_b, long long nnz_b,
-                         const unsigned char* row_keep, const unsigned char* col_a, const unsigned char* col_b, int sign,
-                         int dtype, int* flag_a, int* flag_b, void* comb_a, void* stream);
+                         const unsigned char* row_a, const unsigned char* row_b, const unsigned char* col_a,
+                         const unsigned char* col_b, int sign, int dtype, int* flag_a, int* flag_b, void* comb_a,
+                         void* stream);
 int cb_csr_combine_fill(long long n_rows, const long long* ptr_a, const int* idx_a, const long long* ptr_b,
                         const int* idx_b, const void* val_b, int sign, int dtype, const int* flag_a, const int* flag_b,
                         const long long* scan_a, const long long* scan_b, const void* comb_a, long long* out_ptr,

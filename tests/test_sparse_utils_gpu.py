@@ -139,10 +139,11 @@ def test_output_assembly_full_size_properties(su):
     r, c = (key // G).cpu().numpy(), (key % G).cpu().numpy()
     rng = np.random.default_rng(1)
     raw = sp.csr_matrix((rng.integers(1, 40, size=r.size).astype(np.int32), (r, c)), shape=(R, G))
-    noise = raw.copy()
-    noise.data = rng.binomial(raw.data, 0.3).astype(np.int32)
-    noise.eliminate_zeros()
     cell_inds = np.sort(rng.choice(R, 8000, replace=False))
+    in_cell = np.isin(np.repeat(np.arange(R), np.diff(raw.indptr)), cell_inds)
+    noise = raw.copy()  # noise counts exist only for the called cells (the posterior is computed for them alone)
+    noise.data = (rng.binomial(raw.data, 0.3) * in_cell).astype(np.int32)
+    noise.eliminate_zeros()
     den = su.subtract_noise_in_cells(raw, noise, cell_inds)
     assert den.format == "csc" and den.shape == (R, G) and _canonical(den)
     want_colsum = np.asarray(raw[cell_inds].sum(axis=0)).ravel() - np.asarray(noise[cell_inds].sum(axis=0)).ravel()
