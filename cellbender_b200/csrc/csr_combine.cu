@@ -131,6 +131,30 @@ __global__ void csc_col_ptr_kernel(long long nnz, long long n_cols, const int* _
   col_ptr[g] = g == n_cols ? nnz : lower_bound_col(sorted_col, 0, nnz, int(g));
 }
 
+// ---- dense -> COO (dense_to_sparse_op_torch, sparse_utils.py:10-33) ------------------------------------------------
+// flag[r * n_cols + c] = (mask[r, c] != 0); after an exclusive scan of the flags the second kernel writes the
+// (row, col, value) triplets in row-major order, the order torch.nonzero returns.
+template <typename T>
+__global__ void dense_nonzero_flag_kernel(const T* __restrict__ mask, long long n_rows, long long n_cols, long long ld,
+                                          int* __restrict__ flag) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_rows * n_cols) return;
+  const long long r = k / n_cols, c = k - r * n_cols;
+  flag[k] = mask[r * ld + c] != T(0) ? 1 : 0;
+}
+
+template <typename T>
+__global__ void dense_to_coo_kernel(const T* __restrict__ t, long long n_rows, long long n_cols, long long ld,
+                                    const int* __restrict__ flag, const long long* __restrict__ pos,
+                                    long long* __restrict__ row, long long* __restrict__ col, T* __restrict__ val) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_rows * n_cols || !flag[k]) return;
+  const long long r = k / n_cols, c = k - r * n_cols, o = pos[k];
+  row[o] = r;
+  col[o] = c;
+  val[o] = t[r * ld + c];
+}
+
 }  // namespace cb
 
 #define CB_COMBINE_DISPATCH(dtype, ...)                    \
@@ -189,4 +213,27 @@ extern "C" int cb_csr_to_csc(long long n_rows, long long n_cols, long long nnz, 
                                    nnz, n_rows, ptr, (const T*)val, order, csc_row, (T*)csc_val));
   }
   return cb::check_launch("cb_csr_to_csc");
+}
+
+// dense_to_sparse_op_torch (sparse_utils.py:10-33) in two launches around cb_exclusive_scan_i32: mask / t are row-major
+// [n_rows, n_cols] with leading dimensions ld_mask / ld_t (elements); flag[n_rows * n_cols]; pos = exclusive scan of flag;
+// row / col [nnz] int64 like torch.nonzero, val[nnz] of t's type.  dtype codes as above (mask and t separately).
+extern "C" int cb_dense_nonzero_flags(const void* mask, int dtype, long long n_rows, long long n_cols, long long ld_mask,
+                                      int* flag, void* stream) {
+  CB_REQUIRE(n_rows >= 0 && n_cols >= 0 && ld_mask >= n_cols, "cb_dense_nonzero_flags: bad shape");
+  const long long n = n_rows * n_cols;
+  if (n == 0) return 0;
+  CB_COMBINE_DISPATCH(dtype, cb::dense_nonzero_flag_kernel<T><<<unsigned((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+                                 (const T*)mask, n_rows, n_cols, ld_mask, flag));
+  return cb::check_launch("cb_dense_nonzero_flags");
+}
+
+extern "C" int cb_dense_to_coo(const void* t, int dtype, long long n_rows, long long n_cols, long long ld_t, const int* flag,
+                               const long long* pos, long long* row, long long* col, void* val, void* stream) {
+  CB_REQUIRE(n_rows >= 0 && n_cols >= 0 && ld_t >= n_cols, "cb_dense_to_coo: bad shape");
+  const long long n = n_rows * n_cols;
+  if (n == 0) return 0;
+  CB_COMBINE_DISPATCH(dtype, cb::dense_to_coo_kernel<T><<<unsigned((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+                                 (const T*)t, n_rows, n_cols, ld_t, flag, pos, row, col, (T*)val));
+  return cb::check_launch("cb_dense_to_coo");
 }

@@ -23,6 +23,14 @@ _DTYPE_CODES = {np.dtype(np.int32): 0, np.dtype(np.int64): 1, np.dtype(np.float3
 _TORCH_OF = {0: torch.int32, 1: torch.int64, 2: torch.float32, 3: torch.float64}
 
 
+def _code_of(x: torch.Tensor) -> int:
+    """dtype code of the C ABI (0 int32, 1 int64, 2 float32, 3 float64) of a tensor."""
+    for code, dt in _TORCH_OF.items():
+        if x.dtype == dt:
+            return code
+    raise TypeError(f"unsupported value dtype {x.dtype} (int32, int64, float32, float64)")
+
+
 def _value_dtype(*dtypes) -> np.dtype:
     """numpy's result type of the operands, widened to one of the four value types the kernels are built for."""
     dt = np.result_type(*dtypes)
@@ -78,7 +86,7 @@ class DeviceSparse:
         dev = self.idx.device
         n_rows, n_cols = self.shape
         nnz = self.nnz
-        code = _DTYPE_CODES[np.dtype(str(self.val.dtype).replace("torch.", ""))]
+        code = _code_of(self.val)
         sorted_col, order = torch.sort(self.idx, stable=True)
         col_ptr = torch.empty(n_cols + 1, dtype=torch.int64, device=dev)
         csc_row = torch.empty(nnz, dtype=torch.int32, device=dev)
@@ -125,7 +133,7 @@ def combine_device(a: DeviceSparse, b: Optional[DeviceSparse], sign: int = 1, ro
     for m, n in ((row_a, a.shape[0]), (row_b, a.shape[0]), (col_a, a.shape[1]), (col_b, a.shape[1])):
         if m is not None and (m.dtype != torch.uint8 or m.numel() != n):
             raise ValueError("masks are uint8 vectors over rows / columns")
-    code = _DTYPE_CODES[np.dtype(str(a.val.dtype).replace("torch.", ""))]
+    code = _code_of(a.val)
     L, st = _cabi.lib(), current_stream()
     n_rows = a.shape[0]
     flag_a = torch.empty(a.nnz + 1, dtype=torch.int32, device=dev)
@@ -168,6 +176,51 @@ def combine_csr(mat_a, mat_b=None, sign: int = 1, keep_rows: Optional[Iterable[i
 
 
 # ---- the reference's functions --------------------------------------------------------------------------------
+@torch.no_grad()
+def dense_to_sparse_op_torch(t, tensor_for_nonzeros: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, ...]:
+    """Dense matrix -> COO tuple ``(*nonzero_inds, nonzero_values)`` (reference sparse_utils.py:10-33): indices int64 in
+    torch.nonzero's row-major order; with ``tensor_for_nonzeros`` the positions come from that tensor and the values
+    from ``t``.  Accepts a ``dataprep.MiniBatch`` (what this package's DataLoader yields) in place of a dense tensor."""
+    t = t.dense() if hasattr(t, "dense") and not isinstance(t, torch.Tensor) else t
+    mask = t if tensor_for_nonzeros is None else tensor_for_nonzeros
+    mask = mask.dense() if hasattr(mask, "dense") and not isinstance(mask, torch.Tensor) else mask
+    ops._req_cuda(t, mask)
+    if tuple(mask.shape) != tuple(t.shape):
+        raise ValueError("tensor_for_nonzeros must have the shape of t")
+    if mask.dtype == torch.bool:
+        mask = mask.to(torch.int32)
+    shape = tuple(t.shape)
+    if len(shape) == 0:
+        raise ValueError("dense_to_sparse_op_torch needs a tensor with at least one dimension")
+
+    def as2d(x):  # rows x last dimension, unit stride inside a row (a padded leading dimension is fine)
+        x = x.reshape(1, -1) if x.dim() < 2 else x
+        if x.dim() > 2 or x.stride(-1) != 1 or (x.shape[0] > 1 and x.stride(0) < x.shape[1]):
+            x = x.contiguous().reshape(-1, x.shape[-1])
+        return x
+
+    t2, m2 = as2d(t), as2d(mask)
+    codes = [_code_of(t2), _code_of(m2)]
+    n_rows, n_cols = int(t2.shape[0]), int(t2.shape[1])
+    ld = lambda x: int(x.stride(0)) if x.shape[0] > 1 else max(n_cols, 1)
+    dev = t.device
+    L, st = _cabi.lib(), current_stream()
+    flag = torch.empty(n_rows * n_cols, dtype=torch.int32, device=dev)
+    L.call("cb_dense_nonzero_flags", ptr(m2), codes[1], n_rows, n_cols, ld(m2), ptr(flag), st)
+    pos, total = ops.exclusive_scan_i32(flag)
+    nnz = int(total.item())
+    row = torch.empty(nnz, dtype=torch.int64, device=dev)
+    col = torch.empty(nnz, dtype=torch.int64, device=dev)
+    val = torch.empty(nnz, dtype=t.dtype, device=dev)
+    L.call("cb_dense_to_coo", ptr(t2), codes[0], n_rows, n_cols, ld(t2), ptr(flag), ptr(pos), ptr(row), ptr(col), ptr(val), st)
+    if len(shape) == 2:
+        return row, col, val
+    if len(shape) == 1:
+        return col, val
+    lead = torch.unravel_index(row, shape[:-1])  # N-d input: split the flattened leading index
+    return tuple(lead) + (col, val)
+
+
 def csr_set_rows_to_zero(csr, row_inds) -> sp.csr_matrix:
     """Set all nonzero elements in rows ``row_inds`` to zero (reference sparse_utils.py:58-73).  Happens in place
     for a csr_matrix input, like the reference; the result is returned as well."""

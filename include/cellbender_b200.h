@@ -299,6 +299,12 @@ int cb_csr_combine_fill(long long n_rows, const long long* ptr_a, const int* idx
 int cb_csr_to_csc(long long n_rows, long long n_cols, long long nnz, const long long* ptr, const void* val, int dtype,
                   const long long* order, const int* sorted_col, long long* col_ptr, int* csc_row, void* csc_val,
                   void* stream);
+/* dense_to_sparse_op_torch (sparse_utils.py:10-33): nonzero flags of mask[n_rows, n_cols] (leading dimension ld_mask),
+ * then, with pos = exclusive scan of flag, the (row, col, value) triplets of t in torch.nonzero's row-major order.   */
+int cb_dense_nonzero_flags(const void* mask, int dtype, long long n_rows, long long n_cols, long long ld_mask, int* flag,
+                           void* stream);
+int cb_dense_to_coo(const void* t, int dtype, long long n_rows, long long n_cols, long long ld_t, const int* flag,
+                    const long long* pos, long long* row, long long* col, void* val, void* stream);
 /* PRq posterior regularisation (posterior.py:1002-1225: PRq._compute_log_target_dict, torch_binary_search over
  * PRq._get_alpha_log_constraint_violation_given_beta, renormalisation) over the (m, c)-sorted posterior COO, one
  * thread per m-segment.  log_target[n_seg] (may be NULL) = log(mean + alpha std); beta_out[n_seg] (may be NULL);

@@ -165,3 +165,67 @@ def test_output_assembly_full_size_properties(su):
     raw_cells_colsum = np.asarray(raw[cell_inds].sum(axis=0)).ravel()
     np.testing.assert_array_equal(got_colsum[sel], want_colsum[sel])
     np.testing.assert_array_equal(got_colsum[~sel], raw_cells_colsum[~sel])
+
+
+def test_dense_to_sparse_op_torch_matches_torch_nonzero(su):
+    """reference sparse_utils.py:10-33 = torch.nonzero(as_tuple=True) + gather; all value types, padded rows,
+    `tensor_for_nonzeros`, 1-d and 3-d inputs, empty results."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for dtype in (torch.float32, torch.float64, torch.int32, torch.int64):
+        t = (torch.randint(0, 4, (37, 101), device="cuda", generator=g) * (torch.rand(37, 101, device="cuda", generator=g) < 0.3))
+        t = t.to(dtype)
+        got = su.dense_to_sparse_op_torch(t)
+        want = torch.nonzero(t, as_tuple=True)
+        assert len(got) == 3 and got[0].dtype == torch.int64 and got[2].dtype == dtype
+        for a, b in zip(got[:2], want):
+            assert torch.equal(a, b)
+        assert torch.equal(got[2], t[want].flatten())
+    padded = torch.zeros(9, 104, device="cuda")
+    padded[:, :101] = torch.rand(9, 101, device="cuda", generator=g).round()
+    view = padded[:, :101]  # row stride 104: the layout of this package's dense minibatches
+    got = su.dense_to_sparse_op_torch(view)
+    want = torch.nonzero(view, as_tuple=True)
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]) and torch.equal(got[2], view[want])
+    other = torch.rand(9, 101, device="cuda", generator=g)
+    got = su.dense_to_sparse_op_torch(other, tensor_for_nonzeros=view > 0)
+    assert torch.equal(got[0], want[0]) and torch.equal(got[2], other[want])
+    v = torch.tensor([0.0, 2.0, 0.0, 5.0], device="cuda")
+    got = su.dense_to_sparse_op_torch(v)
+    assert torch.equal(got[0], torch.tensor([1, 3], device="cuda")) and torch.equal(got[1], torch.tensor([2.0, 5.0], device="cuda"))
+    cube = (torch.rand(3, 5, 7, device="cuda", generator=g) < 0.2).float()
+    got = su.dense_to_sparse_op_torch(cube)
+    want = torch.nonzero(cube, as_tuple=True)
+    assert len(got) == 4 and all(torch.equal(a, b) for a, b in zip(got[:3], want))
+    got = su.dense_to_sparse_op_torch(torch.zeros(4, 6, device="cuda"))
+    assert all(x.numel() == 0 for x in got)
+    with pytest.raises(RuntimeError):
+        su.dense_to_sparse_op_torch(torch.zeros(4, 6))
+
+
+def test_dataloader_roundtrip_through_dense_to_sparse_like_the_reference_tests(su):
+    """The reference's tests/test_sparse_utils.py:47-93 and tests/test_dataprep.py:20-100: iterate the (unshuffled, and
+    the sorted) DataLoader, sparsify every minibatch, un-sort the barcode indices, rebuild the count matrix."""
+    from cellbender_b200.dataprep import DataLoader
+
+    rng = np.random.default_rng(5)  # 55 rows = 11 full minibatches (a remainder below SMALLEST_ALLOWED_BATCH is dropped)
+    matrix = sp.csr_matrix((rng.poisson(1.5, size=(55, 40)) * (rng.random((55, 40)) < 0.3)).astype(np.int32))
+    loaders = [DataLoader(matrix, empty_drop_dataset=None, batch_size=5, fraction_empties=0.0, shuffle=False),
+               DataLoader(matrix, empty_drop_dataset=None, batch_size=5, fraction_empties=0.0, shuffle=False,
+                          sort_by=lambda x: -1 * np.array(x.max(axis=1).todense()).squeeze())]
+    with pytest.raises(AssertionError):
+        DataLoader(matrix, empty_drop_dataset=None, batch_size=5, fraction_empties=0.0, shuffle=True,
+                   sort_by=lambda x: -1 * np.array(x.max(axis=1).todense()).squeeze())
+    outs = []
+    for loader in loaders:
+        barcodes, genes, counts, ind = [], [], [], 0
+        for data in loader:
+            bcs_i_chunk, genes_i, counts_i = su.dense_to_sparse_op_torch(data)
+            bcs_i = loader.unsort_inds(bcs_i_chunk + ind)
+            barcodes.append(bcs_i.detach().cpu()), genes.append(genes_i.detach().cpu()), counts.append(counts_i.detach().cpu())
+            ind += data.shape[0]
+        out = sp.csc_matrix((np.concatenate(counts).astype(np.uint32),
+                             (np.concatenate(barcodes).astype(np.uint32), np.concatenate(genes).astype(np.uint32))),
+                            shape=matrix.shape)
+        assert (out != matrix.tocsc()).nnz == 0
+        outs.append(out)
+    assert (outs[0] != outs[1]).nnz == 0
