@@ -62,6 +62,70 @@ __global__ void __launch_bounds__(256) clipped_adam_kernel(float* __restrict__ p
 
 __global__ void advance_step_kernel(long long* step_ptr) { *step_ptr += 1; }
 
+// Data-parallel exchange fused into the optimizer sweep (one kernel = reduce-scatter + ClippedAdam + all-gather over
+// NVLink peer memory).  Every rank owns one contiguous shard of the flat buffers.  For its shard it reads the gradient
+// from EVERY rank's flat gradient buffer (its own from HBM, the peers' through NVLink P2P loads), sums them in rank
+// order, applies the update to its param / exp_avg / exp_avg_sq, and stores the new parameter values into its own
+// flat parameter buffer AND into every peer's (P2P stores).  The gradient and parameter buffers are symmetric-memory
+// allocations (torch.distributed._symmetric_memory); a device-side barrier before the kernel (all ranks finished
+// backward) and one after it (all shards delivered) are the only other traffic.  NVLink carries 4 bytes per element in
+// and 4 (n_ranks - 1) out while HBM carries the sweep's 28: at two ranks both take about the same time, so the exchange
+// costs no extra pass over memory at all.
+constexpr int kMaxRanks = 16;
+struct P2PPointers {
+  const float* grad[kMaxRanks];  // this shard inside every rank's gradient buffer, in rank order
+  float* peer_param[kMaxRanks];  // this shard inside every OTHER rank's parameter buffer
+  int n_grad, n_peer;
+};
+
+template <int NG>  // upper bound of the number of gradient sources (keeps the in-flight loads in registers)
+__global__ void __launch_bounds__(256, NG <= 4 ? 5 : 2) clipped_adam_p2p_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                               float* __restrict__ v, long long n, P2PPointers q,
+                                                               const float* __restrict__ lr_table,
+                                                               const float* __restrict__ beta1_table, long long table_len,
+                                                               const long long* __restrict__ step_ptr, float beta2, float eps,
+                                                               float clip) {
+  const long long t0 = *step_ptr;
+  const long long ti = t0 < table_len ? t0 : table_len - 1;
+  const float lr = lr_table[ti], b1 = beta1_table[ti];
+  const double t = double(t0 + 1);
+  const float step_size = float(double(lr) * sqrt(1.0 - pow(double(beta2), t)) / (1.0 - pow(double(b1), t)));
+  const float omb1 = 1.0f - b1, omb2 = 1.0f - beta2;
+  const long long n4 = n >> 2;  // n is a multiple of 4 (checked on the host)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    // all gradient loads first (the remote ones take an NVLink round trip), L1 bypassed: peers rewrite them every step
+    float4 gsrc[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k)
+      if (k < q.n_grad) gsrc[k] = __ldcg(reinterpret_cast<const float4*>(q.grad[k]) + i);
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float4 gg = gsrc[0];
+#pragma unroll
+    for (int k = 1; k < NG; ++k)
+      if (k < q.n_grad) gg.x += gsrc[k].x, gg.y += gsrc[k].y, gg.z += gsrc[k].z, gg.w += gsrc[k].w;
+    float* pa = reinterpret_cast<float*>(&pp);
+    const float* ga = reinterpret_cast<const float*>(&gg);
+    float* ma = reinterpret_cast<float*>(&mm);
+    float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gc = fminf(fmaxf(ga[k], -clip), clip);
+      ma[k] = b1 * ma[k] + omb1 * gc;
+      va[k] = beta2 * va[k] + omb2 * gc * gc;
+      pa[k] -= step_size * ma[k] / (sqrtf(va[k]) + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+#pragma unroll
+    for (int k = 0; k < NG - 1; ++k)
+      if (k < q.n_peer) __stcg(reinterpret_cast<float4*>(q.peer_param[k]) + i, pp);
+  }
+}
+
 // the same update on a [rows, cols] sub-block of a [rows, ld] matrix (the few feature columns of a weight matrix whose
 // gene block is updated inside the weight-gradient GEMM epilogue)
 __global__ void __launch_bounds__(256) clipped_adam_2d_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -137,4 +201,41 @@ static int adam_range(float* p, const float* g, float* m, float* v, long long n,
                                                                               grad_scale);
   if (advance) cb::advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_ptr);
   return cb::check_launch("cb_clipped_adam_step");
+}
+
+// ClippedAdam on this rank's shard with the data-parallel exchange fused in (see clipped_adam_p2p_kernel).
+// grad_ptrs[n_grad]: the shard's position inside every rank's gradient buffer, rank order (host array of device / peer
+// pointers); peer_param_ptrs[n_peer]: the shard's position inside the other ranks' parameter buffers.  n % 4 == 0.
+extern "C" int cb_clipped_adam_p2p(float* p, float* m, float* v, long long n, const float* const* grad_ptrs, int n_grad,
+                                   float* const* peer_param_ptrs, int n_peer, const float* lr_table,
+                                   const float* beta1_table, long long table_len, long long* step_ptr, float beta2,
+                                   float eps, float clip, int advance, void* stream) {
+  CB_REQUIRE(n >= 0 && (n & 3) == 0 && table_len > 0, "cb_clipped_adam_p2p: n=%lld must be a non-negative multiple of 4", n);
+  CB_REQUIRE(n_grad >= 1 && n_grad <= cb::kMaxRanks && n_peer >= 0 && n_peer < n_grad + (n_grad == 1),
+             "cb_clipped_adam_p2p: %d gradient sources / %d peers (at most %d ranks)", n_grad, n_peer, cb::kMaxRanks);
+  cb::P2PPointers q{};
+  q.n_grad = n_grad, q.n_peer = n_peer;
+  for (int k = 0; k < n_grad; ++k) q.grad[k] = grad_ptrs[k];
+  for (int k = 0; k < n_peer; ++k) q.peer_param[k] = peer_param_ptrs[k];
+  for (const void* x : {(const void*)p, (const void*)m, (const void*)v})
+    CB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "cb_clipped_adam_p2p: buffers must be 16-byte aligned");
+  for (int k = 0; k < n_grad; ++k)
+    CB_REQUIRE(q.grad[k] != nullptr && (reinterpret_cast<uintptr_t>(q.grad[k]) & 15) == 0, "cb_clipped_adam_p2p: bad gradient pointer %d", k);
+  for (int k = 0; k < n_peer; ++k)
+    CB_REQUIRE(q.peer_param[k] != nullptr && (reinterpret_cast<uintptr_t>(q.peer_param[k]) & 15) == 0, "cb_clipped_adam_p2p: bad peer pointer %d", k);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n > 0) {
+    long long blocks = (n / 4 + 255) / 256;
+    const long long cap = 148LL * 8;  // 2 048 threads per SM, a multiple of the SM count
+    if (blocks > cap) blocks = cap;
+#define CB_P2P_LAUNCH(NG) \
+  cb::clipped_adam_p2p_kernel<NG><<<unsigned(blocks), 256, 0, st>>>(p, m, v, n, q, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip)
+    if (n_grad <= 2) CB_P2P_LAUNCH(2);
+    else if (n_grad <= 4) CB_P2P_LAUNCH(4);
+    else if (n_grad <= 8) CB_P2P_LAUNCH(8);
+    else CB_P2P_LAUNCH(16);
+#undef CB_P2P_LAUNCH
+  }
+  if (advance) cb::advance_step_kernel<<<1, 1, 0, st>>>(step_ptr);
+  return cb::check_launch("cb_clipped_adam_p2p");
 }

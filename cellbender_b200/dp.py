@@ -38,6 +38,18 @@ def shard_cells(n_cells: int, rank: int, world_size: int) -> np.ndarray:
     return np.arange(bounds[rank], bounds[rank + 1])
 
 
+def dp_mode() -> str:
+    return os.environ.get("CB_DP_MODE", "sharded")
+
+
+def p2p_group():
+    """Process group for symmetric-memory (NVLink peer) parameter / gradient buffers, or None when the fused P2P
+    exchange is not selected (CB_DP_MODE=p2p) or torch.distributed is not running on NCCL."""
+    if dp_mode() != "p2p" or not dist.is_available() or not dist.is_initialized() or dist.get_backend() != "nccl":
+        return None
+    return dist.group.WORLD
+
+
 def attach(svi, world_size: int):
     """Make ``svi.step`` data-parallel: all-reduce(SUM) the flat gradient buffer between backward and the optimizer."""
     if world_size <= 1:
@@ -52,8 +64,14 @@ def attach(svi, world_size: int):
         # the NCCL kernels compete for the same HBM, so pipelining them buys nothing; one all-reduce is the default
         n_chunks = int(os.environ.get("CB_DP_CHUNKS", "1"))
         # measured on B200 (r01, ms/step at 2 / 4 GPUs): sharded 1.87 / 1.96, overlap 1.92 / 2.06, allreduce 1.87 / 2.10
-        mode = os.environ.get("CB_DP_MODE", "sharded")
-        if mode == "overlap" and n_chunks <= 1:
+        mode = dp_mode()
+        if mode == "p2p":
+            if getattr(svi.optim, "symm_p", None) is None:
+                raise RuntimeError("CB_DP_MODE=p2p needs the optimizer's flat buffers in symmetric memory "
+                                   "(run.setup_inference / optim.get_optimizer(symmetric_group=...))")
+            assert svi.optim.n % (4 * world_size) == 0
+            svi.exchange_and_step = lambda opt: p2p_step(opt, world_size, rank)
+        elif mode == "overlap" and n_chunks <= 1:
             # optional: the reduction of each large gradient block is issued right behind its weight-gradient GEMM, on
             # that GEMM's side stream, followed by the ClippedAdam sweep of the block -- inside backward and inside the
             # captured step graph (NCCL collectives capture fine; drop the graphs before destroying the process group).
@@ -122,6 +140,41 @@ def reduce_scatter_step(opt, world_size: int, rank: int):
                opt.lr_table.data_ptr(), opt.beta1_table.data_ptr(), opt.lr_table.numel(), opt.step_count.data_ptr(),
                float(opt.beta2), float(opt.eps), float(opt.clip), 1, current_stream())
     dist.all_gather_into_tensor(opt.flat_p, opt.flat_p[a:a + sh])
+    opt.host_steps += 1
+
+
+@torch.no_grad()
+def p2p_step(opt, world_size: int, rank: int):
+    """The data-parallel exchange fused into the optimizer sweep, over NVLink peer memory (cb_clipped_adam_p2p):
+    device-side barrier (every rank has finished backward) -> ONE kernel that, for this rank's shard, sums the gradient
+    shards of all ranks straight out of their gradient buffers, applies ClippedAdam and stores the new parameters into
+    every rank's parameter buffer -> device-side barrier (every shard delivered).  Replaces NCCL reduce_scatter + sweep +
+    all_gather; same arithmetic per element (gradients summed in rank order).  Moment buffers are sharded as in
+    ``reduce_scatter_step``."""
+    import ctypes
+
+    from ._cabi import current_stream, lib
+
+    if not opt.constant_learning_rate and opt.host_steps >= opt.total_steps:
+        raise ValueError(f"Tried to step {opt.host_steps + 1} times. The specified number of total steps is {opt.total_steps}")
+    sh = opt.n // world_size
+    a = rank * sh
+    cache = getattr(opt, "_p2p_ptrs", None)
+    if cache is None:
+        f32 = torch.float32
+        grads = [opt.symm_g.get_buffer(r, (opt.n,), f32).data_ptr() + 4 * a for r in range(world_size)]
+        peers = [opt.symm_p.get_buffer(r, (opt.n,), f32).data_ptr() + 4 * a for r in range(world_size) if r != rank]
+        assert grads[rank] == opt.flat_g.data_ptr() + 4 * a, "symmetric gradient buffer is not where flat_g lives"
+        cache = opt._p2p_ptrs = ((ctypes.c_void_p * world_size)(*grads), (ctypes.c_void_p * max(1, len(peers)))(*peers),
+                                 len(peers))
+    g_arr, p_arr, n_peer = cache
+    timeout_ms = 20000  # a rank that never arrives traps the waiting kernels instead of hanging the GPUs
+    opt.symm_g.barrier(channel=0, timeout_ms=timeout_ms)
+    at = lambda t: t.data_ptr() + 4 * a
+    lib().call("cb_clipped_adam_p2p", at(opt.flat_p), at(opt.flat_m), at(opt.flat_v), sh, ctypes.addressof(g_arr), world_size,
+               ctypes.addressof(p_arr), n_peer, opt.lr_table.data_ptr(), opt.beta1_table.data_ptr(), opt.lr_table.numel(),
+               opt.step_count.data_ptr(), float(opt.beta2), float(opt.eps), float(opt.clip), 1, current_stream())
+    opt.symm_p.barrier(channel=1, timeout_ms=timeout_ms)
     opt.host_steps += 1
 
 

@@ -39,7 +39,8 @@ class FlatClippedAdam:
     shapes unchanged), with flat gradient / first-moment / second-moment buffers beside it."""
 
     def __init__(self, params: Iterable[nn.Parameter], learning_rate: float, total_steps: Optional[int],
-                 constant_learning_rate: bool = False, clip_norm: float = 10.0, betas=(0.9, 0.999), eps: float = 1e-8):
+                 constant_learning_rate: bool = False, clip_norm: float = 10.0, betas=(0.9, 0.999), eps: float = 1e-8,
+                 symmetric_group=None):
         self.params: List[nn.Parameter] = [p for p in params if p.requires_grad]
         assert self.params, "no parameters to optimise"
         dev = self.params[0].device
@@ -67,8 +68,19 @@ class FlatClippedAdam:
                 self.tail_start = off
         self.n = (off + 63) // 64 * 64  # a multiple of 4 x (1, 2, 4, 8, 16) ranks: equal 16-byte-aligned shards (dp.py)
         off = self.n
-        self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(off, dtype=torch.float32, device=dev)
+        # data parallel with the exchange fused into the optimizer sweep (dp.p2p_step): the parameter and gradient
+        # buffers are symmetric-memory allocations, mapped into every rank's address space over NVLink
+        self.symm_p = self.symm_g = None
+        if symmetric_group is not None:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self.flat_p = symm_mem.empty(off, dtype=torch.float32, device=dev).zero_()
+            self.flat_g = symm_mem.empty(off, dtype=torch.float32, device=dev).zero_()
+            self.symm_p = symm_mem.rendezvous(self.flat_p, symmetric_group)
+            self.symm_g = symm_mem.rendezvous(self.flat_g, symmetric_group)
+        else:
+            self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
+            self.flat_g = torch.zeros(off, dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(off, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(off, dtype=torch.float32, device=dev)
         self.grad_views = []
@@ -226,7 +238,10 @@ class FlatClippedAdam:
 
 
 def get_optimizer(model, n_batches: int, batch_size: int, epochs: int, learning_rate: float,
-                  constant_learning_rate: bool, total_epochs_for_testing_only: Optional[int] = None) -> FlatClippedAdam:
-    """Reference run.py:593-629 (same arguments, plus the model whose parameters are optimised)."""
+                  constant_learning_rate: bool, total_epochs_for_testing_only: Optional[int] = None,
+                  symmetric_group=None) -> FlatClippedAdam:
+    """Reference run.py:593-629 (same arguments, plus the model whose parameters are optimised; ``symmetric_group``:
+    process group over which the flat parameter / gradient buffers become NVLink peer memory, see dp.py)."""
     total_steps = n_batches * (total_epochs_for_testing_only if total_epochs_for_testing_only is not None else epochs)
-    return FlatClippedAdam(model.parameters(), learning_rate, total_steps, constant_learning_rate=constant_learning_rate)
+    return FlatClippedAdam(model.parameters(), learning_rate, total_steps, constant_learning_rate=constant_learning_rate,
+                           symmetric_group=symmetric_group)

@@ -82,9 +82,14 @@ def setup_inference(dataset_obj, args, device: Optional[str] = None, total_epoch
     train_loader, test_loader = prep_sparse_data_for_training(
         dataset=count_matrix, empty_drop_dataset=empties, batch_size=batch_size, training_fraction=frac,
         fraction_empties=args.fraction_empties, shuffle=True, device=device)
+    symmetric_group = None
+    if world_size > 1:
+        from .dp import p2p_group
+
+        symmetric_group = p2p_group()  # None unless CB_DP_MODE=p2p
     scheduler = get_optimizer(model, n_batches=len(train_loader), batch_size=train_loader.batch_size, epochs=args.epochs,
                               learning_rate=args.learning_rate, constant_learning_rate=args.constant_learning_rate,
-                              total_epochs_for_testing_only=total_epochs_for_testing_only)
+                              total_epochs_for_testing_only=total_epochs_for_testing_only, symmetric_group=symmetric_group)
     svi = SVI(model, scheduler, use_cuda_graph=getattr(args, "use_cuda_graph", True))
     return model, scheduler, svi, train_loader, test_loader
 

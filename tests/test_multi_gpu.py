@@ -19,8 +19,8 @@ def _dataset():
     return synth.prepare_dataset(sim, expected_cells=200, total_droplets_included=500)
 
 
-def _worker(rank, world, port, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+def _worker(rank, world, port, q, mode="sharded", posterior=True):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), CB_DP_MODE=mode)
     torch.cuda.set_device(rank)
     dev = f"cuda:{rank}"
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
@@ -47,6 +47,11 @@ def _worker(rank, world, port, q):
         dist.all_gather(others, flat)
         same = all(torch.equal(others[0], o) for o in others)
         moved = float((flat - p0).abs().max())
+        if not posterior:
+            q.put((rank, same, moved, flat.cpu().numpy(), len(svi._graphs)))
+            svi._graphs.clear()
+            torch.cuda.synchronize()
+            return
         # posterior: shards + gather vs everything on one rank, seeded per chunk, shard boundaries on chunk boundaries
         dp.sync_buffers(model, world)
         model.eval()
@@ -83,3 +88,28 @@ def test_data_parallel_replicas_stay_identical_and_sharded_posterior_matches():
         assert moved > 0
         assert n_graphs >= 1  # forward + backward ran as CUDA-graph replays around the eager all-reduce
     assert res[0][3] is True
+
+
+def _train(world, mode):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() + (7 if mode == "p2p" else 3)) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode, False)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted((q.get(timeout=150) for _ in range(world)), key=lambda t: t[0])
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), mode
+    return res
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_p2p_exchange_matches_nccl_sharded_exchange():
+    """CB_DP_MODE=p2p (cb_clipped_adam_p2p: gradient shards summed out of the peers' buffers over NVLink, ClippedAdam,
+    parameters stored into every rank's buffer, all in one kernel between two device-side barriers) must train exactly
+    like the NCCL reduce_scatter -> sweep -> all_gather exchange: replicas identical, same parameters as the NCCL run."""
+    ref = _train(2, "sharded")
+    got = _train(2, "p2p")
+    for rank, same, moved, flat, n_graphs in got:
+        assert same, "parameter replicas diverged with the fused P2P exchange"
+        assert moved > 0 and n_graphs >= 1
+    np.testing.assert_allclose(got[0][3], ref[0][3], rtol=0, atol=1e-6)
