@@ -436,6 +436,15 @@ def run_b200(args):
                                         "note": "host scipy in -> device combine -> host scipy CSC out, transfers included"}
         model.train()
 
+    if world > 1 and os.environ.get("CB_DP_TIMING") == "1":
+        from cellbender_b200 import dp as _dp
+
+        tm = _dp.p2p_timing(svi.optim)
+        if tm is not None:
+            sys.stderr.write(f"[rank {rank}] p2p exchange: barrier {tm[0]:.4f} ms, fused kernel {tm[1]:.4f} ms, "
+                             f"barrier {tm[2]:.4f} ms\n")
+            sys.stderr.flush()
+
     def shutdown():
         if world > 1:
             svi._graphs.clear()  # graphs that captured NCCL collectives must go before the process group does

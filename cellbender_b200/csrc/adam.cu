@@ -12,6 +12,8 @@
 // with lr and b1 taken from torch.optim.lr_scheduler.OneCycleLR (cycle_momentum: b1 cycles 0.95 -> 0.85 -> 0.95),
 // precomputed on the host into per-step tables; the step counter lives on the device so that the whole training
 // step can be replayed as a CUDA graph.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cb {
@@ -76,6 +78,7 @@ struct P2PPointers {
   const float* grad[kMaxRanks];  // this shard inside every rank's gradient buffer, in rank order
   float* peer_param[kMaxRanks];  // this shard inside every OTHER rank's parameter buffer
   int n_grad, n_peer;
+  int own;  // index in grad[] of this rank's own (local HBM) gradient buffer
 };
 
 template <int NG>  // upper bound of the number of gradient sources (keeps the in-flight loads in registers)
@@ -150,6 +153,140 @@ __global__ void __launch_bounds__(256) clipped_adam_2d_kernel(float* __restrict_
   }
 }
 
+
+// ---- the same sweep with the peers' gradient shards fetched by TMA bulk copies ------------------------------------
+// Plain P2P loads keep only ~20 KB per SM in flight (one float4 per thread), far too little for the NVLink round trip:
+// the kernel above reaches ~320 GB/s per direction.  Here one elected thread per CTA streams the remote gradient tiles
+// (4 KB per peer per tile) into a shared-memory ring with cp.async.bulk (global -> shared, completion on an mbarrier),
+// several stages ahead of the threads that consume them, so each SM keeps STAGES x n_peers x 4 KB x (resident CTAs) in
+// flight.  Local operands (own gradient, param, exp_avg, exp_avg_sq) are ordinary coalesced loads issued before the
+// wait; the updated parameters go to the peers as posted P2P stores.
+__device__ __forceinline__ uint32_t adam_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void adam_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(adam_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void adam_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(adam_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void adam_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(adam_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void adam_bulk_load(void* dst_smem, const void* src_global, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   adam_smem_u32(dst_smem)),
+               "l"(src_global), "r"(bytes), "r"(adam_smem_u32(bar))
+               : "memory");
+}
+
+constexpr int kP2PTile = 256;  // float4 per tile = one per thread (4 KB per gradient source)
+
+template <int NG, int STAGES>
+__global__ void __launch_bounds__(256) clipped_adam_p2p_bulk_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                                    float* __restrict__ v, long long n, P2PPointers q,
+                                                                    const float* __restrict__ lr_table,
+                                                                    const float* __restrict__ beta1_table,
+                                                                    long long table_len, const long long* __restrict__ step_ptr,
+                                                                    float beta2, float eps, float clip) {
+  extern __shared__ __align__(128) unsigned char p2p_ring[];  // [STAGES][n_remote][kP2PTile] float4
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  const long long t0 = *step_ptr;
+  const long long ti = t0 < table_len ? t0 : table_len - 1;
+  const float lr = lr_table[ti], b1 = beta1_table[ti];
+  const double t = double(t0 + 1);
+  const float step_size = float(double(lr) * sqrt(1.0 - pow(double(beta2), t)) / (1.0 - pow(double(b1), t)));
+  const float omb1 = 1.0f - b1, omb2 = 1.0f - beta2;
+  const long long n4 = n >> 2;
+  const long long n_tiles = (n4 + kP2PTile - 1) / kP2PTile;
+  const int n_remote = q.n_grad - 1;
+  const int tid = threadIdx.x;
+  float4* ring = reinterpret_cast<float4*>(p2p_ring);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) adam_mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](long long tile, int s) {  // elected thread: fetch every peer's piece of this tile
+    const long long f0 = tile * kP2PTile;
+    const long long left = n4 - f0;
+    const uint32_t bytes = uint32_t(left < kP2PTile ? left : kP2PTile) * 16u;
+    adam_mbar_expect_tx(&full_bar[s], bytes * uint32_t(n_remote));
+    int r = 0;
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      if (k < q.n_grad && k != q.own) {
+        adam_bulk_load(ring + (size_t(s) * n_remote + r) * kP2PTile, reinterpret_cast<const float4*>(q.grad[k]) + f0, bytes,
+                       &full_bar[s]);
+        ++r;
+      }
+    }
+  };
+
+  if (tid == 0 && n_remote > 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      const long long tile = blockIdx.x + (long long)s * gridDim.x;
+      if (tile < n_tiles) issue(tile, s);
+    }
+  }
+  long long it = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int s = int(it % STAGES);
+    const uint32_t parity = uint32_t(it / STAGES) & 1u;
+    const long long i = tile * kP2PTile + tid;
+    const bool active = i < n4;
+    float4 gl = make_float4(0.f, 0.f, 0.f, 0.f), pp = gl, mm = gl, vv = gl;
+    if (active) {
+      gl = __ldcg(reinterpret_cast<const float4*>(q.grad[q.own]) + i);
+      pp = reinterpret_cast<float4*>(p)[i];
+      mm = reinterpret_cast<float4*>(m)[i];
+      vv = reinterpret_cast<float4*>(v)[i];
+    }
+    if (n_remote > 0) adam_mbar_wait(&full_bar[s], parity);
+    if (active) {
+      // sum in rank order (the result does not depend on which rank owns the shard)
+      float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
+      int r = 0;
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        if (k < q.n_grad) {
+          float4 x;
+          if (k == q.own) x = gl;
+          else x = ring[(size_t(s) * n_remote + r++) * kP2PTile + tid];
+          if (k == 0) gg = x;
+          else gg.x += x.x, gg.y += x.y, gg.z += x.z, gg.w += x.w;
+        }
+      }
+      float* pa = reinterpret_cast<float*>(&pp);
+      const float* ga = reinterpret_cast<const float*>(&gg);
+      float* ma = reinterpret_cast<float*>(&mm);
+      float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gc = fminf(fmaxf(ga[k], -clip), clip);
+        ma[k] = b1 * ma[k] + omb1 * gc;
+        va[k] = beta2 * va[k] + omb2 * gc * gc;
+        pa[k] -= step_size * ma[k] / (sqrtf(va[k]) + eps);
+      }
+      reinterpret_cast<float4*>(p)[i] = pp;
+      reinterpret_cast<float4*>(m)[i] = mm;
+      reinterpret_cast<float4*>(v)[i] = vv;
+#pragma unroll
+      for (int k = 0; k < NG - 1; ++k)
+        if (k < q.n_peer) __stcg(reinterpret_cast<float4*>(q.peer_param[k]) + i, pp);
+    }
+    __syncthreads();  // every thread has read stage s: it can be refilled
+    const long long next = tile + (long long)STAGES * gridDim.x;
+    if (tid == 0 && n_remote > 0 && next < n_tiles) issue(next, s);
+  }
+}
+
 }  // namespace cb
 
 static int adam_range(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
@@ -206,15 +343,35 @@ static int adam_range(float* p, const float* g, float* m, float* v, long long n,
 // ClippedAdam on this rank's shard with the data-parallel exchange fused in (see clipped_adam_p2p_kernel).
 // grad_ptrs[n_grad]: the shard's position inside every rank's gradient buffer, rank order (host array of device / peer
 // pointers); peer_param_ptrs[n_peer]: the shard's position inside the other ranks' parameter buffers.  n % 4 == 0.
+template <int NG, int STAGES>
+static int launch_p2p_bulk(float* p, float* m, float* v, long long n, const cb::P2PPointers& q, const float* lr_table,
+                           const float* beta1_table, long long table_len, const long long* step_ptr, float beta2, float eps,
+                           float clip, cudaStream_t st) {
+  auto kern = cb::clipped_adam_p2p_bulk_kernel<NG, STAGES>;
+  const int n_remote = q.n_grad - 1;
+  const int smem = STAGES * (n_remote > 0 ? n_remote : 1) * cb::kP2PTile * 16;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 3;
+  int per_sm = 0, dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess || per_sm < 1) return 4;
+  const long long n_tiles = (n / 4 + cb::kP2PTile - 1) / cb::kP2PTile;
+  long long blocks = (long long)n_sm * per_sm;  // persistent: every CTA resident, tiles strided over them
+  if (blocks > n_tiles) blocks = n_tiles;
+  kern<<<unsigned(blocks), 256, smem, st>>>(p, m, v, n, q, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip);
+  return 0;
+}
+
 extern "C" int cb_clipped_adam_p2p(float* p, float* m, float* v, long long n, const float* const* grad_ptrs, int n_grad,
-                                   float* const* peer_param_ptrs, int n_peer, const float* lr_table,
+                                   int own, float* const* peer_param_ptrs, int n_peer, const float* lr_table,
                                    const float* beta1_table, long long table_len, long long* step_ptr, float beta2,
                                    float eps, float clip, int advance, void* stream) {
   CB_REQUIRE(n >= 0 && (n & 3) == 0 && table_len > 0, "cb_clipped_adam_p2p: n=%lld must be a non-negative multiple of 4", n);
   CB_REQUIRE(n_grad >= 1 && n_grad <= cb::kMaxRanks && n_peer >= 0 && n_peer < n_grad + (n_grad == 1),
              "cb_clipped_adam_p2p: %d gradient sources / %d peers (at most %d ranks)", n_grad, n_peer, cb::kMaxRanks);
+  CB_REQUIRE(own >= 0 && own < n_grad, "cb_clipped_adam_p2p: own=%d outside [0, %d)", own, n_grad);
   cb::P2PPointers q{};
-  q.n_grad = n_grad, q.n_peer = n_peer;
+  q.n_grad = n_grad, q.n_peer = n_peer, q.own = own;
   for (int k = 0; k < n_grad; ++k) q.grad[k] = grad_ptrs[k];
   for (int k = 0; k < n_peer; ++k) q.peer_param[k] = peer_param_ptrs[k];
   for (const void* x : {(const void*)p, (const void*)m, (const void*)v})
@@ -224,7 +381,17 @@ extern "C" int cb_clipped_adam_p2p(float* p, float* m, float* v, long long n, co
   for (int k = 0; k < n_peer; ++k)
     CB_REQUIRE(q.peer_param[k] != nullptr && (reinterpret_cast<uintptr_t>(q.peer_param[k]) & 15) == 0, "cb_clipped_adam_p2p: bad peer pointer %d", k);
   cudaStream_t st = (cudaStream_t)stream;
-  if (n > 0) {
+  // CB_P2P_BULK=0 selects the plain-load kernel (A/B timing); default: TMA bulk prefetch of the peers' gradients
+  const char* bulk_env = getenv("CB_P2P_BULK");
+  const bool bulk = bulk_env == nullptr || bulk_env[0] != '0';
+  if (n > 0 && bulk) {
+    int rc = 0;
+    if (n_grad <= 2) rc = launch_p2p_bulk<2, 8>(p, m, v, n, q, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip, st);
+    else if (n_grad <= 4) rc = launch_p2p_bulk<4, 8>(p, m, v, n, q, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip, st);
+    else if (n_grad <= 8) rc = launch_p2p_bulk<8, 4>(p, m, v, n, q, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip, st);
+    else rc = launch_p2p_bulk<16, 3>(p, m, v, n, q, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip, st);
+    CB_REQUIRE(rc == 0, "cb_clipped_adam_p2p: kernel configuration failed (code %d)", rc);
+  } else if (n > 0) {
     long long blocks = (n / 4 + 255) / 256;
     const long long cap = 148LL * 8;  // 2 048 threads per SM, a multiple of the SM count
     if (blocks > cap) blocks = cap;

@@ -169,13 +169,33 @@ def p2p_step(opt, world_size: int, rank: int):
                                  len(peers))
     g_arr, p_arr, n_peer = cache
     timeout_ms = 20000  # a rank that never arrives traps the waiting kernels instead of hanging the GPUs
+    timing = os.environ.get("CB_DP_TIMING") == "1"  # CUDA events around the three phases (diagnostics, see p2p_timing)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timing else None
+    if timing:
+        ev[0].record()
     opt.symm_g.barrier(channel=0, timeout_ms=timeout_ms)
+    if timing:
+        ev[1].record()
     at = lambda t: t.data_ptr() + 4 * a
     lib().call("cb_clipped_adam_p2p", at(opt.flat_p), at(opt.flat_m), at(opt.flat_v), sh, ctypes.addressof(g_arr), world_size,
-               ctypes.addressof(p_arr), n_peer, opt.lr_table.data_ptr(), opt.beta1_table.data_ptr(), opt.lr_table.numel(),
+               rank, ctypes.addressof(p_arr), n_peer, opt.lr_table.data_ptr(), opt.beta1_table.data_ptr(), opt.lr_table.numel(),
                opt.step_count.data_ptr(), float(opt.beta2), float(opt.eps), float(opt.clip), 1, current_stream())
+    if timing:
+        ev[2].record()
     opt.symm_p.barrier(channel=1, timeout_ms=timeout_ms)
+    if timing:
+        ev[3].record()
+        opt.__dict__.setdefault("_p2p_events", []).append(ev)
     opt.host_steps += 1
+
+
+def p2p_timing(opt, last: int = 50):
+    """Mean milliseconds of (barrier before, fused kernel, barrier after) over the last recorded steps (CB_DP_TIMING=1)."""
+    evs = getattr(opt, "_p2p_events", [])[-last:]
+    if not evs:
+        return None
+    torch.cuda.synchronize()
+    return tuple(float(np.mean([e[i].elapsed_time(e[i + 1]) for e in evs])) for i in range(3))
 
 
 @torch.no_grad()

@@ -233,8 +233,9 @@ int cb_clipped_adam_2d(float* p, const float* g, float* m, float* v, int rows, i
 /* Data-parallel exchange fused into the optimizer sweep (new surface, the reference is single-GPU): ClippedAdam on
  * this rank's contiguous shard, reading the shard's gradient from every rank's gradient buffer (peer memory over
  * NVLink, summed in rank order) and storing the updated parameters into every rank's parameter buffer.
- * grad_ptrs[n_grad] / peer_param_ptrs[n_peer]: HOST arrays of device (peer-mapped) pointers.  n % 4 == 0.          */
-int cb_clipped_adam_p2p(float* p, float* m, float* v, long long n, const float* const* grad_ptrs, int n_grad,
+ * grad_ptrs[n_grad] / peer_param_ptrs[n_peer]: HOST arrays of device (peer-mapped) pointers; grad_ptrs[own] is this
+ * rank's own buffer (read from HBM, the others are fetched with TMA bulk copies over NVLink).  n % 4 == 0.          */
+int cb_clipped_adam_p2p(float* p, float* m, float* v, long long n, const float* const* grad_ptrs, int n_grad, int own,
                         float* const* peer_param_ptrs, int n_peer, const float* lr_table, const float* beta1_table,
                         long long table_len, long long* step_ptr, float beta2, float eps, float clip, int advance,
                         void* stream);

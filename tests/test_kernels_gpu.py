@@ -743,3 +743,56 @@ def test_prmu_matches_reference_golden(ops, golden_dir, tag, per_gene, fpr):
     np.testing.assert_allclose(reg.data, g[key + "_data"], rtol=1e-6, atol=1e-6)
     with pytest.raises(AssertionError):
         PRmu.regularize(noise_count_posterior_coo=coo, noise_offsets=offsets, raw_count_matrix=raw)
+
+
+# ---------------------------------------------------------------------------------------------- fused P2P Adam
+@pytest.mark.parametrize("bulk", ["1", "0"])
+@pytest.mark.parametrize("n_ranks,own", [(1, 0), (2, 0), (2, 1), (3, 1), (4, 3), (8, 5), (16, 0)])
+def test_clipped_adam_p2p_matches_sum_then_sweep(ops, monkeypatch, n_ranks, own, bulk):
+    """cb_clipped_adam_p2p on ONE device (the 'peer' buffers are local allocations): gradients of all ranks summed in
+    rank order + ClippedAdam on the shard + parameter stores into every peer buffer must equal sum -> cb_clipped_adam_range
+    -> copy; both the TMA bulk-prefetch kernel and the plain-load kernel; ragged last tile; step counter advanced."""
+    import ctypes
+
+    from cellbender_b200 import _cabi
+
+    monkeypatch.setenv("CB_P2P_BULK", bulk)
+    g = torch.Generator(device=DEV).manual_seed(n_ranks * 17 + own)
+    n_total, a = 4 * (256 * 37 + 13) + 64, 64  # the shard starts 64 elements into the buffers
+    n = n_total - a
+    rnd = lambda scale=1.0: torch.randn(n_total, device=DEV, generator=g) * scale
+    p0, m0, v0 = rnd(), rnd(0.1), rnd(0.1).abs()
+    grads = [rnd(8.0) for _ in range(n_ranks)]  # some values beyond the +-10 clamp
+    lr = torch.tensor([1e-3, 2e-3, 3e-3], device=DEV)
+    b1 = torch.tensor([0.95, 0.9, 0.85], device=DEV)
+    L = _cabi.lib()
+    st = _cabi.current_stream()
+    # reference: rank-order sum, then the single-GPU sweep
+    gsum = grads[0].clone()
+    for x in grads[1:]:
+        gsum += x
+    p_ref, m_ref, v_ref = p0.clone(), m0.clone(), v0.clone()
+    step_ref = torch.tensor([1], dtype=torch.int64, device=DEV)
+    at = lambda t: t.data_ptr() + 4 * a
+    L.call("cb_clipped_adam_range", at(p_ref), at(gsum), at(m_ref), at(v_ref), n, lr.data_ptr(), b1.data_ptr(), 3,
+           step_ref.data_ptr(), 0.999, 1e-8, 10.0, 1, st)
+    # fused kernel
+    p, m, v = p0.clone(), m0.clone(), v0.clone()
+    peers = [torch.full((n_total,), 7.0, device=DEV) for _ in range(n_ranks - 1)]
+    step = torch.tensor([1], dtype=torch.int64, device=DEV)
+    g_arr = (ctypes.c_void_p * n_ranks)(*[at(x) for x in grads])
+    p_arr = (ctypes.c_void_p * max(1, n_ranks - 1))(*[at(x) for x in peers])
+    L.call("cb_clipped_adam_p2p", at(p), at(m), at(v), n, ctypes.addressof(g_arr), n_ranks, own, ctypes.addressof(p_arr),
+           n_ranks - 1, lr.data_ptr(), b1.data_ptr(), 3, step.data_ptr(), 0.999, 1e-8, 10.0, 1, st)
+    torch.cuda.synchronize()
+    assert int(step) == 2 and int(step_ref) == 2
+    for got, want in ((p, p_ref), (m, m_ref), (v, v_ref)):
+        assert torch.equal(got[:a], want[:a]), "elements before the shard were touched"
+        torch.testing.assert_close(got[a:], want[a:], rtol=1e-6, atol=1e-8)
+    assert float((p[a:] - p0[a:]).abs().max()) > 0
+    for peer in peers:
+        assert torch.equal(peer[a:], p[a:]), "peer parameter buffer must receive exactly the owner's new values"
+        assert float(peer[:a].sub(7.0).abs().max()) == 0.0
+    with pytest.raises(_cabi.CabiError):
+        L.call("cb_clipped_adam_p2p", at(p), at(m), at(v), n - 1, ctypes.addressof(g_arr), n_ranks, own, ctypes.addressof(p_arr),
+               n_ranks - 1, lr.data_ptr(), b1.data_ptr(), 3, step.data_ptr(), 0.999, 1e-8, 10.0, 1, st)
