@@ -480,7 +480,11 @@ def run_b200(args):
         "config": {"workload": args.workload, "genes": model.n_genes, "analysed_droplets": int(ds.analyzed_barcode_inds.size),
                    "minibatch_rows": 255, "steps_per_epoch_per_gpu": spe_rank, "steps_per_epoch_global": spe_global,
                    "l2": "inputs > L2: each step streams 275 MB of weights + 1.9 GB of optimizer state",
-                   "gemm_backend": __import__("cellbender_b200.gemm", fromlist=["BACKEND"]).BACKEND},
+                   "gemm_backend": __import__("cellbender_b200.gemm", fromlist=["BACKEND"]).BACKEND,
+                   "dp_exchange": (None if world == 1 else
+                                   "p2p: exchange fused into the ClippedAdam sweep over NVLink peer memory"
+                                   if getattr(svi.optim, "symm_p", None) is not None and os.environ.get("CB_DP_MODE", "p2p") == "p2p"
+                                   else os.environ.get("CB_DP_MODE", "sharded (NCCL)"))},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * 255, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / K,

@@ -8,5 +8,5 @@ LAUNCHES = {
     "cb_latent_prepare": 1, "cb_latent_beta_sample": 1, "cb_latent_forward": 1, "cb_latent_backward": 1,
     "cb_simplex_forward": 1, "cb_posterior_tilt": 1, "cb_prq_regularize": 1, "cb_nbpc_exact_log_prob_fwd": 1, "cb_nbpc_exact_log_prob_bwd": 1, "cb_gemm_tf32_dw_adam": 1, "cb_clipped_adam_range": 1, "cb_clipped_adam_2d": 1, "cb_encoder_features": 1, "cb_head_forward": 1, "cb_head_backward": 1, "cb_obs_loss": 1,
     "cb_obs_small_grads": 1, "cb_bn_act_forward": 1, "cb_bn_act_backward": 1, "cb_simplex_backward": 1,
-    "cb_csr_combine_flags": 1, "cb_csr_combine_fill": 1, "cb_csr_to_csc": 2, "cb_clipped_adam_p2p": 2, "cb_dense_nonzero_flags": 1, "cb_dense_to_coo": 1,
+    "cb_csr_combine_flags": 1, "cb_csr_combine_fill": 1, "cb_csr_to_csc": 2, "cb_clipped_adam_p2p": 2, "cb_clipped_adam_nvls": 2, "cb_dense_nonzero_flags": 1, "cb_dense_to_coo": 1,
 }

@@ -287,6 +287,63 @@ __global__ void __launch_bounds__(256) clipped_adam_p2p_bulk_kernel(float* __res
   }
 }
 
+// ---- the same sweep through the NVSwitch (NVLS): in-switch gradient reduction, multicast parameter store -----------
+// mc_grad / mc_param are MULTICAST addresses of the symmetric gradient / parameter buffers (one address that names
+// the same offset on every rank).  multimem.ld_reduce returns the sum over all ranks computed inside the switch, so a
+// rank receives 16 bytes per float4 however many ranks there are (plain P2P loads: 16 (R - 1)); multimem.st delivers
+// the updated parameters to every rank with ONE outgoing store.  Per rank and direction the links then carry about
+// one parameter set per step for any R, where the plain P2P kernel carries 2 (R - 1) / R of it.
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc_ptr) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc_ptr)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st(float* mc_ptr, const float4& x) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_ptr), "f"(x.x), "f"(x.y), "f"(x.z),
+               "f"(x.w)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256) clipped_adam_nvls_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                                float* __restrict__ v, long long n,
+                                                                const float* __restrict__ mc_grad, float* __restrict__ mc_param,
+                                                                const float* __restrict__ lr_table,
+                                                                const float* __restrict__ beta1_table, long long table_len,
+                                                                const long long* __restrict__ step_ptr, float beta2, float eps,
+                                                                float clip) {
+  const long long t0 = *step_ptr;
+  const long long ti = t0 < table_len ? t0 : table_len - 1;
+  const float lr = lr_table[ti], b1 = beta1_table[ti];
+  const double t = double(t0 + 1);
+  const float step_size = float(double(lr) * sqrt(1.0 - pow(double(beta2), t)) / (1.0 - pow(double(b1), t)));
+  const float omb1 = 1.0f - b1, omb2 = 1.0f - beta2;
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 gg = multimem_ld_reduce_add(mc_grad + 4 * i);
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = reinterpret_cast<float*>(&pp);
+    const float* ga = reinterpret_cast<const float*>(&gg);
+    float* ma = reinterpret_cast<float*>(&mm);
+    float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gc = fminf(fmaxf(ga[k], -clip), clip);
+      ma[k] = b1 * ma[k] + omb1 * gc;
+      va[k] = beta2 * va[k] + omb2 * gc * gc;
+      pa[k] -= step_size * ma[k] / (sqrtf(va[k]) + eps);
+    }
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    multimem_st(mc_param + 4 * i, pp);  // every rank's parameter buffer, this rank's included
+  }
+}
+
 }  // namespace cb
 
 static int adam_range(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
@@ -405,4 +462,25 @@ extern "C" int cb_clipped_adam_p2p(float* p, float* m, float* v, long long n, co
   }
   if (advance) cb::advance_step_kernel<<<1, 1, 0, st>>>(step_ptr);
   return cb::check_launch("cb_clipped_adam_p2p");
+}
+
+// The NVLS form of cb_clipped_adam_p2p: mc_grad / mc_param are the multicast addresses of this rank's shard inside the
+// symmetric gradient / parameter buffers; p / m / v the local shard (p is only read here: the multicast store writes it).
+extern "C" int cb_clipped_adam_nvls(float* p, float* m, float* v, long long n, const float* mc_grad, float* mc_param,
+                                    const float* lr_table, const float* beta1_table, long long table_len,
+                                    long long* step_ptr, float beta2, float eps, float clip, int advance, void* stream) {
+  CB_REQUIRE(n >= 0 && (n & 3) == 0 && table_len > 0, "cb_clipped_adam_nvls: n=%lld must be a non-negative multiple of 4", n);
+  CB_REQUIRE(mc_grad != nullptr && mc_param != nullptr, "cb_clipped_adam_nvls: multicast pointers must not be NULL");
+  for (const void* x : {(const void*)p, (const void*)m, (const void*)v, (const void*)mc_grad, (const void*)mc_param})
+    CB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "cb_clipped_adam_nvls: buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n > 0) {
+    long long blocks = (n / 4 + 255) / 256;
+    const long long cap = 148LL * 6;
+    if (blocks > cap) blocks = cap;
+    cb::clipped_adam_nvls_kernel<<<unsigned(blocks), 256, 0, st>>>(p, m, v, n, mc_grad, mc_param, lr_table, beta1_table, table_len,
+                                                                   step_ptr, beta2, eps, clip);
+  }
+  if (advance) cb::advance_step_kernel<<<1, 1, 0, st>>>(step_ptr);
+  return cb::check_launch("cb_clipped_adam_nvls");
 }

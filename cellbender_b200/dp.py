@@ -39,13 +39,17 @@ def shard_cells(n_cells: int, rank: int, world_size: int) -> np.ndarray:
 
 
 def dp_mode() -> str:
-    return os.environ.get("CB_DP_MODE", "sharded")
+    """Exchange mode of data-parallel training: 'p2p' (default: exchange fused into the optimizer sweep over NVLink peer
+    memory, ``p2p_step``), 'sharded' (NCCL reduce_scatter -> sweep -> all_gather), 'allreduce', 'overlap'."""
+    return os.environ.get("CB_DP_MODE", "p2p")
 
 
 def p2p_group():
     """Process group for symmetric-memory (NVLink peer) parameter / gradient buffers, or None when the fused P2P
     exchange is not selected (CB_DP_MODE=p2p) or torch.distributed is not running on NCCL."""
     if dp_mode() != "p2p" or not dist.is_available() or not dist.is_initialized() or dist.get_backend() != "nccl":
+        return None
+    if dist.get_world_size() > 16:  # cb_clipped_adam_p2p carries at most 16 gradient sources
         return None
     return dist.group.WORLD
 
@@ -65,11 +69,15 @@ def attach(svi, world_size: int):
         n_chunks = int(os.environ.get("CB_DP_CHUNKS", "1"))
         # measured on B200 (r01, ms/step at 2 / 4 GPUs): sharded 1.87 / 1.96, overlap 1.92 / 2.06, allreduce 1.87 / 2.10
         mode = dp_mode()
-        if mode == "p2p":
-            if getattr(svi.optim, "symm_p", None) is None:
+        if mode == "p2p" and (getattr(svi.optim, "symm_p", None) is None or svi.optim.n % (4 * world_size) != 0):
+            # the optimizer's buffers are not NVLink peer memory (symmetric-memory rendezvous unavailable on this system,
+            # optimizer built without a group, more than 16 ranks): NCCL carries the exchange instead
+            if "CB_DP_MODE" in os.environ:
                 raise RuntimeError("CB_DP_MODE=p2p needs the optimizer's flat buffers in symmetric memory "
                                    "(run.setup_inference / optim.get_optimizer(symmetric_group=...))")
-            assert svi.optim.n % (4 * world_size) == 0
+            mode = "sharded"
+        if mode == "p2p":
+            # measured on B200 (r01, ms/step at 2 / 4 GPUs): 1.46 / 1.72 against 1.85 / 1.96 for the NCCL exchange
             svi.exchange_and_step = lambda opt: p2p_step(opt, world_size, rank)
         elif mode == "overlap" and n_chunks <= 1:
             # optional: the reduction of each large gradient block is issued right behind its weight-gradient GEMM, on
@@ -143,6 +151,22 @@ def reduce_scatter_step(opt, world_size: int, rank: int):
     opt.host_steps += 1
 
 
+def p2p_uses_nvls(opt, world_size: int) -> bool:
+    """NVLS form (multimem.ld_reduce / multimem.st through the NVSwitch) when the symmetric buffers have multicast
+    addresses and CB_P2P_NVLS=1 asks for it.  (Plain peer loads / stores put 2 (R - 1) / R parameter sets per step on
+    every link, NVLS about one for any R.)"""
+    have = bool(getattr(opt.symm_g, "has_multicast_support", False)) and int(getattr(opt.symm_g, "multicast_ptr", 0) or 0) != 0 \
+        and int(getattr(opt.symm_p, "multicast_ptr", 0) or 0) != 0
+    env = os.environ.get("CB_P2P_NVLS")
+    if env == "0" or not have:
+        if env == "1":
+            raise RuntimeError("CB_P2P_NVLS=1 but the symmetric buffers have no multicast address on this system")
+        return False
+    # measured on B200 (r01): fused kernel 0.72 ms (NVLS) vs 0.43 ms (peer loads / stores) at 2 GPUs, 0.64 vs 0.64 at 4:
+    # the one-load-per-thread NVLS loop is latency-bound, so it stays opt-in until it is unrolled
+    return env == "1"
+
+
 @torch.no_grad()
 def p2p_step(opt, world_size: int, rank: int):
     """The data-parallel exchange fused into the optimizer sweep, over NVLink peer memory (cb_clipped_adam_p2p):
@@ -177,9 +201,15 @@ def p2p_step(opt, world_size: int, rank: int):
     if timing:
         ev[1].record()
     at = lambda t: t.data_ptr() + 4 * a
-    lib().call("cb_clipped_adam_p2p", at(opt.flat_p), at(opt.flat_m), at(opt.flat_v), sh, ctypes.addressof(g_arr), world_size,
-               rank, ctypes.addressof(p_arr), n_peer, opt.lr_table.data_ptr(), opt.beta1_table.data_ptr(), opt.lr_table.numel(),
-               opt.step_count.data_ptr(), float(opt.beta2), float(opt.eps), float(opt.clip), 1, current_stream())
+    tab = (opt.lr_table.data_ptr(), opt.beta1_table.data_ptr(), opt.lr_table.numel(), opt.step_count.data_ptr(),
+           float(opt.beta2), float(opt.eps), float(opt.clip), 1, current_stream())
+    if p2p_uses_nvls(opt, world_size):
+        # in-switch reduction of the gradients, multicast store of the parameters
+        lib().call("cb_clipped_adam_nvls", at(opt.flat_p), at(opt.flat_m), at(opt.flat_v), sh,
+                   int(opt.symm_g.multicast_ptr) + 4 * a, int(opt.symm_p.multicast_ptr) + 4 * a, *tab)
+    else:
+        lib().call("cb_clipped_adam_p2p", at(opt.flat_p), at(opt.flat_m), at(opt.flat_v), sh, ctypes.addressof(g_arr),
+                   world_size, rank, ctypes.addressof(p_arr), n_peer, *tab)
     if timing:
         ev[2].record()
     opt.symm_p.barrier(channel=1, timeout_ms=timeout_ms)

@@ -4,6 +4,7 @@ batch size rule, train/test split, optimizer.  The CLI, file I/O, report and che
 scope -- a caller that has a prepared dataset object gets the same model trained the same way.
 """
 import argparse
+import os
 import logging
 import random
 from typing import Optional, Tuple
@@ -87,9 +88,24 @@ def setup_inference(dataset_obj, args, device: Optional[str] = None, total_epoch
         from .dp import p2p_group
 
         symmetric_group = p2p_group()  # None unless CB_DP_MODE=p2p
-    scheduler = get_optimizer(model, n_batches=len(train_loader), batch_size=train_loader.batch_size, epochs=args.epochs,
-                              learning_rate=args.learning_rate, constant_learning_rate=args.constant_learning_rate,
-                              total_epochs_for_testing_only=total_epochs_for_testing_only, symmetric_group=symmetric_group)
+    opt_args = dict(n_batches=len(train_loader), batch_size=train_loader.batch_size, epochs=args.epochs,
+                    learning_rate=args.learning_rate, constant_learning_rate=args.constant_learning_rate,
+                    total_epochs_for_testing_only=total_epochs_for_testing_only)
+    scheduler = None
+    if symmetric_group is not None:
+        # the parameters are re-homed by the optimizer, so probe the symmetric-memory rendezvous BEFORE building it: if
+        # this system cannot map peer memory (every rank sees the same failure), NCCL carries the exchange (dp.attach)
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            probe = symm_mem.empty(64, dtype=torch.float32, device=device or "cuda")
+            symm_mem.rendezvous(probe, symmetric_group)
+        except Exception as exc:  # noqa: BLE001
+            if "CB_DP_MODE" in os.environ:
+                raise
+            logger.warning(f"symmetric memory unavailable ({type(exc).__name__}: {exc}); data-parallel exchange through NCCL")
+            symmetric_group = None
+    scheduler = get_optimizer(model, symmetric_group=symmetric_group, **opt_args)
     svi = SVI(model, scheduler, use_cuda_graph=getattr(args, "use_cuda_graph", True))
     return model, scheduler, svi, train_loader, test_loader
 

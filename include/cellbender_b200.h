@@ -239,6 +239,12 @@ int cb_clipped_adam_p2p(float* p, float* m, float* v, long long n, const float* 
                         float* const* peer_param_ptrs, int n_peer, const float* lr_table, const float* beta1_table,
                         long long table_len, long long* step_ptr, float beta2, float eps, float clip, int advance,
                         void* stream);
+/* The same exchange through the NVSwitch (NVLS): mc_grad / mc_param = multicast addresses of the shard in the symmetric
+ * gradient / parameter buffers; multimem.ld_reduce sums the gradients inside the switch, multimem.st delivers the new
+ * parameters to every rank.                                                                                         */
+int cb_clipped_adam_nvls(float* p, float* m, float* v, long long n, const float* mc_grad, float* mc_param,
+                         const float* lr_table, const float* beta1_table, long long table_len, long long* step_ptr,
+                         float beta2, float eps, float clip, int advance, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * A10-A12  posterior noise-count log-probability over the stored (non-zero) counts.  Replaces
