@@ -77,7 +77,8 @@ def attach(svi, world_size: int):
                                    "(run.setup_inference / optim.get_optimizer(symmetric_group=...))")
             mode = "sharded"
         if mode == "p2p":
-            # measured on B200 (r01, ms/step at 2 / 4 GPUs): 1.46 / 1.72 against 1.85 / 1.96 for the NCCL exchange
+            # measured on B200 (r01, ms/step): 2 GPUs 1.46 against 1.85 for the NCCL exchange; 4 GPUs fused kernel 0.64 ms,
+            # step ~1.72 (the NVLS variant with the same kernel time measured 1.714) against 1.96 (profiles/r01d_dp_exchange.txt)
             svi.exchange_and_step = lambda opt: p2p_step(opt, world_size, rank)
         elif mode == "overlap" and n_chunks <= 1:
             # optional: the reduction of each large gradient block is issued right behind its weight-gradient GEMM, on
