@@ -180,7 +180,7 @@ def test_training_loop_scheduler_and_graph_replay():
     assert opt.host_steps == n_batches * 4 and int(opt.step_count.item()) == opt.host_steps
     assert 0.9 * args.learning_rate * 10 < max(opt._lrs) <= args.learning_rate * 10 + 1e-12  # OneCycle peak = 10 lr
     assert abs(opt._lrs[-1] - args.learning_rate * 10 / 25 / 1e4) < 1e-12  # ends at initial_lr / 1e4
-    with pytest.raises(ValueError):
+    with pytest.raises(ValueError, match=r"Tried to step .* times. The specified number of total steps is .*"):
         svi.step(next(iter(train_loader)))  # one step beyond total_steps raises, like torch's OneCycleLR
 
 
