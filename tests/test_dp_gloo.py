@@ -78,3 +78,44 @@ def test_two_rank_exchange_on_gloo():
         assert gathered == expect
         assert flat_g == [3.0] * 5  # 1 + 2
         assert offset == {"logit_p": 1.5, "epsilon": -0.25}
+
+
+def test_owner_shard_exchange_scheme_equals_allreduce_then_full_sweep():
+    """The arithmetic contract of dp.p2p_step / dp.reduce_scatter_step, emulated in numpy with the oracle's ClippedAdam:
+    every rank owns one contiguous shard, sums the shard's gradients of all ranks in rank order, updates its shard and
+    delivers the new parameters to every rank.  Result: every replica holds exactly what all-reduce + a full sweep on
+    every rank would give (the sum order per element is the same rank order), for several steps and rank counts."""
+    from oracle.train_step import ClippedAdamPerTensor
+
+    rng = np.random.default_rng(0)
+    n = 64 * 12
+    for world in (2, 3, 4, 8):
+        if n % (4 * world):
+            continue
+        p0 = torch.tensor(rng.normal(size=n), dtype=torch.float32)
+        # reference: one replica, gradients summed in rank order, full sweep
+        ref_p = {"w": p0.clone()}
+        ref_opt = ClippedAdamPerTensor(ref_p, lr=1e-3)
+        # scheme: world replicas of the parameters, but moments only for the owned shard
+        sh = n // world
+        replicas = [p0.clone() for _ in range(world)]
+        shard_p = [{"w": replicas[r][r * sh:(r + 1) * sh].clone()} for r in range(world)]
+        shard_opt = [ClippedAdamPerTensor(shard_p[r], lr=1e-3) for r in range(world)]
+        for step in range(3):
+            grads = [torch.tensor(rng.normal(scale=8.0, size=n), dtype=torch.float32) for _ in range(world)]
+            total = grads[0].clone()
+            for g in grads[1:]:
+                total += g
+            ref_p["w"].grad = total.clone()
+            ref_opt.step()
+            for r in range(world):  # owner r: rank-order sum of its shard, sweep, deliver to everybody
+                acc = grads[0][r * sh:(r + 1) * sh].clone()
+                for g in grads[1:]:
+                    acc += g[r * sh:(r + 1) * sh]
+                shard_p[r]["w"].grad = acc
+                shard_opt[r].step()
+                for rep in replicas:
+                    rep[r * sh:(r + 1) * sh] = shard_p[r]["w"]
+            for rep in replicas:
+                assert torch.equal(rep, replicas[0])
+            assert torch.equal(replicas[0], ref_p["w"]), (world, step)
