@@ -12,12 +12,16 @@
 // with lr and b1 taken from torch.optim.lr_scheduler.OneCycleLR (cycle_momentum: b1 cycles 0.95 -> 0.85 -> 0.95),
 // precomputed on the host into per-step tables; the step counter lives on the device so that the whole training
 // step can be replayed as a CUDA graph.
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace cb {
 
+// Residency: the sweep is HBM-bound and runs on a side stream WHILE the latency-bound chain of backward kernels runs on
+// others (optim.early_block_update).  It therefore must not fill every thread slot of the SMs (a grid of 2 048
+// threads/SM made small kernels of the critical chain wait ~50 us for a slot, r02 timeline): the grid is capped at four
+// 256-thread CTAs per SM and each thread keeps two 16-byte loads per array in flight (128 KB per SM, twice what HBM
+// latency x bandwidth needs).
+constexpr int kAdamUnroll = 2;
 __global__ void __launch_bounds__(256) clipped_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                            float* __restrict__ m, float* __restrict__ v, long long n,
                                                            const float* __restrict__ lr_table,
@@ -33,25 +37,37 @@ __global__ void __launch_bounds__(256) clipped_adam_kernel(float* __restrict__ p
 
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 pp = reinterpret_cast<float4*>(p)[i];
-    const float4 gg = reinterpret_cast<const float4*>(g)[i];
-    float4 mm = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
-    float* pa = reinterpret_cast<float*>(&pp);
-    const float* ga = reinterpret_cast<const float*>(&gg);
-    float* ma = reinterpret_cast<float*>(&mm);
-    float* va = reinterpret_cast<float*>(&vv);
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n4; i0 += stride * kAdamUnroll) {
+    float4 pp[kAdamUnroll], gg[kAdamUnroll], mm[kAdamUnroll], vv[kAdamUnroll];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float gc = fminf(fmaxf(ga[k] * grad_scale, -clip), clip);
-      ma[k] = b1 * ma[k] + omb1 * gc;
-      va[k] = beta2 * va[k] + omb2 * gc * gc;
-      pa[k] -= step_size * ma[k] / (sqrtf(va[k]) + eps);
+    for (int u = 0; u < kAdamUnroll; ++u) {  // all loads first
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        pp[u] = reinterpret_cast<float4*>(p)[i];
+        gg[u] = reinterpret_cast<const float4*>(g)[i];
+        mm[u] = reinterpret_cast<float4*>(m)[i];
+        vv[u] = reinterpret_cast<float4*>(v)[i];
+      }
     }
-    reinterpret_cast<float4*>(p)[i] = pp;
-    reinterpret_cast<float4*>(m)[i] = mm;
-    reinterpret_cast<float4*>(v)[i] = vv;
+#pragma unroll
+    for (int u = 0; u < kAdamUnroll; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= n4) break;
+      float* pa = reinterpret_cast<float*>(&pp[u]);
+      const float* ga = reinterpret_cast<const float*>(&gg[u]);
+      float* ma = reinterpret_cast<float*>(&mm[u]);
+      float* va = reinterpret_cast<float*>(&vv[u]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gc = fminf(fmaxf(ga[k] * grad_scale, -clip), clip);
+        ma[k] = b1 * ma[k] + omb1 * gc;
+        va[k] = beta2 * va[k] + omb2 * gc * gc;
+        pa[k] -= step_size * ma[k] / (sqrtf(va[k]) + eps);
+      }
+      reinterpret_cast<float4*>(p)[i] = pp[u];
+      reinterpret_cast<float4*>(m)[i] = mm[u];
+      reinterpret_cast<float4*>(v)[i] = vv[u];
+    }
   }
   for (long long i = 4 * n4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
     const float gc = fminf(fmaxf(g[i] * grad_scale, -clip), clip);
@@ -80,79 +96,6 @@ struct P2PPointers {
   int n_grad, n_peer;
   int own;  // index in grad[] of this rank's own (local HBM) gradient buffer
 };
-
-template <int NG>  // upper bound of the number of gradient sources (keeps the in-flight loads in registers)
-__global__ void __launch_bounds__(256, NG <= 4 ? 5 : 2) clipped_adam_p2p_kernel(float* __restrict__ p, float* __restrict__ m,
-                                                               float* __restrict__ v, long long n, P2PPointers q,
-                                                               const float* __restrict__ lr_table,
-                                                               const float* __restrict__ beta1_table, long long table_len,
-                                                               const long long* __restrict__ step_ptr, float beta2, float eps,
-                                                               float clip) {
-  const long long t0 = *step_ptr;
-  const long long ti = t0 < table_len ? t0 : table_len - 1;
-  const float lr = lr_table[ti], b1 = beta1_table[ti];
-  const double t = double(t0 + 1);
-  const float step_size = float(double(lr) * sqrt(1.0 - pow(double(beta2), t)) / (1.0 - pow(double(b1), t)));
-  const float omb1 = 1.0f - b1, omb2 = 1.0f - beta2;
-  const long long n4 = n >> 2;  // n is a multiple of 4 (checked on the host)
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
-    // all gradient loads first (the remote ones take an NVLink round trip), L1 bypassed: peers rewrite them every step
-    float4 gsrc[NG];
-#pragma unroll
-    for (int k = 0; k < NG; ++k)
-      if (k < q.n_grad) gsrc[k] = __ldcg(reinterpret_cast<const float4*>(q.grad[k]) + i);
-    float4 pp = reinterpret_cast<float4*>(p)[i];
-    float4 mm = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
-    float4 gg = gsrc[0];
-#pragma unroll
-    for (int k = 1; k < NG; ++k)
-      if (k < q.n_grad) gg.x += gsrc[k].x, gg.y += gsrc[k].y, gg.z += gsrc[k].z, gg.w += gsrc[k].w;
-    float* pa = reinterpret_cast<float*>(&pp);
-    const float* ga = reinterpret_cast<const float*>(&gg);
-    float* ma = reinterpret_cast<float*>(&mm);
-    float* va = reinterpret_cast<float*>(&vv);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float gc = fminf(fmaxf(ga[k], -clip), clip);
-      ma[k] = b1 * ma[k] + omb1 * gc;
-      va[k] = beta2 * va[k] + omb2 * gc * gc;
-      pa[k] -= step_size * ma[k] / (sqrtf(va[k]) + eps);
-    }
-    reinterpret_cast<float4*>(p)[i] = pp;
-    reinterpret_cast<float4*>(m)[i] = mm;
-    reinterpret_cast<float4*>(v)[i] = vv;
-#pragma unroll
-    for (int k = 0; k < NG - 1; ++k)
-      if (k < q.n_peer) __stcg(reinterpret_cast<float4*>(q.peer_param[k]) + i, pp);
-  }
-}
-
-// the same update on a [rows, cols] sub-block of a [rows, ld] matrix (the few feature columns of a weight matrix whose
-// gene block is updated inside the weight-gradient GEMM epilogue)
-__global__ void __launch_bounds__(256) clipped_adam_2d_kernel(float* __restrict__ p, const float* __restrict__ g,
-                                                              float* __restrict__ m, float* __restrict__ v, int rows, int cols,
-                                                              long long ld, const float* __restrict__ lr_table,
-                                                              const float* __restrict__ beta1_table, long long table_len,
-                                                              const long long* __restrict__ step_ptr, float beta2, float eps,
-                                                              float clip) {
-  const long long t0 = *step_ptr;
-  const long long ti = t0 < table_len ? t0 : table_len - 1;
-  const float lr = lr_table[ti], b1 = beta1_table[ti];
-  const double t = double(t0 + 1);
-  const float step_size = float(double(lr) * sqrt(1.0 - pow(double(beta2), t)) / (1.0 - pow(double(b1), t)));
-  const float omb1 = 1.0f - b1, omb2 = 1.0f - beta2;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)rows * cols; i += (long long)gridDim.x * blockDim.x) {
-    const long long idx = (i / cols) * ld + (i % cols);
-    const float gc = fminf(fmaxf(g[idx], -clip), clip);
-    const float mk = b1 * m[idx] + omb1 * gc;
-    const float vk = beta2 * v[idx] + omb2 * gc * gc;
-    m[idx] = mk, v[idx] = vk;
-    p[idx] -= step_size * mk / (sqrtf(vk) + eps);
-  }
-}
-
 
 // ---- the same sweep with the peers' gradient shards fetched by TMA bulk copies ------------------------------------
 // Plain P2P loads keep only ~20 KB per SM in flight (one float4 per thread), far too little for the NVLink round trip:
@@ -307,9 +250,11 @@ __device__ __forceinline__ void multimem_st(float* mc_ptr, const float4& x) {
                : "memory");
 }
 
-__global__ void __launch_bounds__(256) clipped_adam_nvls_kernel(float* __restrict__ p, float* __restrict__ m,
-                                                                float* __restrict__ v, long long n,
-                                                                const float* __restrict__ mc_grad, float* __restrict__ mc_param,
+// kNvlsUnroll in-switch reductions are issued back to back before the first one is consumed: the round trip through the
+// NVSwitch is several microseconds, and one 16-byte request per thread (r01) left the links latency-bound.
+constexpr int kNvlsUnroll = 4;
+__global__ void __launch_bounds__(256) clipped_adam_nvls_kernel(float* p, float* __restrict__ m, float* __restrict__ v, long long n,
+                                                                const float* mc_grad, float* mc_param,
                                                                 const float* __restrict__ lr_table,
                                                                 const float* __restrict__ beta1_table, long long table_len,
                                                                 const long long* __restrict__ step_ptr, float beta2, float eps,
@@ -322,25 +267,41 @@ __global__ void __launch_bounds__(256) clipped_adam_nvls_kernel(float* __restric
   const float omb1 = 1.0f - b1, omb2 = 1.0f - beta2;
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 gg = multimem_ld_reduce_add(mc_grad + 4 * i);
-    float4 pp = reinterpret_cast<float4*>(p)[i];
-    float4 mm = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
-    float* pa = reinterpret_cast<float*>(&pp);
-    const float* ga = reinterpret_cast<const float*>(&gg);
-    float* ma = reinterpret_cast<float*>(&mm);
-    float* va = reinterpret_cast<float*>(&vv);
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n4; i0 += stride * kNvlsUnroll) {
+    float4 gg[kNvlsUnroll], pp[kNvlsUnroll], mm[kNvlsUnroll], vv[kNvlsUnroll];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float gc = fminf(fmaxf(ga[k], -clip), clip);
-      ma[k] = b1 * ma[k] + omb1 * gc;
-      va[k] = beta2 * va[k] + omb2 * gc * gc;
-      pa[k] -= step_size * ma[k] / (sqrtf(va[k]) + eps);
+    for (int u = 0; u < kNvlsUnroll; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) gg[u] = multimem_ld_reduce_add(mc_grad + 4 * i);
     }
-    reinterpret_cast<float4*>(m)[i] = mm;
-    reinterpret_cast<float4*>(v)[i] = vv;
-    multimem_st(mc_param + 4 * i, pp);  // every rank's parameter buffer, this rank's included
+#pragma unroll
+    for (int u = 0; u < kNvlsUnroll; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        pp[u] = reinterpret_cast<const float4*>(p)[i];
+        mm[u] = reinterpret_cast<const float4*>(m)[i];
+        vv[u] = reinterpret_cast<const float4*>(v)[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kNvlsUnroll; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= n4) break;
+      float* pa = reinterpret_cast<float*>(&pp[u]);
+      const float* ga = reinterpret_cast<const float*>(&gg[u]);
+      float* ma = reinterpret_cast<float*>(&mm[u]);
+      float* va = reinterpret_cast<float*>(&vv[u]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gc = fminf(fmaxf(ga[k], -clip), clip);
+        ma[k] = b1 * ma[k] + omb1 * gc;
+        va[k] = beta2 * va[k] + omb2 * gc * gc;
+        pa[k] -= step_size * ma[k] / (sqrtf(va[k]) + eps);
+      }
+      reinterpret_cast<float4*>(m)[i] = mm[u];
+      reinterpret_cast<float4*>(v)[i] = vv[u];
+      multimem_st(mc_param + 4 * i, pp[u]);  // every rank's parameter buffer, this rank's included
+    }
   }
 }
 
@@ -365,16 +326,6 @@ extern "C" int cb_clipped_adam_range(float* p, const float* g, float* m, float* 
   return adam_range(p, g, m, v, n, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip, 1.0f, advance, stream);
 }
 
-extern "C" int cb_clipped_adam_2d(float* p, const float* g, float* m, float* v, int rows, int cols, long long ld,
-                                  const float* lr_table, const float* beta1_table, long long table_len,
-                                  const long long* step_ptr, float beta2, float eps, float clip, void* stream) {
-  CB_REQUIRE(rows > 0 && cols > 0 && ld >= cols && table_len > 0, "cb_clipped_adam_2d: bad shape [%d, %d] ld=%lld", rows, cols, ld);
-  const long long n = (long long)rows * cols;
-  cb::clipped_adam_2d_kernel<<<unsigned((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, rows, cols, ld, lr_table,
-                                                                                         beta1_table, table_len, step_ptr, beta2,
-                                                                                         eps, clip);
-  return cb::check_launch("cb_clipped_adam_2d");
-}
 
 static int adam_range(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
                       const float* beta1_table, long long table_len, long long* step_ptr, float beta2, float eps, float clip,
@@ -387,8 +338,8 @@ static int adam_range(float* p, const float* g, float* m, float* v, long long n,
   for (const void* q : {(const void*)p, (const void*)g, (const void*)m, (const void*)v})
     CB_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0, "cb_clipped_adam_step: buffers must be 16-byte aligned");
   const long long n4 = (n + 3) / 4;
-  long long blocks = (n4 + 255) / 256;
-  const long long cap = 148LL * 16;  // persistent-ish grid: a multiple of the SM count
+  long long blocks = (n4 + 256 * cb::kAdamUnroll - 1) / (256 * cb::kAdamUnroll);
+  const long long cap = 4LL * cb::sm_count();  // half of the SMs' thread slots stay free for concurrent kernels
   if (blocks > cap) blocks = cap;
   cb::clipped_adam_kernel<<<unsigned(blocks), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_table, beta1_table,
                                                                               table_len, step_ptr, beta2, eps, clip,
@@ -408,9 +359,8 @@ static int launch_p2p_bulk(float* p, float* m, float* v, long long n, const cb::
   const int n_remote = q.n_grad - 1;
   const int smem = STAGES * (n_remote > 0 ? n_remote : 1) * cb::kP2PTile * 16;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 3;
-  int per_sm = 0, dev = 0, n_sm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = 0;
+  const int n_sm = cb::sm_count();
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess || per_sm < 1) return 4;
   const long long n_tiles = (n / 4 + cb::kP2PTile - 1) / cb::kP2PTile;
   long long blocks = (long long)n_sm * per_sm;  // persistent: every CTA resident, tiles strided over them
@@ -438,27 +388,13 @@ extern "C" int cb_clipped_adam_p2p(float* p, float* m, float* v, long long n, co
   for (int k = 0; k < n_peer; ++k)
     CB_REQUIRE(q.peer_param[k] != nullptr && (reinterpret_cast<uintptr_t>(q.peer_param[k]) & 15) == 0, "cb_clipped_adam_p2p: bad peer pointer %d", k);
   cudaStream_t st = (cudaStream_t)stream;
-  // CB_P2P_BULK=0 selects the plain-load kernel (A/B timing); default: TMA bulk prefetch of the peers' gradients
-  const char* bulk_env = getenv("CB_P2P_BULK");
-  const bool bulk = bulk_env == nullptr || bulk_env[0] != '0';
-  if (n > 0 && bulk) {
+  if (n > 0) {  // TMA bulk prefetch of the peers' gradient tiles into a shared-memory ring
     int rc = 0;
     if (n_grad <= 2) rc = launch_p2p_bulk<2, 8>(p, m, v, n, q, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip, st);
     else if (n_grad <= 4) rc = launch_p2p_bulk<4, 8>(p, m, v, n, q, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip, st);
     else if (n_grad <= 8) rc = launch_p2p_bulk<8, 4>(p, m, v, n, q, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip, st);
     else rc = launch_p2p_bulk<16, 3>(p, m, v, n, q, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip, st);
     CB_REQUIRE(rc == 0, "cb_clipped_adam_p2p: kernel configuration failed (code %d)", rc);
-  } else if (n > 0) {
-    long long blocks = (n / 4 + 255) / 256;
-    const long long cap = 148LL * 8;  // 2 048 threads per SM, a multiple of the SM count
-    if (blocks > cap) blocks = cap;
-#define CB_P2P_LAUNCH(NG) \
-  cb::clipped_adam_p2p_kernel<NG><<<unsigned(blocks), 256, 0, st>>>(p, m, v, n, q, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip)
-    if (n_grad <= 2) CB_P2P_LAUNCH(2);
-    else if (n_grad <= 4) CB_P2P_LAUNCH(4);
-    else if (n_grad <= 8) CB_P2P_LAUNCH(8);
-    else CB_P2P_LAUNCH(16);
-#undef CB_P2P_LAUNCH
   }
   if (advance) cb::advance_step_kernel<<<1, 1, 0, st>>>(step_ptr);
   return cb::check_launch("cb_clipped_adam_p2p");
@@ -475,8 +411,8 @@ extern "C" int cb_clipped_adam_nvls(float* p, float* m, float* v, long long n, c
     CB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "cb_clipped_adam_nvls: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (n > 0) {
-    long long blocks = (n / 4 + 255) / 256;
-    const long long cap = 148LL * 6;
+    long long blocks = (n / 4 + 256 * cb::kNvlsUnroll - 1) / (256 * cb::kNvlsUnroll);
+    const long long cap = 6LL * cb::sm_count();
     if (blocks > cap) blocks = cap;
     cb::clipped_adam_nvls_kernel<<<unsigned(blocks), 256, 0, st>>>(p, m, v, n, mc_grad, mc_param, lr_table, beta1_table, table_len,
                                                                    step_ptr, beta2, eps, clip);

@@ -11,6 +11,7 @@ constexpr int kWarp = 32;
 // ---- error plumbing for the C ABI (status int + last-error string) ----------------
 void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);  // cudaGetLastError() -> status
+int sm_count();                      // SMs of the current device (cached per device)
 
 #define CB_REQUIRE(cond, ...)              \
   do {                                     \

@@ -244,29 +244,6 @@ __global__ void __launch_bounds__(kColsumCols* kColsumGroups) colsum_rows_kernel
   }
 }
 
-// Row logsumexp of a [R, ld] matrix (used by the posterior pass).
-__global__ void __launch_bounds__(256) row_lse_kernel(const float* __restrict__ in, int G, long long ld,
-                                                      float* __restrict__ lse) {
-  __shared__ float red[32];
-  const float* row = in + (long long)blockIdx.x * ld;
-  const int G4 = G >> 2;
-  float mx = -INFINITY;
-  for (int i = threadIdx.x; i < G4; i += blockDim.x) {
-    const float4 l = *reinterpret_cast<const float4*>(row + 4 * i);
-    mx = fmaxf(fmaxf(mx, fmaxf(l.x, l.y)), fmaxf(l.z, l.w));
-  }
-  for (int g = 4 * G4 + threadIdx.x; g < G; g += blockDim.x) mx = fmaxf(mx, row[g]);
-  mx = block_max(mx, red);
-  float se[1] = {0.f};
-  for (int i = threadIdx.x; i < G4; i += blockDim.x) {
-    const float4 l = *reinterpret_cast<const float4*>(row + 4 * i);
-    se[0] += expf(l.x - mx) + expf(l.y - mx) + expf(l.z - mx) + expf(l.w - mx);
-  }
-  for (int g = 4 * G4 + threadIdx.x; g < G; g += blockDim.x) se[0] += expf(row[g] - mx);
-  block_sum<float, 1>(se, red);
-  if (threadIdx.x == 0) lse[blockIdx.x] = mx + logf(se[0]);
-}
-
 }  // namespace cb
 
 extern "C" int cb_elbo_obs_fwd_bwd(const long long* indptr, const int* indices, const float* data,
@@ -296,13 +273,4 @@ extern "C" int cb_colsum_rows(const float* in, int n_rows, int n_cols, long long
   cb::colsum_rows_kernel<<<(n_cols + cb::kColsumCols - 1) / cb::kColsumCols, cb::kColsumCols * cb::kColsumGroups, 0,
                            (cudaStream_t)stream>>>(in, n_rows, n_cols, ld, out);
   return cb::check_launch("cb_colsum_rows");
-}
-
-extern "C" int cb_row_logsumexp(const float* in, int n_rows, int n_cols, long long ld, float* lse, void* stream) {
-  if (n_rows == 0) return 0;
-  CB_REQUIRE(n_rows > 0 && n_cols > 0 && ld >= n_cols && (ld & 3) == 0, "cb_row_logsumexp: bad shape [%d, %d] ld=%lld",
-             n_rows, n_cols, ld);
-  CB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0, "cb_row_logsumexp: input not 16-byte aligned");
-  cb::row_lse_kernel<<<n_rows, 256, 0, (cudaStream_t)stream>>>(in, n_cols, ld, lse);
-  return cb::check_launch("cb_row_logsumexp");
 }

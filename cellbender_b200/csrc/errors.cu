@@ -22,6 +22,18 @@ int check_launch(const char* what) {
   }
   return 0;
 }
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;  // B200
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
 }  // namespace cb
 
 extern "C" const char* cb_last_error(void) { return cb::g_last_error; }

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) nbpc_elementwise_kernel(
 
 static int grid_for(long long total) {
   long long blocks = (total + 255) / 256;
-  const long long cap = 148LL * 8;
+  const long long cap = 8LL * cb::sm_count();
   return int(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 

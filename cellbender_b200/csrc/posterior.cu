@@ -5,9 +5,15 @@
 //   _log_prob_noise_count_tensor  :784-859   dense [128, G, 20] fp32 temporaries (343 MB each), x 20 samples
 //   noise_log_pdf                 :669-735   logsumexp normalisation + running log-mean over samples
 //   _get_cell_noise_count_posterior_coo :528-576  exp / two masked writes / nonzero / CPU index translation
-//   sparse_utils.dense_to_sparse_op_torch   sparse_utils.py:10-33
-// The reference evaluates every (cell, gene, c) and then throws away x == 0 (92-95 % of the work); here one
-// thread owns one stored count and walks the S samples with the window pmf in registers.
+//   sparse_utils.dense_to_sparse_op_torch   sparse_utils.py:10-33;  IndexConverter.get_m_indices  posterior.py:1554-1575
+// The reference evaluates every (cell, gene, c) and then throws away x == 0 (92-95 % of the work).
+//
+// Data layout (r02): the decoder output of a chunk of cells is produced TRANSPOSED and cell-major,
+//   logits_t[g, b * S + s] = W_dec[g, :] . h[b * S + s, :]            (cb_gemm_tf32 with A = W_dec, B = h; no bias)
+// so that the S latent samples of one (cell, gene) are S consecutive floats (80 bytes at S = 20: 3 sectors instead of
+// the 20 scattered sectors of a sample-major [S * cells, G] layout).  Four lanes share one stored count: lane j walks
+// samples j, j + 4, ... (each load instruction of the quad reads 16 contiguous bytes), the quad's partial window pmfs are
+// combined with two shuffle steps.  The softmax denominators come from cb_col_logsumexp over the same matrix.
 //
 // Quirks reproduced on purpose:
 //   * the window size n = min(n_counts_max, max count of the reference minibatch) is passed per cell;
@@ -18,55 +24,87 @@
 
 namespace cb {
 
-constexpr int kPostThreads = 128;
+constexpr int kPostThreads = 256;  // 64 stored counts per CTA
 
-// acc_out [E, NMAX] : log of the sample-mean pmf;  low_out [E];  keep_cnt [E] = #(c : logp >= thresh & prob != 0)
+// logp_out [E, NMAX] : log of the sample-mean pmf;  low_out [E];  keep_cnt [E] = #(c : logp >= thresh);
+// entry_m [E] = barcode_all[cell] * total_n_genes + gene_all[g].  E = entry_start[n_cells] stored counts of the chunk,
+// in (cell, gene) order.
 template <int NMAX>
 __global__ void __launch_bounds__(kPostThreads) posterior_window_kernel(
     const long long* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ data,
-    const long long* __restrict__ cell_rows, int n_cells, int n_samples, const float* __restrict__ logits,
-    long long ldl, const float* __restrict__ lse, const float* __restrict__ chi_amb, const float* __restrict__ chi_bar,
-    const float* __restrict__ a_mu, const float* __restrict__ c_a, const float* __restrict__ c_b,
-    const float* __restrict__ alpha, const int* __restrict__ n_window, const long long* __restrict__ entry_start,
-    float log_thresh, float lambda_multiplier, float* __restrict__ logp_out, int* __restrict__ low_out,
-    int* __restrict__ keep_cnt) {
-  const int b = blockIdx.x;
-  const long long r = cell_rows[b];
-  const long long s = indptr[r], e = indptr[r + 1];
-  const long long out0 = entry_start[b];
-  const int n = n_window[b] < NMAX ? n_window[b] : NMAX;
-  const float inv_s = 1.0f / float(n_samples);
-  for (long long j = s + threadIdx.x; j < e; j += blockDim.x) {
-    const long long eo = out0 + (j - s);
-    const float x = data[j];
-    int low = 0, cnt = 0;
-    float acc[NMAX];
+    const long long* __restrict__ cell_rows, int n_cells, int n_samples, const float* __restrict__ logits_t,
+    long long ldt, const float* __restrict__ dec_bias, const float* __restrict__ lse, const float* __restrict__ chi_amb,
+    const float* __restrict__ chi_bar, const float* __restrict__ a_mu, const float* __restrict__ c_a,
+    const float* __restrict__ c_b, const float* __restrict__ alpha, const int* __restrict__ n_window,
+    const long long* __restrict__ entry_start, const long long* __restrict__ barcode_all,
+    const long long* __restrict__ gene_all, long long total_n_genes, float log_thresh, float lambda_multiplier,
+    float* __restrict__ logp_out, int* __restrict__ low_out, int* __restrict__ keep_cnt, long long* __restrict__ entry_m) {
+  const long long n_entries = entry_start[n_cells];
+  const long long e = blockIdx.x * (long long)(kPostThreads / 4) + (threadIdx.x >> 2);
+  const int sub = threadIdx.x & 3;
+  const bool active = e < n_entries;
+  // cell of this entry: last b with entry_start[b] <= e
+  int b = 0;
+  if (active) {
+    int lo = 0, hi = n_cells;  // invariant: entry_start[lo] <= e < entry_start[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (entry_start[mid] <= e) lo = mid;
+      else hi = mid;
+    }
+    b = lo;
+  }
+  float acc[NMAX];
 #pragma unroll
-    for (int k = 0; k < NMAX; ++k) acc[k] = 0.f;
+  for (int k = 0; k < NMAX; ++k) acc[k] = 0.f;
+  int low = 0, n = 0, g = 0;
+  float x = 0.f;
+  if (active) {
+    const long long j = indptr[cell_rows[b]] + (e - entry_start[b]);
+    x = data[j];
+    g = indices[j];
+    n = n_window[b] < NMAX ? n_window[b] : NMAX;
     if (x > 0.f && n > 0) {
-      const int g = indices[j];
-      const float ca = chi_amb[g], cb_ = chi_bar[g];
-      for (int smp = 0; smp < n_samples; ++smp) {
-        const long long row = (long long)smp * n_cells + b;
-        const float chi = expf(logits[row * ldl + g] - lse[row]);
+      const float ca = chi_amb[g], cb_ = chi_bar[g], bg = dec_bias ? dec_bias[g] : 0.f;
+      const long long base = (long long)b * n_samples;
+      const float* lrow = logits_t + (long long)g * ldt + base;
+      for (int smp = sub; smp < n_samples; smp += 4) {
+        const float chi = expf(lrow[smp] + bg - lse[base + smp]);
         // posterior.py:708-710 safeguards
-        const float mu = a_mu[row] * chi + 1e-30f;
-        const float lam = (c_a[row] * ca + c_b[row] * cb_) * lambda_multiplier + 1e-30f;
+        const float mu = a_mu[base + smp] * chi + 1e-30f;
+        const float lam = (c_a[base + smp] * ca + c_b[base + smp] * cb_) * lambda_multiplier + 1e-30f;
         const float al = alpha[smp] + 1e-30f;
-        float p[NMAX];
-        low = noise_window_pmf<NMAX>(x, mu, lam, al, n, p);
-#pragma unroll
-        for (int k = 0; k < NMAX; ++k) acc[k] += p[k];
+        const int lw = noise_window_pmf_accumulate<NMAX>(x, mu, lam, al, n, acc);
+        if (smp == n_samples - 1) low = lw;
       }
     }
+  }
+  // combine the quad (all 32 lanes take part in the shuffles)
+#pragma unroll
+  for (int k = 0; k < NMAX; ++k) {
+    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+    acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
+  }
+  low += __shfl_xor_sync(0xffffffffu, low, 1);  // exactly one lane of the quad holds the last sample's low
+  low += __shfl_xor_sync(0xffffffffu, low, 2);
+  const float inv_s = 1.0f / float(n_samples);
+  int cnt = 0;
+  if (active) {
 #pragma unroll
     for (int k = 0; k < NMAX; ++k) {
-      const float lp = (acc[k] > 0.f) ? logf(acc[k] * inv_s) : -INFINITY;
-      logp_out[eo * NMAX + k] = lp;
-      cnt += (k < n && lp >= log_thresh) ? 1 : 0;
+      if ((k & 3) == sub) {  // lane j of the quad finishes columns j, j + 4, ...: 16 contiguous bytes per store instruction
+        const float lp = (acc[k] > 0.f) ? logf(acc[k] * inv_s) : -INFINITY;
+        logp_out[e * NMAX + k] = lp;
+        cnt += (k < n && lp >= log_thresh) ? 1 : 0;
+      }
     }
-    low_out[eo] = low;
-    keep_cnt[eo] = cnt;
+  }
+  cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+  cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+  if (active && sub == 0) {
+    low_out[e] = low;
+    keep_cnt[e] = cnt;
+    entry_m[e] = barcode_all[b] * total_n_genes + gene_all[g];
   }
 }
 
@@ -99,34 +137,83 @@ __global__ void __launch_bounds__(256) posterior_compact_kernel(
   }
 }
 
-// m index of every stored count of the selected cells: m = barcode_all[cell] * G_all + gene_all[g]  (IndexConverter)
-__global__ void __launch_bounds__(kPostThreads) posterior_entry_index_kernel(
-    const long long* __restrict__ indptr, const int* __restrict__ indices, const long long* __restrict__ cell_rows,
-    const long long* __restrict__ barcode_all, const long long* __restrict__ gene_all, long long total_n_genes,
-    const long long* __restrict__ entry_start, long long* __restrict__ entry_m) {
-  const int b = blockIdx.x;
-  const long long r = cell_rows[b];
-  const long long s = indptr[r], e = indptr[r + 1];
-  const long long base = barcode_all[b] * total_n_genes;
-  for (long long j = s + threadIdx.x; j < e; j += blockDim.x) entry_m[entry_start[b] + (j - s)] = base + gene_all[indices[j]];
+// has_off[i] = keep_cnt[i] > 0 && low[i] != 0  (entries that contribute an (m, offset) pair)
+__global__ void __launch_bounds__(256) posterior_offset_flags_kernel(long long n, const int* __restrict__ keep_cnt,
+                                                                     const int* __restrict__ low, int* __restrict__ flag) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (keep_cnt[i] > 0 && low[i] != 0) ? 1 : 0;
+}
+
+// ---- column logsumexp of a [R, ld] matrix with an optional per-row additive term: out[c] = log sum_r exp(in[r, c] + add[r]) ----
+// pass 1: a CTA owns 128 columns x one of `n_split` row ranges, online (max, sum) per thread; pass 2 merges the ranges.
+constexpr int kColLseThreads = 128;
+__global__ void __launch_bounds__(kColLseThreads) col_lse_partial_kernel(const float* __restrict__ in, int R, int C, long long ld,
+                                                                         const float* __restrict__ add, int rows_per_split,
+                                                                         float* __restrict__ part_max, float* __restrict__ part_sum) {
+  const int c = blockIdx.x * kColLseThreads + threadIdx.x;
+  if (c >= C) return;
+  const int r0 = blockIdx.y * rows_per_split, r1 = min(R, r0 + rows_per_split);
+  float mx = -INFINITY, sm = 0.f;
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {  // four independent loads in flight per thread
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = in[(long long)(r + u) * ld + c] + (add ? add[r + u] : 0.f);
+    const float m4 = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+    if (m4 > mx) {
+      sm *= expf(mx - m4);  // exp(-inf) = 0 on the first group
+      mx = m4;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sm += expf(v[u] - mx);
+  }
+  for (; r < r1; ++r) {
+    const float v = in[(long long)r * ld + c] + (add ? add[r] : 0.f);
+    if (v > mx) {
+      sm *= expf(mx - v);
+      mx = v;
+    }
+    sm += expf(v - mx);
+  }
+  part_max[(long long)blockIdx.y * C + c] = mx;
+  part_sum[(long long)blockIdx.y * C + c] = sm;
+}
+
+__global__ void __launch_bounds__(256) col_lse_final_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
+                                                            int n_split, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mx = -INFINITY;
+  for (int s = 0; s < n_split; ++s) mx = fmaxf(mx, part_max[(long long)s * C + c]);
+  float sm = 0.f;
+  for (int s = 0; s < n_split; ++s) {
+    const float pm = part_max[(long long)s * C + c];
+    if (pm > -INFINITY) sm += part_sum[(long long)s * C + c] * expf(pm - mx);
+  }
+  out[c] = mx + logf(sm);
 }
 
 }  // namespace cb
 
 extern "C" int cb_posterior_noise_window(const long long* indptr, const int* indices, const float* data,
                                          const long long* cell_rows, int n_cells, int n_genes, int n_samples,
-                                         const float* logits, long long ldl, const float* lse, const float* chi_ambient,
-                                         const float* chi_bar, const float* a_mu, const float* c_a, const float* c_b,
-                                         const float* alpha, const int* n_window, const long long* entry_start,
-                                         int n_counts_max, float log_thresh, float lambda_multiplier, float* logp_out,
-                                         int* low_out, int* keep_cnt, void* stream) {
-  if (n_cells == 0) return 0;
-  CB_REQUIRE(n_cells > 0 && n_genes > 0 && n_samples > 0, "cb_posterior_noise_window: bad shape");
+                                         const float* logits_t, long long ldt, const float* dec_bias, const float* lse,
+                                         const float* chi_ambient, const float* chi_bar, const float* a_mu, const float* c_a,
+                                         const float* c_b, const float* alpha, const int* n_window,
+                                         const long long* entry_start, long long n_entries, const long long* barcode_all,
+                                         const long long* gene_all, long long total_n_genes, int n_counts_max,
+                                         float log_thresh, float lambda_multiplier, float* logp_out, int* low_out,
+                                         int* keep_cnt, long long* entry_m, void* stream) {
+  if (n_cells == 0 || n_entries == 0) return 0;
+  CB_REQUIRE(n_cells > 0 && n_genes > 0 && n_samples > 0 && n_entries > 0, "cb_posterior_noise_window: bad shape");
+  CB_REQUIRE(ldt >= (long long)n_cells * n_samples, "cb_posterior_noise_window: ldt=%lld < n_cells * n_samples", ldt);
   CB_REQUIRE(n_counts_max > 0 && n_counts_max <= 64, "cb_posterior_noise_window: n_counts_max=%d not in [1, 64]", n_counts_max);
-#define CB_LAUNCH_POST(NMAX)                                                                                         \
-  cb::posterior_window_kernel<NMAX><<<n_cells, cb::kPostThreads, 0, (cudaStream_t)stream>>>(                          \
-      indptr, indices, data, cell_rows, n_cells, n_samples, logits, ldl, lse, chi_ambient, chi_bar, a_mu, c_a, c_b, \
-      alpha, n_window, entry_start, log_thresh, lambda_multiplier, logp_out, low_out, keep_cnt)
+  const unsigned grid = unsigned((n_entries + cb::kPostThreads / 4 - 1) / (cb::kPostThreads / 4));
+#define CB_LAUNCH_POST(NMAX)                                                                                          \
+  cb::posterior_window_kernel<NMAX><<<grid, cb::kPostThreads, 0, (cudaStream_t)stream>>>(                              \
+      indptr, indices, data, cell_rows, n_cells, n_samples, logits_t, ldt, dec_bias, lse, chi_ambient, chi_bar, a_mu, \
+      c_a, c_b, alpha, n_window, entry_start, barcode_all, gene_all, total_n_genes, log_thresh, lambda_multiplier,    \
+      logp_out, low_out, keep_cnt, entry_m)
   if (n_counts_max <= 20) CB_LAUNCH_POST(20);
   else if (n_counts_max <= 32) CB_LAUNCH_POST(32);
   else CB_LAUNCH_POST(64);
@@ -137,14 +224,11 @@ extern "C" int cb_posterior_noise_window(const long long* indptr, const int* ind
 // row stride of logp_out for a given n_counts_max (20, 32 or 64)
 extern "C" int cb_posterior_window_stride(int n_counts_max) { return n_counts_max <= 20 ? 20 : (n_counts_max <= 32 ? 32 : 64); }
 
-extern "C" int cb_posterior_entry_index(const long long* indptr, const int* indices, const long long* cell_rows,
-                                        int n_cells, const long long* barcode_all, const long long* gene_all,
-                                        long long total_n_genes, const long long* entry_start, long long* entry_m,
-                                        void* stream) {
-  if (n_cells == 0) return 0;
-  cb::posterior_entry_index_kernel<<<n_cells, cb::kPostThreads, 0, (cudaStream_t)stream>>>(
-      indptr, indices, cell_rows, barcode_all, gene_all, total_n_genes, entry_start, entry_m);
-  return cb::check_launch("cb_posterior_entry_index");
+extern "C" int cb_posterior_offset_flags(long long n_entries, const int* keep_cnt, const int* low, int* flag, void* stream) {
+  if (n_entries == 0) return 0;
+  cb::posterior_offset_flags_kernel<<<unsigned((n_entries + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_entries, keep_cnt, low,
+                                                                                                      flag);
+  return cb::check_launch("cb_posterior_offset_flags");
 }
 
 extern "C" int cb_posterior_compact(long long n_entries, int n_counts_max, const long long* entry_m, const float* logp,
@@ -163,4 +247,26 @@ extern "C" int cb_posterior_compact(long long n_entries, int n_counts_max, const
   else CB_LAUNCH_COMPACT(64);
 #undef CB_LAUNCH_COMPACT
   return cb::check_launch("cb_posterior_compact");
+}
+
+// scratch floats cb_col_logsumexp needs for an [n_rows, n_cols] matrix
+extern "C" long long cb_col_logsumexp_scratch_elems(int n_rows, int n_cols) {
+  const int n_split = n_rows >= 64 * 64 ? 64 : (n_rows + 63) / 64;
+  return 2LL * (n_split < 1 ? 1 : n_split) * n_cols;
+}
+
+extern "C" int cb_col_logsumexp(const float* in, int n_rows, int n_cols, long long ld, const float* row_add, float* scratch,
+                                float* out, void* stream) {
+  if (n_cols == 0) return 0;
+  CB_REQUIRE(n_rows > 0 && n_cols > 0 && ld >= n_cols, "cb_col_logsumexp: bad shape [%d, %d] ld=%lld", n_rows, n_cols, ld);
+  int n_split = n_rows >= 64 * 64 ? 64 : (n_rows + 63) / 64;
+  if (n_split < 1) n_split = 1;
+  const int rows_per_split = (n_rows + n_split - 1) / n_split;
+  float* part_max = scratch;
+  float* part_sum = scratch + (long long)n_split * n_cols;
+  dim3 grid((n_cols + cb::kColLseThreads - 1) / cb::kColLseThreads, n_split);
+  cb::col_lse_partial_kernel<<<grid, cb::kColLseThreads, 0, (cudaStream_t)stream>>>(in, n_rows, n_cols, ld, row_add, rows_per_split,
+                                                                                  part_max, part_sum);
+  cb::col_lse_final_kernel<<<(n_cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(part_max, part_sum, n_split, n_cols, out);
+  return cb::check_launch("cb_col_logsumexp");
 }

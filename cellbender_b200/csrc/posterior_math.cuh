@@ -77,4 +77,52 @@ CB_HD int noise_window_pmf(float x, float mu, float lam, float alpha, int n, flo
   return low;
 }
 
+// The same pmf accumulated in place: acc[j] += P(noise = low + j).  Arithmetic identical to noise_window_pmf (same
+// operations in the same order); only the temporaries are shared (one NMAX-array instead of two) so that the sample
+// loop of the posterior kernel keeps acc[] + t[] = 2 NMAX registers live.  Returns low.
+template <int NMAX>
+CB_HD int noise_window_pmf_accumulate(float x, float mu, float lam, float alpha, int n, float (&acc)[NMAX]) {
+  const int low = noise_window_low(x, lam, n);
+  const float log_lam_over_s = logf(lam) + log1pf(alpha / mu);
+  float t[NMAX];
+  float tmax = 0.0f;
+  t[0] = 0.0f;
+  bool dead = false;
+#pragma unroll
+  for (int j = 1; j < NMAX; ++j) {
+    if (j < n) {
+      const float c = float(low + j - 1);
+      const float k = x - c;
+      if (dead || k <= 0.0f) {
+        dead = true;
+        t[j] = -INFINITY;
+      } else {
+        t[j] = t[j - 1] + (log_lam_over_s + logf(k / ((c + 1.0f) * (alpha + k - 1.0f))));
+        tmax = fmaxf(tmax, t[j]);
+      }
+    } else {
+      t[j] = -INFINITY;
+    }
+  }
+  if (isinf(tmax)) {
+    int last = 0;
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j)
+      if (j < n && float(low + j) <= x) last = j;
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) acc[j] += (j == last) ? 1.0f : 0.0f;
+    return low;
+  }
+  float z = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    t[j] = (j < n) ? expf(t[j] - tmax) : 0.0f;
+    z += t[j];
+  }
+  const float inv = 1.0f / z;
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) acc[j] += t[j] * inv;
+  return low;
+}
+
 }  // namespace cb

@@ -105,6 +105,40 @@ __global__ void __launch_bounds__(32 * kHeadGroups) head_backward_kernel(const f
   }
 }
 
+
+// Weight gradient of the few hand-made feature columns of Linear(cat(feat, x)) (vae/encoder.py:283-298):
+//   dw[h, f] = sum_b dy[b, h] * feat[b, f]     h < H, f < F <= 8, written into the first F columns of a [H, ldw] block.
+// A CTA owns 32 output rows h (coalesced dy reads), its 8 warps split the minibatch rows; fixed-order reduction.
+constexpr int kFeatDwGroups = 8;
+__global__ void __launch_bounds__(32 * kFeatDwGroups) feat_dw_kernel(const float* __restrict__ dy, long long ldy,
+                                                                      const float* __restrict__ feat, int F, int B, int H,
+                                                                      float* __restrict__ dw, long long ldw) {
+  __shared__ float s[kFeatDwGroups][8][33];
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int h = blockIdx.x * 32 + c;
+  float acc[8];
+#pragma unroll
+  for (int f = 0; f < 8; ++f) acc[f] = 0.f;
+  if (h < H) {
+#pragma unroll 4
+    for (int b = g; b < B; b += kFeatDwGroups) {
+      const float d = dy[b * ldy + h];
+#pragma unroll
+      for (int f = 0; f < 8; ++f)
+        if (f < F) acc[f] = fmaf(d, feat[b * F + f], acc[f]);
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < 8; ++f) s[g][f][c] = acc[f];
+  __syncthreads();
+  if (h < H && g < F) {  // warp g finishes feature column g
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < kFeatDwGroups; ++i) t += s[i][g][c];
+    dw[h * ldw + g] = t;
+  }
+}
+
 // loss = sum_b sum_k w[b, k] L[b, k],  neg_loss = -loss   (L = sums[:, 0:3]); one CTA, fp64 accumulation
 __global__ void __launch_bounds__(256) obs_loss_kernel(const float* __restrict__ sums, int ld_sums, const float* __restrict__ w, int B,
                                                        float* __restrict__ loss, float* __restrict__ neg_loss) {
@@ -184,4 +218,13 @@ extern "C" int cb_obs_small_grads(const float* sums, int ld_sums, const float* w
   CB_REQUIRE(n_rows > 0 && ld_sums >= 12, "cb_obs_small_grads: bad shape");
   cb::obs_small_grads_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums, ld_sums, w, g_up, n_rows, d_coef, d_alpha, d_w);
   return cb::check_launch("cb_obs_small_grads");
+}
+
+extern "C" int cb_feat_dw(const float* dy, long long ldy, const float* feat, int n_feat, int n_rows, int n_out, float* dw,
+                          long long ldw, void* stream) {
+  CB_REQUIRE(n_rows > 0 && n_out > 0 && n_feat > 0 && n_feat <= 8, "cb_feat_dw: bad shape [%d, %d] x %d features", n_rows, n_out,
+             n_feat);
+  cb::feat_dw_kernel<<<(n_out + 31) / 32, 32 * cb::kFeatDwGroups, 0, (cudaStream_t)stream>>>(dy, ldy, feat, n_feat, n_rows, n_out, dw,
+                                                                                           ldw);
+  return cb::check_launch("cb_feat_dw");
 }

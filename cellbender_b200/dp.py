@@ -63,7 +63,6 @@ def attach(svi, world_size: int):
     torch.cuda.manual_seed(1234 + 104729 * rank)
     svi.after_backward = lambda opt: dist.all_reduce(opt.flat_g, op=dist.ReduceOp.SUM)
     if getattr(getattr(svi.optim, "flat_g", None), "is_cuda", False):
-        svi.optim.fuse_weight_updates = False  # the gradients are needed for the exchange
         # measured on 2 x B200 (r01, ms/step): 1 piece 2.04, 2 pieces 2.10, 4 pieces 2.14 -- the Adam sweep is HBM-bound and
         # the NCCL kernels compete for the same HBM, so pipelining them buys nothing; one all-reduce is the default
         n_chunks = int(os.environ.get("CB_DP_CHUNKS", "1"))

@@ -2,37 +2,29 @@
 layer; reference vae/encoder.py:97-105,211,220 and vae/decoder.py:41-47), their backward, and the gene-wise
 BatchNorm + row dropout in front of them (vae/encoder.py:239,279).
 
-``BACKEND``:
-  'tcgen05'  csrc/gemm_tf32.cu -- hand-written TMA-fed tcgen05.mma kind::tf32 with TMEM accumulators (default on
-             the training / posterior path).  TF32 multiply (10-bit mantissa, truncation), fp32 accumulation.
-             Stated tolerance vs an fp32/fp64 product: 2e-3 of the output scale per element (tests/test_gemm_gpu.py);
-             on the ELBO: <= 2e-3 relative (tests/test_step_gpu.py::test_elbo_tf32_backend_tolerance).
-  'cublas'   torch.matmul in full fp32 (library SIMT SGEMM) -- the reference's arithmetic; used by the 1e-5 parity
-             tests and as the "library baseline" in profiles/.
+Every product goes through csrc/gemm_tf32.cu -- hand-written TMA-fed tcgen05.mma kind::tf32 with TMEM accumulators
+and a TMA-store epilogue.  TF32 multiply (10-bit mantissa, truncation), fp32 accumulation.  Stated tolerance vs an
+fp32/fp64 product: 2e-3 of the output scale per element (tests/test_gemm_gpu.py); on the ELBO: <= 2e-3 relative
+(tests/test_step_gpu.py::test_elbo_tf32_tolerance); end to end: cell calls and removed counts within 1 % of the
+reference-style fp32 pipeline (tests/test_e2e_gpu.py).  There is no other back-end: operands that TMA cannot address
+(unaligned base, row pitch not a multiple of 16 bytes) are an error, not a reason to fall back to a library GEMM.  The
+parity tests that need full-fp32 products substitute ``ops.gemm_tf32`` from inside tests/ (tests/conftest.py).
 Weight gradients are written by the GEMM epilogue straight into the optimizer's flat gradient buffer (the
 nn.Parameter carries its gradient view as ``_cb_grad_view``), so no extra copy or accumulation pass exists.
 """
 from typing import Optional
 
 import torch
-import torch.nn.functional as F
 
 from . import ops
 from ._cabi import current_stream, lib, ptr
 
-BACKEND = "tcgen05"
-# optimizer whose update is fused into the weight-gradient GEMM epilogues during the current backward pass (set by
-# train.SVI around loss.backward(); None = gradients are written to the flat gradient buffer as usual)
+# optimizer whose piecewise sweep is issued behind the weight-gradient GEMMs during the current backward pass (set by
+# train.SVI around loss.backward(); None = gradients are only written to the flat gradient buffer)
 FUSED_OPT = None
-# only matrices with at least this many elements take the fused path: the epilogue needs many CTAs to stream the
-# optimizer state at HBM speed (a 512 x 512 layer has 8 tiles; its fused update is slower than the separate sweep)
-FUSED_MIN_NUMEL = 1 << 22  # = optim.BIG_BLOCK_NUMEL: the blocks the optimizer lays out first
-
-
-def set_backend(name: str):
-    global BACKEND
-    assert name in ("cublas", "tcgen05")
-    BACKEND = name
+# only matrices with at least this many elements are swept early (= optim.BIG_BLOCK_NUMEL: the blocks the optimizer lays
+# out first)
+FUSED_MIN_NUMEL = 1 << 22
 
 
 def _grad_target(weight: torch.Tensor):
@@ -45,14 +37,6 @@ def _grad_target(weight: torch.Tensor):
         return t, t
     weight._cb_grad_direct = True
     return gv, None
-
-
-def fused_update_applies(w: torch.Tensor) -> bool:
-    opt = FUSED_OPT
-    return (opt is not None and getattr(opt, "fuse_weight_updates", False) and BACKEND == "tcgen05"
-            and getattr(w, "_cb_block", None) is not None
-            and getattr(w, "_cb_grad_view", None) is not None and w.requires_grad and w.numel() >= FUSED_MIN_NUMEL
-            and w.shape[0] > 128)
 
 
 _PENDING_JOINS = []
@@ -79,9 +63,32 @@ def early_update_applies(w: torch.Tensor) -> bool:
             and getattr(w, "_cb_grad_view", None) is not None and w.requires_grad and w.numel() >= FUSED_MIN_NUMEL)
 
 
-def _tma_ok(t: torch.Tensor) -> bool:
-    return (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0
-            and t.data_ptr() % 16 == 0)
+def _require_tma(t: torch.Tensor, what: str, col_offset: int = 0):
+    """The tensor-core path is the only path: fail loudly when an operand cannot be addressed by TMA."""
+    ok = (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0
+          and (t.data_ptr() + 4 * col_offset) % 16 == 0)
+    if not ok:
+        raise RuntimeError(
+            f"cellbender_b200.gemm: {what} (shape {tuple(t.shape)}, strides {tuple(t.stride())}, dtype {t.dtype}, device "
+            f"{t.device}) is not TMA-addressable: needs a CUDA fp32 matrix with unit column stride, a row pitch that is a "
+            f"multiple of 4 floats and a 16-byte aligned base.  Large weights get such a layout from "
+            f"gemm.pad_big_weights(module) / optim.FlatClippedAdam; there is no library-GEMM fallback.")
+
+
+def pad_big_weights(module: torch.nn.Module, min_numel: int = 1 << 16):
+    """Re-home every large 2-D weight of ``module`` into storage whose row pitch is a multiple of 4 floats (G = 33 538
+    and G + 4 are not), so that TMA can address it; names, shapes and values are unchanged (the nn.Parameter becomes a
+    [rows, cols] view of a [rows, ld] block whose padding columns stay zero).  The optimizer does the same when it builds
+    its flat buffer (optim.FlatClippedAdam); this covers models that never see an optimizer (posterior from a checkpoint)."""
+    with torch.no_grad():
+        for p in module.parameters():
+            if p.dim() == 2 and p.numel() >= min_numel and (p.stride(1) != 1 or p.stride(0) % 4 != 0 or p.data_ptr() % 16 != 0):
+                rows, cols = p.shape
+                ld = (cols + 3) // 4 * 4
+                block = torch.zeros((rows, ld), dtype=p.dtype, device=p.device)
+                block[:, :cols].copy_(p.data)
+                p.data = block[:, :cols]
+    return module
 
 
 class _MultiLinearBig(torch.autograd.Function):
@@ -97,14 +104,14 @@ class _MultiLinearBig(torch.autograd.Function):
         B = x.shape[0]
         ys = []
         for feat, w, b in zip(feats, weights, biases):
-            if feat is not None and col_offset % 4 == 0 and feat.is_contiguous() and feat.shape[1] == col_offset:
+            if feat is not None:
                 # Linear(cat(feat, x)): the few feature columns ride along as a second operand pair (one extra k-block)
+                if not (col_offset % 4 == 0 and feat.is_contiguous() and feat.shape[1] == col_offset):
+                    raise RuntimeError("multi_linear_big: the feature block must be contiguous [B, col_offset] with col_offset % 4 == 0")
                 y = ops.gemm_tf32(x, w[:, col_offset:col_offset + n_in], B, w.shape[0], n_in, bias=b,
                                   a2=feat, b2=w[:, :col_offset], K2=col_offset)
             else:
                 y = ops.gemm_tf32(x, w[:, col_offset:col_offset + n_in], B, w.shape[0], n_in, bias=b)
-                if feat is not None:
-                    y = torch.addmm(y, feat, w[:, :col_offset].t())
             ys.append(y)
         ctx.save_for_backward(x, *[t for t in feats if t is not None], *weights)
         ctx.meta = (len(weights), n_in, col_offset, [f is not None for f in feats], [b is not None for b in biases])
@@ -139,27 +146,22 @@ class _MultiLinearBig(torch.autograd.Function):
                 dw_t, db_t = targets[i]
                 if dw_t is not None:
                     # dW[H, n_in] = dy^T[H, B] . x[B, n_in]: both operands stored with the reduction dim (B) as rows
-                    if fused[i]:
-                        FUSED_OPT.fused_dw(weights_p[i], dy, x, H, n_in, B, off)  # ... and W -= Adam(dW) in the epilogue
-                    else:
-                        ops.gemm_tf32(dy, x, H, n_in, B, a_mn=True, b_mn=True, out=dw_t[0][:, off:off + n_in], split_k=1)
-                    if off:
-                        dw_t[0][:, :off] = dy.t() @ feat
+                    ops.gemm_tf32(dy, x, H, n_in, B, a_mn=True, b_mn=True, out=dw_t[0][:, off:off + n_in], split_k=1)
+                    if off:  # the few feature columns in front of the gene block
+                        ops.feat_dw(dy, feat, dw_t[0])
                 if db_t is not None:
                     ops.colsum_rows(dy, H, out=db_t[0])
 
         # the weight-gradient products and the input-gradient product are independent: fork the former onto a side
-        # stream (parallel branches of the captured step graph), join before returning -- unless a weight is updated
-        # inside its gradient GEMM: then the input-gradient product (a reader of the OLD weights) must come first
-        fused = [targets[i][0] is not None and fused_update_applies(weights_p[i]) for i in range(n)]
-        fork = need_dx and not any(fused) and any(t[0] is not None or t[1] is not None for t in targets)
+        # stream (parallel branches of the captured step graph), join before returning
+        fork = need_dx and any(t[0] is not None or t[1] is not None for t in targets)
         main = torch.cuda.current_stream()
         if fork:
             side = ops.side_stream(x.device, 0)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 parameter_gradients()
-        elif not any(fused):
+        else:
             parameter_gradients()
         if need_dx:
             if n == 2:
@@ -172,12 +174,10 @@ class _MultiLinearBig(torch.autograd.Function):
                     w = weights[i]
                     ops.gemm_tf32(dys[i], w[:, off:off + n_in], B, n_in, w.shape[0], b_mn=True, out=dx, accumulate=i > 0,
                                   split_k=1)
-        if any(fused):
-            parameter_gradients()  # after the readers of the old weights
         # piecewise optimizer sweep: the large weight blocks of this node are complete -> update them now, on the stream
         # that produced their gradients, overlapping the rest of backward (the sweep is HBM-bound, backward is not);
         # it must follow every reader of the OLD weights, i.e. the input-gradient product issued above
-        early = [i for i in range(n) if targets[i][0] is not None and early_update_applies(weights_p[i]) and not fused[i]
+        early = [i for i in range(n) if targets[i][0] is not None and early_update_applies(weights_p[i])
                  and targets[i][0][1] is None]
         if early:
             upd_stream = side if fork else main
@@ -190,10 +190,9 @@ class _MultiLinearBig(torch.autograd.Function):
                     FUSED_OPT.early_block_update(weights_p[i])
         grads = []
         for i in range(n):
-            dfeat = None
             if feats[i] is not None and ctx.needs_input_grad[3 + 3 * i]:
-                dfeat = dys[i] @ weights[i][:, :off]
-            grads += [dfeat, targets[i][0][1] if targets[i][0] is not None else None,
+                raise RuntimeError("multi_linear_big: the hand-made feature block is data (vae/encoder.py:250-287); it has no gradient")
+            grads += [None, targets[i][0][1] if targets[i][0] is not None else None,
                       targets[i][1][1] if targets[i][1] is not None else None]
         if fork:
             # join now only if autograd receives a tensor produced on the side stream; otherwise at the end of backward
@@ -211,27 +210,15 @@ def multi_linear_big(x: torch.Tensor, layers, n_in: int, col_offset: int = 0, bi
     x may carry padding columns beyond n_in (16-byte-aligned rows from the gather / BN kernels).
     ``bias_grad_elsewhere``: the layer feeds ``bn_act`` which also produces the Linear bias gradient (the column sums
     of its input gradient), so no separate reduction over dy is launched here."""
-    ws = [lin.weight for lin, _ in layers]
-    use_tc = (BACKEND == "tcgen05" and _tma_ok(x) and all(_tma_ok(w) for w in ws)
-              and all((w.data_ptr() + 4 * col_offset) % 16 == 0 for w in ws))
-    if use_tc:
-        args = []
-        for lin, feat in layers:
-            bias = lin.bias
-            if bias is not None and bias_grad_elsewhere and torch.is_grad_enabled():
-                bias = bias.detach()
-            args += [feat, lin.weight, bias]
-        return _MultiLinearBig.apply(x, n_in, col_offset, *args)
-    outs = []
+    _require_tma(x, "the input activations")
+    args = []
     for lin, feat in layers:
+        _require_tma(lin.weight, "an nn.Linear weight", col_offset)
         bias = lin.bias
         if bias is not None and bias_grad_elsewhere and torch.is_grad_enabled():
             bias = bias.detach()
-        y = F.linear(x[:, :n_in], lin.weight[:, col_offset:col_offset + n_in], bias)
-        if feat is not None:
-            y = y + feat @ lin.weight[:, :col_offset].t()
-        outs.append(y)
-    return tuple(outs)
+        args += [feat, lin.weight, bias]
+    return _MultiLinearBig.apply(x, n_in, col_offset, *args)
 
 
 def linear_big(x: torch.Tensor, lin: torch.nn.Linear, n_in: int, col_offset: int = 0, feat: Optional[torch.Tensor] = None,
@@ -270,13 +257,12 @@ class _BN0Dropout(torch.autograd.Function):
 
 def bn0_dropout(x: torch.Tensor, bn: torch.nn.BatchNorm1d, keep: Optional[torch.Tensor], training: bool, n_genes: int):
     """dropout(bn(x[:, :n_genes])) as a [B, n_genes] view of a 16-byte-row buffer (GEMM/TMA friendly)."""
-    if x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1:
-        if training and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
-        return _BN0Dropout.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, keep if training else None, training,
-                                 bn.momentum if bn.momentum is not None else 0.1, bn.eps, n_genes)
-    y = bn(x[:, :n_genes])
-    return y * keep.unsqueeze(-1) if (training and keep is not None) else y
+    if not (x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1):
+        raise RuntimeError("cellbender_b200 ops require fp32 CUDA tensors with unit column stride (no CPU fallback)")
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return _BN0Dropout.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, keep if training else None, training,
+                             bn.momentum if bn.momentum is not None else 0.1, bn.eps, n_genes)
 
 
 ACT_CODE = {None: 0, "identity": 0, "softplus": 1, "relu": 2}

@@ -19,37 +19,11 @@ from typing import Any, Dict, Optional
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
-from torch.distributions import Beta, Gamma, LogNormal, Normal, constraints, transform_to
+from torch.distributions import constraints, transform_to
 
 from . import consts, gemm, latent, ops
 from .exceptions import NanException
 from .vae import CompositeEncoder, EncoderInputs
-
-
-def calculate_lambda(model_type: str, epsilon, chi_ambient, d_empty, y=None, d_cell=None, rho=None, chi_bar=None):
-    """Noise rate (reference model.py:25-58); dense form kept for callers outside the fused kernel."""
-    if model_type in ("simple", "ambient"):
-        return epsilon.unsqueeze(-1) * d_empty.unsqueeze(-1) * chi_ambient
-    if model_type == "swapping":
-        return (rho.unsqueeze(-1) * chi_bar * epsilon.unsqueeze(-1)
-                * (y.unsqueeze(-1) * d_cell.unsqueeze(-1) + d_empty.unsqueeze(-1)))
-    if model_type == "full":
-        return epsilon.unsqueeze(-1) * (
-            (1.0 - rho.unsqueeze(-1)) * chi_ambient * d_empty.unsqueeze(-1)
-            + rho.unsqueeze(-1) * chi_bar * (y.unsqueeze(-1) * d_cell.unsqueeze(-1) + d_empty.unsqueeze(-1)))
-    raise NotImplementedError(f"model_type was set to {model_type}, which is not implemented.")
-
-
-def calculate_mu(model_type: str, epsilon, d_cell, chi, y=None, rho=None):
-    """Mean expression (reference model.py:61-85)."""
-    if model_type == "simple":
-        return epsilon.unsqueeze(-1) * d_cell.unsqueeze(-1) * chi
-    if model_type == "ambient":
-        return y.unsqueeze(-1) * epsilon.unsqueeze(-1) * d_cell.unsqueeze(-1) * chi
-    if model_type in ("swapping", "full"):
-        return (1.0 - rho.unsqueeze(-1)) * y.unsqueeze(-1) * epsilon.unsqueeze(-1) * d_cell.unsqueeze(-1) * chi
-    raise NotImplementedError(f"model_type was set to {model_type}, which is not implemented.")
 
 
 def rate_coefficients(model_type: str, epsilon, d_cell, d_empty, rho):
@@ -117,16 +91,6 @@ class ParamStore(nn.Module):
         return {k: self.get(k) for k in self.unconstrained.keys()}
 
 
-def _masked_lower_median(values: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-    """values[mask].median() (torch.median = lower median) without a host sync: sort with +inf padding and
-    gather element (k-1)//2.  Returns 1.0 when the mask is empty (the reference would raise there)."""
-    k = mask.sum()
-    srt, _ = torch.sort(torch.where(mask, values, torch.full_like(values, float("inf"))))
-    idx = torch.clamp((k - 1) // 2, min=0)
-    med = srt.gather(0, idx.reshape(1)).squeeze(0)
-    return torch.where(k > 0, med, torch.ones_like(med))
-
-
 class _ObsTerm(torch.autograd.Function):
     """sum_b sum_k w[b,k] * L[b,k] with L = (L_y1, L_y0, L_E) of the fused observation kernel.  All gradients
     are produced by the same launch that produces the value, so backward only hands them out (upstream
@@ -139,10 +103,7 @@ class _ObsTerm(torch.autograd.Function):
         G = csr.n_genes
         B = h_dec.shape[0]
         logits = bufs["logits"][:B]
-        if gemm.BACKEND == "tcgen05":
-            ops.gemm_tf32(h_dec.contiguous(), w_out, B, G, w_out.shape[1], out=logits[:, :G], bias=b_out, split_k=1)
-        else:
-            torch.addmm(b_out, h_dec, w_out.t(), out=logits[:, :G])  # library fp32 GEMM (parity-test back-end)
+        ops.gemm_tf32(h_dec.contiguous(), w_out, B, G, w_out.shape[1], out=logits[:, :G], bias=b_out, split_k=1)
         chi_a = bufs["chi_a"]
         if chi_ambient.data_ptr() != chi_a.data_ptr():
             chi_a[:G].copy_(chi_ambient)
@@ -169,44 +130,31 @@ class _ObsTerm(torch.autograd.Function):
         G = ctx.G
         if ctx.dchi_ready is not None:
             torch.cuda.current_stream().wait_event(ctx.dchi_ready)
-        dl = dlogits[:, :G]
-        if gemm.BACKEND == "tcgen05":
-            B, H = h_dec.shape
-            h_c = h_dec.contiguous()
-            w_param = ctx.w_param
-            d_w_buf, d_w = gemm._grad_target(w_param)
-            d_b_buf, d_b = gemm._grad_target(ctx.bias_param)
-            main = torch.cuda.current_stream()
-            if gemm.fused_update_applies(w_param):
-                # the hidden-activation gradient reads the OLD decoder weights: issue it first, then the weight-gradient
-                # GEMM whose epilogue applies the optimizer update in place
-                d_h = ops.gemm_tf32(dlogits, w_out, B, H, G, b_mn=True) * g
-                gemm.FUSED_OPT.fused_dw(w_param, dlogits, h_c, G, H, B, 0)
-                ops.colsum_rows(dlogits, G, out=d_b_buf)
-            else:
-                # decoder weight / bias gradients on a side stream, the hidden-activation gradient on this one
-                side = ops.side_stream(dlogits.device, 0)
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    ops.gemm_tf32(dlogits, h_c, G, H, B, a_mn=True, b_mn=True, out=d_w_buf, split_k=1)  # dlogits^T . h
-                    ops.colsum_rows(dlogits, G, out=d_b_buf)
-                d_h = ops.gemm_tf32(dlogits, w_out, B, H, G, b_mn=True) * g          # dlogits[B,G] . Wd[G,H], split-K
-                if d_w is None and gemm.early_update_applies(w_param):
-                    # the decoder weights are no longer read this step: sweep their block now, behind the gradient GEMM
-                    readers_done = torch.cuda.Event()
-                    readers_done.record(main)
-                    side.wait_event(readers_done)
-                    with torch.cuda.stream(side):
-                        gemm.FUSED_OPT.early_block_update(w_param)
-                if d_w is None and d_b is None:
-                    h_c.record_stream(side), dlogits.record_stream(side)
-                    gemm.defer_join(side)  # both gradients went straight to the flat buffer: join at the end of backward
-                else:
-                    main.wait_stream(side)
+        B, H = h_dec.shape
+        h_c = h_dec.contiguous()
+        w_param = ctx.w_param
+        d_w_buf, d_w = gemm._grad_target(w_param)
+        d_b_buf, d_b = gemm._grad_target(ctx.bias_param)
+        main = torch.cuda.current_stream()
+        # decoder weight / bias gradients on a side stream, the hidden-activation gradient on this one
+        side = ops.side_stream(dlogits.device, 0)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ops.gemm_tf32(dlogits, h_c, G, H, B, a_mn=True, b_mn=True, out=d_w_buf, split_k=1)  # dlogits^T . h
+            ops.colsum_rows(dlogits, G, out=d_b_buf)
+        d_h = ops.gemm_tf32(dlogits, w_out, B, H, G, b_mn=True) * g          # dlogits[B,G] . Wd[G,H], split-K
+        if d_w is None and gemm.early_update_applies(w_param):
+            # the decoder weights are no longer read this step: sweep their block now, behind the gradient GEMM
+            readers_done = torch.cuda.Event()
+            readers_done.record(main)
+            side.wait_event(readers_done)
+            with torch.cuda.stream(side):
+                gemm.FUSED_OPT.early_block_update(w_param)
+        if d_w is None and d_b is None:
+            h_c.record_stream(side), dlogits.record_stream(side)
+            gemm.defer_join(side)  # both gradients went straight to the flat buffer: join at the end of backward
         else:
-            d_h = (dl @ w_out) * g
-            d_w = dl.t() @ h_dec  # [G, H]
-            d_b = ops.colsum_rows(dlogits, G)
+            main.wait_stream(side)
         d_coef, d_alpha, d_weights = ops.obs_small_grads(sums, w, g.contiguous(), want_dw=ctx.needs_input_grad[6])
         d_alpha = d_alpha.reshape(ctx.alpha_shape)
         return d_h, d_w, d_b, dchi_amb * g, d_coef, d_alpha, d_weights, None
@@ -302,6 +250,7 @@ class RemoveBackgroundPyroModel(nn.Module):
         ps.setup("phi_scale", self.phi_scale_prior, constraints.positive)
         self.param_store = ps
         self.to(dev)
+        gemm.pad_big_weights(self)  # TMA-addressable rows for the G-wide weights even without an optimizer
         self._d_empty_loc_now = None
         if "other" in encoder:
             encoder["other"].d_empty_loc_fn = lambda: (self._d_empty_loc_now if self._d_empty_loc_now is not None

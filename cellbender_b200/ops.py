@@ -246,10 +246,14 @@ def colsum_rows(mat: torch.Tensor, n_cols: int, out: Optional[torch.Tensor] = No
     return out
 
 
-def row_logsumexp(mat: torch.Tensor, n_cols: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _req_cuda(mat)
-    out = torch.empty(mat.shape[0], dtype=torch.float32, device=mat.device) if out is None else out
-    _cabi.lib().call("cb_row_logsumexp", ptr(mat), mat.shape[0], n_cols, mat.stride(0), ptr(out), current_stream())
+def col_logsumexp(mat: torch.Tensor, n_rows: int, n_cols: int, row_add: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[c] = log sum_r exp(mat[r, c] + row_add[r]) over the first n_rows x n_cols block of ``mat`` (cb_col_logsumexp)."""
+    _req_cuda(mat, row_add)
+    L = _cabi.lib()
+    out = torch.empty(n_cols, dtype=torch.float32, device=mat.device) if out is None else out
+    scratch = torch.empty(int(L.raw("cb_col_logsumexp_scratch_elems")(n_rows, n_cols)), dtype=torch.float32, device=mat.device)
+    L.call("cb_col_logsumexp", ptr(mat), n_rows, n_cols, mat.stride(0), ptr(row_add), ptr(scratch), ptr(out), current_stream())
     return out
 
 
@@ -276,51 +280,84 @@ def exclusive_scan_i32(x: torch.Tensor):
 # ------------------------------------------------------------------------------------------------------
 # posterior noise-count COO
 # ------------------------------------------------------------------------------------------------------
-@torch.no_grad()
-def posterior_coo(csr: DeviceCSR, cell_rows, logits, lse, chi_ambient, chi_bar, a_mu, c_a, c_b, alpha, n_window,
-                  barcode_all, gene_all, total_n_genes: int, n_counts_max: int = 20, log_thresh: float = -10.0,
-                  lambda_multiplier: float = 1.0):
-    """Noise-count posterior of the stored counts of `cell_rows`, as sorted COO arrays on the device.
+class PosteriorWorkspace:
+    """Per-stored-count outputs of the noise-window kernel for a whole posterior pass (all chunks), sized once from the
+    cells' stored-count numbers so that no host synchronisation is needed between chunks: logp [E, stride], low [E],
+    keep [E], entry_m [E]."""
 
-    logits [S*Bc, ld] / lse [S*Bc] hold the decoder output of every latent sample (row = s*Bc + b);
-    a_mu, c_a, c_b [S*Bc], alpha [S] the per-sample rate coefficients; n_window [Bc] int32;
-    barcode_all [Bc] / gene_all [G] int64 map to indices of the full count matrix.
-    Returns (m int64, c int32, log_prob fp32, off_m int64, off_v int32)."""
-    _req_cuda(cell_rows, logits, lse, a_mu, c_a, c_b, alpha, n_window, barcode_all, gene_all)
+    def __init__(self, n_entries: int, n_counts_max: int, device):
+        self.n_entries = int(n_entries)
+        self.n_counts_max = int(n_counts_max)
+        self.stride = int(_cabi.lib().raw("cb_posterior_window_stride")(int(n_counts_max)))
+        n = max(self.n_entries, 1)
+        self.logp = torch.empty((n, self.stride), dtype=torch.float32, device=device)
+        self.low = torch.empty(n, dtype=torch.int32, device=device)
+        self.keep = torch.empty(n, dtype=torch.int32, device=device)
+        self.entry_m = torch.empty(n, dtype=torch.int64, device=device)
+
+
+@torch.no_grad()
+def posterior_window(csr: DeviceCSR, cell_rows, logits_t, dec_bias, lse, chi_ambient, chi_bar, a_mu, c_a, c_b, alpha, n_window,
+                     entry_start, n_entries: int, barcode_all, gene_all, total_n_genes: int, ws: PosteriorWorkspace,
+                     entry_offset: int, log_thresh: float = -10.0, lambda_multiplier: float = 1.0):
+    """cb_posterior_noise_window for one chunk of cells, writing rows [entry_offset, entry_offset + n_entries) of ``ws``.
+
+    logits_t [G, ldt]: transposed, cell-major decoder output (column b * S + s); lse [Bc * S]; a_mu, c_a, c_b [Bc * S];
+    alpha [S]; n_window [Bc] int32; entry_start [Bc + 1] int64 (chunk-local prefix sums of the stored-count numbers);
+    barcode_all [Bc] / gene_all [G] int64 map to indices of the full count matrix."""
+    _req_cuda(cell_rows, logits_t, lse, a_mu, c_a, c_b, alpha, n_window, entry_start, barcode_all, gene_all)
+    Bc, G, S = int(cell_rows.numel()), csr.n_genes, int(alpha.numel())
+    assert logits_t.stride(1) == 1 and logits_t.shape[0] >= G and entry_offset + n_entries <= max(ws.n_entries, 1)
+    o = int(entry_offset)
+    _cabi.lib().call(
+        "cb_posterior_noise_window", ptr(csr.indptr), ptr(csr.indices), ptr(csr.data), ptr(cell_rows), Bc, G, S, ptr(logits_t),
+        logits_t.stride(0), ptr(dec_bias), ptr(lse), ptr(chi_ambient), ptr(chi_bar), ptr(a_mu), ptr(c_a), ptr(c_b), ptr(alpha),
+        ptr(n_window), ptr(entry_start), int(n_entries), ptr(barcode_all), ptr(gene_all), int(total_n_genes), ws.n_counts_max,
+        float(log_thresh), float(lambda_multiplier), ws.logp.data_ptr() + 4 * ws.stride * o, ws.low.data_ptr() + 4 * o,
+        ws.keep.data_ptr() + 4 * o, ws.entry_m.data_ptr() + 8 * o, current_stream())
+
+
+@torch.no_grad()
+def posterior_compact(ws: PosteriorWorkspace, log_thresh: float = -10.0):
+    """Thresholded COO of a filled workspace: (m int64, c int32, log_prob fp32, off_m int64, off_v int32), entries in
+    workspace order (cell, gene, c).  The ONE host synchronisation of a posterior pass (two output sizes) happens here."""
     L = _cabi.lib()
     st = current_stream()
-    dev = logits.device
-    Bc, G = int(cell_rows.numel()), csr.n_genes
-    S = int(alpha.numel())
-    assert logits.shape[0] == S * Bc and logits.stride(1) == 1
-    nnz_per_cell = (csr.indptr[cell_rows + 1] - csr.indptr[cell_rows])
-    entry_start = torch.zeros(Bc + 1, dtype=torch.int64, device=dev)
-    entry_start[1:] = torch.cumsum(nnz_per_cell, 0)
-    n_entries = int(entry_start[-1].item())
-    stride = int(L.raw("cb_posterior_window_stride")(int(n_counts_max)))
-    logp = torch.empty((max(n_entries, 1), stride), dtype=torch.float32, device=dev)
-    low = torch.empty(max(n_entries, 1), dtype=torch.int32, device=dev)
-    keep = torch.empty(max(n_entries, 1), dtype=torch.int32, device=dev)
-    entry_m = torch.empty(max(n_entries, 1), dtype=torch.int64, device=dev)
-    L.call("cb_posterior_noise_window", ptr(csr.indptr), ptr(csr.indices), ptr(csr.data), ptr(cell_rows), Bc, G, S,
-           ptr(logits), logits.stride(0), ptr(lse), ptr(chi_ambient), ptr(chi_bar), ptr(a_mu), ptr(c_a), ptr(c_b),
-           ptr(alpha), ptr(n_window), ptr(entry_start), int(n_counts_max), float(log_thresh), float(lambda_multiplier),
-           ptr(logp), ptr(low), ptr(keep), st)
-    L.call("cb_posterior_entry_index", ptr(csr.indptr), ptr(csr.indices), ptr(cell_rows), Bc, ptr(barcode_all),
-           ptr(gene_all), int(total_n_genes), ptr(entry_start), ptr(entry_m), st)
-    keep = keep[:n_entries]
+    dev = ws.logp.device
+    n = ws.n_entries
+    if n == 0:
+        z = lambda dt: torch.zeros(0, dtype=dt, device=dev)
+        return z(torch.int64), z(torch.int32), z(torch.float32), z(torch.int64), z(torch.int32)
+    keep = ws.keep[:n]
     keep_pos, keep_total = exclusive_scan_i32(keep)
-    has_off = ((keep > 0) & (low[:n_entries] != 0)).to(torch.int32)
+    has_off = torch.empty(n, dtype=torch.int32, device=dev)
+    L.call("cb_posterior_offset_flags", n, ptr(keep), ptr(ws.low), ptr(has_off), st)
     off_pos, off_total = exclusive_scan_i32(has_off)
-    n_keep, n_off = int(keep_total.item()), int(off_total.item())
+    n_keep, n_off = (int(v) for v in torch.cat((keep_total, off_total)).tolist())
     coo_m = torch.empty(n_keep, dtype=torch.int64, device=dev)
     coo_c = torch.empty(n_keep, dtype=torch.int32, device=dev)
     coo_lp = torch.empty(n_keep, dtype=torch.float32, device=dev)
     off_m = torch.empty(n_off, dtype=torch.int64, device=dev)
     off_v = torch.empty(n_off, dtype=torch.int32, device=dev)
-    L.call("cb_posterior_compact", n_entries, int(n_counts_max), ptr(entry_m), ptr(logp), ptr(low), ptr(keep),
-           ptr(keep_pos), ptr(off_pos), float(log_thresh), ptr(coo_m), ptr(coo_c), ptr(coo_lp), ptr(off_m), ptr(off_v), st)
+    L.call("cb_posterior_compact", n, ws.n_counts_max, ptr(ws.entry_m), ptr(ws.logp), ptr(ws.low), ptr(keep), ptr(keep_pos),
+           ptr(off_pos), float(log_thresh), ptr(coo_m), ptr(coo_c), ptr(coo_lp), ptr(off_m), ptr(off_v), st)
     return coo_m, coo_c, coo_lp, off_m, off_v
+
+
+@torch.no_grad()
+def posterior_coo(csr: DeviceCSR, cell_rows, logits_t, dec_bias, lse, chi_ambient, chi_bar, a_mu, c_a, c_b, alpha, n_window,
+                  barcode_all, gene_all, total_n_genes: int, n_counts_max: int = 20, log_thresh: float = -10.0,
+                  lambda_multiplier: float = 1.0):
+    """One-chunk convenience wrapper (tests): window kernel + compaction.  See ``posterior_window`` for the operands."""
+    dev = logits_t.device
+    nnz_per_cell = (csr.indptr[cell_rows + 1] - csr.indptr[cell_rows])
+    entry_start = torch.zeros(int(cell_rows.numel()) + 1, dtype=torch.int64, device=dev)
+    entry_start[1:] = torch.cumsum(nnz_per_cell, 0)
+    n_entries = int(entry_start[-1].item())
+    ws = PosteriorWorkspace(n_entries, n_counts_max, dev)
+    posterior_window(csr, cell_rows, logits_t, dec_bias, lse, chi_ambient, chi_bar, a_mu, c_a, c_b, alpha, n_window, entry_start,
+                     n_entries, barcode_all, gene_all, total_n_genes, ws, 0, log_thresh, lambda_multiplier)
+    return posterior_compact(ws, log_thresh)
 
 
 def gather_feats(csr: DeviceCSR, row_ids: torch.Tensor, amb_unit: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -337,7 +374,7 @@ _GEMM_WS = {}
 def gemm_tf32(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
               out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, accumulate: bool = False,
               split_k: Optional[int] = None, a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None,
-              K2: int = 0) -> torch.Tensor:
+              K2: int = 0, tile_cfg: int = 0) -> torch.Tensor:
     """C[M,N] (=,+=) A[M,K] @ B[N,K]^T (+ bias) through cb_gemm_tf32.
 
     a: stored [M, >=K] (a_mn=False) or [K, >=M] (a_mn=True), last dim contiguous, row stride % 4 == 0; same for b."""
@@ -357,7 +394,12 @@ def gemm_tf32(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn: bo
         if ws is None or ws.numel() < ws_elems:
             ws = torch.empty(ws_elems, dtype=torch.float32, device=dev)
             _GEMM_WS[key] = ws
-    if a2 is None:
+    if tile_cfg:  # explicit tile configuration (tools/gemm_bench.py)
+        a2_, b2_ = (a, b) if a2 is None else (a2, b2)
+        L.call("cb_gemm_tf32_ex", ptr(a), a.stride(0), ptr(b), b.stride(0), K, ptr(a2_), a2_.stride(0), ptr(b2_), b2_.stride(0), K2,
+               int(a_mn), int(b_mn), ptr(out), out.stride(0), M, N, ptr(bias), int(accumulate), split_k, ptr(ws), ws_elems,
+               int(tile_cfg), current_stream())
+    elif a2 is None:
         L.call("cb_gemm_tf32", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out), out.stride(0), M, N, K,
                ptr(bias), int(accumulate), split_k, ptr(ws), ws_elems, current_stream())
     else:  # C = A B^T + A2 B2^T in one launch (shared TMEM accumulator)
@@ -428,6 +470,15 @@ def head(x: torch.Tensor, lin: torch.nn.Linear, feat: Optional[torch.Tensor] = N
     _req_cuda(x, feat)
     assert lin.out_features == 1 and lin.weight.is_contiguous()
     return _Head.apply(x, lin.weight, lin.bias, None if feat is None else feat.contiguous())
+
+
+def feat_dw(dy: torch.Tensor, feat: torch.Tensor, dw: torch.Tensor):
+    """dw[:, :F] = dy^T @ feat (cb_feat_dw): the feature columns of the weight gradient of Linear(cat(feat, x))."""
+    _req_cuda(dy, feat, dw)
+    B, H = dy.shape
+    F_ = feat.shape[1]
+    assert dy.stride(1) == 1 and feat.is_contiguous() and dw.stride(1) == 1 and dw.shape[0] == H
+    _cabi.lib().call("cb_feat_dw", ptr(dy), dy.stride(0), ptr(feat), F_, B, H, ptr(dw), dw.stride(0), current_stream())
 
 
 def obs_loss(sums: torch.Tensor, w: torch.Tensor):

@@ -8,7 +8,6 @@ clamp at +-10 (pyro ClippedAdam ``clip_norm``), beta2 0.999, eps 1e-8, no weight
 ``total_steps`` raises like torch's scheduler does (pinned by the reference's tests/test_train.py:87-108).
 ``constant_learning_rate=True`` gives plain ClippedAdam at ``lr`` with beta1 0.9 (run.py:621-627).
 """
-import os
 from typing import Iterable, List, Optional
 
 import torch
@@ -112,14 +111,6 @@ class FlatClippedAdam:
         self.beta2, self.eps, self.clip = betas[1], eps, clip_norm
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)  # optimizer steps taken (device side)
         self.host_steps = 0
-        # Optional (CB_FUSE_ADAM=1): apply the update of the four G x 512 weight matrices (99 % of the parameters) inside
-        # the weight-gradient GEMM itself (cb_gemm_tf32_dw_adam: persistent CTAs, TMEM-double-buffered accumulators, the
-        # gradient tile never leaves the SM), which removes the gradient write + read (-25 % of a step's HBM bytes).
-        # Correct (tests/test_gemm_gpu.py, tests/test_step_gpu.py) but OFF by default: measured on B200 (r01) the fused
-        # kernel takes 131-185 us per matrix against 55 us (GEMM) + 76 us (its share of the Adam sweep): the twelve
-        # epilogue warps keep ~72 KB of optimizer state in flight per SM and reach 3.5 TB/s, the stand-alone sweep (2048
-        # threads per SM) reaches 6.2 TB/s.  Next: move the state tiles with TMA.
-        self.fuse_weight_updates = os.environ.get("CB_FUSE_ADAM", "0") == "1"
         # Default on a single GPU: the ClippedAdam sweep of each large weight block is issued as soon as that block's
         # gradient GEMM has finished, on the same (side) stream, so that the HBM-bound sweep overlaps the rest of the
         # backward pass (which is latency / L2-bound); the sweep at the end of the step covers what is left.
@@ -149,21 +140,6 @@ class FlatClippedAdam:
         if src:
             torch._foreach_copy_(dst, src)
 
-    def fused_dw(self, w: nn.Parameter, dy: torch.Tensor, x: torch.Tensor, rows: int, n_in: int, n_batch: int, col_offset: int):
-        """dW[rows, n_in] = dy^T x with the ClippedAdam update of W[:, col_offset:col_offset + n_in] applied in the GEMM
-        epilogue.  The caller guarantees that every reader of the OLD weights (input-gradient products) was issued before."""
-        from ._cabi import current_stream, lib
-
-        o, n_rows, ld, cols = w._cb_block
-        assert n_rows == rows and col_offset + n_in <= cols
-        byte = 4 * (o + col_offset)
-        lib().call("cb_gemm_tf32_dw_adam", dy.data_ptr(), dy.stride(0), 1, x.data_ptr(), x.stride(0), 1, ld, rows, n_in, n_batch,
-                   self.flat_p.data_ptr() + byte, self.flat_m.data_ptr() + byte, self.flat_v.data_ptr() + byte,
-                   self.lr_table.data_ptr(), self.beta1_table.data_ptr(), self.lr_table.numel(), self.step_count.data_ptr(),
-                   float(self.beta2), float(self.eps), float(self.clip), current_stream())
-        w._cb_grad_direct = True
-        self._fused_done.append((o, n_rows, ld, cols, col_offset))
-
     def early_block_update(self, w: nn.Parameter):
         """ClippedAdam sweep of one [rows, ld] weight block of the flat buffers, on the current stream, without advancing
         the step counter.  The caller guarantees the block's gradient is complete and its old values are no longer read."""
@@ -184,11 +160,10 @@ class FlatClippedAdam:
             raise ValueError(f"Tried to step {self.host_steps + 1} times. The specified number of total steps is "
                              f"{self.total_steps}")
         if self._fused_done:
-            # blocks already updated by their weight-gradient GEMM: sweep the ranges between them, plus the few feature
-            # columns in front of each gene block (their gradient went to the flat buffer the usual way)
+            # blocks already swept behind their weight-gradient GEMM (early_block_update): sweep the ranges between them
             from ._cabi import current_stream, lib
 
-            assert grad_scale == 1.0, "fused weight updates do not support gradient rescaling"
+            assert grad_scale == 1.0, "piecewise weight updates do not support gradient rescaling"
             L, st = lib(), current_stream()
             tab = (self.lr_table.data_ptr(), self.beta1_table.data_ptr(), self.lr_table.numel(), self.step_count.data_ptr(),
                    float(self.beta2), float(self.eps), float(self.clip))
@@ -206,9 +181,6 @@ class FlatClippedAdam:
                 assert o >= cur, "fused blocks overlap"
                 L.call("cb_clipped_adam_range", at(self.flat_p, cur), at(self.flat_g, cur), at(self.flat_m, cur),
                        at(self.flat_v, cur), o - cur, *tab, 0, st)
-                if off:
-                    L.call("cb_clipped_adam_2d", at(self.flat_p, o), at(self.flat_g, o), at(self.flat_m, o), at(self.flat_v, o),
-                           rows, off, ld, *tab, st)
                 cur = o + rows * ld
             L.call("cb_clipped_adam_range", at(self.flat_p, cur), at(self.flat_g, cur), at(self.flat_m, cur), at(self.flat_v, cur),
                    self.n - cur, *tab, 1, st)

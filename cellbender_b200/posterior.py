@@ -5,9 +5,11 @@ same return types (scipy COO keyed by m = n * G_all + g plus the offsets dict).
 
 Differences in HOW:
   * the encoder runs once per cell chunk, not once per latent sample (it is deterministic in eval mode);
-  * all S latent samples of a chunk go through ONE decoder GEMM ([S * cells, 512] x [512, G]);
+  * all S latent samples of a chunk go through ONE decoder GEMM whose output is written transposed and cell-major
+    ([G, cells * S]: the S samples of a (cell, gene) are contiguous);
   * the noise-count log-probability is evaluated only at stored counts, with the sample average kept in registers
-    (csrc/posterior.cu), and the COO is emitted on the device already in the reference's (m, c) order;
+    (csrc/posterior.cu); cells are visited in barcode order, so the COO comes out globally (m, c)-sorted with no sort,
+    and there is no host synchronisation between chunks (output rows are sized from the stored-count numbers);
   * the estimators consume the device-resident COO directly (estimation.DevicePosteriorCOO).
 Monte-Carlo noise: torch's CUDA generator instead of pyro's trace order, so individual draws differ from a pyro run;
 the distribution they are drawn from is the guide's (model.py:506-567), and y is fixed to its MAP (y_map=True).
@@ -20,7 +22,7 @@ import scipy.sparse as sp
 import torch
 from torch.distributions import Beta, Gamma, LogNormal, Normal
 
-from . import consts, gemm, ops
+from . import consts, ops
 from .estimation import DevicePosteriorCOO, EstimationMethod, IndexConverter
 from .sparse_utils import csr_set_rows_to_zero, subtract_noise_in_cells  # noqa: F401  (re-exported like the reference)
 from .model import RemoveBackgroundPyroModel
@@ -119,24 +121,34 @@ class Posterior:
         return self._noise_count_posterior_coo
 
     @torch.no_grad()
-    def sample_rate_coefficients(self, enc: Dict[str, torch.Tensor], n_samples: int, y_map: bool = True):
-        """S latent draws from the guide for a chunk of B droplets (sample_mu_lambda_alpha, posterior.py:737-782,
-        with the model's returned quantities in factored form: mu = a_mu * chi(z), lam = c_a * chi_ambient + c_b *
-        chi_bar, alpha = 1 / phi).  NOTE the reference returns the lambda of the empty-droplet regulariser block
-        (epsilon = 1, y = 0; model.py:385-393,445), reproduced here."""
+    def sample_rate_coefficients(self, enc: Dict[str, torch.Tensor], n_samples: int, y_map: bool = True,
+                                 noise: Optional[Dict[str, torch.Tensor]] = None):
+        """S latent draws from the guide for a chunk of B droplets (sample_mu_lambda_alpha, posterior.py:737-782, with the
+        model's returned quantities in factored form: mu = a_mu * chi(z), lam = c_a * chi_ambient + c_b * chi_bar,
+        alpha = 1 / phi), laid out CELL-MAJOR: z [B, S, Z]; a_mu, c_a, c_b [B, S]; alpha [S].
+        NOTE the reference returns the lambda of the empty-droplet regulariser block (epsilon = 1, y = 0;
+        model.py:385-393, 445), reproduced here.  ``noise`` (tests) supplies the draws themselves: phi [S]; rho, d_empty,
+        d_cell, epsilon [B, S]; z [B, S, Z]."""
         if not y_map:
             raise NotImplementedError("only y_map=True (the value the reference's pipeline uses) is supported")
         m, ps = self.vi_model, self.vi_model.param_store
         B, S = enc["p_y"].shape[0], n_samples
-        phi_loc, phi_scale = ps["phi_loc"], ps["phi_scale"]
-        phi = Gamma(phi_loc.pow(2) / phi_scale.pow(2), phi_loc / phi_scale.pow(2)).sample((S,))
-        rho = Beta(ps["rho_alpha"], ps["rho_beta"]).sample((S, B)) if m.include_rho else torch.zeros((S, B), device=self.device)
-        d_empty = LogNormal(ps["d_empty_loc"], ps["d_empty_scale"]).sample((S, B))
-        z = Normal(enc["z"]["loc"].reshape(B, -1), enc["z"]["scale"].reshape(B, -1)).sample((S,))
+        z_loc, z_scale = enc["z"]["loc"].reshape(B, -1), enc["z"]["scale"].reshape(B, -1)
         prob = enc["p_y"].sigmoid()
-        d_cell = LogNormal(prob * enc["d_loc"] + (1 - prob) * m.d_cell_loc_prior, ps["d_cell_scale"]).sample((S,))
-        epsilon = Gamma((prob * enc["epsilon"] + (1 - prob)) * m.epsilon_prior, m.epsilon_prior).sample((S,))
-        y = (enc["p_y"] > 0).float().expand(S, B)
+        if noise is None:
+            phi_loc, phi_scale = ps["phi_loc"], ps["phi_scale"]
+            phi = Gamma(phi_loc.pow(2) / phi_scale.pow(2), phi_loc / phi_scale.pow(2)).sample((S,)).reshape(S)
+            rho = Beta(ps["rho_alpha"], ps["rho_beta"]).sample((B, S)).reshape(B, S) if m.include_rho \
+                else torch.zeros((B, S), device=self.device)
+            d_empty = LogNormal(ps["d_empty_loc"], ps["d_empty_scale"]).sample((B, S)).reshape(B, S)
+            z = z_loc[:, None, :] + z_scale[:, None, :] * torch.randn((B, S, z_loc.shape[1]), device=self.device)
+            d_cell = LogNormal((prob * enc["d_loc"] + (1 - prob) * m.d_cell_loc_prior)[:, None].expand(B, S),
+                               ps["d_cell_scale"]).sample()
+            epsilon = Gamma(((prob * enc["epsilon"] + (1 - prob)) * m.epsilon_prior)[:, None].expand(B, S),
+                            m.epsilon_prior).sample()
+        else:
+            phi, rho, d_empty, z, d_cell, epsilon = (noise[k].to(self.device) for k in ("phi", "rho", "d_empty", "z", "d_cell", "epsilon"))
+        y = (enc["p_y"] > 0).float()[:, None].expand(B, S)
         if m.model_type == "full":
             a_mu, c_a, c_b = (1 - rho) * y * epsilon * d_cell, (1 - rho) * d_empty, rho * d_empty
         elif m.model_type == "swapping":
@@ -155,23 +167,18 @@ class Posterior:
         self._noise_count_posterior_coo_offsets = dev_post.offsets_dict()
         return self._noise_count_posterior_coo
 
-    @torch.no_grad()
-    def device_posterior(self, n_samples: int = 20, y_map: bool = True, n_counts_max: int = 20,
-                         smallest_log_probability: float = -10.0, cell_subset: Optional[np.ndarray] = None,
-                         lambda_multiplier: float = 1.0, seed: Optional[int] = None) -> DevicePosteriorCOO:
-        """The posterior COO, computed and left on the device.  ``cell_subset`` (indices into the p > 0.5 cell list)
-        restricts the computation (used for barcode sharding across GPUs).  ``seed``: reseed the generator per chunk
-        with seed + first cell index, which makes the Monte-Carlo draws a function of the cell chunk only (sharded and
-        unsharded runs then agree bit for bit when shard boundaries fall on chunk boundaries)."""
-        m = self.vi_model
+    def posterior_cell_order(self, n_counts_max: int = 20):
+        """The cells the reference's posterior loop visits (p > 0.5, minus a dropped trailing minibatch of < 4 cells,
+        dataprep.py:155-161), re-ordered by barcode index of the full matrix so that the emitted COO is globally (m, c)
+        sorted, with the per-cell window size of the reference's 128-cell minibatch the cell belongs to
+        (n = min(n_counts_max, data.max()), posterior.py:816).  Returns (rows int64 [n] of the analysed matrix,
+        n_window int32 [n] device tensor, barcodes int64 [n])."""
         csr = self._device_csr()
-        G = csr.n_genes
         cell_logic = self.latents_map["p"] > consts.CELL_PROB_CUTOFF
         if cell_logic.sum() == 0:
             logger.error(f"ERROR: Found zero droplets with posterior cell probability > {consts.CELL_PROB_CUTOFF}.")
             raise RuntimeError("Zero cells found!")
-        cell_rows_all = np.flatnonzero(cell_logic)  # rows of the analysed count matrix
-        # window size per cell: min(n_counts_max, max count inside the reference's minibatch of that cell)
+        cell_rows_all = np.flatnonzero(cell_logic)  # rows of the analysed count matrix, the reference's loader order
         feats = []
         for start in range(0, cell_rows_all.size, 4096):
             rows = torch.as_tensor(cell_rows_all[start:start + 4096], device=self.device)
@@ -182,14 +189,49 @@ class Posterior:
         padded = torch.zeros(n_b * pb, device=self.device)
         padded[: row_max.numel()] = row_max
         group_max = padded.view(n_b, pb).max(dim=1).values
-        # the reference drops a trailing minibatch of < 4 cells (dataprep.py:155-161)
-        n_eff = cell_rows_all.size if (cell_rows_all.size % pb == 0 or cell_rows_all.size % pb >= consts.SMALLEST_ALLOWED_BATCH) \
-            else cell_rows_all.size - cell_rows_all.size % pb
-        n_window_all = torch.clamp(group_max.repeat_interleave(pb)[: cell_rows_all.size], max=float(n_counts_max)).to(torch.int32)
-        sel = np.arange(n_eff) if cell_subset is None else np.asarray(cell_subset)[np.asarray(cell_subset) < n_eff]
+        tail = cell_rows_all.size % pb
+        n_eff = cell_rows_all.size if (tail == 0 or tail >= consts.SMALLEST_ALLOWED_BATCH) else cell_rows_all.size - tail
+        n_window_all = torch.clamp(group_max.repeat_interleave(pb)[:n_eff], max=float(n_counts_max)).to(torch.int32)
+        barcodes = np.asarray(self.dataset_obj.analyzed_barcode_inds)[cell_rows_all[:n_eff]].astype(np.int64)
+        order = np.argsort(barcodes, kind="stable")
+        return cell_rows_all[:n_eff][order], n_window_all[torch.as_tensor(order, device=self.device)].contiguous(), barcodes[order]
 
-        barcode_all = torch.as_tensor(np.asarray(self.dataset_obj.analyzed_barcode_inds)[cell_rows_all].astype(np.int64),
-                                      device=self.device)
+    @torch.no_grad()
+    def device_posterior(self, n_samples: int = 20, y_map: bool = True, n_counts_max: int = 20,
+                         smallest_log_probability: float = -10.0, cell_subset: Optional[np.ndarray] = None,
+                         lambda_multiplier: float = 1.0, seed: Optional[int] = None,
+                         noise_fn=None) -> DevicePosteriorCOO:
+        """The posterior COO, computed and left on the device, sorted by (m, c).
+
+        ``cell_subset``: a contiguous range of positions in ``posterior_cell_order()`` (barcode-sorted cell list) --
+        barcode sharding across GPUs: the shards' COO pieces concatenate, in rank order, to the sorted whole.
+        ``seed``: reseed the generator per chunk with seed + position of the chunk's first cell, which makes the
+        Monte-Carlo draws a function of the chunk only (sharded and unsharded runs then agree bit for bit when shard
+        boundaries fall on chunk boundaries).  ``noise_fn(position_slice, enc) -> dict`` (tests) injects the latent draws.
+        No host synchronisation happens between chunks; the single one is the read of the output sizes at the end."""
+        m = self.vi_model
+        csr = self._device_csr()
+        G = csr.n_genes
+        rows_sorted, n_window, barcodes = self.posterior_cell_order(n_counts_max)
+        lo, hi = 0, rows_sorted.size
+        if cell_subset is not None:
+            cs = np.asarray(cell_subset)
+            cs = cs[cs < rows_sorted.size]
+            if cs.size:
+                assert np.all(np.diff(cs) == 1), "cell_subset must be a contiguous range of the barcode-sorted cell list"
+                lo, hi = int(cs[0]), int(cs[-1]) + 1
+            else:
+                lo = hi = 0
+        S = n_samples
+        # stored counts per cell from the host copy of the analysed matrix: output rows of every chunk are known up front
+        host_indptr = self._host_indptr()
+        nnz_cell = (host_indptr[rows_sorted[lo:hi] + 1] - host_indptr[rows_sorted[lo:hi]]).astype(np.int64)
+        prefix = np.concatenate(([0], np.cumsum(nnz_cell)))
+        ws = ops.PosteriorWorkspace(int(prefix[-1]), n_counts_max, self.device)
+        rows_dev = torch.as_tensor(rows_sorted[lo:hi], device=self.device)
+        barcode_dev = torch.as_tensor(barcodes[lo:hi], device=self.device)
+        prefix_dev = torch.as_tensor(prefix, device=self.device)
+        n_window = n_window[lo:hi]
         gene_all = torch.as_tensor(np.asarray(self.analyzed_gene_inds).astype(np.int64), device=self.device)
         ld = ops.round_up(G, 4)
         chi_a = torch.zeros(ld, device=self.device)
@@ -197,44 +239,37 @@ class Posterior:
         chi_a[:G] = m.param_store["chi_ambient"].detach()
         chi_b[:G] = m.avg_gene_expression
         lin = m.decoder.out_linear
-        pieces = []
-        S = n_samples
-        logits = None
-        for start in range(0, sel.size, self.cells_per_chunk):
-            idx = sel[start:start + self.cells_per_chunk]
-            rows = torch.as_tensor(cell_rows_all[idx], device=self.device)
-            Bc = rows.numel()
+        cpc = self.cells_per_chunk
+        logits_t = torch.empty((G, ops.round_up(S * cpc, 4)), device=self.device)  # [G, cells * S]: transposed, cell-major
+        for start in range(0, hi - lo, cpc):
+            stop = min(hi - lo, start + cpc)
+            Bc = stop - start
+            rows = rows_dev[start:stop]
             if seed is not None:
-                torch.manual_seed(int(seed) + int(idx[0]))
+                torch.manual_seed(int(seed) + lo + start)
             _, enc = self._encode(rows)
-            z, a_mu, c_a, c_b, alpha = self.sample_rate_coefficients(enc, S, y_map=y_map)
-            h = m.decoder.hidden(z.reshape(S * Bc, -1))
-            if logits is None or logits.shape[0] < S * Bc:
-                logits = torch.zeros((S * self.cells_per_chunk, ld), device=self.device)
-            lg = logits[: S * Bc]
-            # ONE decoder GEMM for all samples of the chunk ([S * Bc, 512] x [512, G])
-            if gemm.BACKEND == "tcgen05":
-                ops.gemm_tf32(h.contiguous(), lin.weight, S * Bc, G, lin.weight.shape[1], out=lg[:, :G], bias=lin.bias, split_k=1)
-            else:
-                torch.addmm(lin.bias, h, lin.weight.t(), out=lg[:, :G])
-            lse = ops.row_logsumexp(lg, G)
-            idx_t = torch.as_tensor(idx, device=self.device)
-            pieces.append(ops.posterior_coo(
-                csr, rows, lg, lse, chi_a, chi_b, a_mu.reshape(-1).contiguous(), c_a.reshape(-1).contiguous(),
-                c_b.reshape(-1).contiguous(), alpha.contiguous(), n_window_all[idx_t].contiguous(),
-                barcode_all[idx_t].contiguous(), gene_all, int(self.count_matrix_shape[1]), n_counts_max=n_counts_max,
-                log_thresh=smallest_log_probability, lambda_multiplier=lambda_multiplier))
-        cat = lambda i, dt: torch.cat([p[i] for p in pieces]) if pieces else torch.zeros(0, dtype=dt, device=self.device)
-        post = DevicePosteriorCOO(cat(0, torch.int64), cat(1, torch.int32), cat(2, torch.float32), cat(3, torch.int64),
-                                  cat(4, torch.int32), n_cols=n_counts_max)
-        # barcode indices of the full matrix need not be increasing in cell-list order -> make (m, c) order global
-        post.ensure_sorted()
-        if post.off_m.numel() > 1:
-            o = torch.argsort(post.off_m)
-            post.off_m, post.off_v = post.off_m[o].contiguous(), post.off_v[o].contiguous()
+            noise = None if noise_fn is None else noise_fn(slice(lo + start, lo + stop), enc)
+            z, a_mu, c_a, c_b, alpha = self.sample_rate_coefficients(enc, S, y_map=y_map, noise=noise)
+            h = m.decoder.hidden(z.reshape(Bc * S, -1))
+            # ONE decoder GEMM for all samples of the chunk, output transposed: logits_t[g, b * S + s] = W[g, :] . h[b * S + s, :]
+            lt = logits_t[:, : Bc * S]
+            ops.gemm_tf32(lin.weight, h.contiguous(), G, Bc * S, lin.weight.shape[1], out=lt, split_k=1)
+            lse = ops.col_logsumexp(logits_t, G, Bc * S, row_add=lin.bias)
+            ops.posterior_window(
+                csr, rows, logits_t, lin.bias, lse, chi_a, chi_b, a_mu.reshape(-1).contiguous(), c_a.reshape(-1).contiguous(),
+                c_b.reshape(-1).contiguous(), alpha.contiguous(), n_window[start:stop].contiguous(),
+                (prefix_dev[start:stop + 1] - prefix_dev[start]).contiguous(), int(prefix[stop] - prefix[start]),
+                barcode_dev[start:stop].contiguous(), gene_all, int(self.count_matrix_shape[1]), ws, int(prefix[start]),
+                log_thresh=smallest_log_probability, lambda_multiplier=lambda_multiplier)
+        post = DevicePosteriorCOO(*ops.posterior_compact(ws, smallest_log_probability), n_cols=n_counts_max)
         if cell_subset is None:
             self._device_posterior = post
         return post
+
+    def _host_indptr(self) -> np.ndarray:
+        if getattr(self, "_indptr_host", None) is None:
+            self._indptr_host = self._device_csr().indptr.cpu().numpy()
+        return self._indptr_host
 
     # ---- posterior regularisation (posterior.py:332-378) ----------------------------------------------------
     def regularize_posterior(self, regularization, **kwargs) -> sp.coo_matrix:

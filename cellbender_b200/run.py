@@ -122,3 +122,57 @@ def run_inference(dataset_obj, args, device: Optional[str] = None, total_epochs_
                      final_elbo_fail_fraction=args.final_elbo_fail_fraction, learning_rate=args.learning_rate)
         logger.info("Inference procedure complete.")
     return model, scheduler, train_loader, test_loader
+
+
+def compute_output_denoised_counts(posterior, args, fpr_list=None):
+    """The estimation half of ``compute_output_denoised_counts_reports_metrics`` (run.py:228-330) without the file
+    writers / report: estimator choice (:253-286), MCKP per-gene targets from the Mean estimator at each FPR
+    (posterior.py:1589-1650), ``Posterior.compute_denoised_counts`` and ``restore_eliminated_features_in_cells``.
+    Returns {fpr: scipy CSC [all barcodes, all genes]}."""
+    from .estimation import (MAP, Mean, MultipleChoiceKnapsack, SingleSample, ThresholdCDF,
+                             compute_mean_target_removal_as_function)
+    from .sparse_utils import csr_set_rows_to_zero
+
+    posterior.cell_noise_count_posterior_coo()
+    ds = posterior.dataset_obj
+    noise_target_fun = None
+    estimators = {"map": MAP, "mean": Mean, "sample": SingleSample, "cdf": ThresholdCDF, "mckp": MultipleChoiceKnapsack}
+    if args.estimator not in estimators:
+        raise ValueError('Input --estimator must be one of ["map", "mean", "sample", "cdf", "mckp"]')
+    estimator = estimators[args.estimator]
+    if args.estimator == "mckp":
+        logger.info("Computing target noise counts per gene for MCKP estimator")
+        count_matrix = ds.matrix  # all barcodes
+        cell_inds = np.asarray(ds.analyzed_barcode_inds)[posterior.latents_map["p"] > consts.CELL_PROB_CUTOFF]
+        empty_inds = np.setdiff1d(np.arange(count_matrix.shape[0]), cell_inds)
+        cell_counts = csr_set_rows_to_zero(csr=count_matrix, row_inds=empty_inds)
+        # the device-resident COO (same entries as the scipy one, already (m, c)-sorted) feeds the estimators directly
+        coo = posterior._device_posterior if posterior._device_posterior is not None else posterior._noise_count_posterior_coo
+        per_cell = compute_mean_target_removal_as_function(
+            noise_count_posterior_coo=coo, noise_offsets=posterior._noise_count_posterior_coo_offsets,
+            index_converter=posterior.index_converter, raw_count_csr_for_cells=cell_counts, n_cells=len(cell_inds),
+            device=posterior.device, per_gene=True)
+        noise_target_fun = lambda x: per_cell(x) * len(cell_inds)
+    out = {}
+    for fpr in (fpr_list if fpr_list is not None else args.fpr):
+        noise_targets = noise_target_fun(fpr).detach().cpu().numpy() if noise_target_fun is not None else None
+        denoised = posterior.compute_denoised_counts(
+            estimator_constructor=estimator, noise_targets_per_gene=noise_targets, q=getattr(args, "cdf_threshold_q", 0.5),
+            alpha=getattr(args, "prq_alpha", 1.0), device=posterior.device, use_multiple_processes=False)
+        denoised = ds.restore_eliminated_features_in_cells(denoised, posterior.latents_map["p"])
+        assert np.all(denoised.data >= 0), "Negative count matrix entries in output"
+        out[fpr] = denoised
+    return out
+
+
+def run_remove_background(dataset_obj, args, device: Optional[str] = None):
+    """``run_remove_background`` from the prepared dataset on (run.py:126-168, 228-330): inference, posterior, denoised
+    counts per FPR.  File output, report and checkpoint tarballs stay with the caller.  Returns (posterior, {fpr: csc})."""
+    from .posterior import Posterior
+
+    model, _, _, _ = run_inference(dataset_obj, args, device=device)
+    model.eval()
+    posterior = Posterior(dataset_obj=dataset_obj, vi_model=model, posterior_batch_size=args.posterior_batch_size,
+                          debug=getattr(args, "debug", False))
+    denoised = compute_output_denoised_counts(posterior, args)
+    return posterior, denoised

@@ -133,6 +133,60 @@ def simulate_dataset(n_genes: int = 1000, cells_of_each_type: List[int] = (334, 
             "chi": chi_types.cpu().numpy(), "n_cells": n_cells}
 
 
+def simulate_dataset_host(n_genes: int = 1000, cells_of_each_type: List[int] = (334, 333, 333), n_droplets: int = 10000,
+                          cell_mean_umi: float = 5000.0, cell_lognormal_sigma: float = 0.2, empty_mean_umi: float = 200.0,
+                          empty_lognormal_sigma: float = 0.4, dirichlet_alpha: float = 0.05, alpha0: float = 5000.0,
+                          epsilon_param: float = 100.0, rho_alpha: float = 3.0, rho_beta: float = 80.0,
+                          seed: int = 0) -> Dict[str, Any]:
+    """The same Dirichlet-Poisson 'full'-model recipe, dense on the host with ONE ``np.random.RandomState(seed)`` stream
+    (legacy numpy generators are bit-reproducible across machines, torch's device generators are not): the datasets of
+    the end-to-end parity fixtures (tests/golden/e2e_*.npz) are regenerated from the seed on the GPU box and must equal
+    what the golden run saw in the build container.  Small shapes only (two dense [n_droplets, n_genes] arrays).
+    Additionally returns the true / background count matrices."""
+    rng = np.random.RandomState(seed)
+    G, n_types, n_cells = n_genes, len(cells_of_each_type), int(sum(cells_of_each_type))
+    assert n_droplets > n_cells
+    chi_types = rng.dirichlet(np.full(G, dirichlet_alpha), size=n_types)
+    chi_ambient = (chi_types * (np.asarray(cells_of_each_type, dtype=np.float64) * cell_mean_umi)[:, None]).sum(0)
+    chi_ambient = chi_ambient / chi_ambient.sum()
+    c_real = np.zeros((n_droplets, G), dtype=np.int64)
+    c_bkg = np.zeros((n_droplets, G), dtype=np.int64)
+    labels = np.zeros(n_droplets, dtype=np.int64)
+
+    def latents(n):
+        eps = rng.gamma(shape=epsilon_param, scale=1.0 / epsilon_param, size=n)
+        v = rng.lognormal(mean=np.log(empty_mean_umi), sigma=empty_lognormal_sigma, size=n)
+        return eps, v, rng.beta(a=rho_alpha, b=rho_beta, size=n)
+
+    row = 0
+    for t, n in enumerate(cells_of_each_type):
+        chi = rng.dirichlet(chi_types[t] * alpha0 + 1e-20, size=n)
+        eps, v, rho = latents(n)
+        d = rng.lognormal(mean=np.log(cell_mean_umi), sigma=cell_lognormal_sigma, size=n)
+        c_real[row:row + n] = rng.poisson(((1 - rho) * eps * d)[:, None] * chi)
+        c_bkg[row:row + n] = rng.poisson((eps * ((1 - rho) * v + rho * (d + v)))[:, None] * chi_ambient[None, :])
+        labels[row:row + n] = t + 1
+        row += n
+    eps, v, rho = latents(n_droplets - row)
+    c_bkg[row:] = rng.poisson((eps * v)[:, None] * chi_ambient[None, :])  # y = 0: lambda = eps * v * chi_ambient
+    matrix = sp.csr_matrix((c_real + c_bkg).astype(np.float32))
+    return {"matrix": matrix, "chi_ambient": chi_ambient, "droplet_labels": labels, "chi": chi_types, "n_cells": n_cells,
+            "counts_true": sp.csr_matrix(c_real), "counts_bkg": sp.csr_matrix(c_bkg)}
+
+
+def dataset_checksum(matrix: sp.csr_matrix) -> int:
+    """Order-sensitive 64-bit checksum of a canonical CSR matrix (fixture guard: same data here and on the GPU box)."""
+    m = sp.csr_matrix(matrix)
+    m.sum_duplicates()
+    m.sort_indices()
+    acc = np.uint64(1469598103934665603)
+    with np.errstate(over="ignore"):
+        for arr in (m.indptr.astype(np.uint64), m.indices.astype(np.uint64), m.data.astype(np.int64).astype(np.uint64)):
+            w = (np.arange(arr.size, dtype=np.uint64) * np.uint64(2654435761) + np.uint64(40503))
+            acc = acc * np.uint64(1099511628211) + np.uint64((arr * w).sum(dtype=np.uint64))
+    return int(acc)
+
+
 def prepare_dataset(sim: Dict[str, Any], expected_cells: int, total_droplets_included: int,
                     low_count_threshold: int = 5, fraction_empties: float = 0.2) -> PreparedDataset:
     """Barcode trimming and priors as the reference computes them when --expected-cells and
@@ -174,7 +228,8 @@ def prepare_dataset(sim: Dict[str, Any], expected_cells: int, total_droplets_inc
     return PreparedDataset(matrix=matrix, analyzed_barcode_inds=np.asarray(analyzed), empty_barcode_inds=np.asarray(empties),
                            analyzed_gene_inds=np.arange(matrix.shape[1]), priors=priors,
                            empty_UMI_threshold=empty_UMI_threshold,
-                           truth={k: sim[k] for k in ("chi_ambient", "droplet_labels", "n_cells")})
+                           truth={k: sim[k] for k in ("chi_ambient", "droplet_labels", "n_cells", "counts_true", "counts_bkg")
+                                  if k in sim})
 
 
 CONFIGS = {
@@ -187,8 +242,9 @@ CONFIGS = {
 }
 
 
-def make_config_dataset(name: str, seed: int = 0, device: Optional[str] = None) -> PreparedDataset:
+def make_config_dataset(name: str, seed: int = 0, device: Optional[str] = None, host: bool = False) -> PreparedDataset:
+    """``host=True``: machine-independent numpy generation (small shapes; the end-to-end parity fixtures)."""
     cfg = dict(CONFIGS[name])
     expected_cells, total = cfg.pop("expected_cells"), cfg.pop("total_droplets")
-    sim = simulate_dataset(seed=seed, device=device, **cfg)
+    sim = simulate_dataset_host(seed=seed, **cfg) if host else simulate_dataset(seed=seed, device=device, **cfg)
     return prepare_dataset(sim, expected_cells, total)

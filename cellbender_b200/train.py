@@ -73,9 +73,9 @@ class SVI:
         self.optim.zero_grad()
         terms = self.loss_terms(batch)
         loss = terms["loss"]
-        # single GPU: the large weight matrices are updated inside their weight-gradient GEMMs (optim.fused_dw)
+        # single GPU: the ClippedAdam sweep of each large weight block is issued right behind its weight-gradient GEMM
         fuse = ((self.after_backward is None or self.dp_overlap) and self.model.training
-                and (self.optim.fuse_weight_updates or getattr(self.optim, "early_weight_updates", False)))
+                and getattr(self.optim, "early_weight_updates", False))
         gemm.FUSED_OPT = self.optim if fuse else None
         try:
             loss.backward()

@@ -80,7 +80,6 @@ int cb_elbo_obs_fwd_bwd(const long long* indptr, const int* indices, const float
                         const float* chi_bar, const float* coef, const float* alpha, const float* w, float* sums,
                         float* dlogits, float* qamb, long long ldq, float* lse_out, int* nan_flag, void* stream);
 int cb_colsum_rows(const float* in, int n_rows, int n_cols, long long ld, float* out, void* stream);
-int cb_row_logsumexp(const float* in, int n_rows, int n_cols, long long ld, float* lse, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * A4  self.dropout50(self.batchnorm0(x)) of EncodeNonZLatents.forward (vae/encoder.py:239,279), forward + backward.
@@ -135,7 +134,8 @@ int cb_obs_small_grads(const float* sums, int ld_sums, const float* w, const flo
  *   C[M, N] (=, +=) A[M, K] * B[N, K]^T (+ bias[N])
  * a_mn / b_mn = 0: operand stored [M|N rows, K cols] (K-major, the nn.Linear forward case);
  *             = 1: operand stored [K rows, M|N cols] (what dW = dY^T X and dX = dY W see, no transposes in memory).
- * lda / ldb multiples of 4 and 16-byte aligned bases (TMA); out-of-range rows/cols are zero-filled.
+ * lda / ldb / ldc multiples of 4 and 16-byte aligned bases (TMA loads and TMA stores); out-of-range rows/cols are
+ * zero-filled on load and clipped on store; accumulate uses the TMA unit's element-wise reduce-add.
  * split_k > 1 streams K across CTAs (skinny M): partial tiles in `workspace`
  * (cb_gemm_tf32_workspace_elems floats), summed in a fixed order.                                            */
 long long cb_gemm_tf32_workspace_elems(int M, int N, int split_k);
@@ -149,13 +149,17 @@ int cb_gemm_tf32_pair(const float* A, long long lda, const float* B, long long l
 int cb_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* C,
                  long long ldc, int M, int N, int K, const float* bias, int accumulate, int split_k, float* workspace,
                  long long workspace_elems, void* stream);
-/* Weight-gradient product with the optimizer step fused into its epilogue (train.py:56-60 after loss.backward()):
- * G = A B^T is never stored; param / exp_avg / exp_avg_sq ([M, ldc], indexed like the gradient would be) receive the
- * ClippedAdam update of cb_clipped_adam_step with the lr / beta1 of step *step_ptr (read, not advanced).          */
-int cb_gemm_tf32_dw_adam(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, long long ldc,
-                         int M, int N, int K, float* param, float* exp_avg, float* exp_avg_sq, const float* lr_table,
-                         const float* beta1_table, long long table_len, const long long* step_ptr, float beta2, float eps,
-                         float clip, void* stream);
+/* The same product with an explicit tile configuration (tuning / benchmarking): tile_cfg 0 = heuristic, 1 = 256 x 128
+ * tile, 2-stage ring, two CTAs per SM; 2 = 256 x 128 deep ring; 3 = 256 x 256 deep ring; 4 / 5 = 128 x 256 (2-stage / deep);
+ * 6 / 7 = 128 x 128 (2-stage / deep).  K2 = 0: single operand pair.                                                */
+int cb_gemm_tf32_ex(const float* A, long long lda, const float* B, long long ldb, int K, const float* A2,
+                    long long lda2, const float* B2, long long ldb2, int K2, int a_mn, int b_mn, float* C,
+                    long long ldc, int M, int N, const float* bias, int accumulate, int split_k, float* workspace,
+                    long long workspace_elems, int tile_cfg, void* stream);
+/* Weight gradient of the hand-made feature columns of Linear(cat(feat, x)) (vae/encoder.py:283-298, autograd of
+ * layer1 / layer2 / eps_network.0): dw[h, f] = sum_b dy[b, h] feat[b, f] into the first n_feat columns of dw [n_out, ldw]. */
+int cb_feat_dw(const float* dy, long long ldy, const float* feat, int n_feat, int n_rows, int n_out, float* dw,
+               long long ldw, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * A4(tail)+A9  the per-droplet latent algebra of RemoveBackgroundPyroModel.model / .guide (model.py:232-445, 447-574),
@@ -222,14 +226,11 @@ int cb_simplex_backward(int n, const float* y, const float* grad_y, float* grad_
 int cb_clipped_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
                          const float* beta1_table, long long table_len, long long* step_ptr, float beta2, float eps,
                          float clip, float grad_scale, void* stream);
-/* the same update on one contiguous range (step counter advanced only if advance != 0; n = 0 allowed) and on a
- * [rows, cols] sub-block of a [rows, ld] matrix: the parts of the flat buffer NOT covered by cb_gemm_tf32_dw_adam.  */
+/* the same update on one contiguous range (step counter advanced only if advance != 0; n = 0 allowed): the sweep of one
+ * large weight block right behind its weight-gradient product, and of the ranges between such blocks.              */
 int cb_clipped_adam_range(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
                           const float* beta1_table, long long table_len, long long* step_ptr, float beta2, float eps,
                           float clip, int advance, void* stream);
-int cb_clipped_adam_2d(float* p, const float* g, float* m, float* v, int rows, int cols, long long ld, const float* lr_table,
-                       const float* beta1_table, long long table_len, const long long* step_ptr, float beta2, float eps,
-                       float clip, void* stream);
 /* Data-parallel exchange fused into the optimizer sweep (new surface, the reference is single-GPU): ClippedAdam on
  * this rank's contiguous shard, reading the shard's gradient from every rank's gradient buffer (peer memory over
  * NVLink, summed in rank order) and storing the updated parameters into every rank's parameter buffer.
@@ -253,21 +254,34 @@ int cb_clipped_adam_nvls(float* p, float* m, float* v, long long n, const float*
  * _get_cell_noise_count_posterior_coo (posterior.py:528-576), dense_to_sparse_op_torch (sparse_utils.py:10-33),
  * IndexConverter.get_m_indices (posterior.py:1554-1575).
  *   cell_rows[n_cells]     CSR rows of the cells (p > 0.5) of this chunk
- *   logits[n_samples*n_cells, ldl], lse[n_samples*n_cells]   decoder output per latent sample (row = s*n_cells + b)
- *   a_mu/c_a/c_b [n_samples*n_cells], alpha[n_samples]   mu = a_mu*chi, lam = c_a*chi_ambient + c_b*chi_bar
- *   n_window[n_cells]      n = min(n_counts_max, max count of the cell's reference minibatch) (posterior.py:816)
- *   entry_start[n_cells+1] exclusive prefix of the cells' stored-count numbers
- *   logp_out[n_entries, stride], low_out[n_entries], keep_cnt[n_entries]; stride = cb_posterior_window_stride() */
+ *   logits_t[n_genes, ldt] decoder output of the chunk, TRANSPOSED and cell-major: logits_t[g, b * n_samples + s]
+ *                          (cb_gemm_tf32 with A = decoder weight, B = hidden activations; bias NOT included);
+ *   dec_bias[n_genes]      decoder output bias (may be NULL);  lse[n_cells * n_samples] = cb_col_logsumexp(logits_t, dec_bias)
+ *   a_mu/c_a/c_b [n_cells * n_samples] (index b * n_samples + s), alpha[n_samples]:
+ *                          mu = a_mu * chi, lam = c_a * chi_ambient + c_b * chi_bar
+ *   n_window[n_cells]      min(n_counts_max, max count of the reference minibatch of the cell) (posterior.py:816)
+ *   entry_start[n_cells+1] prefix sums of the cells' stored-count numbers; n_entries = entry_start[n_cells]
+ *   barcode_all[n_cells] / gene_all[n_genes]  indices into the full count matrix (IndexConverter, posterior.py:1554-1575)
+ * outputs, one row per stored count in (cell, gene) order:
+ *   logp_out[n_entries, stride] (stride = cb_posterior_window_stride()), low_out, keep_cnt, entry_m[n_entries]
+ * cb_posterior_offset_flags: flag[i] = keep_cnt[i] > 0 && low[i] != 0 (entries that carry a noise-count offset).
+ * cb_posterior_compact: thresholded COO triplets + (m, offset) pairs from exclusive scans of keep_cnt / flag.      */
 int cb_posterior_window_stride(int n_counts_max);
 int cb_posterior_noise_window(const long long* indptr, const int* indices, const float* data, const long long* cell_rows,
-                              int n_cells, int n_genes, int n_samples, const float* logits, long long ldl,
-                              const float* lse, const float* chi_ambient, const float* chi_bar, const float* a_mu,
-                              const float* c_a, const float* c_b, const float* alpha, const int* n_window,
-                              const long long* entry_start, int n_counts_max, float log_thresh, float lambda_multiplier,
-                              float* logp_out, int* low_out, int* keep_cnt, void* stream);
-int cb_posterior_entry_index(const long long* indptr, const int* indices, const long long* cell_rows, int n_cells,
-                             const long long* barcode_all, const long long* gene_all, long long total_n_genes,
-                             const long long* entry_start, long long* entry_m, void* stream);
+                              int n_cells, int n_genes, int n_samples, const float* logits_t, long long ldt,
+                              const float* dec_bias, const float* lse, const float* chi_ambient, const float* chi_bar,
+                              const float* a_mu, const float* c_a, const float* c_b, const float* alpha,
+                              const int* n_window, const long long* entry_start, long long n_entries,
+                              const long long* barcode_all, const long long* gene_all, long long total_n_genes,
+                              int n_counts_max, float log_thresh, float lambda_multiplier, float* logp_out, int* low_out,
+                              int* keep_cnt, long long* entry_m, void* stream);
+int cb_posterior_offset_flags(long long n_entries, const int* keep_cnt, const int* low, int* flag, void* stream);
+/* out[c] = log sum_r exp(in[r, c] + row_add[r]) over an [n_rows, ld] matrix (row_add may be NULL): the softmax
+ * denominators of Decoder.forward (vae/decoder.py:46-47) for the transposed logits of a posterior chunk.
+ * scratch: cb_col_logsumexp_scratch_elems(n_rows, n_cols) floats.                                                   */
+long long cb_col_logsumexp_scratch_elems(int n_rows, int n_cols);
+int cb_col_logsumexp(const float* in, int n_rows, int n_cols, long long ld, const float* row_add, float* scratch,
+                     float* out, void* stream);
 int cb_posterior_compact(long long n_entries, int n_counts_max, const long long* entry_m, const float* logp,
                          const int* low, const int* keep_cnt, const long long* keep_pos, const long long* off_pos,
                          float log_thresh, long long* coo_m, int* coo_c, float* coo_lp, long long* off_m, int* off_v,

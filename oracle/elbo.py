@@ -112,12 +112,13 @@ def _masked_median(values, mask):
 
 def elbo(x: torch.Tensor, params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor], cfg: Dict, noise: Dict,
          row_keep_scale: Optional[torch.Tensor], training: bool, likelihood: str = "reference",
-         model_type: str = "full") -> Dict[str, torch.Tensor]:
+         model_type: str = "full", update_bn: bool = False) -> Dict[str, torch.Tensor]:
     """All ELBO terms for the dense minibatch ``x`` [B, G].
 
     params: 'enc_z.*', 'enc_o.*', 'dec.*' (reference state_dict keys) and 'ps.<name>' = UNCONSTRAINED pyro params.
     buffers: BatchNorm running statistics under the same prefixes.  cfg: priors and encoder constants.
-    noise: see draw_noise.  Returns the terms (same names as cellbender_b200.model.elbo_terms) and 'loss' = -ELBO."""
+    noise: see draw_noise.  update_bn: training mode also updates the BatchNorm running statistics in ``buffers``
+    (the buffers of ``sub(...)`` views are the same tensors).  Returns the terms (same names as cellbender_b200.model.elbo_terms) and 'loss' = -ELBO."""
     dt = x.dtype
     sd = {**params, **buffers}
     ps = {k[3:]: transform_to(CONSTRAINTS[k[3:]])(v) for k, v in params.items() if k.startswith("ps.")}
@@ -138,7 +139,8 @@ def elbo(x: torch.Tensor, params: Dict[str, torch.Tensor], buffers: Dict[str, to
     enc = ovae.encode_nonz(x, chi_ambient.detach(), zz["loc"].detach(), sub("enc_o."), d_empty_loc=ps["d_empty_loc"].detach(),
                            log_count_crossover=cfg["log_count_crossover"], prior_log_cell_counts=cfg["prior_log_cell_counts"],
                            empty_log_count_threshold=cfg["empty_log_count_threshold"], offset=cfg["offset"],
-                           training=training, row_keep_scale=row_keep_scale)
+                           training=training, row_keep_scale=row_keep_scale,
+                           bn_momentum=0.1 if (update_bn and training) else None)  # nn.BatchNorm1d default momentum
     p_y = enc["p_y"]
     v = p_y + P_LOGIT_SCALE * noise["p_logit_reg"]
     z = zz["loc"] + zz["scale"] * noise["z"]
@@ -153,7 +155,8 @@ def elbo(x: torch.Tensor, params: Dict[str, torch.Tensor], buffers: Dict[str, to
     q1, q0 = log_q1.exp(), log_q0.exp()
 
     # ---------------- model (model.py:232-445), y in {0, 1} enumerated ----------------
-    chi = ovae.decode(z, sub("dec."), training=training)
+    chi = ovae.decode(z, sub("dec."), training=training,
+                      bn_momentum=0.01 if (update_bn and training) else None)  # vae/base.py:71 momentum=0.01
     counts = x.sum(-1)
     t: Dict[str, torch.Tensor] = {}
     t["phi"] = Gamma(c(cfg["phi_conc_prior"]), c(cfg["phi_rate_prior"])).log_prob(phi) - Gamma(phi_conc, phi_rate).log_prob(phi)

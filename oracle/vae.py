@@ -34,14 +34,21 @@ def transform_input(x, transform: Optional[str], eps: float = 1e-5):
     raise NotImplementedError(transform)
 
 
-def batch_norm(x, sd: Dict[str, torch.Tensor], prefix: str, training: bool, eps: float = 1e-5):
+def batch_norm(x, sd: Dict[str, torch.Tensor], prefix: str, training: bool, eps: float = 1e-5,
+               momentum: Optional[float] = None):
     """nn.BatchNorm1d forward: batch statistics (biased variance) in training, running
-    statistics in eval.  Running-stat updates are not modelled (they do not affect the
-    forward value of the same step)."""
+    statistics in eval.  ``momentum`` (training only): also update the running statistics in
+    place as torch does (running = (1 - m) running + m batch, UNBIASED batch variance); None
+    leaves them alone (they do not affect the forward value of the same step)."""
     w, b = sd[prefix + ".weight"], sd[prefix + ".bias"]
     if training:
         mean = x.mean(dim=0)
         var = x.var(dim=0, unbiased=False)
+        if momentum is not None:
+            with torch.no_grad():
+                n = x.shape[0]
+                sd[prefix + ".running_mean"].mul_(1 - momentum).add_(momentum * mean.detach())
+                sd[prefix + ".running_var"].mul_(1 - momentum).add_(momentum * var.detach() * (n / max(n - 1, 1)))
     else:
         mean, var = sd[prefix + ".running_mean"], sd[prefix + ".running_var"]
     return (x - mean) / torch.sqrt(var + eps) * w + b
@@ -58,7 +65,8 @@ def encode_z(x, sd: Dict[str, torch.Tensor], prefix: str = ""):
 
 def encode_nonz(x, chi_ambient, z_loc, sd: Dict[str, torch.Tensor], *, d_empty_loc, log_count_crossover: float,
                 prior_log_cell_counts: float, empty_log_count_threshold: float, offset: Dict[str, float],
-                training: bool, row_keep_scale: Optional[torch.Tensor] = None, prefix: str = ""):
+                training: bool, row_keep_scale: Optional[torch.Tensor] = None, prefix: str = "",
+                bn_momentum: Optional[float] = None):
     """EncodeNonZLatents.forward (encoder.py:241-340) with input_transform='log_normalize'.
 
     ``row_keep_scale`` [B] is the Dropout1d(0.5) realisation for 2-D input: 0 for a
@@ -75,7 +83,7 @@ def encode_nonz(x, chi_ambient, z_loc, sd: Dict[str, torch.Tensor], *, d_empty_l
     eps_overlap = (x_amb_norm * x).sum(dim=-1, keepdim=True)
 
     xt = transform_input(x, "log_normalize")
-    x_in = batch_norm(xt, sd, prefix + "batchnorm0", training)
+    x_in = batch_norm(xt, sd, prefix + "batchnorm0", training, momentum=bn_momentum)
     if training and row_keep_scale is not None:
         x_in = x_in * row_keep_scale.unsqueeze(-1)
     znorm = torch.linalg.vector_norm(z_loc, ord=2, dim=-1, keepdim=True)
@@ -85,12 +93,12 @@ def encode_nonz(x, chi_ambient, z_loc, sd: Dict[str, torch.Tensor], *, d_empty_l
     def lin(name, inp):
         return F.linear(inp, sd[prefix + name + ".weight"], sd[prefix + name + ".bias"])
 
-    h = F.softplus(batch_norm(lin("layer1", torch.cat((p_feat, x_in), -1)), sd, prefix + "batchnorm1", training))
-    h = F.softplus(batch_norm(lin("layer2", torch.cat((p_feat, h), -1)), sd, prefix + "batchnorm2", training))
+    h = F.softplus(batch_norm(lin("layer1", torch.cat((p_feat, x_in), -1)), sd, prefix + "batchnorm1", training, momentum=bn_momentum))
+    h = F.softplus(batch_norm(lin("layer2", torch.cat((p_feat, h), -1)), sd, prefix + "batchnorm2", training, momentum=bn_momentum))
     p_out = lin("layer3", torch.cat((p_feat, h), -1)).squeeze(-1)
 
-    e = F.softplus(batch_norm(lin("eps_network.0", torch.cat((e_feat, x_in), -1)), sd, prefix + "eps_network.1", training))
-    e = F.softplus(batch_norm(lin("eps_network.3", e), sd, prefix + "eps_network.4", training))
+    e = F.softplus(batch_norm(lin("eps_network.0", torch.cat((e_feat, x_in), -1)), sd, prefix + "eps_network.1", training, momentum=bn_momentum))
+    e = F.softplus(batch_norm(lin("eps_network.3", e), sd, prefix + "eps_network.4", training, momentum=bn_momentum))
     eps_out = lin("eps_network.6", e).squeeze(-1)
 
     ls = log_sum.squeeze(-1)
@@ -117,9 +125,10 @@ def first_forward_offsets(p_out, eps_out, log_sum, log_count_crossover: float) -
     return {"logit_p": float(p_out.mean()), "epsilon": float(eps_out[cells].mean())}
 
 
-def decode(z, sd: Dict[str, torch.Tensor], training: bool, prefix: str = "", return_logits: bool = False):
+def decode(z, sd: Dict[str, torch.Tensor], training: bool, prefix: str = "", return_logits: bool = False,
+           bn_momentum: Optional[float] = None):
     """Decoder with hidden_dims=[H]: Linear(Z->H)+BatchNorm1d(H, eps=1e-3)+ReLU, Linear(H->G), softmax."""
     h = F.linear(z, sd[prefix + "network.0.layer.0.weight"], sd[prefix + "network.0.layer.0.bias"])
-    h = F.relu(batch_norm(h, sd, prefix + "network.0.layer.1", training, eps=1e-3))
+    h = F.relu(batch_norm(h, sd, prefix + "network.0.layer.1", training, eps=1e-3, momentum=bn_momentum))
     logits = F.linear(h, sd[prefix + "network.1.layer.0.weight"], sd[prefix + "network.1.layer.0.bias"])
     return logits if return_logits else torch.softmax(logits, dim=-1)

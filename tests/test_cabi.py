@@ -44,4 +44,4 @@ def test_ops_refuse_cpu_tensors(built):
     from cellbender_b200 import ops
 
     with pytest.raises(RuntimeError):
-        ops.row_logsumexp(torch.zeros(2, 4), 4)
+        ops.col_logsumexp(torch.zeros(4, 4), 4, 4)

@@ -14,7 +14,7 @@ def _tf32_trunc(t):
     return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
 
 
-def _check(M, N, K, a_mn, b_mn, split_k=None, bias=False, accumulate=False, seed=0):
+def _check(M, N, K, a_mn, b_mn, split_k=None, bias=False, accumulate=False, seed=0, tile_cfg=0):
     from cellbender_b200 import ops
 
     g = torch.Generator(device=DEV).manual_seed(seed)
@@ -26,7 +26,8 @@ def _check(M, N, K, a_mn, b_mn, split_k=None, bias=False, accumulate=False, seed
     bias_t = torch.randn(N, device=DEV, generator=g) if bias else None
     out = torch.full((M, ld(N)), 7.0, device=DEV)
     c0 = out[:, :N].clone()
-    ops.gemm_tf32(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, out=out[:, :N], bias=bias_t, accumulate=accumulate, split_k=split_k)
+    ops.gemm_tf32(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, out=out[:, :N], bias=bias_t, accumulate=accumulate, split_k=split_k,
+                  tile_cfg=tile_cfg)
     torch.cuda.synchronize()
     extra = (bias_t.double() if bias else 0) + (c0.double() if accumulate else 0)
     ref_trunc = _tf32_trunc(Al.contiguous()).double() @ _tf32_trunc(Bl.contiguous()).double().t() + extra
@@ -53,14 +54,14 @@ def test_gemm_split_k_bias_accumulate(split_k):
     _check(255, 130, 999, False, False, split_k=1, bias=True, accumulate=True)
 
 
-def test_gemm_cluster_multicast_variant(monkeypatch):
-    """CB_GEMM_CLUSTER=1: the split-K products with four column tiles run as four-CTA clusters with the A tile TMA
-    multicast; same results as the default kernel (both major orders of B, bias, accumulate, ragged K)."""
-    monkeypatch.setenv("CB_GEMM_CLUSTER", "1")
-    _check(255, 512, 5000, False, False, split_k=7, bias=True)
-    _check(255, 512, 5000, False, True, split_k=7, bias=True, accumulate=True)
-    _check(200, 400, 33538, False, False, bias=True)
-    _check(255, 512, 33538, False, True)
+@pytest.mark.parametrize("tile_cfg", [1, 2, 3, 4, 5, 6, 7])
+def test_gemm_every_tile_configuration(tile_cfg):
+    """cb_gemm_tf32_ex: every tile configuration (256 x 128 / 256 x 256 / 128 x 256 / 128 x 128, 2-stage double-CTA and deep
+    rings) gives the same product, with bias, accumulation (TMA reduce-add), split-K and ragged edges (TMA-store clipping)."""
+    _check(255, 512, 1000, False, False, split_k=1, bias=True, tile_cfg=tile_cfg)
+    _check(255, 1030, 255, True, True, split_k=1, tile_cfg=tile_cfg)
+    _check(200, 333, 999, False, True, split_k=3, bias=True, accumulate=True, tile_cfg=tile_cfg)
+    _check(300, 77, 333, True, False, split_k=1, accumulate=True, tile_cfg=tile_cfg)
 
 
 def test_gemm_training_step_shapes():
@@ -90,45 +91,30 @@ def test_gemm_two_operand_pairs_share_the_accumulator():
     assert float((out[:, :G].double() - ref).abs().max()) / float(ref.abs().max()) < 2e-5
 
 
-@pytest.mark.parametrize("M,N,off", [(512, 256, 4), (256, 512, 0), (512, 33538, 4), (33538, 512, 0), (300, 250, 0)])
-def test_weight_gradient_gemm_with_fused_clipped_adam(M, N, off):
-    """cb_gemm_tf32_dw_adam: W[:, off:off+N] -= Adam(dY^T X) inside the GEMM epilogue must equal the unfused sequence
-    (cb_gemm_tf32 into a gradient buffer, then cb_clipped_adam_step over it), element for element; columns outside
-    [off, off + N) and the padding stay untouched."""
-    from cellbender_b200 import _cabi, ops
+def test_gemm_rejects_operands_tma_cannot_address():
+    """No library fallback: an output / operand with a row pitch that is not a multiple of 16 bytes is an error."""
+    from cellbender_b200 import _cabi, gemm, ops
 
-    K = 255
-    g = torch.Generator(device=DEV).manual_seed(M + N)
-    ld = ops.round_up(off + N, 4)
-    dy = torch.randn(K, ops.round_up(M, 4), device=DEV, generator=g)
-    x = torch.randn(K, ops.round_up(N, 4), device=DEV, generator=g)
-    p0 = torch.randn(M, ld, device=DEV, generator=g)
-    m0 = torch.randn(M, ld, device=DEV, generator=g) * 0.1
-    v0 = torch.rand(M, ld, device=DEV, generator=g) * 0.01
-    lr_table = torch.tensor([1e-3, 2e-3, 3e-3], device=DEV)
-    b1_table = torch.tensor([0.95, 0.9, 0.85], device=DEV)
-    step = torch.tensor([1], dtype=torch.int64, device=DEV)
+    a = torch.randn(64, 33, device=DEV)
+    b = torch.randn(64, 33, device=DEV)
+    with pytest.raises((AssertionError, _cabi.CabiError)):
+        ops.gemm_tf32(a, b, 64, 64, 33)
+    lin = torch.nn.Linear(33, 64).to(DEV)
+    with pytest.raises(RuntimeError, match="TMA"):
+        gemm.linear_big(a, lin, n_in=33)
+    big = torch.nn.Linear(33538 + 4, 512).to(DEV)
+    gemm.pad_big_weights(big)
+    assert big.weight.stride(0) % 4 == 0 and big.weight.shape == (512, 33542)
 
-    # unfused reference: gradient to memory, then the flat Adam sweep over the [M, N] block (row by row)
-    grad = torch.zeros(M, ld, device=DEV)
-    ops.gemm_tf32(dy, x, M, N, K, a_mn=True, b_mn=True, out=grad[:, off:off + N], split_k=1)
-    p_ref, m_ref, v_ref = p0.clone(), m0.clone(), v0.clone()
-    pr, mr, vr, gr = (t[:, off:off + N].contiguous().reshape(-1) for t in (p_ref, m_ref, v_ref, grad))
-    step_ref = step.clone()
-    ops.clipped_adam_step(pr, gr, mr, vr, lr_table, b1_table, step_ref, beta2=0.999, eps=1e-8, clip=10.0)
-    for dst, src in ((p_ref, pr), (m_ref, mr), (v_ref, vr)):
-        dst[:, off:off + N] = src.view(M, N)
 
-    p, m, v = p0.clone(), m0.clone(), v0.clone()
-    byte = 4 * off
-    _cabi.lib().call("cb_gemm_tf32_dw_adam", dy.data_ptr(), dy.stride(0), 1, x.data_ptr(), x.stride(0), 1, ld, M, N, K,
-                     p.data_ptr() + byte, m.data_ptr() + byte, v.data_ptr() + byte, lr_table.data_ptr(), b1_table.data_ptr(), 3,
-                     step.data_ptr(), 0.999, 1e-8, 10.0, _cabi.current_stream())
-    torch.cuda.synchronize()
-    assert int(step) == 1  # read, not advanced
-    for got, ref, name in ((p, p_ref, "param"), (m, m_ref, "exp_avg"), (v, v_ref, "exp_avg_sq")):
-        diff = (got - ref).abs()
-        bad = int((diff > 1e-6 * (1 + ref.abs())).sum())
-        rows_bad = torch.nonzero((diff > 1e-6 * (1 + ref.abs())).any(dim=1)).flatten()[:8].tolist()
-        assert bad == 0, (name, bad, float(diff.max()), rows_bad)
-    assert float((p - p0).abs().max()) > 0
+def test_feat_dw_matches_matmul():
+    from cellbender_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(11)
+    dy = torch.randn(255, 512, device=DEV, generator=g)
+    feat = torch.randn(255, 4, device=DEV, generator=g)
+    dw = torch.full((512, 36), 7.0, device=DEV)
+    ops.feat_dw(dy, feat, dw)
+    ref = (dy.double().t() @ feat.double()).float()
+    torch.testing.assert_close(dw[:, :4], ref, rtol=1e-5, atol=1e-4)
+    assert float((dw[:, 4:] - 7.0).abs().max()) == 0.0

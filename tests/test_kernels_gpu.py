@@ -220,8 +220,12 @@ def test_exclusive_scan_and_colsum_and_lse(ops):
     m[:, :1001] = torch.randn(37, 1001, device=DEV)
     np.testing.assert_allclose(ops.colsum_rows(m, 1001).cpu().numpy(), m[:, :1001].double().sum(0).cpu().numpy(),
                                rtol=1e-5, atol=1e-5)
-    np.testing.assert_allclose(ops.row_logsumexp(m, 1001).cpu().numpy(),
-                               torch.logsumexp(m[:, :1001].double(), -1).cpu().numpy(), rtol=1e-6, atol=1e-6)
+    add = torch.randn(37, device=DEV)
+    np.testing.assert_allclose(ops.col_logsumexp(m, 37, 1001, row_add=add).cpu().numpy(),
+                               torch.logsumexp(m[:, :1001].double() + add.double()[:, None], 0).cpu().numpy(), rtol=1e-6, atol=1e-6)
+    big = torch.randn(5000, 300, device=DEV) * 3
+    np.testing.assert_allclose(ops.col_logsumexp(big, 5000, 300).cpu().numpy(),
+                               torch.logsumexp(big.double(), 0).cpu().numpy(), rtol=1e-6, atol=1e-6)
 
 
 def test_clipped_adam_matches_per_tensor_reference(ops):
@@ -410,18 +414,22 @@ def test_posterior_coo_vs_dense_oracle(ops, scale, n_max):
         pdf = lp if s == 1 else torch.logaddexp(pdf + np.log(1 - 1 / s), lp + np.log(1 / s))
     n_i, g_i, c_i, lp_i, off_i = opost.sparsify_posterior(pdf, low, data, -10.0)
     m_ref = opost.m_index(barcode_all[n_i.numpy()], gene_all[g_i.numpy()], G_all)
-    # device
+    # device: transposed, cell-major logits [G, Bc * S] (column b * S + s), decoder bias passed separately
     d = ops.DeviceCSR.from_scipy(sp.csr_matrix(data.numpy().astype(np.float32)), DEV)
-    lg = ops.alloc_rows(S * Bc, G, DEV)
-    lg[:, :G] = torch.tensor(logits)
-    lse = ops.row_logsumexp(lg, G)
-    n_win = int(min(n_max, data.max().item()))
+    bias = (rng.normal(size=G) * 0.5).astype(np.float32)
+    cm = lambda v: np.ascontiguousarray(np.asarray(v).reshape(S, Bc).T).reshape(-1)  # sample-major [S * Bc] -> cell-major [Bc * S]
+    lt = ops.alloc_rows(G, Bc * S, DEV)
+    lt[:, :Bc * S] = torch.tensor(np.ascontiguousarray((logits - bias[None, :]).reshape(S, Bc, G).transpose(2, 1, 0)).reshape(G, Bc * S))
     t = lambda a, dt=torch.float32: torch.as_tensor(a, dtype=dt, device=DEV)
-    ld = lg.shape[1]
+    lse = ops.col_logsumexp(lt, G, Bc * S, row_add=t(bias))
+    lse_ref = torch.logsumexp(torch.tensor(logits, dtype=torch.float64), -1).numpy()
+    np.testing.assert_allclose(lse.cpu().numpy(), cm(lse_ref), rtol=2e-6, atol=2e-6)
+    n_win = int(min(n_max, data.max().item()))
+    ld = ops.round_up(G, 4)
     ca, cb = torch.zeros(ld, device=DEV), torch.zeros(ld, device=DEV)
     ca[:G], cb[:G] = t(chi_a), t(chi_b)
     m, c, lp, off_m, off_v = ops.posterior_coo(
-        d, torch.arange(Bc, device=DEV), lg, lse, ca, cb, t(a_mu), t(c_a), t(c_b), t(alpha),
+        d, torch.arange(Bc, device=DEV), lt, t(bias), lse, ca, cb, t(cm(a_mu)), t(cm(c_a)), t(cm(c_b)), t(alpha),
         torch.full((Bc,), n_win, dtype=torch.int32, device=DEV), t(barcode_all, torch.int64), t(gene_all, torch.int64),
         G_all, n_counts_max=n_max)
     m, c, lp = m.cpu().numpy(), c.cpu().numpy(), lp.cpu().numpy()
@@ -746,17 +754,15 @@ def test_prmu_matches_reference_golden(ops, golden_dir, tag, per_gene, fpr):
 
 
 # ---------------------------------------------------------------------------------------------- fused P2P Adam
-@pytest.mark.parametrize("bulk", ["1", "0"])
 @pytest.mark.parametrize("n_ranks,own", [(1, 0), (2, 0), (2, 1), (3, 1), (4, 3), (8, 5), (16, 0)])
-def test_clipped_adam_p2p_matches_sum_then_sweep(ops, monkeypatch, n_ranks, own, bulk):
+def test_clipped_adam_p2p_matches_sum_then_sweep(ops, n_ranks, own):
     """cb_clipped_adam_p2p on ONE device (the 'peer' buffers are local allocations): gradients of all ranks summed in
     rank order + ClippedAdam on the shard + parameter stores into every peer buffer must equal sum -> cb_clipped_adam_range
-    -> copy; both the TMA bulk-prefetch kernel and the plain-load kernel; ragged last tile; step counter advanced."""
+    -> copy (TMA bulk prefetch of the peers' gradient tiles); ragged last tile; step counter advanced."""
     import ctypes
 
     from cellbender_b200 import _cabi
 
-    monkeypatch.setenv("CB_P2P_BULK", bulk)
     g = torch.Generator(device=DEV).manual_seed(n_ranks * 17 + own)
     n_total, a = 4 * (256 * 37 + 13) + 64, 64  # the shard starts 64 elements into the buffers
     n = n_total - a

@@ -12,43 +12,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _small_dataset(seed=0, n_genes=96):
-    from cellbender_b200 import synth
-
-    sim = synth.simulate_dataset(n_genes=n_genes, cells_of_each_type=[25, 25], n_droplets=600, cell_mean_umi=2000.0,
-                                 empty_mean_umi=60.0, dirichlet_alpha=0.5, seed=seed, device="cpu", cell_chunk=64)
-    return synth.prepare_dataset(sim, expected_cells=50, total_droplets_included=150)
-
-
-def _setup(model_type="full", epochs=3):
-    from cellbender_b200 import run
-
-    ds = _small_dataset()
-    args = run.default_args(epochs=epochs, z_dim=8, z_hidden_dims=[32], model=model_type)
-    model, opt, svi, train_loader, test_loader = run.setup_inference(ds, args, device=DEV)
-    return ds, args, model, opt, svi, train_loader, test_loader
-
-
-def _oracle_inputs(model, offset):
-    params, buffers = {}, {}
-    for pre, mod in (("enc_z.", model.encoder["z"]), ("enc_o.", model.encoder["other"]), ("dec.", model.decoder)):
-        for k, v in mod.named_parameters():
-            params[pre + k] = v.detach().double().cpu().clone().requires_grad_(True)
-        for k, v in mod.named_buffers():
-            buffers[pre + k] = v.detach().double().cpu().clone()
-    for k, v in model.param_store.unconstrained.items():
-        params["ps." + k] = v.detach().double().cpu().clone().requires_grad_(True)
-    enc_o = model.encoder["other"]
-    cfg = dict(chi_bar=model.avg_gene_expression.double().cpu(), log_count_crossover=enc_o.log_count_crossover,
-               prior_log_cell_counts=float(enc_o.prior_log_cell_counts),
-               empty_log_count_threshold=float(enc_o.empty_log_count_threshold), offset=offset,
-               d_cell_loc_prior=float(model.d_cell_loc_prior), d_cell_scale_prior=float(model.d_cell_scale_prior),
-               epsilon_prior=float(model.epsilon_prior), phi_conc_prior=float(model.phi_conc_prior),
-               phi_rate_prior=float(model.phi_rate_prior), rho_alpha_prior=float(model.rho_alpha_prior),
-               rho_beta_prior=float(model.rho_beta_prior), d_empty_loc_prior=float(model.d_empty_loc_prior),
-               d_empty_scale_prior=float(model.d_empty_scale_prior), empty_UMI_threshold=float(model.empty_UMI_threshold),
-               p_logit_prior=float(model.p_logit_prior))
-    return params, buffers, cfg
+from _helpers import _oracle_inputs, _setup, _small_dataset  # noqa: E402,F401
 
 
 def _grad_of(p):
@@ -69,38 +33,28 @@ def _product_param_grads(model):
     return out
 
 
-@pytest.fixture(autouse=True)
-def _default_backend():
-    from cellbender_b200 import gemm
-
-    yield
-    gemm.set_backend("tcgen05")
+@pytest.mark.parametrize("training", [True, False])
+def test_elbo_terms_and_gradients_match_oracle(training, fp32_gemm):
+    """fp32 library GEMMs substituted from the test side (the reference's arithmetic) + the hand-written kernels: 1e-5 on
+    every term."""
+    _elbo_parity(training, rtol_terms=1e-5, rtol_grads=2e-3)
 
 
 @pytest.mark.parametrize("training", [True, False])
-def test_elbo_terms_and_gradients_match_oracle(training):
-    """fp32 library GEMMs (the reference's arithmetic) + the hand-written kernels: 1e-5 on every term."""
-    _elbo_parity(training, backend="cublas", rtol_terms=1e-5, rtol_grads=2e-3)
-
-
-@pytest.mark.parametrize("training", [True, False])
-def test_elbo_tf32_backend_tolerance(training):
-    """Same comparison with the tcgen05 TF32 GEMMs: stated tolerance 2e-3 relative on the ELBO terms (TF32 keeps 10
-    mantissa bits in the four large contractions), 3e-2 of scale on gradients."""
-    _elbo_parity(training, backend="tcgen05", rtol_terms=2e-3, rtol_grads=3e-2)
+def test_elbo_tf32_tolerance(training):
+    """Same comparison with the product as shipped (tcgen05 TF32 GEMMs): stated tolerance 2e-3 relative on the ELBO terms
+    (TF32 keeps 10 mantissa bits in the large contractions), 3e-2 of scale on gradients."""
+    _elbo_parity(training, rtol_terms=2e-3, rtol_grads=3e-2)
 
 
 @pytest.mark.parametrize("model_type", ["ambient", "swapping"])
-def test_elbo_other_model_types_match_oracle(model_type):
+def test_elbo_other_model_types_match_oracle(model_type, fp32_gemm):
     """The rate mixtures of calculate_mu / calculate_lambda for --model ambient and swapping (model.py:25-85): same
     term-by-term and gradient-by-gradient comparison as for the default 'full' model."""
-    _elbo_parity(True, backend="cublas", rtol_terms=1e-5, rtol_grads=2e-3, model_type=model_type)
+    _elbo_parity(True, rtol_terms=1e-5, rtol_grads=2e-3, model_type=model_type)
 
 
-def _elbo_parity(training, backend, rtol_terms, rtol_grads, model_type="full"):
-    from cellbender_b200 import gemm
-
-    gemm.set_backend(backend)
+def _elbo_parity(training, rtol_terms, rtol_grads, model_type="full"):
     ds, args, model, opt, svi, train_loader, _ = _setup(model_type)
     batch = next(iter(train_loader))
     model.train()
@@ -221,12 +175,10 @@ def test_training_improves_elbo_graph_and_eager_agree_statistically():
     assert abs(finals[True] - finals[False]) < 0.15 * abs(finals[False])
 
 
-@pytest.mark.parametrize("mode", ["early", "fused"])
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_fused_weight_update_equals_separate_adam(use_graph, mode):
+def test_early_weight_update_equals_separate_adam(use_graph):
     """Single-GPU training sweeps the ClippedAdam update of each large weight matrix as soon as its gradient GEMM has
-    finished, overlapping the rest of backward ('early': optim.early_block_update, the default), or applies it inside
-    the epilogue of that GEMM ('fused': cb_gemm_tf32_dw_adam).  Same seed, same data: parameters and both moment buffers
+    finished, overlapping the rest of backward (optim.early_block_update).  Same seed, same data: parameters and both moment buffers
     must equal those of the plain path (every gradient to HBM, one Adam sweep over the whole flat buffer at the end).  Compared after the first
     steps: biases that feed a BatchNorm have a mathematically zero gradient, Adam normalises their rounding noise to
     O(lr) steps, so later on the two runs drift apart in exactly those (irrelevant) parameters -- as any two runs do."""
@@ -243,8 +195,7 @@ def test_fused_weight_update_equals_separate_adam(use_graph, mode):
             ds = synth.prepare_dataset(sim, expected_cells=80, total_droplets_included=300)
             args = run.default_args(epochs=5, z_dim=16, z_hidden_dims=[512], learning_rate=1e-3, use_cuda_graph=use_graph)
             model, opt, svi, tl, _ = run.setup_inference(ds, args, device=DEV)
-            opt.fuse_weight_updates = fuse and mode == "fused"
-            opt.early_weight_updates = fuse and mode == "early"
+            opt.early_weight_updates = fuse
             blocks = [p for p in opt.params if getattr(p, "_cb_block", None) is not None]
             assert len(blocks) >= 4  # the G x 512 matrices (and the 512 x 516 / 512 x 512 hidden layers) qualify
             model.train()

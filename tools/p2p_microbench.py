@@ -1,5 +1,5 @@
 """Single-process NVLink microbenchmark of cb_clipped_adam_p2p on two GPUs (peer buffers on cuda:1, kernel on cuda:0):
-DMA copy rate, remote-read-only, remote-write-only and both, plain-load vs TMA-bulk kernel.  Diagnostics for dp.p2p_step."""
+DMA copy rate, remote-read-only, remote-write-only and both.  Diagnostics for dp.p2p_step."""
 import ctypes
 import os
 import sys
@@ -57,11 +57,8 @@ def run(grads, peers):
     return timed(fn)
 
 
-for bulk in ("1", "0"):
-    os.environ["CB_P2P_BULK"] = bulk
-    print(f"--- CB_P2P_BULK={bulk}")
-    print(f"local only             : {run([g], []):.4f} ms")
-    print(f"local + local 2nd grad : {run([g, x0], []):.4f} ms")
-    print(f"remote grad read       : {run([g, x1], []):.4f} ms")
-    print(f"remote param write     : {run([g], [y1]):.4f} ms")
-    print(f"remote read + write    : {run([g, x1], [y1]):.4f} ms")
+print(f"local only             : {run([g], []):.4f} ms")
+print(f"local + local 2nd grad : {run([g, x0], []):.4f} ms")
+print(f"remote grad read       : {run([g, x1], []):.4f} ms")
+print(f"remote param write     : {run([g], [y1]):.4f} ms")
+print(f"remote read + write    : {run([g, x1], [y1]):.4f} ms")

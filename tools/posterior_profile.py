@@ -1,0 +1,67 @@
+"""Run the posterior pass (encoder once per chunk, S latent samples, decoder GEMM, noise-count window, COO) on the first
+``--cells`` droplets of the PBMC8k-shape synthetic dataset with a randomly initialised model.  Used under
+`ncu --metrics gpu__time_duration.sum` for the launch list of the posterior phase (profiles/), and stand-alone for
+CUDA-event timings of the phase.
+
+    python tools/posterior_profile.py --cells 2048 --reps 3
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cells", type=int, default=2048)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--workload", default="pbmc8k")
+    ap.add_argument("--estimators", action="store_true")
+    a = ap.parse_args()
+    import torch
+
+    from cellbender_b200 import run, synth
+    from cellbender_b200.posterior import Posterior
+
+    dev = "cuda:0"
+    ds = synth.make_config_dataset(a.workload, seed=0, device=dev)
+    model = run.build_model(ds, run.default_args(), device=dev)
+    model.eval()
+    model.encoder["other"].offset = {"logit_p": 0.0, "epsilon": 0.0}
+    post = Posterior(ds, model, posterior_batch_size=128)
+    n_all = int(ds.analyzed_barcode_inds.size)
+    n_cells = min(a.cells, n_all)
+    post._latents = {"p": np.concatenate([np.ones(n_cells), np.zeros(n_all - n_cells)]), "z": None, "d": None,
+                     "epsilon": None, "phi_loc_scale": None}
+    post.device_posterior(cell_subset=np.arange(min(128, n_cells)))
+    torch.cuda.synchronize()
+    for _ in range(a.reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dp_ = post.device_posterior()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        print(f"posterior: {n_cells} cells, {int(dp_.m.numel())} COO entries, {dt * 1e3:.2f} ms, {n_cells / dt:.0f} droplets/s",
+              flush=True)
+    if a.estimators:
+        from cellbender_b200.estimation import Mean, MultipleChoiceKnapsack
+
+        conv = post.index_converter
+        for _ in range(2):
+            t0 = time.perf_counter()
+            mean_csr = Mean(index_converter=conv).estimate_noise(dp_, None, device=dev)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            tgt = np.asarray(mean_csr.sum(axis=0)).ravel().astype(np.float64)
+            noise = MultipleChoiceKnapsack(index_converter=conv).estimate_noise(dp_, None, noise_targets_per_gene=tgt, device=dev)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            print(f"Mean {1e3 * (t1 - t0):.1f} ms, MCKP {1e3 * (t2 - t1):.1f} ms, removed {int(noise.sum())}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
