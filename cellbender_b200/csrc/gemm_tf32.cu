@@ -408,7 +408,16 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   return launch_cfg<MT, BN, A_MN, B_MN, kDeep, 1>(ta, tb, ta2, tb2, tc, p, st);
 }
 
-static int tile_heuristic(int M, int N, const GemmParams& p) {
+// Measured on B200 (tools/gemm_bench.py, profiles/r02_gemm_bench.txt; PBMC8k shapes, L2 flushed):
+//   dW = dY^T X (M = 512, N = G, K = 255)      256x256 deep 36.9 us | 256x128 s2x2 39.0 | 256x128 deep 44.0
+//   dX pair (M = 255, N = G, K = 2 x 512)      256x256 deep 48.1 us | 256x128 s2x2 51.1
+//   dWd = dlogits^T h (M = G, N = 512, K = 255) 128x256 s2x2 32.8 us | 256x128 s2x2 34.8
+//   decoder forward (M = 255, N = G, K = 512)  256x128 s2x2 33.8 us | 256x256 deep 36.9
+// The 256-wide tiles win where the small operand (dY, 0.5-1 MB) is re-read from L2 by every column tile: they halve that
+// traffic; the K-major forward products prefer two co-resident CTAs per SM.
+static int tile_heuristic(int M, int N, const GemmParams& p, bool a_mn, bool b_mn, bool pair) {
+  if (M > 128 && N >= 4096 && p.split_k == 1 && (a_mn || pair)) return k2x256_deep;
+  if (a_mn && b_mn && M >= 4096 && N >= 256 && p.split_k == 1 && p.k_blocks_per_split <= 16) return k1x256_s2;
   const bool two = M > 128;
   const bool wide = (!two) && N >= 256;
   // short K: two co-resident CTAs per SM with a 2-stage ring each (one CTA's epilogue overlaps the other's loads) -- but
@@ -493,7 +502,7 @@ static int gemm_tf32_impl(const float* A, long long lda, const float* B, long lo
     CB_REQUIRE(e == 0, "cb_gemm_tf32: cuTensorMapEncodeTiled failed for B2 (code %d)", e);
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (tile_cfg == kAuto) tile_cfg = tile_heuristic(M, N, p);
+  if (tile_cfg == kAuto) tile_cfg = tile_heuristic(M, N, p, a_mn != 0, b_mn != 0, K2 > 0);
   CB_REQUIRE(tile_cfg >= k2x128_s2 && tile_cfg <= k1x128_deep, "cb_gemm_tf32_ex: tile_cfg=%d not in [0, 7]", tile_cfg);
   const bool deep = tile_cfg == k2x128_deep || tile_cfg == k2x256_deep || tile_cfg == k1x256_deep || tile_cfg == k1x128_deep;
   int rc = 0;

@@ -91,6 +91,16 @@ def pad_big_weights(module: torch.nn.Module, min_numel: int = 1 << 16):
     return module
 
 
+class LazyFeat:
+    """Place-holder for the hand-made feature block of Linear(cat(feat, x)) when the gene-wide product is launched before
+    the features exist (they need EncodeZ's output): the forward product then covers the gene block only, ``bn_act`` adds
+    the feature term, and the backward pass (which runs long after ``value`` has been set) computes the feature columns
+    of the weight gradient as usual."""
+
+    def __init__(self):
+        self.value: Optional[torch.Tensor] = None
+
+
 class _MultiLinearBig(torch.autograd.Function):
     """Several nn.Linear layers that read the SAME wide input x (EncodeNonZLatents' layer1 and eps_network.0, or the
     single EncodeZ input layer):
@@ -99,12 +109,23 @@ class _MultiLinearBig(torch.autograd.Function):
     add pass over [B, G]) and every dW_i lands directly in the optimizer's flat gradient buffer."""
 
     @staticmethod
-    def forward(ctx, x, n_in: int, col_offset: int, *args):
+    def forward(ctx, x, n_in: int, col_offset: int, streams, *args):
         feats, weights, biases = args[0::3], args[1::3], args[2::3]
         B = x.shape[0]
         ys = []
-        for feat, w, b in zip(feats, weights, biases):
-            if feat is not None:
+        main = torch.cuda.current_stream()
+        for i, (feat, w, b) in enumerate(zip(feats, weights, biases)):
+            st = streams[i] if streams is not None else None
+            if st is not None:  # this product runs on its own stream (the caller joins it before consuming the output)
+                y = torch.empty((B, ops.round_up(w.shape[0], 4)), dtype=torch.float32, device=x.device)[:, :w.shape[0]]
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    assert feat is None or isinstance(feat, LazyFeat)
+                    ops.gemm_tf32(x, w[:, col_offset:col_offset + n_in], B, w.shape[0], n_in, bias=b, out=y)
+                y.record_stream(st), x.record_stream(st)
+            elif isinstance(feat, LazyFeat):
+                y = ops.gemm_tf32(x, w[:, col_offset:col_offset + n_in], B, w.shape[0], n_in, bias=b)
+            elif feat is not None:
                 # Linear(cat(feat, x)): the few feature columns ride along as a second operand pair (one extra k-block)
                 if not (col_offset % 4 == 0 and feat.is_contiguous() and feat.shape[1] == col_offset):
                     raise RuntimeError("multi_linear_big: the feature block must be contiguous [B, col_offset] with col_offset % 4 == 0")
@@ -113,6 +134,8 @@ class _MultiLinearBig(torch.autograd.Function):
             else:
                 y = ops.gemm_tf32(x, w[:, col_offset:col_offset + n_in], B, w.shape[0], n_in, bias=b)
             ys.append(y)
+        ctx.lazy = [f if isinstance(f, LazyFeat) else None for f in feats]
+        feats = [None if isinstance(f, LazyFeat) else f for f in feats]
         ctx.save_for_backward(x, *[t for t in feats if t is not None], *weights)
         ctx.meta = (len(weights), n_in, col_offset, [f is not None for f in feats], [b is not None for b in biases])
         ctx.biases = biases  # the nn.Parameter objects (they carry the optimizer's gradient views)
@@ -125,6 +148,7 @@ class _MultiLinearBig(torch.autograd.Function):
         saved = list(ctx.saved_tensors)
         x = saved.pop(0)
         feats = [saved.pop(0) if h else None for h in has_feat]
+        feats = [lz.value if lz is not None else f for f, lz in zip(feats, ctx.lazy)]
         weights = saved
         weights_p = ctx.weights_p
         B = x.shape[0]
@@ -135,8 +159,8 @@ class _MultiLinearBig(torch.autograd.Function):
         targets = []
         for i in range(n):
             w = weights[i]
-            dw_t = _grad_target(weights_p[i]) if ctx.needs_input_grad[3 + 3 * i + 1] else None
-            db_t = _grad_target(ctx.biases[i]) if (has_bias[i] and ctx.needs_input_grad[3 + 3 * i + 2]) else None
+            dw_t = _grad_target(weights_p[i]) if ctx.needs_input_grad[4 + 3 * i + 1] else None
+            db_t = _grad_target(ctx.biases[i]) if (has_bias[i] and ctx.needs_input_grad[4 + 3 * i + 2]) else None
             targets.append((dw_t, db_t))
 
         def parameter_gradients():
@@ -148,6 +172,8 @@ class _MultiLinearBig(torch.autograd.Function):
                     # dW[H, n_in] = dy^T[H, B] . x[B, n_in]: both operands stored with the reduction dim (B) as rows
                     ops.gemm_tf32(dy, x, H, n_in, B, a_mn=True, b_mn=True, out=dw_t[0][:, off:off + n_in], split_k=1)
                     if off:  # the few feature columns in front of the gene block
+                        if feat is None:
+                            raise RuntimeError("multi_linear_big: a Linear with feature columns was differentiated without its features")
                         ops.feat_dw(dy, feat, dw_t[0])
                 if db_t is not None:
                     ops.colsum_rows(dy, H, out=db_t[0])
@@ -190,7 +216,7 @@ class _MultiLinearBig(torch.autograd.Function):
                     FUSED_OPT.early_block_update(weights_p[i])
         grads = []
         for i in range(n):
-            if feats[i] is not None and ctx.needs_input_grad[3 + 3 * i]:
+            if feats[i] is not None and ctx.lazy[i] is None and ctx.needs_input_grad[4 + 3 * i]:
                 raise RuntimeError("multi_linear_big: the hand-made feature block is data (vae/encoder.py:250-287); it has no gradient")
             grads += [None, targets[i][0][1] if targets[i][0] is not None else None,
                       targets[i][1][1] if targets[i][1] is not None else None]
@@ -202,14 +228,16 @@ class _MultiLinearBig(torch.autograd.Function):
                 defer_join(side)
             else:
                 main.wait_stream(side)
-        return (dx, None, None, *grads)
+        return (dx, None, None, None, *grads)
 
 
-def multi_linear_big(x: torch.Tensor, layers, n_in: int, col_offset: int = 0, bias_grad_elsewhere: bool = False):
-    """``layers`` = [(nn.Linear, feat or None), ...] applied to the same wide input x; returns a tuple of outputs.
-    x may carry padding columns beyond n_in (16-byte-aligned rows from the gather / BN kernels).
+def multi_linear_big(x: torch.Tensor, layers, n_in: int, col_offset: int = 0, bias_grad_elsewhere: bool = False,
+                     streams=None):
+    """``layers`` = [(nn.Linear, feat or LazyFeat or None), ...] applied to the same wide input x; returns a tuple of
+    outputs.  x may carry padding columns beyond n_in (16-byte-aligned rows from the gather / BN kernels).
     ``bias_grad_elsewhere``: the layer feeds ``bn_act`` which also produces the Linear bias gradient (the column sums
-    of its input gradient), so no separate reduction over dy is launched here."""
+    of its input gradient), so no separate reduction over dy is launched here.
+    ``streams``: one CUDA stream (or None) per layer on which its forward product is issued."""
     _require_tma(x, "the input activations")
     args = []
     for lin, feat in layers:
@@ -218,7 +246,7 @@ def multi_linear_big(x: torch.Tensor, layers, n_in: int, col_offset: int = 0, bi
         if bias is not None and bias_grad_elsewhere and torch.is_grad_enabled():
             bias = bias.detach()
         args += [feat, lin.weight, bias]
-    return _MultiLinearBig.apply(x, n_in, col_offset, *args)
+    return _MultiLinearBig.apply(x, n_in, col_offset, streams, *args)
 
 
 def linear_big(x: torch.Tensor, lin: torch.nn.Linear, n_in: int, col_offset: int = 0, feat: Optional[torch.Tensor] = None,
@@ -274,17 +302,22 @@ class _BNAct(torch.autograd.Function):
     written straight into the optimizer's flat gradient buffer."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, bn, act: int, training: bool, bias):
+    def forward(ctx, x, gamma, beta, bn, act: int, training: bool, bias, feat, feat_weight):
         B, N = x.shape
         if x.stride(1) != 1:
+            if feat is not None:
+                raise RuntimeError("bn_act: the feature term is written back into x, which must have unit column stride")
             x = x.contiguous()
         y = torch.empty((B, N), dtype=torch.float32, device=x.device)
         mean = torch.empty(N, dtype=torch.float32, device=x.device)
         rstd = torch.empty(N, dtype=torch.float32, device=x.device)
         momentum = bn.momentum if bn.momentum is not None else 0.1
+        n_feat = 0 if feat is None else feat.shape[1]
         lib().call("cb_bn_act_forward", ptr(x), x.stride(0), B, N, ptr(gamma), ptr(beta), ptr(bn.running_mean),
                    ptr(bn.running_var), ptr(bn.num_batches_tracked) if training else None, int(training), float(momentum),
-                   float(bn.eps), act, ptr(y), y.stride(0), ptr(mean), ptr(rstd), current_stream())
+                   float(bn.eps), act, ptr(y), y.stride(0), ptr(mean), ptr(rstd), ptr(feat), n_feat,
+                   ptr(feat_weight) if feat is not None else None, feat_weight.stride(0) if feat is not None else 0,
+                   current_stream())
         ctx.save_for_backward(x, mean, rstd)
         ctx.params = (gamma, beta, bias)
         ctx.meta = (act, training)
@@ -309,14 +342,20 @@ class _BNAct(torch.autograd.Function):
         lib().call("cb_bn_act_backward", ptr(x), x.stride(0), ptr(dy), dy.stride(0), B, N, ptr(gamma), ptr(beta), ptr(mean),
                    ptr(rstd), int(training), act, ptr(dx), dx.stride(0), ptr(dg_buf), ptr(db_buf), ptr(dbias_buf),
                    current_stream())
-        return dx, dg, db, None, None, None, None
+        return dx, dg, db, None, None, None, None, None, None
 
 
 def bn_act(x: torch.Tensor, bn: torch.nn.BatchNorm1d, act: Optional[str], training: bool,
-           bias_of: Optional[torch.nn.Linear] = None) -> torch.Tensor:
+           bias_of: Optional[torch.nn.Linear] = None, feat: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``act(bn(x))`` in one kernel each way.  ``bias_of``: the nn.Linear that produced ``x`` when its bias gradient
-    should come out of this op's backward (pair with ``bias_grad_elsewhere=True`` on that layer)."""
+    should come out of this op's backward (pair with ``bias_grad_elsewhere=True`` on that layer).
+    ``feat`` [B, F]: x was produced WITHOUT the first F (feature) input columns of ``bias_of`` (multi_linear_big with a
+    LazyFeat); their contribution feat @ bias_of.weight[:, :F]^T is added here, in place, before the normalisation."""
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):
         raise RuntimeError("cellbender_b200 ops require 2-D fp32 CUDA tensors (no CPU fallback)")
     bias = bias_of.bias if (bias_of is not None and bias_of.bias is not None and torch.is_grad_enabled()) else None
-    return _BNAct.apply(x, bn.weight, bn.bias, bn, ACT_CODE[act], training, bias)
+    fw = None
+    if feat is not None:
+        assert bias_of is not None and feat.is_contiguous() and feat.shape[1] <= 8
+        fw = bias_of.weight.detach()
+    return _BNAct.apply(x, bn.weight, bn.bias, bn, ACT_CODE[act], training, bias, feat, fw)

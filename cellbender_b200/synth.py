@@ -188,9 +188,12 @@ def dataset_checksum(matrix: sp.csr_matrix) -> int:
 
 
 def prepare_dataset(sim: Dict[str, Any], expected_cells: int, total_droplets_included: int,
-                    low_count_threshold: int = 5, fraction_empties: float = 0.2) -> PreparedDataset:
+                    low_count_threshold: int = 5, fraction_empties: float = 0.2,
+                    analyzed_barcode_inds: Optional[np.ndarray] = None,
+                    empty_barcode_inds: Optional[np.ndarray] = None) -> PreparedDataset:
     """Barcode trimming and priors as the reference computes them when --expected-cells and
-    --total-droplets-included are supplied."""
+    --total-droplets-included are supplied.  ``analyzed_barcode_inds`` / ``empty_barcode_inds`` pin the barcode selection
+    (fixtures: the order of equal UMI counts under an unstable argsort is not portable across CPUs)."""
     matrix: sp.csr_matrix = sim["matrix"].tocsr()
     umi = np.asarray(matrix.sum(axis=1)).ravel()
     order = np.argsort(umi)[::-1]
@@ -225,11 +228,37 @@ def prepare_dataset(sim: Dict[str, Any], expected_cells: int, total_droplets_inc
     priors["chi_ambient"] = torch.tensor(amb / amb.sum()).float()
     bar = np.asarray(matrix.sum(axis=0)).ravel() + ep
     priors["chi_bar"] = torch.tensor(bar / bar.sum()).float()
+    if analyzed_barcode_inds is not None:
+        analyzed, empties = np.asarray(analyzed_barcode_inds, dtype=np.int64), np.asarray(empty_barcode_inds, dtype=np.int64)
     return PreparedDataset(matrix=matrix, analyzed_barcode_inds=np.asarray(analyzed), empty_barcode_inds=np.asarray(empties),
                            analyzed_gene_inds=np.arange(matrix.shape[1]), priors=priors,
                            empty_UMI_threshold=empty_UMI_threshold,
-                           truth={k: sim[k] for k in ("chi_ambient", "droplet_labels", "n_cells", "counts_true", "counts_bkg")
-                                  if k in sim})
+                           truth={k: sim[k] for k in ("chi_ambient", "droplet_labels", "n_cells", "counts_true", "counts_bkg",
+                                                        "bkg_per_droplet") if k in sim})
+
+
+def save_fixture_dataset(path: str, ds: PreparedDataset, expected_cells: int, total_droplets: int):
+    """The raw count matrix + the barcode selection of a prepared (small) dataset as a compressed .npz fixture."""
+    m = sp.csr_matrix(ds.matrix)
+    m.sort_indices()
+    assert m.data.max() < 65536 and m.shape[1] < 32768
+    bkg = np.asarray(ds.truth["counts_bkg"].sum(axis=1)).ravel() if "counts_bkg" in ds.truth else np.zeros(m.shape[0])
+    np.savez_compressed(path, indptr=m.indptr.astype(np.int32), indices=m.indices.astype(np.int16), data=m.data.astype(np.uint16),
+                        shape=np.array(m.shape), analyzed_barcode_inds=np.asarray(ds.analyzed_barcode_inds).astype(np.int32),
+                        empty_barcode_inds=np.asarray(ds.empty_barcode_inds).astype(np.int32), bkg_per_droplet=bkg.astype(np.int32),
+                        expected_cells=np.array(expected_cells), total_droplets=np.array(total_droplets))
+
+
+def load_fixture_dataset(path: str) -> PreparedDataset:
+    """Inverse of save_fixture_dataset: priors are recomputed from the stored matrix (deterministic), the barcode
+    selection is the stored one."""
+    f = np.load(path)
+    matrix = sp.csr_matrix((f["data"].astype(np.float32), f["indices"].astype(np.int32), f["indptr"].astype(np.int64)),
+                           shape=tuple(int(v) for v in f["shape"]))
+    sim = {"matrix": matrix, "chi_ambient": None, "droplet_labels": None, "n_cells": int(f["expected_cells"]),
+           "bkg_per_droplet": f["bkg_per_droplet"].astype(np.int64)}
+    return prepare_dataset(sim, int(f["expected_cells"]), int(f["total_droplets"]),
+                           analyzed_barcode_inds=f["analyzed_barcode_inds"], empty_barcode_inds=f["empty_barcode_inds"])
 
 
 CONFIGS = {

@@ -220,51 +220,64 @@ class EncodeNonZLatents(nn.Module):
         G = self.n_genes
         d_empty_loc = self._d_empty_loc(z.device) if chi_ambient is not None else None
         inp = _as_inputs(x, G, chi_ambient, d_empty_loc)
-        # hand-made features (encoder.py:250-287): log1p(counts), log1p(nnz), overlap with the empty-droplet size /
-        # ambient dot product, ||z||_2 -- one kernel instead of ~15 elementwise launches
-        p_feat, e_feat = ops.encoder_features(inp.feats, z, d_empty_loc)
-        log_sum = p_feat[:, 0:1]
-
         # BatchNorm over genes + Dropout1d(0.5), which on a 2-D input drops whole droplet rows (torch 2.11):
         # one fused kernel (csrc/bn_act.cu) writing a 16-byte-row buffer the tensor-core GEMMs can read through TMA.
         B = inp.feats.shape[0]
         if x_in is None:
             x_in = self.normalize_input(inp, row_keep_scale)
         x_in, bn0_stream = x_in
-        if bn0_stream is not None:
-            torch.cuda.current_stream().wait_stream(bn0_stream)
-            x_in.record_stream(torch.cuda.current_stream())
-
-        # Linear(cat(feat, x_in)) of both towers: the large gene block through the tensor-core GEMM (shared input),
-        # the 4 feature columns as a rank-4 update
+        main = torch.cuda.current_stream()
         e = self.eps_network[0]
-        h1, he = multi_linear_big(x_in, [(self.layer1, p_feat), (e, e_feat)], n_in=G, col_offset=4, bias_grad_elsewhere=True)
+        eps_bn1, eps_lin2, eps_bn2, eps_lin3 = self.eps_network[1], self.eps_network[3], self.eps_network[4], self.eps_network[6]
+        fork = x_in.is_cuda and TOWER_STREAMS and bn0_stream is not None
+        lazy_p, lazy_e = gemm.LazyFeat(), gemm.LazyFeat()
+        if fork:
+            # The two G-wide products Linear(cat(feat, x_in)) of the towers need only batchnorm0's output for their gene
+            # block: they are issued right behind it, each on its own stream, while THIS stream computes the hand-made
+            # features (which need z, i.e. the tail of EncodeZ).  The feature columns join in bn_act (gemm.LazyFeat).
+            side_p, side_e = bn0_stream, ops.side_stream(x_in.device, 2)
+            bn0_done = torch.cuda.Event()
+            bn0_done.record(bn0_stream)
+            side_e.wait_event(bn0_done)
+            with torch.cuda.stream(bn0_stream):  # makes the node's "current stream" the one x_in lives on
+                h1, he = multi_linear_big(x_in, [(self.layer1, lazy_p), (e, lazy_e)], n_in=G, col_offset=4,
+                                          bias_grad_elsewhere=True, streams=[None, side_e])
+        # hand-made features (encoder.py:250-287): log1p(counts), log1p(nnz), overlap with the empty-droplet size /
+        # ambient dot product, ||z||_2 -- one kernel instead of ~15 elementwise launches
+        p_feat, e_feat = ops.encoder_features(inp.feats, z, d_empty_loc)
+        log_sum = p_feat[:, 0:1]
+        lazy_p.value, lazy_e.value = p_feat, e_feat
+        if not fork:
+            if bn0_stream is not None:
+                main.wait_stream(bn0_stream)
+                x_in.record_stream(main)
+            h1, he = multi_linear_big(x_in, [(self.layer1, lazy_p), (e, lazy_e)], n_in=G, col_offset=4, bias_grad_elsewhere=True)
+
         # The two towers are independent chains of small, latency-bound launches ([B, 512] tensors): the epsilon tower
         # runs on an auxiliary stream, the cell-probability tower on the calling one (parallel branches of the captured
-        # step graph; autograd replays each backward node on its forward stream).  Fork: the side stream first waits for
-        # everything issued so far; join: the calling stream waits for the side stream before eps_out is consumed.
-        eps_bn1, eps_lin2, eps_bn2, eps_lin3 = self.eps_network[1], self.eps_network[3], self.eps_network[4], self.eps_network[6]
-
+        # step graph; autograd replays each backward node on its forward stream).
         def eps_tower():
-            h = bn_act(he, eps_bn1, "softplus", self.training, bias_of=e)
+            h = bn_act(he, eps_bn1, "softplus", self.training, bias_of=e, feat=e_feat)
             h = linear_big(h, eps_lin2, n_in=h.shape[1], bias_grad_elsewhere=True)
             h = bn_act(h, eps_bn2, "softplus", self.training, bias_of=eps_lin2)
             return ops.head(h, eps_lin3)
 
-        fork = he.is_cuda and TOWER_STREAMS
         if fork:
-            main, side = torch.cuda.current_stream(), ops.side_stream(he.device, 2)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
+            feats_done = torch.cuda.Event()
+            feats_done.record(main)
+            side_e.wait_event(feats_done)
+            with torch.cuda.stream(side_e):
                 eps_out = eps_tower()
+            main.wait_stream(side_p)  # layer1's product
+            h1.record_stream(main), x_in.record_stream(main)
         # hidden layers: Linear (tensor-core GEMM + rank-4 feature update) -> fused BatchNorm + Softplus kernel
-        x_ = bn_act(h1, self.batchnorm1, "softplus", self.training, bias_of=self.layer1)
+        x_ = bn_act(h1, self.batchnorm1, "softplus", self.training, bias_of=self.layer1, feat=p_feat)
         h2 = linear_big(x_, self.layer2, n_in=x_.shape[1], col_offset=4, feat=p_feat, bias_grad_elsewhere=True)
         x_ = bn_act(h2, self.batchnorm2, "softplus", self.training, bias_of=self.layer2)
         p_out = ops.head(x_, self.layer3, p_feat)
         if fork:
-            main.wait_stream(side)
-            he.record_stream(side), e_feat.record_stream(side), eps_out.record_stream(main)
+            main.wait_stream(side_e)
+            he.record_stream(side_e), e_feat.record_stream(side_e), eps_out.record_stream(main)
         else:
             eps_out = eps_tower()
 

@@ -98,11 +98,14 @@ int cb_bn0_backward(const float* x, long long ldx, const float* dy, long long ld
  * FullyConnectedLayer BatchNorm1d(momentum 0.01, eps 1e-3) + ReLU (vae/base.py:66-79); forward and backward.
  * act: 0 identity, 1 softplus, 2 relu.  training = 1: minibatch statistics, running stats and *num_batches_tracked
  * (may be NULL) updated.  backward: dx [n_rows, lddx], dgamma, dbeta [n_cols]; dbias (may be NULL) = column sums of dx,
- * the gradient of the Linear bias that fed the BatchNorm.                                                       */
-int cb_bn_act_forward(const float* x, long long ldx, int n_rows, int n_cols, const float* gamma, const float* beta,
+ * the gradient of the Linear bias that fed the BatchNorm.
+ * feat[n_rows, n_feat] / feat_weight[n_cols, ldw] (may be NULL): the hand-made feature columns of Linear(cat(feat, x_in))
+ * (vae/encoder.py:283-298) enter here, x[r, c] += sum_f feat[r, f] * feat_weight[c, f] (written back to x), so that the
+ * gene-wide product that produced x need not wait for the features.                                             */
+int cb_bn_act_forward(float* x, long long ldx, int n_rows, int n_cols, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, long long* num_batches_tracked, int training,
                       float momentum, float eps, int act, float* y, long long ldy, float* save_mean, float* save_rstd,
-                      void* stream);
+                      const float* feat, int n_feat, const float* feat_weight, long long ldw, void* stream);
 int cb_bn_act_backward(const float* x, long long ldx, const float* dy, long long lddy, int n_rows, int n_cols,
                        const float* gamma, const float* beta, const float* save_mean, const float* save_rstd, int training,
                        int act, float* dx, long long lddx, float* dgamma, float* dbeta, float* dbias, void* stream);

@@ -36,7 +36,9 @@ def summarize(ds, p, noise_csr, denoised_csc):
     out = {"p": p.astype(np.float64), "n_cells": int(cells.sum()), "removed_total": float(removed_gene.sum()),
            "removed_per_gene": removed_gene, "removed_per_analyzed_droplet": removed_cell,
            "raw_total_in_cells": float(raw_cells.sum()), "denoised_total": float(denoised_csc.sum())}
-    if "counts_bkg" in ds.truth:
+    if "bkg_per_droplet" in ds.truth:
+        out["true_background_in_cells"] = float(np.asarray(ds.truth["bkg_per_droplet"])[cell_inds].sum())
+    elif "counts_bkg" in ds.truth:
         out["true_background_in_cells"] = float(ds.truth["counts_bkg"][cell_inds].sum())
     return out
 
@@ -50,6 +52,10 @@ def make_golden(a):
 
     torch.set_num_threads(os.cpu_count())
     ds = synth.make_config_dataset(a.config, seed=0, host=True)
+    # the dataset itself travels as a fixture: numpy's samplers are not bit-reproducible across CPUs (libm variants)
+    cfg = synth.CONFIGS[a.config]
+    synth.save_fixture_dataset(os.path.join(GOLDEN_DIR, f"e2e_{a.config}_dataset.npz"), ds, cfg["expected_cells"], cfg["total_droplets"])
+    ds = synth.load_fixture_dataset(os.path.join(GOLDEN_DIR, f"e2e_{a.config}_dataset.npz"))
     ref = None
     log_prob_fn = None
     if ref_shim.reference_available() and not a.no_reference:
@@ -102,7 +108,7 @@ def run_product(config: str, epochs: int, device: str = "cuda:0", fpr: float = 0
 
     from cellbender_b200 import run, synth
 
-    ds = synth.make_config_dataset(config, seed=0, host=True)
+    ds = synth.load_fixture_dataset(os.path.join(GOLDEN_DIR, f"e2e_{config}_dataset.npz"))
     args = run.default_args(epochs=epochs, fpr=[fpr])
     t0 = time.time()
     posterior, denoised = run.run_remove_background(ds, args, device=device)
@@ -119,7 +125,8 @@ def run_product(config: str, epochs: int, device: str = "cuda:0", fpr: float = 0
     noise = (sp.csr_matrix(sp.diags(keep.astype(ds.matrix.dtype)) @ ds.matrix) - den.tocsr()).tocsr()
     s = summarize(ds, p, noise, den)
     m = posterior.vi_model
-    s["scalars"] = {k: float(m.param_store[k].reshape(-1)[0]) for k in m.param_store.keys() if m.param_store[k].numel() == 1}
+    s["scalars"] = {k: float(m.param_store[k].detach().reshape(-1)[0]) for k in m.param_store.keys()
+                    if m.param_store[k].numel() == 1}
     s["chi_ambient"] = m.param_store["chi_ambient"].detach().double().cpu().numpy()
     s["train_loss_last"] = -m.loss["train"]["elbo"][-1]
     s["seconds"] = seconds
