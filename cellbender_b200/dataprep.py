@@ -90,6 +90,8 @@ class DataLoader:
         self._dev_ids = None
         self._gbuf = None
         self._count_only = False
+        self._max_batches: Optional[int] = None  # data parallel: every rank serves the same number of minibatches per epoch
+        self._served = 0
         self._reset()
 
     # -- device plumbing ---------------------------------------------------------------------------------
@@ -137,6 +139,13 @@ class DataLoader:
         if self.shuffle:
             np.random.shuffle(self.ind_list)
         self.ptr = 0
+        self._served = 0
+
+    def limit_batches(self, n: int):
+        """Serve at most ``n`` minibatches per epoch (dp.agree_on_steps: ranks whose shard would yield one more stop
+        early; the droplets left over are reshuffled into the next epoch like any others)."""
+        self._max_batches = int(n)
+        self._length = None
 
     def get_state(self):
         return {"ind_list": self.ind_list, "ptr": self.ptr}
@@ -176,6 +185,9 @@ class DataLoader:
     def next_row_ids(self) -> np.ndarray:
         """Host part of __next__ (dataprep.py:153-193): indices of this minibatch in the stacked CSR."""
         remaining_cells = self.ind_list.size - self.ptr
+        if self._max_batches is not None and self._served >= self._max_batches:
+            self._reset()
+            raise StopIteration()
         if remaining_cells < consts.SMALLEST_ALLOWED_BATCH:
             if remaining_cells > 0:
                 logger.debug(f"Dropped last minibatch of {remaining_cells} cells")
@@ -190,6 +202,7 @@ class DataLoader:
         else:
             ids = cell_inds
         self.ptr = next_ptr
+        self._served += 1
         return np.asarray(ids, dtype=np.int64)
 
     def __next__(self) -> MiniBatch:

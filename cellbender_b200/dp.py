@@ -1,25 +1,32 @@
-"""Multi-GPU execution: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch) for the single exchange
-step of training; no collective on the posterior/estimation path until the final gather.  The reference is
-single-GPU only ("CellBender only makes use of 1 GPU", docs/source/troubleshooting/index.rst:399), so this is new
-surface; SURVEY.md section 8e states the semantics.
+"""Multi-GPU execution: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch) for the plumbing; the single
+exchange step of training is ONE kernel over NVLink peer memory; no collective on the posterior/estimation path until
+the final gather.  The reference is single-GPU only ("CellBender only makes use of 1 GPU",
+docs/source/troubleshooting/index.rst:399), so this is new surface; SURVEY.md section 8e states the semantics.
 
 Training (data parallel): every rank holds the full parameter set and the surely-empty droplets, and a disjoint
-shard of the analysed droplets (``shard_rows``).  Each step every rank runs its own 255-droplet minibatch (forward + backward as one CUDA-graph replay); the ELBO is
-a plain SUM over droplets (train.py:56-63), so the exchange is ONE reduction of the flat fp32 gradient buffer
-(69.4 M values at the PBMC8k shape), issued eagerly between graph replays: by default reduce-scatter -> ClippedAdam sweep
-of this rank's 1/world_size shard -> all-gather of the parameters (``reduce_scatter_step``); ``CB_DP_MODE=allreduce``
-selects all-reduce + the full sweep on every rank.
-Stated consequences: the global minibatch is 255 x world_size droplets; an epoch is n_batches(shard) steps, so
-OneCycleLR's total_steps shrinks by world_size; BatchNorm statistics, Dropout1d masks, epsilon medians and the
-reparameterisation noise are per-rank (different CUDA seeds per rank; ``sync_buffers`` averages the BN running
-statistics before evaluation); the encoder's first-forward offset heuristic
-(encoder.py:300-309) is computed on rank 0 and broadcast.
+shard of the analysed droplets (``shard_rows``).  Each step every rank runs its own 255-droplet minibatch (forward +
+backward as one CUDA-graph replay); the ELBO is a plain SUM over droplets (train.py:56-63), so the exchange is ONE
+reduction of the flat fp32 gradient buffer (69.4 M values at the PBMC8k shape) followed by the optimizer sweep.  Two
+exchange paths, chosen once in ``attach`` (no environment switch):
+  'p2p'      (default) the exchange is FUSED into the optimizer sweep over NVLink peer memory (``p2p_step``,
+             cb_clipped_adam_p2p / cb_clipped_adam_nvls): every rank owns a 1/R shard, sums the peers' gradient shards
+             out of their buffers (TMA bulk reads, or one multimem.ld_reduce through the NVSwitch), applies ClippedAdam
+             and stores the new parameters into every rank's buffer;
+  'sharded'  NCCL reduce_scatter -> sweep of the 1/R shard -> all_gather: the path taken when the symmetric-memory
+             rendezvous is unavailable on the system.
+Stated consequences: the global minibatch is 255 x world_size droplets; every rank takes the SAME number of steps per
+epoch (``agree_on_steps``: the minimum over ranks of the shard loaders' lengths), so OneCycleLR's total_steps =
+agreed steps x epochs shrinks by about world_size; BatchNorm batch statistics, Dropout1d masks, epsilon medians and the
+reparameterisation noise are per rank (different CUDA seeds per rank); BatchNorm RUNNING statistics are averaged over
+ranks at the end of every epoch and before evaluation (``sync_buffers``); the encoder's first-forward offset heuristic
+(encoder.py:300-309) is computed on rank 0 and broadcast right after the first step; the test ELBO used by the failure
+criteria is averaged over ranks; ``FlatClippedAdam.state_dict()`` gathers the sharded moment buffers.
 
-Posterior / estimation: ``shard_cells`` splits the p > 0.5 cell list into contiguous ranges; ranks compute their COO
-pieces independently (``Posterior.device_posterior(cell_subset=...)``) and ``gather_posterior`` concatenates them.
-MCKP needs all cells of a gene, so it runs on the gathered COO (one gene-keyed exchange = the gather itself).
+Posterior / estimation: ``shard_cells`` splits the barcode-sorted cell list into contiguous ranges; ranks compute their
+COO pieces independently (``Posterior.device_posterior(cell_subset=...)``) and ``gather_posterior`` concatenates them in
+rank order, which IS the (m, c)-sorted whole.  MCKP needs all cells of a gene, so it runs on the gathered COO (one
+gene-keyed exchange = the gather itself).
 """
-import os
 from typing import List, Optional
 
 import numpy as np
@@ -32,70 +39,97 @@ def shard_rows(n_rows: int, rank: int, world_size: int) -> np.ndarray:
     return np.arange(rank, n_rows, world_size)
 
 
-def shard_cells(n_cells: int, rank: int, world_size: int) -> np.ndarray:
-    """Contiguous range of the cell list (keeps each rank's COO piece in (m, c) order)."""
+def shard_cells(n_cells: int, rank: int, world_size: int, align: int = 1) -> np.ndarray:
+    """Contiguous range of the (barcode-sorted) cell list, boundaries on multiples of ``align`` (= cells_per_chunk makes
+    sharded and unsharded posterior passes use the same chunks, hence the same per-chunk random streams)."""
     bounds = np.linspace(0, n_cells, world_size + 1).astype(np.int64)
+    if align > 1:
+        bounds[1:-1] = np.minimum(n_cells, (bounds[1:-1] + align - 1) // align * align)
     return np.arange(bounds[rank], bounds[rank + 1])
 
 
-def dp_mode() -> str:
-    """Exchange mode of data-parallel training: 'p2p' (default: exchange fused into the optimizer sweep over NVLink peer
-    memory, ``p2p_step``), 'sharded' (NCCL reduce_scatter -> sweep -> all_gather), 'allreduce', 'overlap'."""
-    return os.environ.get("CB_DP_MODE", "p2p")
-
-
 def p2p_group():
-    """Process group for symmetric-memory (NVLink peer) parameter / gradient buffers, or None when the fused P2P
-    exchange is not selected (CB_DP_MODE=p2p) or torch.distributed is not running on NCCL."""
-    if dp_mode() != "p2p" or not dist.is_available() or not dist.is_initialized() or dist.get_backend() != "nccl":
+    """Process group for symmetric-memory (NVLink peer) parameter / gradient buffers, or None when torch.distributed is
+    not running on NCCL (or spans more ranks than cb_clipped_adam_p2p carries gradient sources for)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_backend() != "nccl":
         return None
-    if dist.get_world_size() > 16:  # cb_clipped_adam_p2p carries at most 16 gradient sources
+    if dist.get_world_size() > 16:
         return None
     return dist.group.WORLD
 
 
-def attach(svi, world_size: int):
-    """Make ``svi.step`` data-parallel: all-reduce(SUM) the flat gradient buffer between backward and the optimizer."""
+def agree_on_steps(n_local: int, device=None) -> int:
+    """Steps per epoch every rank will take: the minimum over ranks of the shard loaders' lengths.  The train / test split
+    and the shard sizes differ by rank, so the loaders' lengths can differ by one; ranks that issued different numbers of
+    exchange steps would dead-lock the barriers (and sweep their parameter shards with different OneCycleLR tables)."""
+    if not dist.is_initialized() or dist.get_world_size() <= 1:
+        return int(n_local)
+    t = torch.tensor([int(n_local)], dtype=torch.int64, device=device if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(t.item())
+
+
+def attach(svi, world_size: int, mode: Optional[str] = None):
+    """Make ``svi.step`` data-parallel.  ``mode``: None = 'p2p' when the optimizer's flat buffers are NVLink peer memory
+    (run.setup_inference arranges that when the symmetric-memory rendezvous works), else 'sharded'."""
     if world_size <= 1:
         return svi
     rank = dist.get_rank()
     torch.manual_seed(1234 + 104729 * rank)
-    torch.cuda.manual_seed(1234 + 104729 * rank)
-    svi.after_backward = lambda opt: dist.all_reduce(opt.flat_g, op=dist.ReduceOp.SUM)
-    if getattr(getattr(svi.optim, "flat_g", None), "is_cuda", False):
-        # measured on 2 x B200 (r01, ms/step): 1 piece 2.04, 2 pieces 2.10, 4 pieces 2.14 -- the Adam sweep is HBM-bound and
-        # the NCCL kernels compete for the same HBM, so pipelining them buys nothing; one all-reduce is the default
-        n_chunks = int(os.environ.get("CB_DP_CHUNKS", "1"))
-        # measured on B200 (r01, ms/step at 2 / 4 GPUs): sharded 1.87 / 1.96, overlap 1.92 / 2.06, allreduce 1.87 / 2.10
-        mode = dp_mode()
-        if mode == "p2p" and (getattr(svi.optim, "symm_p", None) is None or svi.optim.n % (4 * world_size) != 0):
-            # the optimizer's buffers are not NVLink peer memory (symmetric-memory rendezvous unavailable on this system,
-            # optimizer built without a group, more than 16 ranks): NCCL carries the exchange instead
-            if "CB_DP_MODE" in os.environ:
-                raise RuntimeError("CB_DP_MODE=p2p needs the optimizer's flat buffers in symmetric memory "
-                                   "(run.setup_inference / optim.get_optimizer(symmetric_group=...))")
-            mode = "sharded"
-        if mode == "p2p":
-            # measured on B200 (r01, ms/step): 2 GPUs 1.46 against 1.85 for the NCCL exchange; 4 GPUs fused kernel 0.64 ms,
-            # step ~1.72 (the NVLS variant with the same kernel time measured 1.714) against 1.96 (profiles/r01d_dp_exchange.txt)
-            svi.exchange_and_step = lambda opt: p2p_step(opt, world_size, rank)
-        elif mode == "overlap" and n_chunks <= 1:
-            # optional: the reduction of each large gradient block is issued right behind its weight-gradient GEMM, on
-            # that GEMM's side stream, followed by the ClippedAdam sweep of the block -- inside backward and inside the
-            # captured step graph (NCCL collectives capture fine; drop the graphs before destroying the process group).
-            # It hides the exchange behind backward but measures slower than the sharded sweep: the NCCL kernels and the
-            # backward kernels compete for the same HBM / L2 bandwidth.
-            svi.optim.dp_reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            svi.optim.early_weight_updates = True
-            svi.dp_overlap = True
-        elif n_chunks > 1:
-            svi.exchange_and_step = lambda opt: allreduce_and_step(opt, n_chunks)
-        elif mode == "sharded" and svi.optim.n % (4 * world_size) == 0:
-            # default: reduce-scatter -> every rank sweeps 1/world_size of the flat buffers -> all-gather of the
-            # parameters.  Same bytes on the NVLink fabric as the all-reduce, 1/world_size of the 1.9 GB optimizer sweep.
-            svi.exchange_and_step = lambda opt: reduce_scatter_step(opt, world_size, rank)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(1234 + 104729 * rank)
+    opt = svi.optim
+    have_symm = getattr(opt, "symm_p", None) is not None and getattr(opt, "n", 1) % (4 * world_size) == 0
+    if mode is None:
+        mode = "p2p" if have_symm else "sharded"
+    if mode == "p2p":
+        if not have_symm:
+            raise RuntimeError("data-parallel mode 'p2p' needs the optimizer's flat buffers in symmetric memory "
+                               "(run.setup_inference / optim.get_optimizer(symmetric_group=...))")
+        svi.exchange_and_step = lambda o: p2p_step(o, world_size, rank)
+    elif mode == "sharded":
+        if getattr(opt, "n", 0) % (4 * world_size) == 0 and getattr(getattr(opt, "flat_g", None), "is_cuda", False):
+            svi.exchange_and_step = lambda o: reduce_scatter_step(o, world_size, rank)
+        else:  # host-logic tests (gloo): plain SUM all-reduce of the flat gradient buffer, then the full sweep
+            svi.after_backward = lambda o: dist.all_reduce(o.flat_g, op=dist.ReduceOp.SUM)
+    else:
+        raise ValueError(f"unknown data-parallel mode {mode!r}: 'p2p' or 'sharded'")
+    if svi.after_backward is None:
+        svi.after_backward = lambda o: None  # marks the step as data parallel (the exchange runs outside the step graph)
+    svi.dp_mode = mode
+    # consistency hooks the training loop calls (train.SVI.step / train.run_training / optim.state_dict)
     svi.sync_offsets = lambda: broadcast_encoder_offsets(svi.model)
+    svi.sync_buffers = lambda: sync_buffers(svi.model, world_size)
+    svi.reduce_mean = lambda v: all_reduce_mean(v, svi.model.device)
+    if hasattr(opt, "flat_m"):
+        opt.gather_state = lambda: gather_optimizer_state(opt, world_size, rank)
     return svi
+
+
+class LocalPeers:
+    """Single-device stand-in for the symmetric-memory handle of R ranks: rank r's "peer" buffers are the other virtual
+    ranks' local tensors and the barriers are no-ops, because the virtual ranks are stepped one after the other on one
+    stream (each owner only writes its own shard, so sequential execution equals the concurrent one).  Lets the whole
+    ``p2p_step`` path -- pointer tables, shard arithmetic, cb_clipped_adam_p2p -- run on a one-GPU box
+    (tests/test_dp_single_gpu.py)."""
+
+    has_multicast_support = False
+    multicast_ptr = 0
+
+    def __init__(self, buffers: List[torch.Tensor]):
+        self.buffers = buffers
+
+    def get_buffer(self, rank: int, shape, dtype):
+        return self.buffers[rank]
+
+    def barrier(self, channel: int = 0, timeout_ms: int = 0):
+        return None
+
+
+def all_reduce_mean(value: float, device) -> float:
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item()) / dist.get_world_size()
 
 
 def chunk_bounds(n: int, n_chunks: int, align: int = 4):
@@ -103,29 +137,6 @@ def chunk_bounds(n: int, n_chunks: int, align: int = 4):
     ``align`` elements (16-byte alignment of the fp32 buffers for the vectorised Adam kernel)."""
     cuts = [0] + [min(n, (i * n // n_chunks) // align * align) for i in range(1, n_chunks)] + [n]
     return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
-
-
-@torch.no_grad()
-def allreduce_and_step(opt, n_chunks: int = 8):
-    """The exchange step of data-parallel training, pipelined: the flat gradient buffer is all-reduced in ``n_chunks``
-    pieces (queued back to back on NCCL's stream) and the ClippedAdam sweep of piece i runs on the compute stream as
-    soon as piece i has arrived, i.e. while pieces i+1.. are still on the NVLink fabric.  Same arithmetic as
-    ``all_reduce(flat_g)`` followed by ``opt.step()``."""
-    from ._cabi import current_stream, lib
-
-    if not opt.constant_learning_rate and opt.host_steps >= opt.total_steps:
-        raise ValueError(f"Tried to step {opt.host_steps + 1} times. The specified number of total steps is {opt.total_steps}")
-    bounds = chunk_bounds(opt.n, n_chunks)
-    works = [dist.all_reduce(opt.flat_g[a:b], op=dist.ReduceOp.SUM, async_op=True) for a, b in bounds]
-    L, st = lib(), current_stream()
-    tab = (opt.lr_table.data_ptr(), opt.beta1_table.data_ptr(), opt.lr_table.numel(), opt.step_count.data_ptr(),
-           float(opt.beta2), float(opt.eps), float(opt.clip))
-    for i, ((a, b), w) in enumerate(zip(bounds, works)):
-        w.wait()  # makes the compute stream wait for this piece only
-        at = lambda t: t.data_ptr() + 4 * a
-        L.call("cb_clipped_adam_range", at(opt.flat_p), at(opt.flat_g), at(opt.flat_m), at(opt.flat_v), b - a, *tab,
-               1 if i == len(bounds) - 1 else 0, st)
-    opt.host_steps += 1
 
 
 @torch.no_grad()
@@ -153,18 +164,14 @@ def reduce_scatter_step(opt, world_size: int, rank: int):
 
 def p2p_uses_nvls(opt, world_size: int) -> bool:
     """NVLS form (multimem.ld_reduce / multimem.st through the NVSwitch) when the symmetric buffers have multicast
-    addresses and CB_P2P_NVLS=1 asks for it.  (Plain peer loads / stores put 2 (R - 1) / R parameter sets per step on
-    every link, NVLS about one for any R.)"""
+    addresses and there are at least ``NVLS_MIN_RANKS`` ranks.  Plain peer loads / stores put 2 (R - 1) / R parameter sets
+    per step on every link direction, NVLS about one for any R: it pays from four ranks on (at two ranks both move one)."""
     have = bool(getattr(opt.symm_g, "has_multicast_support", False)) and int(getattr(opt.symm_g, "multicast_ptr", 0) or 0) != 0 \
         and int(getattr(opt.symm_p, "multicast_ptr", 0) or 0) != 0
-    env = os.environ.get("CB_P2P_NVLS")
-    if env == "0" or not have:
-        if env == "1":
-            raise RuntimeError("CB_P2P_NVLS=1 but the symmetric buffers have no multicast address on this system")
-        return False
-    # measured on B200 (r01): fused kernel 0.72 ms (NVLS) vs 0.43 ms (peer loads / stores) at 2 GPUs, 0.64 vs 0.64 at 4:
-    # the one-load-per-thread NVLS loop is latency-bound, so it stays opt-in until it is unrolled
-    return env == "1"
+    return have and world_size >= NVLS_MIN_RANKS
+
+
+NVLS_MIN_RANKS = 4
 
 
 @torch.no_grad()
@@ -193,7 +200,7 @@ def p2p_step(opt, world_size: int, rank: int):
                                  len(peers))
     g_arr, p_arr, n_peer = cache
     timeout_ms = 20000  # a rank that never arrives traps the waiting kernels instead of hanging the GPUs
-    timing = os.environ.get("CB_DP_TIMING") == "1"  # CUDA events around the three phases (diagnostics, see p2p_timing)
+    timing = bool(getattr(opt, "p2p_timing", False))  # CUDA events around the three phases (diagnostics, see p2p_timing)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timing else None
     if timing:
         ev[0].record()
@@ -220,7 +227,8 @@ def p2p_step(opt, world_size: int, rank: int):
 
 
 def p2p_timing(opt, last: int = 50):
-    """Mean milliseconds of (barrier before, fused kernel, barrier after) over the last recorded steps (CB_DP_TIMING=1)."""
+    """Mean milliseconds of (barrier before, fused kernel, barrier after) over the last recorded steps (set
+    ``opt.p2p_timing = True`` before stepping)."""
     evs = getattr(opt, "_p2p_events", [])[-last:]
     if not evs:
         return None

@@ -82,13 +82,24 @@ def pad_big_weights(module: torch.nn.Module, min_numel: int = 1 << 16):
     its flat buffer (optim.FlatClippedAdam); this covers models that never see an optimizer (posterior from a checkpoint)."""
     with torch.no_grad():
         for p in module.parameters():
-            if p.dim() == 2 and p.numel() >= min_numel and (p.stride(1) != 1 or p.stride(0) % 4 != 0 or p.data_ptr() % 16 != 0):
+            if p.dim() == 2 and p.numel() >= min_numel:
+                lead, ld = padded_layout(p)
+                if p.stride(1) == 1 and p.stride(0) == ld and (p.data_ptr() - 4 * lead) % 128 == 0:
+                    continue
                 rows, cols = p.shape
-                ld = (cols + 3) // 4 * 4
                 block = torch.zeros((rows, ld), dtype=p.dtype, device=p.device)
-                block[:, :cols].copy_(p.data)
-                p.data = block[:, :cols]
+                block[:, lead:lead + cols].copy_(p.data)
+                p.data = block[:, lead:lead + cols]
     return module
+
+
+def padded_layout(p: torch.Tensor):
+    """(lead, ld) of the storage block of a large 2-D weight: ``ld`` floats per row (a multiple of 32: rows start on
+    128-byte lines) of which the first ``lead`` are padding.  ``p._cb_lead`` (set by the module that owns the weight)
+    shifts the row so that the G-wide block of a Linear(cat(feat, x)) weight -- which starts ``col_offset`` columns into
+    the row -- begins on a 128-byte line too."""
+    lead = int(getattr(p, "_cb_lead", 0))
+    return lead, ops.row_pitch(lead + p.shape[1])
 
 
 class LazyFeat:
@@ -117,7 +128,7 @@ class _MultiLinearBig(torch.autograd.Function):
         for i, (feat, w, b) in enumerate(zip(feats, weights, biases)):
             st = streams[i] if streams is not None else None
             if st is not None:  # this product runs on its own stream (the caller joins it before consuming the output)
-                y = torch.empty((B, ops.round_up(w.shape[0], 4)), dtype=torch.float32, device=x.device)[:, :w.shape[0]]
+                y = torch.empty((B, ops.row_pitch(w.shape[0])), dtype=torch.float32, device=x.device)[:, :w.shape[0]]
                 st.wait_stream(main)
                 with torch.cuda.stream(st):
                     assert feat is None or isinstance(feat, LazyFeat)

@@ -269,7 +269,7 @@ class RemoveBackgroundPyroModel(nn.Module):
         if key not in self._bufs or self._bufs[key]["cap"] < B:
             G, dev = self.n_genes, self.device
             cap = max(B, 8)
-            ld = ops.round_up(G, 4)
+            ld = ops.row_pitch(G)
             chi_b = torch.zeros(ld, device=dev)
             chi_b[:G] = self.avg_gene_expression
             self._bufs[key] = {

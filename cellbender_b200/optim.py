@@ -44,11 +44,13 @@ class FlatClippedAdam:
         assert self.params, "no parameters to optimise"
         dev = self.params[0].device
         self.device = dev
-        # each tensor starts on a 16-byte boundary; large 2-D weights additionally get a row stride that is a
-        # multiple of 4 floats (TMA needs 16-byte rows; G = 33 538 is not a multiple of 4) -- the nn.Parameter then is
-        # a strided view [rows, cols] of a [rows, ld] block, the padding columns stay zero forever.
+        # each tensor starts on a 16-byte boundary; large 2-D weights additionally get 128-byte-aligned rows (a row pitch
+        # that is a multiple of 32 floats; G = 33 538 is not even a multiple of 4) -- the nn.Parameter then is a strided
+        # view [rows, cols] of a [rows, ld] block (gemm.padded_layout), the padding columns stay zero forever.
+        from .gemm import padded_layout
+
         def padded_ld(p):
-            return (p.shape[1] + 3) // 4 * 4 if (p.dim() == 2 and p.numel() >= (1 << 16)) else None
+            return padded_layout(p) if (p.dim() == 2 and p.numel() >= (1 << 16)) else None
 
         # layout: the few very large matrices first (each one is a unit of the piecewise optimizer sweep and, data
         # parallel, of the overlapped gradient reduction), everything else behind them in ONE contiguous tail
@@ -58,8 +60,10 @@ class FlatClippedAdam:
         self.tail_start = 0
         for i in order:
             p = self.params[i]
-            ld = padded_ld(p)
-            n = p.numel() if ld is None else p.shape[0] * ld
+            ld = padded_ld(p)  # None or (lead padding, row pitch)
+            n = p.numel() if ld is None else p.shape[0] * ld[1]
+            if ld is not None:
+                off = (off + 31) // 32 * 32  # padded blocks start on 128-byte lines
             self.offsets[i] = off
             self.lds[i] = ld
             off += (n + 3) // 4 * 4
@@ -90,8 +94,9 @@ class FlatClippedAdam:
                     gview = self.flat_g[o:o + p.numel()].view(p.shape)
                 else:
                     rows, cols = p.shape
-                    view = self.flat_p[o:o + rows * ld].view(rows, ld)[:, :cols]
-                    gview = self.flat_g[o:o + rows * ld].view(rows, ld)[:, :cols]
+                    lead, ld = ld
+                    view = self.flat_p[o:o + rows * ld].view(rows, ld)[:, lead:lead + cols]
+                    gview = self.flat_g[o:o + rows * ld].view(rows, ld)[:, lead:lead + cols]
                 view.copy_(p.data)
                 p.data = view
                 p._cb_grad_view = gview  # GEMM epilogues write weight gradients here directly (gemm.py)
@@ -99,15 +104,9 @@ class FlatClippedAdam:
                     p._cb_block = (o, p.shape[0], ld, p.shape[1])  # [rows, ld] block of the flat buffers
                 self.grad_views.append(gview)
         self.learning_rate = learning_rate
-        self.total_steps = total_steps
-        self.constant_learning_rate = constant_learning_rate or total_steps is None
-        if self.constant_learning_rate:
-            lrs, b1s = [learning_rate], [betas[0]]
-        else:
-            lrs, b1s = one_cycle_tables(learning_rate, total_steps)
-        self._lrs = lrs
-        self.lr_table = torch.tensor(lrs, dtype=torch.float32, device=dev)
-        self.beta1_table = torch.tensor(b1s, dtype=torch.float32, device=dev)
+        self._beta1_constant = betas[0]
+        self._constant_requested = constant_learning_rate
+        self.set_total_steps(total_steps)
         self.beta2, self.eps, self.clip = betas[1], eps, clip_norm
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)  # optimizer steps taken (device side)
         self.host_steps = 0
@@ -115,11 +114,22 @@ class FlatClippedAdam:
         # gradient GEMM has finished, on the same (side) stream, so that the HBM-bound sweep overlaps the rest of the
         # backward pass (which is latency / L2-bound); the sweep at the end of the step covers what is left.
         self.early_weight_updates = True
-        # data parallel (dp.attach): callable that all-reduces a contiguous slice of the flat gradient buffer.  With it
-        # set, every early block update first reduces that block across ranks (on the side stream of its gradient GEMM,
-        # i.e. overlapped with the rest of backward) and step() reduces what is left before sweeping it.
-        self.dp_reduce = None
+        # data parallel with sharded sweeps (dp.attach): callable that completes flat_m / flat_v on every rank
+        self.gather_state = None
         self._fused_done: List[tuple] = []
+
+    def set_total_steps(self, total_steps: Optional[int]):
+        """(Re)build the per-step lr / beta1 tables of OneCycleLR for ``total_steps`` optimizer steps."""
+        self.total_steps = total_steps
+        # epochs == 0 ("will only initialize the model", run.py:789): nothing to schedule
+        self.constant_learning_rate = self._constant_requested or total_steps is None or total_steps <= 0
+        if self.constant_learning_rate:
+            lrs, b1s = [self.learning_rate], [self._beta1_constant]
+        else:
+            lrs, b1s = one_cycle_tables(self.learning_rate, total_steps)
+        self._lrs = lrs
+        self.lr_table = torch.tensor(lrs, dtype=torch.float32, device=self.device)
+        self.beta1_table = torch.tensor(b1s, dtype=torch.float32, device=self.device)
 
     def zero_grad(self):
         self._fused_done = []
@@ -147,8 +157,6 @@ class FlatClippedAdam:
 
         o, rows, ld, cols = w._cb_block
         at = lambda t: t.data_ptr() + 4 * o
-        if self.dp_reduce is not None:
-            self.dp_reduce(self.flat_g[o:o + rows * ld])
         lib().call("cb_clipped_adam_range", at(self.flat_p), at(self.flat_g), at(self.flat_m), at(self.flat_v), rows * ld,
                    self.lr_table.data_ptr(), self.beta1_table.data_ptr(), self.lr_table.numel(), self.step_count.data_ptr(),
                    float(self.beta2), float(self.eps), float(self.clip), 0, current_stream())
@@ -169,14 +177,6 @@ class FlatClippedAdam:
                    float(self.beta2), float(self.eps), float(self.clip))
             at = lambda t, off: t.data_ptr() + 4 * off
             cur = 0
-            if self.dp_reduce is not None:  # reduce the ranges no early block update has covered (normally: the tail)
-                c0 = 0
-                for o, rows, ld, cols, off in sorted(self._fused_done):
-                    if o > c0:
-                        self.dp_reduce(self.flat_g[c0:o])
-                    c0 = o + rows * ld
-                if self.n > c0:
-                    self.dp_reduce(self.flat_g[c0:self.n])
             for o, rows, ld, cols, off in sorted(self._fused_done):
                 assert o >= cur, "fused blocks overlap"
                 L.call("cb_clipped_adam_range", at(self.flat_p, cur), at(self.flat_g, cur), at(self.flat_m, cur),
@@ -186,8 +186,6 @@ class FlatClippedAdam:
                    self.n - cur, *tab, 1, st)
             self._fused_done = []
         else:
-            if self.dp_reduce is not None:
-                self.dp_reduce(self.flat_g)
             ops.clipped_adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_table, self.beta1_table,
                                   self.step_count, beta2=self.beta2, eps=self.eps, clip=self.clip, grad_scale=grad_scale)
         self.host_steps += 1
@@ -199,6 +197,8 @@ class FlatClippedAdam:
         return [self._lrs[min(self.host_steps, len(self._lrs) - 1)]]
 
     def state_dict(self):
+        if self.gather_state is not None:
+            self.gather_state()  # sharded data-parallel sweeps keep only this rank's slice of the moments current
         return {"flat_m": self.flat_m, "flat_v": self.flat_v, "step": self.step_count, "host_steps": self.host_steps,
                 "total_steps": self.total_steps, "learning_rate": self.learning_rate}
 

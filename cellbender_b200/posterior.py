@@ -233,14 +233,14 @@ class Posterior:
         prefix_dev = torch.as_tensor(prefix, device=self.device)
         n_window = n_window[lo:hi]
         gene_all = torch.as_tensor(np.asarray(self.analyzed_gene_inds).astype(np.int64), device=self.device)
-        ld = ops.round_up(G, 4)
+        ld = ops.row_pitch(G)
         chi_a = torch.zeros(ld, device=self.device)
         chi_b = torch.zeros(ld, device=self.device)
         chi_a[:G] = m.param_store["chi_ambient"].detach()
         chi_b[:G] = m.avg_gene_expression
         lin = m.decoder.out_linear
         cpc = self.cells_per_chunk
-        logits_t = torch.empty((G, ops.round_up(S * cpc, 4)), device=self.device)  # [G, cells * S]: transposed, cell-major
+        logits_t = torch.empty((G, ops.row_pitch(S * cpc)), device=self.device)  # [G, cells * S]: transposed, cell-major
         for start in range(0, hi - lo, cpc):
             stop = min(hi - lo, start + cpc)
             Bc = stop - start

@@ -64,9 +64,10 @@ def build_model(dataset_obj, args, device: Optional[str] = None) -> RemoveBackgr
 
 
 def setup_inference(dataset_obj, args, device: Optional[str] = None, total_epochs_for_testing_only: Optional[int] = None,
-                    rank: int = 0, world_size: int = 1):
+                    rank: int = 0, world_size: int = 1, dp_mode: Optional[str] = None):
     """Everything run_inference builds before training starts (run.py:658-786).  With world_size > 1 every rank
-    builds the identical model (same seed) and takes a disjoint shard of the training droplets (see dp.py)."""
+    builds the identical model (same seed) and takes a disjoint shard of the training droplets (see dp.py);
+    ``dp_mode``: None (fused NVLink exchange when peer memory can be mapped, else NCCL), 'p2p' or 'sharded'."""
     # the reference switches distribution argument validation off (run.py:659-660); it costs a host sync per check
     torch.distributions.Distribution.set_default_validate_args(False)
     set_rng_seed(consts.RANDOM_SEED)
@@ -83,15 +84,19 @@ def setup_inference(dataset_obj, args, device: Optional[str] = None, total_epoch
     train_loader, test_loader = prep_sparse_data_for_training(
         dataset=count_matrix, empty_drop_dataset=empties, batch_size=batch_size, training_fraction=frac,
         fraction_empties=args.fraction_empties, shuffle=True, device=device)
+    n_batches = len(train_loader)
     symmetric_group = None
     if world_size > 1:
-        from .dp import p2p_group
+        from .dp import agree_on_steps, p2p_group
 
-        symmetric_group = p2p_group()  # None unless CB_DP_MODE=p2p
-    opt_args = dict(n_batches=len(train_loader), batch_size=train_loader.batch_size, epochs=args.epochs,
+        # every rank must take the same number of steps per epoch (and sweep with the same OneCycleLR table): the shards
+        # and the random train / test split make the loaders' lengths differ by one between ranks
+        n_batches = agree_on_steps(n_batches, device=device)
+        train_loader.limit_batches(n_batches)
+        symmetric_group = p2p_group() if dp_mode in (None, "p2p") else None
+    opt_args = dict(n_batches=n_batches, batch_size=train_loader.batch_size, epochs=args.epochs,
                     learning_rate=args.learning_rate, constant_learning_rate=args.constant_learning_rate,
                     total_epochs_for_testing_only=total_epochs_for_testing_only)
-    scheduler = None
     if symmetric_group is not None:
         # the parameters are re-homed by the optimizer, so probe the symmetric-memory rendezvous BEFORE building it: if
         # this system cannot map peer memory (every rank sees the same failure), NCCL carries the exchange (dp.attach)
@@ -101,7 +106,7 @@ def setup_inference(dataset_obj, args, device: Optional[str] = None, total_epoch
             probe = symm_mem.empty(64, dtype=torch.float32, device=device or "cuda")
             symm_mem.rendezvous(probe, symmetric_group)
         except Exception as exc:  # noqa: BLE001
-            if "CB_DP_MODE" in os.environ:
+            if dp_mode == "p2p":
                 raise
             logger.warning(f"symmetric memory unavailable ({type(exc).__name__}: {exc}); data-parallel exchange through NCCL")
             symmetric_group = None
@@ -131,7 +136,7 @@ def compute_output_denoised_counts(posterior, args, fpr_list=None):
     Returns {fpr: scipy CSC [all barcodes, all genes]}."""
     from .estimation import (MAP, Mean, MultipleChoiceKnapsack, SingleSample, ThresholdCDF,
                              compute_mean_target_removal_as_function)
-    from .sparse_utils import csr_set_rows_to_zero
+    from .sparse_utils import combine_csr
 
     posterior.cell_noise_count_posterior_coo()
     ds = posterior.dataset_obj
@@ -145,7 +150,10 @@ def compute_output_denoised_counts(posterior, args, fpr_list=None):
         count_matrix = ds.matrix  # all barcodes
         cell_inds = np.asarray(ds.analyzed_barcode_inds)[posterior.latents_map["p"] > consts.CELL_PROB_CUTOFF]
         empty_inds = np.setdiff1d(np.arange(count_matrix.shape[0]), cell_inds)
-        cell_counts = csr_set_rows_to_zero(csr=count_matrix, row_inds=empty_inds)
+        # csr_set_rows_to_zero(count_matrix, empty_inds) of run.py:268, NOT in place: the reference's helper zeroes a
+        # csr_matrix argument in place (its own data["matrix"] is CSC, so it works on a converted copy); the raw counts
+        # of this dataset object must survive for restore_eliminated_features_in_cells
+        cell_counts = combine_csr(count_matrix, zero_rows=empty_inds)
         # the device-resident COO (same entries as the scipy one, already (m, c)-sorted) feeds the estimators directly
         coo = posterior._device_posterior if posterior._device_posterior is not None else posterior._noise_count_posterior_coo
         per_cell = compute_mean_target_removal_as_function(

@@ -51,9 +51,12 @@ class SVI:
         self.graph_warmup = graph_warmup
         self._graphs = {}
         self._eager_steps = 0
-        self.after_backward = None  # hook(optim): e.g. the data-parallel gradient all-reduce (dp.attach)
-        self.exchange_and_step = None  # hook(optim): all-reduce pipelined with the optimizer sweep (dp.attach)
-        self.dp_overlap = False  # data parallel with the reductions issued inside backward / the step graph (dp.attach)
+        # data parallel (dp.attach): the exchange runs eagerly between replays of the forward + backward graph
+        self.after_backward = None  # hook(optim): gradient exchange that precedes a full optimizer sweep
+        self.exchange_and_step = None  # hook(optim): exchange fused with / followed by the sharded optimizer sweep
+        self.sync_offsets = None  # hook(): broadcast the encoder's first-forward offsets (called after the first step)
+        self.sync_buffers = None  # hook(): average the BatchNorm running statistics over ranks (end of epoch / before eval)
+        self.reduce_mean = None  # hook(float) -> float: mean over ranks (test ELBO for the failure criteria)
 
     def _ambient_unit_vector(self) -> torch.Tensor:
         """x_ambient / ||x_ambient||_2 of EncodeNonZLatents.forward (vae/encoder.py:266-270); the d_empty factor
@@ -74,8 +77,7 @@ class SVI:
         terms = self.loss_terms(batch)
         loss = terms["loss"]
         # single GPU: the ClippedAdam sweep of each large weight block is issued right behind its weight-gradient GEMM
-        fuse = ((self.after_backward is None or self.dp_overlap) and self.model.training
-                and getattr(self.optim, "early_weight_updates", False))
+        fuse = (self.after_backward is None and self.model.training and getattr(self.optim, "early_weight_updates", False))
         gemm.FUSED_OPT = self.optim if fuse else None
         try:
             loss.backward()
@@ -90,11 +92,8 @@ class SVI:
         return loss
 
     def _exchange_and_step(self):
-        if self.dp_overlap:
-            self.optim.step()  # reduces whatever the early block updates have not covered, then sweeps it
-            return
         if self.exchange_and_step is not None:
-            self.exchange_and_step(self.optim)  # chunked all-reduce overlapped with the Adam sweep of earlier chunks
+            self.exchange_and_step(self.optim)  # the exchange and the (sharded) sweep are one operation
             return
         if self.after_backward is not None:
             self.after_backward(self.optim)
@@ -103,8 +102,12 @@ class SVI:
     def step(self, batch: MiniBatch) -> torch.Tensor:
         """One training step; returns the loss (-ELBO, summed over the minibatch) as a 0-dim device tensor."""
         if not self.use_cuda_graph or self.model.encoder["other"].offset is None or self._eager_steps < self.graph_warmup:
-            self._eager_steps += 1  # first steps run eagerly (sets the encoder offsets, warms allocator and cuBLAS)
-            return self._step_eager(batch)
+            self._eager_steps += 1  # first steps run eagerly (sets the encoder offsets, warms the allocator)
+            first = self._eager_steps == 1
+            loss = self._step_eager(batch)
+            if first and self.sync_offsets is not None:
+                self.sync_offsets()  # data parallel: every rank continues with rank 0's first-forward offsets
+            return loss
         key = (id(batch.loader), batch.n, self.model.training)
         entry = self._graphs.get(key)
         if entry is None:
@@ -117,7 +120,7 @@ class SVI:
                              f"{self.optim.total_steps}")
         graph.replay()
         _cabi.lib().launch_count += n_launch  # kernels of ours inside the replayed graph
-        if self.after_backward is not None and not self.dp_overlap:
+        if self.after_backward is not None:
             # data parallel, exchange outside the graph: all-reduce (NCCL) and the fused Adam run eagerly between replays
             self._exchange_and_step()
         else:
@@ -132,7 +135,7 @@ class SVI:
         snap_step, host_steps = self.optim.step_count.clone(), self.optim.host_steps
         bn_state = {k: v.clone() for k, v in self.model.state_dict().items() if "running_" in k or "num_batches" in k}
         # single GPU: the whole step is one graph.  Data parallel: forward + backward + gradient collection only.
-        body = self._step_eager if (self.after_backward is None or self.dp_overlap) else self._forward_backward
+        body = self._step_eager if self.after_backward is None else self._forward_backward
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -212,9 +215,13 @@ def run_training(model: RemoveBackgroundPyroModel, svi: SVI, train_loader: DataL
             else:
                 logger.info("[epoch %03d]  average training loss: %.4f" % (epoch, total_epoch_loss_train))
 
+            if svi.sync_buffers is not None:
+                svi.sync_buffers()  # data parallel: one set of BatchNorm running statistics on every rank
             if (test_loader is not None) and (len(test_loader) > 0) and epoch % test_freq == 0:
                 model.eval()
                 total_epoch_loss_test = evaluate_epoch(svi, test_loader)
+                if svi.reduce_mean is not None:  # the failure criteria below must fire on every rank or on none
+                    total_epoch_loss_test = svi.reduce_mean(total_epoch_loss_test)
                 model.loss["test"]["epoch"].append(epoch)
                 model.loss["test"]["elbo"].append(-total_epoch_loss_test)
                 logger.info("[epoch %03d] average test loss: %.4f" % (epoch, total_epoch_loss_test))

@@ -188,6 +188,10 @@ class EncodeNonZLatents(nn.Module):
         self.x_scaling = None
         self.batchnorm0 = nn.BatchNorm1d(num_features=self.n_genes)
         self.d_empty_loc_fn = None  # callable -> 0-dim tensor (set by RemoveBackgroundPyroModel)
+        # storage hint (gemm.padded_layout): the G-wide block of these weights starts 4 feature columns into the row; 28
+        # floats of lead padding put it on a 128-byte line (names, shapes, values and state_dict keys are unaffected)
+        self.layer1.weight._cb_lead = ops.ROW_ALIGN - additional_features_p
+        self.eps_network[0].weight._cb_lead = ops.ROW_ALIGN - additional_features_eps
 
     def _d_empty_loc(self, device):
         if self.d_empty_loc_fn is None:

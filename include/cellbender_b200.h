@@ -138,7 +138,9 @@ int cb_obs_small_grads(const float* sums, int ld_sums, const float* w, const flo
  * a_mn / b_mn = 0: operand stored [M|N rows, K cols] (K-major, the nn.Linear forward case);
  *             = 1: operand stored [K rows, M|N cols] (what dW = dY^T X and dX = dY W see, no transposes in memory).
  * lda / ldb / ldc multiples of 4 and 16-byte aligned bases (TMA loads and TMA stores); out-of-range rows/cols are
- * zero-filled on load and clipped on store; accumulate uses the TMA unit's element-wise reduce-add.
+ * zero-filled on load and clipped on store (rows exactly, columns at 16-byte granularity: up to 3 padding columns behind
+ * column N - 1 of a row -- inside the row's padded pitch -- may be overwritten with zeros); accumulate uses the TMA
+ * unit's element-wise reduce-add.
  * split_k > 1 streams K across CTAs (skinny M): partial tiles in `workspace`
  * (cb_gemm_tf32_workspace_elems floats), summed in a fixed order.                                            */
 long long cb_gemm_tf32_workspace_elems(int M, int N, int split_k);

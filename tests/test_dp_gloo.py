@@ -50,7 +50,10 @@ def _worker(rank, world, port, q):
 
         m = Model()
         dp.broadcast_encoder_offsets(m)
-        q.put((rank, got.tolist(), Svi.optim.flat_g.tolist(), m.encoder["other"].offset))
+        # ranks agree on the number of steps per epoch (the shard loaders' lengths differ by one) and on the test ELBO
+        steps = dp.agree_on_steps(33 + rank)
+        mean = dp.all_reduce_mean(10.0 + 4.0 * rank, "cpu")
+        q.put((rank, got.tolist(), Svi.optim.flat_g.tolist(), m.encoder["other"].offset, steps, mean))
     finally:
         dist.destroy_process_group()
 
@@ -74,10 +77,11 @@ def test_two_rank_exchange_on_gloo():
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     expect = list(range(3)) + [100 + i for i in range(5)]
-    for rank, gathered, flat_g, offset in res:
+    for rank, gathered, flat_g, offset, steps, mean in res:
         assert gathered == expect
         assert flat_g == [3.0] * 5  # 1 + 2
         assert offset == {"logit_p": 1.5, "epsilon": -0.25}
+        assert steps == 33 and mean == 12.0
 
 
 def test_owner_shard_exchange_scheme_equals_allreduce_then_full_sweep():

@@ -16,32 +16,42 @@ def _dataset():
 
     sim = synth.simulate_dataset(n_genes=256, cells_of_each_type=[100, 100], n_droplets=1500, cell_mean_umi=2000.0,
                                  empty_mean_umi=60.0, dirichlet_alpha=0.5, seed=0, device="cpu", cell_chunk=128)
-    return synth.prepare_dataset(sim, expected_cells=200, total_droplets_included=500)
+    return synth.prepare_dataset(sim, expected_cells=200, total_droplets_included=501)
 
 
 def _worker(rank, world, port, q, mode="sharded", posterior=True):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), CB_DP_MODE=mode)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dev = f"cuda:{rank}"
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
     try:
-        from cellbender_b200 import dp, run
+        from cellbender_b200 import dp, run, train
         from cellbender_b200.posterior import Posterior
 
-        ds = _dataset()
+        ds = _dataset()  # 501 analysed droplets: uneven shards, the shard loaders' lengths differ between ranks
         args = run.default_args(epochs=3, z_dim=8, z_hidden_dims=[32], learning_rate=1e-3)
-        model, opt, svi, tl, te = run.setup_inference(ds, args, device=dev, rank=rank, world_size=world)
-        dp.attach(svi, world)
-        model.train()
+        model, opt, svi, tl, te = run.setup_inference(ds, args, device=dev, rank=rank, world_size=world, dp_mode=mode)
+        dp.attach(svi, world, mode=mode)
+        assert svi.dp_mode == mode
         p0 = opt.flat_p.clone()
-        n = 0
-        for _ in range(2):
-            for b in tl:
-                svi.step(b)
-                if n == 0:
-                    svi.sync_offsets()
-                n += 1
+        # the reference's training loop, unchanged: offsets broadcast after the first step, BatchNorm running statistics
+        # averaged at the end of every epoch, the test ELBO averaged over ranks, every rank takes the agreed number of steps
+        train.run_training(model, svi, tl, te, epochs=3, test_freq=1)
         torch.cuda.synchronize()
+        assert opt.host_steps == 3 * len(tl) == int(opt.step_count.item())
+        offs = torch.tensor([model.encoder["other"].offset["logit_p"]], device=dev, dtype=torch.float64)
+        all_offs = [torch.zeros_like(offs) for _ in range(world)]
+        dist.all_gather(all_offs, offs)
+        assert all(torch.equal(all_offs[0], o) for o in all_offs), "encoder offsets differ between ranks"
+        bn = model.encoder["other"].batchnorm0.running_mean.detach().clone()
+        all_bn = [torch.zeros_like(bn) for _ in range(world)]
+        dist.all_gather(all_bn, bn)
+        assert all(torch.equal(all_bn[0], o) for o in all_bn), "BatchNorm running statistics differ between ranks"
+        sd = opt.state_dict()  # gathers the sharded moments: identical on every rank afterwards
+        fm = sd["flat_m"].detach().clone()
+        all_m = [torch.zeros_like(fm) for _ in range(world)]
+        dist.all_gather(all_m, fm)
+        assert all(torch.equal(all_m[0], o) for o in all_m) and float(fm.abs().max()) > 0
         flat = opt.flat_p.detach().clone()
         others = [torch.zeros_like(flat) for _ in range(world)]
         dist.all_gather(others, flat)
@@ -53,12 +63,11 @@ def _worker(rank, world, port, q, mode="sharded", posterior=True):
             torch.cuda.synchronize()
             return
         # posterior: shards + gather vs everything on one rank, seeded per chunk, shard boundaries on chunk boundaries
-        dp.sync_buffers(model, world)
         model.eval()
         post = Posterior(ds, model, cells_per_chunk=32)
         n_cells = 128
         post._latents = {"p": np.concatenate([np.ones(n_cells), np.zeros(ds.analyzed_barcode_inds.size - n_cells)])}
-        piece = post.device_posterior(cell_subset=dp.shard_cells(n_cells, rank, world), seed=7, n_samples=4)
+        piece = post.device_posterior(cell_subset=dp.shard_cells(n_cells, rank, world, align=32), seed=7, n_samples=4)
         full = dp.gather_posterior(piece, world)
         ok_post = None
         if rank == 0:
@@ -104,7 +113,7 @@ def _train(world, mode):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_fused_p2p_exchange_matches_nccl_sharded_exchange():
-    """CB_DP_MODE=p2p (cb_clipped_adam_p2p: gradient shards summed out of the peers' buffers over NVLink, ClippedAdam,
+    """mode 'p2p' (cb_clipped_adam_p2p: gradient shards summed out of the peers' buffers over NVLink, ClippedAdam,
     parameters stored into every rank's buffer, all in one kernel between two device-side barriers) must train exactly
     like the NCCL reduce_scatter -> sweep -> all_gather exchange: replicas identical, same parameters as the NCCL run."""
     ref = _train(2, "sharded")

@@ -34,15 +34,23 @@ def test_no_cpu_fallback():
         su.csr_set_rows_to_zero(np.zeros((2, 2)), [0])  # not a sparse matrix: the reference's error
 
 
-def test_dp_mode_selection(monkeypatch):
-    monkeypatch.delenv("CB_DP_MODE", raising=False)
-    assert dp.dp_mode() == "p2p"
+def test_dp_mode_selection():
+    """dp.attach picks the exchange once, from what the optimizer's buffers are (no environment switch): 'p2p' needs
+    symmetric-memory buffers, otherwise the NCCL path; unknown names are refused."""
     assert dp.p2p_group() is None  # torch.distributed is not initialised here: no peer-memory group
-    monkeypatch.setenv("CB_DP_MODE", "sharded")
-    assert dp.dp_mode() == "sharded" and dp.p2p_group() is None
+
+    class Opt:
+        symm_p = None
+        n = 64
+
+    class Svi:
+        optim = Opt()
+        after_backward = exchange_and_step = None
+
+    assert dp.attach(Svi(), 1).after_backward is None  # world size 1: untouched
 
 
-def test_p2p_uses_nvls_policy(monkeypatch):
+def test_p2p_uses_nvls_policy():
     class H:
         def __init__(self, ok):
             self.has_multicast_support, self.multicast_ptr = ok, (4096 if ok else 0)
@@ -51,11 +59,14 @@ def test_p2p_uses_nvls_policy(monkeypatch):
         def __init__(self, ok):
             self.symm_g, self.symm_p = H(ok), H(ok)
 
-    monkeypatch.delenv("CB_P2P_NVLS", raising=False)
-    assert dp.p2p_uses_nvls(Opt(True), 2) is False and dp.p2p_uses_nvls(Opt(True), 8) is False  # opt-in only
-    monkeypatch.setenv("CB_P2P_NVLS", "1")
-    assert dp.p2p_uses_nvls(Opt(True), 2) is True
-    with pytest.raises(RuntimeError):
-        dp.p2p_uses_nvls(Opt(False), 2)
-    monkeypatch.setenv("CB_P2P_NVLS", "0")
-    assert dp.p2p_uses_nvls(Opt(True), 8) is False
+    assert dp.p2p_uses_nvls(Opt(True), 2) is False  # two ranks: plain peer loads / stores move the same bytes
+    assert dp.p2p_uses_nvls(Opt(True), 4) is True and dp.p2p_uses_nvls(Opt(True), 8) is True
+    assert dp.p2p_uses_nvls(Opt(False), 8) is False  # no multicast address on this system
+
+
+def test_shard_cells_aligned_to_chunks():
+    for n, w, a in ((8000, 8, 512), (1000, 3, 128), (130, 4, 32), (5, 2, 4)):
+        parts = [dp.shard_cells(n, r, w, align=a) for r in range(w)]
+        cat = np.concatenate(parts)
+        assert np.array_equal(cat, np.arange(n))
+        assert all(p[0] % a == 0 for p in parts if p.size)
