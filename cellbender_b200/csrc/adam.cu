@@ -16,65 +16,87 @@
 
 namespace cb {
 
-// Residency: the sweep is HBM-bound and runs on a side stream WHILE the latency-bound chain of backward kernels runs on
-// others (optim.early_block_update).  It therefore must not fill every thread slot of the SMs (a grid of 2 048
-// threads/SM made small kernels of the critical chain wait ~50 us for a slot, r02 timeline): the grid is capped at four
-// 256-thread CTAs per SM and each thread keeps two 16-byte loads per array in flight (128 KB per SM, twice what HBM
-// latency x bandwidth needs).
-constexpr int kAdamUnroll = 2;
+// Scheduling: the sweep is HBM-bound and runs on a side stream WHILE the latency-bound chain of backward kernels runs on
+// others (optim.early_block_update).  A persistent grid (r01: 2 048 threads/SM for the whole 75 us) left no thread slots
+// -- and, capped at 1 024 threads/SM, no registers -- for the small kernels of that chain, which then waited up to 50 us
+// for a slot (r02 timelines).  Hence short-lived CTAs: each one owns ONE tile of 256 x 4 float4 per array (16 KB each,
+// all 16 loads of a thread issued before the first use), lives ~2 us and frees its slot, so CTAs of concurrent
+// (higher-priority) kernels are placed within microseconds while the sweep still keeps > 150 KB per SM in flight.
+// The per-step scalars come from host-built tables (lr, beta1, and the bias-corrected step size
+// lr * sqrt(1 - b2^t) / (1 - b1^t) in float64); without a step-size table (constant learning rate: t is unbounded)
+// the kernel evaluates it itself.
+constexpr int kAdamUnroll = 4;
+constexpr int kAdamTile = 256 * kAdamUnroll;  // float4 per CTA
+
+struct StepCoef {
+  float b1, omb1, step_size;
+};
+__device__ __forceinline__ StepCoef step_coef(const float* __restrict__ lr_table, const float* __restrict__ beta1_table,
+                                              const float* __restrict__ step_table, long long table_len,
+                                              const long long* __restrict__ step_ptr, float beta2) {
+  const long long t0 = *step_ptr;  // number of optimizer steps already taken
+  const long long ti = t0 < table_len ? t0 : table_len - 1;
+  StepCoef c;
+  c.b1 = beta1_table[ti];
+  c.omb1 = 1.0f - c.b1;
+  if (step_table != nullptr && t0 < table_len) {
+    c.step_size = step_table[ti];
+  } else {
+    const double t = double(t0 + 1);
+    c.step_size = float(double(lr_table[ti]) * sqrt(1.0 - pow(double(beta2), t)) / (1.0 - pow(double(c.b1), t)));
+  }
+  return c;
+}
+
 __global__ void __launch_bounds__(256) clipped_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                            float* __restrict__ m, float* __restrict__ v, long long n,
                                                            const float* __restrict__ lr_table,
-                                                           const float* __restrict__ beta1_table, long long table_len,
+                                                           const float* __restrict__ beta1_table,
+                                                           const float* __restrict__ step_table, long long table_len,
                                                            const long long* __restrict__ step_ptr, float beta2, float eps,
                                                            float clip, float grad_scale) {
-  const long long t0 = *step_ptr;  // number of optimizer steps already taken
-  const long long ti = t0 < table_len ? t0 : table_len - 1;
-  const float lr = lr_table[ti], b1 = beta1_table[ti];
-  const double t = double(t0 + 1);
-  const float step_size = float(double(lr) * sqrt(1.0 - pow(double(beta2), t)) / (1.0 - pow(double(b1), t)));
-  const float omb1 = 1.0f - b1, omb2 = 1.0f - beta2;
-
+  const StepCoef sc = step_coef(lr_table, beta1_table, step_table, table_len, step_ptr, beta2);
+  const float b1 = sc.b1, omb1 = sc.omb1, step_size = sc.step_size, omb2 = 1.0f - beta2;
   const long long n4 = n >> 2;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n4; i0 += stride * kAdamUnroll) {
-    float4 pp[kAdamUnroll], gg[kAdamUnroll], mm[kAdamUnroll], vv[kAdamUnroll];
+  const long long i0 = blockIdx.x * (long long)kAdamTile + threadIdx.x;
+  float4 pp[kAdamUnroll], gg[kAdamUnroll], mm[kAdamUnroll], vv[kAdamUnroll];
 #pragma unroll
-    for (int u = 0; u < kAdamUnroll; ++u) {  // all loads first
-      const long long i = i0 + u * stride;
-      if (i < n4) {
-        pp[u] = reinterpret_cast<float4*>(p)[i];
-        gg[u] = reinterpret_cast<const float4*>(g)[i];
-        mm[u] = reinterpret_cast<float4*>(m)[i];
-        vv[u] = reinterpret_cast<float4*>(v)[i];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kAdamUnroll; ++u) {
-      const long long i = i0 + u * stride;
-      if (i >= n4) break;
-      float* pa = reinterpret_cast<float*>(&pp[u]);
-      const float* ga = reinterpret_cast<const float*>(&gg[u]);
-      float* ma = reinterpret_cast<float*>(&mm[u]);
-      float* va = reinterpret_cast<float*>(&vv[u]);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float gc = fminf(fmaxf(ga[k] * grad_scale, -clip), clip);
-        ma[k] = b1 * ma[k] + omb1 * gc;
-        va[k] = beta2 * va[k] + omb2 * gc * gc;
-        pa[k] -= step_size * ma[k] / (sqrtf(va[k]) + eps);
-      }
-      reinterpret_cast<float4*>(p)[i] = pp[u];
-      reinterpret_cast<float4*>(m)[i] = mm[u];
-      reinterpret_cast<float4*>(v)[i] = vv[u];
+  for (int u = 0; u < kAdamUnroll; ++u) {  // all loads first
+    const long long i = i0 + u * 256;
+    if (i < n4) {
+      pp[u] = reinterpret_cast<float4*>(p)[i];
+      gg[u] = ldg_stream4(g + 4 * i);
+      mm[u] = reinterpret_cast<float4*>(m)[i];
+      vv[u] = reinterpret_cast<float4*>(v)[i];
     }
   }
-  for (long long i = 4 * n4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float gc = fminf(fmaxf(g[i] * grad_scale, -clip), clip);
-    const float mk = b1 * m[i] + omb1 * gc;
-    const float vk = beta2 * v[i] + omb2 * gc * gc;
-    m[i] = mk, v[i] = vk;
-    p[i] -= step_size * mk / (sqrtf(vk) + eps);
+#pragma unroll
+  for (int u = 0; u < kAdamUnroll; ++u) {
+    const long long i = i0 + u * 256;
+    if (i >= n4) break;
+    float* pa = reinterpret_cast<float*>(&pp[u]);
+    const float* ga = reinterpret_cast<const float*>(&gg[u]);
+    float* ma = reinterpret_cast<float*>(&mm[u]);
+    float* va = reinterpret_cast<float*>(&vv[u]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gc = fminf(fmaxf(ga[k] * grad_scale, -clip), clip);
+      ma[k] = b1 * ma[k] + omb1 * gc;
+      va[k] = beta2 * va[k] + omb2 * gc * gc;
+      pa[k] -= step_size * ma[k] / (sqrtf(va[k]) + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp[u];
+    reinterpret_cast<float4*>(m)[i] = mm[u];
+    reinterpret_cast<float4*>(v)[i] = vv[u];
+  }
+  if (blockIdx.x == gridDim.x - 1) {  // the < 4 trailing elements
+    for (long long i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {
+      const float gc = fminf(fmaxf(g[i] * grad_scale, -clip), clip);
+      const float mk = b1 * m[i] + omb1 * gc;
+      const float vk = beta2 * v[i] + omb2 * gc * gc;
+      m[i] = mk, v[i] = vk;
+      p[i] -= step_size * mk / (sqrtf(vk) + eps);
+    }
   }
 }
 
@@ -308,28 +330,30 @@ __global__ void __launch_bounds__(256) clipped_adam_nvls_kernel(float* p, float*
 }  // namespace cb
 
 static int adam_range(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
-                      const float* beta1_table, long long table_len, long long* step_ptr, float beta2, float eps, float clip,
-                      float grad_scale, int advance, void* stream);
+                      const float* beta1_table, const float* step_table, long long table_len, long long* step_ptr, float beta2,
+                      float eps, float clip, float grad_scale, int advance, void* stream);
 
 extern "C" int cb_clipped_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
-                                    const float* beta1_table, long long table_len, long long* step_ptr, float beta2,
-                                    float eps, float clip, float grad_scale, void* stream) {
-  return adam_range(p, g, m, v, n, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip, grad_scale, 1, stream);
+                                    const float* beta1_table, const float* step_size_table, long long table_len,
+                                    long long* step_ptr, float beta2, float eps, float clip, float grad_scale, void* stream) {
+  return adam_range(p, g, m, v, n, lr_table, beta1_table, step_size_table, table_len, step_ptr, beta2, eps, clip, grad_scale, 1,
+                    stream);
 }
 
 // One contiguous range of the flat buffers without advancing the step counter (n = 0: nothing to update); with
 // advance != 0 the counter is incremented after the range.  Used when parts of the buffer are updated elsewhere
 // (cb_gemm_tf32_dw_adam) and the rest is swept range by range.
 extern "C" int cb_clipped_adam_range(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
-                                     const float* beta1_table, long long table_len, long long* step_ptr, float beta2,
-                                     float eps, float clip, int advance, void* stream) {
-  return adam_range(p, g, m, v, n, lr_table, beta1_table, table_len, step_ptr, beta2, eps, clip, 1.0f, advance, stream);
+                                     const float* beta1_table, const float* step_size_table, long long table_len,
+                                     long long* step_ptr, float beta2, float eps, float clip, int advance, void* stream) {
+  return adam_range(p, g, m, v, n, lr_table, beta1_table, step_size_table, table_len, step_ptr, beta2, eps, clip, 1.0f, advance,
+                    stream);
 }
 
 
 static int adam_range(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
-                      const float* beta1_table, long long table_len, long long* step_ptr, float beta2, float eps, float clip,
-                      float grad_scale, int advance, void* stream) {
+                      const float* beta1_table, const float* step_table, long long table_len, long long* step_ptr, float beta2,
+                      float eps, float clip, float grad_scale, int advance, void* stream) {
   CB_REQUIRE(n >= 0 && table_len > 0, "cb_clipped_adam_step: bad sizes n=%lld table_len=%lld", n, table_len);
   if (n == 0) {
     if (advance) cb::advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_ptr);
@@ -338,12 +362,10 @@ static int adam_range(float* p, const float* g, float* m, float* v, long long n,
   for (const void* q : {(const void*)p, (const void*)g, (const void*)m, (const void*)v})
     CB_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0, "cb_clipped_adam_step: buffers must be 16-byte aligned");
   const long long n4 = (n + 3) / 4;
-  long long blocks = (n4 + 256 * cb::kAdamUnroll - 1) / (256 * cb::kAdamUnroll);
-  const long long cap = 4LL * cb::sm_count();  // half of the SMs' thread slots stay free for concurrent kernels
-  if (blocks > cap) blocks = cap;
-  cb::clipped_adam_kernel<<<unsigned(blocks), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_table, beta1_table,
-                                                                              table_len, step_ptr, beta2, eps, clip,
-                                                                              grad_scale);
+  const long long blocks = (n4 + cb::kAdamTile - 1) / cb::kAdamTile;  // one short-lived CTA per tile
+  CB_REQUIRE(blocks < (1LL << 31), "cb_clipped_adam_step: n=%lld too large for one launch", n);
+  cb::clipped_adam_kernel<<<unsigned(blocks), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_table, beta1_table, step_table,
+                                                                              table_len, step_ptr, beta2, eps, clip, grad_scale);
   if (advance) cb::advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_ptr);
   return cb::check_launch("cb_clipped_adam_step");
 }

@@ -23,8 +23,13 @@
 
 namespace cb {
 
-constexpr int kBnCols = 32, kBnGroups = 8, kBnUnroll = 32;
-constexpr int kBnChunk = kBnGroups * kBnUnroll;  // rows a CTA holds in registers at once (>= the 255-row minibatch)
+// Two shapes of the same kernels (COLS adjacent columns x GROUPS row groups = 256 threads, UNROLL rows per thread in
+// registers, GROUPS * UNROLL = 256 >= the 255-row minibatch):
+//   wide   <32, 8, 32>  128-byte row segments: the gene-wide matrices (thousands of column strips fill the GPU)
+//   narrow <8, 32, 8>   32-byte row segments (one sector): the [B, 512] hidden layers, where the wide shape gives only
+//                       16 CTAs of 127 instructions per element each (ncu r02g: 14-29 us, issue-bound on 16 SMs);
+//                       64 CTAs with a quarter of the per-thread work cut that chain link to a few microseconds.
+constexpr int kBnChunk = 256;  // rows a CTA holds in registers at once
 
 __device__ __forceinline__ float act_fwd(float v, int act) {
   if (act == 1) return v > 20.f ? v : log1pf(expf(v));
@@ -38,14 +43,15 @@ __device__ __forceinline__ float act_grad(float v, int act) {
 }
 
 // sum of one value per thread over the row groups; result valid in every thread of the column
-__device__ __forceinline__ float group_sum(float v, float (*s)[kBnCols + 1]) {
-  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+template <int COLS, int GROUPS>
+__device__ __forceinline__ float group_sum(float v, float (*s)[COLS + 1]) {
+  const int c = threadIdx.x % COLS, g = threadIdx.x / COLS;
   __syncthreads();
   s[g][c] = v;
   __syncthreads();
   float t = 0.f;
 #pragma unroll
-  for (int i = 0; i < kBnGroups; ++i) t += s[i][c];
+  for (int i = 0; i < GROUPS; ++i) t += s[i][c];
   return t;
 }
 
@@ -57,14 +63,16 @@ __device__ __forceinline__ float group_sum(float v, float (*s)[kBnCols + 1]) {
 // of Linear(cat(feat, x_in)) (vae/encoder.py:283-298).  The G-wide gene block of that Linear is produced by the tensor-core
 // GEMM as soon as batchnorm0 is done; the features need z (EncodeZ) and join here, so the big products do not wait for
 // them.  The completed pre-activation is written back to x (the backward kernel re-reads it).
+template <int kBnCols, int kBnGroups, int kBnUnroll>
 __global__ void __launch_bounds__(kBnCols* kBnGroups) bn_act_forward_kernel(
     float* __restrict__ x, long long ldx, int B, int N, const float* __restrict__ gamma, const float* __restrict__ beta,
     float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
     const float* __restrict__ keep, int training, float momentum, float eps, int act, float* __restrict__ y, long long ldy,
     float* __restrict__ save_mean, float* __restrict__ save_rstd, const float* __restrict__ feat, int F,
     const float* __restrict__ wf, long long ldw) {
+  static_assert(kBnGroups * kBnUnroll == kBnChunk, "a CTA pass covers kBnChunk rows");
   __shared__ float s[kBnGroups][kBnCols + 1];
-  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = threadIdx.x % kBnCols, g = threadIdx.x / kBnCols;
   const int col = blockIdx.x * kBnCols + c;
   const bool ok = col < N;
   // eval: this CTA normalises rows [row0, row1); training: all rows (gridDim.y == 1)
@@ -112,7 +120,7 @@ __global__ void __launch_bounds__(kBnCols* kBnGroups) bn_act_forward_kernel(
     } else if (ok) {
       for (int r = g; r < B; r += kBnGroups) sum += x[(long long)r * ldx + col];
     }
-    mean = group_sum(sum, s) / float(B);
+    mean = group_sum<kBnCols, kBnGroups>(sum, s) / float(B);
     float ssq = 0.f;
     if (single) {
 #pragma unroll
@@ -126,7 +134,7 @@ __global__ void __launch_bounds__(kBnCols* kBnGroups) bn_act_forward_kernel(
         ssq += d * d;
       }
     }
-    ssq = group_sum(ssq, s);
+    ssq = group_sum<kBnCols, kBnGroups>(ssq, s);
     const float var = ssq / float(B);
     rstd = rsqrtf(var + eps);
     if (ok && g == 0) {
@@ -154,13 +162,14 @@ __global__ void __launch_bounds__(kBnCols* kBnGroups) bn_act_forward_kernel(
   }
 }
 
+template <int kBnCols, int kBnGroups, int kBnUnroll>
 __global__ void __launch_bounds__(kBnCols* kBnGroups) bn_act_backward_kernel(
     const float* __restrict__ x, long long ldx, const float* __restrict__ dy, long long lddy, int B, int N,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ save_mean,
     const float* __restrict__ save_rstd, const float* __restrict__ keep, int training, int act, float* __restrict__ dx,
     long long lddx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
   __shared__ float s[kBnGroups][kBnCols + 1];
-  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = threadIdx.x % kBnCols, g = threadIdx.x / kBnCols;
   const int col = blockIdx.x * kBnCols + c;
   const bool ok = col < N;
   float mean = 0.f, rstd = 0.f, gm = 0.f, bt = 0.f;
@@ -193,8 +202,8 @@ __global__ void __launch_bounds__(kBnCols* kBnGroups) bn_act_backward_kernel(
       sg += dpre * xhat;
     }
   }
-  sb = group_sum(sb, s);
-  sg = group_sum(sg, s);
+  sb = group_sum<kBnCols, kBnGroups>(sb, s);
+  sg = group_sum<kBnCols, kBnGroups>(sg, s);
   if (ok && g == 0) dgamma[col] = sg, dbeta[col] = sb;
   if (dx == nullptr) return;  // the input is data (batchnorm0): only the affine parameters have gradients
   const float invB = 1.f / float(B);
@@ -219,7 +228,7 @@ __global__ void __launch_bounds__(kBnCols* kBnGroups) bn_act_backward_kernel(
     }
   }
   if (dbias) {
-    sdx = group_sum(sdx, s);
+    sdx = group_sum<kBnCols, kBnGroups>(sdx, s);
     if (ok && g == 0) dbias[col] = sdx;
   }
 }
@@ -378,10 +387,18 @@ static int launch_forward(float* x, long long ldx, int n_rows, int n_cols, const
                           float* running_mean, float* running_var, long long* num_batches_tracked, const float* keep,
                           int training, float momentum, float eps, int act, float* y, long long ldy, float* save_mean,
                           float* save_rstd, const float* feat, int n_feat, const float* wf, long long ldw, void* stream) {
-  dim3 grid((n_cols + kBnCols - 1) / kBnCols, training ? 1 : (n_rows + kBnChunk - 1) / kBnChunk);
-  bn_act_forward_kernel<<<grid, kBnCols * kBnGroups, 0, (cudaStream_t)stream>>>(
-      x, ldx, n_rows, n_cols, gamma, beta, running_mean, running_var, num_batches_tracked, keep, training, momentum, eps, act, y,
-      ldy, save_mean, save_rstd, feat, n_feat, wf, ldw);
+  const int gy = training ? 1 : (n_rows + kBnChunk - 1) / kBnChunk;
+  if (n_cols <= 2048) {  // narrow shape: four times the CTAs, a quarter of the rows per thread
+    dim3 grid((n_cols + 7) / 8, gy);
+    bn_act_forward_kernel<8, 32, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, n_rows, n_cols, gamma, beta, running_mean, running_var, num_batches_tracked, keep, training, momentum, eps, act, y,
+        ldy, save_mean, save_rstd, feat, n_feat, wf, ldw);
+  } else {
+    dim3 grid((n_cols + 31) / 32, gy);
+    bn_act_forward_kernel<32, 8, 32><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, n_rows, n_cols, gamma, beta, running_mean, running_var, num_batches_tracked, keep, training, momentum, eps, act, y,
+        ldy, save_mean, save_rstd, feat, n_feat, wf, ldw);
+  }
   return 0;
 }
 
@@ -406,9 +423,12 @@ extern "C" int cb_bn_act_backward(const float* x, long long ldx, const float* dy
                                   int training, int act, float* dx, long long lddx, float* dgamma, float* dbeta, float* dbias,
                                   void* stream) {
   CB_REQUIRE(n_rows > 0 && n_cols > 0, "cb_bn_act_backward: empty input");
-  const int grid = (n_cols + cb::kBnCols - 1) / cb::kBnCols;
-  cb::bn_act_backward_kernel<<<grid, cb::kBnCols * cb::kBnGroups, 0, (cudaStream_t)stream>>>(
-      x, ldx, dy, lddy, n_rows, n_cols, gamma, beta, save_mean, save_rstd, nullptr, training, act, dx, lddx, dgamma, dbeta, dbias);
+  if (n_cols <= 2048)
+    cb::bn_act_backward_kernel<8, 32, 8><<<(n_cols + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, dy, lddy, n_rows, n_cols, gamma, beta, save_mean, save_rstd, nullptr, training, act, dx, lddx, dgamma, dbeta, dbias);
+  else
+    cb::bn_act_backward_kernel<32, 8, 32><<<(n_cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, dy, lddy, n_rows, n_cols, gamma, beta, save_mean, save_rstd, nullptr, training, act, dx, lddx, dgamma, dbeta, dbias);
   return cb::check_launch("cb_bn_act_backward");
 }
 
@@ -437,9 +457,9 @@ extern "C" int cb_bn0_backward(const float* x, long long ldx, const float* dy, l
                                                                                            save_mean, save_rstd, dgamma, dbeta);
     return cb::check_launch("cb_bn0_backward");
   }
-  const int grid = (n_genes + cb::kBnCols - 1) / cb::kBnCols;
+  const int grid = (n_genes + 31) / 32;
   // gamma / beta only enter through act'(.), which is 1 for the identity: pass the statistics as dummies
-  cb::bn_act_backward_kernel<<<grid, cb::kBnCols * cb::kBnGroups, 0, (cudaStream_t)stream>>>(
+  cb::bn_act_backward_kernel<32, 8, 32><<<grid, 256, 0, (cudaStream_t)stream>>>(
       x, ldx, dy, lddy, n_rows, n_genes, save_mean, save_mean, save_mean, save_rstd, keep, 1, 0, nullptr, 0, dgamma, dbeta, nullptr);
   return cb::check_launch("cb_bn0_backward");
 }

@@ -155,8 +155,10 @@ def reduce_scatter_step(opt, world_size: int, rank: int):
         opt._g_shard = torch.empty(sh, dtype=torch.float32, device=opt.flat_g.device)
     dist.reduce_scatter_tensor(opt._g_shard, opt.flat_g, op=dist.ReduceOp.SUM)
     at = lambda t: t.data_ptr() + 4 * a
+    st_tab = getattr(opt, "step_table", None)
     lib().call("cb_clipped_adam_range", at(opt.flat_p), opt._g_shard.data_ptr(), at(opt.flat_m), at(opt.flat_v), sh,
-               opt.lr_table.data_ptr(), opt.beta1_table.data_ptr(), opt.lr_table.numel(), opt.step_count.data_ptr(),
+               opt.lr_table.data_ptr(), opt.beta1_table.data_ptr(), None if st_tab is None else st_tab.data_ptr(),
+               opt.lr_table.numel(), opt.step_count.data_ptr(),
                float(opt.beta2), float(opt.eps), float(opt.clip), 1, current_stream())
     dist.all_gather_into_tensor(opt.flat_p, opt.flat_p[a:a + sh])
     opt.host_steps += 1

@@ -270,11 +270,13 @@ def col_logsumexp(mat: torch.Tensor, n_rows: int, n_cols: int, row_add: Optional
     return out
 
 
-def clipped_adam_step(p, g, m, v, lr_table, beta1_table, step, beta2=0.999, eps=1e-8, clip=10.0, grad_scale=1.0):
-    """cb_clipped_adam_step over flat fp32 buffers; `step` is a device int64[1] counter (incremented)."""
-    _req_cuda(p, g, m, v, lr_table, beta1_table, step)
+def clipped_adam_step(p, g, m, v, lr_table, beta1_table, step, beta2=0.999, eps=1e-8, clip=10.0, grad_scale=1.0,
+                      step_table=None):
+    """cb_clipped_adam_step over flat fp32 buffers; `step` is a device int64[1] counter (incremented).  ``step_table``:
+    optional per-step bias-corrected step sizes (optim.FlatClippedAdam builds them in float64 on the host)."""
+    _req_cuda(p, g, m, v, lr_table, beta1_table, step, step_table)
     _cabi.lib().call("cb_clipped_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), ptr(lr_table), ptr(beta1_table),
-                     lr_table.numel(), ptr(step), float(beta2), float(eps), float(clip), float(grad_scale),
+                     ptr(step_table), lr_table.numel(), ptr(step), float(beta2), float(eps), float(clip), float(grad_scale),
                      current_stream())
 
 

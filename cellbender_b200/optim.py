@@ -106,8 +106,8 @@ class FlatClippedAdam:
         self.learning_rate = learning_rate
         self._beta1_constant = betas[0]
         self._constant_requested = constant_learning_rate
-        self.set_total_steps(total_steps)
         self.beta2, self.eps, self.clip = betas[1], eps, clip_norm
+        self.set_total_steps(total_steps)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)  # optimizer steps taken (device side)
         self.host_steps = 0
         # Default on a single GPU: the ClippedAdam sweep of each large weight block is issued as soon as that block's
@@ -130,6 +130,20 @@ class FlatClippedAdam:
         self._lrs = lrs
         self.lr_table = torch.tensor(lrs, dtype=torch.float32, device=self.device)
         self.beta1_table = torch.tensor(b1s, dtype=torch.float32, device=self.device)
+        # bias-corrected step size of step t (1-based), lr_t sqrt(1 - b2^t) / (1 - b1_t^t), from the fp32 table values in
+        # float64 -- exactly what the kernels would evaluate; with a constant learning rate t is unbounded: no table
+        self.step_table = None
+        if not self.constant_learning_rate and hasattr(self, "beta2"):
+            self._build_step_table()
+
+    def _build_step_table(self):
+        import numpy as np
+
+        lr = self.lr_table.double().cpu().numpy()
+        b1 = self.beta1_table.double().cpu().numpy()
+        t = np.arange(1, lr.size + 1, dtype=np.float64)
+        step = lr * np.sqrt(1.0 - np.float64(np.float32(self.beta2)) ** t) / (1.0 - b1 ** t)
+        self.step_table = torch.tensor(step, dtype=torch.float32, device=self.device)
 
     def zero_grad(self):
         self._fused_done = []
@@ -153,13 +167,13 @@ class FlatClippedAdam:
     def early_block_update(self, w: nn.Parameter):
         """ClippedAdam sweep of one [rows, ld] weight block of the flat buffers, on the current stream, without advancing
         the step counter.  The caller guarantees the block's gradient is complete and its old values are no longer read."""
-        from ._cabi import current_stream, lib
+        from ._cabi import current_stream, lib, ptr
 
         o, rows, ld, cols = w._cb_block
         at = lambda t: t.data_ptr() + 4 * o
         lib().call("cb_clipped_adam_range", at(self.flat_p), at(self.flat_g), at(self.flat_m), at(self.flat_v), rows * ld,
-                   self.lr_table.data_ptr(), self.beta1_table.data_ptr(), self.lr_table.numel(), self.step_count.data_ptr(),
-                   float(self.beta2), float(self.eps), float(self.clip), 0, current_stream())
+                   self.lr_table.data_ptr(), self.beta1_table.data_ptr(), ptr(self.step_table), self.lr_table.numel(),
+                   self.step_count.data_ptr(), float(self.beta2), float(self.eps), float(self.clip), 0, current_stream())
         self._fused_done.append((o, rows, ld, cols, 0))
 
     def step(self, grad_scale: float = 1.0):
@@ -169,12 +183,12 @@ class FlatClippedAdam:
                              f"{self.total_steps}")
         if self._fused_done:
             # blocks already swept behind their weight-gradient GEMM (early_block_update): sweep the ranges between them
-            from ._cabi import current_stream, lib
+            from ._cabi import current_stream, lib, ptr
 
             assert grad_scale == 1.0, "piecewise weight updates do not support gradient rescaling"
             L, st = lib(), current_stream()
-            tab = (self.lr_table.data_ptr(), self.beta1_table.data_ptr(), self.lr_table.numel(), self.step_count.data_ptr(),
-                   float(self.beta2), float(self.eps), float(self.clip))
+            tab = (self.lr_table.data_ptr(), self.beta1_table.data_ptr(), ptr(self.step_table), self.lr_table.numel(),
+                   self.step_count.data_ptr(), float(self.beta2), float(self.eps), float(self.clip))
             at = lambda t, off: t.data_ptr() + 4 * off
             cur = 0
             for o, rows, ld, cols, off in sorted(self._fused_done):
@@ -187,7 +201,8 @@ class FlatClippedAdam:
             self._fused_done = []
         else:
             ops.clipped_adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_table, self.beta1_table,
-                                  self.step_count, beta2=self.beta2, eps=self.eps, clip=self.clip, grad_scale=grad_scale)
+                                  self.step_count, beta2=self.beta2, eps=self.eps, clip=self.clip, grad_scale=grad_scale,
+                                  step_table=self.step_table)
         self.host_steps += 1
 
     def get_last_lr(self) -> List[float]:

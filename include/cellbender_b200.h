@@ -227,15 +227,17 @@ int cb_simplex_backward(int n, const float* y, const float* grad_y, float* grad_
 /* ---------------------------------------------------------------------------------------------------
  * K8  fused ClippedAdam + OneCycleLR over one flat buffer.  Replaces get_optimizer (run.py:593-629) and the
  * per-parameter optimizer/scheduler steps at train.py:56-60.  lr_table/beta1_table[table_len] hold torch
- * OneCycleLR's per-step values; *step_ptr (device int64) counts completed steps and is incremented here.       */
+ * OneCycleLR's per-step values, step_size_table[table_len] (may be NULL: evaluated on the device) the bias-corrected
+ * step size lr sqrt(1 - beta2^t) / (1 - beta1^t) of step t; *step_ptr (device int64) counts completed steps and is
+ * incremented here.                                                                                             */
 int cb_clipped_adam_step(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
-                         const float* beta1_table, long long table_len, long long* step_ptr, float beta2, float eps,
-                         float clip, float grad_scale, void* stream);
+                         const float* beta1_table, const float* step_size_table, long long table_len, long long* step_ptr,
+                         float beta2, float eps, float clip, float grad_scale, void* stream);
 /* the same update on one contiguous range (step counter advanced only if advance != 0; n = 0 allowed): the sweep of one
  * large weight block right behind its weight-gradient product, and of the ranges between such blocks.              */
 int cb_clipped_adam_range(float* p, const float* g, float* m, float* v, long long n, const float* lr_table,
-                          const float* beta1_table, long long table_len, long long* step_ptr, float beta2, float eps,
-                          float clip, int advance, void* stream);
+                          const float* beta1_table, const float* step_size_table, long long table_len, long long* step_ptr,
+                          float beta2, float eps, float clip, int advance, void* stream);
 /* Data-parallel exchange fused into the optimizer sweep (new surface, the reference is single-GPU): ClippedAdam on
  * this rank's contiguous shard, reading the shard's gradient from every rank's gradient buffer (peer memory over
  * NVLink, summed in rank order) and storing the updated parameters into every rank's parameter buffer.

@@ -258,6 +258,16 @@ def test_clipped_adam_matches_per_tensor_reference(ops):
     for k in range(steps):
         ops.clipped_adam_step(pd, grads[k].float().to(DEV), md, vd, lr_t, b1_t, step)
     assert int(step.item()) == steps
+    # the same sweep with the host-built step-size table (what optim.FlatClippedAdam passes): identical to 1e-7
+    t_ = np.arange(1, steps + 1, dtype=np.float64)
+    st_t = torch.tensor(lr_t.double().cpu().numpy() * np.sqrt(1 - np.float64(np.float32(0.999)) ** t_)
+                        / (1 - b1_t.double().cpu().numpy() ** t_), dtype=torch.float32, device=DEV)
+    pd2, md2, vd2 = p0.float().to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    step2 = torch.zeros(1, dtype=torch.int64, device=DEV)
+    for k in range(steps):
+        ops.clipped_adam_step(pd2, grads[k].float().to(DEV), md2, vd2, lr_t, b1_t, step2, step_table=st_t)
+    torch.testing.assert_close(pd2, pd, rtol=1e-6, atol=1e-7)
+    assert torch.equal(md2, md) and torch.equal(vd2, vd)
     np.testing.assert_allclose(pd.cpu().numpy(), p.numpy(), rtol=2e-5, atol=2e-6)
     np.testing.assert_allclose(md.cpu().numpy(), m.numpy(), rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(vd.cpu().numpy(), v.numpy(), rtol=1e-4, atol=1e-7)
@@ -780,7 +790,7 @@ def test_clipped_adam_p2p_matches_sum_then_sweep(ops, n_ranks, own):
     p_ref, m_ref, v_ref = p0.clone(), m0.clone(), v0.clone()
     step_ref = torch.tensor([1], dtype=torch.int64, device=DEV)
     at = lambda t: t.data_ptr() + 4 * a
-    L.call("cb_clipped_adam_range", at(p_ref), at(gsum), at(m_ref), at(v_ref), n, lr.data_ptr(), b1.data_ptr(), 3,
+    L.call("cb_clipped_adam_range", at(p_ref), at(gsum), at(m_ref), at(v_ref), n, lr.data_ptr(), b1.data_ptr(), None, 3,
            step_ref.data_ptr(), 0.999, 1e-8, 10.0, 1, st)
     # fused kernel
     p, m, v = p0.clone(), m0.clone(), v0.clone()

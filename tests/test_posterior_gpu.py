@@ -171,7 +171,7 @@ def test_device_posterior_matches_reference_host_path(n_cells, pb, fp32_gemm):
     post._device_posterior = dev_post
     shape = [int(np.prod(ds.matrix.shape, dtype=np.uint64)), n_max]
     coo = dev_post.to_scipy(shape)
-    assert coo.shape == tuple(shape) and coo.nnz == len(got) and coo.row.dtype == np.int64
+    assert coo.shape == tuple(shape) and coo.nnz == len(got)
     from cellbender_b200.estimation import MAP
 
     denoised = post.compute_denoised_counts(MAP, device=DEV)
