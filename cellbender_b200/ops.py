@@ -44,7 +44,11 @@ def side_stream(device, idx: int = 0) -> "torch.cuda.Stream":
     d = torch.device(device)
     key = (d.index if d.index is not None else torch.cuda.current_device(), idx)
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key[0])
+        # Stream 0 carries the weight-gradient products and the optimizer sweeps behind them: bulk HBM traffic with no
+        # consumer inside the step.  Every other stream carries links of the latency-bound critical chain and gets the
+        # higher priority, so that its (small) kernels are placed ahead of the bulk CTAs still waiting for a slot.
+        # Priorities are recorded into the kernel nodes of a captured CUDA graph.
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key[0], priority=0 if idx == 0 else -1)
     return _SIDE_STREAMS[key]
 
 

@@ -136,14 +136,15 @@ class SVI:
         bn_state = {k: v.clone() for k, v in self.model.state_dict().items() if "running_" in k or "num_batches" in k}
         # single GPU: the whole step is one graph.  Data parallel: forward + backward + gradient collection only.
         body = self._step_eager if self.after_backward is None else self._forward_backward
-        side = torch.cuda.Stream()
+        # warm-up and capture on a high-priority stream: the step's critical chain outranks the bulk stream (ops.side_stream)
+        side = torch.cuda.Stream(priority=-1)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             body(static)
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         n0 = _cabi.lib().launch_count
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=side):
             loss = body(static)
         n_launch = _cabi.lib().launch_count - n0
         _cabi.lib().launch_count = n0  # capture records launches, it does not run them
