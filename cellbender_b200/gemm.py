@@ -40,21 +40,44 @@ def _grad_target(weight: torch.Tensor):
 
 
 _PENDING_JOINS = []
+_BULK_PENDING = []
+BULK_STREAM, SMALL_GRAD_STREAM = 0, 5  # ops.side_stream indices
+
+
+def grad_stream(device, weights) -> "torch.cuda.Stream":
+    """Stream for the weight-gradient products of a layer: the bulk stream (low priority; also carries the optimizer sweeps
+    of the large blocks) for the G-wide matrices, a high-priority one for the small layers -- queued behind ~300 us of
+    bulk sweeps their 8 us products used to finish last and hold up the end of the step (r02h timeline)."""
+    big = any(w.numel() >= FUSED_MIN_NUMEL for w in weights)
+    return ops.side_stream(device, BULK_STREAM if big else SMALL_GRAD_STREAM)
 
 
 def defer_join(side: "torch.cuda.Stream"):
     """Postpone ``current_stream().wait_stream(side)`` to the end of the running backward pass.  Weight / bias gradients
     that a forked kernel writes straight into the optimizer's flat gradient buffer have no consumer inside backward, so
     the calling stream (which carries the critical chain of input-gradient kernels) need not stall for them at the end
-    of the node; the autograd engine's final callback joins every such stream before control returns to the caller."""
-    if not _PENDING_JOINS:
+    of the node; the autograd engine's final callback joins every such stream before control returns to the caller --
+    except the bulk stream, which the optimizer joins as late as it can (``join_bulk``: after the sweep of everything
+    the bulk stream does not touch)."""
+    if not _PENDING_JOINS and not _BULK_PENDING:
         def _join_all():
             main = torch.cuda.current_stream()
             while _PENDING_JOINS:
                 main.wait_stream(_PENDING_JOINS.pop())
         torch.autograd.Variable._execution_engine.queue_callback(_join_all)
-    if side not in _PENDING_JOINS:
+    bulk = ops.side_stream(side.device, BULK_STREAM)
+    if side is bulk and FUSED_OPT is not None:  # an optimizer step follows and will join (train.SVI sets FUSED_OPT)
+        if side not in _BULK_PENDING:
+            _BULK_PENDING.append(side)
+    elif side not in _PENDING_JOINS:
         _PENDING_JOINS.append(side)
+
+
+def join_bulk():
+    """Make the current stream wait for the bulk stream(s) forked during the last backward pass (no-op when none)."""
+    main = torch.cuda.current_stream()
+    while _BULK_PENDING:
+        main.wait_stream(_BULK_PENDING.pop())
 
 
 def early_update_applies(w: torch.Tensor) -> bool:
@@ -194,7 +217,7 @@ class _MultiLinearBig(torch.autograd.Function):
         fork = need_dx and any(t[0] is not None or t[1] is not None for t in targets)
         main = torch.cuda.current_stream()
         if fork:
-            side = ops.side_stream(x.device, 0)
+            side = grad_stream(x.device, weights)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 parameter_gradients()

@@ -137,7 +137,7 @@ class _ObsTerm(torch.autograd.Function):
         d_b_buf, d_b = gemm._grad_target(ctx.bias_param)
         main = torch.cuda.current_stream()
         # decoder weight / bias gradients on a side stream, the hidden-activation gradient on this one
-        side = ops.side_stream(dlogits.device, 0)
+        side = gemm.grad_stream(dlogits.device, [w_param])
         side.wait_stream(main)
         with torch.cuda.stream(side):
             ops.gemm_tf32(dlogits, h_c, G, H, B, a_mn=True, b_mn=True, out=d_w_buf, split_k=1)  # dlogits^T . h

@@ -181,8 +181,11 @@ class FlatClippedAdam:
         if not self.constant_learning_rate and self.host_steps >= self.total_steps:
             raise ValueError(f"Tried to step {self.host_steps + 1} times. The specified number of total steps is "
                              f"{self.total_steps}")
+        from . import gemm
+
         if self._fused_done:
-            # blocks already swept behind their weight-gradient GEMM (early_block_update): sweep the ranges between them
+            # blocks already swept behind their weight-gradient GEMM (early_block_update): sweep the ranges between them;
+            # nothing here depends on the bulk stream, which is joined only before the step counter advances
             from ._cabi import current_stream, lib, ptr
 
             assert grad_scale == 1.0, "piecewise weight updates do not support gradient rescaling"
@@ -197,9 +200,13 @@ class FlatClippedAdam:
                        at(self.flat_v, cur), o - cur, *tab, 0, st)
                 cur = o + rows * ld
             L.call("cb_clipped_adam_range", at(self.flat_p, cur), at(self.flat_g, cur), at(self.flat_m, cur), at(self.flat_v, cur),
-                   self.n - cur, *tab, 1, st)
+                   self.n - cur, *tab, 0, st)
+            gemm.join_bulk()  # the early block sweeps read the step counter: advance it only behind them
+            L.call("cb_clipped_adam_range", at(self.flat_p, 0), at(self.flat_g, 0), at(self.flat_m, 0), at(self.flat_v, 0),
+                   0, *tab, 1, current_stream())
             self._fused_done = []
         else:
+            gemm.join_bulk()
             ops.clipped_adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr_table, self.beta1_table,
                                   self.step_count, beta2=self.beta2, eps=self.eps, clip=self.clip, grad_scale=grad_scale,
                                   step_table=self.step_table)
