@@ -1,14 +1,19 @@
 """Benchmark of the remove-background hot path on B200 (driver contract: one JSON line on stdout from rank 0).
 
-    python bench.py --gpus N --steps K --warmup W            # the B200 path (torchrun for N > 1)
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference-style CPU port, rank 0 only
+    python bench.py --gpus N --steps K --warmup W                        # the B200 path (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W       # the reference's CPU path (oracle port), rank 0 only
+    python bench.py --impl reference --device cuda ...                   # the reference's torch-CUDA path (same port on the GPU)
 
 Metric (BASELINE.json): train s/epoch on the PBMC8k-shape synthetic dataset (33,538 genes, 25,000 analysed droplets,
 8,000 expected cells; 255-droplet minibatches, 111 per epoch), with posterior droplets/s reported beside it.
 A "step" is one training minibatch: device-resident CSR gather -> encoders -> sampling -> decoder -> fused
 observation-term kernel (fwd+bwd) -> backward -> fused ClippedAdam.  ``value`` times K steps with row ids already
-on the device; ``e2e`` times the public ``SVI.step(batch)`` API including the host loader logic, the pinned
-host->device copy of each step's row ids and a device->host read of each step's loss.
+on the device (CUDA events); ``e2e`` times the public ``SVI.step(batch)`` API including the host loader logic, the pinned
+host->device copy of each step's row ids and a device->host read of each step's loss.  Inputs exceed L2 every step (275 MB
+of weights + 1.9 GB of optimizer state stream through the 126 MB L2).
+
+Other workloads (BASELINE.json configs 3 / 4): --workload citeseq | atlas.  The posterior pass (config 5: posterior +
+estimation from a trained / initialised model, barcode-sharded over the ranks) runs in every call unless --no-posterior.
 """
 import argparse
 import json
@@ -23,12 +28,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram bytes of one clipped_adam_kernel launch at the PBMC8k shape from the committed ncu --set full capture
-# (profiles/r01_step_kernels_ncu_summary.txt: 1.111406 GB read + 781.773 MB written)
-ADAM_NCU_DRAM_BYTES = 1.111406e9 + 781.773312e6
 METRIC = "train_s_per_epoch"
 UNIT = "s/epoch"
 WORKLOAD = "pbmc8k"
+# dram bytes of one full-buffer clipped_adam_kernel launch at the PBMC8k shape from the committed ncu --set full capture
+# (profiles/r01_step_kernels_ncu_summary.txt: 1.111406 GB read + 781.773 MB written)
+ADAM_NCU_DRAM_BYTES = 1.111406e9 + 781.773312e6
 
 
 def parse_args():
@@ -37,11 +42,14 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: host cores or the same GPU")
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-posterior", action="store_true")
-    ap.add_argument("--posterior-cells", type=int, default=8000)
+    ap.add_argument("--posterior-cells", type=int, default=None, help="default: the workload's expected cells")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline table")
     ap.add_argument("--short-warmup", action="store_true", help="profiling runs: skip the epoch-long graph warm-up")
+    ap.add_argument("--full-job", action="store_true", help="additionally time the whole job: 150 epochs + posterior + MCKP")
     return ap.parse_args()
 
 
@@ -124,37 +132,35 @@ class ClockSampler:
                 "samples": len(self.rows), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
-def job_estimate(s_per_epoch, posterior, torch_cuda, epochs: int = 150):
-    """Whole remove-background job at the reference's default 150 epochs, assembled from the parts measured in this
-    run: training + posterior + Mean targets + MCKP + output assembly.  Derived, not timed as one."""
-    try:
-        if posterior is None:
-            return None
-        est, asm = posterior.get("estimation") or {}, posterior.get("output_assembly") or {}
-        parts = {"train_s": epochs * float(s_per_epoch), "posterior_s": float(posterior["seconds"]),
-                 "mean_targets_s": float(est.get("mean_seconds") or 0.0), "mckp_s": float(est.get("mckp_seconds") or 0.0),
-                 "output_assembly_s": float(asm.get("denoise_seconds") or 0.0) + float(asm.get("restore_seconds") or 0.0)}
-        out = {"epochs": epochs, **parts, "total_s": sum(parts.values()),
-               "note": "sum of the separately measured phases of this run; posterior phase covers the benchmarked cells only"}
-        if torch_cuda is not None:
-            out["reference_torch_cuda_train_s"] = epochs * float(torch_cuda["value"])
-            out["train_speedup_vs_reference_torch_cuda"] = float(torch_cuda["value"]) / float(s_per_epoch)
-        return out
-    except Exception:  # a derived convenience figure must never break the bench line
-        return None
-
-
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         return json.load(open(path)), "measured"
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1390.0}, "fallback (B200_PROFILING.md)"
+
+
+def steps_per_epoch(ds) -> int:
+    n_train = int(round(0.9 * ds.analyzed_barcode_inds.size))
+    cell_bs = int(256 * 0.8)
+    return (n_train + cell_bs - 1) // cell_bs
+
+
+def workload_config(workload: str, ds, world: int) -> dict:
+    """The ``config`` object of the JSON line: describes the WORKLOAD only, so both arms print the same dict."""
+    spe = steps_per_epoch(ds)
+    return {"workload": workload, "genes": int(ds.analyzed_gene_inds.size), "analysed_droplets": int(ds.analyzed_barcode_inds.size),
+            "minibatch_rows": 255, "steps_per_epoch_global": spe, "steps_per_epoch_per_gpu": (spe + world - 1) // world,
+            "posterior": {"n_samples": 20, "n_counts_max": 20, "batch": 128},
+            "l2": "inputs > L2: each step streams 275 MB of weights + 1.9 GB of optimizer state through the 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------------------------
-# reference-style CPU arm (oracle port of the reference step; the oracle is only ever the baseline / the checker)
+# reference arms: the oracle port of the reference's step / posterior batch (the oracle is only ever the baseline / the
+# checker).  pyro-ppl, PyTables, anndata and matplotlib are in neither the image nor the wheelhouse, so the unmodified
+# reference cannot be installed (DESIGN.md): the port runs the reference's own arithmetic WITHOUT pyro's tracing
+# overhead, i.e. it is a lower bound on the reference's time.
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(ds, n_steps: int, warmup: int, z_dim=64, hidden=512, device="cpu"):
+def reference_steps(ds, n_steps: int, warmup: int, z_dim=64, hidden=512, device="cpu"):
     """Seconds per reference-style training step (oracle/train_step.py) on ``device``: the reference's host loader
     (scipy slicing + densify; plus, on a GPU, the 34 MB H2D copy of every dense minibatch, dataprep.py:291-292), the
     dense eager fp32 ELBO with the reference's own likelihood formula, autograd, per-tensor ClippedAdam."""
@@ -193,38 +199,192 @@ def cpu_reference_steps(ds, n_steps: int, warmup: int, z_dim=64, hidden=512, dev
     return (time.perf_counter() - t0) / n_steps
 
 
-def steps_per_epoch(ds) -> int:
-    n_train = int(round(0.9 * ds.analyzed_barcode_inds.size))
-    cell_bs = int(256 * 0.8)
-    return (n_train + cell_bs - 1) // cell_bs
+def reference_posterior(ds, n_batches: int, n_samples: int, device="cpu", z_dim=64, hidden=512):
+    """Droplets/s of the reference's posterior loop (posterior.py:424-594, 669-859) on ``device``, restated by the oracle:
+    per 128-cell minibatch the host loader densifies the counts (+ H2D), and for each of the ``n_samples`` latent samples
+    the encoders and the decoder run again, the dense [128, G, 20] noise-count log-prob tensor is built
+    (_log_prob_noise_count_tensor), normalised and folded into the running log-mean; then exp / two masked writes /
+    nonzero and the transfer of the COO pieces to the host.  Extrapolated linearly to the configured 20 samples."""
+    import torch
+
+    from oracle import pipeline as pl
+    from oracle import posterior as opost
+    from oracle import train_step as ots
+
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    cm = ds.get_count_matrix()
+    params, buffers = ots.init_state(cm.shape[1], z_dim, hidden, ds.priors, device=device)
+    cfg = ots.make_cfg(ds.priors, ds.empty_UMI_threshold, device=device)
+    cfg["offset"] = {"logit_p": 0.0, "epsilon": 0.0}
+    params = {k: v.detach() for k, v in params.items()}
+    on_gpu = str(device).startswith("cuda")
+
+    def batch(i):
+        x = torch.from_numpy(np.asarray(cm[i * 128:(i + 1) * 128].todense(), dtype=np.float32)).to(device)
+        total = low = None
+        for s in range(1, n_samples + 1):
+            mu, lam, alpha = pl.sample_mu_lambda_alpha(x, params, buffers, cfg, "full", device=device)
+            lp, low = opost.log_prob_noise_count_tensor(x, mu + 1e-30, lam + 1e-30, alpha + 1e-30, n_counts_max=20)
+            lp = lp - torch.logsumexp(lp, dim=-1, keepdim=True)
+            total = lp if s == 1 else torch.logaddexp(total + float(np.log(1 - 1 / s)), lp + float(np.log(1 / s)))
+        n_i, g_i, c_i, lpv, off = opost.sparsify_posterior(total, low, x, -10.0)
+        return [t.cpu() for t in (n_i, g_i, c_i, lpv, off)]
+
+    batch(0)  # warm-up
+    if on_gpu:
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n_batches):
+        batch(i + 1)
+    if on_gpu:
+        torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return 128.0 * n_batches / (dt * 20.0 / n_samples), dt
+
+
+def reference_mckp(coo_m, coo_c, coo_lp, off_m, off_v, shape, n_entries: int):
+    """Entries/s of the reference's MCKP estimator on a bounded slice of the posterior COO (whole (n, g) segments):
+    oracle/estimation.py restates estimation.py:420-702 as numpy segment loops (pinned bit-exact against the reference;
+    the reference itself runs pandas apply / nsmallest per gene chunk: SURVEY probe 0.18 M entries/s)."""
+    import scipy.sparse as sp
+
+    from oracle import estimation as oest
+
+    n = int(min(n_entries, coo_m.size))
+    while n < coo_m.size and coo_m[n] == coo_m[n - 1]:
+        n += 1
+    m, c, lp = coo_m[:n], coo_c[:n], coo_lp[:n]
+    coo = sp.coo_matrix((lp, (m, c)), shape=(shape[0] * shape[1], 20))
+    offs = {int(k): int(v) for k, v in zip(off_m, off_v) if k <= m[-1]}
+    t0 = time.perf_counter()
+    mean = oest.estimate_mean(coo, offs, shape)
+    tgt = np.asarray(mean.sum(axis=0)).ravel().astype(np.float64) * 1.1
+    oest.estimate_mckp(coo, offs, shape, tgt)
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
+
     from cellbender_b200 import synth
 
-    ds = synth.make_config_dataset(args.workload, device="cpu" if not _cuda() else None)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    on_gpu = args.device == "cuda"
+    if on_gpu:
+        assert torch.cuda.is_available(), "--impl reference --device cuda needs a GPU"
+    dev = "cuda:0" if on_gpu else "cpu"
+    ds = synth.make_config_dataset(args.workload, device="cuda:0" if torch.cuda.is_available() else "cpu")
     spe = steps_per_epoch(ds)
-    k = max(1, min(args.steps, 30))  # bounded sample: each CPU step is ~0.5-1 s at this shape
-    w = max(1, min(args.warmup, 3))
-    s_step = cpu_reference_steps(ds, k, w)
-    value = s_step * spe
+    # each step is a bounded sample of the workload (one 255-row minibatch, ~0.5 s on the host); K and W are honoured
+    # up to a cap that keeps the run within a few minutes
+    k = max(1, min(args.steps, 200 if on_gpu else 60))
+    w = max(0, min(args.warmup, 20 if on_gpu else 10))
+    s_step = reference_steps(ds, k, w, device=dev)
+    spe_rank = (spe + world - 1) // world
+    value = s_step * spe  # the reference is single-process: an epoch is the global number of minibatches
+    post = None
+    if not args.no_posterior:
+        n_b, n_s = (4, 20) if on_gpu else (1, 2)
+        rate, dt = reference_posterior(ds, n_b, n_s, device=dev)
+        post = {"droplets_per_s": rate, "sample": f"{n_b} minibatches of 128 cells x {n_s} latent samples in {dt:.2f} s, scaled to 20 samples"}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": w,
             "ms_per_step": s_step * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": args.workload, "steps_per_epoch": spe, "minibatch_rows": 255},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "data": "synthetic", "config": workload_config(args.workload, ds, world),
+            "reference_device": "torch-CUDA on the same B200 (pyro overhead excluded)" if on_gpu else "host cores",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count() if not on_gpu else 0, "kind": "port",
                              "sample": f"{k} minibatch steps of the {args.workload} shape (reference loader + dense eager ELBO "
-                                       f"+ per-tensor ClippedAdam, pyro overhead excluded), extrapolated to {spe} steps/epoch"},
+                                       f"+ per-tensor ClippedAdam, pyro overhead excluded) x {spe} steps/epoch"
+                                       + ("; on the GPU: + 34 MB H2D per minibatch" if on_gpu else "")},
+            "posterior": post,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    _ = spe_rank
     print(json.dumps(line), flush=True)
 
 
-def _cuda():
+# ------------------------------------------------------------------------------------------------------------
+# per-kernel rooflines, timed live (CUDA events on the launching stream, L2 flushed between launches)
+# ------------------------------------------------------------------------------------------------------------
+def kernel_table(model, opt, svi, batch, peaks, dev):
     import torch
 
-    return torch.cuda.is_available()
+    from cellbender_b200 import _cabi, ops
+
+    lib = _cabi.lib()
+    hbm = peaks["hbm_gbs"]
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps=7):
+        ts = []
+        for _ in range(reps):
+            flush.zero_()  # L2 flush between timed launches (buffer > 126 MB L2)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    def row(ms, nbytes, note=""):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return {"ms": ms, "algorithmic_bytes": nbytes, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm, **({"note": note} if note else {})}
+
+    out = {}
+    G, B = model.n_genes, batch.size(0)
+    H = model.decoder.out_linear.weight.shape[1]
+    # ---- the optimizer sweep over the whole flat buffer
+    step_save = opt.step_count.clone()
+    ms = timed(lambda: ops.clipped_adam_step(opt.flat_p, opt.flat_g, opt.flat_m, opt.flat_v, opt.lr_table, opt.beta1_table,
+                                             opt.step_count, grad_scale=0.0, step_table=opt.step_table), reps=9)
+    opt.step_count.copy_(step_save)
+    out["clipped_adam_kernel"] = row(ms, 28.0 * opt.n, "read p, g, m, v; write p, m, v (fp32); zero gradient scale")
+    # ---- the large contractions (PBMC8k: algorithmic bytes = weight matrix + the [B, G] activation / gradient matrix)
+    g = torch.Generator(device=dev).manual_seed(0)
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+    ldG = ops.row_pitch(G + 32)
+    x, W, W2 = rn(B, ldG), rn(H, ldG), rn(H, ldG)
+    Wd, h, dy, dy2, dl, bias = rn(G, H), rn(B, H), rn(B, H), rn(B, H), rn(B, ldG), rn(G)
+    o_bh, o_bg = ops.alloc_rows(B, H, dev), ops.alloc_rows(B, G, dev)
+    dW, dWd = torch.zeros(H, ldG, device=dev), torch.zeros(G, H, device=dev)
+    wb = 4.0 * G * H + 4.0 * B * G
+    out["gemm_encoder_forward"] = row(timed(lambda: ops.gemm_tf32(x, W[:, 32:32 + G], B, H, G, out=o_bh[:, :H])), wb, "split-K + reduce")
+    out["gemm_decoder_forward"] = row(timed(lambda: ops.gemm_tf32(h, Wd, B, G, H, out=o_bg[:, :G], bias=bias, split_k=1)), wb)
+    out["gemm_dh"] = row(timed(lambda: ops.gemm_tf32(dl, Wd, B, H, G, b_mn=True, out=o_bh[:, :H])), wb, "split-K + reduce")
+    out["gemm_dW_encoder"] = row(timed(lambda: ops.gemm_tf32(dy, x, H, G, B, a_mn=True, b_mn=True, out=dW[:, 32:32 + G], split_k=1)), wb)
+    out["gemm_dW_decoder"] = row(timed(lambda: ops.gemm_tf32(dl, h, G, H, B, a_mn=True, b_mn=True, out=dWd, split_k=1)), wb)
+    out["gemm_dX_pair"] = row(timed(lambda: ops.gemm_tf32(dy, W[:, 32:32 + G], B, G, H, b_mn=True, out=o_bg[:, :G], split_k=1, a2=dy2,
+                                                          b2=W2[:, 32:32 + G], K2=H)), 8.0 * G * H + 4.0 * B * G)
+    # ---- the fused observation kernel on one minibatch
+    inp = batch.encoder_inputs(svi._ambient_unit_vector())
+    with torch.no_grad():
+        model.elbo_terms(batch.loader.csr, batch.row_ids, inp)
+    csr_, rows_, bufs_ = model._obs_ctx
+    coef = torch.rand((B, 7), device=dev) * torch.tensor([3000, 100, 30, 100, 3, 100, 3], device=dev)
+    wts, al = -torch.rand((B, 3), device=dev), torch.tensor([5.0], device=dev)
+    oo = bufs_["obs_out"]
+    ptr = _cabi.ptr
+    ms = timed(lambda: lib.call(
+        "cb_elbo_obs_fwd_bwd", ptr(csr_.indptr), ptr(csr_.indices), ptr(csr_.data), ptr(rows_), B, G, ptr(bufs_["logits"]),
+        bufs_["logits"].stride(0), ptr(bufs_["chi_a"]), ptr(bufs_["chi_b"]), ptr(coef), ptr(al), ptr(wts), ptr(oo["sums"]),
+        ptr(oo["dlogits"]), ptr(oo["qamb"]), bufs_["logits"].stride(0), ptr(oo["lse"]), ptr(oo["nan_flag"]), _cabi.current_stream()))
+    out["elbo_obs_kernel"] = {**row(ms, 12.0 * B * G, "read logits, write dlogits, write qamb; bound is FP32 / XU issue, not HBM"),
+                              "elements_per_s": 2.0 * B * G / (ms * 1e-3)}
+    model.nan_flag.zero_()
+    # ---- gather + batchnorm0
+    unit = svi._ambient_unit_vector()
+    out["gather_rows_kernel"] = row(timed(lambda: batch.encoder_inputs(unit)), 8.0 * B * G, "write norm + lognorm rows")
+    enc_o = model.encoder["other"]
+    keep = torch.full((B,), 2.0, device=dev)
+    from cellbender_b200 import gemm
+
+    with torch.no_grad():
+        out["bn0_forward_kernel"] = row(timed(lambda: gemm.bn0_dropout(inp.x_lognorm, enc_o.batchnorm0, keep, True, G)), 8.0 * B * G)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -232,7 +392,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from cellbender_b200 import _cabi, ops, run, synth
+    from cellbender_b200 import _cabi, dp, ops, run, synth
     from cellbender_b200.posterior import Posterior
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -244,17 +404,18 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     lib = _cabi.lib()
+    peaks, peak_src = measured_peaks()
 
     # ---- synthetic dataset of the named shape, generated on the device (seed 0 on every rank) ----
     ds = synth.make_config_dataset(args.workload, seed=0, device=dev)
     a = run.default_args()
     model, opt, svi, train_loader, test_loader = run.setup_inference(ds, a, device=dev, rank=rank, world_size=world)
-    spe_global = steps_per_epoch(ds)
+    cfg = workload_config(args.workload, ds, world)
+    spe_global, spe_rank = cfg["steps_per_epoch_global"], cfg["steps_per_epoch_per_gpu"]
     model.train()
     if world > 1:
-        from cellbender_b200 import dp
-
         dp.attach(svi, world)
+        opt.p2p_timing = True
 
     def fresh_batches(n):
         out = []
@@ -315,155 +476,172 @@ def run_b200(args):
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
     model.check_nan()
+    # ---- (3) one real epoch through train.train_epoch: the loader's own epoch (all minibatches incl. the short last one),
+    # losses accumulated on the device and read once -- wall clock ----
+    from cellbender_b200 import train as cb_train
 
-    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    while True:  # align to an epoch boundary
+        try:
+            svi.step(next(train_loader))
+        except StopIteration:
+            break
+    barrier()
+    t0 = time.perf_counter()
+    cb_train.train_epoch(svi, train_loader)
+    barrier()
+    epoch_wall = time.perf_counter() - t0
+
+    t = torch.tensor([ms_dev, ms_e2e, epoch_wall], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    ms_dev, ms_e2e, epoch_wall = float(t[0]), float(t[1]), float(t[2])
     ms_per_step = ms_dev / K
     # weak scaling: every rank steps through its own shard, so an epoch needs spe_global / world steps per rank
-    spe_rank = (spe_global + world - 1) // world
     value = ms_per_step * spe_rank / 1e3
     e2e_value = (ms_e2e / K) * spe_rank / 1e3
+    dp_exchange_ms = None
+    if world > 1:
+        tm = dp.p2p_timing(opt)
+        if tm is not None:
+            dp_exchange_ms = {"barrier_before": tm[0], "fused_exchange_kernel": tm[1], "barrier_after": tm[2],
+                              "exposed_total": sum(tm), "nvls": bool(dp.p2p_uses_nvls(opt, world))}
 
-    # ---- roofline of the dominant HBM-bound kernel of the step (fused ClippedAdam), timed live ----
-    peaks, peak_src = measured_peaks()
-    n_param = opt.n
-    reps = 20
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    step_save = opt.step_count.clone()
-    e0.record()
-    for _ in range(reps):
-        ops.clipped_adam_step(opt.flat_p, opt.flat_g, opt.flat_m, opt.flat_v, opt.lr_table, opt.beta1_table, opt.step_count,
-                              grad_scale=0.0)  # zero gradient scale: parameters move only by the (tiny) momentum term
-    e1.record()
-    torch.cuda.synchronize()
-    opt.step_count.copy_(step_save)
-    adam_ms = e0.elapsed_time(e1) / reps
-    adam_bytes = 28.0 * n_param  # read p, g, m, v; write p, m, v  (fp32)
-    adam_gbs = adam_bytes / (adam_ms * 1e-3) / 1e9
-    # the fused observation kernel, timed the same way on one 255-row minibatch
-    b = batches[0]
-    inp = b.encoder_inputs(svi._ambient_unit_vector())
-    with torch.no_grad():
-        model.elbo_terms(b.loader.csr, b.row_ids, inp)
-    csr_, rows_, bufs_ = model._obs_ctx
-    Bn, Gn = b.size(0), model.n_genes
-    coef = torch.rand((Bn, 7), device=dev) * torch.tensor([3000, 100, 30, 100, 3, 100, 3], device=dev)
-    wts = -torch.rand((Bn, 3), device=dev)
-    al = torch.tensor([5.0], device=dev)
-    oo = bufs_["obs_out"]
-    outd = {"sums": oo["sums"][:Bn], "dlogits": oo["dlogits"][:Bn], "qamb": oo["qamb"][:Bn], "dchi_ambient": oo["dchi_ambient"],
-            "lse": oo["lse"], "nan_flag": oo["nan_flag"]}
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-    obs_ms = []
-    for _ in range(8):
-        flush.zero_()  # L2 flush between timed launches (buffer > 126 MB L2)
-        e0.record()
-        lib.call("cb_elbo_obs_fwd_bwd", _cabi.ptr(csr_.indptr), _cabi.ptr(csr_.indices), _cabi.ptr(csr_.data), _cabi.ptr(rows_),
-                 Bn, Gn, _cabi.ptr(bufs_["logits"]), bufs_["logits"].stride(0), _cabi.ptr(bufs_["chi_a"]), _cabi.ptr(bufs_["chi_b"]),
-                 _cabi.ptr(coef), _cabi.ptr(al), _cabi.ptr(wts), _cabi.ptr(outd["sums"]), _cabi.ptr(outd["dlogits"]),
-                 _cabi.ptr(outd["qamb"]), bufs_["logits"].stride(0), _cabi.ptr(outd["lse"]), _cabi.ptr(outd["nan_flag"]),
-                 _cabi.current_stream())
-        e1.record()
-        torch.cuda.synchronize()
-        obs_ms.append(e0.elapsed_time(e1))
-    obs_ms = float(np.median(obs_ms))
-    obs_bytes = 12.0 * Bn * Gn  # read logits, write dlogits, write qamb (fp32); CSR + profiles are negligible
-    model.nan_flag.zero_()
+    # ---- per-kernel rooflines (rank 0) ----
+    kernels = None
+    if rank == 0 and not args.no_kernels:
+        kernels = kernel_table(model, opt, svi, batches[0], peaks, dev)
 
-    # ---- posterior droplets/s on a bounded sample of cells (encoder once + 20 samples + COO emission) ----
+    # ---- posterior droplets/s: encoder once + 20 samples + decoder GEMM + noise-count window + COO; barcode-sharded ----
     posterior = None
-    if not args.no_posterior and rank == 0:
+    if not args.no_posterior:
         model.eval()
         post = Posterior(ds, model, posterior_batch_size=128)
-        # random-init weights call few droplets cells; run the pass on the top-UMI droplets instead: all expected cells
-        n_cells = min(args.posterior_cells, int(ds.analyzed_barcode_inds.size))
-        post._latents = {"p": np.concatenate([np.ones(n_cells), np.zeros(ds.analyzed_barcode_inds.size - n_cells)]), "z": None,
-                         "d": None, "epsilon": None, "phi_loc_scale": None}
+        n_all = int(ds.analyzed_barcode_inds.size)
+        # random-init weights call few droplets cells: run the pass on the top-UMI droplets instead (all expected cells)
+        n_cells = int(min(args.posterior_cells or synth.CONFIGS[args.workload]["expected_cells"], n_all))
+        post._latents = {"p": np.concatenate([np.ones(n_cells), np.zeros(n_all - n_cells)]), "z": None, "d": None,
+                         "epsilon": None, "phi_loc_scale": None}
+        cpc = post.cells_per_chunk
+        shard = dp.shard_cells(n_cells, rank, world, align=cpc) if world > 1 else None
         post.device_posterior(cell_subset=np.arange(min(128, n_cells)))  # warm-up
         times = []
         for _ in range(3):
-            torch.cuda.synchronize()
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
-            dp_ = post.device_posterior()
-            torch.cuda.synchronize()
-            times.append(time.perf_counter() - t0)
-        dt = float(np.median(times))
-        n_entries = int(dp_.m.numel())
-        posterior = {"droplets_per_s": n_cells / dt, "cells": n_cells, "n_samples": 20, "coo_entries": n_entries, "seconds": dt,
-                     "timing": "median of 3 full passes (encoder once per chunk, 20 latent samples, decoder GEMM, "
-                               "noise-count window over the stored counts, thresholded COO left on the device)"}
-        # estimation on that posterior through the reference-facing API (scipy CSR results on the host):
-        # Mean (-> per-gene MCKP targets at FPR 0.01, posterior.py:1589-1650) and the default MCKP estimator
-        from cellbender_b200.estimation import Mean, MultipleChoiceKnapsack
-
-        conv = post.index_converter
-        t0 = time.perf_counter()
-        mean_csr = Mean(index_converter=conv).estimate_noise(dp_, None, device=dev)
-        torch.cuda.synchronize()
-        t_mean = time.perf_counter() - t0
-        cell_rows = np.asarray(ds.analyzed_barcode_inds)[:n_cells]
-        raw = ds.matrix[cell_rows].astype(np.float64) if hasattr(ds, "matrix") else None
-        tgt = np.asarray(mean_csr.sum(axis=0)).ravel().astype(np.float64)
-        if raw is not None:
-            tgt = tgt + 0.01 * (np.asarray(raw.sum(axis=0)).ravel() - tgt)
-        t0 = time.perf_counter()
-        noise_csr = MultipleChoiceKnapsack(index_converter=conv).estimate_noise(dp_, None, noise_targets_per_gene=tgt, device=dev)
-        torch.cuda.synchronize()
-        t_mckp = time.perf_counter() - t0
-        posterior["estimation"] = {"mean_seconds": t_mean, "mckp_seconds": t_mckp, "mckp_entries_per_s": n_entries / t_mckp,
-                                   "noise_counts_removed": int(noise_csr.sum()), "output": "scipy CSR on the host (reference API)"}
-        # output assembly through the reference-facing API (scipy in, scipy CSC out): counts of the called cells minus
-        # their noise, every other droplet emptied (posterior.py:315-328), then restore_eliminated_features_in_cells
-        from cellbender_b200.sparse_utils import restore_eliminated_features_in_cells, subtract_noise_in_cells
-
-        subtract_noise_in_cells(ds.matrix[:64], noise_csr[:64], np.arange(8))  # warm-up
-        t0 = time.perf_counter()
-        denoised = subtract_noise_in_cells(ds.matrix, noise_csr, cell_rows)
-        t_den = time.perf_counter() - t0
-        p_all = np.zeros(int(ds.analyzed_barcode_inds.size))
-        p_all[:n_cells] = 1.0
-        t0 = time.perf_counter()
-        restored = restore_eliminated_features_in_cells(denoised, ds.matrix, ds.analyzed_gene_inds, ds.analyzed_barcode_inds, p_all)
-        t_res = time.perf_counter() - t0
-        # the same combine with operands already resident in HBM, CUDA events (kernels + scans + the radix sort of the
-        # CSR -> CSC step); algorithmic bytes = read both operands once (index + value) + write the result once
-        from cellbender_b200 import sparse_utils as su
-
-        vdt = su._value_dtype(ds.matrix.dtype, noise_csr.dtype)
-        dev_a = su.DeviceSparse.from_scipy(ds.matrix, vdt, dev)
-        dev_b = su.DeviceSparse.from_scipy(noise_csr, vdt, dev)
-        keep = su._mask(dev_a.shape[0], cell_rows, dev)
-        ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        for _ in range(2):
             ev0.record()
-            dev_out = su.combine_device(dev_a, dev_b, -1, keep, None)
+            piece = post.device_posterior(cell_subset=shard)
             ev1.record()
-            dev_out.transpose()
-            ev2.record()
-        torch.cuda.synchronize()
-        item = 4 + vdt.itemsize
-        comb_bytes = item * (dev_a.nnz + dev_b.nnz + dev_out.nnz) + 8 * 3 * (dev_a.shape[0] + 1)
-        comb_ms, tr_ms = ev0.elapsed_time(ev1), ev1.elapsed_time(ev2)
-        posterior["output_assembly_device"] = {
-            "combine_ms": comb_ms, "csr_to_csc_ms": tr_ms, "algorithmic_bytes": comb_bytes,
-            "combine_gbs": comb_bytes / comb_ms / 1e6, "hbm_frac": comb_bytes / comb_ms / 1e6 / peaks["hbm_gbs"],
-            "note": "second of two back-to-back runs; includes the host read-back of the output size between the passes"}
-        posterior["output_assembly"] = {"denoise_seconds": t_den, "restore_seconds": t_res, "stored_counts_in": int(ds.matrix.nnz),
-                                        "stored_counts_out": int(restored.nnz), "counts_out": int(restored.sum()),
-                                        "note": "host scipy in -> device combine -> host scipy CSC out, transfers included"}
+            torch.cuda.synchronize()
+            times.append((time.perf_counter() - t0, ev0.elapsed_time(ev1) * 1e-3))
+        dt_wall, dt_dev = (float(np.median([x[i] for x in times])) for i in (0, 1))
+        tt = torch.tensor([dt_wall, dt_dev], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            barrier()
+            t0 = time.perf_counter()
+            dev_post = dp.gather_posterior(piece, world)
+            torch.cuda.synchronize()
+            gather_s = time.perf_counter() - t0
+        else:
+            dev_post, gather_s = piece, 0.0
+        dt_wall, dt_dev = float(tt[0]), float(tt[1])
+        n_entries = int(dev_post.m.numel())
+        S, Hd, G = 20, model.decoder.out_linear.weight.shape[1], model.n_genes
+        flops = 2.0 * n_cells * S * Hd * G / world  # decoder output layer, per rank
+        logit_bytes = 2.0 * 4.0 * n_cells * S * G / world  # transposed logits written once, read once (column logsumexp)
+        tf32_peak = 0.5 * peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        t_roof = max(flops / (tf32_peak * 1e12), logit_bytes / (peaks["hbm_gbs"] * 1e9))
+        posterior = {"droplets_per_s": n_cells / dt_wall, "cells": n_cells, "n_samples": S, "coo_entries": n_entries,
+                     "seconds": dt_wall, "seconds_device": dt_dev, "gather_seconds": gather_s, "ranks": world,
+                     "timing": "median of 3 full passes, max over ranks (encoder once per 512-cell chunk, 20 latent samples, one "
+                               "transposed decoder GEMM per chunk, column logsumexp, noise-count window over the stored counts, "
+                               "thresholded (m, c)-sorted COO left on the device; one host sync per pass)",
+                     "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel (decoder output layer, all samples of a chunk)",
+                                  "achieved": flops / dt_dev / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                                  "frac": t_roof / dt_dev,
+                                  "peak_source": f"0.5 x bf16_tflops_sustained ({peak_src}): TF32 runs at half the bf16 rate",
+                                  "note": "frac = time at the roofline max(decoder flops / TF32 peak, logits bytes / HBM peak) / measured "
+                                          "device time of the WHOLE pass; achieved = decoder flops / whole-pass time"}}
+        if rank == 0:
+            # the reference-facing API: scipy COO + offsets dict on the host (D2H of the whole COO included)
+            if world == 1:
+                t0 = time.perf_counter()
+                post._noise_count_posterior_coo = None
+                coo = post.cell_noise_count_posterior_coo()
+                posterior["api_seconds_scipy_coo_on_host"] = time.perf_counter() - t0
+                posterior["api_droplets_per_s"] = n_cells / posterior["api_seconds_scipy_coo_on_host"]
+                del coo
+            # estimation on that posterior through the reference-facing API (scipy CSR results on the host):
+            # Mean (-> per-gene MCKP targets at FPR 0.01, posterior.py:1589-1650) and the default MCKP estimator
+            from cellbender_b200.estimation import Mean, MultipleChoiceKnapsack
+
+            conv = post.index_converter
+            Mean(index_converter=conv).estimate_noise(dev_post, None, device=dev)  # warm-up
+            t0 = time.perf_counter()
+            mean_csr = Mean(index_converter=conv).estimate_noise(dev_post, None, device=dev)
+            torch.cuda.synchronize()
+            t_mean = time.perf_counter() - t0
+            cell_rows = np.asarray(ds.analyzed_barcode_inds)[:n_cells]
+            tgt = np.asarray(mean_csr.sum(axis=0)).ravel().astype(np.float64)
+            tgt = tgt + 0.01 * (np.asarray(ds.matrix[cell_rows].astype(np.float64).sum(axis=0)).ravel() - tgt)
+            t0 = time.perf_counter()
+            noise_csr = MultipleChoiceKnapsack(index_converter=conv).estimate_noise(dev_post, None, noise_targets_per_gene=tgt, device=dev)
+            torch.cuda.synchronize()
+            t_mckp = time.perf_counter() - t0
+            posterior["estimation"] = {"mean_seconds": t_mean, "mckp_seconds": t_mckp, "mckp_entries_per_s": n_entries / t_mckp,
+                                       "noise_counts_removed": int(noise_csr.sum()), "output": "scipy CSR on the host (reference API)"}
+            if not args.no_cpu_baseline and world == 1:
+                rate, n_used, dt = reference_mckp(dev_post.m[:400000].cpu().numpy(), dev_post.c[:400000].cpu().numpy(),
+                                                  dev_post.log_prob[:400000].cpu().numpy(), dev_post.off_m.cpu().numpy(),
+                                                  dev_post.off_v.cpu().numpy(), ds.matrix.shape, 200000)
+                posterior["estimation"]["reference_mckp_entries_per_s"] = rate
+                posterior["estimation"]["reference_mckp_sample"] = f"{n_used} COO entries in {dt:.2f} s on the host (oracle restatement, 1 core)"
+            # output assembly through the reference-facing API (scipy in, scipy CSC out): counts of the called cells minus
+            # their noise, every other droplet emptied (posterior.py:315-328), then restore_eliminated_features_in_cells
+            from cellbender_b200 import sparse_utils as su
+
+            su.subtract_noise_in_cells(ds.matrix[:64], noise_csr[:64], np.arange(8))  # warm-up
+            t0 = time.perf_counter()
+            denoised = su.subtract_noise_in_cells(ds.matrix, noise_csr, cell_rows)
+            t_den = time.perf_counter() - t0
+            p_all = np.zeros(n_all)
+            p_all[:n_cells] = 1.0
+            t0 = time.perf_counter()
+            restored = su.restore_eliminated_features_in_cells(denoised, ds.matrix, ds.analyzed_gene_inds, ds.analyzed_barcode_inds, p_all)
+            t_res = time.perf_counter() - t0
+            vdt = su._value_dtype(ds.matrix.dtype, noise_csr.dtype)
+            dev_a, dev_b = su.DeviceSparse.from_scipy(ds.matrix, vdt, dev), su.DeviceSparse.from_scipy(noise_csr, vdt, dev)
+            keep = su._mask(dev_a.shape[0], cell_rows, dev)
+            ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            for _ in range(2):
+                ev0.record()
+                dev_out = su.combine_device(dev_a, dev_b, -1, keep, None)
+                ev1.record()
+                dev_out.transpose()
+                ev2.record()
+            torch.cuda.synchronize()
+            item = 4 + vdt.itemsize
+            comb_bytes = item * (dev_a.nnz + dev_b.nnz + dev_out.nnz) + 8 * 3 * (dev_a.shape[0] + 1)
+            comb_ms, tr_ms = ev0.elapsed_time(ev1), ev1.elapsed_time(ev2)
+            posterior["output_assembly"] = {
+                "denoise_seconds": t_den, "restore_seconds": t_res, "stored_counts_in": int(ds.matrix.nnz),
+                "stored_counts_out": int(restored.nnz), "device_combine_ms": comb_ms, "device_csr_to_csc_ms": tr_ms,
+                "device_combine_frac_of_hbm_peak": comb_bytes / comb_ms / 1e6 / peaks["hbm_gbs"],
+                "note": "host scipy in -> device combine -> host scipy CSC out, transfers included; device_* = operands resident"}
         model.train()
 
-    if world > 1 and os.environ.get("CB_DP_TIMING") == "1":
-        from cellbender_b200 import dp as _dp
-
-        tm = _dp.p2p_timing(svi.optim)
-        if tm is not None:
-            sys.stderr.write(f"[rank {rank}] p2p exchange: barrier {tm[0]:.4f} ms, fused kernel {tm[1]:.4f} ms, "
-                             f"barrier {tm[2]:.4f} ms\n")
-            sys.stderr.flush()
+    # ---- the whole job, measured (optional): 150 epochs through run_training + posterior + MCKP + output assembly ----
+    full_job = None
+    if args.full_job and world == 1:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        a_full = run.default_args(epochs=150)
+        post_full, denoised_full = run.run_remove_background(ds, a_full, device=dev)
+        torch.cuda.synchronize()
+        full_job = {"seconds": time.perf_counter() - t0, "epochs": 150, "cells_called": int((post_full.latents_map["p"] > 0.5).sum()),
+                    "note": "run_remove_background: run_inference (150 epochs, test pass every 5) + latents + posterior COO (scipy on the "
+                            "host) + Mean targets + MCKP + denoised counts + restore, through the public API"}
 
     def shutdown():
         if world > 1:
@@ -476,51 +654,55 @@ def run_b200(args):
         shutdown()
         return
 
-    # ---- CPU baseline: the reference-style port on this box's host cores, bounded sample ----
-    cpu = None
-    torch_cuda = None
+    # ---- baselines timed on this box (N = 1 only): the reference's CPU path and its torch-CUDA path (oracle port) ----
+    cpu = torch_cuda = None
     if not args.no_cpu_baseline and world == 1:
         k_cpu = 16
-        s_step = cpu_reference_steps(ds, k_cpu, 2)
+        s_step = reference_steps(ds, k_cpu, 2)
         cpu = {"value": s_step * spe_global, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                "sample": f"{k_cpu} minibatch steps of the {args.workload} shape on the host (reference loader + dense eager "
                          f"fp32 ELBO + per-tensor ClippedAdam; pyro overhead excluded), x {spe_global} steps/epoch"}
-        # the reference's torch-CUDA path, same stand-in on this GPU: a LOWER bound on the real
-        # `--cuda` step time because pyro's tracing / enumeration Python overhead is not in it
         k_gpu = 20
-        s_gpu = cpu_reference_steps(ds, k_gpu, 3, device=dev)
+        s_gpu = reference_steps(ds, k_gpu, 3, device=dev)
         torch_cuda = {"value": s_gpu * spe_global, "unit": UNIT, "ms_per_step": s_gpu * 1e3, "kind": "port",
                       "sample": f"{k_gpu} steps: reference host loader + 34 MB H2D per minibatch + dense eager torch fp32 ELBO "
-                                f"(reference modules' arithmetic) + per-tensor ClippedAdam on the same B200; pyro overhead excluded"}
+                                f"(reference modules' arithmetic) + per-tensor ClippedAdam on the same B200; pyro overhead excluded",
+                      "train_speedup": s_gpu * spe_global / value}
+        if posterior is not None:
+            rate_gpu, dt_g = reference_posterior(ds, 4, 20, device=dev)
+            rate_cpu, dt_c = reference_posterior(ds, 1, 2, device="cpu")
+            posterior["reference_torch_cuda_droplets_per_s"] = rate_gpu
+            posterior["reference_cpu_droplets_per_s"] = rate_cpu
+            posterior["reference_sample"] = (f"torch-CUDA: 4 x 128 cells x 20 samples in {dt_g:.2f} s; host ({os.cpu_count()} cores): "
+                                             f"1 x 128 cells x 2 samples in {dt_c:.2f} s scaled to 20 samples; dense [128, G, 20] path "
+                                             f"of posterior.py:784-859, pyro overhead excluded")
+            posterior["speedup_vs_reference_torch_cuda"] = posterior["droplets_per_s"] / rate_gpu
 
-    job = job_estimate(value, posterior, torch_cuda)
+    adam = (kernels or {}).get("clipped_adam_kernel")
+    step_bytes = 16.0 * model.n_genes * 512 * 2 + 4.0 * model.n_genes * 512 + 16.0 * 255 * model.n_genes + 28.0 * opt.n
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": args.workload, "genes": model.n_genes, "analysed_droplets": int(ds.analyzed_barcode_inds.size),
-                   "minibatch_rows": 255, "steps_per_epoch_per_gpu": spe_rank, "steps_per_epoch_global": spe_global,
-                   "l2": "inputs > L2: each step streams 275 MB of weights + 1.9 GB of optimizer state",
-                   "gemm": "tcgen05 kind::tf32 (fp32 accumulate); tolerance 2e-3 relative on ELBO terms, end-to-end 1 % "
-                           "(tests/test_step_gpu.py, tests/test_e2e_gpu.py)",
-                   "dp_exchange": (None if world == 1 else
-                                   "p2p: exchange fused into the ClippedAdam sweep over NVLink peer memory"
-                                   if getattr(svi.optim, "symm_p", None) is not None and os.environ.get("CB_DP_MODE", "p2p") == "p2p"
-                                   else os.environ.get("CB_DP_MODE", "sharded (NCCL)"))},
+        "data": "synthetic", "config": cfg,
+        "implementation": {"gemm": "tcgen05 kind::tf32 (fp32 accumulate), TMA loads + TMA-store epilogue; tolerance 2e-3 relative on "
+                                   "ELBO terms, end to end within 1 % of the reference-style fp32 pipeline (tests/test_e2e_gpu.py)",
+                           "dp_exchange": None if world == 1 else getattr(svi, "dp_mode", None)},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * 255, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / K,
                 "note": "counts are device-resident (uploaded once); per step only the 255 row ids go host->device"},
+        "epoch_wall_s": epoch_wall,
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "clipped_adam_kernel", "achieved": adam_gbs, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": adam_gbs / peaks["hbm_gbs"], "traffic": ADAM_NCU_DRAM_BYTES, "peak_source": peak_src,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of clipped_adam_kernel, ncu --set full, "
-                                       "profiles/r01_step_kernels_ncu_summary.txt",
-                     "algorithmic_bytes_per_launch": adam_bytes, "ms_per_launch": adam_ms},
-        "kernels": {"elbo_obs_kernel": {"ms": obs_ms, "algorithmic_bytes": obs_bytes,
-                                        "achieved_GBps": obs_bytes / (obs_ms * 1e-3) / 1e9,
-                                        "elements_per_s": 2.0 * Bn * Gn / (obs_ms * 1e-3)}},
-        "cpu_baseline": cpu, "reference_torch_cuda": torch_cuda, "posterior": posterior, "job_estimate": job,
+        "roofline": None if adam is None else {
+            "bound": "hbm", "kernel": "clipped_adam_kernel", "achieved": adam["achieved_GBps"], "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": adam["frac_of_hbm_peak"], "traffic": ADAM_NCU_DRAM_BYTES, "peak_source": peak_src,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of clipped_adam_kernel, ncu --set full, "
+                              "profiles/r01_step_kernels_ncu_summary.txt",
+            "algorithmic_bytes_per_launch": adam["algorithmic_bytes"], "ms_per_launch": adam["ms"]},
+        "roofline_step": {"bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+        "dp_exchange_ms": dp_exchange_ms,
+        "kernels": kernels, "cpu_baseline": cpu, "reference_torch_cuda": torch_cuda, "posterior": posterior, "full_job": full_job,
     }
     print(json.dumps(line), flush=True)
     shutdown()

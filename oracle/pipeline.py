@@ -182,7 +182,7 @@ def latents_map(ds, state, batch: int = 500) -> Dict[str, np.ndarray]:
 
 
 @torch.no_grad()
-def sample_mu_lambda_alpha(x, params, buffers, cfg, model_type: str = "full"):
+def sample_mu_lambda_alpha(x, params, buffers, cfg, model_type: str = "full", device=None):
     """One latent sample of (mu, lam, alpha) for the dense minibatch x as Posterior.sample_mu_lambda_alpha returns it
     (posterior.py:737-782): guide draws, y forced to its MAP, and the model's returned ``lam`` -- which is the lambda of
     the obs_empty regulariser block (epsilon = 1, y = 0; model.py:385-393 overwrites ``lam`` before the return at :445)."""
@@ -202,8 +202,10 @@ def sample_mu_lambda_alpha(x, params, buffers, cfg, model_type: str = "full"):
     y = (enc["p_y"] > 0).float()
     chi = ovae.decode(z, sub("dec."), training=False)
     mu = onb.calculate_mu(model_type, epsilon=epsilon, d_cell=d_cell, chi=chi, y=y, rho=rho)
-    lam = onb.calculate_lambda(model_type, epsilon=torch.ones(B), chi_ambient=ps["chi_ambient"], d_empty=d_empty,
-                               y=torch.zeros(B), d_cell=d_cell, rho=rho, chi_bar=torch.as_tensor(cfg["chi_bar"]))
+    dev = x.device
+    lam = onb.calculate_lambda(model_type, epsilon=torch.ones(B, device=dev), chi_ambient=ps["chi_ambient"], d_empty=d_empty,
+                               y=torch.zeros(B, device=dev), d_cell=d_cell, rho=rho,
+                               chi_bar=torch.as_tensor(cfg["chi_bar"]).to(dev))
     return mu, lam, phi.reciprocal()
 
 
