@@ -40,7 +40,7 @@ def log_prob_noise_count_tensor(data, mu_est, lambda_est, alpha_est, n_counts_ma
     low = (lambda_est - n / 2).int()
     cdt = torch.float32 if mimic_float_casts else data.dtype
     low = torch.clamp(torch.min(low, (data - n + 1).int()), min=0).to(cdt)
-    c = torch.arange(0, n, dtype=cdt).expand(data.shape[0], data.shape[1], n) + low.unsqueeze(-1)
+    c = torch.arange(0, n, dtype=cdt, device=data.device).expand(data.shape[0], data.shape[1], n) + low.unsqueeze(-1)
     lam = lambda_est.unsqueeze(-1)
     pois = torch.xlogy(c, lam) - lam - (c + 1).lgamma()
     k = data.unsqueeze(-1) - c
@@ -48,7 +48,7 @@ def log_prob_noise_count_tensor(data, mu_est, lambda_est, alpha_est, n_counts_ma
         mu = mu_est.unsqueeze(-1)
         other = torch.xlogy(k, mu) - mu - (k + 1).lgamma()
     else:
-        alpha_est = torch.as_tensor(alpha_est, dtype=data.dtype)
+        alpha_est = torch.as_tensor(alpha_est, dtype=data.dtype, device=data.device)
         logits = (mu_est.log() - alpha_est.log()).unsqueeze(-1)
         tc = alpha_est.unsqueeze(-1) if alpha_est.dim() > 0 else alpha_est
         unnorm = tc * F.logsigmoid(-logits) + k * F.logsigmoid(logits)

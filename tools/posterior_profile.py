@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--workload", default="pbmc8k")
     ap.add_argument("--estimators", action="store_true")
+    ap.add_argument("--timeline", default=None, help="write a per-kernel timeline of one pass (torch.profiler / CUPTI)")
     a = ap.parse_args()
     import torch
 
@@ -47,6 +48,33 @@ def main():
         dt = time.perf_counter() - t0
         print(f"posterior: {n_cells} cells, {int(dp_.m.numel())} COO entries, {dt * 1e3:.2f} ms, {n_cells / dt:.0f} droplets/s",
               flush=True)
+    if a.timeline:
+        import collections
+        import json
+        import tempfile
+
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            post.device_posterior()
+            torch.cuda.synchronize()
+        path = os.path.join(tempfile.mkdtemp(), "trace.json")
+        prof.export_chrome_trace(path)
+        ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "ts" in e]
+        ev.sort(key=lambda e: e["ts"])
+        t0, t1 = ev[0]["ts"], ev[-1]["ts"] + ev[-1]["dur"]
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for e in ev:
+            n = e["name"].replace("void ", "").split("(")[0][:100]
+            agg[n][0] += 1
+            agg[n][1] += e["dur"]
+        busy = sum(v[1] for v in agg.values())
+        lines = [f"# posterior pass, {n_cells} cells: {len(ev)} kernels, span {t1 - t0:.0f} us, sum of kernel durations {busy:.0f} us "
+                 f"({100 * busy / (t1 - t0):.0f} % of the span: the rest is launch gaps / host)", "# total_us  launches  kernel"]
+        for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+            lines.append(f"{t:10.1f} {c:6d}  {n}")
+        open(a.timeline, "w").write("\n".join(lines) + "\n")
+        print("\n".join(lines[:12]))
     if a.estimators:
         from cellbender_b200.estimation import Mean, MultipleChoiceKnapsack
 
