@@ -38,8 +38,13 @@ __global__ void __launch_bounds__(kPostThreads) posterior_window_kernel(
     const float* __restrict__ c_b, const float* __restrict__ alpha, const int* __restrict__ n_window,
     const long long* __restrict__ entry_start, const long long* __restrict__ barcode_all,
     const long long* __restrict__ gene_all, long long total_n_genes, float log_thresh, float lambda_multiplier,
-    float* __restrict__ logp_out, int* __restrict__ low_out, int* __restrict__ keep_cnt, long long* __restrict__ entry_m) {
+    const long long* __restrict__ out_offset, float* __restrict__ logp_out, int* __restrict__ low_out,
+    int* __restrict__ keep_cnt, long long* __restrict__ entry_m) {
+  // the grid may be sized for an upper bound of the chunk's stored counts (CUDA-graph replays): surplus CTAs exit here
   const long long n_entries = entry_start[n_cells];
+  if (blockIdx.x * (long long)(kPostThreads / 4) >= n_entries) return;
+  const long long o0 = out_offset ? out_offset[0] : 0;  // first output row of this chunk (device scalar)
+  logp_out += o0 * NMAX, low_out += o0, keep_cnt += o0, entry_m += o0;
   const long long e = blockIdx.x * (long long)(kPostThreads / 4) + (threadIdx.x >> 2);
   const int sub = threadIdx.x & 3;
   const bool active = e < n_entries;
@@ -200,11 +205,12 @@ extern "C" int cb_posterior_noise_window(const long long* indptr, const int* ind
                                          const float* logits_t, long long ldt, const float* dec_bias, const float* lse,
                                          const float* chi_ambient, const float* chi_bar, const float* a_mu, const float* c_a,
                                          const float* c_b, const float* alpha, const int* n_window,
-                                         const long long* entry_start, long long n_entries, const long long* barcode_all,
+                                         const long long* entry_start, long long max_entries, const long long* barcode_all,
                                          const long long* gene_all, long long total_n_genes, int n_counts_max,
-                                         float log_thresh, float lambda_multiplier, float* logp_out, int* low_out,
-                                         int* keep_cnt, long long* entry_m, void* stream) {
-  if (n_cells == 0 || n_entries == 0) return 0;
+                                         float log_thresh, float lambda_multiplier, const long long* out_offset,
+                                         float* logp_out, int* low_out, int* keep_cnt, long long* entry_m, void* stream) {
+  if (n_cells == 0 || max_entries == 0) return 0;
+  const long long n_entries = max_entries;
   CB_REQUIRE(n_cells > 0 && n_genes > 0 && n_samples > 0 && n_entries > 0, "cb_posterior_noise_window: bad shape");
   CB_REQUIRE(ldt >= (long long)n_cells * n_samples, "cb_posterior_noise_window: ldt=%lld < n_cells * n_samples", ldt);
   CB_REQUIRE(n_counts_max > 0 && n_counts_max <= 64, "cb_posterior_noise_window: n_counts_max=%d not in [1, 64]", n_counts_max);
@@ -213,7 +219,7 @@ extern "C" int cb_posterior_noise_window(const long long* indptr, const int* ind
   cb::posterior_window_kernel<NMAX><<<grid, cb::kPostThreads, 0, (cudaStream_t)stream>>>(                              \
       indptr, indices, data, cell_rows, n_cells, n_samples, logits_t, ldt, dec_bias, lse, chi_ambient, chi_bar, a_mu, \
       c_a, c_b, alpha, n_window, entry_start, barcode_all, gene_all, total_n_genes, log_thresh, lambda_multiplier,    \
-      logp_out, low_out, keep_cnt, entry_m)
+      out_offset, logp_out, low_out, keep_cnt, entry_m)
   if (n_counts_max <= 20) CB_LAUNCH_POST(20);
   else if (n_counts_max <= 32) CB_LAUNCH_POST(32);
   else CB_LAUNCH_POST(64);

@@ -54,6 +54,7 @@ class Posterior:
         self.float_threshold = float_threshold
         self.posterior_batch_size = posterior_batch_size
         self.cells_per_chunk = cells_per_chunk
+        self.use_cuda_graph = True  # replay one captured graph per full chunk of the posterior pass (device_posterior)
         self._noise_count_posterior_coo: Optional[sp.coo_matrix] = None
         self._noise_count_posterior_kwargs: Optional[dict] = None
         self._noise_count_posterior_coo_offsets: Optional[Dict[int, int]] = None
@@ -227,44 +228,112 @@ class Posterior:
         host_indptr = self._host_indptr()
         nnz_cell = (host_indptr[rows_sorted[lo:hi] + 1] - host_indptr[rows_sorted[lo:hi]]).astype(np.int64)
         prefix = np.concatenate(([0], np.cumsum(nnz_cell)))
-        ws = ops.PosteriorWorkspace(int(prefix[-1]), n_counts_max, self.device)
+        ws = self._workspace(int(prefix[-1]), n_counts_max)
         rows_dev = torch.as_tensor(rows_sorted[lo:hi], device=self.device)
         barcode_dev = torch.as_tensor(barcodes[lo:hi], device=self.device)
         prefix_dev = torch.as_tensor(prefix, device=self.device)
         n_window = n_window[lo:hi]
-        gene_all = torch.as_tensor(np.asarray(self.analyzed_gene_inds).astype(np.int64), device=self.device)
-        ld = ops.row_pitch(G)
-        chi_a = torch.zeros(ld, device=self.device)
-        chi_b = torch.zeros(ld, device=self.device)
-        chi_a[:G] = m.param_store["chi_ambient"].detach()
-        chi_b[:G] = m.avg_gene_expression
+        # per-model constants in persistent buffers (a cached chunk graph refers to them by address): refreshed in place
+        pc = getattr(self, "_pc", None)
+        if pc is None:
+            ld = ops.row_pitch(G)
+            pc = self._pc = {"chi_a": torch.zeros(ld, device=self.device), "chi_b": torch.zeros(ld, device=self.device),
+                             "gene_all": torch.as_tensor(np.asarray(self.analyzed_gene_inds).astype(np.int64), device=self.device)}
+        chi_a, chi_b, gene_all = pc["chi_a"], pc["chi_b"], pc["gene_all"]
+        chi_a[:G].copy_(m.param_store["chi_ambient"].detach())
+        chi_b[:G].copy_(m.avg_gene_expression)
         lin = m.decoder.out_linear
         cpc = self.cells_per_chunk
-        logits_t = torch.empty((G, ops.row_pitch(S * cpc)), device=self.device)  # [G, cells * S]: transposed, cell-major
-        for start in range(0, hi - lo, cpc):
-            stop = min(hi - lo, start + cpc)
-            Bc = stop - start
-            rows = rows_dev[start:stop]
-            if seed is not None:
-                torch.manual_seed(int(seed) + lo + start)
+        logits_t = self._logits_buffer(G, S, cpc)  # [G, cells * S]: transposed, cell-major
+        n_sel = hi - lo
+        total_genes = int(self.count_matrix_shape[1])
+
+        def chunk(rows, nwin, estart, barcodes_c, Bc, n_entries, out_offset, pos0):
+            """Everything of one chunk of Bc cells; no host synchronisation inside."""
             _, enc = self._encode(rows)
-            noise = None if noise_fn is None else noise_fn(slice(lo + start, lo + stop), enc)
+            noise = None if noise_fn is None else noise_fn(slice(pos0, pos0 + Bc), enc)
             z, a_mu, c_a, c_b, alpha = self.sample_rate_coefficients(enc, S, y_map=y_map, noise=noise)
             h = m.decoder.hidden(z.reshape(Bc * S, -1))
             # ONE decoder GEMM for all samples of the chunk, output transposed: logits_t[g, b * S + s] = W[g, :] . h[b * S + s, :]
-            lt = logits_t[:, : Bc * S]
-            ops.gemm_tf32(lin.weight, h.contiguous(), G, Bc * S, lin.weight.shape[1], out=lt, split_k=1)
+            ops.gemm_tf32(lin.weight, h.contiguous(), G, Bc * S, lin.weight.shape[1], out=logits_t[:, : Bc * S], split_k=1)
             lse = ops.col_logsumexp(logits_t, G, Bc * S, row_add=lin.bias)
             ops.posterior_window(
                 csr, rows, logits_t, lin.bias, lse, chi_a, chi_b, a_mu.reshape(-1).contiguous(), c_a.reshape(-1).contiguous(),
-                c_b.reshape(-1).contiguous(), alpha.contiguous(), n_window[start:stop].contiguous(),
-                (prefix_dev[start:stop + 1] - prefix_dev[start]).contiguous(), int(prefix[stop] - prefix[start]),
-                barcode_dev[start:stop].contiguous(), gene_all, int(self.count_matrix_shape[1]), ws, int(prefix[start]),
-                log_thresh=smallest_log_probability, lambda_multiplier=lambda_multiplier)
+                c_b.reshape(-1).contiguous(), alpha.contiguous(), nwin, estart, n_entries, barcodes_c, gene_all, total_genes, ws,
+                out_offset, log_thresh=smallest_log_probability, lambda_multiplier=lambda_multiplier)
+
+        n_full = n_sel // cpc
+        # Full chunks replay ONE captured CUDA graph (a chunk is ~250 small launches -- encoders, sampling, decoder hidden
+        # layer -- whose launch latency exceeded the GPU time of the chunk: r02j timeline, kernels busy 59 % of the span);
+        # the chunk's varying operands live in static device buffers, the grid of the window kernel is sized for the
+        # largest chunk and the output offset is a device scalar.  Seeded / injected-noise passes (tests, sharded-equals-
+        # unsharded checks) and the ragged last chunk run eagerly.
+        use_graph = self.use_cuda_graph and seed is None and noise_fn is None and n_full >= 2
+        if use_graph:
+            chunk_entries = np.array([int(prefix[(i + 1) * cpc] - prefix[i * cpc]) for i in range(n_full)])
+            key = (S, n_counts_max, float(smallest_log_probability), float(lambda_multiplier), bool(y_map), cpc, id(ws), id(logits_t))
+            cached = getattr(self, "_chunk_graph", None)
+            if cached is not None and cached["key"] == key and cached["max_entries"] >= int(chunk_entries.max()):
+                st, graph, max_entries = cached["st"], cached["graph"], cached["max_entries"]
+            else:
+                cached = None
+                max_entries = int(chunk_entries.max() * 1.25) + 1024  # head-room: later passes reuse the captured graph
+                st = {"rows": torch.zeros(cpc, dtype=torch.int64, device=self.device),
+                      "nwin": torch.zeros(cpc, dtype=torch.int32, device=self.device),
+                      "estart": torch.zeros(cpc + 1, dtype=torch.int64, device=self.device),
+                      "barcode": torch.zeros(cpc, dtype=torch.int64, device=self.device),
+                      "offset": torch.zeros(1, dtype=torch.int64, device=self.device)}
+
+            def load(i):
+                a0, a1 = i * cpc, (i + 1) * cpc
+                st["rows"].copy_(rows_dev[a0:a1]), st["nwin"].copy_(n_window[a0:a1]), st["barcode"].copy_(barcode_dev[a0:a1])
+                torch.sub(prefix_dev[a0:a1 + 1], prefix_dev[a0], out=st["estart"])
+                st["offset"].copy_(prefix_dev[a0:a0 + 1])
+
+            if cached is None:
+                body = lambda: chunk(st["rows"], st["nwin"], st["estart"], st["barcode"], cpc, max_entries, st["offset"], 0)
+                load(0)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    body()  # warm-up outside capture (allocator, lazy initialisation); its outputs are overwritten below
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    body()
+                self._chunk_graph = {"key": key, "st": st, "graph": graph, "max_entries": max_entries}
+            for i in range(n_full):
+                load(i)
+                graph.replay()
+            first_eager = n_full * cpc
+        else:
+            first_eager = 0
+        for start in range(first_eager, n_sel, cpc):
+            stop = min(n_sel, start + cpc)
+            if seed is not None:
+                torch.manual_seed(int(seed) + lo + start)
+            chunk(rows_dev[start:stop], n_window[start:stop].contiguous(), (prefix_dev[start:stop + 1] - prefix_dev[start]).contiguous(),
+                  barcode_dev[start:stop].contiguous(), stop - start, int(prefix[stop] - prefix[start]), int(prefix[start]), lo + start)
         post = DevicePosteriorCOO(*ops.posterior_compact(ws, smallest_log_probability), n_cols=n_counts_max)
         if cell_subset is None:
             self._device_posterior = post
         return post
+
+    def _workspace(self, n_entries: int, n_counts_max: int) -> "ops.PosteriorWorkspace":
+        """Per-stored-count scratch of a pass, kept between passes (grown when needed) so that the cached chunk graph,
+        which refers to it by address, stays valid; the compaction at the end of a pass copies the result out."""
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.n_counts_max != n_counts_max or ws.capacity < n_entries:
+            ws = self._ws = ops.PosteriorWorkspace(int(n_entries * 1.1) + 1024, n_counts_max, self.device)
+        ws.n_entries = int(n_entries)
+        return ws
+
+    def _logits_buffer(self, G: int, S: int, cpc: int) -> torch.Tensor:
+        need = (G, ops.row_pitch(S * cpc))
+        buf = getattr(self, "_logits_t", None)
+        if buf is None or tuple(buf.shape) != need:
+            self._logits_t = buf = torch.empty(need, device=self.device)
+        return buf
 
     def _host_indptr(self) -> np.ndarray:
         if getattr(self, "_indptr_host", None) is None:

@@ -267,7 +267,10 @@ int cb_clipped_adam_nvls(float* p, float* m, float* v, long long n, const float*
  *   a_mu/c_a/c_b [n_cells * n_samples] (index b * n_samples + s), alpha[n_samples]:
  *                          mu = a_mu * chi, lam = c_a * chi_ambient + c_b * chi_bar
  *   n_window[n_cells]      min(n_counts_max, max count of the reference minibatch of the cell) (posterior.py:816)
- *   entry_start[n_cells+1] prefix sums of the cells' stored-count numbers; n_entries = entry_start[n_cells]
+ *   entry_start[n_cells+1] prefix sums of the cells' stored-count numbers (device); entry_start[n_cells] entries are
+ *                          processed, max_entries (host) only sizes the grid and may be an upper bound, so that one
+ *                          captured CUDA graph serves every chunk of a pass
+ *   out_offset             device scalar (may be NULL = 0): first row of this chunk inside the output arrays
  *   barcode_all[n_cells] / gene_all[n_genes]  indices into the full count matrix (IndexConverter, posterior.py:1554-1575)
  * outputs, one row per stored count in (cell, gene) order:
  *   logp_out[n_entries, stride] (stride = cb_posterior_window_stride()), low_out, keep_cnt, entry_m[n_entries]
@@ -278,10 +281,10 @@ int cb_posterior_noise_window(const long long* indptr, const int* indices, const
                               int n_cells, int n_genes, int n_samples, const float* logits_t, long long ldt,
                               const float* dec_bias, const float* lse, const float* chi_ambient, const float* chi_bar,
                               const float* a_mu, const float* c_a, const float* c_b, const float* alpha,
-                              const int* n_window, const long long* entry_start, long long n_entries,
+                              const int* n_window, const long long* entry_start, long long max_entries,
                               const long long* barcode_all, const long long* gene_all, long long total_n_genes,
-                              int n_counts_max, float log_thresh, float lambda_multiplier, float* logp_out, int* low_out,
-                              int* keep_cnt, long long* entry_m, void* stream);
+                              int n_counts_max, float log_thresh, float lambda_multiplier, const long long* out_offset,
+                              float* logp_out, int* low_out, int* keep_cnt, long long* entry_m, void* stream);
 int cb_posterior_offset_flags(long long n_entries, const int* keep_cnt, const int* low, int* flag, void* stream);
 /* out[c] = log sum_r exp(in[r, c] + row_add[r]) over an [n_rows, ld] matrix (row_add may be NULL): the softmax
  * denominators of Decoder.forward (vae/decoder.py:46-47) for the transposed logits of a posterior chunk.
