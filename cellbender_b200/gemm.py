@@ -86,11 +86,14 @@ def early_update_applies(w: torch.Tensor) -> bool:
             and getattr(w, "_cb_grad_view", None) is not None and w.requires_grad and w.numel() >= FUSED_MIN_NUMEL)
 
 
+def _tma_addressable(t: torch.Tensor, col_offset: int = 0) -> bool:
+    return (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0
+            and (t.data_ptr() + 4 * col_offset) % 16 == 0)
+
+
 def _require_tma(t: torch.Tensor, what: str, col_offset: int = 0):
     """The tensor-core path is the only path: fail loudly when an operand cannot be addressed by TMA."""
-    ok = (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0
-          and (t.data_ptr() + 4 * col_offset) % 16 == 0)
-    if not ok:
+    if not _tma_addressable(t, col_offset):
         raise RuntimeError(
             f"cellbender_b200.gemm: {what} (shape {tuple(t.shape)}, strides {tuple(t.stride())}, dtype {t.dtype}, device "
             f"{t.device}) is not TMA-addressable: needs a CUDA fp32 matrix with unit column stride, a row pitch that is a "
@@ -98,16 +101,22 @@ def _require_tma(t: torch.Tensor, what: str, col_offset: int = 0):
             f"gemm.pad_big_weights(module) / optim.FlatClippedAdam; there is no library-GEMM fallback.")
 
 
-def pad_big_weights(module: torch.nn.Module, min_numel: int = 1 << 16):
-    """Re-home every large 2-D weight of ``module`` into storage whose row pitch is a multiple of 4 floats (G = 33 538
-    and G + 4 are not), so that TMA can address it; names, shapes and values are unchanged (the nn.Parameter becomes a
-    [rows, cols] view of a [rows, ld] block whose padding columns stay zero).  The optimizer does the same when it builds
-    its flat buffer (optim.FlatClippedAdam); this covers models that never see an optimizer (posterior from a checkpoint)."""
+def needs_padded_layout(p: torch.Tensor) -> bool:
+    """2-D weights that get a padded storage block: the large ones (128-byte-aligned rows) and every one whose row length
+    is not a multiple of 4 floats (TMA needs 16-byte rows: Linear(6 -> 512) with --z-dim 6, Linear(516 -> 512) is fine)."""
+    return p.dim() == 2 and (p.numel() >= (1 << 16) or p.shape[1] % 4 != 0)
+
+
+def pad_big_weights(module: torch.nn.Module):
+    """Re-home every 2-D weight of ``module`` that needs it (``needs_padded_layout``) into storage TMA can address; names,
+    shapes and values are unchanged (the nn.Parameter becomes a [rows, cols] view of a [rows, ld] block whose padding
+    columns stay zero).  The optimizer does the same when it builds its flat buffer (optim.FlatClippedAdam); this covers
+    models that never see an optimizer (posterior from a checkpoint)."""
     with torch.no_grad():
         for p in module.parameters():
-            if p.dim() == 2 and p.numel() >= min_numel:
+            if needs_padded_layout(p):
                 lead, ld = padded_layout(p)
-                if p.stride(1) == 1 and p.stride(0) == ld and (p.data_ptr() - 4 * lead) % 128 == 0:
+                if p.stride(1) == 1 and p.stride(0) == ld and (p.data_ptr() - 4 * lead) % (128 if ld % 32 == 0 else 16) == 0:
                     continue
                 rows, cols = p.shape
                 block = torch.zeros((rows, ld), dtype=p.dtype, device=p.device)
@@ -122,6 +131,8 @@ def padded_layout(p: torch.Tensor):
     shifts the row so that the G-wide block of a Linear(cat(feat, x)) weight -- which starts ``col_offset`` columns into
     the row -- begins on a 128-byte line too."""
     lead = int(getattr(p, "_cb_lead", 0))
+    if p.numel() < (1 << 16) and lead == 0:
+        return 0, ops.round_up(p.shape[1], 4)  # small layer: 16-byte rows are all TMA needs
     return lead, ops.row_pitch(lead + p.shape[1])
 
 
@@ -272,6 +283,10 @@ def multi_linear_big(x: torch.Tensor, layers, n_in: int, col_offset: int = 0, bi
     ``bias_grad_elsewhere``: the layer feeds ``bn_act`` which also produces the Linear bias gradient (the column sums
     of its input gradient), so no separate reduction over dy is launched here.
     ``streams``: one CUDA stream (or None) per layer on which its forward product is issued."""
+    if not _tma_addressable(x) and x.dim() == 2 and x.is_cuda and x.shape[0] * n_in <= (1 << 22):
+        # a SMALL activation matrix whose row pitch is not a multiple of 16 bytes (z with --z-dim 6, say): zero-pad the rows
+        # (differentiable); the wide [B, G] matrices always come from kernels that write padded rows
+        x = torch.nn.functional.pad(x[:, :n_in], (0, (-n_in) % 4))
     _require_tma(x, "the input activations")
     args = []
     for lin, feat in layers:

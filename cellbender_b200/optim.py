@@ -47,10 +47,10 @@ class FlatClippedAdam:
         # each tensor starts on a 16-byte boundary; large 2-D weights additionally get 128-byte-aligned rows (a row pitch
         # that is a multiple of 32 floats; G = 33 538 is not even a multiple of 4) -- the nn.Parameter then is a strided
         # view [rows, cols] of a [rows, ld] block (gemm.padded_layout), the padding columns stay zero forever.
-        from .gemm import padded_layout
+        from .gemm import needs_padded_layout, padded_layout
 
         def padded_ld(p):
-            return padded_layout(p) if (p.dim() == 2 and p.numel() >= (1 << 16)) else None
+            return padded_layout(p) if needs_padded_layout(p) else None
 
         # layout: the few very large matrices first (each one is a unit of the piecewise optimizer sweep and, data
         # parallel, of the overlapped gradient reduction), everything else behind them in ONE contiguous tail

@@ -107,9 +107,9 @@ class Posterior:
             _, enc = self._encode(rows)
             sl = slice(start, start + rows.numel())
             z[sl] = enc["z"]["loc"].reshape(rows.numel(), -1)
-            d[sl] = LogNormal(loc=enc["d_loc"], scale=d_cell_scale).mean
+            d[sl] = LogNormal(loc=enc["d_loc"], scale=d_cell_scale, validate_args=False).mean
             p[sl] = enc["p_y"].sigmoid()
-            eps[sl] = Gamma(enc["epsilon"] * m.epsilon_prior, m.epsilon_prior).mean
+            eps[sl] = Gamma(enc["epsilon"] * m.epsilon_prior, m.epsilon_prior, validate_args=False).mean
         self._latents = {"z": z.double().cpu().numpy(), "d": d.double().cpu().numpy(), "p": p.double().cpu().numpy(),
                          "phi_loc_scale": [m.param_store["phi_loc"].item(), m.param_store["phi_scale"].item()],
                          "epsilon": eps.double().cpu().numpy()}
@@ -138,15 +138,18 @@ class Posterior:
         prob = enc["p_y"].sigmoid()
         if noise is None:
             phi_loc, phi_scale = ps["phi_loc"], ps["phi_scale"]
-            phi = Gamma(phi_loc.pow(2) / phi_scale.pow(2), phi_loc / phi_scale.pow(2)).sample((S,)).reshape(S)
-            rho = Beta(ps["rho_alpha"], ps["rho_beta"]).sample((B, S)).reshape(B, S) if m.include_rho \
+            # validate_args=False: argument validation synchronises with the host (and is illegal under graph capture);
+            # the reference switches it off globally (run.py:659-660)
+            va = dict(validate_args=False)
+            phi = Gamma(phi_loc.pow(2) / phi_scale.pow(2), phi_loc / phi_scale.pow(2), **va).sample((S,)).reshape(S)
+            rho = Beta(ps["rho_alpha"], ps["rho_beta"], **va).sample((B, S)).reshape(B, S) if m.include_rho \
                 else torch.zeros((B, S), device=self.device)
-            d_empty = LogNormal(ps["d_empty_loc"], ps["d_empty_scale"]).sample((B, S)).reshape(B, S)
+            d_empty = LogNormal(ps["d_empty_loc"], ps["d_empty_scale"], **va).sample((B, S)).reshape(B, S)
             z = z_loc[:, None, :] + z_scale[:, None, :] * torch.randn((B, S, z_loc.shape[1]), device=self.device)
             d_cell = LogNormal((prob * enc["d_loc"] + (1 - prob) * m.d_cell_loc_prior)[:, None].expand(B, S),
-                               ps["d_cell_scale"]).sample()
+                               ps["d_cell_scale"], **va).sample()
             epsilon = Gamma(((prob * enc["epsilon"] + (1 - prob)) * m.epsilon_prior)[:, None].expand(B, S),
-                            m.epsilon_prior).sample()
+                            m.epsilon_prior, **va).sample()
         else:
             phi, rho, d_empty, z, d_cell, epsilon = (noise[k].to(self.device) for k in ("phi", "rho", "d_empty", "z", "d_cell", "epsilon"))
         y = (enc["p_y"] > 0).float()[:, None].expand(B, S)

@@ -107,10 +107,15 @@ def test_gemm_rejects_operands_tma_cannot_address():
         ops.gemm_tf32(a, b, 64, 64, 33)
     lin = torch.nn.Linear(33, 64).to(DEV)
     with pytest.raises(RuntimeError, match="TMA"):
-        gemm.linear_big(a, lin, n_in=33)
+        gemm.linear_big(a, lin, n_in=33)  # the weight's 132-byte rows: not addressable until re-homed
+    gemm.pad_big_weights(lin)
+    assert lin.weight.stride(0) == 36 and lin.weight.shape == (64, 33)
+    y = gemm.linear_big(a, lin, n_in=33)  # the small activation matrix is zero-padded on the fly
+    ref = torch.nn.functional.linear(a.double(), lin.weight.double(), lin.bias.double())
+    assert float((y.double() - ref).abs().max()) < 2e-2
     big = torch.nn.Linear(33538 + 4, 512).to(DEV)
     gemm.pad_big_weights(big)
-    assert big.weight.stride(0) % 4 == 0 and big.weight.shape == (512, 33542)
+    assert big.weight.stride(0) % 32 == 0 and big.weight.shape == (512, 33542)
 
 
 def test_feat_dw_matches_matmul():

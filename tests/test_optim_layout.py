@@ -8,7 +8,8 @@ from cellbender_b200 import optim
 
 def _toy_model(big_numel):
     m = nn.ModuleDict({
-        "a": nn.Linear(37, 5),                       # small: no padding
+        "a": nn.Linear(37, 5),                       # small, 37 % 4 != 0: rows padded to 40 floats (TMA needs 16-byte rows)
+        "a2": nn.Linear(36, 5),                      # small, 16-byte rows already: no padding
         "big1": nn.Linear(1030, big_numel // 1030 + 1),  # >= BIG_BLOCK_NUMEL once multiplied out (see below)
         "mid": nn.Linear(258, 300),                  # >= 65536 elements: padded rows (258 -> 288), but not "big"
         "b": nn.BatchNorm1d(11),
