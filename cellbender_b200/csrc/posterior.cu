@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kPostThreads) posterior_window_kernel(
       const long long base = (long long)b * n_samples;
       const float* lrow = logits_t + (long long)g * ldt + base;
       for (int smp = sub; smp < n_samples; smp += 4) {
-        const float chi = expf(lrow[smp] + bg - lse[base + smp]);
+        const float chi = __expf(lrow[smp] + bg - lse[base + smp]);
         // posterior.py:708-710 safeguards
         const float mu = a_mu[base + smp] * chi + 1e-30f;
         const float lam = (c_a[base + smp] * ca + c_b[base + smp] * cb_) * lambda_multiplier + 1e-30f;

@@ -28,72 +28,72 @@ CB_HD int noise_window_low(float x, float lam, int n) {
   return lo > 0 ? lo : 0;
 }
 
+// Fast device math (one MUFU instruction each: lg2.approx / ex2.approx / rcp.approx, abs. error ~2^-22); the host build
+// of the same source (tools/host_math_check.cu) uses the exact library functions.
+CB_HD float pm_log2(float v) {
+#ifdef __CUDA_ARCH__
+  return __log2f(v);
+#else
+  return log2f(v);
+#endif
+}
+CB_HD float pm_exp2(float v) {
+#ifdef __CUDA_ARCH__
+  return exp2f(v);  // ex2.approx.ftz with the build's default fast exp2 path
+#else
+  return exp2f(v);
+#endif
+}
+CB_HD float pm_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+
 // Normalised pmf over the window, accumulated in place: acc[j] += P(noise = low + j), j < n (0 where low + j > x).
-// mu, lam, alpha must already carry the reference's +1e-30 safeguards (posterior.py:708-710).  No transcendental functions: consecutive terms
-// differ by the rational factor r(c) = (lam / s) (x - c) / ((c + 1) (alpha + x - c - 1)), lam / s = lam (1 + alpha / mu), so
-// the un-normalised pmf is a running product.  Its dynamic range is tamed by rescaling with exact powers of two whenever
-// the product leaves [2^-64, 2^64] (the rescale events are remembered as two bit masks), and r is clamped to
-// [2^-60, 2^60] -- a neighbour more than 10^18 times less likely lies far below every threshold the posterior is stored
-// with (log p >= -10).  Per sample this is n divisions and multiplications instead of ~n logf + n expf: the window
-// kernel was issue-bound on exactly those (ncu r02k: 980 M warp instructions per chunk, 1 240 per sample evaluation).
-// Relative error of the result ~ n x 2^-24 (products) -- tighter than the summed-logarithm form.  Returns low.
+// mu, lam, alpha must already carry the reference's +1e-30 safeguards (posterior.py:708-710).
+// Consecutive terms differ by the rational factor r(c) = (lam / s) (x - c) / ((c + 1) (alpha + x - c - 1)) with
+// lam / s = lam (1 + alpha / mu); the relative log2-pmf is the running sum of log2 r, one lg2.approx per term, and the
+// terms are exponentiated with one ex2.approx each.  (The first version used logf / log1pf / expf and an IEEE division
+// per term: 1 240 instructions per sample evaluation, the window kernel was issue-bound on them -- ncu r02k.)
+// lam / s is clamped to 3e37: with mu -> 0 (+1e-30) all mass piles onto the last valid count, which the clamp reproduces
+// to far below the stored threshold log p >= -10.  Returns low.
 template <int NMAX>
 CB_HD int noise_window_pmf_accumulate(float x, float mu, float lam, float alpha, int n, float (&acc)[NMAX]) {
-  static_assert(NMAX <= 64, "rescale masks are 64-bit");
   const int low = noise_window_low(x, lam, n);
-  const float a_ratio = fminf(lam * (1.0f + alpha / mu), 3.0e37f);  // lam / s; alpha / mu may overflow: clamp, r is clamped anyway
-  constexpr float kBig = 18446744073709551616.0f, kSmall = 5.421010862427522e-20f;  // 2^64, 2^-64
-  constexpr float kRmax = 1152921504606846976.0f, kRmin = 8.673617379884035e-19f;   // 2^60, 2^-60
-  float w[NMAX];
-  unsigned long long up = 0ull, down = 0ull;
-  float cur = 1.0f;
-  w[0] = 1.0f;  // relative probability of c = low (always <= x because low <= max(x - n + 1, 0) <= x)
-  int scale = 0, best_scale = 0;  // in units of 2^64
-  float best = 1.0f;
+  const float l_ratio = pm_log2(fminf(lam * (1.0f + pm_div(alpha, mu)), 3.0e37f));  // log2(lam / s)
+  float t[NMAX];
+  float tmax = 0.0f;
+  t[0] = 0.0f;  // relative log2 prob of c = low (always <= x because low <= max(x - n + 1, 0) <= x)
   bool dead = false;
 #pragma unroll
   for (int j = 1; j < NMAX; ++j) {
-    float wj = 0.0f;
+    float tj = -INFINITY;
     if (j < n && !dead) {
       const float c = float(low + j - 1);  // ratio p(c + 1) / p(c)
       const float k = x - c;               // NB count at c
       if (k <= 0.0f) {
         dead = true;
       } else {
-        float r = a_ratio * (k / ((c + 1.0f) * (alpha + k - 1.0f)));
-        r = fminf(fmaxf(r, kRmin), kRmax);
-        cur *= r;
-        if (cur > kBig) {
-          cur *= kSmall, up |= 1ull << j, ++scale;
-        } else if (cur < kSmall) {
-          cur *= kBig, down |= 1ull << j, --scale;
-        }
-        wj = cur;
-        if (scale > best_scale || (scale == best_scale && cur > best)) best_scale = scale, best = cur;
+        tj = t[j - 1] + (l_ratio + pm_log2(pm_div(k, (c + 1.0f) * (alpha + k - 1.0f))));
+        tmax = fmaxf(tmax, tj);
       }
     }
-    w[j] = wj;
+    t[j] = tj;
   }
-  // bring every term onto the scale of the largest one: factors are exact powers of two, terms 2^-128 below the
-  // maximum vanish
-  const float inv_best = 1.0f / best;
   float z = 0.0f;
-  int sc = 0;
 #pragma unroll
   for (int j = 0; j < NMAX; ++j) {
-    sc += int((up >> j) & 1ull) - int((down >> j) & 1ull);
-    const int d = sc - best_scale;  // <= 0
-    float v = w[j] * inv_best;
-    v = (d == 0) ? v : (d == -1 ? v * kSmall : 0.0f);
-    w[j] = v;
-    z += v;
+    t[j] = (j < n) ? pm_exp2(t[j] - tmax) : 0.0f;  // exp2(-inf) = 0 for the dead tail
+    z += t[j];
   }
   const float inv = 1.0f / z;
 #pragma unroll
-  for (int j = 0; j < NMAX; ++j) acc[j] += w[j] * inv;
+  for (int j = 0; j < NMAX; ++j) acc[j] += t[j] * inv;
   return low;
 }
-
 
 // prob[j] = P(noise = low + j): the accumulate form on a zeroed array (tests)
 template <int NMAX>

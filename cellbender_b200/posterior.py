@@ -20,7 +20,7 @@ from typing import Dict, Optional
 import numpy as np
 import scipy.sparse as sp
 import torch
-from torch.distributions import Beta, Gamma, LogNormal, Normal
+from torch.distributions import Gamma, LogNormal
 
 from . import consts, ops
 from .estimation import DevicePosteriorCOO, EstimationMethod, IndexConverter
@@ -138,18 +138,25 @@ class Posterior:
         prob = enc["p_y"].sigmoid()
         if noise is None:
             phi_loc, phi_scale = ps["phi_loc"], ps["phi_scale"]
-            # validate_args=False: argument validation synchronises with the host (and is illegal under graph capture);
-            # the reference switches it off globally (run.py:659-660)
-            va = dict(validate_args=False)
-            phi = Gamma(phi_loc.pow(2) / phi_scale.pow(2), phi_loc / phi_scale.pow(2), **va).sample((S,)).reshape(S)
-            rho = Beta(ps["rho_alpha"], ps["rho_beta"], **va).sample((B, S)).reshape(B, S) if m.include_rho \
-                else torch.zeros((B, S), device=self.device)
-            d_empty = LogNormal(ps["d_empty_loc"], ps["d_empty_scale"], **va).sample((B, S)).reshape(B, S)
-            z = z_loc[:, None, :] + z_scale[:, None, :] * torch.randn((B, S, z_loc.shape[1]), device=self.device)
-            d_cell = LogNormal((prob * enc["d_loc"] + (1 - prob) * m.d_cell_loc_prior)[:, None].expand(B, S),
-                               ps["d_cell_scale"], **va).sample()
-            epsilon = Gamma(((prob * enc["epsilon"] + (1 - prob)) * m.epsilon_prior)[:, None].expand(B, S),
-                            m.epsilon_prior, **va).sample()
+            # The guide's distributions (model.py:506-567) sampled from their definitions with torch's graph-capturable
+            # generators (randn, _standard_gamma): Gamma(c, r) = G(c) / r, Beta(a, b) = G(a) / (G(a) + G(b)) (what
+            # torch.distributions.Beta draws through a Dirichlet), LogNormal(l, s) = exp(l + s n).  torch.distributions
+            # objects are avoided on purpose: their sampling path invalidates CUDA-graph capture (r02 probe).
+            dev = self.device
+            tiny = torch.finfo(torch.float32).tiny
+            sg = lambda conc: torch._standard_gamma(conc.contiguous()).clamp_min(tiny)
+            phi_loc, phi_scale = ps["phi_loc"].reshape(()), ps["phi_scale"].reshape(())
+            phi = sg((phi_loc.pow(2) / phi_scale.pow(2)).expand(S)) / (phi_loc / phi_scale.pow(2))
+            if m.include_rho:
+                ga, gb = sg(ps["rho_alpha"].reshape(()).expand(B, S)), sg(ps["rho_beta"].reshape(()).expand(B, S))
+                rho = ga / (ga + gb)
+            else:
+                rho = torch.zeros((B, S), device=dev)
+            d_empty = torch.exp(ps["d_empty_loc"].reshape(()) + ps["d_empty_scale"].reshape(()) * torch.randn((B, S), device=dev))
+            z = z_loc[:, None, :] + z_scale[:, None, :] * torch.randn((B, S, z_loc.shape[1]), device=dev)
+            d_cell = torch.exp((prob * enc["d_loc"] + (1 - prob) * m.d_cell_loc_prior)[:, None]
+                               + ps["d_cell_scale"].reshape(()) * torch.randn((B, S), device=dev))
+            epsilon = sg(((prob * enc["epsilon"] + (1 - prob)) * m.epsilon_prior)[:, None].expand(B, S)) / m.epsilon_prior
         else:
             phi, rho, d_empty, z, d_cell, epsilon = (noise[k].to(self.device) for k in ("phi", "rho", "d_empty", "z", "d_cell", "epsilon"))
         y = (enc["p_y"] > 0).float()[:, None].expand(B, S)

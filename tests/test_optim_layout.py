@@ -37,6 +37,8 @@ def test_flat_layout_big_blocks_first_and_views_alias(monkeypatch):
         if p.dim() == 2 and p.numel() >= (1 << 16):
             assert ld == (lead, (lead + p.shape[1] + 31) // 32 * 32) and p.stride(0) == ld[1] and o % 32 == 0
             assert p._cb_block == (o, p.shape[0], ld[1], p.shape[1])
+        elif p.dim() == 2 and p.shape[1] % 4 != 0:  # small layer with rows TMA could not address: 16-byte row pitch
+            assert ld == (0, (p.shape[1] + 3) // 4 * 4) and p.stride(0) == ld[1] and o % 32 == 0
         else:
             assert ld is None and not hasattr(p, "_cb_block")
     # big blocks occupy [0, tail_start) back to back; every other tensor lives in the tail
