@@ -89,6 +89,7 @@ class DataLoader:
         self._pinned = None
         self._dev_ids = None
         self._gbuf = None
+        self._retired = []
         self._count_only = False
         self._max_batches: Optional[int] = None  # data parallel: every rank serves the same number of minibatches per epoch
         self._served = 0
@@ -123,6 +124,8 @@ class DataLoader:
     def _gather_buffers(self, n: int) -> dict:
         if self._gbuf is None or self._gbuf["cap"] < n:
             G = self.csr.n_genes
+            if self._gbuf is not None:
+                self._retired.append(self._gbuf)  # captured step graphs refer to the old buffers by address: keep them alive
             self._gbuf = {"cap": n, "norm": ops.alloc_rows(n, G, self.device), "lognorm": ops.alloc_rows(n, G, self.device),
                           "feats": torch.empty((n, 4), device=self.device)}
         b = self._gbuf

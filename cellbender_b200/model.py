@@ -257,6 +257,7 @@ class RemoveBackgroundPyroModel(nn.Module):
                                                        else self.param_store["d_empty_loc"])
         self._obs_ctx = None
         self._bufs: Dict[int, dict] = {}
+        self._retired_bufs: list = []
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
     # ---- pyro.param(...) compatibility -----------------------------------------------------------------
@@ -269,6 +270,8 @@ class RemoveBackgroundPyroModel(nn.Module):
         if key not in self._bufs or self._bufs[key]["cap"] < B:
             G, dev = self.n_genes, self.device
             cap = max(B, 8)
+            if key in self._bufs:
+                self._retired_bufs.append(self._bufs[key])  # captured step graphs refer to the old buffers by address
             ld = ops.row_pitch(G)
             chi_b = torch.zeros(ld, device=dev)
             chi_b[:G] = self.avg_gene_expression

@@ -395,9 +395,6 @@ def gather_feats(csr: DeviceCSR, row_ids: torch.Tensor, amb_unit: Optional[torch
 # ------------------------------------------------------------------------------------------------------
 # tcgen05 TF32 GEMM
 # ------------------------------------------------------------------------------------------------------
-_GEMM_WS = {}
-
-
 def gemm_tf32(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
               out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, accumulate: bool = False,
               split_k: Optional[int] = None, a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None,
@@ -414,13 +411,10 @@ def gemm_tf32(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, a_mn: bo
     if split_k is None:
         split_k = int(L.raw("cb_gemm_tf32_suggest_split")(M, N, K + K2))
     ws_elems = int(L.raw("cb_gemm_tf32_workspace_elems")(M, N, split_k))
-    ws = None
-    if ws_elems:
-        key = (dev, torch.cuda.current_stream().cuda_stream)
-        ws = _GEMM_WS.get(key)
-        if ws is None or ws.numel() < ws_elems:
-            ws = torch.empty(ws_elems, dtype=torch.float32, device=dev)
-            _GEMM_WS[key] = ws
+    # split-K partial tiles: a fresh allocation per call from torch's stream-ordered caching allocator.  A captured CUDA
+    # graph refers to the workspace by address, so it must never be a cached buffer that a later call (another minibatch
+    # size, the posterior pass) could replace and free: the allocator keeps a captured graph's memory in that graph's pool.
+    ws = torch.empty(ws_elems, dtype=torch.float32, device=dev) if ws_elems else None
     if tile_cfg:  # explicit tile configuration (tools/gemm_bench.py)
         a2_, b2_ = (a, b) if a2 is None else (a2, b2)
         L.call("cb_gemm_tf32_ex", ptr(a), a.stride(0), ptr(b), b.stride(0), K, ptr(a2_), a2_.stride(0), ptr(b2_), b2_.stride(0), K2,

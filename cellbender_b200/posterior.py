@@ -281,9 +281,10 @@ class Posterior:
         use_graph = self.use_cuda_graph and seed is None and noise_fn is None and n_full >= 2
         if use_graph:
             chunk_entries = np.array([int(prefix[(i + 1) * cpc] - prefix[i * cpc]) for i in range(n_full)])
-            key = (S, n_counts_max, float(smallest_log_probability), float(lambda_multiplier), bool(y_map), cpc, id(ws), id(logits_t))
+            key = (S, n_counts_max, float(smallest_log_probability), float(lambda_multiplier), bool(y_map), cpc)
             cached = getattr(self, "_chunk_graph", None)
-            if cached is not None and cached["key"] == key and cached["max_entries"] >= int(chunk_entries.max()):
+            if (cached is not None and cached["key"] == key and cached["ws"] is ws and cached["logits_t"] is logits_t
+                    and cached["max_entries"] >= int(chunk_entries.max())):
                 st, graph, max_entries = cached["st"], cached["graph"], cached["max_entries"]
             else:
                 cached = None
@@ -311,7 +312,8 @@ class Posterior:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     body()
-                self._chunk_graph = {"key": key, "st": st, "graph": graph, "max_entries": max_entries}
+                self._chunk_graph = {"key": key, "st": st, "graph": graph, "max_entries": max_entries, "ws": ws,
+                                     "logits_t": logits_t}
             for i in range(n_full):
                 load(i)
                 graph.replay()

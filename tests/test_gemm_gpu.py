@@ -129,3 +129,41 @@ def test_feat_dw_matches_matmul():
     ref = (dy.double().t() @ feat.double()).float()
     torch.testing.assert_close(dw[:, :4], ref, rtol=1e-5, atol=1e-4)
     assert float((dw[:, 4:] - 7.0).abs().max()) == 0.0
+
+
+def test_captured_split_k_product_survives_later_larger_workspaces():
+    """A captured CUDA graph refers to the split-K workspace by address.  A later product that needs a LARGER workspace
+    (the smaller last minibatch of an epoch picks more splits) followed by torch.cuda.empty_cache() -- which every
+    torch.cuda.graph() capture performs -- must leave the first graph replayable: the workspace may not be a cached buffer
+    that gets replaced and freed (found as an illegal address at the first replay after the second capture)."""
+    from cellbender_b200 import ops
+
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(3)
+    a = torch.randn((64, 4096), device=dev, generator=g)
+    b = torch.randn((128, 4096), device=dev, generator=g)
+    out = torch.zeros((64, 128), device=dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.gemm_tf32(a, b, 64, 128, 4096, out=out, split_k=4)
+    torch.cuda.current_stream().wait_stream(side)
+    want = out.clone()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ops.gemm_tf32(a, b, 64, 128, 4096, out=out, split_k=4)
+    out.zero_()
+    graph.replay()
+    assert torch.equal(out, want)
+    # a product with a much larger workspace, then a second capture (which empties the allocator's cache)
+    a2 = torch.randn((256, 8192), device=dev, generator=g)
+    b2 = torch.randn((512, 8192), device=dev, generator=g)
+    ops.gemm_tf32(a2, b2, 256, 512, 8192, split_k=16)
+    graph2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph2):
+        ops.gemm_tf32(a2, b2, 256, 512, 8192, split_k=16)
+    torch.cuda.empty_cache()
+    out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
