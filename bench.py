@@ -415,7 +415,6 @@ def run_b200(args):
     model.train()
     if world > 1:
         dp.attach(svi, world)
-        opt.p2p_timing = True
 
     def fresh_batches(n):
         out = []
@@ -501,10 +500,13 @@ def run_b200(args):
     e2e_value = (ms_e2e / K) * spe_rank / 1e3
     dp_exchange_ms = None
     if world > 1:
-        tm = dp.p2p_timing(opt)
-        if tm is not None:
-            dp_exchange_ms = {"barrier_before": tm[0], "fused_exchange_kernel": tm[1], "barrier_after": tm[2],
-                              "exposed_total": sum(tm), "nvls": bool(dp.p2p_uses_nvls(opt, world))}
+        # the whole exchange issued alone on idle GPUs (all ranks together): what the overlapped step has to hide
+        alone = dp.exchange_microbench(opt) if svi.dp_mode == "p2p" else None
+        if alone is not None:
+            dp_exchange_ms = {"whole_exchange_alone": alone, "nvls": bool(opt.exchange.nvls),
+                              "regions": len(dp.exchange_regions(opt)),
+                              "note": "barriers + fused reduce / ClippedAdam / parameter delivery of every range, back to back "
+                                      "outside a step; inside the step the large blocks' exchanges overlap backward"}
 
     # ---- per-kernel rooflines (rank 0) ----
     kernels = None

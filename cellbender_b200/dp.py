@@ -8,10 +8,12 @@ shard of the analysed droplets (``shard_rows``).  Each step every rank runs its 
 backward as one CUDA-graph replay); the ELBO is a plain SUM over droplets (train.py:56-63), so the exchange is ONE
 reduction of the flat fp32 gradient buffer (69.4 M values at the PBMC8k shape) followed by the optimizer sweep.  Two
 exchange paths, chosen once in ``attach`` (no environment switch):
-  'p2p'      (default) the exchange is FUSED into the optimizer sweep over NVLink peer memory (``p2p_step``,
-             cb_clipped_adam_p2p / cb_clipped_adam_nvls): every rank owns a 1/R shard, sums the peers' gradient shards
-             out of their buffers (TMA bulk reads, or one multimem.ld_reduce through the NVSwitch), applies ClippedAdam
-             and stores the new parameters into every rank's buffer;
+  'p2p'      (default) the exchange is FUSED into the optimizer sweep over NVLink peer memory (``P2PExchange``,
+             cb_clipped_adam_p2p / cb_clipped_adam_nvls): of every range of the flat buffers each rank owns a 1/R shard,
+             sums the peers' gradient shards out of their buffers (TMA bulk reads, or one multimem.ld_reduce through the
+             NVSwitch), applies ClippedAdam and stores the new parameters into every rank's buffer.  The large weight
+             blocks are exchanged from inside backward, right behind their weight-gradient products, so the NVLink
+             transfer overlaps the rest of backward; the whole step, barriers included, is ONE captured graph;
   'sharded'  NCCL reduce_scatter -> sweep of the 1/R shard -> all_gather: the path taken when the symmetric-memory
              rendezvous is unavailable on the system.
 Stated consequences: the global minibatch is 255 x world_size droplets; every rank takes the SAME number of steps per
@@ -86,7 +88,9 @@ def attach(svi, world_size: int, mode: Optional[str] = None):
         if not have_symm:
             raise RuntimeError("data-parallel mode 'p2p' needs the optimizer's flat buffers in symmetric memory "
                                "(run.setup_inference / optim.get_optimizer(symmetric_group=...))")
-        svi.exchange_and_step = lambda o: p2p_step(o, world_size, rank)
+        # the exchange runs INSIDE the step (and its captured graph): large blocks behind their weight-gradient products,
+        # the rest in FlatClippedAdam.step -- the training loop sees an ordinary single-process step
+        opt.exchange = P2PExchange(opt, world_size, rank)
     elif mode == "sharded":
         if getattr(opt, "n", 0) % (4 * world_size) == 0 and getattr(getattr(opt, "flat_g", None), "is_cuda", False):
             svi.exchange_and_step = lambda o: reduce_scatter_step(o, world_size, rank)
@@ -94,8 +98,8 @@ def attach(svi, world_size: int, mode: Optional[str] = None):
             svi.after_backward = lambda o: dist.all_reduce(o.flat_g, op=dist.ReduceOp.SUM)
     else:
         raise ValueError(f"unknown data-parallel mode {mode!r}: 'p2p' or 'sharded'")
-    if svi.after_backward is None:
-        svi.after_backward = lambda o: None  # marks the step as data parallel (the exchange runs outside the step graph)
+    if mode == "sharded" and svi.after_backward is None:
+        svi.after_backward = lambda o: None  # marks the step as split: the NCCL exchange runs outside the step graph
     svi.dp_mode = mode
     # consistency hooks the training loop calls (train.SVI.step / train.run_training / optim.state_dict)
     svi.sync_offsets = lambda: broadcast_encoder_offsets(svi.model)
@@ -130,13 +134,6 @@ def all_reduce_mean(value: float, device) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device if dist.get_backend() == "nccl" else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item()) / dist.get_world_size()
-
-
-def chunk_bounds(n: int, n_chunks: int, align: int = 4):
-    """[(begin, end)] covering [0, n) in n_chunks nearly equal pieces whose interior boundaries are multiples of
-    ``align`` elements (16-byte alignment of the fp32 buffers for the vectorised Adam kernel)."""
-    cuts = [0] + [min(n, (i * n // n_chunks) // align * align) for i in range(1, n_chunks)] + [n]
-    return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
 
 
 @torch.no_grad()
@@ -176,72 +173,150 @@ def p2p_uses_nvls(opt, world_size: int) -> bool:
 NVLS_MIN_RANKS = 4
 
 
+def region_shard(off: int, n: int, rank: int, world_size: int):
+    """Rank ``rank``'s part [a, b) of the range [off, off + n) of the flat buffers: R nearly equal pieces whose boundaries
+    are multiples of 4 floats (16 bytes: float4 / TMA bulk / multimem granularity); n % 4 == 0."""
+    q = n // 4
+    return off + (q * rank // world_size) * 4, off + (q * (rank + 1) // world_size) * 4
+
+
+class P2PExchange:
+    """The data-parallel exchange fused into the optimizer sweep over NVLink peer memory, one contiguous RANGE of the flat
+    buffers at a time (cb_clipped_adam_p2p / cb_clipped_adam_nvls).  ``region(off, n)``: device-side barrier (on every
+    rank the gradient of the range is complete and its old parameter values are no longer read) -> ONE kernel that, for
+    this rank's 1/R shard of the range, sums the gradient shards of all ranks straight out of their gradient buffers (in
+    rank order), applies ClippedAdam and stores the new parameters into every rank's parameter buffer.  ``finish()``
+    advances the step counter and closes the step with a second barrier (every shard delivered everywhere).
+
+    The large weight blocks are exchanged from INSIDE the backward pass, each right behind its weight-gradient product on
+    the bulk stream (optim.early_block_update), so the NVLink transfer of a block overlaps the rest of backward; the
+    barriers and kernels are ordinary launches and are captured into the step graph with everything else.  Barriers of
+    successive ranges use successive signal-pad channels (same order on every rank)."""
+
+    def __init__(self, opt, world_size: int, rank: int, timeout_ms: int = 20000):
+        self.world, self.rank = int(world_size), int(rank)
+        self.timeout_ms = timeout_ms  # a rank that never arrives traps the waiting kernels instead of hanging the GPUs
+        self.symm_g, self.symm_p = opt.symm_g, opt.symm_p
+        f32 = torch.float32
+        self._g_base = [self.symm_g.get_buffer(r, (opt.n,), f32).data_ptr() for r in range(self.world)]
+        self._p_base = [self.symm_p.get_buffer(r, (opt.n,), f32).data_ptr() for r in range(self.world)]
+        assert self._g_base[rank] == opt.flat_g.data_ptr(), "symmetric gradient buffer is not where flat_g lives"
+        assert self._p_base[rank] == opt.flat_p.data_ptr(), "symmetric parameter buffer is not where flat_p lives"
+        self.nvls = p2p_uses_nvls(opt, self.world)
+        self.opt = opt
+        self._channel = 0
+        self.owned = set()  # (begin, end) element ranges whose moment buffers this rank keeps current
+
+    def shard(self, off: int, n: int):
+        return region_shard(off, n, self.rank, self.world)
+
+    @torch.no_grad()
+    def region(self, off: int, n: int):
+        import ctypes
+
+        from ._cabi import current_stream, lib
+
+        if n <= 0:
+            return
+        assert off % 4 == 0 and n % 4 == 0, "exchange ranges must be 16-byte aligned"
+        opt = self.opt
+        c, self._channel = self._channel, self._channel + 1
+        self.symm_g.barrier(channel=c, timeout_ms=self.timeout_ms)
+        a, b = self.shard(off, n)
+        if b <= a:
+            return
+        self.owned.add((a, b))
+        at = lambda t: t.data_ptr() + 4 * a
+        tab = (opt.lr_table.data_ptr(), opt.beta1_table.data_ptr(), opt.lr_table.numel(), opt.step_count.data_ptr(),
+               float(opt.beta2), float(opt.eps), float(opt.clip), 0, current_stream())
+        if self.nvls:  # in-switch reduction of the gradients, multicast store of the parameters
+            lib().call("cb_clipped_adam_nvls", at(opt.flat_p), at(opt.flat_m), at(opt.flat_v), b - a,
+                       int(self.symm_g.multicast_ptr) + 4 * a, int(self.symm_p.multicast_ptr) + 4 * a, *tab)
+        else:
+            grads = (ctypes.c_void_p * self.world)(*[g + 4 * a for g in self._g_base])
+            peers = [p + 4 * a for r, p in enumerate(self._p_base) if r != self.rank]
+            p_arr = (ctypes.c_void_p * max(1, len(peers)))(*peers)
+            lib().call("cb_clipped_adam_p2p", at(opt.flat_p), at(opt.flat_m), at(opt.flat_v), b - a, ctypes.addressof(grads),
+                       self.world, self.rank, ctypes.addressof(p_arr), len(peers), *tab)
+
+    @torch.no_grad()
+    def finish(self, opt=None):
+        from ._cabi import current_stream, lib
+
+        opt = self.opt
+        at0 = lambda t: t.data_ptr()
+        lib().call("cb_clipped_adam_range", at0(opt.flat_p), at0(opt.flat_g), at0(opt.flat_m), at0(opt.flat_v), 0,
+                   opt.lr_table.data_ptr(), opt.beta1_table.data_ptr(), None, opt.lr_table.numel(), opt.step_count.data_ptr(),
+                   float(opt.beta2), float(opt.eps), float(opt.clip), 1, current_stream())
+        self.symm_p.barrier(channel=0, timeout_ms=self.timeout_ms)
+        self._channel = 0
+
+
+def exchange_regions(opt):
+    """The ranges a whole-buffer exchange walks: every large weight block (laid out first), then the tail."""
+    blocks = sorted({p._cb_block[0]: p._cb_block for p in opt.params
+                     if getattr(p, "_cb_block", None) is not None and p._cb_block[0] < opt.tail_start}.values())
+    out, cur = [], 0
+    for o, rows, ld, cols in blocks:
+        if o > cur:
+            out.append((cur, o - cur))
+        out.append((o, rows * ld))
+        cur = o + rows * ld
+    out.append((cur, opt.n - cur))
+    return [(o, n) for o, n in out if n > 0]
+
+
 @torch.no_grad()
-def p2p_step(opt, world_size: int, rank: int):
-    """The data-parallel exchange fused into the optimizer sweep, over NVLink peer memory (cb_clipped_adam_p2p):
-    device-side barrier (every rank has finished backward) -> ONE kernel that, for this rank's shard, sums the gradient
-    shards of all ranks straight out of their gradient buffers, applies ClippedAdam and stores the new parameters into
-    every rank's parameter buffer -> device-side barrier (every shard delivered).  Replaces NCCL reduce_scatter + sweep +
-    all_gather; same arithmetic per element (gradients summed in rank order).  Moment buffers are sharded as in
-    ``reduce_scatter_step``."""
-    import ctypes
-
-    from ._cabi import current_stream, lib
-
+def p2p_step(opt, world_size: int, rank: int, regions=None):
+    """One whole exchange + sweep outside a backward pass (every range back to back; ``regions`` = [(offset, n)] tiling
+    the buffer, default ``exchange_regions``): what tests/test_dp_single_gpu.py drives with virtual ranks."""
     if not opt.constant_learning_rate and opt.host_steps >= opt.total_steps:
         raise ValueError(f"Tried to step {opt.host_steps + 1} times. The specified number of total steps is {opt.total_steps}")
-    sh = opt.n // world_size
-    a = rank * sh
-    cache = getattr(opt, "_p2p_ptrs", None)
-    if cache is None:
-        f32 = torch.float32
-        grads = [opt.symm_g.get_buffer(r, (opt.n,), f32).data_ptr() + 4 * a for r in range(world_size)]
-        peers = [opt.symm_p.get_buffer(r, (opt.n,), f32).data_ptr() + 4 * a for r in range(world_size) if r != rank]
-        assert grads[rank] == opt.flat_g.data_ptr() + 4 * a, "symmetric gradient buffer is not where flat_g lives"
-        cache = opt._p2p_ptrs = ((ctypes.c_void_p * world_size)(*grads), (ctypes.c_void_p * max(1, len(peers)))(*peers),
-                                 len(peers))
-    g_arr, p_arr, n_peer = cache
-    timeout_ms = 20000  # a rank that never arrives traps the waiting kernels instead of hanging the GPUs
-    timing = bool(getattr(opt, "p2p_timing", False))  # CUDA events around the three phases (diagnostics, see p2p_timing)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timing else None
-    if timing:
-        ev[0].record()
-    opt.symm_g.barrier(channel=0, timeout_ms=timeout_ms)
-    if timing:
-        ev[1].record()
-    at = lambda t: t.data_ptr() + 4 * a
-    tab = (opt.lr_table.data_ptr(), opt.beta1_table.data_ptr(), opt.lr_table.numel(), opt.step_count.data_ptr(),
-           float(opt.beta2), float(opt.eps), float(opt.clip), 1, current_stream())
-    if p2p_uses_nvls(opt, world_size):
-        # in-switch reduction of the gradients, multicast store of the parameters
-        lib().call("cb_clipped_adam_nvls", at(opt.flat_p), at(opt.flat_m), at(opt.flat_v), sh,
-                   int(opt.symm_g.multicast_ptr) + 4 * a, int(opt.symm_p.multicast_ptr) + 4 * a, *tab)
-    else:
-        lib().call("cb_clipped_adam_p2p", at(opt.flat_p), at(opt.flat_m), at(opt.flat_v), sh, ctypes.addressof(g_arr),
-                   world_size, rank, ctypes.addressof(p_arr), n_peer, *tab)
-    if timing:
-        ev[2].record()
-    opt.symm_p.barrier(channel=1, timeout_ms=timeout_ms)
-    if timing:
-        ev[3].record()
-        opt.__dict__.setdefault("_p2p_events", []).append(ev)
+    ex = opt.exchange
+    if ex is None:
+        ex = opt.exchange = P2PExchange(opt, world_size, rank)
+    for off, n in (exchange_regions(opt) if regions is None else regions):
+        ex.region(off, n)
+    ex.finish()
     opt.host_steps += 1
 
 
-def p2p_timing(opt, last: int = 50):
-    """Mean milliseconds of (barrier before, fused kernel, barrier after) over the last recorded steps (set
-    ``opt.p2p_timing = True`` before stepping)."""
-    evs = getattr(opt, "_p2p_events", [])[-last:]
-    if not evs:
+def exchange_microbench(opt, reps: int = 20):
+    """Mean milliseconds of one whole exchange (all ranges back to back, barriers included) issued alone on an idle GPU:
+    the cost the overlapped step hides.  Changes the parameters (real sweeps with the current gradients, step counter
+    restored): call after the measurements that matter."""
+    ex = opt.exchange
+    if ex is None:
         return None
+    step0 = opt.step_count.clone()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    regions = exchange_regions(opt)
+    for i in range(reps + 3):
+        if i == 3:
+            ev[0].record()
+        for off, n in regions:
+            ex.region(off, n)
+        ex.finish()
+    ev[1].record()
     torch.cuda.synchronize()
-    return tuple(float(np.mean([e[i].elapsed_time(e[i + 1]) for e in evs])) for i in range(3))
+    opt.step_count.copy_(step0)
+    return ev[0].elapsed_time(ev[1]) / reps
 
 
 @torch.no_grad()
 def gather_optimizer_state(opt, world_size: int, rank: int):
     """Make the moment buffers complete on every rank after sharded stepping (call before saving a checkpoint)."""
     if world_size <= 1:
+        return
+    ex = getattr(opt, "exchange", None)
+    if ex is not None:
+        # fused exchange: every range of the buffers has its own 1/R shards; keep what this rank owns, sum over ranks
+        mask = torch.zeros(opt.n, dtype=torch.float32, device=opt.flat_m.device)
+        for a, b in ex.owned:
+            mask[a:b] = 1.0
+        for buf in (opt.flat_m, opt.flat_v):
+            buf.mul_(mask)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
         return
     sh = opt.n // world_size
     for buf in (opt.flat_m, opt.flat_v):

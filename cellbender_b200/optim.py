@@ -116,6 +116,11 @@ class FlatClippedAdam:
         self.early_weight_updates = True
         # data parallel with sharded sweeps (dp.attach): callable that completes flat_m / flat_v on every rank
         self.gather_state = None
+        # data parallel over NVLink peer memory (dp.attach, mode 'p2p'): object whose ``region(offset, n)`` performs the
+        # exchange + sharded sweep of one contiguous range of the flat buffers and whose ``finish()`` is the closing barrier;
+        # ``exchange_local`` = True while a step graph is warmed up before capture (no communication: ranks capture alone)
+        self.exchange = None
+        self.exchange_local = False
         self._fused_done: List[tuple] = []
 
     def set_total_steps(self, total_steps: Optional[int]):
@@ -170,11 +175,14 @@ class FlatClippedAdam:
         from ._cabi import current_stream, lib, ptr
 
         o, rows, ld, cols = w._cb_block
+        self._fused_done.append((o, rows, ld, cols, 0))
+        if self.exchange is not None and not self.exchange_local:
+            self.exchange.region(o, rows * ld)  # all ranks: gradient block complete, old weights no longer read
+            return
         at = lambda t: t.data_ptr() + 4 * o
         lib().call("cb_clipped_adam_range", at(self.flat_p), at(self.flat_g), at(self.flat_m), at(self.flat_v), rows * ld,
                    self.lr_table.data_ptr(), self.beta1_table.data_ptr(), ptr(self.step_table), self.lr_table.numel(),
                    self.step_count.data_ptr(), float(self.beta2), float(self.eps), float(self.clip), 0, current_stream())
-        self._fused_done.append((o, rows, ld, cols, 0))
 
     def step(self, grad_scale: float = 1.0):
         """One ClippedAdam step over the flat buffers + one scheduler step."""
@@ -183,6 +191,23 @@ class FlatClippedAdam:
                              f"{self.total_steps}")
         from . import gemm
 
+        if self.exchange is not None and not self.exchange_local:
+            # data parallel: join the bulk stream (the large blocks' exchanges, issued from inside backward), then exchange
+            # the ranges in between (everything but the large blocks), advance the step counter and close the step with the
+            # barrier.  The join comes FIRST so that on every rank the barriers form one dependency chain in the same
+            # order: whatever order the hardware serialises independent graph branches in, a spinning barrier can then
+            # never sit in front of a kernel that an earlier barrier of a peer is waiting for.
+            gemm.join_bulk()
+            cur = 0
+            for o, rows, ld, cols, off in sorted(self._fused_done):
+                assert o >= cur, "fused blocks overlap"
+                self.exchange.region(cur, o - cur)
+                cur = o + rows * ld
+            self.exchange.region(cur, self.n - cur)
+            self.exchange.finish()
+            self._fused_done = []
+            self.host_steps += 1
+            return
         if self._fused_done:
             # blocks already swept behind their weight-gradient GEMM (early_block_update): sweep the ranges between them;
             # nothing here depends on the bulk stream, which is joined only before the step counter advances

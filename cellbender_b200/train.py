@@ -51,7 +51,8 @@ class SVI:
         self.graph_warmup = graph_warmup
         self._graphs = {}
         self._eager_steps = 0
-        # data parallel (dp.attach): the exchange runs eagerly between replays of the forward + backward graph
+        # data parallel (dp.attach): mode 'p2p' puts the exchange inside the step (optim.exchange), nothing to hook here;
+        # mode 'sharded' runs the NCCL exchange eagerly between replays of the forward + backward graph
         self.after_backward = None  # hook(optim): gradient exchange that precedes a full optimizer sweep
         self.exchange_and_step = None  # hook(optim): exchange fused with / followed by the sharded optimizer sweep
         self.sync_offsets = None  # hook(): broadcast the encoder's first-forward offsets (called after the first step)
@@ -139,8 +140,14 @@ class SVI:
         # warm-up and capture on a high-priority stream: the step's critical chain outranks the bulk stream (ops.side_stream)
         side = torch.cuda.Stream(priority=-1)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            body(static)
+        # data parallel with the exchange inside the step: the warm-up run stays local (plain sweeps, no barriers) -- ranks
+        # capture on their own (minibatch sizes differ between shards) and the state is restored below anyway
+        self.optim.exchange_local = True
+        try:
+            with torch.cuda.stream(side):
+                body(static)
+        finally:
+            self.optim.exchange_local = False
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         n0 = _cabi.lib().launch_count

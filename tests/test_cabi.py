@@ -22,6 +22,17 @@ def test_library_exports_every_declared_symbol(built):
     assert not missing, f"declared in the header but not exported: {missing}"
 
 
+def test_launch_count_table_covers_the_header():
+    """gpu_launches (bench.py) is counted per C-ABI call from _cabi_counts: every declared entry point is either a
+    launching call with a count or a host-side query, and the table names nothing the header does not declare."""
+    from cellbender_b200._cabi_counts import LAUNCHES, QUERIES
+
+    declared = set(_cabi.parse_header()) - {"cb_last_error"}
+    assert set(LAUNCHES) | set(QUERIES) == declared, (sorted(declared - set(LAUNCHES) - set(QUERIES)),
+                                                      sorted((set(LAUNCHES) | set(QUERIES)) - declared))
+    assert not set(LAUNCHES) & set(QUERIES) and all(v >= 1 for v in LAUNCHES.values())
+
+
 def test_abi_version_and_error_string(built):
     assert built.raw("cb_abi_version")() == 1
     assert isinstance(built.last_error(), str)

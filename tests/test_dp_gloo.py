@@ -58,13 +58,17 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_chunk_bounds_cover_the_buffer_with_aligned_cuts():
-    for n, k in ((69_441_234, 8), (1000, 8), (7, 8), (4096, 1), (17, 3)):
-        b = dp.chunk_bounds(n, k)
-        assert b[0][0] == 0 and b[-1][1] == n
-        assert all(x[1] == y[0] for x, y in zip(b[:-1], b[1:]))
-        assert all(x[0] % 4 == 0 for x in b)
-        assert all(x[1] > x[0] for x in b)
+def test_region_shards_tile_every_range_with_aligned_cuts():
+    """dp.region_shard: the R shards of a range of the flat buffers tile it exactly, in rank order, on 16-byte boundaries,
+    for lengths that are not multiples of 4 R (the tail behind the large blocks) and ranges shorter than R float4s."""
+    for off, n in ((0, 69_547_264), (17_187_840, 4 * 1013), (64, 4), (128, 12), (0, 4096)):
+        for world in (1, 2, 3, 4, 8, 16):
+            cuts = [dp.region_shard(off, n, r, world) for r in range(world)]
+            assert cuts[0][0] == off and cuts[-1][1] == off + n
+            assert all(x[1] == y[0] for x, y in zip(cuts[:-1], cuts[1:]))
+            assert all(a % 4 == 0 and b % 4 == 0 and b >= a for a, b in cuts)
+            sizes = [b - a for a, b in cuts]
+            assert max(sizes) - min(sizes) <= 4
 
 
 def test_two_rank_exchange_on_gloo():

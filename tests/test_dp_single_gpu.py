@@ -46,7 +46,10 @@ def test_virtual_ranks_p2p_step_equals_allreduce_plus_full_sweep(world):
     # reference state of the contract: full-size moment buffers swept with the summed gradient
     p_ref, m_ref, v_ref = opts[0].flat_p.clone(), torch.zeros_like(opts[0].flat_p), torch.zeros_like(opts[0].flat_p)
     step_ref = torch.zeros(1, dtype=torch.int64, device=DEV)
-    sh = opts[0].n // world
+    # three ranges with sizes that are multiples of 4 floats but not of 4 x world: shards of every range are uneven
+    n = opts[0].n
+    cuts = [0, 4 * 1013, 4 * 1013 + 4 * 2027, n]
+    regions = [(a, b - a) for a, b in zip(cuts[:-1], cuts[1:])] if n > cuts[2] + 64 else None
     for epoch in range(2):
         its = [iter(tl) for tl in loaders]
         for k in range(n_steps):
@@ -57,13 +60,17 @@ def test_virtual_ranks_p2p_step_equals_allreduce_plus_full_sweep(world):
                 g_sum += o.flat_g
             ops.clipped_adam_step(p_ref, g_sum, m_ref, v_ref, opts[0].lr_table, opts[0].beta1_table, step_ref)
             for r in range(world):
-                dp.p2p_step(opts[r], world, r)
+                dp.p2p_step(opts[r], world, r, regions=regions)
             torch.cuda.synchronize()
+            covered = torch.zeros(n, dtype=torch.int32, device=DEV)
             for r, o in enumerate(opts):
                 assert torch.equal(o.flat_p, opts[0].flat_p), "replicas diverged"
-                torch.testing.assert_close(o.flat_m[r * sh:(r + 1) * sh], m_ref[r * sh:(r + 1) * sh], rtol=1e-6, atol=1e-9)
-                torch.testing.assert_close(o.flat_v[r * sh:(r + 1) * sh], v_ref[r * sh:(r + 1) * sh], rtol=1e-6, atol=1e-12)
+                for a, b in o.exchange.owned:  # the moment buffers are current where the rank owns the shard
+                    torch.testing.assert_close(o.flat_m[a:b], m_ref[a:b], rtol=1e-6, atol=1e-9)
+                    torch.testing.assert_close(o.flat_v[a:b], v_ref[a:b], rtol=1e-6, atol=1e-12)
+                    covered[a:b] += 1
                 assert int(o.step_count.item()) == int(step_ref.item()) == o.host_steps
+            assert bool((covered == 1).all()), "the ranks' shards must tile the flat buffers exactly once"
             torch.testing.assert_close(opts[0].flat_p, p_ref, rtol=1e-6, atol=1e-7)
         for it in its:  # every rank's epoch ends after the agreed number of steps
             with pytest.raises(StopIteration):

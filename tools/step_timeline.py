@@ -24,10 +24,21 @@ def main():
 
     from cellbender_b200 import run, synth
 
-    dev = "cuda:0"
+    # under torchrun: the data-parallel step (rank 0 writes its timeline)
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        import torch.distributed as dist
+
+        from cellbender_b200 import dp
+
+        dist.init_process_group("nccl", device_id=torch.device(dev))
     ds = synth.make_config_dataset(a.workload, seed=0, device=dev)
-    model, opt, svi, train_loader, _ = run.setup_inference(ds, run.default_args(), device=dev)
+    model, opt, svi, train_loader, _ = run.setup_inference(ds, run.default_args(), device=dev, rank=rank, world_size=world)
     model.train()
+    if world > 1:
+        dp.attach(svi, world)
     batches = []
     while len(batches) < 12 + a.steps:
         try:
@@ -41,6 +52,13 @@ def main():
         for b in batches[12:]:
             svi.step(b)
         torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        svi._graphs.clear()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
     path = os.path.join(tempfile.mkdtemp(), "trace.json")
     prof.export_chrome_trace(path)
     ev = json.load(open(path))["traceEvents"]
