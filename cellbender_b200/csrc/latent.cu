@@ -163,9 +163,14 @@ __device__ void block_sum_d(double (&v)[N], double* smem) { block_sum<double, N>
 
 // Lower medians (torch.median) of vals over the two disjoint droplet classes mask bit 1 (probable empties) and bit 2
 // (probable cells): index of the element of rank (k-1)/2 in (value, index) order within its class, -1 for an empty
-// class.  Every droplet belongs to exactly one class, so one O(B^2 / threads) rank-counting sweep finds both.
+// class.  Every droplet belongs to exactly one class.  Each droplet gets ONE sortable 64-bit key (class, value bits in
+// total order, index), so its rank inside its class is (number of smaller keys) - (size of the lower class): the
+// rank-counting sweep is one 64-bit compare per pair, split over all threads of the CTA (B x P work items, P = threads
+// / B pieces of the j range per droplet).  r02x profile: the former per-pair class / value / index tests were 30 % of the
+// forward kernel's instructions on half of its warps.
 // res[0] = cells, res[1] = empties, res[2] = number of droplets with mask bit 4 (surely cells).
-__device__ void class_medians(const float* vals, const unsigned char* mask, int B, int* res, int* cnt) {
+__device__ void class_medians(const float* vals, const unsigned char* mask, int B, int* res, int* cnt,
+                              unsigned long long* keys, int* rank_s) {
   if (threadIdx.x < 3) res[threadIdx.x] = (threadIdx.x == 2) ? 0 : -1;
   if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -173,24 +178,57 @@ __device__ void class_medians(const float* vals, const unsigned char* mask, int 
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
     const unsigned char m = mask[i];
     c_cell += (m & 2) ? 1 : 0, c_empty += (m & 1) ? 1 : 0, c_sure += (m & 4) ? 1 : 0;
+    unsigned int bits = __float_as_uint(vals[i]);
+    bits = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);  // unsigned order == float order
+    const unsigned long long cls = ((m & 3) == 2) ? 0ull : 1ull;  // cells sort below empties
+    keys[i] = (cls << 63) | ((unsigned long long)bits << 16) | (unsigned long long)i;
+    rank_s[i] = 0;
   }
   if (c_cell) atomicAdd(&cnt[0], c_cell);
   if (c_empty) atomicAdd(&cnt[1], c_empty);
   if (c_sure) atomicAdd(&res[2], c_sure);
   __syncthreads();
-  for (int i = threadIdx.x; i < B; i += blockDim.x) {
-    const unsigned char bit = mask[i] & 3;
-    const int which = (bit == 2) ? 0 : 1;
-    const int want = (cnt[which] - 1) / 2;
-    const float vi = vals[i];
-    int rank = 0;
-    for (int j = 0; j < B; ++j) {
-      const float vj = vals[j];
-      rank += ((mask[j] & 3) == bit) && ((vj < vi) || (vj == vi && j < i));
-    }
-    if (rank == want) res[which] = i;
+  const int P = (int(blockDim.x) / B) > 1 ? int(blockDim.x) / B : 1;
+  const int len = (B + P - 1) / P;
+  for (int w = threadIdx.x; w < B * P; w += blockDim.x) {
+    const int i = w % B, part = w / B;
+    const unsigned long long ki = keys[i];
+    const int j1 = (part + 1) * len < B ? (part + 1) * len : B;
+    int c = 0;
+#pragma unroll 4
+    for (int j = part * len; j < j1; ++j) c += keys[j] < ki;
+    if (c) atomicAdd(&rank_s[i], c);
   }
   __syncthreads();
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const int which = int(keys[i] >> 63);
+    const int rank = rank_s[i] - (which ? cnt[0] : 0);
+    if (rank == (cnt[which] - 1) / 2) res[which] = i;
+  }
+  __syncthreads();
+}
+
+// ---- z = loc + exp(log_scale) * n over [B, Z]: work distribution of the vector path --------------------------------
+// Z % 4 == 0 and every row 16-byte aligned: LPR lanes (a power of two, Z / 4 rounded up, at most 32) share one droplet,
+// each lane walks float4 columns; a warp covers 32 / LPR droplets at once and the row sums need log2(LPR) shuffles.
+// (Z = 64: 16 lanes per droplet, one float4 each -- a quarter of the instructions of the 32-wide scalar slices.)
+struct ZLanes {
+  int lpr, sub, rw, rows_per_warp;
+};
+__device__ __forceinline__ ZLanes z_lanes(int Z) {
+  ZLanes t;
+  const int z4 = Z >> 2;
+  t.lpr = 1;
+  while (t.lpr < z4 && t.lpr < 32) t.lpr <<= 1;
+  const int lane = threadIdx.x & 31;
+  t.sub = lane & (t.lpr - 1);
+  t.rw = lane / t.lpr;
+  t.rows_per_warp = 32 / t.lpr;
+  return t;
+}
+__device__ __forceinline__ float group_sum(float v, int lpr) {
+  for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -223,9 +261,14 @@ __global__ void latent_beta_kernel(float* __restrict__ gdraw, int B, float* __re
   }
 }
 
+// dynamic shared memory: float zpart_p[B * nchunk], zpart_q[B * nchunk], eps[B], q1[B]; uchar mask[B]; (8-byte aligned)
+// u64 keys[B]; int rank[B]
+__host__ __device__ inline size_t latent_keys_offset(int B, int Z) {
+  return (size_t(B) * ((2 * ((Z + 31) / 32) + 2) * sizeof(float) + 1) + 15) / 16 * 16;
+}
+
 enum Term { T_PHI = 0, T_Z, T_DCELL, T_RHO, T_EPS, T_DEMPTY, T_Y, T_PLR, T_SOFT_EMPTY, T_SOFT_CELL, T_EPS_MEAN, T_EPS_EMPTY_MEAN, T_N };
 
-// dynamic smem layout (both kernels): float zpart_p[B * nchunk], zpart_q[B * nchunk], eps[B], q1[B]; uchar mask[B]
 constexpr int kLatentThreads = 512, kZUnroll = 8;
 __global__ void __launch_bounds__(kLatentThreads) latent_forward_kernel(
     const float* __restrict__ feats, const float* __restrict__ p_out, const float* __restrict__ eps_out,
@@ -233,13 +276,15 @@ __global__ void __launch_bounds__(kLatentThreads) latent_forward_kernel(
     const float* __restrict__ n_z, const float* __restrict__ n_row, const float* __restrict__ g_gamma,
     const float* __restrict__ xx, ScalarParams sp, LatentConsts k, float* __restrict__ z_out, float* __restrict__ coef,
     float* __restrict__ alpha_out, float* __restrict__ w_out, float* __restrict__ terms, float* __restrict__ loss_local,
-    float* __restrict__ enc_out, int* __restrict__ med_idx) {
+    float* __restrict__ enc_out, int* __restrict__ med_idx, int vec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nchunk = (Z + 31) >> 5;
   float* zpart_p = reinterpret_cast<float*>(smem_raw);  // [B * nchunk] partial sums of the prior log-density
   float* zpart_q = zpart_p + B * nchunk;                // [B * nchunk] partial sums of the guide log-density
   float* eps_s = zpart_q + B * nchunk;
   unsigned char* mask = reinterpret_cast<unsigned char*>(eps_s + 2 * B);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + latent_keys_offset(B, Z));
+  int* rank_s = reinterpret_cast<int*>(keys + B);
   __shared__ double red[T_N * 32];
   __shared__ int s_res[3], s_cnt[2];
 
@@ -247,28 +292,78 @@ __global__ void __launch_bounds__(kLatentThreads) latent_forward_kernel(
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
 
   // ---- z = loc + exp(log_scale) * n; sums of the prior and guide log-densities (model.py:262-264, 553-555).
-  // Work unit = (droplet, 32-wide slice of z); every warp keeps kZUnroll units' loads in flight (latency-bound).
-  const int n_units = B * nchunk;
-  for (int u0 = wid * kZUnroll; u0 < n_units; u0 += nw * kZUnroll) {
-    float nn[kZUnroll], ll[kZUnroll], mm[kZUnroll];
+  const int zn = vec ? 1 : nchunk;  // partial sums per droplet
+  if (vec) {
+    const ZLanes t = z_lanes(Z);
+    const int z4 = Z >> 2;
+    constexpr int U = 2;  // droplet groups per iteration: their loads are issued before the first use
+    for (int r0 = wid * t.rows_per_warp; r0 < B; r0 += nw * t.rows_per_warp * U) {
+      float sp_[U], sq_[U];
 #pragma unroll
-    for (int i = 0; i < kZUnroll; ++i) {
-      const int u = u0 + i, r = u / nchunk, j = (u - r * nchunk) * 32 + lane;
-      const bool in = u < n_units && j < Z;
-      nn[i] = in ? n_z[(long long)r * Z + j] : 0.f;
-      ll[i] = in ? z_ls[r * ldz + j] : 0.f;
-      mm[i] = in ? z_loc[r * ldz + j] : 0.f;
+      for (int i = 0; i < U; ++i) sp_[i] = sq_[i] = 0.f;
+      for (int c = t.sub; c < z4; c += t.lpr) {
+        float4 nn[U], ll[U], mm[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          const int r = r0 + i * nw * t.rows_per_warp + t.rw;
+          if (r < B) {
+            nn[i] = *reinterpret_cast<const float4*>(n_z + (long long)r * Z + 4 * c);
+            ll[i] = *reinterpret_cast<const float4*>(z_ls + r * ldz + 4 * c);
+            mm[i] = *reinterpret_cast<const float4*>(z_loc + r * ldz + 4 * c);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          const int r = r0 + i * nw * t.rows_per_warp + t.rw;
+          if (r < B) {
+            const float* n4 = reinterpret_cast<const float*>(&nn[i]);
+            const float* l4 = reinterpret_cast<const float*>(&ll[i]);
+            const float* m4 = reinterpret_cast<const float*>(&mm[i]);
+            float4 zo;
+            float* z4o = reinterpret_cast<float*>(&zo);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const R z = R(m4[e]) + exp(R(l4[e])) * R(n4[e]);
+              z4o[e] = float(z);
+              sp_[i] += float(-R(0.5) * z * z - kHalfLog2Pi);
+              sq_[i] += float(-R(0.5) * R(n4[e]) * R(n4[e]) - R(l4[e]) - kHalfLog2Pi);
+            }
+            *reinterpret_cast<float4*>(z_out + (long long)r * Z + 4 * c) = zo;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const int r = r0 + i * nw * t.rows_per_warp + t.rw;
+        const float a = group_sum(sp_[i], t.lpr), b2 = group_sum(sq_[i], t.lpr);
+        if (r < B && t.sub == 0) zpart_p[r] = a, zpart_q[r] = b2;
+      }
     }
+  } else {
+    // scalar path (Z % 4 != 0 or unaligned rows): work unit = (droplet, 32-wide slice of z); every warp keeps kZUnroll
+    // units' loads in flight
+    const int n_units = B * nchunk;
+    for (int u0 = wid * kZUnroll; u0 < n_units; u0 += nw * kZUnroll) {
+      float nn[kZUnroll], ll[kZUnroll], mm[kZUnroll];
 #pragma unroll
-    for (int i = 0; i < kZUnroll; ++i) {
-      const int u = u0 + i, r = u / nchunk, j = (u - r * nchunk) * 32 + lane;
-      const bool in = u < n_units && j < Z;
-      const R z = R(mm[i]) + exp(R(ll[i])) * R(nn[i]);
-      if (in) z_out[(long long)r * Z + j] = float(z);
-      float sp_ = in ? float(-R(0.5) * z * z - kHalfLog2Pi) : 0.f;
-      float sq_ = in ? float(-R(0.5) * R(nn[i]) * R(nn[i]) - R(ll[i]) - kHalfLog2Pi) : 0.f;
-      sp_ = warp_sum(sp_), sq_ = warp_sum(sq_);
-      if (lane == 0 && u < n_units) zpart_p[u] = sp_, zpart_q[u] = sq_;
+      for (int i = 0; i < kZUnroll; ++i) {
+        const int u = u0 + i, r = u / nchunk, j = (u - r * nchunk) * 32 + lane;
+        const bool in = u < n_units && j < Z;
+        nn[i] = in ? n_z[(long long)r * Z + j] : 0.f;
+        ll[i] = in ? z_ls[r * ldz + j] : 0.f;
+        mm[i] = in ? z_loc[r * ldz + j] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kZUnroll; ++i) {
+        const int u = u0 + i, r = u / nchunk, j = (u - r * nchunk) * 32 + lane;
+        const bool in = u < n_units && j < Z;
+        const R z = R(mm[i]) + exp(R(ll[i])) * R(nn[i]);
+        if (in) z_out[(long long)r * Z + j] = float(z);
+        float sp_ = in ? float(-R(0.5) * z * z - kHalfLog2Pi) : 0.f;
+        float sq_ = in ? float(-R(0.5) * R(nn[i]) * R(nn[i]) - R(ll[i]) - kHalfLog2Pi) : 0.f;
+        sp_ = warp_sum(sp_), sq_ = warp_sum(sq_);
+        if (lane == 0 && u < n_units) zpart_p[u] = sp_, zpart_q[u] = sq_;
+      }
     }
   }
   __syncthreads();
@@ -299,7 +394,7 @@ __global__ void __launch_bounds__(kLatentThreads) latent_forward_kernel(
 
     {
       R zp = R(0.0), zq = R(0.0);
-      for (int c2 = 0; c2 < nchunk; ++c2) zp += R(zpart_p[b * nchunk + c2]), zq += R(zpart_q[b * nchunk + c2]);
+      for (int c2 = 0; c2 < zn; ++c2) zp += R(zpart_p[b * zn + c2]), zq += R(zpart_q[b * zn + c2]);
       acc[T_Z] += zp - e.q1 * zq;
     }
     {  // d_cell: LogNormal prior vs guide (the -log d_cell of both LogNormal densities cancels)
@@ -308,13 +403,15 @@ __global__ void __launch_bounds__(kLatentThreads) latent_forward_kernel(
     }
     if (g.has_rho) {
       const R a0 = k.rho_alpha_prior, b0 = k.rho_beta_prior, lr = log(r), l1r = log1p(-r);
-      const R prior = xlogy_d(a0 - R(1.0), r) + (b0 - R(1.0)) * l1r + lgamma(a0 + b0) - lgamma(a0) - lgamma(b0);
-      const R guide = (g.ra - R(1.0)) * lr + (g.rb - R(1.0)) * l1r + lgamma(g.ra + g.rb) - lgamma(g.ra) - lgamma(g.rb);
+      // the log-normalisers of both Beta densities are the same for every droplet: added once below (7 lgammas per
+      // droplet were a fifth of this kernel's instructions)
+      const R prior = xlogy_d(a0 - R(1.0), r) + (b0 - R(1.0)) * l1r;
+      const R guide = (g.ra - R(1.0)) * lr + (g.rb - R(1.0)) * l1r;
       acc[T_RHO] += prior - guide;
     }
     {
       const R le = log(ee);
-      const R prior = ep * log(ep) + (ep - R(1.0)) * le - ep * ee - lgamma(ep);
+      const R prior = ep * log(ep) + (ep - R(1.0)) * le - ep * ee;  // - lgamma(ep): added once below
       const R guide = s.eps_conc * log(ep) + (s.eps_conc - R(1.0)) * le - ep * ee - lgamma(s.eps_conc);
       acc[T_EPS] += prior - guide;
     }
@@ -337,6 +434,17 @@ __global__ void __launch_bounds__(kLatentThreads) latent_forward_kernel(
     const bool surely_cell = e.counts >= exp(R(k.d_cell_loc_prior));
     mask[b] = (unsigned char)((is_empty ? 1 : 2) | (surely_cell ? 4 : 0));
   }
+  {  // droplet-independent log-normalisers, B times each, one lgamma per thread of the last warp (idle in the row loop
+     // when B < threads)
+    const int t = int(blockDim.x) - 1 - int(threadIdx.x);
+    if (t < 7) {
+      const R a0 = k.rho_alpha_prior, b0 = k.rho_beta_prior;
+      const R arg = t == 0 ? a0 + b0 : t == 1 ? a0 : t == 2 ? b0 : t == 3 ? g.ra + g.rb : t == 4 ? g.ra : t == 5 ? g.rb : ep;
+      const double sign = (t == 0 || t == 4 || t == 5) ? 1.0 : -1.0;  // prior - guide
+      if (t == 6) acc[T_EPS] += -double(B) * double(lgamma(arg));
+      else if (g.has_rho) acc[T_RHO] += sign * double(B) * double(lgamma(arg));
+    }
+  }
   if (threadIdx.x == 0) {
     const R pc0 = k.phi_conc_prior, pr0 = k.phi_rate_prior, lphi = log(phi);
     const R prior = pc0 * log(pr0) + (pc0 - R(1.0)) * lphi - pr0 * phi - lgamma(pc0);
@@ -346,7 +454,7 @@ __global__ void __launch_bounds__(kLatentThreads) latent_forward_kernel(
   }
   __syncthreads();
   // ---- epsilon medians over probable cells / probable empties (model.py:429-443)
-  class_medians(eps_s, mask, B, s_res, s_cnt);
+  class_medians(eps_s, mask, B, s_res, s_cnt, keys, rank_s);
   if (threadIdx.x == 0) {
     const int i_cell = s_res[0], i_empty = s_res[1], n_surely = s_res[2];
     const R lognorm = -log(R(0.01)) - kHalfLog2Pi;
@@ -376,7 +484,7 @@ __global__ void __launch_bounds__(kLatentThreads) latent_backward_kernel(
     const int* __restrict__ med_idx, ScalarParams sp, LatentConsts k, const float* __restrict__ d_z,
     const float* __restrict__ d_coef, const float* __restrict__ d_alpha, const float* __restrict__ d_w,
     const float* __restrict__ g_local, float* __restrict__ d_p_out, float* __restrict__ d_eps_out,
-    float* __restrict__ d_z_loc, float* __restrict__ d_z_ls, long long lddz, ScalarGrads sg) {
+    float* __restrict__ d_z_loc, float* __restrict__ d_z_ls, long long lddz, ScalarGrads sg, int vec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nchunk = (Z + 31) >> 5;
   float* zpart_q = reinterpret_cast<float*>(smem_raw) + B * nchunk;  // same layout as the forward kernel
@@ -392,33 +500,90 @@ __global__ void __launch_bounds__(kLatentThreads) latent_backward_kernel(
     q1_s[b] = float(e.q1);
   }
   __syncthreads();
-  // ---- z: d loss / d loc, d loss / d log_scale; guide log-density sums for the d q1 path (units as in the forward)
-  const int n_units = B * nchunk;
-  for (int u0 = wid * kZUnroll; u0 < n_units; u0 += nw * kZUnroll) {
-    float nn[kZUnroll], ll[kZUnroll], mm[kZUnroll], dd[kZUnroll];
+  // ---- z: d loss / d loc, d loss / d log_scale; guide log-density sums for the d q1 path (work split as in the forward)
+  const int zn = vec ? 1 : nchunk;
+  if (vec) {
+    const ZLanes t = z_lanes(Z);
+    const int z4 = Z >> 2;
+    constexpr int U = 2;
+    for (int r0 = wid * t.rows_per_warp; r0 < B; r0 += nw * t.rows_per_warp * U) {
+      float sq_[U];
 #pragma unroll
-    for (int i = 0; i < kZUnroll; ++i) {
-      const int u = u0 + i, r = u / nchunk, j = (u - r * nchunk) * 32 + lane;
-      const bool in = u < n_units && j < Z;
-      nn[i] = in ? n_z[(long long)r * Z + j] : 0.f;
-      ll[i] = in ? z_ls[r * ldz + j] : 0.f;
-      mm[i] = in ? z_loc[r * ldz + j] : 0.f;
-      dd[i] = (in && d_z) ? d_z[(long long)r * Z + j] : 0.f;
-    }
+      for (int i = 0; i < U; ++i) sq_[i] = 0.f;
+      for (int c = t.sub; c < z4; c += t.lpr) {
+        float4 nn[U], ll[U], mm[U], dd[U];
 #pragma unroll
-    for (int i = 0; i < kZUnroll; ++i) {
-      const int u = u0 + i, r = u / nchunk, j = (u - r * nchunk) * 32 + lane;
-      const bool in = u < n_units && j < Z;
-      const R n = nn[i], ls = ll[i], sc = exp(ls);
-      const R z = R(mm[i]) + sc * n;
-      const R gz = gl * z + R(dd[i]);  // -d/dz of the N(0,1) prior term + observation path
-      if (in) {
-        d_z_loc[r * lddz + j] = float(gz);
-        d_z_ls[r * lddz + j] = float(gz * n * sc - gl * R(q1_s[r]));
+        for (int i = 0; i < U; ++i) {
+          const int r = r0 + i * nw * t.rows_per_warp + t.rw;
+          dd[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < B) {
+            nn[i] = *reinterpret_cast<const float4*>(n_z + (long long)r * Z + 4 * c);
+            ll[i] = *reinterpret_cast<const float4*>(z_ls + r * ldz + 4 * c);
+            mm[i] = *reinterpret_cast<const float4*>(z_loc + r * ldz + 4 * c);
+            if (d_z) dd[i] = *reinterpret_cast<const float4*>(d_z + (long long)r * Z + 4 * c);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          const int r = r0 + i * nw * t.rows_per_warp + t.rw;
+          if (r < B) {
+            const float* n4 = reinterpret_cast<const float*>(&nn[i]);
+            const float* l4 = reinterpret_cast<const float*>(&ll[i]);
+            const float* m4 = reinterpret_cast<const float*>(&mm[i]);
+            const float* d4 = reinterpret_cast<const float*>(&dd[i]);
+            const R q1 = R(q1_s[r]);
+            float4 o_loc, o_ls;
+            float* ol = reinterpret_cast<float*>(&o_loc);
+            float* os = reinterpret_cast<float*>(&o_ls);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const R n = n4[e], ls = l4[e], sc = exp(ls);
+              const R z = R(m4[e]) + sc * n;
+              const R gz = gl * z + R(d4[e]);  // -d/dz of the N(0,1) prior term + observation path
+              ol[e] = float(gz);
+              os[e] = float(gz * n * sc - gl * q1);
+              sq_[i] += float(-R(0.5) * n * n - ls - kHalfLog2Pi);
+            }
+            *reinterpret_cast<float4*>(d_z_loc + r * lddz + 4 * c) = o_loc;
+            *reinterpret_cast<float4*>(d_z_ls + r * lddz + 4 * c) = o_ls;
+          }
+        }
       }
-      float sq_ = in ? float(-R(0.5) * n * n - ls - kHalfLog2Pi) : 0.f;
-      sq_ = warp_sum(sq_);
-      if (lane == 0 && u < n_units) zpart_q[u] = sq_;
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const int r = r0 + i * nw * t.rows_per_warp + t.rw;
+        const float a = group_sum(sq_[i], t.lpr);
+        if (r < B && t.sub == 0) zpart_q[r] = a;
+      }
+    }
+  } else {
+    const int n_units = B * nchunk;
+    for (int u0 = wid * kZUnroll; u0 < n_units; u0 += nw * kZUnroll) {
+      float nn[kZUnroll], ll[kZUnroll], mm[kZUnroll], dd[kZUnroll];
+#pragma unroll
+      for (int i = 0; i < kZUnroll; ++i) {
+        const int u = u0 + i, r = u / nchunk, j = (u - r * nchunk) * 32 + lane;
+        const bool in = u < n_units && j < Z;
+        nn[i] = in ? n_z[(long long)r * Z + j] : 0.f;
+        ll[i] = in ? z_ls[r * ldz + j] : 0.f;
+        mm[i] = in ? z_loc[r * ldz + j] : 0.f;
+        dd[i] = (in && d_z) ? d_z[(long long)r * Z + j] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < kZUnroll; ++i) {
+        const int u = u0 + i, r = u / nchunk, j = (u - r * nchunk) * 32 + lane;
+        const bool in = u < n_units && j < Z;
+        const R n = nn[i], ls = ll[i], sc = exp(ls);
+        const R z = R(mm[i]) + sc * n;
+        const R gz = gl * z + R(dd[i]);  // -d/dz of the N(0,1) prior term + observation path
+        if (in) {
+          d_z_loc[r * lddz + j] = float(gz);
+          d_z_ls[r * lddz + j] = float(gz * n * sc - gl * R(q1_s[r]));
+        }
+        float sq_ = in ? float(-R(0.5) * n * n - ls - kHalfLog2Pi) : 0.f;
+        sq_ = warp_sum(sq_);
+        if (lane == 0 && u < n_units) zpart_q[u] = sq_;
+      }
     }
   }
   __syncthreads();
@@ -458,10 +623,10 @@ __global__ void __launch_bounds__(kLatentThreads) latent_backward_kernel(
       const R a0 = k.rho_alpha_prior, b0 = k.rho_beta_prior;
       const R dt_dr = (a0 - R(1.0)) / r - (b0 - R(1.0)) / (R(1.0) - r) - (g.ra - R(1.0)) / r + (g.rb - R(1.0)) / (R(1.0) - r);
       G_r += -gl * dt_dr;
-      const R psi_ab = digamma_d(g.ra + g.rb);
-      const R dt_da = -(log(r) + psi_ab - digamma_d(g.ra)), dt_db = -(log1p(-r) + psi_ab - digamma_d(g.rb));
-      ga[3] += -gl * dt_da + G_r * R(dgrad[2 * b]) * (R(1.0) - r);
-      ga[4] += -gl * dt_db - G_r * R(dgrad[2 * b + 1]) * r;
+      // d/d(alpha, beta) of the guide's log-normaliser, psi(a + b) - psi(a | b), is the same for every droplet: added
+      // once below
+      ga[3] += gl * log(r) + G_r * R(dgrad[2 * b]) * (R(1.0) - r);
+      ga[4] += gl * log1p(-r) - G_r * R(dgrad[2 * b + 1]) * r;
     }
     // epsilon (+ the two median regularisers)
     G_e += -gl * (ep - s.eps_conc) / ee;
@@ -477,11 +642,20 @@ __global__ void __launch_bounds__(kLatentThreads) latent_backward_kernel(
     const R dt_y = q1q0 * ((logsigmoid_d(plp) - e.lq1) - (logsigmoid_d(-plp) - e.lq0));
     const R dt_plr = -(e.p_y + R(2.0) * s.n_v - R(k.p_logit_prior)) / R(4.0);
     R zq = R(0.0);
-    for (int c2 = 0; c2 < nchunk; ++c2) zq += R(zpart_q[b * nchunk + c2]);
+    for (int c2 = 0; c2 < zn; ++c2) zq += R(zpart_q[b * zn + c2]);
     const R dt_z = -zq * q1q0;
     R G_py = -gl * (dt_y + dt_plr + dt_z);
     if (d_w) G_py += (-R(d_w[3 * b]) + R(d_w[3 * b + 1]) + R(0.01) * R(d_w[3 * b + 2])) * q1q0;
     d_p_out[b] = float(G_py * e.dpy_dpout);
+  }
+  if (g.has_rho) {  // droplet-independent digammas, B times each, one per thread of the last warp
+    const int t = int(blockDim.x) - 1 - int(threadIdx.x);
+    if (t < 3) {
+      const double v = double(B) * double(gl) * double(digamma_d(t == 0 ? g.ra + g.rb : t == 1 ? g.ra : g.rb));
+      if (t == 0) ga[3] += v, ga[4] += v;
+      else if (t == 1) ga[3] -= v;
+      else ga[4] -= v;
+    }
   }
   R g_pl = R(0.0), g_ps = R(0.0);
   if (threadIdx.x == 0) {  // phi (global)
@@ -608,6 +782,11 @@ __global__ void __launch_bounds__(kSimplexThreads) simplex_backward_kernel(int n
   }
 }
 
+template <typename... P>
+static bool aligned16(const P*... p) {  // null pointers (optional operands) count as aligned
+  return (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ...);
+}
+
 static LatentConsts load_consts(const float* h) {
   LatentConsts k;
   float* dst = reinterpret_cast<float*>(&k);
@@ -615,7 +794,7 @@ static LatentConsts load_consts(const float* h) {
   return k;
 }
 
-static size_t latent_smem(int B, int Z) { return size_t(B) * ((2 * ((Z + 31) / 32) + 2) * sizeof(float) + 1) + 16; }
+static size_t latent_smem(int B, int Z) { return latent_keys_offset(B, Z) + size_t(B) * 12 + 16; }
 
 }  // namespace cb
 
@@ -650,9 +829,10 @@ extern "C" int cb_latent_forward(const float* feats, const float* p_out, const f
                                  void* stream) {
   CB_REQUIRE(n_rows > 0 && n_rows <= 2048 && z_dim > 0 && z_dim <= 256, "cb_latent_forward: n_rows %d / z_dim %d out of range", n_rows, z_dim);
   cb::ScalarParams sp{u_d_cell_scale, u_d_empty_loc, u_d_empty_scale, u_rho_alpha, u_rho_beta, u_phi_loc, u_phi_scale};
+  const int vec = z_dim % 4 == 0 && ldz % 4 == 0 && cb::aligned16(z_loc, z_log_scale, noise_z, z_out);
   cb::latent_forward_kernel<<<1, cb::kLatentThreads, cb::latent_smem(n_rows, z_dim), (cudaStream_t)stream>>>(
       feats, p_out, eps_out, z_loc, z_log_scale, ldz, n_rows, z_dim, noise_z, noise_row, gamma_draws, xx, sp,
-      cb::load_consts(consts_h), z_out, coef, alpha, w, terms, loss_local, enc_out, med_idx);
+      cb::load_consts(consts_h), z_out, coef, alpha, w, terms, loss_local, enc_out, med_idx, vec);
   return cb::check_launch("cb_latent_forward");
 }
 
@@ -670,10 +850,12 @@ extern "C" int cb_latent_backward(const float* feats, const float* p_out, const 
   CB_REQUIRE(n_rows > 0 && n_rows <= 2048 && z_dim > 0 && z_dim <= 256, "cb_latent_backward: n_rows %d / z_dim %d out of range", n_rows, z_dim);
   cb::ScalarParams sp{u_d_cell_scale, u_d_empty_loc, u_d_empty_scale, u_rho_alpha, u_rho_beta, u_phi_loc, u_phi_scale};
   cb::ScalarGrads sg{g_d_cell_scale, g_d_empty_loc, g_d_empty_scale, g_rho_alpha, g_rho_beta, g_phi_loc, g_phi_scale};
+  const int vec = z_dim % 4 == 0 && ldz % 4 == 0 && lddz % 4 == 0 &&
+                  cb::aligned16(z_loc, z_log_scale, noise_z, d_z, d_z_loc, d_z_log_scale);
   cb::latent_backward_kernel<<<1, cb::kLatentThreads, cb::latent_smem(n_rows, z_dim), (cudaStream_t)stream>>>(
       feats, p_out, eps_out, z_loc, z_log_scale, ldz, n_rows, z_dim, noise_z, noise_row, gamma_draws, xx, gamma_grad,
       dirichlet_grad, med_idx, sp, cb::load_consts(consts_h), d_z, d_coef, d_alpha, d_w, g_local, d_p_out, d_eps_out, d_z_loc,
-      d_z_log_scale, lddz, sg);
+      d_z_log_scale, lddz, sg, vec);
   return cb::check_launch("cb_latent_backward");
 }
 

@@ -41,7 +41,8 @@ def _grad_target(weight: torch.Tensor):
 
 _PENDING_JOINS = []
 _BULK_PENDING = []
-BULK_STREAM, SMALL_GRAD_STREAM = 0, 5  # ops.side_stream indices
+_CALLBACK_QUEUED = []  # non-empty while the running backward pass has its end-of-backward join callback queued
+BULK_STREAM, SMALL_GRAD_STREAM, LATE_GRAD_STREAM = 0, 5, 6  # ops.side_stream indices
 
 
 def grad_stream(device, weights) -> "torch.cuda.Stream":
@@ -52,6 +53,14 @@ def grad_stream(device, weights) -> "torch.cuda.Stream":
     return ops.side_stream(device, BULK_STREAM if big else SMALL_GRAD_STREAM)
 
 
+def late_grad_stream(device) -> "torch.cuda.Stream":
+    """High-priority stream for the G-wide weight-gradient products of the encoders' input layers.  They run at the very end
+    of backward, when nothing of the critical chain is left to protect: on the low-priority bulk stream they queued behind
+    the optimizer sweeps of the blocks finished before them and crawled (r02y timeline: 201 us for a 37 us product), which
+    postponed their own sweeps -- the tail of the step.  Only the sweeps stay on the bulk stream."""
+    return ops.side_stream(device, LATE_GRAD_STREAM)
+
+
 def defer_join(side: "torch.cuda.Stream"):
     """Postpone ``current_stream().wait_stream(side)`` to the end of the running backward pass.  Weight / bias gradients
     that a forked kernel writes straight into the optimizer's flat gradient buffer have no consumer inside backward, so
@@ -59,11 +68,13 @@ def defer_join(side: "torch.cuda.Stream"):
     of the node; the autograd engine's final callback joins every such stream before control returns to the caller --
     except the bulk stream, which the optimizer joins as late as it can (``join_bulk``: after the sweep of everything
     the bulk stream does not touch)."""
-    if not _PENDING_JOINS and not _BULK_PENDING:
+    if not _CALLBACK_QUEUED:
         def _join_all():
+            _CALLBACK_QUEUED.clear()
             main = torch.cuda.current_stream()
             while _PENDING_JOINS:
                 main.wait_stream(_PENDING_JOINS.pop())
+        _CALLBACK_QUEUED.append(True)
         torch.autograd.Variable._execution_engine.queue_callback(_join_all)
     bulk = ops.side_stream(side.device, BULK_STREAM)
     if side is bulk and FUSED_OPT is not None:  # an optimizer step follows and will join (train.SVI sets FUSED_OPT)
@@ -208,6 +219,10 @@ class _MultiLinearBig(torch.autograd.Function):
             db_t = _grad_target(ctx.biases[i]) if (has_bias[i] and ctx.needs_input_grad[4 + 3 * i + 2]) else None
             targets.append((dw_t, db_t))
 
+        early = [i for i in range(n) if targets[i][0] is not None and early_update_applies(weights_p[i])
+                 and targets[i][0][1] is None]
+        dw_done = {}
+
         def parameter_gradients():
             for i in range(n):
                 dy, w, feat = dys[i], weights[i], feats[i]
@@ -222,13 +237,17 @@ class _MultiLinearBig(torch.autograd.Function):
                         ops.feat_dw(dy, feat, dw_t[0])
                 if db_t is not None:
                     ops.colsum_rows(dy, H, out=db_t[0])
+                if i in early:
+                    dw_done[i] = torch.cuda.Event()
+                    dw_done[i].record()
 
         # the weight-gradient products and the input-gradient product are independent: fork the former onto a side
         # stream (parallel branches of the captured step graph), join before returning
-        fork = need_dx and any(t[0] is not None or t[1] is not None for t in targets)
+        big = any(w.numel() >= FUSED_MIN_NUMEL for w in weights)
+        fork = (need_dx or big) and any(t[0] is not None or t[1] is not None for t in targets)
         main = torch.cuda.current_stream()
         if fork:
-            side = grad_stream(x.device, weights)
+            side = late_grad_stream(x.device) if big else grad_stream(x.device, weights)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 parameter_gradients()
@@ -245,19 +264,20 @@ class _MultiLinearBig(torch.autograd.Function):
                     w = weights[i]
                     ops.gemm_tf32(dys[i], w[:, off:off + n_in], B, n_in, w.shape[0], b_mn=True, out=dx, accumulate=i > 0,
                                   split_k=1)
-        # piecewise optimizer sweep: the large weight blocks of this node are complete -> update them now, on the stream
-        # that produced their gradients, overlapping the rest of backward (the sweep is HBM-bound, backward is not);
-        # it must follow every reader of the OLD weights, i.e. the input-gradient product issued above
-        early = [i for i in range(n) if targets[i][0] is not None and early_update_applies(weights_p[i])
-                 and targets[i][0][1] is None]
+        # piecewise optimizer sweep: the large weight blocks of this node are complete -> update them now, overlapping the
+        # rest of backward (the sweep is HBM-bound, backward is not); it must follow every reader of the OLD weights, i.e.
+        # the input-gradient product issued above
+        bulk = None
         if early:
-            upd_stream = side if fork else main
-            if fork:
-                readers_done = torch.cuda.Event()
-                readers_done.record(main)
-                upd_stream.wait_event(readers_done)
-            with torch.cuda.stream(upd_stream):
+            # the sweeps go to the low-priority bulk stream, each behind its own gradient product and the readers of the
+            # old weights
+            bulk = ops.side_stream(x.device, BULK_STREAM)
+            readers_done = torch.cuda.Event()
+            readers_done.record(main)
+            bulk.wait_event(readers_done)
+            with torch.cuda.stream(bulk):
                 for i in early:
+                    bulk.wait_event(dw_done[i])
                     FUSED_OPT.early_block_update(weights_p[i])
         grads = []
         for i in range(n):
@@ -273,6 +293,8 @@ class _MultiLinearBig(torch.autograd.Function):
                 defer_join(side)
             else:
                 main.wait_stream(side)
+        if bulk is not None:
+            defer_join(bulk)
         return (dx, None, None, None, *grads)
 
 
