@@ -115,11 +115,17 @@ def setup_inference(dataset_obj, args, device: Optional[str] = None, total_epoch
     return model, scheduler, svi, train_loader, test_loader
 
 
-def run_inference(dataset_obj, args, device: Optional[str] = None, total_epochs_for_testing_only: Optional[int] = None
-                  ) -> Tuple[RemoveBackgroundPyroModel, FlatClippedAdam, DataLoader, DataLoader]:
-    """Full inference procedure (run.py:632-856 without checkpoint tarballs and the ELBO-retry re-entry)."""
+def run_inference(dataset_obj, args, device: Optional[str] = None, total_epochs_for_testing_only: Optional[int] = None,
+                  rank: int = 0, world_size: int = 1) -> Tuple[RemoveBackgroundPyroModel, FlatClippedAdam, DataLoader, DataLoader]:
+    """Full inference procedure (run.py:632-856 without checkpoint tarballs and the ELBO-retry re-entry).  With
+    ``world_size`` > 1 (one process per GPU, torch.distributed initialised) training is data parallel, see dp.py."""
     model, scheduler, svi, train_loader, test_loader = setup_inference(
-        dataset_obj, args, device=device, total_epochs_for_testing_only=total_epochs_for_testing_only)
+        dataset_obj, args, device=device, total_epochs_for_testing_only=total_epochs_for_testing_only, rank=rank,
+        world_size=world_size)
+    if world_size > 1:
+        from . import dp
+
+        dp.attach(svi, world_size)
     if args.epochs > 0:
         logger.info("Running inference...")
         run_training(model=model, svi=svi, train_loader=train_loader, test_loader=test_loader, epochs=args.epochs,
@@ -173,12 +179,14 @@ def compute_output_denoised_counts(posterior, args, fpr_list=None):
     return out
 
 
-def run_remove_background(dataset_obj, args, device: Optional[str] = None):
+def run_remove_background(dataset_obj, args, device: Optional[str] = None, rank: int = 0, world_size: int = 1):
     """``run_remove_background`` from the prepared dataset on (run.py:126-168, 228-330): inference, posterior, denoised
-    counts per FPR.  File output, report and checkpoint tarballs stay with the caller.  Returns (posterior, {fpr: csc})."""
+    counts per FPR.  File output, report and checkpoint tarballs stay with the caller.  Returns (posterior, {fpr: csc}).
+    With ``world_size`` > 1 training is data parallel; every rank then holds the same model and computes the (small)
+    remainder itself."""
     from .posterior import Posterior
 
-    model, _, _, _ = run_inference(dataset_obj, args, device=device)
+    model, _, _, _ = run_inference(dataset_obj, args, device=device, rank=rank, world_size=world_size)
     model.eval()
     posterior = Posterior(dataset_obj=dataset_obj, vi_model=model, posterior_batch_size=args.posterior_batch_size,
                           debug=getattr(args, "debug", False))

@@ -100,7 +100,8 @@ def make_golden(a):
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
-def run_product(config: str, epochs: int, device: str = "cuda:0", fpr: float = 0.01, log=None):
+def run_product(config: str, epochs: int, device: str = "cuda:0", fpr: float = 0.01, log=None, rank: int = 0,
+                world_size: int = 1):
     """The product end to end through its public API: run_inference -> Posterior.latents_map ->
     cell_noise_count_posterior_coo -> compute_mean_target_removal_as_function -> compute_denoised_counts(MCKP) ->
     restore_eliminated_features_in_cells (cellbender_b200.run.run_remove_background)."""
@@ -111,7 +112,7 @@ def run_product(config: str, epochs: int, device: str = "cuda:0", fpr: float = 0
     ds = synth.load_fixture_dataset(os.path.join(GOLDEN_DIR, f"e2e_{config}_dataset.npz"))
     args = run.default_args(epochs=epochs, fpr=[fpr])
     t0 = time.time()
-    posterior, denoised = run.run_remove_background(ds, args, device=device)
+    posterior, denoised = run.run_remove_background(ds, args, device=device, rank=rank, world_size=world_size)
     torch.cuda.synchronize()
     seconds = time.time() - t0
     p = posterior.latents_map["p"]
@@ -186,9 +187,24 @@ def main():
 
         golden = np.load(os.path.join(GOLDEN_DIR, f"e2e_{a.config}.npz"), allow_pickle=False)
         assert int(golden["epochs"]) == a.epochs, "golden was made with a different number of epochs"
-        ds, s = run_product(a.config, a.epochs)
+        # under torchrun: data-parallel training over all ranks (global minibatch 255 x world_size, total steps / world_size);
+        # every rank finishes the pipeline with the common model, rank 0 reports
+        world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        ds, s = run_product(a.config, a.epochs, device=f"cuda:{local}", rank=rank, world_size=world)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+            if rank != 0:
+                return
         res = compare(golden, s, synth.dataset_checksum(ds.matrix))
         res["product_seconds"] = s["seconds"]
+        res["world_size"] = world
         text = json.dumps(res, indent=1)
         print(text)
         if a.out:
