@@ -275,9 +275,17 @@ __device__ __forceinline__ void multimem_st(float* mc_ptr, const float4& x) {
 // kNvlsUnroll in-switch reductions are issued back to back before the first one is consumed: the round trip through the
 // NVSwitch is several microseconds, and one 16-byte request per thread (r01) left the links latency-bound.
 constexpr int kNvlsUnroll = 4;
+struct NvlsPeers {
+  float* param[kMaxRanks];  // this shard inside every OTHER rank's parameter buffer (ST_P2P only)
+  int n_peer;
+};
+// LD: 0 = multimem.ld_reduce of the gradient (in-switch sum), 1 = this rank's gradient only (diagnostic: isolates the
+// store path).  ST: 0 = multimem.st (one multicast store), 1 = plain store to the local buffer + posted P2P stores to
+// every peer, 2 = local store only (diagnostic: isolates the reduction path).
+template <int LD, int ST>
 __global__ void __launch_bounds__(256) clipped_adam_nvls_kernel(float* p, float* __restrict__ m, float* __restrict__ v, long long n,
-                                                                const float* mc_grad, float* mc_param,
-                                                                const float* __restrict__ lr_table,
+                                                                const float* mc_grad, float* mc_param, const float* local_grad,
+                                                                NvlsPeers peers, const float* __restrict__ lr_table,
                                                                 const float* __restrict__ beta1_table, long long table_len,
                                                                 const long long* __restrict__ step_ptr, float beta2, float eps,
                                                                 float clip) {
@@ -294,7 +302,10 @@ __global__ void __launch_bounds__(256) clipped_adam_nvls_kernel(float* p, float*
 #pragma unroll
     for (int u = 0; u < kNvlsUnroll; ++u) {
       const long long i = i0 + u * stride;
-      if (i < n4) gg[u] = multimem_ld_reduce_add(mc_grad + 4 * i);
+      if (i < n4) {
+        if (LD == 0) gg[u] = multimem_ld_reduce_add(mc_grad + 4 * i);
+        else gg[u] = __ldcg(reinterpret_cast<const float4*>(local_grad) + i);
+      }
     }
 #pragma unroll
     for (int u = 0; u < kNvlsUnroll; ++u) {
@@ -322,7 +333,16 @@ __global__ void __launch_bounds__(256) clipped_adam_nvls_kernel(float* p, float*
       }
       reinterpret_cast<float4*>(m)[i] = mm[u];
       reinterpret_cast<float4*>(v)[i] = vv[u];
-      multimem_st(mc_param + 4 * i, pp[u]);  // every rank's parameter buffer, this rank's included
+      if (ST == 0) {
+        multimem_st(mc_param + 4 * i, pp[u]);  // every rank's parameter buffer, this rank's included
+      } else {
+        reinterpret_cast<float4*>(p)[i] = pp[u];
+        if (ST == 1) {
+#pragma unroll
+          for (int k = 0; k < kMaxRanks - 1; ++k)
+            if (k < peers.n_peer) __stcg(reinterpret_cast<float4*>(peers.param[k]) + i, pp[u]);
+        }
+      }
     }
   }
 }
@@ -423,22 +443,56 @@ extern "C" int cb_clipped_adam_p2p(float* p, float* m, float* v, long long n, co
 }
 
 // The NVLS form of cb_clipped_adam_p2p: mc_grad / mc_param are the multicast addresses of this rank's shard inside the
-// symmetric gradient / parameter buffers; p / m / v the local shard (p is only read here: the multicast store writes it).
-extern "C" int cb_clipped_adam_nvls(float* p, float* m, float* v, long long n, const float* mc_grad, float* mc_param,
-                                    const float* lr_table, const float* beta1_table, long long table_len,
-                                    long long* step_ptr, float beta2, float eps, float clip, int advance, void* stream) {
+// symmetric gradient / parameter buffers; p / m / v the local shard.  ld_mode / st_mode: see clipped_adam_nvls_kernel
+// (0 / 0 = in-switch reduction + multicast store); local_grad: this rank's own gradient shard (ld_mode 1);
+// peer_param_ptrs[n_peer]: the shard inside the other ranks' parameter buffers (st_mode 1); blocks_per_sm: grid cap.
+extern "C" int cb_clipped_adam_nvls_ex(float* p, float* m, float* v, long long n, const float* mc_grad, float* mc_param,
+                                       const float* local_grad, float* const* peer_param_ptrs, int n_peer, int ld_mode,
+                                       int st_mode, int blocks_per_sm, const float* lr_table, const float* beta1_table,
+                                       long long table_len, long long* step_ptr, float beta2, float eps, float clip,
+                                       int advance, void* stream) {
   CB_REQUIRE(n >= 0 && (n & 3) == 0 && table_len > 0, "cb_clipped_adam_nvls: n=%lld must be a non-negative multiple of 4", n);
-  CB_REQUIRE(mc_grad != nullptr && mc_param != nullptr, "cb_clipped_adam_nvls: multicast pointers must not be NULL");
-  for (const void* x : {(const void*)p, (const void*)m, (const void*)v, (const void*)mc_grad, (const void*)mc_param})
+  CB_REQUIRE(ld_mode >= 0 && ld_mode <= 1 && st_mode >= 0 && st_mode <= 2 && blocks_per_sm >= 1,
+             "cb_clipped_adam_nvls: bad mode %d / %d / %d", ld_mode, st_mode, blocks_per_sm);
+  CB_REQUIRE((ld_mode != 0 || mc_grad != nullptr) && (st_mode != 0 || mc_param != nullptr),
+             "cb_clipped_adam_nvls: multicast pointers must not be NULL");
+  CB_REQUIRE(ld_mode != 1 || local_grad != nullptr, "cb_clipped_adam_nvls: ld_mode 1 needs the local gradient");
+  CB_REQUIRE(n_peer >= 0 && n_peer < cb::kMaxRanks && (st_mode != 1 || n_peer == 0 || peer_param_ptrs != nullptr),
+             "cb_clipped_adam_nvls: bad peer list (%d)", n_peer);
+  for (const void* x : {(const void*)p, (const void*)m, (const void*)v, (const void*)mc_grad, (const void*)mc_param,
+                        (const void*)local_grad})
     CB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "cb_clipped_adam_nvls: buffers must be 16-byte aligned");
+  cb::NvlsPeers peers{};
+  peers.n_peer = st_mode == 1 ? n_peer : 0;
+  for (int k = 0; k < peers.n_peer; ++k) {
+    peers.param[k] = peer_param_ptrs[k];
+    CB_REQUIRE(peers.param[k] != nullptr && (reinterpret_cast<uintptr_t>(peers.param[k]) & 15) == 0,
+               "cb_clipped_adam_nvls: bad peer pointer %d", k);
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (n > 0) {
     long long blocks = (n / 4 + 256 * cb::kNvlsUnroll - 1) / (256 * cb::kNvlsUnroll);
-    const long long cap = 6LL * cb::sm_count();
+    const long long cap = (long long)blocks_per_sm * cb::sm_count();
     if (blocks > cap) blocks = cap;
-    cb::clipped_adam_nvls_kernel<<<unsigned(blocks), 256, 0, st>>>(p, m, v, n, mc_grad, mc_param, lr_table, beta1_table, table_len,
-                                                                   step_ptr, beta2, eps, clip);
+#define CB_NVLS_LAUNCH(LD, ST)                                                                                              \
+  cb::clipped_adam_nvls_kernel<LD, ST><<<unsigned(blocks), 256, 0, st>>>(p, m, v, n, mc_grad, mc_param, local_grad, peers,   \
+                                                                         lr_table, beta1_table, table_len, step_ptr, beta2, \
+                                                                         eps, clip)
+    if (ld_mode == 0 && st_mode == 0) CB_NVLS_LAUNCH(0, 0);
+    else if (ld_mode == 0 && st_mode == 1) CB_NVLS_LAUNCH(0, 1);
+    else if (ld_mode == 0 && st_mode == 2) CB_NVLS_LAUNCH(0, 2);
+    else if (ld_mode == 1 && st_mode == 0) CB_NVLS_LAUNCH(1, 0);
+    else if (ld_mode == 1 && st_mode == 1) CB_NVLS_LAUNCH(1, 1);
+    else CB_NVLS_LAUNCH(1, 2);
+#undef CB_NVLS_LAUNCH
   }
   if (advance) cb::advance_step_kernel<<<1, 1, 0, st>>>(step_ptr);
   return cb::check_launch("cb_clipped_adam_nvls");
+}
+
+extern "C" int cb_clipped_adam_nvls(float* p, float* m, float* v, long long n, const float* mc_grad, float* mc_param,
+                                    const float* lr_table, const float* beta1_table, long long table_len,
+                                    long long* step_ptr, float beta2, float eps, float clip, int advance, void* stream) {
+  return cb_clipped_adam_nvls_ex(p, m, v, n, mc_grad, mc_param, nullptr, nullptr, 0, 0, 0, 6, lr_table, beta1_table, table_len,
+                                 step_ptr, beta2, eps, clip, advance, stream);
 }

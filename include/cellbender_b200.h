@@ -253,6 +253,13 @@ int cb_clipped_adam_p2p(float* p, float* m, float* v, long long n, const float* 
 int cb_clipped_adam_nvls(float* p, float* m, float* v, long long n, const float* mc_grad, float* mc_param,
                          const float* lr_table, const float* beta1_table, long long table_len, long long* step_ptr,
                          float beta2, float eps, float clip, int advance, void* stream);
+/* The same with the transfer paths chosen explicitly (tools/nvls_microbench.py measures them; cb_clipped_adam_nvls is
+ * ld_mode 0, st_mode 0, 6 CTAs per SM).  ld_mode: 0 = multimem.ld_reduce, 1 = local_grad only (diagnostic).  st_mode:
+ * 0 = multimem.st, 1 = local store + posted P2P stores to peer_param_ptrs[n_peer], 2 = local store only (diagnostic). */
+int cb_clipped_adam_nvls_ex(float* p, float* m, float* v, long long n, const float* mc_grad, float* mc_param,
+                            const float* local_grad, float* const* peer_param_ptrs, int n_peer, int ld_mode, int st_mode,
+                            int blocks_per_sm, const float* lr_table, const float* beta1_table, long long table_len,
+                            long long* step_ptr, float beta2, float eps, float clip, int advance, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * A10-A12  posterior noise-count log-probability over the stored (non-zero) counts.  Replaces
