@@ -40,13 +40,14 @@ __global__ void __launch_bounds__(kPostThreads) posterior_window_kernel(
     const long long* __restrict__ gene_all, long long total_n_genes, float log_thresh, float lambda_multiplier,
     const long long* __restrict__ out_offset, float* __restrict__ logp_out, int* __restrict__ low_out,
     int* __restrict__ keep_cnt, long long* __restrict__ entry_m) {
-  // the grid may be sized for an upper bound of the chunk's stored counts (CUDA-graph replays): surplus CTAs exit here
+  // the grid may be sized for an upper bound of the chunk's stored counts (CUDA-graph replays), or capped at a few CTAs
+  // per SM so that the kernel shares the GPU with the decoder product of the next chunk: tiles are strided over the CTAs
   const long long n_entries = entry_start[n_cells];
-  if (blockIdx.x * (long long)(kPostThreads / 4) >= n_entries) return;
   const long long o0 = out_offset ? out_offset[0] : 0;  // first output row of this chunk (device scalar)
   logp_out += o0 * NMAX, low_out += o0, keep_cnt += o0, entry_m += o0;
-  const long long e = blockIdx.x * (long long)(kPostThreads / 4) + (threadIdx.x >> 2);
   const int sub = threadIdx.x & 3;
+  for (long long tile = blockIdx.x; tile * (kPostThreads / 4) < n_entries; tile += gridDim.x) {
+  const long long e = tile * (long long)(kPostThreads / 4) + (threadIdx.x >> 2);
   const bool active = e < n_entries;
   // cell of this entry: last b with entry_start[b] <= e
   int b = 0;
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(kPostThreads) posterior_window_kernel(
     keep_cnt[e] = cnt;
     entry_m[e] = barcode_all[b] * total_n_genes + gene_all[g];
   }
+  }  // tile loop
 }
 
 // Writes the COO triplets in (cell, gene, c) order -- the order torch.nonzero gives the reference.
@@ -208,13 +210,16 @@ extern "C" int cb_posterior_noise_window(const long long* indptr, const int* ind
                                          const long long* entry_start, long long max_entries, const long long* barcode_all,
                                          const long long* gene_all, long long total_n_genes, int n_counts_max,
                                          float log_thresh, float lambda_multiplier, const long long* out_offset,
-                                         float* logp_out, int* low_out, int* keep_cnt, long long* entry_m, void* stream) {
+                                         float* logp_out, int* low_out, int* keep_cnt, long long* entry_m, int ctas_per_sm,
+                                         void* stream) {
   if (n_cells == 0 || max_entries == 0) return 0;
   const long long n_entries = max_entries;
   CB_REQUIRE(n_cells > 0 && n_genes > 0 && n_samples > 0 && n_entries > 0, "cb_posterior_noise_window: bad shape");
   CB_REQUIRE(ldt >= (long long)n_cells * n_samples, "cb_posterior_noise_window: ldt=%lld < n_cells * n_samples", ldt);
   CB_REQUIRE(n_counts_max > 0 && n_counts_max <= 64, "cb_posterior_noise_window: n_counts_max=%d not in [1, 64]", n_counts_max);
-  const unsigned grid = unsigned((n_entries + cb::kPostThreads / 4 - 1) / (cb::kPostThreads / 4));
+  long long tiles = (n_entries + cb::kPostThreads / 4 - 1) / (cb::kPostThreads / 4);
+  if (ctas_per_sm > 0 && tiles > (long long)ctas_per_sm * cb::sm_count()) tiles = (long long)ctas_per_sm * cb::sm_count();
+  const unsigned grid = unsigned(tiles);
 #define CB_LAUNCH_POST(NMAX)                                                                                          \
   cb::posterior_window_kernel<NMAX><<<grid, cb::kPostThreads, 0, (cudaStream_t)stream>>>(                              \
       indptr, indices, data, cell_rows, n_cells, n_samples, logits_t, ldt, dec_bias, lse, chi_ambient, chi_bar, a_mu, \

@@ -319,14 +319,14 @@ class PosteriorWorkspace:
 @torch.no_grad()
 def posterior_window(csr: DeviceCSR, cell_rows, logits_t, dec_bias, lse, chi_ambient, chi_bar, a_mu, c_a, c_b, alpha, n_window,
                      entry_start, n_entries: int, barcode_all, gene_all, total_n_genes: int, ws: PosteriorWorkspace,
-                     entry_offset, log_thresh: float = -10.0, lambda_multiplier: float = 1.0):
+                     entry_offset, log_thresh: float = -10.0, lambda_multiplier: float = 1.0, ctas_per_sm: int = 0):
     """cb_posterior_noise_window for one chunk of cells, writing rows [entry_offset, entry_offset + entry_start[-1]) of
     ``ws``.  ``entry_offset``: host int or a device int64 scalar tensor; ``n_entries``: the chunk's stored counts or an
     upper bound of them (it only sizes the grid) -- both forms exist so that one captured graph can serve all chunks.
 
     logits_t [G, ldt]: transposed, cell-major decoder output (column b * S + s); lse [Bc * S]; a_mu, c_a, c_b [Bc * S];
     alpha [S]; n_window [Bc] int32; entry_start [Bc + 1] int64 (chunk-local prefix sums of the stored-count numbers);
-    barcode_all [Bc] / gene_all [G] int64 map to indices of the full count matrix."""
+    barcode_all [Bc] / gene_all [G] int64 map to indices of the full count matrix.  ``ctas_per_sm`` > 0 caps the grid."""
     _req_cuda(cell_rows, logits_t, lse, a_mu, c_a, c_b, alpha, n_window, entry_start, barcode_all, gene_all)
     Bc, G, S = int(cell_rows.numel()), csr.n_genes, int(alpha.numel())
     assert logits_t.stride(1) == 1 and logits_t.shape[0] >= G
@@ -341,7 +341,7 @@ def posterior_window(csr: DeviceCSR, cell_rows, logits_t, dec_bias, lse, chi_amb
         logits_t.stride(0), ptr(dec_bias), ptr(lse), ptr(chi_ambient), ptr(chi_bar), ptr(a_mu), ptr(c_a), ptr(c_b), ptr(alpha),
         ptr(n_window), ptr(entry_start), int(n_entries), ptr(barcode_all), ptr(gene_all), int(total_n_genes), ws.n_counts_max,
         float(log_thresh), float(lambda_multiplier), off_ptr, ws.logp.data_ptr() + 4 * ws.stride * o, ws.low.data_ptr() + 4 * o,
-        ws.keep.data_ptr() + 4 * o, ws.entry_m.data_ptr() + 8 * o, current_stream())
+        ws.keep.data_ptr() + 4 * o, ws.entry_m.data_ptr() + 8 * o, int(ctas_per_sm), current_stream())
 
 
 @torch.no_grad()

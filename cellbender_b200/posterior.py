@@ -55,6 +55,10 @@ class Posterior:
         self.posterior_batch_size = posterior_batch_size
         self.cells_per_chunk = cells_per_chunk
         self.use_cuda_graph = True  # replay one captured graph per full chunk of the posterior pass (device_posterior)
+        # pipelined pass: tile configuration of the decoder product (3 = 256 x 256 tiles, one CTA per SM) and residency cap
+        # of the window kernel that runs beside it (tools/posterior_profile.py --sweep measures the alternatives)
+        self.pipeline_tile_cfg = 3
+        self.pipeline_window_ctas = 2
         self._noise_count_posterior_coo: Optional[sp.coo_matrix] = None
         self._noise_count_posterior_kwargs: Optional[dict] = None
         self._noise_count_posterior_coo_offsets: Optional[Dict[int, int]] = None
@@ -254,69 +258,100 @@ class Posterior:
         chi_b[:G].copy_(m.avg_gene_expression)
         lin = m.decoder.out_linear
         cpc = self.cells_per_chunk
-        logits_t = self._logits_buffer(G, S, cpc)  # [G, cells * S]: transposed, cell-major
         n_sel = hi - lo
         total_genes = int(self.count_matrix_shape[1])
+        H = int(lin.weight.shape[1])
+        slots = self._pipeline_slots(G, S, cpc, H)
+        for sl in slots:
+            sl["estart"].zero_()  # a stage that runs ahead of / behind the chunk sequence sees an empty chunk
 
-        def chunk(rows, nwin, estart, barcodes_c, Bc, n_entries, out_offset, pos0):
-            """Everything of one chunk of Bc cells; no host synchronisation inside."""
-            _, enc = self._encode(rows)
+        # One chunk = three stages that hand over through the static buffers of a slot:
+        #   stage 0  encoders + S latent draws + decoder hidden layer (a few hundred small launches, latency-bound)
+        #   stage 1  ONE decoder GEMM for all samples of the chunk, output transposed and cell-major:
+        #            logits_t[g, b * S + s] = W[g, :] . h[b * S + s, :] (tensor-bound), then the column logsumexp of
+        #            logits_t + bias (HBM-bound)
+        #   stage 2  noise-count window over the chunk's stored counts                                   (XU-bound)
+        def stage0(sl, Bc, pos0):
+            _, enc = self._encode(sl["rows"][:Bc])
             noise = None if noise_fn is None else noise_fn(slice(pos0, pos0 + Bc), enc)
             z, a_mu, c_a, c_b, alpha = self.sample_rate_coefficients(enc, S, y_map=y_map, noise=noise)
             h = m.decoder.hidden(z.reshape(Bc * S, -1))
-            # ONE decoder GEMM for all samples of the chunk, output transposed: logits_t[g, b * S + s] = W[g, :] . h[b * S + s, :]
-            ops.gemm_tf32(lin.weight, h.contiguous(), G, Bc * S, lin.weight.shape[1], out=logits_t[:, : Bc * S], split_k=1)
-            lse = ops.col_logsumexp(logits_t, G, Bc * S, row_add=lin.bias)
+            sl["h"][: Bc * S].copy_(h)
+            sl["a_mu"][: Bc * S].copy_(a_mu.reshape(-1)), sl["c_a"][: Bc * S].copy_(c_a.reshape(-1))
+            sl["c_b"][: Bc * S].copy_(c_b.reshape(-1)), sl["alpha"].copy_(alpha)
+
+        def stage1(sl, Bc, tile_cfg=0):
+            ops.gemm_tf32(lin.weight, sl["h"][: Bc * S], G, Bc * S, H, out=sl["logits"][:, : Bc * S], split_k=1, tile_cfg=tile_cfg)
+            ops.col_logsumexp(sl["logits"], G, Bc * S, row_add=lin.bias, out=sl["lse"][: Bc * S])
+
+        def stage2(sl, Bc, n_entries, ctas_per_sm=0):
             ops.posterior_window(
-                csr, rows, logits_t, lin.bias, lse, chi_a, chi_b, a_mu.reshape(-1).contiguous(), c_a.reshape(-1).contiguous(),
-                c_b.reshape(-1).contiguous(), alpha.contiguous(), nwin, estart, n_entries, barcodes_c, gene_all, total_genes, ws,
-                out_offset, log_thresh=smallest_log_probability, lambda_multiplier=lambda_multiplier)
+                csr, sl["rows"][:Bc], sl["logits"], lin.bias, sl["lse"], chi_a, chi_b, sl["a_mu"], sl["c_a"], sl["c_b"], sl["alpha"],
+                sl["nwin"][:Bc], sl["estart"][: Bc + 1], n_entries, sl["barcode"][:Bc], gene_all, total_genes, ws, sl["offset"],
+                log_thresh=smallest_log_probability, lambda_multiplier=lambda_multiplier, ctas_per_sm=ctas_per_sm)
+
+        def load(sl, a0, a1):
+            """Static operands of the chunk at positions [a0, a1) of the selected cell list."""
+            n = a1 - a0
+            sl["rows"][:n].copy_(rows_dev[a0:a1]), sl["nwin"][:n].copy_(n_window[a0:a1]), sl["barcode"][:n].copy_(barcode_dev[a0:a1])
+            torch.sub(prefix_dev[a0:a1 + 1], prefix_dev[a0], out=sl["estart"][: n + 1])
+            sl["offset"].copy_(prefix_dev[a0:a0 + 1])
 
         n_full = n_sel // cpc
-        # Full chunks replay ONE captured CUDA graph (a chunk is ~250 small launches -- encoders, sampling, decoder hidden
-        # layer -- whose launch latency exceeded the GPU time of the chunk: r02j timeline, kernels busy 59 % of the span);
-        # the chunk's varying operands live in static device buffers, the grid of the window kernel is sized for the
-        # largest chunk and the output offset is a device scalar.  Seeded / injected-noise passes (tests, sharded-equals-
-        # unsharded checks) and the ragged last chunk run eagerly.
-        use_graph = self.use_cuda_graph and seed is None and noise_fn is None and n_full >= 2
+        # Full chunks run as a three-deep software pipeline: iteration t replays ONE captured CUDA graph whose three
+        # parallel branches are stage 0 of chunk t, stage 1 of chunk t - 1 and stage 2 of chunk t - 2 (slot = chunk mod 3,
+        # so there are three graph variants): the latency-bound small launches hide under the two bulk kernels of the
+        # neighbouring chunks.  The decoder product and the window kernel themselves contend for issue slots and gain
+        # little from running side by side (r02ag timeline: 1.39 ms together, 0.66 + 0.70 ms alone); a fourth stage for the
+        # logsumexp measured slower (36.2 vs 34.8 ms per pass).  Two extra iterations drain the pipeline; the stages that
+        # have no chunk there see an empty one.  Seeded / injected-noise passes (tests, sharded-equals-unsharded checks) and
+        # the ragged last chunk run the stages eagerly, one after the other.
+        NS = self.N_PIPELINE_SLOTS
+        use_graph = self.use_cuda_graph and seed is None and noise_fn is None and n_full >= 3
         if use_graph:
             chunk_entries = np.array([int(prefix[(i + 1) * cpc] - prefix[i * cpc]) for i in range(n_full)])
             key = (S, n_counts_max, float(smallest_log_probability), float(lambda_multiplier), bool(y_map), cpc)
             cached = getattr(self, "_chunk_graph", None)
-            if (cached is not None and cached["key"] == key and cached["ws"] is ws and cached["logits_t"] is logits_t
+            if not (cached is not None and cached["key"] == key and cached["ws"] is ws and cached["slots"] is slots
                     and cached["max_entries"] >= int(chunk_entries.max())):
-                st, graph, max_entries = cached["st"], cached["graph"], cached["max_entries"]
-            else:
-                cached = None
-                max_entries = int(chunk_entries.max() * 1.25) + 1024  # head-room: later passes reuse the captured graph
-                st = {"rows": torch.zeros(cpc, dtype=torch.int64, device=self.device),
-                      "nwin": torch.zeros(cpc, dtype=torch.int32, device=self.device),
-                      "estart": torch.zeros(cpc + 1, dtype=torch.int64, device=self.device),
-                      "barcode": torch.zeros(cpc, dtype=torch.int64, device=self.device),
-                      "offset": torch.zeros(1, dtype=torch.int64, device=self.device)}
+                max_entries = int(chunk_entries.max() * 1.25) + 1024  # head-room: later passes reuse the captured graphs
+                # the small launches of stage 0 outrank the two bulk kernels (priorities are recorded into the graph's kernel
+                # nodes): at equal priority a small kernel waits until every pending CTA of a large grid launched before it
+                # has been placed, and the stages run one after the other (r02ae timeline: no overlap at all)
+                # The window kernel (XU-bound, no shared memory) is capped at two CTAs per SM and outranks the decoder product
+                # (tensor-bound, one 256 x 256-tile CTA per SM): both stay resident side by side for their whole duration.
+                streams = [torch.cuda.Stream(priority=0), torch.cuda.Stream(priority=-1)]
+                capture_stream = torch.cuda.Stream(priority=-1)
 
-            def load(i):
-                a0, a1 = i * cpc, (i + 1) * cpc
-                st["rows"].copy_(rows_dev[a0:a1]), st["nwin"].copy_(n_window[a0:a1]), st["barcode"].copy_(barcode_dev[a0:a1])
-                torch.sub(prefix_dev[a0:a1 + 1], prefix_dev[a0], out=st["estart"])
-                st["offset"].copy_(prefix_dev[a0:a0 + 1])
+                def iteration(v):
+                    main = torch.cuda.current_stream()
+                    for st_ in streams:
+                        st_.wait_stream(main)
+                    stage0(slots[v], cpc, 0)
+                    with torch.cuda.stream(streams[0]):
+                        stage1(slots[(v - 1) % NS], cpc, tile_cfg=self.pipeline_tile_cfg)
+                    with torch.cuda.stream(streams[1]):
+                        stage2(slots[(v - 2) % NS], cpc, max_entries, ctas_per_sm=self.pipeline_window_ctas)
+                    for st_ in streams:
+                        main.wait_stream(st_)
 
-            if cached is None:
-                body = lambda: chunk(st["rows"], st["nwin"], st["estart"], st["barcode"], cpc, max_entries, st["offset"], 0)
-                load(0)
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    body()  # warm-up outside capture (allocator, lazy initialisation); its outputs are overwritten below
-                torch.cuda.current_stream().wait_stream(side)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    body()
-                self._chunk_graph = {"key": key, "st": st, "graph": graph, "max_entries": max_entries, "ws": ws,
-                                     "logits_t": logits_t}
-            for i in range(n_full):
-                load(i)
-                graph.replay()
+                graphs = []
+                for v in range(NS):
+                    capture_stream.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(capture_stream):
+                        iteration(v)  # warm-up outside capture (allocator, lazy initialisation) on empty chunks
+                    torch.cuda.current_stream().wait_stream(capture_stream)
+                    g_ = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_, stream=capture_stream):
+                        iteration(v)
+                    graphs.append(g_)
+                cached = self._chunk_graph = {"key": key, "graphs": graphs, "max_entries": max_entries, "ws": ws, "slots": slots,
+                                              "streams": streams}
+            graphs = cached["graphs"]
+            for t in range(n_full + NS - 1):
+                if t < n_full:
+                    load(slots[t % NS], t * cpc, (t + 1) * cpc)
+                graphs[t % NS].replay()
             first_eager = n_full * cpc
         else:
             first_eager = 0
@@ -324,8 +359,11 @@ class Posterior:
             stop = min(n_sel, start + cpc)
             if seed is not None:
                 torch.manual_seed(int(seed) + lo + start)
-            chunk(rows_dev[start:stop], n_window[start:stop].contiguous(), (prefix_dev[start:stop + 1] - prefix_dev[start]).contiguous(),
-                  barcode_dev[start:stop].contiguous(), stop - start, int(prefix[stop] - prefix[start]), int(prefix[start]), lo + start)
+            sl = slots[0]
+            load(sl, start, stop)
+            stage0(sl, stop - start, lo + start)
+            stage1(sl, stop - start)
+            stage2(sl, stop - start, int(prefix[stop] - prefix[start]))
         post = DevicePosteriorCOO(*ops.posterior_compact(ws, smallest_log_probability), n_cols=n_counts_max)
         if cell_subset is None:
             self._device_posterior = post
@@ -340,12 +378,26 @@ class Posterior:
         ws.n_entries = int(n_entries)
         return ws
 
-    def _logits_buffer(self, G: int, S: int, cpc: int) -> torch.Tensor:
-        need = (G, ops.row_pitch(S * cpc))
-        buf = getattr(self, "_logits_t", None)
-        if buf is None or tuple(buf.shape) != need:
-            self._logits_t = buf = torch.empty(need, device=self.device)
-        return buf
+    N_PIPELINE_SLOTS = 3  # stages of a chunk = depth of the software pipeline of ``device_posterior``
+
+    def _pipeline_slots(self, G: int, S: int, cpc: int, H: int):
+        """``N_PIPELINE_SLOTS`` sets of static buffers through which the stages of a chunk hand over (see ``device_posterior``); kept
+        between passes: the captured graphs refer to them by address.  logits: [G, cells * S] transposed, cell-major
+        (1.37 GB per slot at the PBMC8k shape)."""
+        key = (G, S, cpc, H)
+        if getattr(self, "_slots_key", None) != key:
+            dev = self.device
+            f = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+            self._slots = [{"logits": torch.empty((G, ops.row_pitch(S * cpc)), device=dev), "lse": f(S * cpc), "h": f(cpc * S, H),
+                            "a_mu": f(cpc * S), "c_a": f(cpc * S), "c_b": f(cpc * S), "alpha": f(S),
+                            "rows": torch.zeros(cpc, dtype=torch.int64, device=dev),
+                            "nwin": torch.zeros(cpc, dtype=torch.int32, device=dev),
+                            "estart": torch.zeros(cpc + 1, dtype=torch.int64, device=dev),
+                            "barcode": torch.zeros(cpc, dtype=torch.int64, device=dev),
+                            "offset": torch.zeros(1, dtype=torch.int64, device=dev)} for _ in range(self.N_PIPELINE_SLOTS)]
+            self._slots_key = key
+            self._chunk_graph = None
+        return self._slots
 
     def _host_indptr(self) -> np.ndarray:
         if getattr(self, "_indptr_host", None) is None:

@@ -282,7 +282,9 @@ int cb_clipped_adam_nvls_ex(float* p, float* m, float* v, long long n, const flo
  * outputs, one row per stored count in (cell, gene) order:
  *   logp_out[n_entries, stride] (stride = cb_posterior_window_stride()), low_out, keep_cnt, entry_m[n_entries]
  * cb_posterior_offset_flags: flag[i] = keep_cnt[i] > 0 && low[i] != 0 (entries that carry a noise-count offset).
- * cb_posterior_compact: thresholded COO triplets + (m, offset) pairs from exclusive scans of keep_cnt / flag.      */
+ * cb_posterior_compact: thresholded COO triplets + (m, offset) pairs from exclusive scans of keep_cnt / flag.       *   ctas_per_sm            0: one CTA per 64 stored counts; k > 0: at most k CTAs per SM, tiles strided over them (the
+ *                          kernel then shares the GPU with the decoder product of the next chunk)
+ */
 int cb_posterior_window_stride(int n_counts_max);
 int cb_posterior_noise_window(const long long* indptr, const int* indices, const float* data, const long long* cell_rows,
                               int n_cells, int n_genes, int n_samples, const float* logits_t, long long ldt,
@@ -291,7 +293,8 @@ int cb_posterior_noise_window(const long long* indptr, const int* indices, const
                               const int* n_window, const long long* entry_start, long long max_entries,
                               const long long* barcode_all, const long long* gene_all, long long total_n_genes,
                               int n_counts_max, float log_thresh, float lambda_multiplier, const long long* out_offset,
-                              float* logp_out, int* low_out, int* keep_cnt, long long* entry_m, void* stream);
+                              float* logp_out, int* low_out, int* keep_cnt, long long* entry_m, int ctas_per_sm,
+                              void* stream);
 int cb_posterior_offset_flags(long long n_entries, const int* keep_cnt, const int* low, int* flag, void* stream);
 /* out[c] = log sum_r exp(in[r, c] + row_add[r]) over an [n_rows, ld] matrix (row_add may be NULL): the softmax
  * denominators of Decoder.forward (vae/decoder.py:46-47) for the transposed logits of a posterior chunk.

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--workload", default="pbmc8k")
     ap.add_argument("--estimators", action="store_true")
     ap.add_argument("--timeline", default=None, help="write a per-kernel timeline of one pass (torch.profiler / CUPTI)")
+    ap.add_argument("--sweep", action="store_true", help="time the pipelined pass for several (tile_cfg, window CTAs per SM)")
     a = ap.parse_args()
     import torch
 
@@ -48,6 +49,19 @@ def main():
         dt = time.perf_counter() - t0
         print(f"posterior: {n_cells} cells, {int(dp_.m.numel())} COO entries, {dt * 1e3:.2f} ms, {n_cells / dt:.0f} droplets/s",
               flush=True)
+    if a.sweep:
+        for cfg, ctas in ((0, 0), (3, 0), (3, 1), (3, 2), (3, 3), (0, 2), (1, 2), (3, 4)):
+            post.pipeline_tile_cfg, post.pipeline_window_ctas = cfg, ctas
+            post._chunk_graph = None
+            post.device_posterior()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                post.device_posterior()
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            print(f"tile_cfg {cfg}, window CTAs/SM {ctas}: {1e3 * min(ts):.2f} ms, {n_cells / min(ts):.0f} droplets/s", flush=True)
     if a.timeline:
         import collections
         import json
@@ -73,6 +87,16 @@ def main():
                  f"({100 * busy / (t1 - t0):.0f} % of the span: the rest is launch gaps / host)", "# total_us  launches  kernel"]
         for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
             lines.append(f"{t:10.1f} {c:6d}  {n}")
+        # raw per-stream timeline of the middle of the pass (two pipeline iterations): what overlaps what
+        big = [e for e in ev if "posterior_window" in e["name"]]
+        if len(big) >= 8:
+            w0, w1 = big[len(big) // 2]["ts"], big[len(big) // 2 + 2]["ts"]
+            streams = sorted({e["args"].get("stream", 0) for e in ev})
+            lines.append("# ---- two iterations from the middle of the pass: start_us  dur_us  stream  kernel (>= 8 us only)")
+            for e in ev:
+                if w0 <= e["ts"] < w1 and e["dur"] >= 8:
+                    lines.append(f"{e['ts'] - w0:9.1f} {e['dur']:8.1f}  s{streams.index(e['args'].get('stream', 0))}  "
+                                 f"{e['name'].replace('void ', '').split('(')[0][:80]}")
         open(a.timeline, "w").write("\n".join(lines) + "\n")
         print("\n".join(lines[:12]))
     if a.estimators:
