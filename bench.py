@@ -631,6 +631,28 @@ def run_b200(args):
                 "stored_counts_out": int(restored.nnz), "device_combine_ms": comb_ms, "device_csr_to_csc_ms": tr_ms,
                 "device_combine_frac_of_hbm_peak": comb_bytes / comb_ms / 1e6 / peaks["hbm_gbs"],
                 "note": "host scipy in -> device combine -> host scipy CSC out, transfers included; device_* = operands resident"}
+        if world > 1:
+            # MCKP with the gene-keyed exchange (BASELINE config 5: posterior + MCKP barcode-sharded): the pieces are re-keyed by
+            # gene with one all-to-all, every rank solves its genes, the per-(cell, gene) results are gathered
+            n_genes_total = int(post.index_converter.total_n_genes)
+            tgt_t = torch.zeros(n_genes_total, dtype=torch.float64, device=dev)
+            if rank == 0:
+                tgt_t.copy_(torch.as_tensor(tgt))
+            dist.broadcast(tgt_t, src=0)
+            tgt_all = tgt_t.cpu().numpy()
+            dp.mckp_gene_sharded(piece, tgt_all, n_genes_total, world, rank)  # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            seg_m, noise_seg = dp.mckp_gene_sharded(piece, tgt_all, n_genes_total, world, rank)
+            torch.cuda.synchronize()
+            tt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                posterior["estimation"]["mckp_gene_sharded_seconds"] = float(tt[0])
+                posterior["estimation"]["mckp_gene_sharded_removed"] = int(noise_seg.sum())
+                posterior["estimation"]["mckp_gene_sharded_note"] = (
+                    "all-to-all of the COO pieces by gene owner + per-rank knapsacks + gather of the per-(cell, gene) noise counts, "
+                    "results left on the device; must remove exactly noise_counts_removed")
         model.train()
 
     # ---- the whole job, measured (optional): 150 epochs through run_training + posterior + MCKP + output assembly ----

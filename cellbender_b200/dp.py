@@ -26,8 +26,9 @@ criteria is averaged over ranks; ``FlatClippedAdam.state_dict()`` gathers the sh
 
 Posterior / estimation: ``shard_cells`` splits the barcode-sorted cell list into contiguous ranges; ranks compute their
 COO pieces independently (``Posterior.device_posterior(cell_subset=...)``) and ``gather_posterior`` concatenates them in
-rank order, which IS the (m, c)-sorted whole.  MCKP needs all cells of a gene, so it runs on the gathered COO (one
-gene-keyed exchange = the gather itself).
+rank order, which IS the (m, c)-sorted whole.  MCKP needs all cells of a gene: ``mckp_gene_sharded`` re-keys the pieces by
+gene with ONE all-to-all (rank r receives every entry of the genes g with g mod R == r, still (m, c)-sorted because the
+pieces arrive in barcode order), solves its genes' knapsacks and the per-(cell, gene) results are gathered.
 """
 from typing import List, Optional
 
@@ -359,6 +360,46 @@ def all_gather_varlen(t: torch.Tensor, world_size: int) -> torch.Tensor:
     outs = [torch.zeros_like(buf) for _ in range(world_size)]
     dist.all_gather(outs, buf)
     return torch.cat([o[: int(s)] for o, s in zip(outs, sizes)])
+
+
+def _all_to_all_varlen(t: torch.Tensor, send_counts: List[int], recv_counts: List[int]) -> torch.Tensor:
+    out = torch.empty(int(sum(recv_counts)), dtype=t.dtype, device=t.device)
+    dist.all_to_all_single(out, t.contiguous(), output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts))
+    return out
+
+
+@torch.no_grad()
+def mckp_gene_sharded(piece, targets, n_genes: int, world_size: int, rank: int):
+    """MultipleChoiceKnapsack over barcode-sharded posterior pieces: the knapsack of a gene needs the
+    entries of ALL cells, so the pieces are re-keyed by gene with one all-to-all -- owner of gene g is rank g mod R
+    (interleaved: highly and lowly expressed genes spread evenly) -- each rank runs ``estimation.mckp_device`` on its
+    genes, and the per-(cell, gene) noise counts are gathered and merged by m.  ``piece``: this rank's DevicePosteriorCOO
+    (cells of a contiguous barcode range); ``targets``: per-gene noise targets [n_genes] (every rank passes the same).
+    Returns (seg_m int64, noise int32) of ALL segments, sorted by m, on every rank -- what ``mckp_device`` returns for the
+    gathered COO, bit for bit (tests/test_multi_gpu.py)."""
+    from .estimation import DevicePosteriorCOO, mckp_device
+
+    if world_size <= 1:
+        return mckp_device(piece, targets, n_genes)
+    dev = piece.m.device
+
+    def route(keys_m, *arrays):
+        owner = (keys_m % n_genes) % world_size
+        order = torch.argsort(owner, stable=True)  # stable: every destination keeps the (m, c) order of the piece
+        send = torch.bincount(owner, minlength=world_size)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send)
+        send_l, recv_l = send.cpu().tolist(), recv.cpu().tolist()
+        return [_all_to_all_varlen(a[order], send_l, recv_l) for a in (keys_m,) + arrays]
+
+    m, c, lp = route(piece.m, piece.c, piece.log_prob)
+    off_m, off_v = route(piece.off_m, piece.off_v)
+    # pieces arrive in source-rank order = ascending barcode ranges: the concatenation is sorted by (m, c) already
+    mine = DevicePosteriorCOO(m, c, lp, off_m, off_v, piece.n_cols)
+    seg_m, noise = mckp_device(mine, targets, n_genes)
+    seg_all, noise_all = all_gather_varlen(seg_m, world_size), all_gather_varlen(noise, world_size)
+    order = torch.argsort(seg_all)
+    return seg_all[order].contiguous(), noise_all[order].contiguous()
 
 
 def gather_posterior(piece, world_size: int):

@@ -69,11 +69,20 @@ def _worker(rank, world, port, q, mode="sharded", posterior=True):
         post._latents = {"p": np.concatenate([np.ones(n_cells), np.zeros(ds.analyzed_barcode_inds.size - n_cells)])}
         piece = post.device_posterior(cell_subset=dp.shard_cells(n_cells, rank, world, align=32), seed=7, n_samples=4)
         full = dp.gather_posterior(piece, world)
+        # MCKP with the gene-keyed exchange (all-to-all of the pieces by gene owner) vs MCKP on the gathered COO
+        from cellbender_b200.estimation import mckp_device
+
+        n_genes_total = post.index_converter.total_n_genes
+        targets = np.random.default_rng(11).uniform(0.0, 40.0, size=n_genes_total)
+        seg_m, noise = dp.mckp_gene_sharded(piece, targets, n_genes_total, world, rank)
+        ref_m, ref_noise = mckp_device(full, targets, n_genes_total)
+        ok_mckp = torch.equal(seg_m, ref_m) and torch.equal(noise, ref_noise) and int(noise.sum()) > 0
         ok_post = None
         if rank == 0:
             ref = post.device_posterior(seed=7, n_samples=4)
             ok_post = (torch.equal(ref.m, full.m) and torch.equal(ref.c, full.c) and torch.equal(ref.log_prob, full.log_prob)
                        and torch.equal(ref.off_m, full.off_m) and torch.equal(ref.off_v, full.off_v) and ref.m.numel() > 1000)
+        ok_post = ok_mckp if ok_post is None else (ok_post and ok_mckp)
         q.put((rank, same, moved, ok_post, len(svi._graphs)))
         svi._graphs.clear()  # graphs that captured NCCL collectives must be gone before the process group is destroyed
         torch.cuda.synchronize()
@@ -96,7 +105,7 @@ def test_data_parallel_replicas_stay_identical_and_sharded_posterior_matches():
         assert same, "parameter replicas diverged"
         assert moved > 0
         assert n_graphs >= 1  # forward + backward ran as CUDA-graph replays around the eager all-reduce
-    assert res[0][3] is True
+    assert all(r[3] is True for r in res)  # sharded posterior == unsharded (rank 0), gene-sharded MCKP == gathered MCKP
 
 
 def _train(world, mode):
