@@ -31,9 +31,9 @@ sys.path.insert(0, ROOT)
 METRIC = "train_s_per_epoch"
 UNIT = "s/epoch"
 WORKLOAD = "pbmc8k"
-# dram bytes of one full-buffer clipped_adam_kernel launch at the PBMC8k shape from the committed ncu --set full capture
-# (profiles/r01_step_kernels_ncu_summary.txt: 1.111406 GB read + 781.773 MB written)
-ADAM_NCU_DRAM_BYTES = 1.111406e9 + 781.773312e6
+# dram bytes of the clipped_adam_kernel launches of one step at the PBMC8k shape from the committed ncu --set full capture
+# (profiles/r02_adam_ncu.txt: per large block 275.0 MB read + 151.6 MB written, tail 12.6 MB; 4 blocks + tail)
+ADAM_NCU_DRAM_BYTES = 4 * (275.0e6 + 151.6e6) + 12.6e6
 
 
 def parse_args():
@@ -720,8 +720,9 @@ def run_b200(args):
         "roofline": None if adam is None else {
             "bound": "hbm", "kernel": "clipped_adam_kernel", "achieved": adam["achieved_GBps"], "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": adam["frac_of_hbm_peak"], "traffic": ADAM_NCU_DRAM_BYTES, "peak_source": peak_src,
-            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of clipped_adam_kernel, ncu --set full, "
-                              "profiles/r01_step_kernels_ncu_summary.txt",
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the step's clipped_adam_kernel launches, ncu --set "
+                              "full, profiles/r02_adam_ncu.txt (0.88 x algorithmic: the last dirty lines of a launch leave L2 "
+                              "after it ends; reads = algorithmic, nothing re-read)",
             "algorithmic_bytes_per_launch": adam["algorithmic_bytes"], "ms_per_launch": adam["ms"]},
         "roofline_step": {"bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"]},

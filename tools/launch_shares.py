@@ -1,5 +1,5 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: kernel shares of one training step
-(delimited by two consecutive clipped_adam_kernel launches)."""
+(delimited by two consecutive gather_rows_kernel launches: the first kernel of every step)."""
 import collections
 import csv
 import re
@@ -11,14 +11,14 @@ def main(path, out=None, title=""):
         lines = [l for l in f if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
     names = [r["Kernel Name"] for r in rows]
-    idx = [i for i, n in enumerate(names) if "clipped_adam" in n]
+    idx = [i for i, n in enumerate(names) if "gather_rows_kernel" in n]
 
     def val(r):
         v = float(r["Metric Value"].replace(",", ""))
         u = r["Metric Unit"]
         return v / 1e3 if u.startswith("n") else (v if u.startswith("u") else v * 1e3)
 
-    a, b = idx[-2] + 2, idx[-1] + 2
+    a, b = idx[-2], idx[-1]
     seg = rows[a:b]
     tot = sum(val(r) for r in seg)
     agg = collections.defaultdict(lambda: [0, 0.0])
