@@ -319,15 +319,24 @@ def kernel_table(model, opt, svi, batch, peaks, dev):
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def timed(fn, reps=7):
+    N_SETS, LAUNCHES = 3, 12
+
+    def timed(fn, reps=5, launches=None):
+        """Milliseconds per launch: LAUNCHES back-to-back launches between two CUDA events on the launching stream (a single
+        30 us launch between events would be charged several microseconds of launch latency), median of ``reps`` such
+        measurements.  ``fn(i)`` uses operand set i % N_SETS: three rotating copies of every large operand (> 300 MB per
+        rotation) keep a launch's operands out of the 126 MB L2; the L2 is also flushed before each measurement."""
         ts = []
+        n = launches or LAUNCHES
+        fn(0)
         for _ in range(reps):
-            flush.zero_()  # L2 flush between timed launches (buffer > 126 MB L2)
+            flush.zero_()  # L2 flush (buffer > 126 MB L2)
             e0.record()
-            fn()
+            for i in range(n):
+                fn(i)
             e1.record()
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
+            ts.append(e0.elapsed_time(e1) / n)
         return float(np.median(ts))
 
     def row(ms, nbytes, note=""):
@@ -339,26 +348,35 @@ def kernel_table(model, opt, svi, batch, peaks, dev):
     H = model.decoder.out_linear.weight.shape[1]
     # ---- the optimizer sweep over the whole flat buffer
     step_save = opt.step_count.clone()
-    ms = timed(lambda: ops.clipped_adam_step(opt.flat_p, opt.flat_g, opt.flat_m, opt.flat_v, opt.lr_table, opt.beta1_table,
-                                             opt.step_count, grad_scale=0.0, step_table=opt.step_table), reps=9)
+    ms = timed(lambda i: ops.clipped_adam_step(opt.flat_p, opt.flat_g, opt.flat_m, opt.flat_v, opt.lr_table, opt.beta1_table,
+                                               opt.step_count, grad_scale=0.0, step_table=opt.step_table))
     opt.step_count.copy_(step_save)
     out["clipped_adam_kernel"] = row(ms, 28.0 * opt.n, "read p, g, m, v; write p, m, v (fp32); zero gradient scale")
     # ---- the large contractions (PBMC8k: algorithmic bytes = weight matrix + the [B, G] activation / gradient matrix)
     g = torch.Generator(device=dev).manual_seed(0)
     rn = lambda *s: torch.randn(*s, device=dev, generator=g)
     ldG = ops.row_pitch(G + 32)
-    x, W, W2 = rn(B, ldG), rn(H, ldG), rn(H, ldG)
-    Wd, h, dy, dy2, dl, bias = rn(G, H), rn(B, H), rn(B, H), rn(B, H), rn(B, ldG), rn(G)
-    o_bh, o_bg = ops.alloc_rows(B, H, dev), ops.alloc_rows(B, G, dev)
-    dW, dWd = torch.zeros(H, ldG, device=dev), torch.zeros(G, H, device=dev)
+    sets = []
+    for _ in range(N_SETS):
+        sets.append(dict(x=rn(B, ldG), W=rn(H, ldG), W2=rn(H, ldG), Wd=rn(G, H), h=rn(B, H), dy=rn(B, H), dy2=rn(B, H), dl=rn(B, ldG),
+                         bias=rn(G), o_bh=ops.alloc_rows(B, H, dev), o_bg=ops.alloc_rows(B, G, dev),
+                         dW=torch.zeros(H, ldG, device=dev), dWd=torch.zeros(G, H, device=dev)))
+    S_ = lambda i: sets[i % N_SETS]
     wb = 4.0 * G * H + 4.0 * B * G
-    out["gemm_encoder_forward"] = row(timed(lambda: ops.gemm_tf32(x, W[:, 32:32 + G], B, H, G, out=o_bh[:, :H])), wb, "split-K + reduce")
-    out["gemm_decoder_forward"] = row(timed(lambda: ops.gemm_tf32(h, Wd, B, G, H, out=o_bg[:, :G], bias=bias, split_k=1)), wb)
-    out["gemm_dh"] = row(timed(lambda: ops.gemm_tf32(dl, Wd, B, H, G, b_mn=True, out=o_bh[:, :H])), wb, "split-K + reduce")
-    out["gemm_dW_encoder"] = row(timed(lambda: ops.gemm_tf32(dy, x, H, G, B, a_mn=True, b_mn=True, out=dW[:, 32:32 + G], split_k=1)), wb)
-    out["gemm_dW_decoder"] = row(timed(lambda: ops.gemm_tf32(dl, h, G, H, B, a_mn=True, b_mn=True, out=dWd, split_k=1)), wb)
-    out["gemm_dX_pair"] = row(timed(lambda: ops.gemm_tf32(dy, W[:, 32:32 + G], B, G, H, b_mn=True, out=o_bg[:, :G], split_k=1, a2=dy2,
-                                                          b2=W2[:, 32:32 + G], K2=H)), 8.0 * G * H + 4.0 * B * G)
+    out["gemm_encoder_forward"] = row(timed(lambda i: ops.gemm_tf32(S_(i)["x"], S_(i)["W"][:, 32:32 + G], B, H, G, out=S_(i)["o_bh"][:, :H])),
+                                      wb, "split-K + reduce")
+    out["gemm_decoder_forward"] = row(timed(lambda i: ops.gemm_tf32(S_(i)["h"], S_(i)["Wd"], B, G, H, out=S_(i)["o_bg"][:, :G],
+                                                                    bias=S_(i)["bias"], split_k=1)), wb)
+    out["gemm_dh"] = row(timed(lambda i: ops.gemm_tf32(S_(i)["dl"], S_(i)["Wd"], B, H, G, b_mn=True, out=S_(i)["o_bh"][:, :H])), wb,
+                         "split-K + reduce")
+    out["gemm_dW_encoder"] = row(timed(lambda i: ops.gemm_tf32(S_(i)["dy"], S_(i)["x"], H, G, B, a_mn=True, b_mn=True,
+                                                               out=S_(i)["dW"][:, 32:32 + G], split_k=1)), wb)
+    out["gemm_dW_decoder"] = row(timed(lambda i: ops.gemm_tf32(S_(i)["dl"], S_(i)["h"], G, H, B, a_mn=True, b_mn=True, out=S_(i)["dWd"],
+                                                               split_k=1)), wb)
+    out["gemm_dX_pair"] = row(timed(lambda i: ops.gemm_tf32(S_(i)["dy"], S_(i)["W"][:, 32:32 + G], B, G, H, b_mn=True,
+                                                            out=S_(i)["o_bg"][:, :G], split_k=1, a2=S_(i)["dy2"],
+                                                            b2=S_(i)["W2"][:, 32:32 + G], K2=H)), 8.0 * G * H + 4.0 * B * G)
+    del sets
     # ---- the fused observation kernel on one minibatch
     inp = batch.encoder_inputs(svi._ambient_unit_vector())
     with torch.no_grad():
@@ -368,7 +386,7 @@ def kernel_table(model, opt, svi, batch, peaks, dev):
     wts, al = -torch.rand((B, 3), device=dev), torch.tensor([5.0], device=dev)
     oo = bufs_["obs_out"]
     ptr = _cabi.ptr
-    ms = timed(lambda: lib.call(
+    ms = timed(lambda i: lib.call(
         "cb_elbo_obs_fwd_bwd", ptr(csr_.indptr), ptr(csr_.indices), ptr(csr_.data), ptr(rows_), B, G, ptr(bufs_["logits"]),
         bufs_["logits"].stride(0), ptr(bufs_["chi_a"]), ptr(bufs_["chi_b"]), ptr(coef), ptr(al), ptr(wts), ptr(oo["sums"]),
         ptr(oo["dlogits"]), ptr(oo["qamb"]), bufs_["logits"].stride(0), ptr(oo["lse"]), ptr(oo["nan_flag"]), _cabi.current_stream()))
@@ -377,13 +395,16 @@ def kernel_table(model, opt, svi, batch, peaks, dev):
     model.nan_flag.zero_()
     # ---- gather + batchnorm0
     unit = svi._ambient_unit_vector()
-    out["gather_rows_kernel"] = row(timed(lambda: batch.encoder_inputs(unit)), 8.0 * B * G, "write norm + lognorm rows")
+    # (one operand set: single launches behind an L2 flush, launch latency included)
+    out["gather_rows_kernel"] = row(timed(lambda i: batch.encoder_inputs(unit), reps=7, launches=1), 8.0 * B * G,
+                                    "write norm + lognorm rows; single launch incl. launch latency")
     enc_o = model.encoder["other"]
     keep = torch.full((B,), 2.0, device=dev)
     from cellbender_b200 import gemm
 
     with torch.no_grad():
-        out["bn0_forward_kernel"] = row(timed(lambda: gemm.bn0_dropout(inp.x_lognorm, enc_o.batchnorm0, keep, True, G)), 8.0 * B * G)
+        out["bn0_forward_kernel"] = row(timed(lambda i: gemm.bn0_dropout(inp.x_lognorm, enc_o.batchnorm0, keep, True, G), reps=7,
+                                              launches=1), 8.0 * B * G, "single launch incl. launch latency")
     return out
 
 
