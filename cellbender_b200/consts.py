@@ -26,3 +26,7 @@ REG_LOGIT_SOFT_SCALE = 1.0  # consts.py:84
 PROB_POSTERIOR_BATCH_SIZE = 128  # consts.py:103
 MAX_BATCH_SIZE = 256  # consts.py:112
 SMALLEST_ALLOWED_BATCH = 4  # consts.py:113
+
+USE_EXACT_LOG_PROB = False  # consts.py:68
+# max_poisson of NegativeBinomialPoissonConv when USE_EXACT_LOG_PROB is set (reference model.py:355)
+NBPC_EXACT_MAX_POISSON = 100

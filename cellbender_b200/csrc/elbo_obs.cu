@@ -41,15 +41,18 @@ struct RowCoef {
   float alpha;
 };
 
-// contributions of one (b, g) element; adds into acc[], returns p = dL1/dmu1 * chi and q (dchi_ambient contribution)
-__device__ __forceinline__ void obs_element(float v, float chi, float ca, float cb_, const RowCoef& c, float (&acc)[kNumSums],
-                                            float& p_out, float& q_out) {
+// contributions of one (b, g) element; adds into acc[], returns p = dL1/dmu1 * chi and q (dchi_ambient contribution).
+// MAXP < 0: NegativeBinomialPoissonConvApprox (the reference's default); MAXP >= 0: the exact convolution
+// NegativeBinomialPoissonConv(max_poisson = MAXP) (model.py:336-357 with consts.USE_EXACT_LOG_PROB).
+template <bool EXACT>
+__device__ __forceinline__ void obs_element(float v, float chi, float ca, float cb_, const RowCoef& c, int max_poisson,
+                                            float (&acc)[kNumSums], float& p_out, float& q_out) {
   const float mu1 = fmaf(c.a_mu1, chi, 1e-10f);
   const float lam1 = fmaf(c.cA1, ca, fmaf(c.cB1, cb_, 1e-10f));
   const float lam0 = fmaf(c.cA0, ca, fmaf(c.cB0, cb_, 1e-10f));
   const float lamE = fmaf(c.cAE, ca, fmaf(c.cBE, cb_, 1e-10f));
-  const NbpcOut o1 = nbpc_eval<true>(v, mu1, c.alpha, lam1);
-  const NbpcOut o0 = nbpc_eval<true>(v, 1e-10f, c.alpha, lam0);
+  const NbpcOut o1 = EXACT ? nbpc_exact_eval<true>(v, mu1, c.alpha, lam1, max_poisson) : nbpc_eval<true>(v, mu1, c.alpha, lam1);
+  const NbpcOut o0 = EXACT ? nbpc_exact_eval<true>(v, 1e-10f, c.alpha, lam0, max_poisson) : nbpc_eval<true>(v, 1e-10f, c.alpha, lam0);
   const float LE = poisson_logpmf(v, lamE);
   const float dE = v / lamE - 1.0f;
   acc[0] += o1.L;
@@ -68,15 +71,33 @@ __device__ __forceinline__ void obs_element(float v, float chi, float ca, float 
   q_out = c.w1 * c.cA1 * o1.dlam + c.w0 * c.cA0 * o0.dlam + c.wE * c.cAE * dE;
 }
 
+// x == 0 under the exact convolution: the single term Poisson(0; lam) NB(0; mu, alpha) (...Conv.py:104-108)
+//   L = -lam + alpha log(alpha / (alpha + mu)),  dL/dmu = -alpha / (alpha + mu),  dL/dlam = -1,
+//   dL/dalpha = log(alpha / (alpha + mu)) + mu / (alpha + mu)
+__device__ __forceinline__ NbpcOut nbpc_exact_zero(float mu, float alpha, float inv_alpha, float lam) {
+  NbpcOut o;
+  const float r = mu * inv_alpha;
+  const float lar = -log1pf(r);
+  const float f = 1.0f / (1.0f + r);  // alpha / (alpha + mu)
+  o.L = fmaf(alpha, lar, -lam);
+  o.dmu = -f;
+  o.dlam = -1.0f;
+  o.dalpha = lar + r * f;
+  return o;
+}
+
 // contributions of one gene WITHOUT a stored count (x == 0)
+template <bool EXACT>
 __device__ __forceinline__ void obs_zero_element(float chi, float ca, float cb_, const RowCoef& c, float inv_alpha,
                                                  float (&acc)[kNumSums], float& p_out, float& q_out) {
   const float mu1 = fmaf(c.a_mu1, chi, 1e-10f);
   const float lam1 = fmaf(c.cA1, ca, fmaf(c.cB1, cb_, 1e-10f));
   const float lam0 = fmaf(c.cA0, ca, fmaf(c.cB0, cb_, 1e-10f));
   const float lamE = fmaf(c.cAE, ca, fmaf(c.cBE, cb_, 1e-10f));
-  const NbpcOut o1 = nbpc_zero(mu1, inv_alpha, lam1);
-  const NbpcOut o0 = nbpc_zero_mu_eps(lam0, -0.5f * 1e-10f * 1e-10f * inv_alpha * inv_alpha);
+  const float neg_half_mu2_inv_alpha2 = -0.5f * 1e-10f * 1e-10f * inv_alpha * inv_alpha;
+  const NbpcOut o1 = EXACT ? nbpc_exact_zero(mu1, c.alpha, inv_alpha, lam1) : nbpc_zero(mu1, inv_alpha, lam1);
+  // exact, mu = 1e-10: alpha log(alpha / (alpha + mu)) = -mu to fp32, dL/dalpha = -(mu / alpha)^2 / 2 (no Poisson branch)
+  const NbpcOut o0 = EXACT ? NbpcOut{-(1e-10f + lam0), 0.f, -1.0f, neg_half_mu2_inv_alpha2} : nbpc_zero_mu_eps(lam0, neg_half_mu2_inv_alpha2);
   acc[0] += o1.L;
   acc[1] += o0.L;
   acc[2] -= lamE;  // Poisson(0; lamE)
@@ -93,13 +114,14 @@ __device__ __forceinline__ void obs_zero_element(float chi, float ca, float cb_,
   q_out = c.w1 * c.cA1 * o1.dlam + c.w0 * c.cA0 * o0.dlam - c.wE * c.cAE;
 }
 
+template <bool EXACT>
 __global__ void __launch_bounds__(kObsThreads, 2) elbo_obs_kernel(
     const long long* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ data,
     const long long* __restrict__ row_ids, int G, const float* __restrict__ logits, long long ldl,
     const float* __restrict__ chi_amb, const float* __restrict__ chi_bar, const float* __restrict__ coef,
     const float* __restrict__ alpha, const float* __restrict__ w, float* __restrict__ sums,
     float* __restrict__ dlogits, float* __restrict__ qamb, long long ldq, float* __restrict__ lse_out,
-    int* __restrict__ nan_flag) {
+    int* __restrict__ nan_flag, int max_poisson) {
   extern __shared__ unsigned int bitmap[];  // (G + 31) / 32 words
   __shared__ float red[32];
   __shared__ double dred[kNumSums * 32];
@@ -161,14 +183,15 @@ __global__ void __launch_bounds__(kObsThreads, 2) elbo_obs_kernel(
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       pp[k] = 0.f, qq[k] = 0.f;
-      if (!((bits >> k) & 1u)) obs_zero_element(expf(ll[k] - lse), aa[k], bb[k], c, inv_alpha, acc, pp[k], qq[k]);
+      if (!((bits >> k) & 1u)) obs_zero_element<EXACT>(expf(ll[k] - lse), aa[k], bb[k], c, inv_alpha, acc, pp[k], qq[k]);
     }
     *reinterpret_cast<float4*>(drow + g0) = make_float4(pp[0], pp[1], pp[2], pp[3]);
     *reinterpret_cast<float4*>(qrow + g0) = make_float4(qq[0], qq[1], qq[2], qq[3]);
   }
   for (int g = 4 * G4 + threadIdx.x; g < G; g += blockDim.x) {
     float p = 0.f, q = 0.f;
-    if (!((bitmap[g >> 5] >> (g & 31)) & 1u)) obs_zero_element(expf(lrow[g] - lse), chi_amb[g], chi_bar[g], c, inv_alpha, acc, p, q);
+    if (!((bitmap[g >> 5] >> (g & 31)) & 1u))
+      obs_zero_element<EXACT>(expf(lrow[g] - lse), chi_amb[g], chi_bar[g], c, inv_alpha, acc, p, q);
     drow[g] = p;
     qrow[g] = q;
   }
@@ -178,7 +201,7 @@ __global__ void __launch_bounds__(kObsThreads, 2) elbo_obs_kernel(
   for (long long j = s + threadIdx.x; j < e; j += blockDim.x) {
     const int g = indices[j];
     float p, q;
-    obs_element(data[j], expf(lrow[g] - lse), chi_amb[g], chi_bar[g], c, acc, p, q);
+    obs_element<EXACT>(data[j], expf(lrow[g] - lse), chi_amb[g], chi_bar[g], c, max_poisson, acc, p, q);
     drow[g] = p;
     qrow[g] = q;
   }
@@ -246,11 +269,10 @@ __global__ void __launch_bounds__(kColsumCols* kColsumGroups) colsum_rows_kernel
 
 }  // namespace cb
 
-extern "C" int cb_elbo_obs_fwd_bwd(const long long* indptr, const int* indices, const float* data,
-                                   const long long* row_ids, int n_rows, int n_genes, const float* logits,
-                                   long long ldl, const float* chi_ambient, const float* chi_bar, const float* coef,
-                                   const float* alpha, const float* w, float* sums, float* dlogits, float* qamb,
-                                   long long ldq, float* lse_out, int* nan_flag, void* stream) {
+static int elbo_obs_launch(const long long* indptr, const int* indices, const float* data, const long long* row_ids, int n_rows,
+                           int n_genes, const float* logits, long long ldl, const float* chi_ambient, const float* chi_bar,
+                           const float* coef, const float* alpha, const float* w, float* sums, float* dlogits, float* qamb,
+                           long long ldq, float* lse_out, int* nan_flag, int max_poisson, void* stream) {
   if (n_rows == 0) return 0;
   CB_REQUIRE(n_rows > 0 && n_genes > 0, "cb_elbo_obs_fwd_bwd: bad shape [%d, %d]", n_rows, n_genes);
   CB_REQUIRE((ldl & 3) == 0 && (ldq & 3) == 0 && ldl >= n_genes && ldq >= n_genes,
@@ -260,12 +282,32 @@ extern "C" int cb_elbo_obs_fwd_bwd(const long long* indptr, const int* indices, 
     CB_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "cb_elbo_obs_fwd_bwd: pointer not 16-byte aligned");
   const size_t smem = size_t((n_genes + 31) / 32) * sizeof(unsigned int);
   CB_REQUIRE(smem <= 200 * 1024, "cb_elbo_obs_fwd_bwd: n_genes=%d too large for the shared-memory bitmap", n_genes);
-  if (smem > 40 * 1024)
-    cudaFuncSetAttribute(cb::elbo_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  cb::elbo_obs_kernel<<<n_rows, cb::kObsThreads, smem, (cudaStream_t)stream>>>(
-      indptr, indices, data, row_ids, n_genes, logits, ldl, chi_ambient, chi_bar, coef, alpha, w, sums, dlogits, qamb,
-      ldq, lse_out, nan_flag);
+  auto kern = max_poisson >= 0 ? cb::elbo_obs_kernel<true> : cb::elbo_obs_kernel<false>;
+  if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  kern<<<n_rows, cb::kObsThreads, smem, (cudaStream_t)stream>>>(indptr, indices, data, row_ids, n_genes, logits, ldl, chi_ambient,
+                                                                chi_bar, coef, alpha, w, sums, dlogits, qamb, ldq, lse_out,
+                                                                nan_flag, max_poisson);
   return cb::check_launch("cb_elbo_obs_fwd_bwd");
+}
+
+extern "C" int cb_elbo_obs_fwd_bwd(const long long* indptr, const int* indices, const float* data,
+                                   const long long* row_ids, int n_rows, int n_genes, const float* logits,
+                                   long long ldl, const float* chi_ambient, const float* chi_bar, const float* coef,
+                                   const float* alpha, const float* w, float* sums, float* dlogits, float* qamb,
+                                   long long ldq, float* lse_out, int* nan_flag, void* stream) {
+  return elbo_obs_launch(indptr, indices, data, row_ids, n_rows, n_genes, logits, ldl, chi_ambient, chi_bar, coef, alpha, w, sums,
+                         dlogits, qamb, ldq, lse_out, nan_flag, -1, stream);
+}
+
+// The same with the exact NB (+) Poisson convolution as the likelihood (NegativeBinomialPoissonConv, max_poisson terms).
+extern "C" int cb_elbo_obs_exact_fwd_bwd(const long long* indptr, const int* indices, const float* data,
+                                         const long long* row_ids, int n_rows, int n_genes, const float* logits,
+                                         long long ldl, const float* chi_ambient, const float* chi_bar, const float* coef,
+                                         const float* alpha, const float* w, float* sums, float* dlogits, float* qamb,
+                                         long long ldq, float* lse_out, int* nan_flag, int max_poisson, void* stream) {
+  CB_REQUIRE(max_poisson >= 0 && max_poisson <= 1000, "cb_elbo_obs_exact_fwd_bwd: max_poisson=%d not in [0, 1000]", max_poisson);
+  return elbo_obs_launch(indptr, indices, data, row_ids, n_rows, n_genes, logits, ldl, chi_ambient, chi_bar, coef, alpha, w, sums,
+                         dlogits, qamb, ldq, lse_out, nan_flag, max_poisson, stream);
 }
 
 extern "C" int cb_colsum_rows(const float* in, int n_rows, int n_cols, long long ld, float* out, void* stream) {

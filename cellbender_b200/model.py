@@ -111,7 +111,8 @@ class _ObsTerm(torch.autograd.Function):
         out = ops.elbo_obs(csr, row_ids, logits, chi_a, bufs["chi_b"], coef.contiguous(), alpha.reshape(1).contiguous(),
                            w.contiguous(), out={"sums": oo["sums"][:B], "dlogits": oo["dlogits"][:B], "qamb": oo["qamb"][:B],
                                                 "dchi_ambient": oo["dchi_ambient"], "lse": oo["lse"], "nan_flag": oo["nan_flag"]},
-                           defer_colsum=any(ctx.needs_input_grad))
+                           defer_colsum=any(ctx.needs_input_grad),
+                           max_poisson=consts.NBPC_EXACT_MAX_POISSON if model.use_exact_log_prob else None)
         ctx.dchi_ready = out["dchi_ready"]
         sums = out["sums"]
         L = sums[:, :3]
@@ -176,9 +177,6 @@ class RemoveBackgroundPyroModel(nn.Module):
         if model_type == "simple":
             raise NotImplementedError("the B200 hot path covers model types with empty droplets "
                                       "('ambient', 'swapping', 'full'); 'simple' has no enumerated y")
-        if use_exact_log_prob:
-            raise NotImplementedError("USE_EXACT_LOG_PROB is False in the reference (consts.py:68); "
-                                      "only the default approximate likelihood is on the hot path")
         self.model_type = model_type
         self.include_empties = True
         self.include_rho = model_type in ("full", "swapping")

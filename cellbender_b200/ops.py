@@ -212,10 +212,12 @@ SUM_NAMES = ("L1", "L0", "LE", "dL1_da_mu1", "dL1_dcA1", "dL1_dcB1", "dL1_dalpha
              "dL0_dalpha", "dLE_dcAE", "dLE_dcBE")
 
 
-def elbo_obs(csr: DeviceCSR, row_ids, logits, chi_ambient, chi_bar, coef, alpha, w, *, out=None, defer_colsum: bool = False):
-    """cb_elbo_obs_fwd_bwd + cb_colsum_rows.  logits: [B, ld] buffer (ld % 4 == 0) holding G valid columns.
-    chi_ambient / chi_bar: fp32 [>= G] 16-byte aligned.  Returns dict(sums [B,12], dlogits [B,ld], dchi_ambient [G],
-    lse [B], nan_flag)."""
+def elbo_obs(csr: DeviceCSR, row_ids, logits, chi_ambient, chi_bar, coef, alpha, w, *, out=None, defer_colsum: bool = False,
+             max_poisson: Optional[int] = None):
+    """cb_elbo_obs_fwd_bwd (+ cb_colsum_rows).  logits: [B, ld] buffer (ld % 4 == 0) holding G valid columns.
+    chi_ambient / chi_bar: fp32 [>= G] 16-byte aligned.  ``max_poisson``: None = the approximate likelihood (the
+    reference's default), an int = the exact convolution with that many Poisson terms (cb_elbo_obs_exact_fwd_bwd).
+    Returns dict(sums [B,12], dlogits [B,ld], dchi_ambient [G], lse [B], nan_flag)."""
     _req_cuda(logits, chi_ambient, chi_bar, coef, alpha, w, row_ids)
     B, G = int(row_ids.numel()), csr.n_genes
     ld = logits.stride(0)
@@ -236,9 +238,13 @@ def elbo_obs(csr: DeviceCSR, row_ids, logits, chi_ambient, chi_bar, coef, alpha,
         out["nan_flag"] = torch.zeros(1, dtype=torch.int32, device=dev)
     st = current_stream()
     L = _cabi.lib()
-    L.call("cb_elbo_obs_fwd_bwd", ptr(csr.indptr), ptr(csr.indices), ptr(csr.data), ptr(row_ids), B, G, ptr(logits), ld,
-           ptr(chi_ambient), ptr(chi_bar), ptr(coef), ptr(alpha), ptr(w), ptr(out["sums"]), ptr(out["dlogits"]),
-           ptr(out["qamb"]), ld, ptr(out["lse"]), ptr(out["nan_flag"]), st)
+    operands = (ptr(csr.indptr), ptr(csr.indices), ptr(csr.data), ptr(row_ids), B, G, ptr(logits), ld, ptr(chi_ambient), ptr(chi_bar),
+                ptr(coef), ptr(alpha), ptr(w), ptr(out["sums"]), ptr(out["dlogits"]), ptr(out["qamb"]), ld, ptr(out["lse"]),
+                ptr(out["nan_flag"]))
+    if max_poisson is None:
+        L.call("cb_elbo_obs_fwd_bwd", *operands, st)
+    else:
+        L.call("cb_elbo_obs_exact_fwd_bwd", *operands, int(max_poisson), st)
     if not defer_colsum:
         L.call("cb_colsum_rows", ptr(out["qamb"]), B, G, ld, ptr(out["dchi_ambient"]), st)
         out["dchi_ready"] = None

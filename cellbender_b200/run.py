@@ -60,7 +60,9 @@ def build_model(dataset_obj, args, device: Optional[str] = None) -> RemoveBackgr
         model_type=args.model, encoder=encoder, decoder=decoder, dataset_obj_priors=dataset_obj.priors,
         n_analyzed_genes=n_genes, n_droplets=int(dataset_obj.analyzed_barcode_inds.size),
         analyzed_gene_names=gene_names, empty_UMI_threshold=dataset_obj.empty_UMI_threshold,
-        log_counts_crossover=dataset_obj.priors["log_counts_crossover"], use_cuda=True, device=device)
+        log_counts_crossover=dataset_obj.priors["log_counts_crossover"], use_cuda=True, device=device,
+        # consts.USE_EXACT_LOG_PROB of the reference (consts.py:68, a module constant there): the exact convolution likelihood
+        use_exact_log_prob=bool(getattr(args, "use_exact_log_prob", consts.USE_EXACT_LOG_PROB)))
 
 
 def setup_inference(dataset_obj, args, device: Optional[str] = None, total_epochs_for_testing_only: Optional[int] = None,

@@ -78,7 +78,13 @@ int cb_nbpc_exact_log_prob_bwd(const float* value, const long long* sv, const fl
 int cb_elbo_obs_fwd_bwd(const long long* indptr, const int* indices, const float* data, const long long* row_ids,
                         int n_rows, int n_genes, const float* logits, long long ldl, const float* chi_ambient,
                         const float* chi_bar, const float* coef, const float* alpha, const float* w, float* sums,
-                        float* dlogits, float* qamb, long long ldq, float* lse_out, int* nan_flag, void* stream);
+                        float* dlogits, float* qamb, long long ldq, float* lse_out, int* nan_flag, void* stream);/* The same with the exact NB (+) Poisson convolution as the likelihood: NegativeBinomialPoissonConv(max_poisson)
+ * (distributions/NegativeBinomialPoissonConv.py:89-154; model.py:336-357 with consts.USE_EXACT_LOG_PROB = True).  Genes
+ * without a stored count use the one-term closed form, stored counts the term-by-term sum in float64.               */
+int cb_elbo_obs_exact_fwd_bwd(const long long* indptr, const int* indices, const float* data, const long long* row_ids,
+                        int n_rows, int n_genes, const float* logits, long long ldl, const float* chi_ambient,
+                        const float* chi_bar, const float* coef, const float* alpha, const float* w, float* sums,
+                        float* dlogits, float* qamb, long long ldq, float* lse_out, int* nan_flag, int max_poisson, void* stream);
 int cb_colsum_rows(const float* in, int n_rows, int n_cols, long long ld, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------

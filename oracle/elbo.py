@@ -11,7 +11,9 @@ hand restatement of SURVEY.md section 3.2 (model.py:232-445 model, :447-574 guid
 Two likelihood back-ends:
   'reference'  the reference's own formula (oracle/nbpc.py:nbpc_approx_log_prob) in the tensors' dtype -- this is
                what the reference computes, rounding errors included; used for the timed CPU baseline;
-  'mp'         multiprecision value + analytic gradient per element (small cases) -- the parity target.
+  'mp'         multiprecision value + analytic gradient per element (small cases) -- the parity target;
+  'exact'      the exact NB (+) Poisson convolution (NegativeBinomialPoissonConv, max_poisson = 100) in the tensors' dtype
+               without the reference's float32 cast of its count tables (true value in float64).
 """
 from typing import Dict, Optional
 
@@ -174,7 +176,12 @@ def elbo(x: torch.Tensor, params: Dict[str, torch.Tensor], buffers: Dict[str, to
     t["p_logit_reg"] = (Normal(c(cfg["p_logit_prior"]), P_LOGIT_SCALE).log_prob(v) - Normal(p_y, P_LOGIT_SCALE).log_prob(v)).sum()
 
     alpha = phi.reciprocal() + EPS
-    like = (lambda val, mu, al, lam: _NbpcMp.apply(val, mu, al, lam)) if likelihood == "mp" else onb.nbpc_approx_log_prob
+    if likelihood == "mp":
+        like = lambda val, mu, al, lam: _NbpcMp.apply(val, mu, al, lam)
+    elif likelihood == "exact":  # NegativeBinomialPoissonConv(max_poisson=100): model.py:349-357 (USE_EXACT_LOG_PROB)
+        like = lambda val, mu, al, lam: onb.nbpc_exact_log_prob(val, mu, al, lam, max_poisson=100, float32_tables=False)
+    else:
+        like = onb.nbpc_approx_log_prob
     obs = torch.zeros((), dtype=dt, device=dev)
     for yv, q in ((1.0, q1), (0.0, q0)):
         y = torch.full((B,), yv, dtype=dt, device=dev)

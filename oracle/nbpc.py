@@ -73,7 +73,7 @@ def nbpc_approx_log_prob(value, mu, alpha, lam):
     return torch.where(empty, _poisson_log_prob(lam, value), nb)
 
 
-def nbpc_exact_log_prob(value, mu, alpha, lam, max_poisson: int = 100):
+def nbpc_exact_log_prob(value, mu, alpha, lam, max_poisson: int = 100, float32_tables: bool = True):
     """Exact NB (+) Poisson convolution by direct summation (...Conv.py:89-154):
     closed forms for value 0 and 1, otherwise logsumexp over max_poisson+1 Poisson terms
     starting at clamp(min(int(lam - max_poisson/2), int(value - max_poisson)), 0)."""
@@ -92,8 +92,10 @@ def nbpc_exact_log_prob(value, mu, alpha, lam, max_poisson: int = 100):
     nb_vals = nb_vals.clamp(min=0)
     # NOTE the reference casts the count tables with ``.float()`` (...Conv.py:138-141), so
     # their lgamma terms are evaluated in float32 even when mu/alpha/lam are float64.
-    tot = _poisson_log_prob(lam.unsqueeze(-1), pois_vals.float()) + _neg_binom_log_prob(
-        mu.unsqueeze(-1), alpha.unsqueeze(-1), nb_vals.float()
+    # float32_tables=False: the same sum without that cast (the mathematically exact value in the operands' dtype)
+    cast = (lambda t: t.float()) if float32_tables else (lambda t: t)
+    tot = _poisson_log_prob(lam.unsqueeze(-1), cast(pois_vals)) + _neg_binom_log_prob(
+        mu.unsqueeze(-1), alpha.unsqueeze(-1), cast(nb_vals)
     )
     tot = torch.where(bad, torch.full_like(tot, float("-inf")), tot)
     lp_rest = torch.logsumexp(tot, dim=-1)

@@ -14,11 +14,11 @@ def _small_dataset(seed=0, n_genes=96):
     return synth.prepare_dataset(sim, expected_cells=50, total_droplets_included=150)
 
 
-def _setup(model_type="full", epochs=3, n_genes=96, z_dim=8, hidden=32):
+def _setup(model_type="full", epochs=3, n_genes=96, z_dim=8, hidden=32, exact=False):
     from cellbender_b200 import run
 
     ds = _small_dataset(n_genes=n_genes)
-    args = run.default_args(epochs=epochs, z_dim=z_dim, z_hidden_dims=[hidden], model=model_type)
+    args = run.default_args(epochs=epochs, z_dim=z_dim, z_hidden_dims=[hidden], model=model_type, use_exact_log_prob=exact)
     model, opt, svi, train_loader, test_loader = run.setup_inference(ds, args, device=DEV)
     return ds, args, model, opt, svi, train_loader, test_loader
 

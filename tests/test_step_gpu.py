@@ -54,6 +54,15 @@ def test_elbo_other_model_types_match_oracle(model_type, fp32_gemm):
     _elbo_parity(True, rtol_terms=1e-5, rtol_grads=2e-3, model_type=model_type)
 
 
+@pytest.mark.parametrize("training", [True, False])
+def test_elbo_with_the_exact_convolution_likelihood_matches_oracle(training, fp32_gemm):
+    """consts.USE_EXACT_LOG_PROB (model.py:336-357): the fused observation kernel with NegativeBinomialPoissonConv(
+    max_poisson = 100) as the likelihood -- one-term closed form where no count is stored, the term-by-term float64 sum on
+    the stored counts -- against the oracle's float64 evaluation of the same sum (without the reference's float32 cast of
+    its count tables, oracle/nbpc.py), every term and every gradient."""
+    _elbo_parity(training, rtol_terms=1e-5, rtol_grads=2e-3, likelihood="exact", shape=dict(exact=True))
+
+
 @pytest.mark.parametrize("tf32", [False, True])
 def test_elbo_matches_oracle_at_a_medium_shape(tf32, request):
     """The same term-by-term / gradient-by-gradient comparison at G = 2051 genes (not a multiple of 4: padded rows and weight
