@@ -130,6 +130,73 @@ struct NbpcOut {
   float L, dmu, dlam, dalpha;
 };
 
+// ---- counts above kF64Count: the same cancellation-free decomposition evaluated in float64 -----------------------
+// With counts in the hundreds the individual pieces (v phi(m/v - 1), a2 phi(u), v log ratios) reach 1e3 while L stays
+// O(10): fp32 pieces leave 2-3e-5 of |L|.  Such elements are rare (a few stored counts per droplet), so they take the
+// float64 pipe: same formulas, log1p-based phi (its rounding error scales with |u|, harmless in float64).
+constexpr float kF64Count = 64.0f;
+CB_HD double phi_d(double u) { return log1p(u) - u; }
+CB_HD double log_ratio_d(double num, double den, double num_minus_den) {
+  const double d = num_minus_den / den;
+  return (fabs(d) < 0.25) ? log1p(d) : log(num / den);
+}
+CB_HD double stirling_S_d(double z) {
+  const double r = 1.0 / z, r2 = r * r;
+  return r * (1.0 / 12.0 + r2 * (-1.0 / 360.0 + r2 * (1.0 / 1260.0 - r2 * (1.0 / 1680.0))));
+}
+CB_HD double stirling_S_diff_d(double z, double d) {
+  const double z2 = z + d, r1 = 1.0 / z, r2 = 1.0 / z2;
+  const double q1 = r1 * r1, q2 = r2 * r2;
+  const double hi1 = r1 * q1 * (-1.0 / 360.0 + q1 * (1.0 / 1260.0 - q1 * (1.0 / 1680.0)));
+  const double hi2 = r2 * q2 * (-1.0 / 360.0 + q2 * (1.0 / 1260.0 - q2 * (1.0 / 1680.0)));
+  return -(1.0 / 12.0) * d * r1 * r2 + (hi2 - hi1);
+}
+CB_HD double digamma_P_diff_d(double z, double d) {
+  const double z2 = z + d, r1 = 1.0 / z, r2 = 1.0 / z2;
+  const double q1 = r1 * r1, q2 = r2 * r2;
+  const double hi1 = q1 * q1 * (1.0 / 120.0 - q1 * (1.0 / 252.0 - q1 * (1.0 / 240.0)));
+  const double hi2 = q2 * q2 * (1.0 / 120.0 - q2 * (1.0 / 252.0 - q2 * (1.0 / 240.0)));
+  return 0.5 * d * r1 * r2 + (1.0 / 12.0) * d * (z + z2) * q1 * q2 + (hi2 - hi1);
+}
+
+// (not inlined: a real call keeps its float64 registers out of the callers' hot fp32 paths)
+template <bool GRAD>
+__host__ __device__ __noinline__ NbpcOut nbpc_eval_large_f64(float vf, float muf, float alphaf, float lamf) {
+  NbpcOut o;
+  const double v = vf, mu = muf, alpha = alphaf, lam = lamf;
+  const double m = mu + lam;
+  const double w = (mu / m) * (mu / alpha);
+  const double inv1pw = 1.0 / (1.0 + w);
+  const double q = (w > 0.0) ? log1p(w) / w : 1.0;
+  const double a = fmin(m / w, 1e300);
+  const double apm = a + m;
+  const int k = (a < 8.0) ? 8 : 0;  // shift small alpha_hat up so that the Stirling remainder applies
+  double T = 0.0, S1 = 0.0;
+  for (int i = 0; i < k; ++i) {
+    const double fi = double(i);
+    T += log_ratio_d(a + fi, apm, fi - m);
+    if (GRAD) S1 += (m - fi) / ((a + fi) * (1.0 + w));
+  }
+  const double vr = v - double(k), a2 = a + double(k), m2 = m - double(k);
+  const double u = vr / a2;
+  T += a2 * phi_d(u) - 0.5 * log1p(u) + vr * log_ratio_d(a2 + vr, apm, vr - m2) + stirling_S_diff_d(a2, vr);
+  const double t = m / v;
+  const double pois = v * ((fabs(t - 1.0) < 0.25) ? phi_d(t - 1.0) : log(t) - (t - 1.0)) - 0.5 * log(6.283185307179586 * v)
+                      - stirling_S_d(v);
+  o.L = float(T - a * phi_d(w) + pois);
+  o.dmu = 0.f, o.dlam = 0.f, o.dalpha = 0.f;
+  if (GRAD) {
+    S1 += a * (phi_d(u) + u * m2 / apm + digamma_P_diff_d(a2, vr));
+    const double h = (w < 1e-4) ? -w * (0.5 - w * (2.0 / 3.0 - w * 0.75)) : inv1pw - q;
+    const double dLdm = (v - m) / m * inv1pw;
+    const double A1 = S1 + m * h;
+    o.dmu = float(dLdm - 2.0 * A1 * (lam / m) / mu);
+    o.dlam = float(dLdm + 2.0 * A1 / m);
+    o.dalpha = float(A1 / alpha);
+  }
+  return o;
+}
+
 // One element of NBPCapprox.log_prob (+ gradients when GRAD).  mu, alpha, lam > 0; v >= 0 integer-valued.
 template <bool GRAD>
 CB_HD NbpcOut nbpc_eval(float v, float mu, float alpha, float lam) {
@@ -140,6 +207,7 @@ CB_HD NbpcOut nbpc_eval(float v, float mu, float alpha, float lam) {
     if (GRAD) o.dlam = v / lam - 1.0f;
     return o;
   }
+  if (v > kF64Count) return nbpc_eval_large_f64<GRAD>(v, mu, alpha, lam);
   const float m = mu + lam;
   const float w = (mu / m) * (mu / alpha);  // = m / alpha_hat
   const float inv1pw = 1.0f / (1.0f + w);

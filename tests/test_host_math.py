@@ -35,10 +35,8 @@ def test_nbpc_fp32_math_vs_multiprecision(hostlib, golden_dir):
     hostlib.host_nbpc_eval(n, _p(v), _p(mu), _p(al), _p(lam), _p(L), _p(dmu), _p(dlam), _p(dal))
     ref = g["approx_mp"]
     err = np.abs(L - ref) / np.maximum(np.abs(ref), 1.0)
-    small = v <= 64
-    # tolerance of north_star: 1e-5 relative (to max(|L|,1)); counts in the hundreds get 3e-5
-    assert err[small].max() < 1e-5, err[small].max()
-    assert err.max() < 3e-5, err.max()
+    # tolerance of north_star: 1e-5 relative (to max(|L|,1)) for every count (counts above 64 take the float64 pipe)
+    assert err.max() < 1e-5, (err.max(), v[np.argmax(err)])
     # the reference's own fp32 evaluation is far worse on the same inputs (context for the tolerance)
     ref32 = np.abs(g["approx_f32"] - ref) / np.maximum(np.abs(ref), 1.0)
     assert np.nanmax(ref32) > 1e-2

@@ -81,8 +81,7 @@ def test_nbpc_elementwise_vs_multiprecision(ops, golden_dir):
     lp = ops.nbpc_approx_log_prob(v, mu, al, lam)
     ref = g["approx_mp"]
     err = np.abs(lp.detach().cpu().numpy() - ref) / np.maximum(np.abs(ref), 1.0)
-    small = g["value"] <= 64
-    assert err[small].max() < 1e-5 and err.max() < 3e-5, (err[small].max(), err.max())
+    assert err.max() < 1e-5, err.max()  # every count: above 64 the element takes the float64 pipe (nbpc_eval_large_f64)
     gm, ga, gl = torch.autograd.grad(lp.sum(), (mu, al, lam))
     for name, mine in (("dmu", gm), ("dalpha", ga), ("dlam", gl)):
         r = g[f"approx_{name}_mp"]
