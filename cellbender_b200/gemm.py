@@ -157,6 +157,13 @@ class LazyFeat:
         self.value: Optional[torch.Tensor] = None
 
 
+def _stacked_rows(w0: torch.Tensor, w1: torch.Tensor) -> bool:
+    """True when w1's rows directly follow w0's in memory with the same row pitch (consecutive blocks of the optimizer's
+    flat buffer): [w0; w1] then is ONE matrix."""
+    return (w0.dim() == 2 and w1.dim() == 2 and w0.shape[1] == w1.shape[1] and w0.stride() == w1.stride() and w0.stride(1) == 1
+            and w0.dtype == w1.dtype and w1.data_ptr() == w0.data_ptr() + w0.element_size() * w0.shape[0] * w0.stride(0))
+
+
 class _MultiLinearBig(torch.autograd.Function):
     """Several nn.Linear layers that read the SAME wide input x (EncodeNonZLatents' layer1 and eps_network.0, or the
     single EncodeZ input layer):
@@ -170,7 +177,27 @@ class _MultiLinearBig(torch.autograd.Function):
         B = x.shape[0]
         ys = []
         main = torch.cuda.current_stream()
-        for i, (feat, w, b) in enumerate(zip(feats, weights, biases)):
+        fused = (len(weights) == 2 and all(isinstance(f, LazyFeat) for f in feats) and _stacked_rows(weights[0], weights[1])
+                 and (biases[0] is None) == (biases[1] is None))
+        if fused:
+            # The two towers' input layers sit in consecutive blocks of the flat parameter buffer: [W_0; W_1] is one
+            # [H_0 + H_1, ld] matrix, so both products are ONE launch that reads the wide input once (two separate deep-ring
+            # launches cannot share an SM -- 200 KB of shared memory each -- and ran one after the other: r02z timeline)
+            w0, w1 = weights
+            H0, H1 = w0.shape[0], w1.shape[0]
+            wcat = torch.as_strided(w0, (H0 + H1, w0.shape[1]), w0.stride())
+            bias = None if biases[0] is None else torch.cat([biases[0].reshape(-1), biases[1].reshape(-1)])
+            y = torch.empty((B, ops.row_pitch(H0 + H1)), dtype=torch.float32, device=x.device)
+            ops.gemm_tf32(x, wcat[:, col_offset:col_offset + n_in], B, H0 + H1, n_in, bias=bias, out=y[:, :H0 + H1])
+            ys = [y[:, :H0], y[:, H0:H0 + H1]]
+            if streams is not None:
+                done = torch.cuda.Event()
+                done.record(main)
+                for st in streams:
+                    if st is not None:  # the caller consumes that output on this stream
+                        st.wait_event(done)
+                        y.record_stream(st)
+        for i, (feat, w, b) in enumerate(zip(feats, weights, biases) if not fused else ()):
             st = streams[i] if streams is not None else None
             if st is not None:  # this product runs on its own stream (the caller joins it before consuming the output)
                 y = torch.empty((B, ops.row_pitch(w.shape[0])), dtype=torch.float32, device=x.device)[:, :w.shape[0]]
