@@ -169,6 +169,37 @@ class SVI:
         return self.loss_terms(batch)["loss"].detach()
 
 
+class LossReader:
+    """Host-side reading of EVERY step's loss without stalling the device: ``push(loss)`` issues the device -> host copy of
+    this step's loss into a pinned slot behind the step and returns the value of the PREVIOUS step, whose copy has long
+    finished; ``flush()`` returns the last one.  The reference's ``svi.step`` returns ``loss.item()`` -- a device
+    synchronisation per minibatch, during which the GPU idles while the host draws the next minibatch; with the read one
+    step late the host logic of step t + 1 runs under step t.  (train_epoch needs no per-step value at all: it accumulates
+    on the device and reads once per epoch.)"""
+
+    def __init__(self, n_slots: int = 2):
+        self._host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(n_slots)]
+        self._events = [torch.cuda.Event() for _ in range(n_slots)]
+        self._pending = None
+        self._i = 0
+
+    def push(self, loss: torch.Tensor) -> Optional[float]:
+        prev = self.flush()
+        k = self._i % len(self._host)
+        self._host[k].copy_(loss.detach().reshape(()), non_blocking=True)
+        self._events[k].record()
+        self._pending = k
+        self._i += 1
+        return prev
+
+    def flush(self) -> Optional[float]:
+        if self._pending is None:
+            return None
+        k, self._pending = self._pending, None
+        self._events[k].synchronize()
+        return float(self._host[k])
+
+
 def is_scheduler(optim) -> bool:
     return isinstance(optim, FlatClippedAdam) and not optim.constant_learning_rate
 

@@ -248,3 +248,25 @@ def test_early_weight_update_equals_separate_adam(use_graph):
         if blk is not None:
             n = blk[1] * blk[2]
             assert float((pa[o:o + n] - pb[o:o + n]).abs().max()) < 2e-3, tuple(p_.shape)
+
+
+def test_loss_reader_returns_every_loss_one_step_late():
+    """train.LossReader: push() hands back the previous step's loss (read from a pinned slot whose copy has finished),
+    flush() the last one -- the same values loss.item() gives, without a device synchronisation per step."""
+    from cellbender_b200.train import LossReader
+
+    ds, args, model, opt, svi, train_loader, _ = _setup()
+    model.train()
+    reader = LossReader()
+    want, got = [], []
+    for epoch in range(2):
+        for b in train_loader:
+            loss = svi.step(b)
+            want.append(loss.clone())
+            v = reader.push(loss)
+            if v is not None:
+                got.append(v)
+    got.append(reader.flush())
+    assert reader.flush() is None
+    assert len(got) == len(want) >= 4
+    assert got == [float(w.item()) for w in want]
