@@ -353,6 +353,34 @@ class Posterior:
                     load(slots[t % NS], t * cpc, (t + 1) * cpc)
                 graphs[t % NS].replay()
             first_eager = n_full * cpc
+        elif self.use_cuda_graph and seed is None and noise_fn is None and n_full >= 1:
+            # one or two full chunks (small barcode shards): the pipeline's two drain iterations would cost more than they
+            # hide -- the three stages of a chunk as ONE captured graph, replayed per chunk
+            chunk_entries = np.array([int(prefix[(i + 1) * cpc] - prefix[i * cpc]) for i in range(n_full)])
+            key = (S, n_counts_max, float(smallest_log_probability), float(lambda_multiplier), bool(y_map), cpc)
+            cached = getattr(self, "_chunk_graph_serial", None)
+            if not (cached is not None and cached["key"] == key and cached["ws"] is ws and cached["slots"] is slots
+                    and cached["max_entries"] >= int(chunk_entries.max())):
+                max_entries = int(chunk_entries.max() * 1.25) + 1024
+
+                def whole_chunk():
+                    stage0(slots[0], cpc, 0)
+                    stage1(slots[0], cpc)
+                    stage2(slots[0], cpc, max_entries)
+
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    whole_chunk()  # warm-up outside capture on an empty chunk
+                torch.cuda.current_stream().wait_stream(side)
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_):
+                    whole_chunk()
+                cached = self._chunk_graph_serial = {"key": key, "graph": g_, "max_entries": max_entries, "ws": ws, "slots": slots}
+            for t in range(n_full):
+                load(slots[0], t * cpc, (t + 1) * cpc)
+                cached["graph"].replay()
+            first_eager = n_full * cpc
         else:
             first_eager = 0
         for start in range(first_eager, n_sel, cpc):
@@ -396,7 +424,7 @@ class Posterior:
                             "barcode": torch.zeros(cpc, dtype=torch.int64, device=dev),
                             "offset": torch.zeros(1, dtype=torch.int64, device=dev)} for _ in range(self.N_PIPELINE_SLOTS)]
             self._slots_key = key
-            self._chunk_graph = None
+            self._chunk_graph = self._chunk_graph_serial = None
         return self._slots
 
     def _host_indptr(self) -> np.ndarray:

@@ -213,7 +213,8 @@ def test_public_posterior_coo_caches_and_sums_to_one():
         post2.cell_noise_count_posterior_coo()
 
 
-def test_graph_replayed_chunks_equal_eager_chunks(monkeypatch):
+@pytest.mark.parametrize("n_called", [100, 70])
+def test_graph_replayed_chunks_equal_eager_chunks(monkeypatch, n_called):
     """Full chunks of a posterior pass replay ONE captured CUDA graph (static operand buffers, device-side output
     offset, grid sized for the largest chunk); the ragged last chunk runs eagerly.  With the Monte-Carlo draws replaced
     by their means on both paths the two must produce the identical COO."""
@@ -224,7 +225,7 @@ def test_graph_replayed_chunks_equal_eager_chunks(monkeypatch):
     monkeypatch.setattr(torch, "_standard_gamma", lambda conc: conc.clone())
     n = ds.analyzed_barcode_inds.size
     p = np.zeros(n)
-    p[:100] = 1.0
+    p[:n_called] = 1.0  # 100: 3 full chunks + 4 cells (three-deep pipeline of graphs); 70: 2 full chunks + 6 (one graph per chunk)
     outs = []
     for use_graph in (True, False):
         post = Posterior(ds, model, posterior_batch_size=16, cells_per_chunk=32)  # 3 full chunks + a tail of 4 cells
@@ -232,11 +233,11 @@ def test_graph_replayed_chunks_equal_eager_chunks(monkeypatch):
         post._latents = {"p": p, "z": None, "d": None, "epsilon": None, "phi_loc_scale": None}
         a = post.device_posterior(n_samples=4)
         b = post.device_posterior(n_samples=4)  # second pass: the cached graph and workspace are reused
-        assert (getattr(post, "_chunk_graph", None) is not None) == use_graph
+        assert (getattr(post, "_chunk_graph" if n_called == 100 else "_chunk_graph_serial", None) is not None) == use_graph
         for x, y in zip((a.m, a.c, a.log_prob, a.off_m, a.off_v), (b.m, b.c, b.log_prob, b.off_m, b.off_v)):
             assert torch.equal(x, y)
         outs.append(a)
     g, e = outs
-    assert g.m.numel() > 1000
+    assert g.m.numel() > 700
     assert torch.equal(g.m, e.m) and torch.equal(g.c, e.c) and torch.equal(g.off_m, e.off_m) and torch.equal(g.off_v, e.off_v)
     torch.testing.assert_close(g.log_prob, e.log_prob, rtol=0, atol=0)
