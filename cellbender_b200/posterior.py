@@ -268,9 +268,9 @@ class Posterior:
         # One chunk = three stages that hand over through the static buffers of a slot:
         #   stage 0  encoders + S latent draws + decoder hidden layer (a few hundred small launches, latency-bound)
         #   stage 1  ONE decoder GEMM for all samples of the chunk, output transposed and cell-major:
-        #            logits_t[g, b * S + s] = W[g, :] . h[b * S + s, :] (tensor-bound), then the column logsumexp of
-        #            logits_t + bias (HBM-bound)
-        #   stage 2  noise-count window over the chunk's stored counts                                   (XU-bound)
+        #            logits_t[g, b * S + s] = W[g, :] . h[b * S + s, :]                                  (tensor-bound)
+        #   stage 2  column logsumexp of logits_t + bias (HBM-bound), then the noise-count window over the chunk's stored
+        #            counts (XU-bound)
         def stage0(sl, Bc, pos0):
             _, enc = self._encode(sl["rows"][:Bc])
             noise = None if noise_fn is None else noise_fn(slice(pos0, pos0 + Bc), enc)
@@ -282,9 +282,9 @@ class Posterior:
 
         def stage1(sl, Bc, tile_cfg=0):
             ops.gemm_tf32(lin.weight, sl["h"][: Bc * S], G, Bc * S, H, out=sl["logits"][:, : Bc * S], split_k=1, tile_cfg=tile_cfg)
-            ops.col_logsumexp(sl["logits"], G, Bc * S, row_add=lin.bias, out=sl["lse"][: Bc * S])
 
         def stage2(sl, Bc, n_entries, ctas_per_sm=0):
+            ops.col_logsumexp(sl["logits"], G, Bc * S, row_add=lin.bias, out=sl["lse"][: Bc * S])
             ops.posterior_window(
                 csr, sl["rows"][:Bc], sl["logits"], lin.bias, sl["lse"], chi_a, chi_b, sl["a_mu"], sl["c_a"], sl["c_b"], sl["alpha"],
                 sl["nwin"][:Bc], sl["estart"][: Bc + 1], n_entries, sl["barcode"][:Bc], gene_all, total_genes, ws, sl["offset"],
