@@ -30,6 +30,7 @@ def main():
     from cellbender_b200.posterior import Posterior
 
     dev = "cuda:0"
+    torch.manual_seed(0)  # the model is randomly initialised: same weights (hence the same COO size) in every run
     ds = synth.make_config_dataset(a.workload, seed=0, device=dev)
     model = run.build_model(ds, run.default_args(), device=dev)
     model.eval()
