@@ -1,4 +1,8 @@
-"""torchrun debug driver: the bench's data-parallel warm-up sequence with progress lines (stderr) per step."""
+"""torchrun check of data-parallel training at the PBMC8k shape: two epochs through the loader (full and short last
+minibatch: two captured step graphs, exchange inside), progress lines per step on stderr, then the replicas are compared.
+
+    torchrun --nproc-per-node 4 tools/dp_train_check.py [auto|p2p|sharded]
+"""
 import os
 import sys
 
