@@ -270,3 +270,52 @@ def test_loss_reader_returns_every_loss_one_step_late():
     assert reader.flush() is None
     assert len(got) == len(want) >= 4
     assert got == [float(w.item()) for w in want]
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_restart_from_a_snapshot_is_bit_exact(use_graph):
+    """The reference tests that training resumed from a checkpoint continues bit for bit (tests/test_checkpoint.py:353-507:
+    model, optimizer, loader state and the random number generators are restored).  Same property here, in memory: nothing
+    that feeds the parameters depends on atomics order (fixed-order split-K, column and block reductions), so restoring
+    parameters + BatchNorm buffers + optimizer moments / step counter + loader state + numpy / torch generator states and
+    training on gives exactly the parameters of the uninterrupted run -- eagerly and through the replayed step graphs."""
+    import copy
+
+    from cellbender_b200 import run, synth
+
+    sim = synth.simulate_dataset(n_genes=256, cells_of_each_type=[40, 40], n_droplets=900, cell_mean_umi=2000.0,
+                                 empty_mean_umi=60.0, dirichlet_alpha=0.5, seed=0, device="cpu", cell_chunk=64)
+    ds = synth.prepare_dataset(sim, expected_cells=80, total_droplets_included=300)
+    args = run.default_args(epochs=6, z_dim=16, z_hidden_dims=[64], learning_rate=1e-3, use_cuda_graph=use_graph)
+    model, opt, svi, tl, _ = run.setup_inference(ds, args, device=DEV)
+    model.train()
+
+    def epochs(n):
+        for _ in range(n):
+            for b in tl:
+                svi.step(b)
+        torch.cuda.synchronize()
+
+    epochs(2)  # past the eager warm-up steps: the graphs (if any) are captured
+    snap = {"model": copy.deepcopy(model.state_dict()), "flat_p": opt.flat_p.clone(), "opt": copy.deepcopy(opt.state_dict()),
+            "loader": copy.deepcopy(tl.get_state()), "served": tl._served, "np": np.random.get_state(),
+            "torch": torch.get_rng_state(), "cuda": torch.cuda.get_rng_state(DEV),
+            "offset": dict(model.encoder["other"].offset)}
+    epochs(2)
+    want = opt.flat_p.clone()
+    want_m = opt.flat_m.clone()
+    # restore and run the same two epochs again
+    with torch.no_grad():
+        opt.flat_p.copy_(snap["flat_p"])
+    model.load_state_dict(snap["model"])
+    opt.load_state_dict(snap["opt"])
+    tl.set_state(snap["loader"]["ind_list"].copy(), snap["loader"]["ptr"])
+    tl._served = snap["served"]
+    np.random.set_state(snap["np"])
+    torch.set_rng_state(snap["torch"])
+    torch.cuda.set_rng_state(snap["cuda"], DEV)
+    model.encoder["other"].offset = snap["offset"]
+    epochs(2)
+    assert torch.equal(opt.flat_p, want), float((opt.flat_p - want).abs().max())
+    assert torch.equal(opt.flat_m, want_m)
+    assert float((want - snap["flat_p"]).abs().max()) > 0
