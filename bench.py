@@ -606,9 +606,11 @@ def run_b200(args):
                      "roofline": {"bound": "tensor", "kernel": "gemm_tf32_kernel (decoder output layer, all samples of a chunk)",
                                   "achieved": flops / dt_dev / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
                                   "frac": t_roof / dt_dev,
+                                  "frac_of_serial_bound": (flops / (tf32_peak * 1e12) + logit_bytes / (peaks["hbm_gbs"] * 1e9)) / dt_dev,
                                   "peak_source": f"0.5 x bf16_tflops_sustained ({peak_src}): TF32 runs at half the bf16 rate",
                                   "note": "frac = time at the roofline max(decoder flops / TF32 peak, logits bytes / HBM peak) / measured "
-                                          "device time of the WHOLE pass; achieved = decoder flops / whole-pass time"}}
+                                          "device time of the WHOLE pass; frac_of_serial_bound = the same with the SUM of the two "
+                                          "times (product, then one pass over the logits); achieved = decoder flops / whole-pass time"}}
         if rank == 0:
             # the reference-facing API: scipy COO + offsets dict on the host (D2H of the whole COO included)
             if world == 1:
