@@ -77,7 +77,9 @@ class _LatentStage(torch.autograd.Function):
         kh = host_consts(model)
         sp = _scalar_ptrs(model)
         f32 = dict(dtype=torch.float32, device=dev)
-        need_grad = any(ctx.needs_input_grad[:4])
+        # needs_input_grad reflects requires_grad of the inputs even under torch.no_grad(): without the grad-mode flag the
+        # test pass would compute the backward-only reparameterisation gradients on a side stream nobody joins
+        need_grad = getattr(model, "_grad_mode", True) and any(ctx.needs_input_grad[:4])
 
         conc_gamma = torch.empty(1 + 3 * B, **f32)
         conc_beta = torch.empty((B, 2), **f32)

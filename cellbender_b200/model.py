@@ -111,7 +111,7 @@ class _ObsTerm(torch.autograd.Function):
         out = ops.elbo_obs(csr, row_ids, logits, chi_a, bufs["chi_b"], coef.contiguous(), alpha.reshape(1).contiguous(),
                            w.contiguous(), out={"sums": oo["sums"][:B], "dlogits": oo["dlogits"][:B], "qamb": oo["qamb"][:B],
                                                 "dchi_ambient": oo["dchi_ambient"], "lse": oo["lse"], "nan_flag": oo["nan_flag"]},
-                           defer_colsum=any(ctx.needs_input_grad),
+                           defer_colsum=model._grad_mode and any(ctx.needs_input_grad),
                            max_poisson=consts.NBPC_EXACT_MAX_POISSON if model.use_exact_log_prob else None)
         ctx.dchi_ready = out["dchi_ready"]
         sums = out["sums"]
@@ -254,6 +254,7 @@ class RemoveBackgroundPyroModel(nn.Module):
             encoder["other"].d_empty_loc_fn = lambda: (self._d_empty_loc_now if self._d_empty_loc_now is not None
                                                        else self.param_store["d_empty_loc"])
         self._obs_ctx = None
+        self._grad_mode = True
         self._bufs: Dict[int, dict] = {}
         self._retired_bufs: list = []
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -299,6 +300,7 @@ class RemoveBackgroundPyroModel(nn.Module):
         (keys z, d_cell, d_empty, p_logit_reg: standard normals; phi, epsilon: standard-gamma draws at the current
         concentrations; rho: the Beta draw)."""
         B = inp.feats.shape[0]
+        self._grad_mode = torch.is_grad_enabled()  # autograd.Function.forward cannot see it (grad mode is off in there)
         if chi_ambient is None:
             chi_ambient, _ = self.ambient(B)
         d_empty_loc = self.param_store["d_empty_loc"].detach()

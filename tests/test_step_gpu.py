@@ -319,3 +319,29 @@ def test_restart_from_a_snapshot_is_bit_exact(use_graph):
     assert torch.equal(opt.flat_p, want), float((opt.flat_p - want).abs().max())
     assert torch.equal(opt.flat_m, want_m)
     assert float((want - snap["flat_p"]).abs().max()) > 0
+
+
+def test_evaluate_loss_replays_a_graph_and_agrees_with_eager():
+    """SVI.evaluate_loss (the test pass): captured once per (loader, minibatch size) and replayed; its Monte-Carlo mean
+    over repeated evaluations of one minibatch agrees with the eager evaluation's, and nothing is trained by it."""
+    ds, args, model, opt, svi, train_loader, test_loader = _setup(epochs=4)
+    model.train()
+    for b in train_loader:
+        svi.step(b)  # sets the encoder offsets, warms up
+    model.eval()
+    batch = next(iter(test_loader))
+    p0 = opt.flat_p.clone()
+    n_graphs = len(svi._graphs)
+    n_eval = 300
+    replayed = torch.stack([svi.evaluate_loss(batch) for _ in range(n_eval)]).double()
+    assert len(svi._graphs) == n_graphs + 1
+    svi.use_cuda_graph = False
+    eager = torch.stack([svi.evaluate_loss(batch) for _ in range(n_eval)]).double()
+    assert torch.equal(opt.flat_p, p0)
+    assert float(replayed.std()) > 0  # fresh Monte-Carlo draws in every replay
+    # the loss of one minibatch is a noisy Monte-Carlo estimate (one global phi draw per evaluation): the two means must
+    # agree within their standard errors
+    a, b_ = float(replayed.mean()), float(eager.mean())
+    se = float((replayed.var() / n_eval + eager.var() / n_eval).sqrt())
+    assert abs(a - b_) <= 4.0 * se + 1e-3 * abs(b_), (a, b_, se)
+    assert 0.5 < float(replayed.std() / eager.std()) < 2.0
