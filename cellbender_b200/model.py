@@ -26,39 +26,6 @@ from .exceptions import NanException
 from .vae import CompositeEncoder, EncoderInputs
 
 
-def rate_coefficients(model_type: str, epsilon, d_cell, d_empty, rho):
-    """calculate_mu / calculate_lambda in the factored form the fused kernel consumes:
-       mu_y1 = a_mu1 * chi;  lam_y = cAy * chi_ambient + cBy * chi_bar;  lam_E likewise (epsilon = 1, y = 0,
-       rho and d_cell detached: model.py:378-393).  Returns [B, 7] = a_mu1, cA1, cB1, cA0, cB0, cAE, cBE."""
-    zero = torch.zeros_like(epsilon)
-    if model_type == "full":
-        r = rho
-        rd = rho.detach()
-        cols = ((1 - r) * epsilon * d_cell, epsilon * (1 - r) * d_empty, epsilon * r * (d_cell + d_empty),
-                epsilon * (1 - r) * d_empty, epsilon * r * d_empty, (1 - rd) * d_empty, rd * d_empty)
-    elif model_type == "swapping":
-        r = rho
-        rd = rho.detach()
-        cols = ((1 - r) * epsilon * d_cell, zero, epsilon * r * (d_cell + d_empty), zero, epsilon * r * d_empty, zero,
-                rd * d_empty)
-    elif model_type == "ambient":
-        cols = (epsilon * d_cell, epsilon * d_empty, zero, epsilon * d_empty, zero, d_empty, zero)
-    else:
-        raise NotImplementedError(f"model_type '{model_type}' has no empty-droplet mixture; use 'ambient', 'swapping' or 'full'")
-    return torch.stack(cols, dim=1)
-
-
-def get_p_logit_prior(log_counts, log_cell_prior_counts, surely_empty_counts, naive_p_logit_prior):
-    """Per-droplet logit cell-probability prior (reference model.py:577-592)."""
-    ones = torch.ones_like(log_counts)
-    p = ones * naive_p_logit_prior
-    thresh = (torch.as_tensor(surely_empty_counts, dtype=log_counts.dtype, device=log_counts.device).log()
-              + log_cell_prior_counts) / 2
-    p = torch.where(log_counts <= thresh, ones * -100.0, p)
-    p = torch.where(log_counts >= log_cell_prior_counts, ones * consts.REG_LOGIT_MEAN, p)
-    return p
-
-
 class ParamStore(nn.Module):
     """pyro's param store for this model: unconstrained nn.Parameters + constraint transforms."""
 
