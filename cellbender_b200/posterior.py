@@ -20,7 +20,6 @@ from typing import Dict, Optional
 import numpy as np
 import scipy.sparse as sp
 import torch
-from torch.distributions import Gamma, LogNormal
 
 from . import consts, ops
 from .estimation import DevicePosteriorCOO, EstimationMethod, IndexConverter
@@ -105,15 +104,19 @@ class Posterior:
         n = self._device_csr().shape[0]
         z = torch.empty((n, m.encoder["z"].output_dim), device=self.device)
         d, p, eps = (torch.empty(n, device=self.device) for _ in range(3))
-        d_cell_scale = m.param_store["d_cell_scale"]
-        for start in range(0, n, 500):
-            rows = torch.arange(start, min(n, start + 500), device=self.device)
+        d_cell_scale = m.param_store["d_cell_scale"].reshape(())
+        # The reference walks the droplets 500 at a time (posterior.py:868-871); the eval-mode encoders treat every droplet
+        # on its own, so the batch size is free: 2048 droplets per (launch-bound) pass.  The means are the closed forms of
+        # LogNormal(loc, scale).mean and Gamma(epsilon * c, c).mean (posterior.py:896-914).
+        step = 2048
+        for start in range(0, n, step):
+            rows = torch.arange(start, min(n, start + step), device=self.device)
             _, enc = self._encode(rows)
             sl = slice(start, start + rows.numel())
             z[sl] = enc["z"]["loc"].reshape(rows.numel(), -1)
-            d[sl] = LogNormal(loc=enc["d_loc"], scale=d_cell_scale, validate_args=False).mean
+            d[sl] = torch.exp(enc["d_loc"] + 0.5 * d_cell_scale * d_cell_scale)
             p[sl] = enc["p_y"].sigmoid()
-            eps[sl] = Gamma(enc["epsilon"] * m.epsilon_prior, m.epsilon_prior, validate_args=False).mean
+            eps[sl] = enc["epsilon"]
         self._latents = {"z": z.double().cpu().numpy(), "d": d.double().cpu().numpy(), "p": p.double().cpu().numpy(),
                          "phi_loc_scale": [m.param_store["phi_loc"].item(), m.param_store["phi_scale"].item()],
                          "epsilon": eps.double().cpu().numpy()}
