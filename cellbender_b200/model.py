@@ -104,7 +104,11 @@ class _ObsTerm(torch.autograd.Function):
         d_w_buf, d_w = gemm._grad_target(w_param)
         d_b_buf, d_b = gemm._grad_target(ctx.bias_param)
         main = torch.cuda.current_stream()
-        # decoder weight / bias gradients on a side stream, the hidden-activation gradient on this one
+        # decoder weight / bias gradients on a side stream, the hidden-activation gradient on this one.
+        # CONTRACT: dlogits already is d loss / d logits for an upstream gradient of ONE (the observation kernel folds the
+        # loss weights in), and the weight / bias gradients written straight into the optimizer's flat buffer are not
+        # rescaled by g -- SVI.step differentiates the loss itself; a caller that backpropagates k * loss must not use the
+        # flat-buffer path (d_h, dchi_ambient and the small gradients below do carry g).
         side = gemm.grad_stream(dlogits.device, [w_param])
         side.wait_stream(main)
         with torch.cuda.stream(side):
