@@ -161,9 +161,9 @@ __global__ void __launch_bounds__(kObsThreads, 2) elbo_obs_kernel(
   float se[1] = {0.f};
   for (int i = threadIdx.x; i < G4; i += blockDim.x) {
     const float4 l = *reinterpret_cast<const float4*>(lrow + 4 * i);
-    se[0] += expf(l.x - mx) + expf(l.y - mx) + expf(l.z - mx) + expf(l.w - mx);
+    se[0] += __expf(l.x - mx) + __expf(l.y - mx) + __expf(l.z - mx) + __expf(l.w - mx);
   }
-  for (int g = 4 * G4 + threadIdx.x; g < G; g += blockDim.x) se[0] += expf(lrow[g] - mx);
+  for (int g = 4 * G4 + threadIdx.x; g < G; g += blockDim.x) se[0] += __expf(lrow[g] - mx);
   block_sum<float, 1>(se, red);  // (contains the __syncthreads that also publishes the bitmap)
   const float lse = mx + logf(se[0]);
   if (threadIdx.x == 0 && lse_out != nullptr) lse_out[b] = lse;
@@ -226,14 +226,14 @@ __global__ void __launch_bounds__(kObsThreads, 2) elbo_obs_kernel(
     const int g0 = 4 * i;
     const float4 l = *reinterpret_cast<const float4*>(lrow + g0);
     float4 p = *reinterpret_cast<float4*>(drow + g0);
-    p.x = scale * (p.x - expf(l.x - lse) * s_mu_chi);
-    p.y = scale * (p.y - expf(l.y - lse) * s_mu_chi);
-    p.z = scale * (p.z - expf(l.z - lse) * s_mu_chi);
-    p.w = scale * (p.w - expf(l.w - lse) * s_mu_chi);
+    p.x = scale * (p.x - __expf(l.x - lse) * s_mu_chi);
+    p.y = scale * (p.y - __expf(l.y - lse) * s_mu_chi);
+    p.z = scale * (p.z - __expf(l.z - lse) * s_mu_chi);
+    p.w = scale * (p.w - __expf(l.w - lse) * s_mu_chi);
     *reinterpret_cast<float4*>(drow + g0) = p;
   }
   for (int g = 4 * G4 + threadIdx.x; g < G; g += blockDim.x)
-    drow[g] = scale * (drow[g] - expf(lrow[g] - lse) * s_mu_chi);
+    drow[g] = scale * (drow[g] - __expf(lrow[g] - lse) * s_mu_chi);
 }
 
 // Deterministic column sum of a [R, ld] matrix: out[g] = sum_r in[r, g].  A CTA owns 32 adjacent columns; its 256
