@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kObsThreads, 2) elbo_obs_kernel(
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       pp[k] = 0.f, qq[k] = 0.f;
-      if (!((bits >> k) & 1u)) obs_zero_element<EXACT>(expf(ll[k] - lse), aa[k], bb[k], c, inv_alpha, acc, pp[k], qq[k]);
+      if (!((bits >> k) & 1u)) obs_zero_element<EXACT>(__expf(ll[k] - lse), aa[k], bb[k], c, inv_alpha, acc, pp[k], qq[k]);
     }
     *reinterpret_cast<float4*>(drow + g0) = make_float4(pp[0], pp[1], pp[2], pp[3]);
     *reinterpret_cast<float4*>(qrow + g0) = make_float4(qq[0], qq[1], qq[2], qq[3]);
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kObsThreads, 2) elbo_obs_kernel(
   for (int g = 4 * G4 + threadIdx.x; g < G; g += blockDim.x) {
     float p = 0.f, q = 0.f;
     if (!((bitmap[g >> 5] >> (g & 31)) & 1u))
-      obs_zero_element<EXACT>(expf(lrow[g] - lse), chi_amb[g], chi_bar[g], c, inv_alpha, acc, p, q);
+      obs_zero_element<EXACT>(__expf(lrow[g] - lse), chi_amb[g], chi_bar[g], c, inv_alpha, acc, p, q);
     drow[g] = p;
     qrow[g] = q;
   }
