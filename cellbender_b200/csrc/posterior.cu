@@ -25,6 +25,8 @@
 namespace cb {
 
 constexpr int kPostThreads = 256;  // 64 stored counts per CTA
+// exp as one FMUL + one ex2.approx.ftz (relative error 2^-22)
+__device__ __forceinline__ float exp_fast(float v) { return pm_exp2(v * 1.4426950408889634f); }
 
 // logp_out [E, NMAX] : log of the sample-mean pmf;  low_out [E];  keep_cnt [E] = #(c : logp >= thresh);
 // entry_m [E] = barcode_all[cell] * total_n_genes + gene_all[g].  E = entry_start[n_cells] stored counts of the chunk,
@@ -70,17 +72,23 @@ __global__ void __launch_bounds__(kPostThreads) posterior_window_kernel(
     x = data[j];
     g = indices[j];
     n = n_window[b] < NMAX ? n_window[b] : NMAX;
+  }
+  // live window terms of this entry are at most min(n, x + 1) whatever the sample's window start: the warp's maximum bounds
+  // the unrolled term loops for all eight entries of the warp (most stored counts are 1..3: a few terms instead of 20)
+  const int my_bound = (active && x > 0.f && n > 0) ? min(n, int(fminf(x, float(NMAX))) + 1) : 0;
+  const int live_bound = __reduce_max_sync(0xffffffffu, my_bound);
+  if (active) {
     if (x > 0.f && n > 0) {
       const float ca = chi_amb[g], cb_ = chi_bar[g], bg = dec_bias ? dec_bias[g] : 0.f;
       const long long base = (long long)b * n_samples;
       const float* lrow = logits_t + (long long)g * ldt + base;
       for (int smp = sub; smp < n_samples; smp += 4) {
-        const float chi = __expf(lrow[smp] + bg - lse[base + smp]);
+        const float chi = exp_fast(lrow[smp] + bg - lse[base + smp]);
         // posterior.py:708-710 safeguards
         const float mu = a_mu[base + smp] * chi + 1e-30f;
         const float lam = (c_a[base + smp] * ca + c_b[base + smp] * cb_) * lambda_multiplier + 1e-30f;
         const float al = alpha[smp] + 1e-30f;
-        const int lw = noise_window_pmf_accumulate<NMAX>(x, mu, lam, al, n, acc);
+        const int lw = noise_window_pmf_accumulate<NMAX>(x, mu, lam, al, n, acc, live_bound);
         if (smp == n_samples - 1) low = lw;
       }
     }
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(kPostThreads) posterior_window_kernel(
 #pragma unroll
     for (int k = 0; k < NMAX; ++k) {
       if ((k & 3) == sub) {  // lane j of the quad finishes columns j, j + 4, ...: 16 contiguous bytes per store instruction
-        const float lp = (acc[k] > 0.f) ? logf(acc[k] * inv_s) : -INFINITY;
+        const float lp = (acc[k] > 0.f) ? 0.6931471805599453f * pm_log2(acc[k] * inv_s) : -INFINITY;  // |error| < 2e-7
         logp_out[e * NMAX + k] = lp;
         cnt += (k < n && lp >= log_thresh) ? 1 : 0;
       }
@@ -153,6 +161,8 @@ __global__ void __launch_bounds__(256) posterior_offset_flags_kernel(long long n
 
 // ---- column logsumexp of a [R, ld] matrix with an optional per-row additive term: out[c] = log sum_r exp(in[r, c] + add[r]) ----
 // pass 1: a CTA owns 128 columns x one of `n_split` row ranges, online (max, sum) per thread; pass 2 merges the ranges.
+// exp as ONE ex2.approx.ftz (relative error 2^-22 per term of a 33 538-term sum; arguments <= 0, a flushed term is < 1e-38
+// of the largest): with expf the pass was issue-bound at 0.60 of the HBM rate (ncu r02i: issue 72 %, alu 48 %).
 constexpr int kColLseThreads = 128;
 __global__ void __launch_bounds__(kColLseThreads) col_lse_partial_kernel(const float* __restrict__ in, int R, int C, long long ld,
                                                                          const float* __restrict__ add, int rows_per_split,
@@ -168,19 +178,19 @@ __global__ void __launch_bounds__(kColLseThreads) col_lse_partial_kernel(const f
     for (int u = 0; u < 4; ++u) v[u] = in[(long long)(r + u) * ld + c] + (add ? add[r + u] : 0.f);
     const float m4 = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
     if (m4 > mx) {
-      sm *= expf(mx - m4);  // exp(-inf) = 0 on the first group
+      sm *= exp_fast(mx - m4);  // exp(-inf) = 0 on the first group
       mx = m4;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) sm += expf(v[u] - mx);
+    for (int u = 0; u < 4; ++u) sm += exp_fast(v[u] - mx);
   }
   for (; r < r1; ++r) {
     const float v = in[(long long)r * ld + c] + (add ? add[r] : 0.f);
     if (v > mx) {
-      sm *= expf(mx - v);
+      sm *= exp_fast(mx - v);
       mx = v;
     }
-    sm += expf(v - mx);
+    sm += exp_fast(v - mx);
   }
   part_max[(long long)blockIdx.y * C + c] = mx;
   part_sum[(long long)blockIdx.y * C + c] = sm;
