@@ -389,8 +389,10 @@ def kernel_table(model, opt, svi, batch, peaks, dev):
     ms = timed(lambda i: lib.call(
         "cb_elbo_obs_fwd_bwd", ptr(csr_.indptr), ptr(csr_.indices), ptr(csr_.data), ptr(rows_), B, G, ptr(bufs_["logits"]),
         bufs_["logits"].stride(0), ptr(bufs_["chi_a"]), ptr(bufs_["chi_b"]), ptr(coef), ptr(al), ptr(wts), ptr(oo["sums"]),
-        ptr(oo["dlogits"]), ptr(oo["qamb"]), bufs_["logits"].stride(0), ptr(oo["lse"]), ptr(oo["nan_flag"]), _cabi.current_stream()))
-    out["elbo_obs_kernel"] = {**row(ms, 12.0 * B * G, "read logits, write dlogits, write qamb; bound is FP32 / XU issue, not HBM"),
+        ptr(oo["dlogits"]), ptr(oo["qamb"]), bufs_["logits"].stride(0), ptr(oo["lse"]), ptr(oo["nan_flag"]), ptr(oo["scratch"]),
+        _cabi.current_stream()))
+    out["elbo_obs_kernel"] = {**row(ms, 12.0 * B * G, "three launches over (gene range, droplet) tiles: row logsumexp, likelihood + gradients, "
+                                    "softmax backward; read logits, write dlogits, write qamb; bound is FP32 issue, not HBM"),
                               "elements_per_s": 2.0 * B * G / (ms * 1e-3)}
     model.nan_flag.zero_()
     # ---- gather + batchnorm0

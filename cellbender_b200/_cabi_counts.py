@@ -6,7 +6,7 @@ LAUNCHES = {
     "cb_csr_gather_rows": 1, "cb_encoder_features": 1, "cb_bn0_forward": 1, "cb_bn0_backward": 1, "cb_bn_act_forward": 1,
     "cb_bn_act_backward": 1, "cb_head_forward": 1, "cb_head_backward": 1, "cb_gemm_tf32": 1, "cb_gemm_tf32_pair": 1,
     "cb_gemm_tf32_ex": 1, "cb_feat_dw": 1, "cb_latent_prepare": 1, "cb_latent_beta_sample": 1, "cb_latent_forward": 1,
-    "cb_latent_backward": 1, "cb_simplex_forward": 1, "cb_simplex_backward": 1, "cb_elbo_obs_fwd_bwd": 1, "cb_elbo_obs_exact_fwd_bwd": 1, "cb_colsum_rows": 1,
+    "cb_latent_backward": 1, "cb_simplex_forward": 1, "cb_simplex_backward": 1, "cb_elbo_obs_fwd_bwd": 3, "cb_elbo_obs_exact_fwd_bwd": 3, "cb_colsum_rows": 1,
     "cb_obs_loss": 1, "cb_obs_small_grads": 1, "cb_clipped_adam_step": 2, "cb_clipped_adam_range": 1, "cb_clipped_adam_p2p": 2,
     "cb_clipped_adam_nvls": 2, "cb_clipped_adam_nvls_ex": 2,
     # elementwise likelihoods (the reference's distribution classes)
@@ -24,4 +24,5 @@ LAUNCHES = {
 }
 # entry points that only answer a question on the host (no launch)
 QUERIES = ("cb_abi_version", "cb_gemm_tf32_workspace_elems", "cb_gemm_tf32_suggest_split", "cb_latent_num_consts",
-           "cb_latent_num_terms", "cb_posterior_window_stride", "cb_col_logsumexp_scratch_elems", "cb_scan_scratch_elems")
+           "cb_latent_num_terms", "cb_posterior_window_stride", "cb_col_logsumexp_scratch_elems", "cb_scan_scratch_elems",
+           "cb_elbo_obs_scratch_elems")

@@ -258,10 +258,12 @@ __device__ __forceinline__ float4 group_sum4(float4 v, float4 (*s)[kB0Lanes + 1]
 
 __global__ void __launch_bounds__(kB0Lanes* kB0Groups) bn0_forward_kernel(
     const float* __restrict__ x, long long ldx, int B, int G, const float* __restrict__ gamma, const float* __restrict__ beta,
-    float* __restrict__ running_mean, float* __restrict__ running_var, const float* __restrict__ keep, int training,
-    float momentum, float eps, float* __restrict__ y, long long ldy, float* __restrict__ save_mean,
-    float* __restrict__ save_rstd) {
+    float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
+    const float* __restrict__ keep, int training, float momentum, float eps, float* __restrict__ y, long long ldy,
+    float* __restrict__ save_mean, float* __restrict__ save_rstd) {
   __shared__ float4 s[kB0Groups][kB0Lanes + 1];
+  if (training && num_batches_tracked != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+    num_batches_tracked[0] += 1;  // nn.BatchNorm1d's counter (a separate int64 add-on-self launch sat in front of this kernel)
   const int c = threadIdx.x & (kB0Lanes - 1), g = threadIdx.x / kB0Lanes;
   const int col = (blockIdx.x * kB0Lanes + c) * 4;
   const bool ok = col < G;  // the float4 may straddle G: ld is padded to a multiple of 4, lanes beyond G are masked below
@@ -433,16 +435,19 @@ extern "C" int cb_bn_act_backward(const float* x, long long ldx, const float* dy
 }
 
 extern "C" int cb_bn0_forward(const float* x, long long ldx, int n_rows, int n_genes, const float* gamma, const float* beta,
-                              float* running_mean, float* running_var, const float* keep, int training, float momentum,
-                              float eps, float* y, long long ldy, float* save_mean, float* save_rstd, void* stream) {
+                              float* running_mean, float* running_var, long long* num_batches_tracked, const float* keep,
+                              int training, float momentum, float eps, float* y, long long ldy, float* save_mean,
+                              float* save_rstd, void* stream) {
   CB_REQUIRE(n_rows > 0 && n_genes > 0, "cb_bn0_forward: bad shape [%d, %d]", n_rows, n_genes);
   if ((ldx & 3) == 0 && (ldy & 3) == 0 && cb::aligned16(x) && cb::aligned16(y) && (!training || n_rows <= cb::kB0Chunk)) {
     dim3 grid((n_genes + 4 * cb::kB0Lanes - 1) / (4 * cb::kB0Lanes), training ? 1 : (n_rows + cb::kB0Chunk - 1) / cb::kB0Chunk);
     cb::bn0_forward_kernel<<<grid, cb::kB0Lanes * cb::kB0Groups, 0, (cudaStream_t)stream>>>(
-        x, ldx, n_rows, n_genes, gamma, beta, running_mean, running_var, keep, training, momentum, eps, y, ldy, save_mean, save_rstd);
+        x, ldx, n_rows, n_genes, gamma, beta, running_mean, running_var, num_batches_tracked, keep, training, momentum, eps, y, ldy,
+        save_mean, save_rstd);
     return cb::check_launch("cb_bn0_forward");
   }
-  cb::launch_forward(const_cast<float*>(x), ldx, n_rows, n_genes, gamma, beta, running_mean, running_var, nullptr, keep, training,
+  cb::launch_forward(const_cast<float*>(x), ldx, n_rows, n_genes, gamma, beta, running_mean, running_var,
+                     training ? num_batches_tracked : nullptr, keep, training,
                      momentum, eps, 0, y, ldy, save_mean, save_rstd, nullptr, 0, nullptr, 0, stream);
   return cb::check_launch("cb_bn0_forward");
 }

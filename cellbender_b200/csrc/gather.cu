@@ -10,12 +10,16 @@
 // run; only the B row ids chosen by the host RNG cross PCIe (2 KB).
 //
 // Layout: outputs are row-major [B, ld] fp32, ld % 4 == 0 so rows are 16-byte aligned for the
-// vectorised zero-fill and for TMA/GEMM consumers.  One CTA per droplet row.
+// vectorised zero-fill and for TMA/GEMM consumers.  kGatherSplit CTAs per droplet row, each owning a quarter of the
+// row's columns: with one CTA per row the launch was 255 CTAs of 8 warps (0.22 waves, 20 % of the warp slots -- ncu
+// r02i) and latency-bound at 0.39 of the HBM rate.  Every CTA of a row repeats the row's (cheap, L2-resident)
+// statistics pass in the same order, so all of them divide by bit-identical denominators.
 #include "common.cuh"
 
 namespace cb {
 
 constexpr int kGatherThreads = 256;
+constexpr int kGatherSplit = 4;  // column ranges (CTAs) per droplet row
 
 __global__ void __launch_bounds__(kGatherThreads) gather_rows_kernel(
     const long long* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ data,
@@ -26,7 +30,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_rows_kernel(
     float* __restrict__ x_lognorm,       // [B, ld] or nullptr : log1p(x / (sum + 1e-5))
     float* __restrict__ row_feats) {     // [B, 4]  or nullptr : sum, nnz(x>0), dot(x, amb_unit), max
   __shared__ float red[4 * 32];
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   const long long r = row_ids[b];
   const long long s = indptr[r], e = indptr[r + 1];
 
@@ -42,27 +46,32 @@ __global__ void __launch_bounds__(kGatherThreads) gather_rows_kernel(
   block_sum<float, 3>(acc, red);
   vmax = block_max(vmax, red + 96);
   const float denom = acc[0] + 1e-5f;  // transform_input eps (encoder.py:343)
-  if (threadIdx.x == 0 && row_feats != nullptr) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && row_feats != nullptr) {
     row_feats[b * 4 + 0] = acc[0];
     row_feats[b * 4 + 1] = acc[1];
     row_feats[b * 4 + 2] = acc[2];
     row_feats[b * 4 + 3] = vmax;
   }
 
-  // zero-fill the dense rows (16-byte stores), then scatter the non-zeros
+  // zero-fill this CTA's column range of the dense rows (16-byte stores), then scatter the row's non-zeros that fall in it
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long n4 = ld >> 2;
+  const long long per = (n4 + kGatherSplit - 1) / kGatherSplit;
+  const long long lo4 = blockIdx.x * per, hi4 = min(n4, lo4 + per);
   float* rows[3] = {x_raw, x_norm, x_lognorm};
 #pragma unroll
   for (int t = 0; t < 3; ++t) {
     if (rows[t] == nullptr) continue;
     float4* p = reinterpret_cast<float4*>(rows[t] + (long long)b * ld);
-    for (long long i = threadIdx.x; i < n4; i += blockDim.x) p[i] = z;
+    for (long long i = lo4 + threadIdx.x; i < hi4; i += blockDim.x) p[i] = z;
   }
   __syncthreads();
+  const long long g_lo = 4 * lo4, g_hi = 4 * hi4;
   for (long long j = s + threadIdx.x; j < e; j += blockDim.x) {
+    const long long g = indices[j];
+    if (g < g_lo || g >= g_hi) continue;
     const float v = data[j];
-    const long long o = (long long)b * ld + indices[j];
+    const long long o = (long long)b * ld + g;
     const float xn = v / denom;  // true division: bit-identical to the reference's x / (sum + eps)
     if (x_raw != nullptr) x_raw[o] = v;
     if (x_norm != nullptr) x_norm[o] = xn;
@@ -82,7 +91,8 @@ extern "C" int cb_csr_gather_rows(const long long* indptr, const int* indices, c
              ld, n_genes);
   for (const float* p : {x_raw, x_norm, x_lognorm})
     CB_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "cb_csr_gather_rows: output not 16-byte aligned");
-  cb::gather_rows_kernel<<<n_rows, cb::kGatherThreads, 0, (cudaStream_t)stream>>>(
+  CB_REQUIRE(n_rows <= 65535, "cb_csr_gather_rows: n_rows=%d exceeds the grid's y extent", n_rows);
+  cb::gather_rows_kernel<<<dim3(cb::kGatherSplit, n_rows), cb::kGatherThreads, 0, (cudaStream_t)stream>>>(
       indptr, indices, data, row_ids, n_genes, ld, amb_unit, x_raw, x_norm, x_lognorm, row_feats);
   return cb::check_launch("cb_csr_gather_rows");
 }

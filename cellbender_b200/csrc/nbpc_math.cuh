@@ -258,12 +258,19 @@ CB_HD NbpcOut nbpc_eval(float v, float mu, float alpha, float lam) {
 
 // x == 0 specialisation of nbpc_eval<true> (nbpc_math.cuh): L = -m q(w), q(w) = log1p(w)/w, w = mu^2 / (m alpha);
 //   dL/dmu = -1/(1+w) - 2 h(w) lam/mu,  dL/dlam = 2 h(w) - 1/(1+w),  dL/dalpha = m h(w)/alpha,  h = 1/(1+w) - q.
-// 33 538 genes x 2 enumerated branches of every droplet row take this path, so it is written with three reciprocals
-// and, for w < 1/4 (mu << lam: the common case), the alternating series of q and h instead of log1p and a division.
-// Reciprocal of the dense x == 0 path: rcp.approx (2 ulp) on the device, exact on the host build.
+// 33 538 genes of every droplet row take this path, so it is written with three reciprocals (one MUFU each) and, for
+// w < 1/4 (mu << lam: the common case), degree-6 near-minimax polynomials on [0, 1/4] for q(w) and -h(w)/w
+// (Chebyshev-node interpolants; max relative error 4.6e-10 and 6.3e-9 in exact arithmetic, i.e. below fp32 rounding;
+// the 12-term Taylor series they replace cost twice the FMAs), straight-line with the reference's Poisson branch
+// (mu < 1e-5 lam) applied as a select.
+// Reciprocal of the dense x == 0 path: ONE rcp.approx.ftz (1 ulp; arguments are >= 1e-10, far from the flush range) on
+// the device -- __fdividef(1, v) wraps the same instruction in a five-instruction range rescue, 10 % of the observation
+// kernel's instructions in the r02i ncu capture -- exact on the host build.
 CB_HD float rcp_fast(float v) {
 #ifdef __CUDA_ARCH__
-  return __fdividef(1.0f, v);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
 #else
   return 1.0f / v;
 #endif
@@ -271,39 +278,36 @@ CB_HD float rcp_fast(float v) {
 
 CB_HD NbpcOut nbpc_zero(float mu, float inv_alpha, float lam) {
   NbpcOut o;
-  if (mu < 1e-5f * lam) {  // reference: Poisson(lam) where mu < 1e-5 lam
-    o.L = -lam, o.dmu = 0.f, o.dlam = -1.f, o.dalpha = 0.f;
-    return o;
-  }
   const float m = mu + lam;
   const float inv_m = rcp_fast(m);
   const float w = (mu * inv_m) * (mu * inv_alpha);
   const float inv1pw = rcp_fast(1.0f + w);
   float q, h;
   if (w < 0.25f) {
-    // q = sum_{k>=0} (-w)^k / (k+1)
-    float t = 1.0f / 13.0f;
-    t = fmaf(t, -w, 1.0f / 12.0f);
-    t = fmaf(t, -w, 1.0f / 11.0f);
-    t = fmaf(t, -w, 1.0f / 10.0f);
-    t = fmaf(t, -w, 1.0f / 9.0f);
-    t = fmaf(t, -w, 1.0f / 8.0f);
-    t = fmaf(t, -w, 1.0f / 7.0f);
-    t = fmaf(t, -w, 1.0f / 6.0f);
-    t = fmaf(t, -w, 1.0f / 5.0f);
-    t = fmaf(t, -w, 1.0f / 4.0f);
-    t = fmaf(t, -w, 1.0f / 3.0f);
-    t = fmaf(t, -w, 1.0f / 2.0f);
-    q = fmaf(t, -w, 1.0f);
-    h = h_f(w, inv1pw, q);
+    float t = 7.0580221160e-02f;
+    t = fmaf(t, w, -1.4531815925e-01f);
+    t = fmaf(t, w, 1.9661888013e-01f);
+    t = fmaf(t, w, -2.4971586912e-01f);
+    t = fmaf(t, w, 3.3332176190e-01f);
+    t = fmaf(t, w, -4.9999982126e-01f);
+    q = fmaf(t, w, 1.0f);
+    float u = 3.8702023389e-01f;
+    u = fmaf(u, w, -7.1614602060e-01f);
+    u = fmaf(u, w, 8.1124690281e-01f);
+    u = fmaf(u, w, -7.9815522469e-01f);
+    u = fmaf(u, w, 7.4992512791e-01f);
+    u = fmaf(u, w, -6.6666551211e-01f);
+    u = fmaf(u, w, 0.5f);
+    h = -w * u;
   } else {
     q = log1pf(w) * (1.0f / w);
     h = inv1pw - q;
   }
-  o.L = -m * q;
-  o.dlam = 2.0f * h - inv1pw;
-  o.dmu = -inv1pw - 2.0f * h * lam * rcp_fast(mu);
-  o.dalpha = m * h * inv_alpha;
+  const bool poisson = mu < 1e-5f * lam;  // reference: Poisson(lam) where mu < 1e-5 lam
+  o.L = poisson ? -lam : -m * q;
+  o.dlam = poisson ? -1.0f : 2.0f * h - inv1pw;
+  o.dmu = poisson ? 0.0f : -inv1pw - 2.0f * h * lam * rcp_fast(mu);
+  o.dalpha = poisson ? 0.0f : m * h * inv_alpha;
   return o;
 }
 

@@ -356,14 +356,15 @@ class _BN0Dropout(torch.autograd.Function):
     """dropout50(batchnorm0(x)) of EncodeNonZLatents (vae/encoder.py:239,279) through cb_bn0_forward / _backward."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, keep, training: bool, momentum: float, eps: float, n_genes: int):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, n_tracked, keep, training: bool, momentum: float, eps: float,
+                n_genes: int):
         B, G = x.shape[0], n_genes
         y = ops.alloc_rows(B, G, x.device, zero=False)
         mean = torch.empty(G, device=x.device)
         rstd = torch.empty(G, device=x.device)
         lib().call("cb_bn0_forward", ptr(x), x.stride(0), B, G, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
-                   ptr(keep), int(training), float(momentum), float(eps), ptr(y), y.stride(0), ptr(mean), ptr(rstd),
-                   current_stream())
+                   ptr(n_tracked) if training else None, ptr(keep), int(training), float(momentum), float(eps), ptr(y),
+                   y.stride(0), ptr(mean), ptr(rstd), current_stream())
         ctx.save_for_backward(x, keep if keep is not None else torch.empty(0, device=x.device), mean, rstd)
         ctx.meta = (G, keep is not None)
         return y[:, :G]
@@ -378,17 +379,15 @@ class _BN0Dropout(torch.autograd.Function):
         dbeta = torch.empty(G, device=x.device)
         lib().call("cb_bn0_backward", ptr(x), x.stride(0), ptr(dy), dy.stride(0), x.shape[0], G, ptr(keep) if has_keep else None,
                    ptr(mean), ptr(rstd), ptr(dgamma), ptr(dbeta), current_stream())
-        return None, dgamma, dbeta, None, None, None, None, None, None, None
+        return None, dgamma, dbeta, None, None, None, None, None, None, None, None
 
 
 def bn0_dropout(x: torch.Tensor, bn: torch.nn.BatchNorm1d, keep: Optional[torch.Tensor], training: bool, n_genes: int):
     """dropout(bn(x[:, :n_genes])) as a [B, n_genes] view of a 16-byte-row buffer (GEMM/TMA friendly)."""
     if not (x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1):
         raise RuntimeError("cellbender_b200 ops require fp32 CUDA tensors with unit column stride (no CPU fallback)")
-    if training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
-    return _BN0Dropout.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, keep if training else None, training,
-                             bn.momentum if bn.momentum is not None else 0.1, bn.eps, n_genes)
+    return _BN0Dropout.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                             keep if training else None, training, bn.momentum if bn.momentum is not None else 0.1, bn.eps, n_genes)
 
 
 ACT_CODE = {None: 0, "identity": 0, "softplus": 1, "relu": 2}

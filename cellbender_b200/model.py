@@ -77,7 +77,8 @@ class _ObsTerm(torch.autograd.Function):
         oo = bufs["obs_out"]
         out = ops.elbo_obs(csr, row_ids, logits, chi_a, bufs["chi_b"], coef.contiguous(), alpha.reshape(1).contiguous(),
                            w.contiguous(), out={"sums": oo["sums"][:B], "dlogits": oo["dlogits"][:B], "qamb": oo["qamb"][:B],
-                                                "dchi_ambient": oo["dchi_ambient"], "lse": oo["lse"], "nan_flag": oo["nan_flag"]},
+                                                "dchi_ambient": oo["dchi_ambient"], "lse": oo["lse"], "nan_flag": oo["nan_flag"],
+                                                "scratch": oo["scratch"]},
                            defer_colsum=model._grad_mode and any(ctx.needs_input_grad),
                            max_poisson=consts.NBPC_EXACT_MAX_POISSON if model.use_exact_log_prob else None)
         ctx.dchi_ready = out["dchi_ready"]
@@ -250,7 +251,8 @@ class RemoveBackgroundPyroModel(nn.Module):
                 "chi_unit": torch.zeros(ld, device=dev), "chi_b": chi_b,
                 "obs_out": {"sums": torch.empty((cap, 12), device=dev), "dlogits": torch.zeros((cap, ld), device=dev),
                             "qamb": torch.empty((cap, ld), device=dev), "dchi_ambient": torch.empty(G, device=dev),
-                            "lse": torch.empty(cap, device=dev), "nan_flag": self.nan_flag}}
+                            "lse": torch.empty(cap, device=dev), "nan_flag": self.nan_flag,
+                            "scratch": torch.empty(ops.elbo_obs_scratch_elems(cap), device=dev)}}
         return self._bufs[key]
 
     # ---- the ELBO --------------------------------------------------------------------------------------
@@ -263,21 +265,66 @@ class RemoveBackgroundPyroModel(nn.Module):
         chi = latent.simplex_param(self.param_store.unconstrained["chi_ambient"], bufs)
         return chi, bufs["chi_unit"][:G]
 
+    PROLOGUE_STREAM = 7  # ops.side_stream index
+
+    def step_prologue(self, B: int, row_keep_scale: Optional[torch.Tensor] = None, csr: Optional[ops.DeviceCSR] = None,
+                      row_ids: Optional[torch.Tensor] = None) -> dict:
+        """Everything at the head of a step that does not need the gathered minibatch, issued on an auxiliary stream so that
+        it runs BESIDE the gather instead of in front of / behind it (r02h / r02j timelines: the one-CTA simplex kernel
+        delayed the gather by 12 us, six serial 1.5 us launches sat between the gather and batchnorm0):
+          * the Dropout1d row realisation of the encoder (bernoulli + scale) and the constrained ``d_empty_loc``
+            -> event ``keep_ready`` (all batchnorm0 needs beside the gathered rows);
+          * ``pyro.param("chi_ambient")`` (simplex transform) + the ambient unit vector;
+          * with ``csr`` / ``row_ids``: the per-droplet features [B, 4] INCLUDING the dot product with that unit vector
+            (vae/encoder.py:266-272) -- the gather itself is then called without the ambient profile; both launches
+            reduce the droplet's stored counts in the same order, so the shared features are bit-identical.
+        Returns the handle ``elbo_terms(prologue=...)`` joins."""
+        dev = self.device
+        main = torch.cuda.current_stream()
+        draw = row_keep_scale is None and self.encoder["other"].training
+        # allocated on the caller's stream (whose later reuse of the blocks is ordered behind the join), filled on the side one
+        keep = torch.empty(B, device=dev) if draw else row_keep_scale
+        u = self.param_store.unconstrained["d_empty_loc"].detach()
+        d_empty_loc = torch.empty_like(u)
+        side = ops.side_stream(dev, self.PROLOGUE_STREAM)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if draw:
+                keep.bernoulli_(0.5).mul_(2.0)
+            torch.exp(u, out=d_empty_loc)  # transform_to(constraints.positive)
+            keep_ready = torch.cuda.Event()
+            keep_ready.record(side)
+            chi_ambient, unit = self.ambient(B)
+            feats = ops.gather_feats(csr, row_ids, unit) if csr is not None else None
+        return {"row_keep_scale": keep, "d_empty_loc": d_empty_loc, "keep_ready": keep_ready, "chi_ambient": chi_ambient,
+                "unit": unit, "feats": feats, "stream": side}
+
     def elbo_terms(self, csr: ops.DeviceCSR, row_ids: torch.Tensor, inp: EncoderInputs,
                    noise: Optional[Dict[str, torch.Tensor]] = None, row_keep_scale: Optional[torch.Tensor] = None,
-                   chi_ambient: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                   chi_ambient: Optional[torch.Tensor] = None, prologue: Optional[dict] = None) -> Dict[str, torch.Tensor]:
         """All terms of the ELBO for one minibatch.  Returns a dict of scalar tensors whose
         sum is the ELBO, plus 'loss' = -ELBO.  ``noise`` lets tests inject fixed base randomness
         (keys z, d_cell, d_empty, p_logit_reg: standard normals; phi, epsilon: standard-gamma draws at the current
-        concentrations; rho: the Beta draw)."""
+        concentrations; rho: the Beta draw).  ``prologue``: the handle of ``step_prologue`` (joined here)."""
         B = inp.feats.shape[0]
         self._grad_mode = torch.is_grad_enabled()  # autograd.Function.forward cannot see it (grad mode is off in there)
-        if chi_ambient is None:
-            chi_ambient, _ = self.ambient(B)
-        d_empty_loc = self.param_store["d_empty_loc"].detach()
+        main = torch.cuda.current_stream()
+        if prologue is not None:
+            main.wait_event(prologue["keep_ready"])
+            row_keep_scale, d_empty_loc = prologue["row_keep_scale"], prologue["d_empty_loc"]
+        else:
+            if chi_ambient is None:
+                chi_ambient, _ = self.ambient(B)
+            d_empty_loc = self.param_store["d_empty_loc"].detach()
         self._d_empty_loc_now = d_empty_loc
         x_in = self.encoder["other"].normalize_input(inp, row_keep_scale)  # batchnorm0 + dropout, on a side stream
         z_loc, z_log_scale = self.encoder["z"].forward_raw(inp)
+        if prologue is not None:
+            # first consumers of the simplex transform and of the ambient-dot feature: the hand-made encoder features
+            main.wait_stream(prologue["stream"])
+            chi_ambient = prologue["chi_ambient"]
+            if prologue["feats"] is not None:
+                inp = EncoderInputs(inp.x_norm, inp.x_lognorm, prologue["feats"], inp.n_genes)
         p_out, eps_out, _ = self.encoder["other"].forward_raw(inp, chi_ambient.detach(), z_loc.detach(),
                                                               row_keep_scale=row_keep_scale, x_in=x_in)
         self._d_empty_loc_now = None

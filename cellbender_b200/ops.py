@@ -36,6 +36,9 @@ def _req_cuda(*ts):
 _SIDE_STREAMS = {}
 
 
+LOW_PRIORITY_STREAMS = (0, 4)
+
+
 def side_stream(device, idx: int = 0) -> "torch.cuda.Stream":
     """A persistent auxiliary stream per (device, idx).  Independent kernels of one step (the weight-gradient and
     input-gradient products of a layer; torch's slow reparameterisation-gradient kernels) are forked onto it and joined
@@ -44,11 +47,12 @@ def side_stream(device, idx: int = 0) -> "torch.cuda.Stream":
     d = torch.device(device)
     key = (d.index if d.index is not None else torch.cuda.current_device(), idx)
     if key not in _SIDE_STREAMS:
-        # Stream 0 carries the weight-gradient products and the optimizer sweeps behind them: bulk HBM traffic with no
-        # consumer inside the step.  Every other stream carries links of the latency-bound critical chain and gets the
-        # higher priority, so that its (small) kernels are placed ahead of the bulk CTAs still waiting for a slot.
+        # Stream 0 carries the weight-gradient products and the optimizer sweeps behind them, stream 4 the column sums of
+        # the observation kernel's chi_ambient gradient (consumed at the very end of backward): bulk HBM traffic with no
+        # consumer on the critical chain.  Every other stream carries links of the latency-bound critical chain and gets
+        # the higher priority, so that its (small) kernels are placed ahead of the bulk CTAs still waiting for a slot.
         # Priorities are recorded into the kernel nodes of a captured CUDA graph.
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key[0], priority=0 if idx == 0 else -1)
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key[0], priority=0 if idx in LOW_PRIORITY_STREAMS else -1)
     return _SIDE_STREAMS[key]
 
 
@@ -212,6 +216,11 @@ SUM_NAMES = ("L1", "L0", "LE", "dL1_da_mu1", "dL1_dcA1", "dL1_dcB1", "dL1_dalpha
              "dL0_dalpha", "dLE_dcAE", "dLE_dcBE")
 
 
+def elbo_obs_scratch_elems(n_rows: int) -> int:
+    """fp32 elements of scratch cb_elbo_obs_fwd_bwd needs for ``n_rows`` droplets."""
+    return int(_cabi.lib().raw("cb_elbo_obs_scratch_elems")(int(n_rows)))
+
+
 def elbo_obs(csr: DeviceCSR, row_ids, logits, chi_ambient, chi_bar, coef, alpha, w, *, out=None, defer_colsum: bool = False,
              max_poisson: Optional[int] = None):
     """cb_elbo_obs_fwd_bwd (+ cb_colsum_rows).  logits: [B, ld] buffer (ld % 4 == 0) holding G valid columns.
@@ -238,9 +247,12 @@ def elbo_obs(csr: DeviceCSR, row_ids, logits, chi_ambient, chi_bar, coef, alpha,
         out["nan_flag"] = torch.zeros(1, dtype=torch.int32, device=dev)
     st = current_stream()
     L = _cabi.lib()
+    n_scratch = int(L.raw("cb_elbo_obs_scratch_elems")(B))
+    if "scratch" not in out or out["scratch"].numel() < n_scratch:
+        out["scratch"] = torch.empty(n_scratch, dtype=torch.float32, device=dev)  # per-tile partial sums (float64) + lse pairs
     operands = (ptr(csr.indptr), ptr(csr.indices), ptr(csr.data), ptr(row_ids), B, G, ptr(logits), ld, ptr(chi_ambient), ptr(chi_bar),
                 ptr(coef), ptr(alpha), ptr(w), ptr(out["sums"]), ptr(out["dlogits"]), ptr(out["qamb"]), ld, ptr(out["lse"]),
-                ptr(out["nan_flag"]))
+                ptr(out["nan_flag"]), ptr(out["scratch"]))
     if max_poisson is None:
         L.call("cb_elbo_obs_fwd_bwd", *operands, st)
     else:

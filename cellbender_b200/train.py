@@ -66,10 +66,10 @@ class SVI:
             return self.model.ambient()[1]
 
     def loss_terms(self, batch, noise=None, row_keep_scale=None):
-        chi_ambient, unit = self.model.ambient(batch.n)  # simplex transform of the parameter + unit vector: one kernel
-        inp = batch.encoder_inputs(unit)
-        return self.model.elbo_terms(batch.loader.csr, batch.row_ids, inp, noise=noise, row_keep_scale=row_keep_scale,
-                                     chi_ambient=chi_ambient)
+        # dropout rows, d_empty_loc, simplex transform of chi_ambient and the ambient-dot feature: beside the gather
+        prologue = self.model.step_prologue(batch.n, row_keep_scale, batch.loader.csr, batch.row_ids)
+        inp = batch.encoder_inputs(None)
+        return self.model.elbo_terms(batch.loader.csr, batch.row_ids, inp, noise=noise, prologue=prologue)
 
     def _forward_backward(self, batch) -> torch.Tensor:
         from . import gemm

@@ -74,26 +74,35 @@ int cb_nbpc_exact_log_prob_bwd(const float* value, const long long* sv, const fl
  *   sums[n_rows, 12]  L_y1, L_y0, L_E, dL1/da_mu1, dL1/dcA1, dL1/dcB1, dL1/dalpha, dL0/dcA0, dL0/dcB0, dL0/dalpha,
  *                     dLE/dcAE, dLE/dcBE
  *   dlogits[n_rows, ldl]  d loss / d logits;   qamb[n_rows, ldq]  per-row d loss / d chi_ambient (sum rows with
- *                     cb_colsum_rows);   lse_out[n_rows] row logsumexp of logits (may be NULL)                 */
+ *                     cb_colsum_rows);   lse_out[n_rows] row logsumexp of logits (may be NULL)
+ *   scratch[cb_elbo_obs_scratch_elems(n_rows)]  floats, 8-byte aligned: per (gene range, droplet) tile the partial row
+ *                     sums in float64 and the (max, sum exp) pair of its logits -- a droplet row is split into gene
+ *                     ranges and the three phases (row logsumexp; likelihood + gradients; softmax backward) are three
+ *                     launches over the tiles, ordered by the stream.                                              */
+long long cb_elbo_obs_scratch_elems(int n_rows);
 int cb_elbo_obs_fwd_bwd(const long long* indptr, const int* indices, const float* data, const long long* row_ids,
                         int n_rows, int n_genes, const float* logits, long long ldl, const float* chi_ambient,
                         const float* chi_bar, const float* coef, const float* alpha, const float* w, float* sums,
-                        float* dlogits, float* qamb, long long ldq, float* lse_out, int* nan_flag, void* stream);/* The same with the exact NB (+) Poisson convolution as the likelihood: NegativeBinomialPoissonConv(max_poisson)
+                        float* dlogits, float* qamb, long long ldq, float* lse_out, int* nan_flag, float* scratch,
+                        void* stream);
+/* The same with the exact NB (+) Poisson convolution as the likelihood: NegativeBinomialPoissonConv(max_poisson)
  * (distributions/NegativeBinomialPoissonConv.py:89-154; model.py:336-357 with consts.USE_EXACT_LOG_PROB = True).  Genes
  * without a stored count use the one-term closed form, stored counts the term-by-term sum in float64.               */
 int cb_elbo_obs_exact_fwd_bwd(const long long* indptr, const int* indices, const float* data, const long long* row_ids,
                         int n_rows, int n_genes, const float* logits, long long ldl, const float* chi_ambient,
                         const float* chi_bar, const float* coef, const float* alpha, const float* w, float* sums,
-                        float* dlogits, float* qamb, long long ldq, float* lse_out, int* nan_flag, int max_poisson, void* stream);
+                        float* dlogits, float* qamb, long long ldq, float* lse_out, int* nan_flag, float* scratch,
+                        int max_poisson, void* stream);
 int cb_colsum_rows(const float* in, int n_rows, int n_cols, long long ld, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * A4  self.dropout50(self.batchnorm0(x)) of EncodeNonZLatents.forward (vae/encoder.py:239,279), forward + backward.
  * x / y / dy are [n_rows, ld] fp32; keep[n_rows] is the Dropout1d row realisation (0 or 2; NULL = none);
- * running_mean/var are updated in training mode (momentum 0.1, unbiased variance, as nn.BatchNorm1d).           */
+ * running_mean/var are updated in training mode (momentum 0.1, unbiased variance, as nn.BatchNorm1d) and
+ * *num_batches_tracked (may be NULL) is incremented.                                                             */
 int cb_bn0_forward(const float* x, long long ldx, int n_rows, int n_genes, const float* gamma, const float* beta,
-                   float* running_mean, float* running_var, const float* keep, int training, float momentum, float eps,
-                   float* y, long long ldy, float* save_mean, float* save_rstd, void* stream);
+                   float* running_mean, float* running_var, long long* num_batches_tracked, const float* keep, int training,
+                   float momentum, float eps, float* y, long long ldy, float* save_mean, float* save_rstd, void* stream);
 int cb_bn0_backward(const float* x, long long ldx, const float* dy, long long lddy, int n_rows, int n_genes,
                     const float* keep, const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta,
                     void* stream);
