@@ -17,7 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="pbmc8k")
     ap.add_argument("--out", default="gpurun_out/step_timeline.txt")
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=8)
     a = ap.parse_args()
     import torch
     from torch.profiler import ProfilerActivity, profile
@@ -68,7 +68,12 @@ def main():
     starts = [i for i, e in enumerate(ks) if "gather_rows" in e["name"]]
     lines = []
     if len(starts) >= 3:
-        seg = ks[starts[-2]:starts[-1]]
+        # a complete step: the longest run of kernels between two consecutive gathers (CUPTI can drop the tail of the
+        # last replay; the first replay inside the profiler carries its start-up cost)
+        bounds = list(zip(starts[:-1], starts[1:]))
+        i0, i1 = max(bounds[1:] or bounds, key=lambda b: b[1] - b[0])
+        seg = ks[i0:i1]
+        starts = [i0, i1]
     else:
         seg = ks
     t0 = seg[0]["ts"]
