@@ -1,8 +1,10 @@
 """A few EAGER training steps at the PBMC8k shape (no CUDA graph) for `ncu -k regex:... --set full` captures of single
 kernels of the step, and (--posterior) a short posterior pass for the same purpose.
 
-    ncu --set full --clock-control none --import-source on -k regex:'latent_forward|elbo_obs' -s 6 -c 2 \
+    ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'obs_|gemm_tf32' \
         -o gpurun_out/prof python tools/step_profile.py --steps 5
+
+The script brackets the last eager step (or, with --posterior, one pass over 1024 cells) with cudaProfilerStart / Stop.
 """
 import argparse
 import os
@@ -28,9 +30,14 @@ def main():
     model, opt, svi, train_loader, _ = run.setup_inference(ds, run.default_args(use_cuda_graph=False), device=dev)
     model.train()
     it = iter(train_loader)
-    for _ in range(a.steps):
+    for k in range(a.steps):
+        if k == a.steps - 1 and not a.posterior:  # `ncu --profile-from-start off`: only the last eager step is captured
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
         svi.step(next(it))
     torch.cuda.synchronize()
+    if not a.posterior:
+        torch.cuda.profiler.stop()
     if a.posterior:
         from cellbender_b200.posterior import Posterior
 
@@ -38,8 +45,12 @@ def main():
         post = Posterior(ds, model)
         n_all = int(ds.analyzed_barcode_inds.size)
         post._latents = {"p": np.concatenate([np.ones(1024), np.zeros(n_all - 1024)])}
+        post.device_posterior(cell_subset=np.arange(128))  # builds the workspace and the chunk graphs
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()  # `ncu --profile-from-start off`: one pass over 1024 cells = two 512-cell chunks
         post.device_posterior()
         torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     print("done")
 
 
