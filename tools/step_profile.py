@@ -4,7 +4,7 @@ kernels of the step, and (--posterior) a short posterior pass for the same purpo
     ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'obs_|gemm_tf32' \
         -o gpurun_out/prof python tools/step_profile.py --steps 5
 
-The script brackets the last eager step (or, with --posterior, one pass over 1024 cells) with cudaProfilerStart / Stop.
+The script brackets the last eager step (or, with --posterior, one pass over 2048 cells) with cudaProfilerStart / Stop.
 """
 import argparse
 import os
@@ -44,10 +44,10 @@ def main():
         model.eval()
         post = Posterior(ds, model)
         n_all = int(ds.analyzed_barcode_inds.size)
-        post._latents = {"p": np.concatenate([np.ones(1024), np.zeros(n_all - 1024)])}
+        post._latents = {"p": np.concatenate([np.ones(2048), np.zeros(n_all - 2048)])}
         post.device_posterior(cell_subset=np.arange(128))  # builds the workspace and the chunk graphs
         torch.cuda.synchronize()
-        torch.cuda.profiler.start()  # `ncu --profile-from-start off`: one pass over 1024 cells = two 512-cell chunks
+        torch.cuda.profiler.start()  # `ncu --profile-from-start off`: one pass over 2048 cells = four 512-cell chunks (the pipelined form)
         post.device_posterior()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
