@@ -42,8 +42,15 @@
 
 namespace cb {
 
+// tile shape of the three launches; overridable at compile time for tools/obs_variants.py (A/B builds)
+#ifndef CB_OBS_CHUNKS
+#define CB_OBS_CHUNKS 4
+#endif
+#ifndef CB_OBS_MIN_CTAS
+#define CB_OBS_MIN_CTAS 4  // 64 registers: 592 of the 1020 tiles resident (r02k A/B: 86.4 us against 92.2 us with 3, same bits)
+#endif
 constexpr int kObsThreads = 256;
-constexpr int kObsChunks = 4;  // gene ranges per droplet row
+constexpr int kObsChunks = CB_OBS_CHUNKS;  // gene ranges per droplet row
 constexpr int kNumSums = 12;
 constexpr int kObsScratchPerTile = 2 * kNumSums + 2;  // floats: 12 float64 partial sums + (max, sum exp)
 
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(kObsThreads) obs_row_lse_kernel(int G, int chu
 
 // ---- launch 2: likelihood terms, their gradients and the partial row sums of every (chunk, row) tile ----
 template <bool EXACT>
-__global__ void __launch_bounds__(kObsThreads, 3) obs_main_kernel(
+__global__ void __launch_bounds__(kObsThreads, CB_OBS_MIN_CTAS) obs_main_kernel(
     const long long* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ data,
     const long long* __restrict__ row_ids, int G, int chunk_len, const float* __restrict__ logits, long long ldl,
     const float* __restrict__ chi_amb, const float* __restrict__ chi_bar, const float* __restrict__ coef,

@@ -39,6 +39,10 @@ def _grad_target(weight: torch.Tensor):
     return gv, None
 
 
+# the persistent 0-dim tensor 1.0 that train.SVI backpropagates from (``loss.backward(UNIT_GRAD)``): no ones_like fill per
+# step, and backward functions that recognise it by address skip their multiplications by the upstream gradient
+UNIT_GRAD = None
+
 _PENDING_JOINS = []
 _BULK_PENDING = []
 _CALLBACK_QUEUED = []  # non-empty while the running backward pass has its end-of-backward join callback queued

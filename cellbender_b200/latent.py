@@ -132,6 +132,10 @@ class _LatentStage(torch.autograd.Function):
             ctx.model = model
             ctx.kh = kh
         ctx.mark_non_differentiable(terms, enc_out)
+        # gradients nobody produces (terms, enc_out; any unused output) arrive as None in backward instead of as freshly
+        # zero-filled tensors: each of those was a fill launch in front of latent_backward_kernel on the step's critical
+        # chain (r02j timeline); the kernel treats a null upstream gradient as zero
+        ctx.set_materialize_grads(False)
         return z, coef, alpha, w, loss_local, terms, enc_out
 
     @staticmethod
@@ -144,6 +148,8 @@ class _LatentStage(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=feats.device)
         c = lambda t: None if t is None else t.contiguous()
         d_z, d_coef, d_alpha, d_w, g_local = c(d_z), c(d_coef), c(d_alpha), c(d_w), c(g_local)
+        if g_local is None:  # loss_local unused by the caller (the kernel reads a null pointer here as 1)
+            g_local = torch.zeros((), **f32)
         d_p_out = torch.empty(B, **f32)
         d_eps_out = torch.empty(B, **f32)
         d_z_loc = torch.empty((B, Z), **f32)

@@ -91,12 +91,19 @@ class _ObsTerm(torch.autograd.Function):
         ctx.w_param = w_out
         neg_obs, obs = ops.obs_loss(sums, w)  # sum_b w . L and its negative (the 'obs' ELBO term)
         ctx.mark_non_differentiable(L, obs)
+        ctx.set_materialize_grads(False)  # no zero-filled gradients for L / obs in front of backward (two fill launches)
         return neg_obs, L, obs
 
     @staticmethod
     def backward(ctx, g, _gL, _gobs):
+        if g is None:
+            return (None,) * 8
         h_dec, w_out, sums, w, dlogits, dchi_amb = ctx.saved_tensors
         G = ctx.G
+        # SVI.step backpropagates from its own persistent scalar 1 (gemm.UNIT_GRAD): the two elementwise products by g
+        # below are then identities and their launches (on the critical chain, in front of the decoder's hidden-layer
+        # backward) are skipped.  Any other upstream gradient takes the general path.
+        unit = gemm.UNIT_GRAD is not None and g.data_ptr() == gemm.UNIT_GRAD.data_ptr()
         if ctx.dchi_ready is not None:
             torch.cuda.current_stream().wait_event(ctx.dchi_ready)
         B, H = h_dec.shape
@@ -115,7 +122,9 @@ class _ObsTerm(torch.autograd.Function):
         with torch.cuda.stream(side):
             ops.gemm_tf32(dlogits, h_c, G, H, B, a_mn=True, b_mn=True, out=d_w_buf, split_k=1)  # dlogits^T . h
             ops.colsum_rows(dlogits, G, out=d_b_buf)
-        d_h = ops.gemm_tf32(dlogits, w_out, B, H, G, b_mn=True) * g          # dlogits[B,G] . Wd[G,H], split-K
+        d_h = ops.gemm_tf32(dlogits, w_out, B, H, G, b_mn=True)              # dlogits[B,G] . Wd[G,H], split-K
+        if not unit:
+            d_h = d_h * g
         if d_w is None and gemm.early_update_applies(w_param):
             # the decoder weights are no longer read this step: sweep their block now, behind the gradient GEMM
             readers_done = torch.cuda.Event()
@@ -130,7 +139,7 @@ class _ObsTerm(torch.autograd.Function):
             main.wait_stream(side)
         d_coef, d_alpha, d_weights = ops.obs_small_grads(sums, w, g.contiguous(), want_dw=ctx.needs_input_grad[6])
         d_alpha = d_alpha.reshape(ctx.alpha_shape)
-        return d_h, d_w, d_b, dchi_amb * g, d_coef, d_alpha, d_weights, None
+        return d_h, d_w, d_b, (dchi_amb if unit else dchi_amb * g), d_coef, d_alpha, d_weights, None
 
 
 class RemoveBackgroundPyroModel(nn.Module):

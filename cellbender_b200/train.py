@@ -51,6 +51,7 @@ class SVI:
         self.graph_warmup = graph_warmup
         self._graphs = {}
         self._eager_steps = 0
+        self._unit_grad = torch.ones((), dtype=torch.float32, device=model.device)  # d loss / d loss, never written to
         # data parallel (dp.attach): mode 'p2p' puts the exchange inside the step (optim.exchange), nothing to hook here;
         # mode 'sharded' runs the NCCL exchange eagerly between replays of the forward + backward graph
         self.after_backward = None  # hook(optim): gradient exchange that precedes a full optimizer sweep
@@ -80,10 +81,12 @@ class SVI:
         # single GPU: the ClippedAdam sweep of each large weight block is issued right behind its weight-gradient GEMM
         fuse = (self.after_backward is None and self.model.training and getattr(self.optim, "early_weight_updates", False))
         gemm.FUSED_OPT = self.optim if fuse else None
+        gemm.UNIT_GRAD = self._unit_grad
         try:
-            loss.backward()
+            loss.backward(self._unit_grad)
         finally:
             gemm.FUSED_OPT = None
+            gemm.UNIT_GRAD = None
         self.optim.collect_grads()
         return loss.detach()
 

@@ -18,7 +18,9 @@ def main(path, out=None, title=""):
         u = r["Metric Unit"]
         return v / 1e3 if u.startswith("n") else (v if u.startswith("u") else v * 1e3)
 
-    a, b = idx[-2], idx[-1]
+    # the last complete step: the longest run between two consecutive gathers among the last few (the bench's e2e loop
+    # and tail launch other gathers beside the step's own)
+    a, b = max(list(zip(idx[:-1], idx[1:]))[-12:], key=lambda ab: ab[1] - ab[0])
     seg = rows[a:b]
     tot = sum(val(r) for r in seg)
     agg = collections.defaultdict(lambda: [0, 0.0])
