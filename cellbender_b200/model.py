@@ -104,8 +104,6 @@ class _ObsTerm(torch.autograd.Function):
         # below are then identities and their launches (on the critical chain, in front of the decoder's hidden-layer
         # backward) are skipped.  Any other upstream gradient takes the general path.
         unit = gemm.UNIT_GRAD is not None and g.data_ptr() == gemm.UNIT_GRAD.data_ptr()
-        if ctx.dchi_ready is not None:
-            torch.cuda.current_stream().wait_event(ctx.dchi_ready)
         B, H = h_dec.shape
         h_c = h_dec.contiguous()
         w_param = ctx.w_param
@@ -139,6 +137,11 @@ class _ObsTerm(torch.autograd.Function):
             main.wait_stream(side)
         d_coef, d_alpha, d_weights = ops.obs_small_grads(sums, w, g.contiguous(), want_dw=ctx.needs_input_grad[6])
         d_alpha = d_alpha.reshape(ctx.alpha_shape)
+        if ctx.dchi_ready is not None:
+            # the deferred column sums (d loss / d chi_ambient, handed to autograd below) are joined only here, behind the
+            # launches above: at the top of this function the wait held the hidden-activation product back until the column
+            # sums had finished (r02k timeline: 8 us on the step's critical chain)
+            main.wait_event(ctx.dchi_ready)
         return d_h, d_w, d_b, (dchi_amb if unit else dchi_amb * g), d_coef, d_alpha, d_weights, None
 
 
